@@ -1,0 +1,78 @@
+"""In-tree build of libbtgpu.so (nvcc, sm_100a only) and of the oracle checkers.
+
+`python -m bayestyper_b200.build` or `__graft_entry__.build()`.
+The .so files are git-ignored but travel to the GPU box with the snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+CSRC = ROOT / "bayestyper_b200" / "csrc"
+LIBDIR = ROOT / "bayestyper_b200" / "lib"
+LIB = LIBDIR / "libbtgpu.so"
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _newer(target: Path, sources) -> bool:
+    if not target.exists():
+        return False
+    t = target.stat().st_mtime
+    return all(Path(s).stat().st_mtime <= t for s in sources)
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> Path:
+    LIBDIR.mkdir(parents=True, exist_ok=True)
+    cus = sorted(CSRC.glob("*.cu"))
+    deps = cus + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "btgpu.h"]
+    if not force and _newer(LIB, deps):
+        return LIB
+    if shutil.which(NVCC) is None and not Path(NVCC).exists():
+        raise RuntimeError("nvcc not found; libbtgpu.so cannot be built (no CPU fallback exists)")
+    objdir = ROOT / "build" / "obj"
+    objdir.mkdir(parents=True, exist_ok=True)
+    objs = []
+    procs = []
+    for cu in cus:
+        obj = objdir / (cu.stem + ".o")
+        objs.append(obj)
+        if not force and _newer(obj, [cu] + [d for d in deps if d.suffix in (".cuh", ".h")]):
+            continue
+        cmd = [NVCC, *NVCC_FLAGS, "-I", str(ROOT / "include"), "-c", str(cu), "-o", str(obj)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((cu, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cu, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(out)
+        if p.returncode:
+            raise RuntimeError(f"nvcc failed on {cu}")
+    cmd = [NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a",
+           "-Xcompiler", "-fPIC"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+def build_oracle(force: bool = False) -> Path:
+    """gcc build of the CPU restatement (test infrastructure; see oracle/README.md)."""
+    odir = ROOT / "oracle"
+    subprocess.check_call(["make", "-s", "-C", str(odir)] + (["-B"] if force else []))
+    return odir / "libbtoracle.so"
+
+
+if __name__ == "__main__":
+    v = "-v" in sys.argv
+    print(build_lib(force="-f" in sys.argv, verbose=v))
+    print(build_oracle())
