@@ -1,0 +1,262 @@
+"""Seeded synthetic inputs of the shapes BASELINE.json names.
+
+Produces what the two commands consume: a reference FASTA, a candidate VCF,
+samples.tsv and, per sample, the (canonical 55-mer, count) set a KMC database
+would hold (flat binary `<prefix>.kmers.bin`: u64 n, n x 2 x u64 packed k-mers in
+the boundary layout, n x u8 counts).  Pure numpy — independent of both the CUDA
+kernels and the oracle, so it can feed either side.
+"""
+from __future__ import annotations
+
+import dataclasses
+from pathlib import Path
+
+import numpy as np
+
+K = 55
+_ACGT = np.frombuffer(b"ACGT", np.uint8)
+_CODE = np.full(256, 4, np.uint8)
+for _i, _c in enumerate(b"ACGT"):
+    _CODE[_c] = _i
+    _CODE[ord(chr(_c).lower())] = _i
+
+
+@dataclasses.dataclass
+class Variant:
+    pos: int          # 0-based position of REF[0]
+    ref: bytes
+    alts: list        # list[bytes]
+
+
+@dataclasses.dataclass
+class Workload:
+    name: str
+    chrom: str
+    reference: bytes
+    variants: list            # list[Variant], sorted, non-overlapping
+    genotypes: np.ndarray     # (S, n_variants, 2) allele index per haplotype
+    genders: list             # 'F'/'M' per sample
+    depth_mean: float = 15.0  # haploid k-mer count mean
+    depth_var: float = 25.0
+
+
+def random_reference(length: int, seed: int, n_prefix: int = 0) -> bytes:
+    rng = np.random.default_rng(seed)
+    s = _ACGT[rng.integers(0, 4, length)]
+    if n_prefix:
+        s[:n_prefix] = ord("N")
+    return s.tobytes()
+
+
+def make_variants(reference: bytes, n: int, seed: int, frac_del: float = 0.0, frac_ins: float = 0.0,
+                  max_indel: int = 50, lo: int | None = None, hi: int | None = None) -> list:
+    """n candidate variants at distinct positions; SNV ALT = uniform other base;
+    indel lengths ~ Geometric(0.3) capped at max_indel, VCF-style anchor base.
+    Variants overlapping an earlier deletion's span (or an N) are dropped."""
+    rng = np.random.default_rng(seed)
+    ref = np.frombuffer(reference, np.uint8)
+    L = len(ref)
+    lo = K if lo is None else lo
+    hi = L - K if hi is None else hi
+    pos = np.sort(rng.choice(np.arange(lo, hi), size=n, replace=False))
+    kind = rng.random(n)
+    lens = np.minimum(rng.geometric(0.3, n), max_indel)
+    out = []
+    blocked_until = -1
+    for p, u, ln in zip(pos.tolist(), kind.tolist(), lens.tolist()):
+        if p <= blocked_until:
+            continue
+        if u < frac_del:
+            if p + 1 + ln + K >= L or (_CODE[ref[p:p + 1 + ln]] > 3).any():
+                continue
+            out.append(Variant(p, ref[p:p + 1 + ln].tobytes(), [ref[p:p + 1].tobytes()]))
+            blocked_until = p + ln
+        elif u < frac_del + frac_ins:
+            if _CODE[ref[p]] > 3:
+                continue
+            ins = _ACGT[rng.integers(0, 4, ln)].tobytes()
+            out.append(Variant(p, ref[p:p + 1].tobytes(), [ref[p:p + 1].tobytes() + ins]))
+            blocked_until = p
+        else:
+            if _CODE[ref[p]] > 3:
+                continue
+            alt = _ACGT[(int(_CODE[ref[p]]) + int(rng.integers(1, 4))) % 4]
+            out.append(Variant(p, ref[p:p + 1].tobytes(), [bytes([alt])]))
+            blocked_until = p
+    return out
+
+
+def make_genotypes(n_variants: int, n_samples: int, seed: int, probs=(0.4, 0.4, 0.2), allele_freq=None) -> np.ndarray:
+    """(S, n_variants, 2) alt-allele indicator per haplotype.  Either fixed
+    hom-ref/het/hom-alt probabilities or Hardy-Weinberg draws from allele_freq."""
+    rng = np.random.default_rng(seed)
+    g = np.zeros((n_samples, n_variants, 2), np.uint8)
+    if allele_freq is not None:
+        g[:] = rng.random((n_samples, n_variants, 2)) < allele_freq[None, :, None]
+        return g
+    u = rng.random((n_samples, n_variants))
+    het = (u >= probs[0]) & (u < probs[0] + probs[1])
+    hom = u >= probs[0] + probs[1]
+    side = rng.integers(0, 2, (n_samples, n_variants))
+    g[..., 0] = hom | (het & (side == 0))
+    g[..., 1] = hom | (het & (side == 1))
+    return g
+
+
+def apply_variants(reference: bytes, variants: list, alleles: np.ndarray) -> bytes:
+    """Haplotype sequence with allele index alleles[i] (0 = REF) at variants[i]."""
+    parts = []
+    cur = 0
+    for v, a in zip(variants, alleles.tolist()):
+        if a == 0:
+            continue
+        parts.append(reference[cur:v.pos])
+        parts.append(v.alts[a - 1])
+        cur = v.pos + len(v.ref)
+    parts.append(reference[cur:])
+    return b"".join(parts)
+
+
+# ---- numpy canonical k-mer enumeration (third, independent implementation) ------------------
+def canonical_kmers(seq: bytes) -> np.ndarray:
+    """(n, 2) uint64 canonical 55-mers (boundary layout) of every all-ACGT window, in order."""
+    c = _CODE[np.frombuffer(seq, np.uint8)].astype(np.uint64)
+    L = len(c)
+    if L < K:
+        return np.zeros((0, 2), np.uint64)
+    n = L - K + 1
+    bad = np.concatenate([[0], np.cumsum(c > 3)])
+    valid = (bad[K:] - bad[:-K]) == 0
+    c = np.where(c > 3, 0, c)
+    fw0 = np.zeros(n, np.uint64); fw1 = np.zeros(n, np.uint64)     # boundary words
+    rc0 = np.zeros(n, np.uint64); rc1 = np.zeros(n, np.uint64)
+    fhi = np.zeros(n, np.uint64); flo = np.zeros(n, np.uint64)     # MSB-first, for the compare
+    rhi = np.zeros(n, np.uint64); rlo = np.zeros(n, np.uint64)
+    three = np.uint64(3)
+    for i in range(K):
+        ci = c[i:i + n]
+        cc = three - ci
+        j = K - 1 - i                      # index of comp(nt_i) in the reverse-complement string
+        if i < 32:
+            fw0 |= ci << np.uint64(2 * i)
+        else:
+            fw1 |= ci << np.uint64(2 * (i - 32))
+        if j < 32:
+            rc0 |= cc << np.uint64(2 * j)
+        else:
+            rc1 |= cc << np.uint64(2 * (j - 32))
+        sh = 2 * (K - 1 - i)               # MSB-first position of nt_i
+        if sh >= 64:
+            fhi |= ci << np.uint64(sh - 64)
+        else:
+            flo |= ci << np.uint64(sh)
+        shr = 2 * (K - 1 - j)
+        if shr >= 64:
+            rhi |= cc << np.uint64(shr - 64)
+        else:
+            rlo |= cc << np.uint64(shr)
+    fwd = (fhi < rhi) | ((fhi == rhi) & (flo <= rlo))
+    out = np.empty((n, 2), np.uint64)
+    out[:, 0] = np.where(fwd, fw0, rc0)
+    out[:, 1] = np.where(fwd, fw1, rc1)
+    return out[valid]
+
+
+def unique_kmers(kmers: np.ndarray):
+    """(unique (m,2) array, multiplicity) — sorted by (w1, w0)."""
+    if len(kmers) == 0:
+        return kmers, np.zeros(0, np.int64)
+    order = np.lexsort((kmers[:, 0], kmers[:, 1]))
+    s = kmers[order]
+    new = np.ones(len(s), bool)
+    new[1:] = (s[1:] != s[:-1]).any(axis=1)
+    idx = np.nonzero(new)[0]
+    mult = np.diff(np.append(idx, len(s)))
+    return s[idx], mult
+
+
+def nb_counts(rng, copies: np.ndarray, mean: float, var: float) -> np.ndarray:
+    """NB(mean*copies, var*copies) draws, saturated at 255 (KmerCounts.cpp:178-189)."""
+    p = mean / var
+    size = mean * mean / (var - mean) * copies
+    return np.minimum(rng.negative_binomial(size, p), 255).astype(np.uint8)
+
+
+def sample_kmer_counts(haplotypes: list, seed: int, mean: float, var: float, n_errors: int = 0):
+    """The k-mer spectrum a KMC run on reads of this sample would hold."""
+    rng = np.random.default_rng(seed)
+    km = np.concatenate([canonical_kmers(h) for h in haplotypes])
+    uniq, copies = unique_kmers(km)
+    counts = nb_counts(rng, copies, mean, var)
+    keep = counts > 0                      # KMC -ci1: zero-count k-mers are absent
+    uniq, counts = uniq[keep], counts[keep]
+    if n_errors:
+        err = rng.integers(0, 2**64, size=(n_errors, 2), dtype=np.uint64)
+        err[:, 1] &= np.uint64((1 << (2 * K - 64)) - 1)
+        uniq = np.concatenate([uniq, err])
+        counts = np.concatenate([counts, np.ones(n_errors, np.uint8)])
+    return np.ascontiguousarray(uniq), np.ascontiguousarray(counts)
+
+
+# ---- configs ---------------------------------------------------------------------------------
+def config_a(n_variants: int = 10_000, length: int = 1_000_000, n_samples: int = 1, seed: int = 1) -> Workload:
+    """BASELINE.json configs[0]: 1 sample, 10k SNVs on a 1 Mb reference."""
+    ref = random_reference(length, seed)
+    var = make_variants(ref, n_variants, seed + 1)
+    g = make_genotypes(len(var), n_samples, seed + 2)
+    return Workload("A", "chr1", ref, var, g, ["F"] * n_samples)
+
+
+def config_b(n_variants: int = 300_000, length: int = 50_800_000, n_prefix: int = 10_000_000, seed: int = 11) -> Workload:
+    """configs[1]: chr22-like, 85% SNV / 7.5% deletions / 7.5% insertions, 1 sample."""
+    ref = random_reference(length, seed, n_prefix)
+    var = make_variants(ref, n_variants, seed + 1, 0.075, 0.075, lo=n_prefix + K)
+    g = make_genotypes(len(var), 1, seed + 2)
+    return Workload("B", "chr22", ref, var, g, ["F"])
+
+
+def small_mixed(n_variants: int, length: int, n_samples: int, seed: int, frac_indel: float = 0.15) -> Workload:
+    ref = random_reference(length, seed)
+    var = make_variants(ref, n_variants, seed + 1, frac_indel / 2, frac_indel / 2, max_indel=20)
+    rng = np.random.default_rng(seed + 5)
+    af = rng.beta(0.5, 0.8, len(var))
+    g = make_genotypes(len(var), n_samples, seed + 2, allele_freq=af)
+    genders = ["F" if i % 2 == 0 else "M" for i in range(n_samples)]
+    return Workload("mixed", "chr1", ref, var, g, genders)
+
+
+def sample_spectra(w: Workload, seed: int = 4, n_errors: int = 0):
+    out = []
+    for s in range(w.genotypes.shape[0]):
+        haps = [apply_variants(w.reference, w.variants, w.genotypes[s, :, h]) for h in range(2)]
+        out.append(sample_kmer_counts(haps, seed + 17 * s, w.depth_mean, w.depth_var, n_errors))
+    return out
+
+
+def write_kmer_file(path, kmers: np.ndarray, counts: np.ndarray | None = None) -> None:
+    with open(path, "wb") as f:
+        np.array([len(kmers)], np.uint64).tofile(f)
+        np.ascontiguousarray(kmers, np.uint64).tofile(f)
+        if counts is not None:
+            np.ascontiguousarray(counts, np.uint8).tofile(f)
+
+
+def write_workdir(w: Workload, wd, spectra=None, seed: int = 4, n_errors: int = 0) -> Path:
+    """genome.fa, variants.vcf, samples.tsv and <sample>.kmers.bin under wd."""
+    wd = Path(wd)
+    wd.mkdir(parents=True, exist_ok=True)
+    with open(wd / "genome.fa", "wb") as f:
+        f.write(b">" + w.chrom.encode() + b"\n")
+        for i in range(0, len(w.reference), 60):
+            f.write(w.reference[i:i + 60] + b"\n")
+    with open(wd / "variants.vcf", "w") as f:
+        f.write("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
+        for i, v in enumerate(w.variants):
+            f.write(f"{w.chrom}\t{v.pos + 1}\tv{i}\t{v.ref.decode()}\t{','.join(a.decode() for a in v.alts)}\t.\t.\t.\n")
+    spectra = spectra if spectra is not None else sample_spectra(w, seed, n_errors)
+    with open(wd / "samples.tsv", "w") as f:
+        for s, (km, ct) in enumerate(spectra):
+            prefix = wd / f"S{s + 1}"
+            f.write(f"S{s + 1}\t{w.genders[s]}\t{prefix}\n")
+            write_kmer_file(str(prefix) + ".kmers.bin", km, ct)
+    return wd
