@@ -7,4 +7,17 @@ vp = C.c_void_p
 
 
 def bind(L):
-    pass
+    L.btg_count_dist_create.restype = vp
+    L.btg_count_dist_create.argtypes = [C.c_uint32, vp, vp, C.c_float, C.c_float]
+    L.btg_nb_moments_to_parameters.restype = None
+    L.btg_nb_moments_to_parameters.argtypes = [C.c_double, C.c_double, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.btg_count_dist_set_noise_rates.argtypes = [vp, vp]
+    L.btg_count_dist_get_noise_rates.argtypes = [vp, vp]
+    L.btg_count_dist_tables.argtypes = [vp, vp, vp]
+    L.btg_count_dist_free.argtypes = [vp]
+    L.btg_unit_upload.restype = vp
+    L.btg_unit_upload.argtypes = [vp]
+    L.btg_unit_free.argtypes = [vp]
+    L.btg_estimate_genotypes.argtypes = [vp, vp, vp, vp]
+    L.btg_estimate_noise.argtypes = [vp, vp, vp, vp]
+    L.btg_unit_cluster_tally.argtypes = [vp, C.c_uint32, vp, C.c_uint64]

@@ -1,0 +1,1171 @@
+// gibbs.cu — the per-cluster Gibbs sampler on the device (sm_100a).
+//
+// Replaces, for one inference unit resident in HBM:
+//   InferenceEngine::estimateGenotypes / estimateNoise        src/bayesTyper/InferenceEngine.cpp:135-382
+//   VariantClusterGroup::estimateGenotypes / runGibbsSample   src/bayesTyper/VariantClusterGroup.cpp:220-250
+//   VariantClusterGenotyper (ctor, reset, sampleDiplotypes, sampleDiplotype, calcDiplotypeLogProb,
+//     sampleHaplotypeFrequencies, getNoiseCounts, getGenotypes…)  src/bayesTyper/VariantClusterGenotyper.cpp
+//   VariantClusterHaplotypes (sampleKmerSubset, updateAlleleKmerStats…) src/bayesTyper/VariantClusterHaplotypes.cpp
+//   CountDistribution / NegativeBinomialDistribution tables   src/bayesTyper/CountDistribution.cpp
+//   (Sparse)FrequencyDistribution, SparsityEstimator, DiscreteSampler, KmerStats, CountAllocation
+//
+// Mapping.  Variant-cluster groups are independent and, inside a group, the sampler is
+// a strictly sequential chain (sample s+1 sees the haplotype counts left by sample s; iteration i+1 sees
+// the frequencies drawn in iteration i).  The unit of parallelism is therefore the GROUP: one thread
+// walks one group through all chains x iterations with its state in a private arena slice; groups are
+// sorted by cost so that the 32 lanes of a warp carry similar work.  All arithmetic is f64 (the
+// reference's), table lookups go to the L2-resident log-pmf cache ([S][256][256] doubles).
+//
+// This file handles groups made of ONE cluster (no nested clusters, hence no multicluster k-mers);
+// btg_unit_upload rejects units that contain nested groups (explicit error, no fallback).
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+#include "gibbs_rng.cuh"
+
+using namespace btg;
+
+namespace {
+
+constexpr uint16_t NONE = 0xFFFF;  // Utils::ushort_overflow
+constexpr double kDoubleEps100 = 2.220446049250313e-16 * 100;
+constexpr float kFloatEps100 = 1.1920929e-07f * 100;
+
+__host__ __device__ inline bool doubleCompare(double a, double b) {  // Utils.hpp:81-87
+    return (a == b) || (fabs(a - b) < fabs(a < b ? a : b) * kDoubleEps100);
+}
+__host__ __device__ inline bool floatCompare(float a, float b) {  // Utils.hpp:89-95
+    return (a == b) || (fabsf(a - b) < fabsf(a < b ? a : b) * kFloatEps100);
+}
+__host__ __device__ inline bool floatLess(float a, float b) { return (a < b) && !floatCompare(a, b); }
+__device__ __forceinline__ double logAddition(double a, double b) {  // Utils.hpp:105-124
+    return a < b ? b + log1p(exp(a - b)) : a + log1p(exp(b - a));
+}
+
+// ---------------------------------------------------------------------------------------------
+// CountDistribution tables
+// ---------------------------------------------------------------------------------------------
+__device__ double nbLogPmf(double p, double size, uint32_t obs, uint32_t scale) {  // NegativeBinomialDistribution.cpp:121-147
+    const double coef = lgamma(obs + size * scale) - lgamma(size * scale) - lgamma((double)(obs + 1));
+    return coef + log(p) * size * scale + log(1 - p) * obs;
+}
+__device__ double poissonLogProb(uint32_t value, double rate) {  // CountDistribution.cpp:349-352
+    return value * log(rate) - rate - lgamma((double)(value + 1));
+}
+
+// CountDistribution::updateGenomicCache / genomicCountLogPmf (CountDistribution.cpp:215-238,267-312): one thread per (s, m, c)
+__global__ void k_genomic_table(const double *__restrict__ p, const double *__restrict__ size, uint32_t S, double *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S * 65536u) return;
+    const uint32_t s = i >> 16, m = (i >> 8) & 255u, c = i & 255u;
+    double v;
+    if (m == 0) {
+        v = c == 0 ? 0.0 : -INFINITY;
+    } else {
+        v = nbLogPmf(p[s], size[s], c, m);
+        if (c == 255) {
+            uint32_t limit = c;
+            double prev;
+            do {
+                limit++;
+                prev = v;
+                v = logAddition(v, nbLogPmf(p[s], size[s], limit, m));
+                if (v > 0) { v = 0; break; }
+            } while (!doubleCompare(prev, v));
+        }
+    }
+    out[i] = v;
+}
+
+// CountDistribution::updateNoiseCache / noiseCountLogPmf (CountDistribution.cpp:240-253,314-347): one thread per (s, c)
+__device__ double noiseCountLogPmf(double rate, uint32_t c) {
+    double v = poissonLogProb(c, rate);
+    if (c == 255) {
+        uint32_t limit = c;
+        double prev;
+        do {
+            limit++;
+            prev = v;
+            v = logAddition(v, poissonLogProb(limit, rate));
+            if (v > 0) { v = 0; break; }
+        } while (!doubleCompare(prev, v));
+    }
+    return v;
+}
+__global__ void k_noise_table(const double *__restrict__ rates, uint32_t S, double *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S * 256u) return;
+    out[i] = noiseCountLogPmf(rates[i >> 8], i & 255u);
+}
+
+__global__ void k_lgamma_int(double *out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = lgamma((double)i);  // out[0] = inf, never read
+}
+
+}  // namespace
+
+struct btg_count_dist {
+    uint32_t S = 0;
+    double *p = nullptr, *size = nullptr, *rates = nullptr;  // device [S]
+    double *genomic = nullptr;                               // device [S][256][256]
+    double *noise = nullptr;                                 // device [S][256]
+    float prior_shape = 1.f, prior_scale = 0.01f;
+    std::vector<double> h_p, h_size;
+};
+
+// ---------------------------------------------------------------------------------------------
+// unit on the device
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct ClusterLayout {
+    uint64_t f64_off, u32_off, u8_off;  // arena slices
+    uint32_t group;                     // owning group
+    uint32_t n_alleles;                 // sum of numberOfAlleles over the cluster's variants
+    uint32_t Dall;                      // (H+1)(H+2)/2 diplotype slots (index H = "missing")
+    uint32_t pad;
+};
+
+struct DevUnit {
+    uint32_t S, G, C;
+    const uint8_t *sample_gender, *group_ploidy;
+    const uint64_t *group_cluster_off;
+    const uint32_t *cluster_idx, *cl_nhap;
+    const uint64_t *cl_kmer_off, *cl_var_off, *cl_mult_off;
+    const uint8_t *mult, *k_has_counts, *k_counts, *k_ic;
+    const uint64_t *cl_uniq_off;
+    const uint32_t *uniq_idx;
+    const uint64_t *kmer_vh_off;
+    const uint16_t *vh_var;
+    const uint64_t *vh_bits_off;
+    const uint8_t *vh_bits;
+    const uint64_t *cl_hapvar_off;
+    const uint16_t *hap_alleles, *var_nalleles;
+    const uint8_t *var_dep;
+    const uint64_t *valt_off;    // prefix sums of numberOfAlleles over all variants
+    const ClusterLayout *layout;
+    const uint32_t *order;       // clusters sorted by decreasing cost
+    double *f64_pool;
+    uint32_t *u32_pool;
+    uint8_t *u8_pool;
+    const double *lgamma_int;
+};
+
+// arena sizes (elements) of one cluster — must match the pointer carving in Cl::bind
+struct ArenaSizes { uint64_t f64, u32, u8; };
+__host__ __device__ inline ArenaSizes arena_sizes(uint32_t S, uint32_t H, uint32_t K, uint32_t nvar, uint32_t n_uniq, uint32_t n_alleles, uint32_t Dall) {
+    ArenaSizes a;
+    a.f64 = (uint64_t)H            /* freq */
+          + (H + 1)                /* simplex prob vector */
+          + (uint64_t)S * Dall     /* unique diplotype log-prob cache */
+          + Dall                   /* cumulative log-probs of one draw */
+          + (uint64_t)S * 2 * nvar * 2   /* k-mer stats cache (fraction, mean) */
+          + (uint64_t)n_alleles * S * 6  /* allele k-mer stats: 3 x (fraction, mean) */
+          + 2;                     /* sparsity, spare */
+    a.u32 = (uint64_t)H            /* observation counts */
+          + n_uniq * 2ull          /* unique k-mer order, subset */
+          + (uint64_t)H * nvar     /* subset counters per (haplotype, variant) */
+          + (uint64_t)Dall * S     /* diplotype tallies */
+          + (uint64_t)S * 2 * nvar /* k-mer stats cache counts */
+          + (uint64_t)n_alleles * S * 3  /* allele stats counts */
+          + S                      /* current diplotypes (first | second << 16) */
+          + 32;                    /* misc + rng states */
+    a.u8 = (uint64_t)H + K + S;    /* non-zero flags, uncovered rows, stats-cache update flags */
+    a.u8 = (a.u8 + 7) & ~7ull;
+    return a;
+}
+
+enum Misc { kNSub = 0, kNumHap = 1, kNumMissing = 2, kSimplexNobs = 3, kSimplexPlus = 4, kSimplexLen = 5, kSparse = 6, kCover = 7, kRng0 = 8, kRng1 = 16 };
+
+// per-cluster view
+struct Cl {
+    uint32_t S, H, K, nvar, n_uniq, Dall, n_alleles, c, g;
+    uint64_t row0, var0;
+    const DevUnit *u;
+    const uint8_t *M;
+    double *freq, *simplex, *ucache, *cum, *kc_f, *as_f, *fmisc;
+    uint32_t *obs, *uniq, *uniq_sub, *cnt, *tally, *kc_n, *as_n, *dipl, *misc;
+    uint8_t *nz, *uncovered, *stats_update;
+
+    __device__ void bind(const DevUnit &du, uint32_t cluster) {
+        u = &du; c = cluster;
+        const ClusterLayout L = du.layout[c];
+        g = L.group;
+        S = du.S;
+        H = du.cl_nhap[c];
+        row0 = du.cl_kmer_off[c];
+        K = (uint32_t)(du.cl_kmer_off[c + 1] - row0);
+        var0 = du.cl_var_off[c];
+        nvar = (uint32_t)(du.cl_var_off[c + 1] - var0);
+        n_uniq = (uint32_t)(du.cl_uniq_off[c + 1] - du.cl_uniq_off[c]);
+        Dall = L.Dall;
+        n_alleles = L.n_alleles;
+        M = du.mult + du.cl_mult_off[c];
+        double *f = du.f64_pool + L.f64_off;
+        freq = f; f += H;
+        simplex = f; f += H + 1;
+        ucache = f; f += (uint64_t)S * Dall;
+        cum = f; f += Dall;
+        kc_f = f; f += (uint64_t)S * 2 * nvar * 2;
+        as_f = f; f += (uint64_t)n_alleles * S * 6;
+        fmisc = f;
+        uint32_t *w = du.u32_pool + L.u32_off;
+        obs = w; w += H;
+        uniq = w; w += n_uniq;
+        uniq_sub = w; w += n_uniq;
+        cnt = w; w += (uint64_t)H * nvar;
+        tally = w; w += (uint64_t)Dall * S;
+        kc_n = w; w += (uint64_t)S * 2 * nvar;
+        as_n = w; w += (uint64_t)n_alleles * S * 3;
+        dipl = w; w += S;
+        misc = w;
+        uint8_t *b = du.u8_pool + L.u8_off;
+        nz = b; b += H;
+        uncovered = b; b += K;
+        stats_update = b;
+    }
+    __device__ __forceinline__ uint8_t m(uint32_t k, uint32_t h) const { return M[(size_t)k * H + h]; }
+    __device__ __forceinline__ uint8_t count(uint32_t k, uint32_t s) const { return u->k_has_counts[row0 + k] ? u->k_counts[(row0 + k) * S + s] : 0; }
+    __device__ __forceinline__ uint8_t ic(uint32_t k, uint32_t s) const { return u->k_has_counts[row0 + k] ? u->k_ic[(row0 + k) * 2 + u->sample_gender[s]] : 0; }
+    __device__ __forceinline__ uint16_t nalleles(uint32_t v) const { return u->var_nalleles[var0 + v]; }
+    __device__ __forceinline__ bool isMissing(uint32_t v, uint16_t a) const { return u->var_dep[var0 + v] && a == nalleles(v) - 1; }  // VariantInfo.hpp:82-94
+    __device__ __forceinline__ uint16_t hapAllele(uint32_t h, uint32_t v) const { return u->hap_alleles[u->cl_hapvar_off[c] + (size_t)h * nvar + v]; }
+    __device__ __forceinline__ uint32_t alleleBase(uint32_t v, uint32_t s) const {  // index of (v, s, allele 0) in allele-major arrays
+        return (uint32_t)(u->valt_off[var0 + v] - u->valt_off[var0]) * S + s * nalleles(v);
+    }
+    // dense diplotype slot: h in [0,H], H = missing; first <= second
+    __device__ __forceinline__ uint32_t slot(uint32_t a, uint32_t b) const { return b * (b + 1) / 2 + a; }
+    __device__ __forceinline__ uint8_t diplMult(uint32_t k, uint32_t a, uint32_t b) const {  // …Haplotypes.cpp:45-61
+        uint8_t r = 0;
+        if (a != NONE) r += m(k, a);
+        if (b != NONE) r += m(k, b);
+        return r;
+    }
+};
+
+// KmerStats::addValue without M2 (KmerStats.cpp:51-63); M2 is never read on this path
+__device__ __forceinline__ void kstat_add(uint32_t &n, double &fraction, double &mean, double v) {
+    n++;
+    fraction += ((doubleCompare(v, 0) ? 0.0 : 1.0) - fraction) / n;
+    const double delta = v - mean;
+    mean += delta / n;
+}
+
+struct Tables {
+    const double *genomic;  // [S][256][256]
+    const double *noise;    // [S][256]
+    __device__ __forceinline__ double logProb(uint32_t s, uint8_t m, uint8_t c) const {  // CountDistribution.cpp:255-265
+        return m == 0 ? __ldg(noise + s * 256u + c) : __ldg(genomic + ((size_t)s * 256 + m) * 256 + c);
+    }
+};
+
+// ---- VariantClusterGenotyper ctor: sparsity estimate + frequency reset ------------------------
+__device__ void cl_reset_frequencies(Cl &cl) {  // FrequencyDistribution.cpp:46-51,104-115
+    const double f0 = 1 / static_cast<double>(cl.H);
+    for (uint32_t h = 0; h < cl.H; h++) { cl.obs[h] = 0; cl.freq[h] = f0; cl.nz[h] = 1; }
+}
+
+__device__ void cl_construct(Cl &cl, const btg_gibbs_opts &o, uint64_t group_index, uint32_t chain) {
+    const uint32_t H = cl.H, K = cl.K, S = cl.S;
+    const uint32_t *src = cl.u->uniq_idx + cl.u->cl_uniq_off[cl.c];
+    for (uint32_t i = 0; i < cl.n_uniq; i++) cl.uniq[i] = src[i];
+    for (uint32_t i = 0; i < cl.Dall * S; i++) cl.tally[i] = 0;
+    for (uint32_t s = 0; s < S; s++) { cl.dipl[s] = 0xFFFFFFFFu; cl.stats_update[s] = 1; }
+    for (uint32_t i = 0; i < S * 2 * cl.nvar; i++) { cl.kc_n[i] = 0; cl.kc_f[2 * i] = 0; cl.kc_f[2 * i + 1] = 0; }
+    for (uint32_t i = 0; i < cl.n_alleles * S * 3; i++) { cl.as_n[i] = 0; cl.as_f[2 * i] = 0; cl.as_f[2 * i + 1] = 0; }
+    for (int i = 0; i < 8; i++) cl.misc[i] = 0;
+    cl.misc[kSimplexNobs] = 0xFFFFFFFFu;
+    // SparsityEstimator::estimateMinimumColumnCover (SparsityEstimator.cpp:41-90), stream kind 1
+    Philox sp;
+    sp.init(o.random_seed, group_index, cl.u->cluster_idx[cl.c], kRngSparsity, chain);
+    uint32_t n_unc = 0;
+    for (uint32_t k = 0; k < K; k++) { cl.uncovered[k] = cl.u->k_has_counts[cl.row0 + k]; n_unc += cl.uncovered[k]; }
+    uint32_t cover = 0;
+    while (n_unc > 0) {
+        // column cover = sum of multiplicities over uncovered rows; cnt[] doubles as the scratch row
+        uint32_t mx = 0, ties = 0;
+        for (uint32_t h = 0; h < H; h++) {
+            uint32_t col = 0;
+            for (uint32_t k = 0; k < K; k++) if (cl.uncovered[k]) col += cl.m(k, h);
+            cl.cnt[h] = col;
+            if (col > mx) { mx = col; ties = 1; } else if (col == mx) ties++;
+        }
+        // DiscreteSampler with unit weights (DiscreteSampler.cpp:61-87): u * n against cum = 1..n
+        const double x = sp.u01() * (double)ties;
+        uint32_t idx = 0;
+        if (ties > 1) while (idx + 1 < ties && !(x < (double)(idx + 1))) idx++;
+        uint32_t pick = 0, seen = 0;
+        for (uint32_t h = 0; h < H; h++) if (cl.cnt[h] == mx) { if (seen == idx) { pick = h; break; } seen++; }
+        cover++;
+        for (uint32_t k = 0; k < K; k++) if (cl.uncovered[k] && cl.m(k, pick)) { cl.uncovered[k] = 0; n_unc--; }
+    }
+    cl.misc[kCover] = cover;
+    cl.misc[kSparse] = cover > 0;
+    if (cover > 0) {  // SparseFrequencyDistribution ctor (FrequencyDistribution.cpp:97-103)
+        const double sp_in = cover / static_cast<double>(H), cap = 1 - 2.220446049250313e-16 * 100;
+        cl.fmisc[0] = sp_in < cap ? sp_in : cap;
+    } else cl.fmisc[0] = 0;
+    cl_reset_frequencies(cl);
+}
+
+// VariantClusterHaplotypes::isMaxHaplotypeVariantKmer (VariantClusterHaplotypes.cpp:159-178)
+__device__ bool cl_is_max_hap_var_kmer(Cl &cl, uint32_t k, uint32_t max_kmers) {
+    bool is_max = true;
+    const DevUnit &u = *cl.u;
+    for (uint64_t e = u.kmer_vh_off[cl.row0 + k]; e < u.kmer_vh_off[cl.row0 + k + 1]; e++) {
+        const uint32_t v = u.vh_var[e];
+        const uint8_t *bits = u.vh_bits + u.vh_bits_off[e];
+        for (uint32_t h = 0; h < cl.H; h++)
+            if (bits[h] && cl.cnt[(size_t)h * cl.nvar + v] < max_kmers) { cl.cnt[(size_t)h * cl.nvar + v]++; is_max = false; }
+    }
+    return is_max;
+}
+
+// VariantClusterGenotyper::reset + VariantClusterHaplotypes::sampleKmerSubset (…Genotyper.cpp:113-129, …Haplotypes.cpp:110-157)
+__device__ void cl_reset(Cl &cl, const btg_gibbs_opts &o, Philox &prng) {
+    const double rate = (double)o.kmer_subsampling_rate;
+    for (uint32_t i = 0; i < cl.H * cl.nvar; i++) cl.cnt[i] = 0;
+    for (uint32_t i = cl.n_uniq; i > 1; i--) {  // Fisher-Yates from the back
+        const uint32_t j = prng.uniform_int(i);
+        const uint32_t t = cl.uniq[i - 1]; cl.uniq[i - 1] = cl.uniq[j]; cl.uniq[j] = t;
+    }
+    uint32_t n_sub = 0;
+    for (uint32_t i = 0; i < cl.n_uniq; i++) {
+        const uint32_t k = cl.uniq[i];
+        if (prng.u01() < rate)
+            if (!cl_is_max_hap_var_kmer(cl, k, o.max_haplotype_variant_kmers)) cl.uniq_sub[n_sub++] = k;
+    }
+    cl.misc[kNSub] = n_sub;
+    for (uint32_t s = 0; s < cl.S; s++) cl.stats_update[s] = 1;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (uint32_t i = 0; i < cl.S * cl.Dall; i++) cl.ucache[i] = nan;  // clear the per-sample diplotype caches
+    cl_reset_frequencies(cl);
+}
+
+// VariantClusterGenotyper::calcDiplotypeLogProb (VariantClusterGenotyper.cpp:597-666)
+__device__ double cl_dipl_log_prob(Cl &cl, const Tables &T, uint32_t s, uint32_t a, uint32_t b) {
+    double lp = 0;
+    if (b == NONE) lp += log(cl.freq[a]);
+    else if (a == b) lp += 2 * log(cl.freq[a]);
+    else lp += log(2.0) + log(cl.freq[a]) + log(cl.freq[b]);
+    double *cache = cl.ucache + (size_t)s * cl.Dall + cl.slot(a, b == NONE ? cl.H : b);
+    double acc = *cache;
+    if (acc != acc) {  // not cached yet
+        acc = 0;
+        const uint32_t n_sub = cl.misc[kNSub];
+        for (uint32_t i = 0; i < n_sub; i++) {
+            const uint32_t k = cl.uniq_sub[i];
+            acc += T.logProb(s, (uint8_t)(cl.diplMult(k, a, b) + cl.ic(k, s)), cl.count(k, s));
+        }
+        *cache = acc;
+    }
+    return lp + acc;
+}
+
+__device__ __forceinline__ void cl_increment(Cl &cl, uint32_t h) {  // HaplotypeFrequencyDistribution.cpp:114-126
+    if (h == NONE) { cl.misc[kNumMissing]++; return; }
+    cl.misc[kNumHap]++;
+    cl.obs[h]++;
+}
+
+// VariantClusterGenotyper::sampleDiplotype (VariantClusterGenotyper.cpp:707-755) + LogDiscreteSampler (DiscreteSampler.cpp:106-126)
+__device__ void cl_sample_diplotype(Cl &cl, const Tables &T, uint32_t s, uint8_t ploidy, Philox &prng) {
+    uint32_t n = 0;
+    double run = 0;
+    const uint32_t H = cl.H;
+    if (ploidy == 2) {
+        for (uint32_t a = 0; a < H; a++) {
+            if (!cl.nz[a]) continue;
+            for (uint32_t b = a; b < H; b++) {
+                if (!cl.nz[b]) continue;
+                const double lp = cl_dipl_log_prob(cl, T, s, a, b);
+                run = n == 0 ? lp : logAddition(lp, run);
+                cl.cum[n++] = run;
+            }
+        }
+    } else if (ploidy == 1) {
+        for (uint32_t a = 0; a < H; a++) {
+            if (!cl.nz[a]) continue;
+            const double lp = cl_dipl_log_prob(cl, T, s, a, NONE);
+            run = n == 0 ? lp : logAddition(lp, run);
+            cl.cum[n++] = run;
+        }
+    } else {
+        cl.cum[n++] = 0;
+    }
+    const double x = log(prng.u01()) + run;
+    uint32_t idx = 0;
+    if (n > 1) {  // upper_bound
+        uint32_t lo = 0, hi = n;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (x < cl.cum[mid]) hi = mid; else lo = mid + 1; }
+        idx = lo < n ? lo : n - 1;
+    }
+    // map the outcome index back to (a, b) in enumeration order
+    uint32_t da = NONE, db = NONE;
+    if (ploidy == 2) {
+        uint32_t i = 0;
+        for (uint32_t a = 0; a < H && da == NONE; a++) {
+            if (!cl.nz[a]) continue;
+            for (uint32_t b = a; b < H; b++) {
+                if (!cl.nz[b]) continue;
+                if (i == idx) { da = a; db = b; break; }
+                i++;
+            }
+        }
+    } else if (ploidy == 1) {
+        uint32_t i = 0;
+        for (uint32_t a = 0; a < H; a++) { if (!cl.nz[a]) continue; if (i == idx) { da = a; break; } i++; }
+    }
+    cl.dipl[s] = (da & 0xFFFFu) | (db << 16);
+    cl_increment(cl, da);
+    cl_increment(cl, db);
+}
+
+// VariantClusterHaplotypes::updateAlleleKmerStats (VariantClusterHaplotypes.cpp:235-372), single-cluster groups
+__device__ void cl_add_haplotype_stats(Cl &cl, uint32_t s, uint32_t which, uint32_t h) {  // addHaplotypeKmerStats
+    uint32_t last = NONE;
+    for (uint32_t v = 0; v < cl.nvar; v++) {
+        const uint16_t a = cl.hapAllele(h, v);
+        uint32_t srcv;
+        if (cl.isMissing(v, a)) srcv = last; else { srcv = v; last = v; }
+        const uint32_t ci = (s * 2 + which) * cl.nvar + srcv;
+        const uint32_t n = cl.kc_n[ci];
+        const uint32_t ai = cl.alleleBase(v, s) + a;
+        // AlleleKmerStats::addKmerStats (KmerStats.cpp:115-122): count, fraction (if any), mean (if any)
+        kstat_add(cl.as_n[ai * 3 + 0], cl.as_f[(ai * 3 + 0) * 2], cl.as_f[(ai * 3 + 0) * 2 + 1], (double)n);
+        if (n > 0) {
+            kstat_add(cl.as_n[ai * 3 + 1], cl.as_f[(ai * 3 + 1) * 2], cl.as_f[(ai * 3 + 1) * 2 + 1], cl.kc_f[2 * ci]);
+            kstat_add(cl.as_n[ai * 3 + 2], cl.as_f[(ai * 3 + 2) * 2], cl.as_f[(ai * 3 + 2) * 2 + 1], cl.kc_f[2 * ci + 1]);
+        }
+    }
+}
+
+__device__ void cl_update_allele_stats(Cl &cl) {
+    const DevUnit &u = *cl.u;
+    for (uint32_t s = 0; s < cl.S; s++) {
+        const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
+        if (cl.stats_update[s]) {
+            cl.stats_update[s] = 0;
+            for (uint32_t i = s * 2 * cl.nvar; i < (s + 1) * 2 * cl.nvar; i++) { cl.kc_n[i] = 0; cl.kc_f[2 * i] = 0; cl.kc_f[2 * i + 1] = 0; }
+            if (da != NONE) {
+                const uint32_t n_sub = cl.misc[kNSub];
+                for (uint32_t i = 0; i < n_sub; i++) {
+                    const uint32_t k = cl.uniq_sub[i];
+                    const uint8_t dm = cl.diplMult(k, da, db);
+                    if (dm == 0) continue;
+                    const uint8_t mult = (uint8_t)(dm + cl.ic(k, s));
+                    // updateKmerStatsCache (…Haplotypes.cpp:302-333)
+                    const double kc = u.k_has_counts[cl.row0 + k] ? cl.count(k, s) / static_cast<double>(mult) : 0.0;
+                    for (uint64_t e = u.kmer_vh_off[cl.row0 + k]; e < u.kmer_vh_off[cl.row0 + k + 1]; e++) {
+                        const uint32_t v = u.vh_var[e];
+                        const uint8_t *bits = u.vh_bits + u.vh_bits_off[e];
+                        if (bits[da]) { const uint32_t ci = (s * 2 + 0) * cl.nvar + v; kstat_add(cl.kc_n[ci], cl.kc_f[2 * ci], cl.kc_f[2 * ci + 1], kc); }
+                        if (db != NONE && bits[db]) { const uint32_t ci = (s * 2 + 1) * cl.nvar + v; kstat_add(cl.kc_n[ci], cl.kc_f[2 * ci], cl.kc_f[2 * ci + 1], kc); }
+                    }
+                }
+            }
+        }
+        if (da != NONE) cl_add_haplotype_stats(cl, s, 0, da);
+        if (db != NONE) cl_add_haplotype_stats(cl, s, 1, db);
+    }
+}
+
+// VariantClusterGenotyper::sampleDiplotypes (VariantClusterGenotyper.cpp:668-705)
+__device__ void cl_sample_diplotypes(Cl &cl, const Tables &T, const uint8_t *ploidy, bool collect, Philox &prng) {
+    for (uint32_t s = 0; s < cl.S; s++) {
+        const uint32_t prev = cl.dipl[s];
+        cl_sample_diplotype(cl, T, s, ploidy[s], prng);
+        if (cl.dipl[s] != prev) cl.stats_update[s] = 1;  // …Haplotypes.cpp:199-201
+        if (collect) {
+            const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
+            cl.tally[(size_t)cl.slot(da == NONE ? cl.H : da, db == NONE ? cl.H : db) * cl.S + s]++;
+        }
+    }
+    if (collect) cl_update_allele_stats(cl);
+}
+
+// SparseFrequencyDistribution::updateCachedSimplexProbVector (FrequencyDistribution.cpp:143-196);
+// lgamma of the integer arguments comes from a table shared by all clusters
+__device__ uint32_t cl_simplex_vector(Cl &cl, uint32_t n_obs, uint32_t plus) {
+    const double *lg = cl.u->lgamma_int;
+    const uint32_t H = cl.H;
+    const double sparsity = cl.fmisc[0];
+    const double ls = log(sparsity), l1s = log(1 - sparsity);
+    double prob_z = plus * ls + (H - plus) * l1s;
+    double prob_t = lg[plus] - lg[n_obs + plus];
+    double row_sum = 0 + prob_z + prob_t;
+    uint32_t len = 0;
+    cl.simplex[len++] = row_sum;
+    for (uint32_t j = plus + 1; j < H + 1; j++) {
+        const double cardinal = lg[H - plus + 1] - (lg[j - plus + 1] + lg[H - j + 1]);
+        prob_z = j * ls + (H - j) * l1s;
+        prob_t = lg[j] - lg[n_obs + j];
+        const double prob_eq = cardinal + prob_z + prob_t;
+        row_sum += log(1 + exp(prob_eq - row_sum));
+        cl.simplex[len++] = row_sum;
+        if (doubleCompare(cl.simplex[len - 1], cl.simplex[len - 2])) break;
+    }
+    for (uint32_t i = 0; i < len; i++) cl.simplex[i] = exp(cl.simplex[i] - row_sum);
+    return len;
+}
+
+// VariantClusterGenotyper::sampleHaplotypeFrequencies (…Genotyper.cpp:781-785) ->
+// (Sparse)FrequencyDistribution::sampleFrequencies (FrequencyDistribution.cpp:75-94,209-304)
+__device__ void cl_sample_frequencies(Cl &cl, Philox &fr) {
+    const uint32_t H = cl.H;
+    const uint32_t n_obs = cl.misc[kNumHap];
+    if (n_obs > 0) {
+        if (!cl.misc[kSparse]) {
+            double norm = 0;
+            for (uint32_t h = 0; h < H; h++) { const double f = fr.gamma(cl.obs[h] + 1.0); cl.freq[h] = f; norm += f; cl.obs[h] = 0; }
+            for (uint32_t h = 0; h < H; h++) cl.freq[h] /= norm;
+        } else {
+            uint32_t plus = 0;
+            for (uint32_t h = 0; h < H; h++) plus += cl.obs[h] > 0;
+            if (cl.misc[kSimplexNobs] != n_obs || cl.misc[kSimplexPlus] != plus) {
+                cl.misc[kSimplexLen] = cl_simplex_vector(cl, n_obs, plus);
+                cl.misc[kSimplexNobs] = n_obs;
+                cl.misc[kSimplexPlus] = plus;
+            }
+            const uint32_t len = cl.misc[kSimplexLen];
+            const double uu = fr.u01();
+            uint32_t ub = 0;
+            while (ub < len && !(uu < cl.simplex[ub])) ub++;  // upper_bound
+            const uint32_t simplex_size = ub + plus;
+            double norm = 0;
+            // observed haplotypes, ascending index; nz[] marks membership of the (growing) plus set
+            for (uint32_t h = 0; h < H; h++) {
+                if (cl.obs[h] > 0) { const double f = fr.gamma(cl.obs[h] + 1.0); cl.freq[h] = f; norm += f; cl.nz[h] = 1; }
+                else cl.nz[h] = 0;
+            }
+            uint32_t n_zero = H - plus;
+            while (plus < simplex_size) {
+                const uint32_t posn = fr.uniform_int(n_zero);
+                uint32_t seen = 0, pick = 0;
+                for (uint32_t h = 0; h < H; h++) if (!cl.nz[h]) { if (seen == posn) { pick = h; break; } seen++; }
+                const double f = fr.gamma(1.0);
+                cl.freq[pick] = f; norm += f; cl.nz[pick] = 1;
+                plus++; n_zero--;
+            }
+            for (uint32_t h = 0; h < H; h++) {
+                if (cl.nz[h]) cl.freq[h] /= norm; else cl.freq[h] = 0;
+                cl.obs[h] = 0;
+            }
+        }
+    }
+    cl.misc[kNumHap] = 0;
+    cl.misc[kNumMissing] = 0;
+}
+
+// VariantClusterGenotyper::getGenotypes & co. (VariantClusterGenotyper.cpp:208-567)
+struct ResultView {
+    const uint64_t *allele_off, *geno_off, *valt_off;
+    uint16_t *gt; uint32_t *gq; float *gpp, *app, *nak, *fak, *mac; uint16_t *saf; uint8_t *ploidy;
+    uint32_t *an, *ac; float *af, *acp; uint8_t *anc; uint16_t *hc;
+};
+
+__device__ void cl_summarise(Cl &cl, const btg_gibbs_opts &o, const uint8_t *ploidy, const ResultView &R) {
+    const uint32_t S = cl.S, H = cl.H;
+    for (uint32_t v = 0; v < cl.nvar; v++) {
+        const uint64_t gv = cl.var0 + v;
+        const uint32_t nA = cl.nalleles(v), nG = nA * (nA + 1) / 2;
+        R.hc[gv] = (uint16_t)H;
+        uint8_t *anc = R.anc + R.valt_off[gv];
+        uint32_t *ac = R.ac + R.valt_off[gv];
+        float *acp = R.acp + R.valt_off[gv], *af = R.af + R.valt_off[gv];
+        for (uint32_t a = 0; a < nA; a++) { anc[a] = 1; ac[a] = 0; acp[a] = 0; }
+        for (uint32_t h = 0; h < H; h++) anc[cl.hapAllele(h, v)] = 0;  // getNonCoveredAlleles (…Genotyper.cpp:221-247)
+        if (cl.u->var_dep[gv]) anc[nA - 1] = 0;
+        uint32_t total_count = 0;
+        for (uint32_t s = 0; s < S; s++) {
+            float *gpp = R.gpp + R.geno_off[gv] + (size_t)s * nG;
+            const uint64_t ab = R.allele_off[gv] + (size_t)s * nA;
+            float *app = R.app + ab, *nak = R.nak + ab, *fak = R.fak + ab, *mac = R.mac + ab;
+            uint16_t *saf = R.saf + ab;
+            const uint8_t pl = ploidy[s];
+            R.ploidy[gv * S + s] = pl;
+            const uint32_t n_geno = pl == 2 ? nG : (pl == 1 ? nA : 0), n_all = pl == 0 ? 0 : nA;
+            for (uint32_t i = 0; i < nG; i++) gpp[i] = 0;
+            for (uint32_t i = 0; i < nA; i++) { app[i] = 0; saf[i] = 0; }
+            uint32_t n_it = 0, best_n = 0, best_a = NONE, best_b = NONE;
+            float best_p = 0;
+            for (uint32_t b = 0; b <= H; b++) {
+                for (uint32_t a = 0; a <= b; a++) {
+                    const uint32_t cnt = cl.tally[(size_t)cl.slot(a, b) * S + s];
+                    if (cnt == 0) continue;
+                    uint32_t ga = NONE, gb = NONE, gi = 0;
+                    if (pl == 2) {
+                        ga = a == H ? nA - 1 : cl.hapAllele(a, v);  // haplotypeToAlleleIndex (…Genotyper.cpp:208-219)
+                        gb = b == H ? nA - 1 : cl.hapAllele(b, v);
+                        if (ga > gb) { const uint32_t t = ga; ga = gb; gb = t; }
+                        gi = gb * (gb + 1) / 2 + ga;
+                        gpp[gi] += cnt;
+                        app[ga] += cnt;
+                        if (ga != gb) app[gb] += cnt;
+                    } else if (pl == 1) {
+                        ga = a == H ? nA - 1 : cl.hapAllele(a, v);
+                        gi = ga;
+                        gpp[gi] += cnt;
+                        app[gi] += cnt;
+                    }
+                    n_it += cnt;
+                    if (pl != 0) {
+                        if (floatCompare(best_p, gpp[gi])) best_n++;
+                        else if (best_p < gpp[gi]) { best_n = 1; best_a = ga; best_b = gb; best_p = gpp[gi]; }
+                    }
+                }
+            }
+            best_p /= n_it;
+            for (uint32_t i = 0; i < n_geno; i++) gpp[i] /= n_it;
+            for (uint32_t i = 0; i < n_all; i++) app[i] /= n_it;
+            const uint32_t ai0 = cl.alleleBase(v, s);
+            for (uint32_t a = 0; a < nA; a++) {
+                const uint32_t ai = ai0 + a;
+                nak[a] = cl.as_n[ai * 3 + 0] ? (float)cl.as_f[(ai * 3 + 0) * 2 + 1] : -1.f;
+                fak[a] = cl.as_n[ai * 3 + 1] ? (float)cl.as_f[(ai * 3 + 1) * 2 + 1] : -1.f;
+                mac[a] = cl.as_n[ai * 3 + 2] ? (float)cl.as_f[(ai * 3 + 2) * 2 + 1] : -1.f;
+            }
+            for (uint32_t a = 0; a < n_all; a++) {
+                if (!floatCompare(app[a], 0)) {
+                    if (floatLess(nak[a], o.min_number_of_kmers)) saf[a] += 1;
+                    if (!floatCompare(nak[a], 0))
+                        if (floatLess(fak[a], o.min_fraction_observed_kmers[s])) saf[a] += 2;
+                }
+            }
+            uint32_t gq;
+            if (floatCompare(best_p, 1)) gq = 99;
+            else if (floatCompare(best_p, 0)) gq = 0;
+            else gq = (uint32_t)(-10 * log10f(1 - best_p));
+            R.gq[gv * S + s] = gq;
+            uint16_t *gt = R.gt + (gv * S + s) * 2;
+            gt[0] = NONE;
+            gt[1] = pl == 2 ? NONE : 0xFFFE;
+            if (pl == 2) {
+                if (best_n == 1 && !floatLess(best_p, o.min_genotype_posterior))
+                    if (saf[best_a] == 0 && saf[best_b] == 0) { gt[0] = (uint16_t)best_a; gt[1] = (uint16_t)best_b; }
+            } else if (pl == 1) {
+                if (best_n == 1 && !floatLess(best_p, o.min_genotype_posterior))
+                    if (saf[best_a] == 0) gt[0] = (uint16_t)best_a;
+            }
+            for (int i = 0; i < 2; i++)  // getGenotypeVariantStats (…Genotyper.cpp:470-526)
+                if (gt[i] < 0xFFFE) { total_count++; if (gt[i] > 0) ac[gt[i]]++; }
+            for (uint32_t a = 0; a < n_all; a++)
+                if (saf[a] == 0) acp[a] = fmaxf(acp[a], app[a]);
+        }
+        R.an[gv] = total_count;
+        for (uint32_t a = 0; a < nA; a++) af[a] = total_count > 0 ? ac[a] / static_cast<float>(total_count) : 0.f;
+    }
+}
+
+// InferenceEngine::estimateGenotypesCallback (InferenceEngine.cpp:278-333): one thread = one group, all chains
+__global__ void __launch_bounds__(64) k_estimate_genotypes(DevUnit du, Tables T, btg_gibbs_opts o, ResultView R) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= du.C) return;
+    Cl cl;
+    cl.bind(du, du.order[i]);
+    const uint64_t gidx = o.group_index_base + cl.g;
+    const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
+    cl_construct(cl, o, gidx, 0);
+    Philox prng, fr;
+    prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, 0);
+    fr.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngFrequency, 0);
+    for (uint32_t chain = 0; chain < o.n_chains; chain++) {
+        cl_reset(cl, o, prng);
+        const uint32_t iters = (uint32_t)o.gibbs_burn_in + o.gibbs_samples;
+        for (uint32_t it = 0; it < iters; it++) {
+            cl_sample_diplotypes(cl, T, ploidy, it >= o.gibbs_burn_in, prng);
+            cl_sample_frequencies(cl, fr);
+        }
+    }
+    cl_summarise(cl, o, ploidy, R);
+}
+
+// ---- estimateNoise: lock-step iterations over the selected single-cluster groups ---------------
+struct NoiseState {
+    uint64_t *hist;        // [S][256] CountAllocation (CountAllocation.cpp:34-57)
+    double *rates;         // [S] current noise rates (device copy owned by the count dist)
+    double *noise_table;   // [S][256]
+    double *mean_rates;    // [S]
+    double *trace;         // rows of (chain, iteration, rates...) or nullptr
+    uint32_t *rng;         // persisted Philox state of CountDistribution::prng (kind 4)
+    uint32_t *trace_row;
+};
+
+__global__ void __launch_bounds__(64) k_noise_init(DevUnit du, btg_gibbs_opts o, const uint32_t *sel, uint32_t n_sel, uint32_t chain) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sel) return;
+    Cl cl;
+    cl.bind(du, sel[i]);
+    const uint64_t gidx = o.group_index_base + cl.g;
+    cl_construct(cl, o, gidx, chain);  // fresh genotypers every chain (InferenceEngine.cpp:60-75,240-251)
+    Philox prng, fr;
+    prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, chain);
+    fr.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngFrequency, chain);
+    cl_reset(cl, o, prng);
+    prng.save(cl.misc + kRng0);
+    fr.save(cl.misc + kRng1);
+}
+
+// sampleGenotypesCallback (InferenceEngine.cpp:77-98): one Gibbs iteration + noise-count histogram
+__global__ void __launch_bounds__(64) k_noise_iteration(DevUnit du, Tables T, btg_gibbs_opts o, const uint32_t *sel, uint32_t n_sel, unsigned long long *hist) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_sel) return;
+    Cl cl;
+    cl.bind(du, sel[i]);
+    const uint64_t gidx = o.group_index_base + cl.g;
+    const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
+    Philox prng, fr;
+    prng.load(cl.misc + kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+    fr.load(cl.misc + kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
+    cl_sample_diplotypes(cl, T, ploidy, false, prng);
+    cl_sample_frequencies(cl, fr);
+    // VariantClusterGenotyper::getNoiseCounts (…Genotyper.cpp:757-779)
+    const uint32_t n_sub = cl.misc[kNSub];
+    for (uint32_t s = 0; s < cl.S; s++) {
+        const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
+        for (uint32_t j = 0; j < n_sub; j++) {
+            const uint32_t k = cl.uniq_sub[j];
+            if ((uint8_t)(cl.diplMult(k, da, db) + cl.ic(k, s)) == 0) atomicAdd(hist + s * 256u + cl.count(k, s), 1ULL);
+        }
+    }
+    // clearGenotyperCache: the Poisson table is about to change
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (uint32_t j = 0; j < cl.S * cl.Dall; j++) cl.ucache[j] = nan;
+    prng.save(cl.misc + kRng0);
+    fr.save(cl.misc + kRng1);
+}
+
+// CountDistribution::sampleNoiseParameters / resetNoiseRates + updateNoiseCache, on the device so that the
+// iteration loop never synchronises with the host.  mode 0: reset from the prior; 1: posterior draw from hist;
+// 2: set to the accumulated mean.  One block; thread 0 draws, then all threads rebuild the Poisson rows.
+__global__ void k_noise_update(NoiseState ns, uint32_t S, float prior_shape, float prior_scale, uint32_t seed, int mode, int accumulate,
+                               double chain_label, double iter_label, double mean_div) {
+    __shared__ double sh_rates[BTG_MAX_SAMPLES];
+    if (threadIdx.x == 0) {
+        Philox rng;
+        rng.load(ns.rng, seed, (uint64_t)-1, 0);
+        for (uint32_t s = 0; s < S; s++) {
+            double r;
+            if (mode == 0) {
+                r = rng.gamma((double)prior_shape) * (double)prior_scale;  // CountDistribution.cpp:163-171,202-213
+            } else if (mode == 1) {
+                unsigned long long n_obs = 0, sum = 0;  // calcCountSuffStats (CountDistribution.cpp:188-200)
+                for (uint32_t i = 0; i < 256; i++) { const unsigned long long c = ns.hist[s * 256 + i]; n_obs += c; sum += i * c; ns.hist[s * 256 + i] = 0; }
+                const float shape_f = prior_shape + (float)sum;                                   // float arithmetic as in the
+                const float scale_f = prior_scale / ((float)n_obs * prior_scale + 1);             // reference (CountDistribution.cpp:182)
+                r = rng.gamma((double)shape_f) * (double)scale_f;
+            } else if (mode == 2) {
+                r = ns.mean_rates[s] / mean_div;
+            } else {
+                r = ns.rates[s];  // mode 3: record the current rates, no draw
+            }
+            ns.rates[s] = r;
+            sh_rates[s] = r;
+            if (accumulate) ns.mean_rates[s] += r;
+        }
+        rng.save(ns.rng);
+        if (ns.trace) {
+            double *row = ns.trace + (size_t)(*ns.trace_row) * (2 + S);
+            row[0] = chain_label; row[1] = iter_label;
+            for (uint32_t s = 0; s < S; s++) row[2 + s] = sh_rates[s];
+            (*ns.trace_row)++;
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < S * 256u; i += blockDim.x) ns.noise_table[i] = noiseCountLogPmf(sh_rates[i >> 8], i & 255u);
+}
+
+__global__ void k_noise_rng_init(uint32_t *rng, uint32_t seed) {
+    Philox r;
+    r.init(seed, (uint64_t)-1, 0, kRngNoise);
+    r.save(rng);
+}
+
+template <class T> T *upload(const T *h, size_t n, bool &ok) {
+    T *d = nullptr;
+    if (cudaMalloc(&d, (n ? n : 1) * sizeof(T)) != cudaSuccess) { ok = false; return nullptr; }
+    if (n && cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
+    return d;
+}
+
+}  // namespace
+
+struct btg_unit {
+    DevUnit du{};
+    std::vector<void *> allocs;
+    std::vector<uint64_t> h_valt_off, h_allele_off, h_geno_off;
+    std::vector<uint32_t> h_nhap, h_group_nvar;
+    std::vector<uint64_t> h_group_cluster_off, h_cl_var_off;
+    std::vector<ClusterLayout> h_layout;
+    uint64_t n_variants = 0, n_alleles_total = 0;
+    uint32_t max_h = 0;
+};
+
+extern "C" {
+
+// ---- count distribution ---------------------------------------------------------------------
+btg_count_dist *btg_count_dist_create(uint32_t S, const double *nb_p, const double *nb_size, float prior_shape, float prior_scale) {
+    if (!ctx().ready) { set_error("btg_init() has not been called"); return nullptr; }
+    if (S == 0 || S > BTG_MAX_SAMPLES || !nb_p || !nb_size) { set_error("bad count distribution arguments"); return nullptr; }
+    for (uint32_t s = 0; s < S; s++)
+        if (!(nb_p[s] > 0 && nb_p[s] < 1 && nb_size[s] > 0)) { set_error("negative binomial parameters out of range for sample %u", s); return nullptr; }
+    auto *cd = new btg_count_dist();
+    cd->S = S;
+    cd->prior_shape = prior_shape;
+    cd->prior_scale = prior_scale;
+    cd->h_p.assign(nb_p, nb_p + S);
+    cd->h_size.assign(nb_size, nb_size + S);
+    bool ok = true;
+    cd->p = upload(nb_p, S, ok);
+    cd->size = upload(nb_size, S, ok);
+    std::vector<double> ones(S, 1.0);
+    cd->rates = upload(ones.data(), S, ok);
+    ok = ok && cudaMalloc(&cd->genomic, (size_t)S * 65536 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&cd->noise, (size_t)S * 256 * sizeof(double)) == cudaSuccess;
+    if (!ok) { set_error("count distribution allocation failed"); btg_count_dist_free(cd); return nullptr; }
+    auto s = ctx().stream;
+    k_genomic_table<<<(S * 65536 + 255) / 256, 256, 0, s>>>(cd->p, cd->size, S, cd->genomic);
+    BTG_LAUNCHED();
+    k_noise_table<<<(S * 256 + 255) / 256, 256, 0, s>>>(cd->rates, S, cd->noise);
+    BTG_LAUNCHED();
+    if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("count table kernels failed: %s", cudaGetErrorString(cudaGetLastError())); btg_count_dist_free(cd); return nullptr; }
+    return cd;
+}
+
+void btg_nb_moments_to_parameters(double mean, double var, uint32_t multiplicity, double *p_out, double *size_out) {
+    const double max_p = 0.99;  // NegativeBinomialDistribution.cpp:38,68-79
+    if (max_p < (mean / var)) var = mean / max_p;
+    if (p_out) *p_out = mean / var;
+    if (size_out) *size_out = std::pow(mean, 2) / (var - mean) / multiplicity;  // CountDistribution.cpp:115-116
+}
+
+int btg_count_dist_set_noise_rates(btg_count_dist *cd, const double *rates) {
+    BTG_REQUIRE_INIT();
+    if (!cd || !rates) { set_error("null argument"); return BTG_EINVAL; }
+    auto s = ctx().stream;
+    BTG_CUDA(cudaMemcpyAsync(cd->rates, rates, cd->S * sizeof(double), cudaMemcpyHostToDevice, s));
+    k_noise_table<<<(cd->S * 256 + 255) / 256, 256, 0, s>>>(cd->rates, cd->S, cd->noise);
+    BTG_LAUNCHED();
+    BTG_CUDA(cudaStreamSynchronize(s));
+    return BTG_OK;
+}
+
+int btg_count_dist_get_noise_rates(const btg_count_dist *cd, double *out) {
+    BTG_REQUIRE_INIT();
+    if (!cd || !out) { set_error("null argument"); return BTG_EINVAL; }
+    BTG_CUDA(cudaStreamSynchronize(ctx().stream));
+    BTG_CUDA(cudaMemcpy(out, cd->rates, cd->S * sizeof(double), cudaMemcpyDeviceToHost));
+    return BTG_OK;
+}
+
+int btg_count_dist_tables(const btg_count_dist *cd, double *genomic_out, double *noise_out) {
+    BTG_REQUIRE_INIT();
+    if (!cd) { set_error("null argument"); return BTG_EINVAL; }
+    BTG_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (genomic_out) BTG_CUDA(cudaMemcpy(genomic_out, cd->genomic, (size_t)cd->S * 65536 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (noise_out) BTG_CUDA(cudaMemcpy(noise_out, cd->noise, (size_t)cd->S * 256 * sizeof(double), cudaMemcpyDeviceToHost));
+    return BTG_OK;
+}
+
+void btg_count_dist_free(btg_count_dist *cd) {
+    if (!cd) return;
+    cudaFree(cd->p); cudaFree(cd->size); cudaFree(cd->rates); cudaFree(cd->genomic); cudaFree(cd->noise);
+    delete cd;
+}
+
+// ---- unit -------------------------------------------------------------------------------------
+btg_unit *btg_unit_upload(const btg_unit_desc *d) {
+    if (!ctx().ready) { set_error("btg_init() has not been called"); return nullptr; }
+    if (!d || d->n_samples == 0 || d->n_samples > BTG_MAX_SAMPLES) { set_error("bad unit descriptor"); return nullptr; }
+    const uint32_t S = d->n_samples, G = d->n_groups, C = d->n_clusters;
+    for (uint32_t g = 0; g < G; g++)
+        if (d->group_cluster_off[g + 1] - d->group_cluster_off[g] != 1) {
+            set_error("group %u has %llu clusters: nested variant-cluster groups are not supported by this build", g,
+                      (unsigned long long)(d->group_cluster_off[g + 1] - d->group_cluster_off[g]));
+            return nullptr;
+        }
+    auto *u = new btg_unit();
+    bool ok = true;
+    auto keep = [&](auto *p) { u->allocs.push_back((void *)p); return p; };
+    const uint64_t rows = d->cl_kmer_off[C], nvar = d->cl_var_off[C], n_vh = d->kmer_vh_off[rows];
+    DevUnit &du = u->du;
+    du.S = S; du.G = G; du.C = C;
+    du.sample_gender = keep(upload(d->sample_gender, S, ok));
+    du.group_ploidy = keep(upload(d->group_ploidy, (size_t)G * S, ok));
+    du.group_cluster_off = keep(upload(d->group_cluster_off, G + 1, ok));
+    du.cluster_idx = keep(upload(d->cluster_idx, C, ok));
+    du.cl_nhap = keep(upload(d->cl_nhap, C, ok));
+    du.cl_kmer_off = keep(upload(d->cl_kmer_off, C + 1, ok));
+    du.cl_var_off = keep(upload(d->cl_var_off, C + 1, ok));
+    du.cl_mult_off = keep(upload(d->cl_mult_off, C + 1, ok));
+    du.mult = keep(upload(d->mult, d->cl_mult_off[C], ok));
+    du.k_has_counts = keep(upload(d->k_has_counts, rows, ok));
+    du.k_counts = keep(upload(d->k_counts, rows * S, ok));
+    du.k_ic = keep(upload(d->k_ic, rows * 2, ok));
+    du.cl_uniq_off = keep(upload(d->cl_uniq_off, C + 1, ok));
+    du.uniq_idx = keep(upload(d->uniq_idx, d->cl_uniq_off[C], ok));
+    du.kmer_vh_off = keep(upload(d->kmer_vh_off, rows + 1, ok));
+    du.vh_var = keep(upload(d->vh_var, n_vh, ok));
+    du.vh_bits_off = keep(upload(d->vh_bits_off, n_vh + 1, ok));
+    du.vh_bits = keep(upload(d->vh_bits, d->vh_bits_off[n_vh], ok));
+    du.cl_hapvar_off = keep(upload(d->cl_hapvar_off, C + 1, ok));
+    du.hap_alleles = keep(upload(d->hap_alleles, d->cl_hapvar_off[C], ok));
+    du.var_nalleles = keep(upload(d->var_nalleles, nvar, ok));
+    du.var_dep = keep(upload(d->var_dep, nvar, ok));
+    // result offsets
+    u->n_variants = nvar;
+    u->h_valt_off.assign(nvar + 1, 0);
+    u->h_allele_off.assign(nvar + 1, 0);
+    u->h_geno_off.assign(nvar + 1, 0);
+    for (uint64_t v = 0; v < nvar; v++) {
+        const uint64_t nA = d->var_nalleles[v];
+        u->h_valt_off[v + 1] = u->h_valt_off[v] + nA;
+        u->h_allele_off[v + 1] = u->h_allele_off[v] + S * nA;
+        u->h_geno_off[v + 1] = u->h_geno_off[v] + S * nA * (nA + 1) / 2;
+    }
+    u->n_alleles_total = u->h_valt_off[nvar];
+    du.valt_off = keep(upload(u->h_valt_off.data(), nvar + 1, ok));
+    // arena layout + cost order
+    u->h_layout.resize(C);
+    u->h_nhap.assign(d->cl_nhap, d->cl_nhap + C);
+    u->h_group_cluster_off.assign(d->group_cluster_off, d->group_cluster_off + G + 1);
+    u->h_cl_var_off.assign(d->cl_var_off, d->cl_var_off + C + 1);
+    uint64_t f64_total = 0, u32_total = 0, u8_total = 0;
+    std::vector<uint64_t> cost(C);
+    for (uint32_t g = 0; g < G; g++) {
+        for (uint64_t c = d->group_cluster_off[g]; c < d->group_cluster_off[g + 1]; c++) {
+            const uint32_t H = d->cl_nhap[c];
+            const uint32_t K = (uint32_t)(d->cl_kmer_off[c + 1] - d->cl_kmer_off[c]);
+            const uint32_t nv = (uint32_t)(d->cl_var_off[c + 1] - d->cl_var_off[c]);
+            const uint32_t nu = (uint32_t)(d->cl_uniq_off[c + 1] - d->cl_uniq_off[c]);
+            const uint32_t nal = (uint32_t)(u->h_valt_off[d->cl_var_off[c + 1]] - u->h_valt_off[d->cl_var_off[c]]);
+            if (H == 0 || H >= 0xFFFE) { set_error("cluster %llu: invalid number of haplotypes %u", (unsigned long long)c, H); ok = false; break; }
+            ClusterLayout &L = u->h_layout[c];
+            L.group = g;
+            L.n_alleles = nal;
+            L.Dall = (H + 1) * (H + 2) / 2;
+            L.f64_off = f64_total; L.u32_off = u32_total; L.u8_off = u8_total;
+            const ArenaSizes a = arena_sizes(S, H, K, nv, nu, nal, L.Dall);
+            f64_total += a.f64; u32_total += a.u32; u8_total += a.u8;
+            cost[c] = (uint64_t)S * ((uint64_t)H * (H + 1) / 2) * 8 + nu + (uint64_t)H * K / 16;
+            u->max_h = std::max(u->max_h, H);
+        }
+    }
+    std::vector<uint32_t> order(C);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
+    du.layout = keep(upload(u->h_layout.data(), C, ok));
+    du.order = keep(upload(order.data(), C, ok));
+    double *f64_pool = nullptr; uint32_t *u32_pool = nullptr; uint8_t *u8_pool = nullptr; double *lg = nullptr;
+    ok = ok && cudaMalloc(&f64_pool, (f64_total + 1) * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMalloc(&u32_pool, (u32_total + 1) * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMalloc(&u8_pool, u8_total + 8) == cudaSuccess;
+    const uint32_t n_lg = u->max_h + 2 * S + 4;
+    ok = ok && cudaMalloc(&lg, n_lg * sizeof(double)) == cudaSuccess;
+    keep(f64_pool); keep(u32_pool); keep(u8_pool); keep(lg);
+    du.f64_pool = f64_pool; du.u32_pool = u32_pool; du.u8_pool = u8_pool; du.lgamma_int = lg;
+    if (ok) {
+        k_lgamma_int<<<(n_lg + 127) / 128, 128, 0, ctx().stream>>>(lg, n_lg);
+        BTG_LAUNCHED();
+        ok = cudaStreamSynchronize(ctx().stream) == cudaSuccess;
+    }
+    if (!ok) {
+        if (!*btg_last_error()) set_error("unit upload failed (%s)", cudaGetErrorString(cudaGetLastError()));
+        btg_unit_free(u);
+        return nullptr;
+    }
+    return u;
+}
+
+void btg_unit_free(btg_unit *u) {
+    if (!u) return;
+    for (void *p : u->allocs) cudaFree(p);
+    delete u;
+}
+
+}  // extern "C"
+
+namespace {
+struct DevResult {
+    ResultView R{};
+    std::vector<std::pair<void *, std::pair<void *, size_t>>> copies;  // device -> (host, bytes)
+    std::vector<void *> allocs;
+    bool ok = true;
+    template <class T> T *out(T *host, size_t n) {
+        T *d = nullptr;
+        if (cudaMalloc(&d, (n ? n : 1) * sizeof(T)) != cudaSuccess) { ok = false; return nullptr; }
+        allocs.push_back(d);
+        copies.push_back({d, {host, n * sizeof(T)}});
+        return d;
+    }
+    ~DevResult() { for (void *p : allocs) cudaFree(p); }
+};
+}  // namespace
+
+extern "C" {
+
+int btg_estimate_genotypes(btg_unit *u, const btg_count_dist *cd, const btg_gibbs_opts *opts, btg_genotype_result *out) {
+    BTG_REQUIRE_INIT();
+    if (!u || !cd || !opts || !out) { set_error("null argument"); return BTG_EINVAL; }
+    if (cd->S != u->du.S) { set_error("count distribution has %u samples, unit has %u", cd->S, u->du.S); return BTG_EINVAL; }
+    if (out->n_variants != u->n_variants) { set_error("result sized for %llu variants, unit has %llu", (unsigned long long)out->n_variants, (unsigned long long)u->n_variants); return BTG_EINVAL; }
+    const uint32_t S = u->du.S;
+    const uint64_t nv = u->n_variants, nall = u->h_allele_off[nv], ngen = u->h_geno_off[nv], nalt = u->h_valt_off[nv];
+    DevResult dr;
+    bool ok = true;
+    dr.R.allele_off = upload(u->h_allele_off.data(), nv + 1, ok); dr.allocs.push_back((void *)dr.R.allele_off);
+    dr.R.geno_off = upload(u->h_geno_off.data(), nv + 1, ok); dr.allocs.push_back((void *)dr.R.geno_off);
+    dr.R.valt_off = u->du.valt_off;
+    dr.R.gt = dr.out(out->gt, nv * S * 2); dr.R.gq = dr.out(out->gq, nv * S);
+    dr.R.gpp = dr.out(out->gpp, ngen); dr.R.app = dr.out(out->app, nall);
+    dr.R.nak = dr.out(out->nak, nall); dr.R.fak = dr.out(out->fak, nall); dr.R.mac = dr.out(out->mac, nall);
+    dr.R.saf = dr.out(out->saf, nall); dr.R.ploidy = dr.out(out->ploidy, nv * S);
+    dr.R.an = dr.out(out->an, nv); dr.R.ac = dr.out(out->ac, nalt); dr.R.af = dr.out(out->af, nalt);
+    dr.R.acp = dr.out(out->acp, nalt); dr.R.anc = dr.out(out->anc, nalt); dr.R.hc = dr.out(out->hc, nv);
+    if (!ok || !dr.ok) { set_error("result allocation failed"); return BTG_ENOMEM; }
+    auto s = ctx().stream;
+    Tables T{cd->genomic, cd->noise};
+    if (u->du.C) {
+        k_estimate_genotypes<<<(u->du.C + 63) / 64, 64, 0, s>>>(u->du, T, *opts, dr.R);
+        BTG_LAUNCHED();
+        BTG_CUDA(cudaGetLastError());
+    }
+    for (auto &cp : dr.copies) BTG_CUDA(cudaMemcpyAsync(cp.second.first, cp.first, cp.second.second, cudaMemcpyDeviceToHost, s));
+    BTG_CUDA(cudaStreamSynchronize(s));
+    return BTG_OK;
+}
+
+int btg_unit_cluster_tally(const btg_unit *u, uint32_t cluster, uint32_t *tally_out, uint64_t n) {
+    BTG_REQUIRE_INIT();
+    if (!u || cluster >= u->du.C || !tally_out) { set_error("bad argument"); return BTG_EINVAL; }
+    const ClusterLayout &L = u->h_layout[cluster];
+    const uint32_t H = u->h_nhap[cluster], S = u->du.S;
+    const uint64_t need = (uint64_t)L.Dall * S;
+    if (n < need) { set_error("tally buffer too small"); return BTG_EINVAL; }
+    // tally sits after obs[H], uniq[2*n_uniq], cnt[H*nvar] in the u32 slice (see Cl::bind)
+    uint64_t n_uniq = 0, nvar = 0;
+    {
+        std::vector<uint64_t> tmp(2);
+        BTG_CUDA(cudaMemcpy(tmp.data(), u->du.cl_uniq_off + cluster, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        n_uniq = tmp[1] - tmp[0];
+        nvar = u->h_cl_var_off[cluster + 1] - u->h_cl_var_off[cluster];
+    }
+    const uint64_t off = L.u32_off + H + 2 * n_uniq + (uint64_t)H * nvar;
+    BTG_CUDA(cudaStreamSynchronize(ctx().stream));
+    BTG_CUDA(cudaMemcpy(tally_out, u->du.u32_pool + off, need * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return BTG_OK;
+}
+
+int btg_estimate_noise(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, double *trace_out) {
+    BTG_REQUIRE_INIT();
+    if (!u || !cd || !opts) { set_error("null argument"); return BTG_EINVAL; }
+    if (cd->S != u->du.S) { set_error("count distribution / unit sample mismatch"); return BTG_EINVAL; }
+    const uint32_t S = u->du.S, G = u->du.G;
+    const uint32_t iters = (uint32_t)opts->gibbs_burn_in + opts->gibbs_samples;
+    const size_t trace_rows = (size_t)opts->n_chains * (iters + 1) + 1;
+    auto s = ctx().stream;
+    NoiseState ns{};
+    unsigned long long *hist = nullptr;
+    uint32_t *d_sel = nullptr;
+    std::vector<void *> tmp;
+    auto dalloc = [&](size_t bytes) { void *p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 8) != cudaSuccess) return (void *)nullptr; tmp.push_back(p); cudaMemsetAsync(p, 0, bytes ? bytes : 8, s); return p; };
+    hist = (unsigned long long *)dalloc((size_t)S * 256 * 8);
+    ns.hist = (uint64_t *)hist;
+    ns.rates = cd->rates;
+    ns.noise_table = cd->noise;
+    ns.mean_rates = (double *)dalloc(S * 8);
+    ns.trace = trace_out ? (double *)dalloc(trace_rows * (2 + S) * 8) : nullptr;
+    ns.rng = (uint32_t *)dalloc(8 * 4);
+    ns.trace_row = (uint32_t *)dalloc(4);
+    d_sel = (uint32_t *)dalloc((size_t)G * 4);
+    int rc = BTG_OK;
+    if (!hist || !ns.mean_rates || !ns.rng || !ns.trace_row || !d_sel || (trace_out && !ns.trace)) { set_error("noise estimation allocation failed"); rc = BTG_ENOMEM; }
+    if (rc == BTG_OK) {
+        // the engine's own stream (InferenceEngine.cpp:174) lives on the host: Fisher-Yates with the same Philox recipe
+        struct HostPhilox {
+            uint32_t key[2], ctr[4], buf[4]; int pos;
+            void init(uint32_t seed) { key[0] = seed; key[1] = 0; ctr[0] = ctr[1] = ctr[2] = 0; ctr[3] = kRngEngine; pos = 4; }
+            uint32_t next() {
+                if (pos == 4) {
+                    uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]}, k[2] = {key[0], key[1]};
+                    for (int r = 0; r < 10; r++) {
+                        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+                        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k[0], n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k[1], n3 = (uint32_t)p0;
+                        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+                        k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+                    }
+                    for (int i = 0; i < 4; i++) buf[i] = c[i];
+                    if (++ctr[0] == 0) ++ctr[1];
+                    pos = 0;
+                }
+                return buf[pos++];
+            }
+            uint32_t uniform_int(uint32_t n) { return (uint32_t)(((uint64_t)next() * n) >> 32); }
+        } engine;
+        engine.init(opts->random_seed);
+        std::vector<uint32_t> noise_groups;  // single-cluster groups (InferenceEngine.cpp:144-151)
+        for (uint32_t g = 0; g < G; g++)
+            if (u->h_group_cluster_off[g + 1] - u->h_group_cluster_off[g] == 1) noise_groups.push_back(g);
+        auto group_variants = [&](uint32_t g) {
+            uint64_t n = 0;
+            for (uint64_t c = u->h_group_cluster_off[g]; c < u->h_group_cluster_off[g + 1]; c++) n += u->h_cl_var_off[c + 1] - u->h_cl_var_off[c];
+            return (uint32_t)n;
+        };
+        Tables T{cd->genomic, cd->noise};
+        k_noise_rng_init<<<1, 1, 0, s>>>(ns.rng, opts->random_seed);
+        BTG_LAUNCHED();
+        NoiseState ns_quiet = ns;  // same state, no trace row
+        ns_quiet.trace = nullptr;
+        // CountDistribution ctor draws the initial rates (CountDistribution.cpp:62)
+        k_noise_update<<<1, 256, 0, s>>>(ns_quiet, S, cd->prior_shape, cd->prior_scale, opts->random_seed, 0, 0, 0, 0, 1);
+        BTG_LAUNCHED();
+        const uint32_t noise_variants_batch_size = 100000;  // InferenceEngine.cpp:50
+        std::vector<uint32_t> sel;
+        for (uint32_t chain = 0; chain < opts->n_chains && rc == BTG_OK; chain++) {
+            for (size_t i = noise_groups.size(); i > 1; i--) std::swap(noise_groups[i - 1], noise_groups[engine.uniform_int((uint32_t)i)]);
+            uint32_t end = 0, nvv = 0;
+            while (nvv < noise_variants_batch_size && end < noise_groups.size()) { nvv += group_variants(noise_groups[end]); end++; }
+            std::sort(noise_groups.begin(), noise_groups.begin() + end);
+            sel.clear();
+            for (uint32_t i = 0; i < end; i++) sel.push_back((uint32_t)u->h_group_cluster_off[noise_groups[i]]);
+            if (cudaMemcpyAsync(d_sel, sel.data(), sel.size() * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BTG_ECUDA; break; }
+            cudaStreamSynchronize(s);  // sel is reused by the host next chain
+            const uint32_t n_sel = (uint32_t)sel.size();
+            const uint32_t grid = (n_sel + 63) / 64;
+            if (n_sel) { k_noise_init<<<grid, 64, 0, s>>>(u->du, *opts, d_sel, n_sel, chain + 1); BTG_LAUNCHED(); }
+            // trace row "chain, 0": the rates the chain starts from (mode 3 = record, no draw)
+            if (ns.trace) {
+                k_noise_update<<<1, 256, 0, s>>>(ns, S, cd->prior_shape, cd->prior_scale, opts->random_seed, 3, 0, chain + 1, 0, 1);
+                BTG_LAUNCHED();
+            }
+            for (uint32_t it = 1; it <= iters; it++) {
+                if (n_sel) { k_noise_iteration<<<grid, 64, 0, s>>>(u->du, T, *opts, d_sel, n_sel, hist); BTG_LAUNCHED(); }
+                k_noise_update<<<1, 256, 0, s>>>(ns, S, cd->prior_shape, cd->prior_scale, opts->random_seed, 1, opts->gibbs_burn_in < it, chain + 1, it, 1);
+                BTG_LAUNCHED();
+            }
+            // resetNoiseRates at the end of the chain (InferenceEngine.cpp:253); not a trace row
+            k_noise_update<<<1, 256, 0, s>>>(ns_quiet, S, cd->prior_shape, cd->prior_scale, opts->random_seed, 0, 0, 0, 0, 1);
+            BTG_LAUNCHED();
+            if (cudaGetLastError() != cudaSuccess) rc = BTG_ECUDA;
+        }
+        if (rc == BTG_OK) {
+            // mean of the post-burn-in rates -> setNoiseRates (InferenceEngine.cpp:259-264); final trace row "0 0"
+            k_noise_update<<<1, 256, 0, s>>>(ns, S, cd->prior_shape, cd->prior_scale, opts->random_seed, 2, 0, 0, 0, (double)opts->gibbs_samples * opts->n_chains);
+            BTG_LAUNCHED();
+            if (trace_out) cudaMemcpyAsync(trace_out, ns.trace, trace_rows * (2 + S) * 8, cudaMemcpyDeviceToHost, s);
+            cudaError_t e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) { set_error("noise estimation failed: %s", cudaGetErrorString(e)); rc = BTG_ECUDA; }
+        } else {
+            set_error("noise estimation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    cudaStreamSynchronize(s);
+    for (void *p : tmp) cudaFree(p);
+    return rc;
+}
+
+}  // extern "C"

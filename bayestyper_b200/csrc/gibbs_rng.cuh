@@ -1,0 +1,99 @@
+// gibbs_rng.cuh — counter-based random streams of the Gibbs path (device side).
+//
+// The reference draws from std::mt19937 + libstdc++ distributions (one engine per
+// VariantClusterGenotyper / FrequencyDistribution / SparsityEstimator / CountDistribution,
+// SURVEY.md appendix C).  A 2.5 KB Mersenne state per cluster does not belong in registers;
+// each of those engines becomes an independent Philox4x32-10 stream addressed by
+//   key     = (random_seed, uint32(group_index + 1))
+//   counter = (n_lo, n_hi, cluster_idx_in_group, kind | chain << 8)
+// which keeps the reference's determinism contract (results independent of how groups are
+// scheduled or sharded).  The exact draw recipes are part of the parity contract with
+// oracle/gibbs_oracle.cpp and are documented in DESIGN.md §RNG.
+#pragma once
+#include <cstdint>
+
+namespace btg {
+
+enum RngKind : uint32_t { kRngGenotyper = 0, kRngSparsity = 1, kRngFrequency = 2, kRngBranch = 3, kRngNoise = 4, kRngEngine = 5 };
+
+struct Philox {
+    uint32_t key0, key1;
+    uint32_t c0, c1, c2, c3;  // counter
+    uint32_t b0, b1, b2, b3;  // current block
+    uint32_t pos;             // next word of the block (4 = exhausted)
+
+    __device__ __forceinline__ void init(uint32_t seed, uint64_t group_index, uint32_t cluster_idx, uint32_t kind, uint32_t chain = 0) {
+        key0 = seed;
+        key1 = (uint32_t)(group_index + 1);
+        c0 = c1 = 0;
+        c2 = cluster_idx;
+        c3 = kind | (chain << 8);
+        pos = 4;
+        b0 = b1 = b2 = b3 = 0;
+    }
+    __device__ __forceinline__ void refill() {
+        uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, k0 = key0, k1 = key1;
+#pragma unroll
+        for (int r = 0; r < 10; r++) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+            const uint32_t n0 = hi1 ^ x1 ^ k0, n2 = hi0 ^ x3 ^ k1;
+            x0 = n0; x1 = lo1; x2 = n2; x3 = lo0;
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        b0 = x0; b1 = x1; b2 = x2; b3 = x3;
+        if (++c0 == 0) ++c1;
+        pos = 0;
+    }
+    __device__ __forceinline__ uint32_t next() {
+        if (pos == 4) refill();
+        const uint32_t r = pos == 0 ? b0 : (pos == 1 ? b1 : (pos == 2 ? b2 : b3));
+        pos++;
+        return r;
+    }
+    // ((hi:lo >> 11) + 0.5) * 2^-53, in (0,1)
+    __device__ __forceinline__ double u01() {
+        const uint64_t hi = next(), lo = next();
+        const uint64_t x = (hi << 32) | lo;
+        return ((double)(x >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    }
+    __device__ __forceinline__ uint32_t uniform_int(uint32_t n) { return __umulhi(next(), n); }
+    __device__ __forceinline__ double normal() {
+        const double u1 = u01(), u2 = u01();
+        return sqrt(-2.0 * log(u1)) * cos(6.283185307179586476925286766559 * u2);
+    }
+    // Marsaglia-Tsang, scale 1
+    __device__ double gamma(double a) {
+        double boost = 1.0;
+        if (a < 1.0) {
+            // gamma(a) = gamma(a+1) * U^(1/a); the gamma(a+1) draw comes first
+            const double g = gamma_ge1(a + 1.0);
+            return g * pow(u01(), 1.0 / a);
+        }
+        return boost * gamma_ge1(a);
+    }
+    __device__ double gamma_ge1(double a) {
+        const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+        for (;;) {
+            const double x = normal();
+            double v = 1.0 + c * x;
+            if (v <= 0.0) continue;
+            v = v * v * v;
+            const double u = u01();
+            const double x2 = x * x;
+            if (u < 1.0 - 0.0331 * x2 * x2) return d * v;
+            if (log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) return d * v;
+        }
+    }
+    // persist / restore (noise modes run one iteration per launch)
+    __device__ __forceinline__ void save(uint32_t *p) const {
+        p[0] = c0; p[1] = c1; p[2] = b0; p[3] = b1; p[4] = b2; p[5] = b3; p[6] = pos; p[7] = c3;
+    }
+    __device__ __forceinline__ void load(const uint32_t *p, uint32_t seed, uint64_t group_index, uint32_t cluster_idx) {
+        key0 = seed; key1 = (uint32_t)(group_index + 1); c2 = cluster_idx;
+        c0 = p[0]; c1 = p[1]; b0 = p[2]; b1 = p[3]; b2 = p[4]; b3 = p[5]; pos = p[6]; c3 = p[7];
+    }
+};
+
+}  // namespace btg

@@ -1,0 +1,87 @@
+"""Host-side mirror of the reference's stage objects over the C ABI: CountDistribution and
+InferenceEngine (include/bayesTyper/CountDistribution.hpp, InferenceEngine.hpp).  Thin: every
+method is one libbtgpu call; there is no CPU implementation behind it."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .unit import Unit, GibbsOpts
+
+
+class CountDistribution:
+    """CountDistribution(samples, options) + setGenomicCountDistributions (CountDistribution.cpp:51-141)."""
+
+    def __init__(self, nb_p, nb_size, noise_rate_prior=(1.0, 0.01)):
+        self.lib = capi.load()
+        self.S = len(nb_p)
+        p = np.ascontiguousarray(nb_p, np.float64)
+        sz = np.ascontiguousarray(nb_size, np.float64)
+        self.h = capi.check(self.lib.btg_count_dist_create(self.S, capi.ptr(p), capi.ptr(sz), noise_rate_prior[0], noise_rate_prior[1]), self.lib)
+
+    def set_noise_rates(self, rates):
+        r = np.ascontiguousarray(rates, np.float64)
+        assert len(r) == self.S
+        capi.check(self.lib.btg_count_dist_set_noise_rates(self.h, capi.ptr(r)), self.lib)
+
+    def noise_rates(self):
+        out = np.zeros(self.S)
+        capi.check(self.lib.btg_count_dist_get_noise_rates(self.h, capi.ptr(out)), self.lib)
+        return out
+
+    def tables(self):
+        g = np.zeros((self.S, 256, 256)); n = np.zeros((self.S, 256))
+        capi.check(self.lib.btg_count_dist_tables(self.h, capi.ptr(g), capi.ptr(n)), self.lib)
+        return g, n
+
+    def close(self):
+        if self.h:
+            self.lib.btg_count_dist_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class InferenceEngine:
+    """InferenceEngine over one uploaded unit (InferenceEngine.hpp:56-98)."""
+
+    def __init__(self, unit: Unit):
+        self.lib = capi.load()
+        self.unit = unit
+        self._desc = unit.desc()
+        self.h = capi.check(self.lib.btg_unit_upload(C.addressof(self._desc)), self.lib)
+
+    def estimate_genotypes(self, cd: CountDistribution, opts: GibbsOpts) -> dict:
+        res, arrays = self.unit.alloc_result()
+        capi.check(self.lib.btg_estimate_genotypes(self.h, cd.h, C.addressof(opts), C.addressof(res)), self.lib)
+        return arrays
+
+    def estimate_noise(self, cd: CountDistribution, opts: GibbsOpts, want_trace: bool = True):
+        rows = opts.n_chains * (opts.gibbs_burn_in + opts.gibbs_samples + 1) + 1
+        trace = np.zeros((rows, 2 + self.unit.S)) if want_trace else None
+        capi.check(self.lib.btg_estimate_noise(self.h, cd.h, C.addressof(opts), capi.ptr(trace) if want_trace else None), self.lib)
+        return trace
+
+    def cluster_tally(self, cluster: int) -> np.ndarray:
+        H = int(self.unit.a["cl_nhap"][cluster])
+        n = (H + 1) * (H + 2) // 2
+        out = np.zeros((n, self.unit.S), np.uint32)
+        capi.check(self.lib.btg_unit_cluster_tally(self.h, cluster, capi.ptr(out), out.size), self.lib)
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.btg_unit_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -215,20 +215,22 @@ def config_b(n_variants: int = 300_000, length: int = 50_800_000, n_prefix: int 
     return Workload("B", "chr22", ref, var, g, ["F"])
 
 
-def small_mixed(n_variants: int, length: int, n_samples: int, seed: int, frac_indel: float = 0.15) -> Workload:
+def small_mixed(n_variants: int, length: int, n_samples: int, seed: int, frac_indel: float = 0.15, chrom: str = "chr1") -> Workload:
     ref = random_reference(length, seed)
     var = make_variants(ref, n_variants, seed + 1, frac_indel / 2, frac_indel / 2, max_indel=20)
     rng = np.random.default_rng(seed + 5)
     af = rng.beta(0.5, 0.8, len(var))
     g = make_genotypes(len(var), n_samples, seed + 2, allele_freq=af)
     genders = ["F" if i % 2 == 0 else "M" for i in range(n_samples)]
-    return Workload("mixed", "chr1", ref, var, g, genders)
+    return Workload("mixed", chrom, ref, var, g, genders)
 
 
 def sample_spectra(w: Workload, seed: int = 4, n_errors: int = 0):
     out = []
     for s in range(w.genotypes.shape[0]):
-        haps = [apply_variants(w.reference, w.variants, w.genotypes[s, :, h]) for h in range(2)]
+        # males carry one copy of chrX (ChromosomePloidy.cpp:60-75 genotypes them haploid there)
+        n_hap = 1 if (w.genders[s] == "M" and w.chrom.lower() in ("x", "chrx")) else 2
+        haps = [apply_variants(w.reference, w.variants, w.genotypes[s, :, h]) for h in range(n_hap)]
         out.append(sample_kmer_counts(haps, seed + 17 * s, w.depth_mean, w.depth_var, n_errors))
     return out
 

@@ -1,0 +1,176 @@
+"""Host-side mirror of the C-ABI structs of include/btgpu.h (btg_unit_desc,
+btg_gibbs_opts, btg_genotype_result) as ctypes Structures backed by numpy arrays."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+MAX_SAMPLES = 30
+_P = C.c_void_p
+
+_DESC_FIELDS = [
+    ("sample_gender", np.uint8), ("group_ploidy", np.uint8), ("group_cluster_off", np.uint64),
+    ("group_src_off", np.uint64), ("group_src", np.uint32), ("group_edge_off", np.uint64),
+    ("group_edge_src", np.uint32), ("group_edge_dst", np.uint32), ("cluster_idx", np.uint32),
+    ("cl_nhap", np.uint32), ("cl_kmer_off", np.uint64), ("cl_var_off", np.uint64), ("cl_mult_off", np.uint64),
+    ("mult", np.uint8), ("k_has_counts", np.uint8), ("k_counts", np.uint8), ("k_ic", np.uint8), ("k_shared", np.uint32),
+    ("cl_uniq_off", np.uint64), ("uniq_idx", np.uint32), ("cl_multi_off", np.uint64), ("multi_idx", np.uint32),
+    ("kmer_vh_off", np.uint64), ("vh_var", np.uint16), ("vh_bits_off", np.uint64), ("vh_bits", np.uint8),
+    ("cl_hapvar_off", np.uint64), ("hap_alleles", np.uint16), ("var_nalleles", np.uint16), ("var_dep", np.uint8),
+    ("hap_nested_off", np.uint64), ("hap_nested", np.uint32), ("cl_dep_off", np.uint64), ("dep_cluster", np.uint32),
+    ("dep_var_off", np.uint64), ("dep_var", np.uint16),
+]
+
+
+class UnitDesc(C.Structure):
+    _fields_ = [("n_samples", C.c_uint32), ("n_groups", C.c_uint32), ("n_clusters", C.c_uint32)] + [(n, _P) for n, _ in _DESC_FIELDS]
+
+
+class GibbsOpts(C.Structure):
+    _fields_ = [
+        ("random_seed", C.c_uint32), ("gibbs_burn_in", C.c_uint16), ("gibbs_samples", C.c_uint16),
+        ("n_chains", C.c_uint16), ("first_group_index", C.c_uint16), ("kmer_subsampling_rate", C.c_float),
+        ("max_haplotype_variant_kmers", C.c_uint32), ("min_genotype_posterior", C.c_float),
+        ("min_number_of_kmers", C.c_float), ("min_fraction_observed_kmers", C.c_float * MAX_SAMPLES),
+        ("group_index_base", C.c_uint64),
+    ]
+
+
+_RES_FIELDS = [
+    ("allele_off", np.uint64), ("geno_off", np.uint64), ("gt", np.uint16), ("gq", np.uint32), ("gpp", np.float32),
+    ("app", np.float32), ("nak", np.float32), ("fak", np.float32), ("mac", np.float32), ("saf", np.uint16),
+    ("ploidy", np.uint8), ("an", np.uint32), ("valt_off", np.uint64), ("ac", np.uint32), ("af", np.float32),
+    ("acp", np.float32), ("anc", np.uint8), ("hc", np.uint16),
+]
+
+
+class GenotypeResult(C.Structure):
+    _fields_ = [("n_variants", C.c_uint64)] + [(n, _P) for n, _ in _RES_FIELDS]
+
+
+def default_opts(seed: int = 20190401, burn: int = 100, samples: int = 250, chains: int = 20, rate: float = 0.1,
+                 max_hv: int = 500, min_gpp: float = 0.99, min_kmers: float = 1.0, min_frac=None, group_base: int = 0) -> GibbsOpts:
+    o = GibbsOpts()
+    o.random_seed, o.gibbs_burn_in, o.gibbs_samples, o.n_chains = seed, burn, samples, chains
+    o.kmer_subsampling_rate, o.max_haplotype_variant_kmers = rate, max_hv
+    o.min_genotype_posterior, o.min_number_of_kmers = min_gpp, min_kmers
+    for i in range(MAX_SAMPLES):
+        o.min_fraction_observed_kmers[i] = 0.0 if min_frac is None or i >= len(min_frac) else float(min_frac[i])
+    o.group_index_base = group_base
+    return o
+
+
+def min_fraction_observed(nb_p, nb_size, beta: float = 0.275):
+    """Filters ctor (src/bayesTyper/Filters.cpp:42-53): 1 - exp(-0.275 * NB mean) in float."""
+    mean = np.asarray(nb_size, np.float64) * (1 - np.asarray(nb_p, np.float64)) / np.asarray(nb_p, np.float64)
+    return (1 - np.exp(-(np.float32(beta) * mean))).astype(np.float32)
+
+
+class Unit:
+    """Flat haplotype-candidate descriptors of an inference unit (numpy arrays + ctypes view)."""
+
+    def __init__(self, arrays: dict, n_samples: int):
+        self.a = {}
+        for name, dt in _DESC_FIELDS:
+            self.a[name] = np.ascontiguousarray(arrays[name], dt)
+        self.S = n_samples
+        self.G = len(self.a["group_cluster_off"]) - 1
+        self.Cn = len(self.a["cl_kmer_off"]) - 1
+        self.n_variants = int(self.a["cl_var_off"][-1])
+
+    def desc(self) -> UnitDesc:
+        d = UnitDesc()
+        d.n_samples, d.n_groups, d.n_clusters = self.S, self.G, self.Cn
+        for name, _ in _DESC_FIELDS:
+            setattr(d, name, self.a[name].ctypes.data)
+        return d
+
+    # ---- sizes of the result arrays -----------------------------------------------------------
+    def alloc_result(self):
+        nA = self.a["var_nalleles"].astype(np.uint64)
+        S = np.uint64(self.S)
+        r = {
+            "allele_off": np.concatenate([[0], np.cumsum(S * nA)]).astype(np.uint64),
+            "geno_off": np.concatenate([[0], np.cumsum(S * nA * (nA + np.uint64(1)) // np.uint64(2))]).astype(np.uint64),
+            "valt_off": np.concatenate([[0], np.cumsum(nA)]).astype(np.uint64),
+        }
+        nv = self.n_variants
+        nall, ngen, nalt = int(r["allele_off"][-1]), int(r["geno_off"][-1]), int(r["valt_off"][-1])
+        sizes = {"gt": nv * self.S * 2, "gq": nv * self.S, "gpp": ngen, "app": nall, "nak": nall, "fak": nall, "mac": nall,
+                 "saf": nall, "ploidy": nv * self.S, "an": nv, "ac": nalt, "af": nalt, "acp": nalt, "anc": nalt, "hc": nv}
+        for name, dt in _RES_FIELDS:
+            if name not in r:
+                r[name] = np.zeros(sizes[name], dt)
+        res = GenotypeResult()
+        res.n_variants = nv
+        for name, _ in _RES_FIELDS:
+            setattr(res, name, r[name].ctypes.data)
+        return res, r
+
+    def tally_offsets(self):
+        H = self.a["cl_nhap"].astype(np.uint64)
+        n = (H + np.uint64(1)) * (H + np.uint64(2)) // np.uint64(2) * np.uint64(self.S)
+        return np.concatenate([[0], np.cumsum(n)]).astype(np.uint64)
+
+    def subset_groups(self, groups) -> "Unit":
+        """A new Unit holding only the given groups (used for shards and bounded CPU samples)."""
+        groups = np.asarray(groups, np.int64)
+        a = self.a
+        out = {k: [] for k, _ in _DESC_FIELDS}
+        gco = a["group_cluster_off"]
+        clusters = np.concatenate([np.arange(gco[g], gco[g + 1]) for g in groups]).astype(np.int64) if len(groups) else np.zeros(0, np.int64)
+
+        def take_csr(off_name, data_names, idx, width=None):
+            off = a[off_name]
+            lens = (off[idx + 1] - off[idx]).astype(np.int64)
+            sel = np.concatenate([np.arange(off[i], off[i + 1]) for i in idx]).astype(np.int64) if len(idx) else np.zeros(0, np.int64)
+            new_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+            return new_off, sel
+
+        S = self.S
+        new = {}
+        new["sample_gender"] = a["sample_gender"]
+        new["group_ploidy"] = a["group_ploidy"].reshape(-1, S)[groups].reshape(-1)
+        new["group_cluster_off"], _ = take_csr("group_cluster_off", [], groups)
+        new["group_src_off"], sel = take_csr("group_src_off", [], groups); new["group_src"] = a["group_src"][sel]
+        new["group_edge_off"], sel = take_csr("group_edge_off", [], groups)
+        new["group_edge_src"] = a["group_edge_src"][sel]; new["group_edge_dst"] = a["group_edge_dst"][sel]
+        new["cluster_idx"] = a["cluster_idx"][clusters]
+        new["cl_nhap"] = a["cl_nhap"][clusters]
+        new["cl_kmer_off"], rows = take_csr("cl_kmer_off", [], clusters)
+        new["cl_var_off"], vars_ = take_csr("cl_var_off", [], clusters)
+        new["cl_mult_off"], sel = take_csr("cl_mult_off", [], clusters); new["mult"] = a["mult"][sel]
+        new["k_has_counts"] = a["k_has_counts"][rows]
+        new["k_counts"] = a["k_counts"].reshape(-1, S)[rows].reshape(-1)
+        new["k_ic"] = a["k_ic"].reshape(-1, 2)[rows].reshape(-1)
+        new["k_shared"] = a["k_shared"][rows]
+        new["cl_uniq_off"], sel = take_csr("cl_uniq_off", [], clusters); new["uniq_idx"] = a["uniq_idx"][sel]
+        new["cl_multi_off"], sel = take_csr("cl_multi_off", [], clusters); new["multi_idx"] = a["multi_idx"][sel]
+        new["kmer_vh_off"], vh = take_csr("kmer_vh_off", [], rows); new["vh_var"] = a["vh_var"][vh]
+        new["vh_bits_off"], sel = take_csr("vh_bits_off", [], vh); new["vh_bits"] = a["vh_bits"][sel]
+        new["cl_hapvar_off"], sel = take_csr("cl_hapvar_off", [], clusters); new["hap_alleles"] = a["hap_alleles"][sel]
+        new["var_nalleles"] = a["var_nalleles"][vars_]; new["var_dep"] = a["var_dep"][vars_]
+        # haplotype-indexed arrays
+        hap_start = np.concatenate([[0], np.cumsum(a["cl_nhap"].astype(np.int64))])
+        haps = np.concatenate([np.arange(hap_start[c], hap_start[c + 1]) for c in clusters]).astype(np.int64) if len(clusters) else np.zeros(0, np.int64)
+        new["hap_nested_off"], sel = take_csr("hap_nested_off", [], haps); new["hap_nested"] = a["hap_nested"][sel]
+        new["cl_dep_off"], deps = take_csr("cl_dep_off", [], clusters); new["dep_cluster"] = a["dep_cluster"][deps]
+        new["dep_var_off"], sel = take_csr("dep_var_off", [], deps); new["dep_var"] = a["dep_var"][sel]
+        return Unit(new, S)
+
+
+def from_ref_dumps(haps: dict, graphs: dict, genders, ploidy=None) -> Unit:
+    """Unit from oracle-R's haps.btd + graphs.btd dumps (tests: same input for all three arms)."""
+    S = int(haps["meta"][0])
+    G = len(graphs["group_cluster_off"]) - 1
+    a = dict(haps)
+    a["sample_gender"] = np.array([0 if g in ("F", 0) else 1 for g in genders], np.uint8)
+    a["group_ploidy"] = np.full(G * S, 2, np.uint8) if ploidy is None else np.asarray(ploidy, np.uint8)
+    for k in ("group_cluster_off", "group_src_off", "group_src", "group_edge_off", "group_edge_src", "group_edge_dst", "cluster_idx", "cl_var_off"):
+        a[k] = graphs[k]
+    a["cl_nhap"] = np.diff(haps["cl_hap_off"]).astype(np.uint32)
+    a["var_nalleles"] = (1 + graphs["var_dep"].astype(np.uint16) + graphs["var_nalt"]).astype(np.uint16)
+    a["var_dep"] = graphs["var_dep"]
+    a["k_shared"] = np.full(len(haps["k_has_counts"]), 0xFFFFFFFF, np.uint32)
+    return Unit(a, S)

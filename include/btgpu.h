@@ -93,8 +93,7 @@ void btg_bloom_free(btg_bloom *b);
 /* ---- ThreadedKmerBloom (KmerBloom.hpp:79-108; KmerBloom.cpp:203-286) ----- *
  * 65,536 independent sub-filters selected by NTP64(kmer,k,1029283129)%65536.
  * The reference's per-sub-filter mutex (getKmerLock) exists only to make
- * test-then-set atomic; btg_tbloom_test_and_insert gives that operation
- * directly (first occurrence in call order wins, as under the lock).        */
+ * test-then-set atomic (KmerCounter.cpp:124-139).                            */
 typedef struct btg_tbloom btg_tbloom;
 btg_tbloom *btg_tbloom_create(uint64_t num_kmers, float fpr, int k);
 int btg_tbloom_info(const btg_tbloom *b, uint64_t *sub_kmers, uint64_t *sub_bits, uint32_t *num_hashes);
@@ -120,6 +119,130 @@ int btg_scan_sequence_dev(const char *seq_dev, size_t len, uint64_t *kmers_out_d
 /* fused scan + Bloom probe (the a10 genome scan against a filter): hit_out[p]=1
  * iff the window ending at p is valid and its canonical k-mer is in b */
 int btg_scan_sequence_lookup_dev(const btg_bloom *b, const char *seq_dev, size_t len, uint8_t *hit_out_dev, void *stream);
+
+
+/* ======================= per-cluster Gibbs sampler =========================== *
+ * Replaces InferenceEngine::{estimateNoise,estimateGenotypes,estimateNoiseAndGenotypes}
+ * (include/bayesTyper/InferenceEngine.hpp:62-64, src/bayesTyper/InferenceEngine.cpp:135-472)
+ * and everything below it: VariantClusterGroup::estimateGenotypes, VariantClusterGenotyper,
+ * VariantClusterHaplotypes, CountDistribution, (Sparse)FrequencyDistribution,
+ * DiscreteSampler, SparsityEstimator, CountAllocation, KmerStats.                */
+
+/* ---- CountDistribution (include/bayesTyper/CountDistribution.hpp:44-90) ------ */
+typedef struct btg_count_dist btg_count_dist;
+/* CountDistribution ctor + setGenomicCountDistributions' table build
+ * (src/bayesTyper/CountDistribution.cpp:51-64,215-238,267-312): per sample the
+ * negative-binomial (p, size) of one haploid copy; builds the [S][256][256]
+ * genomic log-pmf cache on the device.  prior = --noise-rate-prior (shape, scale). */
+btg_count_dist *btg_count_dist_create(uint32_t n_samples, const double *nb_p, const double *nb_size,
+                                      float noise_prior_shape, float noise_prior_scale);
+/* NegativeBinomialDistribution::momentsToParameters (NegativeBinomialDistribution.cpp:68-79)
+ * followed by the division of size by the modal multiplicity (CountDistribution.cpp:115-116) */
+void btg_nb_moments_to_parameters(double mean, double var, uint32_t multiplicity, double *p_out, double *size_out);
+/* CountDistribution::setNoiseRates (CountDistribution.cpp:153-161): rebuilds the [S][256] Poisson cache */
+int btg_count_dist_set_noise_rates(btg_count_dist *cd, const double *noise_rates);
+int btg_count_dist_get_noise_rates(const btg_count_dist *cd, double *noise_rates_out);
+/* copies of the device tables (tests / reporting): genomic [S][256][256], noise [S][256] */
+int btg_count_dist_tables(const btg_count_dist *cd, double *genomic_out, double *noise_out);
+void btg_count_dist_free(btg_count_dist *cd);
+
+/* ---- inference unit: flat haplotype-candidate descriptors ---------------------
+ * The state a VariantClusterGenotyper holds after its constructor
+ * (src/bayesTyper/VariantClusterGenotyper.cpp:59-106): VariantClusterHaplotypes
+ * (include/bayesTyper/VariantClusterHaplotypes.hpp:45-112) of every cluster of every
+ * VariantClusterGroup, CSR-flattened.  All arrays are host memory owned by the caller
+ * and are copied by btg_unit_upload.  Offsets are uint64 prefix sums.            */
+typedef struct btg_unit_desc {
+    uint32_t n_samples;               /* S <= 30 */
+    uint32_t n_groups;                /* G, in unit order (after the size sort, src/bayesTyper/main.cpp:247) */
+    uint32_t n_clusters;              /* C: group vertices concatenated in group order */
+    const uint8_t *sample_gender;     /* [S] 0 = Female, 1 = Male (Utils::Gender) */
+    const uint8_t *group_ploidy;      /* [G*S] Utils::Ploidy (0 Null, 1 Haploid, 2 Diploid) on the group's chromosome */
+    const uint64_t *group_cluster_off;/* [G+1] */
+    const uint64_t *group_src_off;    /* [G+1] -> group_src: source vertices (local cluster index), VariantClusterGroup.hpp:86 */
+    const uint32_t *group_src;
+    const uint64_t *group_edge_off;   /* [G+1] -> nested-cluster tree edges (local indices), in out_edges order */
+    const uint32_t *group_edge_src;
+    const uint32_t *group_edge_dst;
+    const uint32_t *cluster_idx;      /* [C] variant_cluster_idx inside the group (seeds; nested lookups) */
+    const uint32_t *cl_nhap;          /* [C] number of haplotype candidates H */
+    const uint64_t *cl_kmer_off;      /* [C+1] rows = k-mers (KmerInfo) */
+    const uint64_t *cl_var_off;       /* [C+1] variants */
+    const uint64_t *cl_mult_off;      /* [C+1] -> mult */
+    const uint8_t *mult;              /* haplotype_kmer_multiplicities, row-major K x H per cluster */
+    const uint8_t *k_has_counts;      /* [rows] KmerInfo::counts != nullptr */
+    const uint8_t *k_counts;          /* [rows*S] KmerCounts::getSampleCount */
+    const uint8_t *k_ic;              /* [rows*2] getInterclusterMultiplicity(Female), (Male) */
+    const uint32_t *k_shared;         /* [rows] group-shared multiplicity record of a multicluster k-mer, else 0xFFFFFFFF */
+    const uint64_t *cl_uniq_off;      /* [C+1] -> uniq_idx  (unique_kmer_indices, local row ids) */
+    const uint32_t *uniq_idx;
+    const uint64_t *cl_multi_off;     /* [C+1] -> multi_idx (multicluster_kmer_indices) */
+    const uint32_t *multi_idx;
+    const uint64_t *kmer_vh_off;      /* [rows+1] -> vh_var: KmerInfo::variant_haplotype_indices */
+    const uint16_t *vh_var;           /* variant index (local) */
+    const uint64_t *vh_bits_off;      /* [n_vh+1] -> vh_bits: one byte per haplotype (H of them) */
+    const uint8_t *vh_bits;
+    const uint64_t *cl_hapvar_off;    /* [C+1] -> hap_alleles */
+    const uint16_t *hap_alleles;      /* HaplotypeInfo::variant_allele_indices, H x nvar per cluster */
+    const uint16_t *var_nalleles;     /* [n_variants] VariantInfo::numberOfAlleles() (include/bayesTyper/VariantInfo.hpp:77-80) */
+    const uint8_t *var_dep;           /* [n_variants] VariantInfo::has_dependency */
+    const uint64_t *hap_nested_off;   /* [n_haplotypes+1] -> hap_nested: sorted nested_variant_cluster_indices */
+    const uint32_t *hap_nested;
+    const uint64_t *cl_dep_off;       /* [C+1] -> dep_cluster: nested_variant_cluster_dependency keys (ascending) */
+    const uint32_t *dep_cluster;
+    const uint64_t *dep_var_off;      /* [n_dep+1] -> dep_var (descending variant indices) */
+    const uint16_t *dep_var;
+} btg_unit_desc;
+
+typedef struct btg_unit btg_unit;
+btg_unit *btg_unit_upload(const btg_unit_desc *desc);
+void btg_unit_free(btg_unit *u);
+
+/* the options InferenceEngine / Filters read (src/bayesTyper/main.cpp:389-403) */
+typedef struct btg_gibbs_opts {
+    uint32_t random_seed;                 /* --random-seed */
+    uint16_t gibbs_burn_in;               /* 100 */
+    uint16_t gibbs_samples;               /* 250 */
+    uint16_t n_chains;                    /* 20  */
+    uint16_t first_group_index;           /* unused (0) */
+    float kmer_subsampling_rate;          /* 0.1 */
+    uint32_t max_haplotype_variant_kmers; /* 500 */
+    float min_genotype_posterior;         /* 0.99 (Filters) */
+    float min_number_of_kmers;            /* 1 */
+    float min_fraction_observed_kmers[BTG_MAX_SAMPLES]; /* Filters.cpp:42-53; 0 when --disable-observed-kmers */
+    uint64_t group_index_base;            /* index of this shard's first group in the whole unit (multi-GPU shards keep the reference's per-group seeds) */
+} btg_gibbs_opts;
+
+/* per-variant results: the fields of `Genotypes` (include/bayesTyper/Genotypes.hpp:46-99)
+ * as flat arrays owned by the caller.  nA = var_nalleles[v]; nG = nA*(nA+1)/2.
+ * Blocks are laid out variant-major, then sample: index (off[v] + s*nX + i).      */
+typedef struct btg_genotype_result {
+    uint64_t n_variants;
+    const uint64_t *allele_off;  /* [n_variants+1] prefix sums of S*nA  (app, nak, fak, mac, saf) */
+    const uint64_t *geno_off;    /* [n_variants+1] prefix sums of S*nG  (gpp) */
+    uint16_t *gt;                /* [n_variants*S*2] genotype_estimate, 0xFFFF = '.', second 0xFFFE = haploid/absent */
+    uint32_t *gq;                /* [n_variants*S] */
+    float *gpp;                  /* genotype_posteriors (first nA entries used when haploid) */
+    float *app;                  /* allele_posteriors */
+    float *nak, *fak, *mac;      /* AlleleKmerStats means, -1 when empty */
+    uint16_t *saf;               /* allele_filters */
+    uint8_t *ploidy;             /* [n_variants*S] ploidy the sample was genotyped with */
+    uint32_t *an;                /* [n_variants] VariantStats::total_count */
+    const uint64_t *valt_off;    /* [n_variants+1] prefix sums of nA (acp, anc) ; ac/af use entries 1.. */
+    uint32_t *ac;                /* [sum nA] alt_allele_counts at index a (a>=1) */
+    float *af;                   /* [sum nA] alt_allele_frequency */
+    float *acp;                  /* [sum nA] allele_call_probabilities */
+    uint8_t *anc;                /* [sum nA] 1 = allele not covered by any haplotype candidate */
+    uint16_t *hc;                /* [n_variants] num_candidates */
+} btg_genotype_result;
+
+/* InferenceEngine::estimateGenotypes (InferenceEngine.cpp:278-382): default mode, fixed noise rates */
+int btg_estimate_genotypes(btg_unit *u, const btg_count_dist *cd, const btg_gibbs_opts *opts, btg_genotype_result *out);
+/* InferenceEngine::estimateNoise (InferenceEngine.cpp:135-276): updates cd's noise rates; trace_out (optional)
+ * receives the <prefix>_noise_parameters.txt rows: [n_chains*(iters+1)+1][2+S] doubles (chain, iteration, rates..) */
+int btg_estimate_noise(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, double *trace_out);
+/* raw diplotype tallies of one cluster (tests): [(H+1)(H+2)/2][S] uint32, pair (h1<=h2), index h2*(h2+1)/2+h1, H = "missing" */
+int btg_unit_cluster_tally(const btg_unit *u, uint32_t cluster, uint32_t *tally_out, uint64_t n);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

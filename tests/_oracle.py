@@ -102,3 +102,71 @@ def bloom_lookup(bits: np.ndarray, m: int, nh: int, kmers: np.ndarray, want_prob
     load().bto_bloom_lookup(bits, m, nh, K, np.ascontiguousarray(kmers).reshape(-1), len(kmers), hit,
                             probes.ctypes.data_as(C.c_void_p))
     return (hit, probes) if want_probes else hit
+
+
+# ---- oracle-P (gibbs_oracle.cpp) ------------------------------------------------------------
+def _bind_gibbs(L):
+    if getattr(L, "_gibbs_bound", False):
+        return
+    dp = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+    L.bto_count_dist_create.restype = C.c_void_p
+    L.bto_count_dist_create.argtypes = [C.c_uint32, dp, dp, C.c_float, C.c_float]
+    L.bto_count_dist_set_noise_rates.argtypes = [C.c_void_p, dp]
+    L.bto_count_dist_get_noise_rates.argtypes = [C.c_void_p, dp]
+    L.bto_count_dist_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.bto_count_dist_free.argtypes = [C.c_void_p]
+    L.bto_nb_moments_to_parameters.argtypes = [C.c_double, C.c_double, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.bto_estimate_genotypes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.bto_estimate_noise.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L._gibbs_bound = True
+
+
+class OracleCountDist:
+    def __init__(self, nb_p, nb_size, prior=(1.0, 0.01)):
+        self.L = load()
+        _bind_gibbs(self.L)
+        self.S = len(nb_p)
+        self.h = self.L.bto_count_dist_create(self.S, np.ascontiguousarray(nb_p, np.float64), np.ascontiguousarray(nb_size, np.float64), prior[0], prior[1])
+
+    def set_noise_rates(self, rates):
+        self.L.bto_count_dist_set_noise_rates(self.h, np.ascontiguousarray(rates, np.float64))
+
+    def noise_rates(self):
+        out = np.zeros(self.S)
+        self.L.bto_count_dist_get_noise_rates(self.h, out)
+        return out
+
+    def tables(self):
+        g = np.zeros((self.S, 256, 256)); n = np.zeros((self.S, 256))
+        self.L.bto_count_dist_tables(self.h, g.ctypes.data, n.ctypes.data)
+        return g, n
+
+    def __del__(self):
+        try:
+            self.L.bto_count_dist_free(self.h)
+        except Exception:
+            pass
+
+
+def oracle_estimate_genotypes(unit, cd: OracleCountDist, opts, want_tally=False):
+    L = load()
+    _bind_gibbs(L)
+    res, arrays = unit.alloc_result()
+    desc = unit.desc()
+    toff = unit.tally_offsets()
+    tally = np.zeros(int(toff[-1]), np.uint32) if want_tally else None
+    rc = L.bto_estimate_genotypes(C.addressof(desc), cd.h, C.addressof(opts), C.addressof(res),
+                                  tally.ctypes.data if want_tally else None, toff.ctypes.data)
+    assert rc == 0, rc
+    return (arrays, tally) if want_tally else arrays
+
+
+def oracle_estimate_noise(unit, cd: OracleCountDist, opts):
+    L = load()
+    _bind_gibbs(L)
+    desc = unit.desc()
+    rows = opts.n_chains * (opts.gibbs_burn_in + opts.gibbs_samples + 1) + 1
+    trace = np.zeros((rows, 2 + unit.S))
+    rc = L.bto_estimate_noise(C.addressof(desc), cd.h, C.addressof(opts), trace.ctypes.data)
+    assert rc == 0, rc
+    return trace

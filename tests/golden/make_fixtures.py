@@ -1,0 +1,86 @@
+"""Generates the committed Gibbs fixtures from the REFERENCE ITSELF (oracle-R = the
+reference's translation units compiled in place, oracle/ref_build).  Run in the build
+container (needs /root/reference):  python tests/golden/make_fixtures.py
+
+Each fixture <name>.btd holds, for a seeded synthetic workload (bayestyper_b200/synth.py):
+  unit.*   the flat haplotype-candidate descriptors dumped from VariantClusterGraph::
+           getHaplotypeCandidates (a13/a14 output) for a subset of groups
+  tab.*    CountDistribution: NB parameters, noise rates after estimateNoise, both log-pmf caches
+  ref.*    what the reference wrote to its VCF for those variants (GT, GQ, GPP, APP, NAK, FAK, MAC, SAF)
+"""
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from bayestyper_b200 import btd, synth, unit as U, vcfio  # noqa: E402
+
+BTREF = ROOT / "oracle" / "_ref" / "btref"
+
+
+def make(name, workload, n_groups, seed=20190401, n_errors=20000):
+    with tempfile.TemporaryDirectory() as td:
+        wd = synth.write_workdir(workload, td, n_errors=n_errors)
+        subprocess.check_call([str(BTREF), "run", "--workdir", str(wd), "--threads", "8", "--seed", str(seed), "--dump-graphs", "--dump-haps"],
+                              stdout=subprocess.DEVNULL)
+        out = Path(wd) / "ref_out"
+        g = btd.read(out / "graphs.btd"); h = btd.read(out / "haps.btd"); t = btd.read(out / "tables.btd")
+        S = int(h["meta"][0])
+        # ploidy per group/sample as ChromosomePloidy assigns it (default human rules, ChromosomePloidy.cpp:40-105)
+        G = len(g["group_cluster_off"]) - 1
+        chrom = workload.chrom.lower()
+        pl = np.full((G, S), 2, np.uint8)
+        for s, gd in enumerate(workload.genders):
+            if chrom in ("x", "chrx") and gd == "M":
+                pl[:, s] = 1
+            if chrom in ("y", "chry"):
+                pl[:, s] = 1 if gd == "M" else 0
+        un = U.from_ref_dumps(h, g, workload.genders, pl.reshape(-1))
+        # keep a spread of groups: the largest ones and a stride through the rest
+        rng = np.random.default_rng(7)
+        keep = np.unique(np.concatenate([np.arange(min(20, G)), rng.choice(G, size=min(n_groups, G), replace=False)]))
+        sub = un.subset_groups(keep)
+        _, rows = vcfio.read_vcf(out / "bayestyper.vcf")
+        byid = {r["id"]: r for r in rows}
+        ids = [bytes(g["var_ids"][g["var_id_off"][i]:g["var_id_off"][i + 1]]).decode() for i in range(len(g["var_pos"]))]
+        gco, cvo = un.a["group_cluster_off"], un.a["cl_var_off"]
+        var_sel = np.concatenate([np.arange(cvo[c], cvo[c + 1]) for gi in keep for c in range(gco[gi], gco[gi + 1])]).astype(np.int64)
+        res, arr = sub.alloc_result()
+        ref = {k: arr[k].copy() for k in ("gt", "gq", "gpp", "app", "nak", "fak", "mac", "saf")}
+        nAs = sub.a["var_nalleles"]
+        for j, v in enumerate(var_sel):
+            r = byid[ids[v]]
+            nA = int(nAs[j]); nG = nA * (nA + 1) // 2
+            for s in range(S):
+                sr = r["samples"][s]
+                gt = sr["GT"].replace("|", "/").split("/")
+                o = (j * S + s) * 2
+                ref["gt"][o] = 0xFFFF if gt[0] == "." else int(gt[0])
+                ref["gt"][o + 1] = (0xFFFF if gt[1] == "." else int(gt[1])) if len(gt) > 1 else 0xFFFE
+                ref["gq"][j * S + s] = sr.get("GQ", 0)
+                if "GPP" in sr:
+                    gp = np.array(sr["GPP"], np.float32)
+                    ref["gpp"][int(arr["geno_off"][j]) + s * nG: int(arr["geno_off"][j]) + s * nG + len(gp)] = gp
+                a0 = int(arr["allele_off"][j]) + s * nA
+                for k in ("app", "nak", "fak", "mac", "saf"):
+                    if k.upper() in sr:
+                        ref[k][a0:a0 + nA] = np.array(sr[k.upper()], ref[k].dtype)
+        pack = {"unit." + k: v for k, v in sub.a.items()}
+        pack.update({"tab." + k: v for k, v in t.items()})
+        pack.update({"ref." + k: v for k, v in ref.items()})
+        pack["meta.n_samples"] = np.array([S], np.uint32)
+        pack["meta.groups"] = keep.astype(np.uint32)            # indices in the full unit (seed derivation)
+        pack["meta.seed"] = np.array([seed], np.uint32)
+        pack["meta.noise_trace"] = np.loadtxt(out / "bayestyper_noise_parameters.txt", skiprows=1, ndmin=2)
+        btd.write(Path(__file__).parent / f"{name}.btd", pack)
+        print(name, "groups", len(keep), "clusters", sub.Cn, "variants", sub.n_variants, "H max", int(sub.a["cl_nhap"].max()))
+
+
+if __name__ == "__main__":
+    make("gibbs_snv_1s", synth.config_a(n_variants=1200, length=120_000), 160)
+    make("gibbs_mixed_3s", synth.small_mixed(700, 60_000, 3, seed=21), 120)
+    make("gibbs_chrx_2s", synth.small_mixed(400, 50_000, 2, seed=33, chrom="chrX"), 80)

@@ -1,0 +1,132 @@
+"""GPU parity of the Gibbs path against oracle-P through the C ABI:
+same Philox streams -> identical diplotype tallies, GPP/APP within 1e-4 (north-star tolerance),
+identical GT/GQ/SAF; count tables within 1e-12 relative (f64 libm differences only)."""
+import numpy as np
+import pytest
+
+from bayestyper_b200 import engine, unit as U
+from tests import _oracle as O
+from tests._fixtures import GIBBS_FIXTURES, GibbsFixture
+
+pytestmark = pytest.mark.gpu
+GPP_TOL = 1e-4   # BASELINE.json north_star: "posteriors within 1e-4 of reference under fixed seed"
+
+
+def _both(fx, opts, noise_rates=None):
+    rates = fx.tab["noise_rates"] if noise_rates is None else noise_rates
+    ocd = O.OracleCountDist(fx.nb_p, fx.nb_size); ocd.set_noise_rates(rates)
+    gcd = engine.CountDistribution(fx.nb_p, fx.nb_size); gcd.set_noise_rates(rates)
+    return ocd, gcd
+
+
+@pytest.mark.parametrize("name", GIBBS_FIXTURES)
+def test_count_tables(btg, name):
+    fx = GibbsFixture(name)
+    ocd, gcd = _both(fx, None)
+    og, on = ocd.tables()
+    gg, gn = gcd.tables()
+    assert (np.isfinite(og) == np.isfinite(gg)).all()
+    fin = np.isfinite(og)
+    rel = np.abs(gg[fin] - og[fin]) / np.maximum(1.0, np.abs(og[fin]))
+    assert rel.max() < 1e-12
+    assert (np.abs(gn - on) / np.maximum(1.0, np.abs(on))).max() < 1e-12
+    # and against the reference's own tables (fixture)
+    ref = fx.tab["genomic_log_pmf"]
+    assert (np.abs(gg[fin] - ref[fin]) / np.maximum(1.0, np.abs(ref[fin]))).max() < 1e-12
+
+
+@pytest.mark.parametrize("name", GIBBS_FIXTURES)
+def test_estimate_genotypes_matches_oracle(btg, name):
+    fx = GibbsFixture(name)
+    opts = fx.opts()
+    ocd, gcd = _both(fx, opts)
+    ores, otally = O.oracle_estimate_genotypes(fx.unit, ocd, opts, want_tally=True)
+    eng = engine.InferenceEngine(fx.unit)
+    gres = eng.estimate_genotypes(gcd, opts)
+    toff = fx.unit.tally_offsets()
+    n_bad = 0
+    for c in range(fx.unit.Cn):
+        t = eng.cluster_tally(c).reshape(-1)
+        n_bad += not (t == otally[int(toff[c]):int(toff[c + 1])]).all()
+    assert n_bad == 0, f"{n_bad} clusters with different diplotype tallies"
+    assert np.abs(gres["gpp"] - ores["gpp"]).max() <= GPP_TOL
+    assert np.abs(gres["app"] - ores["app"]).max() <= GPP_TOL
+    for k in ("gt", "gq", "saf", "an", "ac", "anc", "hc", "ploidy"):
+        assert (gres[k] == ores[k]).all(), k
+    for k in ("nak", "fak", "mac", "af", "acp"):
+        assert np.abs(gres[k] - ores[k]).max() <= 1e-4, k
+    # and statistically against the reference's VCF values held by the fixture
+    d = np.abs(gres["gpp"] - fx.ref["gpp"])
+    assert d.mean() < 2e-3 and np.quantile(d, 0.99) <= 0.1 + 1e-6
+    eng.close()
+
+
+def test_seed_and_shard_invariance(btg):
+    """Per-group streams: a group's result does not depend on which other groups share the launch
+    (the reference's determinism contract, README.md:9), and changes with the seed."""
+    fx = GibbsFixture("gibbs_mixed_3s")
+    opts = fx.opts(chains=3, burn=20, samples=40)
+    _, gcd = _both(fx, opts)
+    eng = engine.InferenceEngine(fx.unit)
+    full = eng.estimate_genotypes(gcd, opts)
+    half = np.arange(fx.unit.G // 2, fx.unit.G)
+    sub = fx.unit.subset_groups(half)
+    eng2 = engine.InferenceEngine(sub)
+    o2 = fx.opts(chains=3, burn=20, samples=40, group_base=int(half[0]))
+    part = eng2.estimate_genotypes(gcd, o2)
+    v0 = int(fx.unit.a["cl_var_off"][int(fx.unit.a["group_cluster_off"][half[0]])])
+    g0 = int(full["geno_off"][v0])
+    assert (part["gpp"] == full["gpp"][g0:]).all()
+    assert (part["gt"] == full["gt"][v0 * fx.S * 2:]).all()
+    o3 = fx.opts(chains=3, burn=20, samples=40, seed=7)
+    other = eng.estimate_genotypes(gcd, o3)
+    assert (other["gpp"] != full["gpp"]).any()
+    eng.close(); eng2.close()
+
+
+def test_estimate_noise_matches_oracle(btg):
+    fx = GibbsFixture("gibbs_snv_1s")
+    opts = fx.opts(chains=3, burn=30, samples=60)
+    ocd, gcd = _both(fx, opts)
+    otrace = O.oracle_estimate_noise(fx.unit, ocd, opts)
+    eng = engine.InferenceEngine(fx.unit)
+    gtrace = eng.estimate_noise(gcd, opts)
+    assert gtrace.shape == otrace.shape
+    assert (gtrace[:, :2] == otrace[:, :2]).all()
+    rel = np.abs(gtrace[:, 2:] - otrace[:, 2:]) / otrace[:, 2:]
+    assert rel.max() < 1e-9
+    assert np.abs(gcd.noise_rates() - ocd.noise_rates()).max() / ocd.noise_rates().max() < 1e-9
+    eng.close()
+
+
+def test_multi_sample_noise(btg):
+    fx = GibbsFixture("gibbs_chrx_2s")
+    opts = fx.opts(chains=2, burn=10, samples=20)
+    ocd, gcd = _both(fx, opts)
+    otrace = O.oracle_estimate_noise(fx.unit, ocd, opts)
+    eng = engine.InferenceEngine(fx.unit)
+    gtrace = eng.estimate_noise(gcd, opts)
+    assert (np.abs(gtrace[:, 2:] - otrace[:, 2:]) / otrace[:, 2:]).max() < 1e-9
+    eng.close()
+
+
+def test_rejects_nested_groups_loudly(btg):
+    fx = GibbsFixture("gibbs_snv_1s")
+    a = dict(fx.unit.a)
+    gco = a["group_cluster_off"].copy()
+    a["group_cluster_off"] = np.concatenate([gco[:1], gco[2:]])      # merge the first two groups
+    a["group_ploidy"] = a["group_ploidy"][fx.S:]
+    a["group_src_off"] = a["group_src_off"][:-1]; a["group_edge_off"] = a["group_edge_off"][:-1]
+    bad = U.Unit(a, fx.S)
+    with pytest.raises(Exception, match="nested"):
+        engine.InferenceEngine(bad)
+
+
+def test_empty_unit(btg):
+    fx = GibbsFixture("gibbs_snv_1s")
+    empty = fx.unit.subset_groups(np.zeros(0, np.int64))
+    eng = engine.InferenceEngine(empty)
+    _, gcd = _both(fx, None)
+    res = eng.estimate_genotypes(gcd, fx.opts())
+    assert res["gpp"].size == 0
+    eng.close()
