@@ -21,3 +21,6 @@ def bind(L):
     L.btg_estimate_genotypes.argtypes = [vp, vp, vp, vp]
     L.btg_estimate_noise.argtypes = [vp, vp, vp, vp]
     L.btg_unit_cluster_tally.argtypes = [vp, C.c_uint32, vp, C.c_uint64]
+    L.btg_estimate_genotypes_async.argtypes = [vp, vp, vp, vp]
+    L.btg_unit_download_result.argtypes = [vp, vp, vp]
+    L.btg_get_stream.restype = vp

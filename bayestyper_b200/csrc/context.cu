@@ -76,6 +76,7 @@ void btg_host_free(void *p) {
     if (p) cudaFreeHost(p);
 }
 
+void *btg_get_stream(void) { return btg::ctx().ready ? (void *)btg::ctx().stream : nullptr; }
 uint64_t btg_launch_count(void) { return btg::g_launches.load(); }
 void btg_launch_count_reset(void) { btg::g_launches = 0; }
 

@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cmath>
 #include <numeric>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -122,12 +123,24 @@ struct btg_count_dist {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
+// Arena layout.  Clusters are sorted by cost and dealt to lanes in that order; the 32 clusters that share a
+// warp share one arena SLOT whose arrays are interleaved across lanes (element e of lane l lives at
+// base + e*32 + l).  A warp reading "the same field" of its 32 clusters therefore touches one or two 128 B
+// lines instead of 32 scattered ones, and the hot state of the resident warps stays in L1.
 struct ClusterLayout {
-    uint64_t f64_off, u32_off, u8_off;  // arena slices
     uint32_t group;                     // owning group
     uint32_t n_alleles;                 // sum of numberOfAlleles over the cluster's variants
     uint32_t Dall;                      // (H+1)(H+2)/2 diplotype slots (index H = "missing")
-    uint32_t pad;
+    uint32_t pos;                       // position in the cost order: slot = pos >> 5, lane = pos & 31
+};
+struct SlotLayout {
+    uint64_t f64_off, u32_off, u8_off;  // element offsets of the slot in the three pools
+    uint32_t H, K, nvar, n_uniq, n_alleles, Dall;  // per-lane capacities = max over the slot's clusters
+};
+template <class T> struct LaneArr {
+    T *p;
+    __device__ __forceinline__ T &operator[](size_t i) const { return p[i * 32]; }
+    __device__ __forceinline__ LaneArr<T> operator+(size_t i) const { return LaneArr<T>{p + i * 32}; }
 };
 
 struct DevUnit {
@@ -148,6 +161,7 @@ struct DevUnit {
     const uint8_t *var_dep;
     const uint64_t *valt_off;    // prefix sums of numberOfAlleles over all variants
     const ClusterLayout *layout;
+    const SlotLayout *slots;
     const uint32_t *order;       // clusters sorted by decreasing cost
     double *f64_pool;
     uint32_t *u32_pool;
@@ -187,9 +201,9 @@ struct Cl {
     uint64_t row0, var0;
     const DevUnit *u;
     const uint8_t *M;
-    double *freq, *simplex, *ucache, *cum, *kc_f, *as_f, *fmisc;
-    uint32_t *obs, *uniq, *uniq_sub, *cnt, *tally, *kc_n, *as_n, *dipl, *misc;
-    uint8_t *nz, *uncovered, *stats_update;
+    LaneArr<double> freq, simplex, ucache, cum, kc_f, as_f, fmisc;
+    LaneArr<uint32_t> obs, uniq, uniq_sub, cnt, tally, kc_n, as_n, dipl, misc;
+    LaneArr<uint8_t> nz, uncovered, stats_update;
 
     __device__ void bind(const DevUnit &du, uint32_t cluster) {
         u = &du; c = cluster;
@@ -205,27 +219,29 @@ struct Cl {
         Dall = L.Dall;
         n_alleles = L.n_alleles;
         M = du.mult + du.cl_mult_off[c];
-        double *f = du.f64_pool + L.f64_off;
-        freq = f; f += H;
-        simplex = f; f += H + 1;
-        ucache = f; f += (uint64_t)S * Dall;
-        cum = f; f += Dall;
-        kc_f = f; f += (uint64_t)S * 2 * nvar * 2;
-        as_f = f; f += (uint64_t)n_alleles * S * 6;
+        const SlotLayout SL = du.slots[L.pos >> 5];
+        const uint32_t lane = L.pos & 31u;
+        LaneArr<double> f{du.f64_pool + SL.f64_off + lane};
+        freq = f; f = f + SL.H;
+        simplex = f; f = f + (SL.H + 1);
+        ucache = f; f = f + (uint64_t)S * SL.Dall;
+        cum = f; f = f + SL.Dall;
+        kc_f = f; f = f + (uint64_t)S * 2 * SL.nvar * 2;
+        as_f = f; f = f + (uint64_t)SL.n_alleles * S * 6;
         fmisc = f;
-        uint32_t *w = du.u32_pool + L.u32_off;
-        obs = w; w += H;
-        uniq = w; w += n_uniq;
-        uniq_sub = w; w += n_uniq;
-        cnt = w; w += (uint64_t)H * nvar;
-        tally = w; w += (uint64_t)Dall * S;
-        kc_n = w; w += (uint64_t)S * 2 * nvar;
-        as_n = w; w += (uint64_t)n_alleles * S * 3;
-        dipl = w; w += S;
+        LaneArr<uint32_t> w{du.u32_pool + SL.u32_off + lane};
+        obs = w; w = w + SL.H;
+        uniq = w; w = w + SL.n_uniq;
+        uniq_sub = w; w = w + SL.n_uniq;
+        cnt = w; w = w + (uint64_t)SL.H * SL.nvar;
+        tally = w; w = w + (uint64_t)SL.Dall * S;
+        kc_n = w; w = w + (uint64_t)S * 2 * SL.nvar;
+        as_n = w; w = w + (uint64_t)SL.n_alleles * S * 3;
+        dipl = w; w = w + S;
         misc = w;
-        uint8_t *b = du.u8_pool + L.u8_off;
-        nz = b; b += H;
-        uncovered = b; b += K;
+        LaneArr<uint8_t> b{du.u8_pool + SL.u8_off + lane};
+        nz = b; b = b + SL.H;
+        uncovered = b; b = b + SL.K;
         stats_update = b;
     }
     __device__ __forceinline__ uint8_t m(uint32_t k, uint32_t h) const { return M[(size_t)k * H + h]; }
@@ -352,8 +368,8 @@ __device__ double cl_dipl_log_prob(Cl &cl, const Tables &T, uint32_t s, uint32_t
     if (b == NONE) lp += log(cl.freq[a]);
     else if (a == b) lp += 2 * log(cl.freq[a]);
     else lp += log(2.0) + log(cl.freq[a]) + log(cl.freq[b]);
-    double *cache = cl.ucache + (size_t)s * cl.Dall + cl.slot(a, b == NONE ? cl.H : b);
-    double acc = *cache;
+    const size_t ci = (size_t)s * cl.Dall + cl.slot(a, b == NONE ? cl.H : b);
+    double acc = cl.ucache[ci];
     if (acc != acc) {  // not cached yet
         acc = 0;
         const uint32_t n_sub = cl.misc[kNSub];
@@ -361,7 +377,7 @@ __device__ double cl_dipl_log_prob(Cl &cl, const Tables &T, uint32_t s, uint32_t
             const uint32_t k = cl.uniq_sub[i];
             acc += T.logProb(s, (uint8_t)(cl.diplMult(k, a, b) + cl.ic(k, s)), cl.count(k, s));
         }
-        *cache = acc;
+        cl.ucache[ci] = acc;
     }
     return lp + acc;
 }
@@ -706,8 +722,8 @@ __global__ void __launch_bounds__(64) k_noise_init(DevUnit du, btg_gibbs_opts o,
     prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, chain);
     fr.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngFrequency, chain);
     cl_reset(cl, o, prng);
-    prng.save(cl.misc + kRng0);
-    fr.save(cl.misc + kRng1);
+    prng.save(cl.misc, kRng0);
+    fr.save(cl.misc, kRng1);
 }
 
 // sampleGenotypesCallback (InferenceEngine.cpp:77-98): one Gibbs iteration + noise-count histogram
@@ -719,8 +735,8 @@ __global__ void __launch_bounds__(64) k_noise_iteration(DevUnit du, Tables T, bt
     const uint64_t gidx = o.group_index_base + cl.g;
     const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
     Philox prng, fr;
-    prng.load(cl.misc + kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
-    fr.load(cl.misc + kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
+    prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+    fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
     cl_sample_diplotypes(cl, T, ploidy, false, prng);
     cl_sample_frequencies(cl, fr);
     // VariantClusterGenotyper::getNoiseCounts (…Genotyper.cpp:757-779)
@@ -735,8 +751,8 @@ __global__ void __launch_bounds__(64) k_noise_iteration(DevUnit du, Tables T, bt
     // clearGenotyperCache: the Poisson table is about to change
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     for (uint32_t j = 0; j < cl.S * cl.Dall; j++) cl.ucache[j] = nan;
-    prng.save(cl.misc + kRng0);
-    fr.save(cl.misc + kRng1);
+    prng.save(cl.misc, kRng0);
+    fr.save(cl.misc, kRng1);
 }
 
 // CountDistribution::sampleNoiseParameters / resetNoiseRates + updateNoiseCache, on the device so that the
@@ -747,7 +763,7 @@ __global__ void k_noise_update(NoiseState ns, uint32_t S, float prior_shape, flo
     __shared__ double sh_rates[BTG_MAX_SAMPLES];
     if (threadIdx.x == 0) {
         Philox rng;
-        rng.load(ns.rng, seed, (uint64_t)-1, 0);
+        rng.load(ns.rng, 0, seed, (uint64_t)-1, 0);
         for (uint32_t s = 0; s < S; s++) {
             double r;
             if (mode == 0) {
@@ -767,7 +783,7 @@ __global__ void k_noise_update(NoiseState ns, uint32_t S, float prior_shape, flo
             sh_rates[s] = r;
             if (accumulate) ns.mean_rates[s] += r;
         }
-        rng.save(ns.rng);
+        rng.save(ns.rng, 0);
         if (ns.trace) {
             double *row = ns.trace + (size_t)(*ns.trace_row) * (2 + S);
             row[0] = chain_label; row[1] = iter_label;
@@ -782,7 +798,7 @@ __global__ void k_noise_update(NoiseState ns, uint32_t S, float prior_shape, flo
 __global__ void k_noise_rng_init(uint32_t *rng, uint32_t seed) {
     Philox r;
     r.init(seed, (uint64_t)-1, 0, kRngNoise);
-    r.save(rng);
+    r.save(rng, 0);
 }
 
 template <class T> T *upload(const T *h, size_t n, bool &ok) {
@@ -796,14 +812,18 @@ template <class T> T *upload(const T *h, size_t n, bool &ok) {
 
 struct btg_unit {
     DevUnit du{};
+    void *res_view = nullptr;  // ResultView* (host struct with device pointers), allocated on first use
     std::vector<void *> allocs;
     std::vector<uint64_t> h_valt_off, h_allele_off, h_geno_off;
     std::vector<uint32_t> h_nhap, h_group_nvar;
     std::vector<uint64_t> h_group_cluster_off, h_cl_var_off;
     std::vector<ClusterLayout> h_layout;
+    std::vector<SlotLayout> h_slots;
     uint64_t n_variants = 0, n_alleles_total = 0;
     uint32_t max_h = 0;
 };
+
+void btg_unit_free_result(btg_unit *u);
 
 extern "C" {
 
@@ -934,7 +954,8 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
     u->h_nhap.assign(d->cl_nhap, d->cl_nhap + C);
     u->h_group_cluster_off.assign(d->group_cluster_off, d->group_cluster_off + G + 1);
     u->h_cl_var_off.assign(d->cl_var_off, d->cl_var_off + C + 1);
-    uint64_t f64_total = 0, u32_total = 0, u8_total = 0;
+    struct Dims { uint32_t H, K, nv, nu, nal, Dall; };
+    std::vector<Dims> dims(C);
     std::vector<uint64_t> cost(C);
     for (uint32_t g = 0; g < G; g++) {
         for (uint64_t c = d->group_cluster_off[g]; c < d->group_cluster_off[g + 1]; c++) {
@@ -948,9 +969,7 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
             L.group = g;
             L.n_alleles = nal;
             L.Dall = (H + 1) * (H + 2) / 2;
-            L.f64_off = f64_total; L.u32_off = u32_total; L.u8_off = u8_total;
-            const ArenaSizes a = arena_sizes(S, H, K, nv, nu, nal, L.Dall);
-            f64_total += a.f64; u32_total += a.u32; u8_total += a.u8;
+            dims[c] = Dims{H, K, nv, nu, nal, L.Dall};
             cost[c] = (uint64_t)S * ((uint64_t)H * (H + 1) / 2) * 8 + nu + (uint64_t)H * K / 16;
             u->max_h = std::max(u->max_h, H);
         }
@@ -958,7 +977,24 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
     std::vector<uint32_t> order(C);
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
+    // one arena slot per warp of the cost order, sized by the largest cluster in it
+    const uint32_t n_slots = (C + 31) / 32;
+    u->h_slots.assign(n_slots ? n_slots : 1, SlotLayout{});
+    uint64_t f64_total = 0, u32_total = 0, u8_total = 0;
+    for (uint32_t w = 0; w < n_slots; w++) {
+        SlotLayout &SL = u->h_slots[w];
+        for (uint32_t i = w * 32; i < std::min<uint64_t>(C, (uint64_t)w * 32 + 32); i++) {
+            const Dims &D = dims[order[i]];
+            u->h_layout[order[i]].pos = i;
+            SL.H = std::max(SL.H, D.H); SL.K = std::max(SL.K, D.K); SL.nvar = std::max(SL.nvar, D.nv);
+            SL.n_uniq = std::max(SL.n_uniq, D.nu); SL.n_alleles = std::max(SL.n_alleles, D.nal); SL.Dall = std::max(SL.Dall, D.Dall);
+        }
+        const ArenaSizes a = arena_sizes(S, SL.H, SL.K, SL.nvar, SL.n_uniq, SL.n_alleles, SL.Dall);
+        SL.f64_off = f64_total; SL.u32_off = u32_total; SL.u8_off = u8_total;
+        f64_total += a.f64 * 32; u32_total += a.u32 * 32; u8_total += a.u8 * 32;
+    }
     du.layout = keep(upload(u->h_layout.data(), C, ok));
+    du.slots = keep(upload(u->h_slots.data(), u->h_slots.size(), ok));
     du.order = keep(upload(order.data(), C, ok));
     double *f64_pool = nullptr; uint32_t *u32_pool = nullptr; uint8_t *u8_pool = nullptr; double *lg = nullptr;
     ok = ok && cudaMalloc(&f64_pool, (f64_total + 1) * sizeof(double)) == cudaSuccess;
@@ -983,61 +1019,95 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
 
 void btg_unit_free(btg_unit *u) {
     if (!u) return;
+    cudaStreamSynchronize(ctx().stream);
     for (void *p : u->allocs) cudaFree(p);
+    btg_unit_free_result(u);
     delete u;
 }
 
 }  // extern "C"
 
 namespace {
+// device-side result arrays owned by the unit (allocated on first use)
 struct DevResult {
     ResultView R{};
-    std::vector<std::pair<void *, std::pair<void *, size_t>>> copies;  // device -> (host, bytes)
     std::vector<void *> allocs;
-    bool ok = true;
-    template <class T> T *out(T *host, size_t n) {
-        T *d = nullptr;
-        if (cudaMalloc(&d, (n ? n : 1) * sizeof(T)) != cudaSuccess) { ok = false; return nullptr; }
-        allocs.push_back(d);
-        copies.push_back({d, {host, n * sizeof(T)}});
-        return d;
-    }
+    uint64_t nv = 0, nall = 0, ngen = 0, nalt = 0;
     ~DevResult() { for (void *p : allocs) cudaFree(p); }
 };
+
+DevResult *unit_result(btg_unit *u) {
+    if (u->res_view) return static_cast<DevResult *>(u->res_view);
+    auto *dr = new DevResult();
+    const uint32_t S = u->du.S;
+    const uint64_t nv = u->n_variants, nall = u->h_allele_off[nv], ngen = u->h_geno_off[nv], nalt = u->h_valt_off[nv];
+    dr->nv = nv; dr->nall = nall; dr->ngen = ngen; dr->nalt = nalt;
+    bool ok = true;
+    auto mk = [&](auto *&dst, size_t n) {
+        void *d = nullptr;
+        if (cudaMalloc(&d, (n ? n : 1) * sizeof(*dst)) != cudaSuccess) { ok = false; return; }
+        dr->allocs.push_back(d);
+        dst = static_cast<std::remove_reference_t<decltype(dst)>>(d);
+    };
+    dr->R.allele_off = upload(u->h_allele_off.data(), nv + 1, ok); dr->allocs.push_back((void *)dr->R.allele_off);
+    dr->R.geno_off = upload(u->h_geno_off.data(), nv + 1, ok); dr->allocs.push_back((void *)dr->R.geno_off);
+    dr->R.valt_off = u->du.valt_off;
+    mk(dr->R.gt, nv * S * 2); mk(dr->R.gq, nv * S); mk(dr->R.gpp, ngen); mk(dr->R.app, nall);
+    mk(dr->R.nak, nall); mk(dr->R.fak, nall); mk(dr->R.mac, nall); mk(dr->R.saf, nall); mk(dr->R.ploidy, nv * S);
+    mk(dr->R.an, nv); mk(dr->R.ac, nalt); mk(dr->R.af, nalt); mk(dr->R.acp, nalt); mk(dr->R.anc, nalt); mk(dr->R.hc, nv);
+    if (!ok) { delete dr; return nullptr; }
+    u->res_view = dr;
+    return dr;
+}
 }  // namespace
 
 extern "C" {
 
-int btg_estimate_genotypes(btg_unit *u, const btg_count_dist *cd, const btg_gibbs_opts *opts, btg_genotype_result *out) {
+int btg_estimate_genotypes_async(btg_unit *u, const btg_count_dist *cd, const btg_gibbs_opts *opts, void *stream) {
     BTG_REQUIRE_INIT();
-    if (!u || !cd || !opts || !out) { set_error("null argument"); return BTG_EINVAL; }
+    if (!u || !cd || !opts) { set_error("null argument"); return BTG_EINVAL; }
     if (cd->S != u->du.S) { set_error("count distribution has %u samples, unit has %u", cd->S, u->du.S); return BTG_EINVAL; }
-    if (out->n_variants != u->n_variants) { set_error("result sized for %llu variants, unit has %llu", (unsigned long long)out->n_variants, (unsigned long long)u->n_variants); return BTG_EINVAL; }
-    const uint32_t S = u->du.S;
-    const uint64_t nv = u->n_variants, nall = u->h_allele_off[nv], ngen = u->h_geno_off[nv], nalt = u->h_valt_off[nv];
-    DevResult dr;
-    bool ok = true;
-    dr.R.allele_off = upload(u->h_allele_off.data(), nv + 1, ok); dr.allocs.push_back((void *)dr.R.allele_off);
-    dr.R.geno_off = upload(u->h_geno_off.data(), nv + 1, ok); dr.allocs.push_back((void *)dr.R.geno_off);
-    dr.R.valt_off = u->du.valt_off;
-    dr.R.gt = dr.out(out->gt, nv * S * 2); dr.R.gq = dr.out(out->gq, nv * S);
-    dr.R.gpp = dr.out(out->gpp, ngen); dr.R.app = dr.out(out->app, nall);
-    dr.R.nak = dr.out(out->nak, nall); dr.R.fak = dr.out(out->fak, nall); dr.R.mac = dr.out(out->mac, nall);
-    dr.R.saf = dr.out(out->saf, nall); dr.R.ploidy = dr.out(out->ploidy, nv * S);
-    dr.R.an = dr.out(out->an, nv); dr.R.ac = dr.out(out->ac, nalt); dr.R.af = dr.out(out->af, nalt);
-    dr.R.acp = dr.out(out->acp, nalt); dr.R.anc = dr.out(out->anc, nalt); dr.R.hc = dr.out(out->hc, nv);
-    if (!ok || !dr.ok) { set_error("result allocation failed"); return BTG_ENOMEM; }
-    auto s = ctx().stream;
+    DevResult *dr = unit_result(u);
+    if (!dr) { set_error("result allocation failed"); return BTG_ENOMEM; }
     Tables T{cd->genomic, cd->noise};
     if (u->du.C) {
-        k_estimate_genotypes<<<(u->du.C + 63) / 64, 64, 0, s>>>(u->du, T, *opts, dr.R);
+        k_estimate_genotypes<<<(u->du.C + 63) / 64, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R);
         BTG_LAUNCHED();
         BTG_CUDA(cudaGetLastError());
     }
-    for (auto &cp : dr.copies) BTG_CUDA(cudaMemcpyAsync(cp.second.first, cp.first, cp.second.second, cudaMemcpyDeviceToHost, s));
+    return BTG_OK;
+}
+
+int btg_unit_download_result(btg_unit *u, btg_genotype_result *out, void *stream) {
+    BTG_REQUIRE_INIT();
+    if (!u || !out) { set_error("null argument"); return BTG_EINVAL; }
+    if (out->n_variants != u->n_variants) { set_error("result sized for %llu variants, unit has %llu", (unsigned long long)out->n_variants, (unsigned long long)u->n_variants); return BTG_EINVAL; }
+    DevResult *dr = unit_result(u);
+    if (!dr) { set_error("result allocation failed"); return BTG_ENOMEM; }
+    const uint32_t S = u->du.S;
+    auto s = pick_stream(stream);
+    const ResultView &R = dr->R;
+#define BTG_DL(field, n) BTG_CUDA(cudaMemcpyAsync(out->field, R.field, (n) * sizeof(*R.field), cudaMemcpyDeviceToHost, s))
+    BTG_DL(gt, dr->nv * S * 2); BTG_DL(gq, dr->nv * S); BTG_DL(gpp, dr->ngen); BTG_DL(app, dr->nall);
+    BTG_DL(nak, dr->nall); BTG_DL(fak, dr->nall); BTG_DL(mac, dr->nall); BTG_DL(saf, dr->nall); BTG_DL(ploidy, dr->nv * S);
+    BTG_DL(an, dr->nv); BTG_DL(ac, dr->nalt); BTG_DL(af, dr->nalt); BTG_DL(acp, dr->nalt); BTG_DL(anc, dr->nalt); BTG_DL(hc, dr->nv);
+#undef BTG_DL
     BTG_CUDA(cudaStreamSynchronize(s));
     return BTG_OK;
 }
+
+int btg_estimate_genotypes(btg_unit *u, const btg_count_dist *cd, const btg_gibbs_opts *opts, btg_genotype_result *out) {
+    if (!out) { set_error("null argument"); return BTG_EINVAL; }
+    int rc = btg_estimate_genotypes_async(u, cd, opts, nullptr);
+    if (rc != BTG_OK) return rc;
+    return btg_unit_download_result(u, out, nullptr);
+}
+
+}  // extern "C"
+void btg_unit_free_result(btg_unit *u) {
+    if (u->res_view) { delete static_cast<DevResult *>(u->res_view); u->res_view = nullptr; }
+}
+extern "C" {
 
 int btg_unit_cluster_tally(const btg_unit *u, uint32_t cluster, uint32_t *tally_out, uint64_t n) {
     BTG_REQUIRE_INIT();
@@ -1046,17 +1116,12 @@ int btg_unit_cluster_tally(const btg_unit *u, uint32_t cluster, uint32_t *tally_
     const uint32_t H = u->h_nhap[cluster], S = u->du.S;
     const uint64_t need = (uint64_t)L.Dall * S;
     if (n < need) { set_error("tally buffer too small"); return BTG_EINVAL; }
-    // tally sits after obs[H], uniq[2*n_uniq], cnt[H*nvar] in the u32 slice (see Cl::bind)
-    uint64_t n_uniq = 0, nvar = 0;
-    {
-        std::vector<uint64_t> tmp(2);
-        BTG_CUDA(cudaMemcpy(tmp.data(), u->du.cl_uniq_off + cluster, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-        n_uniq = tmp[1] - tmp[0];
-        nvar = u->h_cl_var_off[cluster + 1] - u->h_cl_var_off[cluster];
-    }
-    const uint64_t off = L.u32_off + H + 2 * n_uniq + (uint64_t)H * nvar;
+    // tally sits after obs[H], uniq[2*n_uniq], cnt[H*nvar] in the slot's u32 arrays (see Cl::bind), lane-interleaved
+    (void)H;
+    const SlotLayout &SL = u->h_slots[L.pos >> 5];
+    const uint64_t off = SL.u32_off + (L.pos & 31u) + ((uint64_t)SL.H + 2ull * SL.n_uniq + (uint64_t)SL.H * SL.nvar) * 32;
     BTG_CUDA(cudaStreamSynchronize(ctx().stream));
-    BTG_CUDA(cudaMemcpy(tally_out, u->du.u32_pool + off, need * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    BTG_CUDA(cudaMemcpy2D(tally_out, sizeof(uint32_t), u->du.u32_pool + off, 32 * sizeof(uint32_t), sizeof(uint32_t), need, cudaMemcpyDeviceToHost));
     return BTG_OK;
 }
 

@@ -87,12 +87,13 @@ struct Philox {
         }
     }
     // persist / restore (noise modes run one iteration per launch)
-    __device__ __forceinline__ void save(uint32_t *p) const {
-        p[0] = c0; p[1] = c1; p[2] = b0; p[3] = b1; p[4] = b2; p[5] = b3; p[6] = pos; p[7] = c3;
+    // A: anything indexable (plain pointer or a lane-interleaved accessor)
+    template <class A> __device__ __forceinline__ void save(A p, uint32_t o) const {
+        p[o + 0] = c0; p[o + 1] = c1; p[o + 2] = b0; p[o + 3] = b1; p[o + 4] = b2; p[o + 5] = b3; p[o + 6] = pos; p[o + 7] = c3;
     }
-    __device__ __forceinline__ void load(const uint32_t *p, uint32_t seed, uint64_t group_index, uint32_t cluster_idx) {
+    template <class A> __device__ __forceinline__ void load(A p, uint32_t o, uint32_t seed, uint64_t group_index, uint32_t cluster_idx) {
         key0 = seed; key1 = (uint32_t)(group_index + 1); c2 = cluster_idx;
-        c0 = p[0]; c1 = p[1]; b0 = p[2]; b1 = p[3]; b2 = p[4]; b3 = p[5]; pos = p[6]; c3 = p[7];
+        c0 = p[o + 0]; c1 = p[o + 1]; b0 = p[o + 2]; b1 = p[o + 3]; b2 = p[o + 4]; b3 = p[o + 5]; pos = p[o + 6]; c3 = p[o + 7];
     }
 };
 

@@ -59,6 +59,8 @@ int btg_device_sm_count(void);
 void *btg_host_alloc(size_t bytes);
 void btg_host_free(void *p);
 /* number of kernel launches issued by this library since btg_init / last reset */
+/* the library's cudaStream_t (host entry points run on it), for callers that time with CUDA events */
+void *btg_get_stream(void);
 uint64_t btg_launch_count(void);
 void btg_launch_count_reset(void);
 
@@ -238,6 +240,10 @@ typedef struct btg_genotype_result {
 
 /* InferenceEngine::estimateGenotypes (InferenceEngine.cpp:278-382): default mode, fixed noise rates */
 int btg_estimate_genotypes(btg_unit *u, const btg_count_dist *cd, const btg_gibbs_opts *opts, btg_genotype_result *out);
+/* the same, split for callers that keep results on the device: launch on `stream` (NULL = library
+ * stream) without synchronising, then copy the result arrays out when needed */
+int btg_estimate_genotypes_async(btg_unit *u, const btg_count_dist *cd, const btg_gibbs_opts *opts, void *stream);
+int btg_unit_download_result(btg_unit *u, btg_genotype_result *out, void *stream);
 /* InferenceEngine::estimateNoise (InferenceEngine.cpp:135-276): updates cd's noise rates; trace_out (optional)
  * receives the <prefix>_noise_parameters.txt rows: [n_chains*(iters+1)+1][2+S] doubles (chain, iteration, rates..) */
 int btg_estimate_noise(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, double *trace_out);
