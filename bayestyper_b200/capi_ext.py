@@ -24,3 +24,8 @@ def bind(L):
     L.btg_estimate_genotypes_async.argtypes = [vp, vp, vp, vp]
     L.btg_unit_download_result.argtypes = [vp, vp, vp]
     L.btg_get_stream.restype = vp
+    L.btg_graphs_upload.restype = vp
+    L.btg_graphs_upload.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.btg_graphs_free.argtypes = [vp]
+    L.btg_find_sample_paths.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.btg_get_best_paths.argtypes = [vp, vp, vp, vp, C.c_uint64]

@@ -263,6 +263,15 @@ btg_bloom *alloc_bloom(uint64_t num_kmers, uint64_t num_bits) {
 
 }  // namespace
 
+namespace btg_internal {
+BloomView bloom_view(const btg_bloom *b) { return b->view(); }
+}  // namespace btg_internal
+
+// experiment hook: select the probe load flavour (see kmer.cuh)
+extern "C" __attribute__((visibility("default"))) int btg_debug_set_probe_mode(int mode) {
+    return cudaMemcpyToSymbol(g_probe_mode, &mode, sizeof(int)) == cudaSuccess ? 0 : -2;
+}
+
 extern "C" {
 
 btg_bloom *btg_bloom_create(uint64_t num_kmers_in, float fpr, int k) {

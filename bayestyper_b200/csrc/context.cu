@@ -1,4 +1,6 @@
 // context.cu — library lifecycle (btg_init / btg_shutdown / errors).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace btg {
@@ -43,6 +45,13 @@ int btg_init(int device) {
     }
     c.device = device;
     c.sm_count = prop.multiProcessorCount;
+    if (const char *g = getenv("BTG_L2_FETCH")) {  // experiment knob: DRAM fetch granularity of L2 misses (32/64/128 B)
+        size_t before = 0, after = 0;
+        cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+        cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "[btgpu] cudaLimitMaxL2FetchGranularity %zu -> %zu (%s)\n", before, after, cudaGetErrorString(e));
+    }
     BTG_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     BTG_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     c.ready = true;

@@ -20,6 +20,7 @@
 // btg_unit_upload rejects units that contain nested groups (explicit error, no fallback).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 #include <type_traits>
 #include <vector>
@@ -139,7 +140,7 @@ struct SlotLayout {
 };
 template <class T> struct LaneArr {
     T *p;
-    __device__ __forceinline__ T &operator[](size_t i) const { return p[i * 32]; }
+    __device__ __forceinline__ T &operator[](uint32_t i) const { return p[i * 32u]; }
     __device__ __forceinline__ LaneArr<T> operator+(size_t i) const { return LaneArr<T>{p + i * 32}; }
 };
 
@@ -170,15 +171,17 @@ struct DevUnit {
 };
 
 // arena sizes (elements) of one cluster — must match the pointer carving in Cl::bind
+constexpr uint32_t kSimplexTableMaxH = 32;
 struct ArenaSizes { uint64_t f64, u32, u8; };
 __host__ __device__ inline ArenaSizes arena_sizes(uint32_t S, uint32_t H, uint32_t K, uint32_t nvar, uint32_t n_uniq, uint32_t n_alleles, uint32_t Dall) {
     ArenaSizes a;
-    a.f64 = (uint64_t)H            /* freq */
-          + (H + 1)                /* simplex prob vector */
+    a.f64 = (uint64_t)H * 2        /* freq, log(freq) */
+          + (H + 1)                /* simplex prob vector (H > kSimplexTableMaxH: most recent key only) */
+          + (H <= kSimplexTableMaxH ? (uint64_t)H * (H + 1) : 0) /* else: one vector per plus-count, + lengths */
           + (uint64_t)S * Dall     /* unique diplotype log-prob cache */
           + Dall                   /* cumulative log-probs of one draw */
           + (uint64_t)S * 2 * nvar * 2   /* k-mer stats cache (fraction, mean) */
-          + (uint64_t)n_alleles * S * 6  /* allele k-mer stats: 3 x (fraction, mean) */
+          + (uint64_t)n_alleles * S * 3  /* allele k-mer stats: 3 sums (count, fraction, mean) */
           + 2;                     /* sparsity, spare */
     a.u32 = (uint64_t)H            /* observation counts */
           + n_uniq * 2ull          /* unique k-mer order, subset */
@@ -198,10 +201,11 @@ enum Misc { kNSub = 0, kNumHap = 1, kNumMissing = 2, kSimplexNobs = 3, kSimplexP
 // per-cluster view
 struct Cl {
     uint32_t S, H, K, nvar, n_uniq, Dall, n_alleles, c, g;
+    bool has_simplex_tab;
     uint64_t row0, var0;
     const DevUnit *u;
     const uint8_t *M;
-    LaneArr<double> freq, simplex, ucache, cum, kc_f, as_f, fmisc;
+    LaneArr<double> freq, logf, simplex, simplex_tab, ucache, cum, kc_f, as_f, fmisc;
     LaneArr<uint32_t> obs, uniq, uniq_sub, cnt, tally, kc_n, as_n, dipl, misc;
     LaneArr<uint8_t> nz, uncovered, stats_update;
 
@@ -223,11 +227,14 @@ struct Cl {
         const uint32_t lane = L.pos & 31u;
         LaneArr<double> f{du.f64_pool + SL.f64_off + lane};
         freq = f; f = f + SL.H;
+        logf = f; f = f + SL.H;
         simplex = f; f = f + (SL.H + 1);
+        has_simplex_tab = SL.H <= kSimplexTableMaxH;
+        simplex_tab = f; f = f + (has_simplex_tab ? (uint64_t)SL.H * (SL.H + 1) : 0);
         ucache = f; f = f + (uint64_t)S * SL.Dall;
         cum = f; f = f + SL.Dall;
         kc_f = f; f = f + (uint64_t)S * 2 * SL.nvar * 2;
-        as_f = f; f = f + (uint64_t)SL.n_alleles * S * 6;
+        as_f = f; f = f + (uint64_t)SL.n_alleles * S * 3;
         fmisc = f;
         LaneArr<uint32_t> w{du.u32_pool + SL.u32_off + lane};
         obs = w; w = w + SL.H;
@@ -263,12 +270,15 @@ struct Cl {
     }
 };
 
-// KmerStats::addValue without M2 (KmerStats.cpp:51-63); M2 is never read on this path
-__device__ __forceinline__ void kstat_add(uint32_t &n, double &fraction, double &mean, double v) {
+// KmerStats (KmerStats.cpp:51-63) keeps Welford running means; only the means (count, fraction of non-zero,
+// mean) are ever read on this path, so the kernel keeps plain sums and divides once when a value is consumed
+// (two f64 divisions per addValue become one addition; the quotient differs from Welford's by rounding only).
+// k-mer stats cache entry: kc_n = #values, kc_f[2i] = #non-zero values -> fraction, kc_f[2i+1] = sum -> mean
+// (both finalised in place after a cache rebuild); allele stats entry: as_n = #values, as_f = sum.
+__device__ __forceinline__ void kc_add(uint32_t &n, double &nonzero, double &sum, double v) {
     n++;
-    fraction += ((doubleCompare(v, 0) ? 0.0 : 1.0) - fraction) / n;
-    const double delta = v - mean;
-    mean += delta / n;
+    nonzero += v != 0.0 ? 1.0 : 0.0;
+    sum += v;
 }
 
 struct Tables {
@@ -292,7 +302,7 @@ __device__ void cl_construct(Cl &cl, const btg_gibbs_opts &o, uint64_t group_ind
     for (uint32_t i = 0; i < cl.Dall * S; i++) cl.tally[i] = 0;
     for (uint32_t s = 0; s < S; s++) { cl.dipl[s] = 0xFFFFFFFFu; cl.stats_update[s] = 1; }
     for (uint32_t i = 0; i < S * 2 * cl.nvar; i++) { cl.kc_n[i] = 0; cl.kc_f[2 * i] = 0; cl.kc_f[2 * i + 1] = 0; }
-    for (uint32_t i = 0; i < cl.n_alleles * S * 3; i++) { cl.as_n[i] = 0; cl.as_f[2 * i] = 0; cl.as_f[2 * i + 1] = 0; }
+    for (uint32_t i = 0; i < cl.n_alleles * S * 3; i++) { cl.as_n[i] = 0; cl.as_f[i] = 0; }
     for (int i = 0; i < 8; i++) cl.misc[i] = 0;
     cl.misc[kSimplexNobs] = 0xFFFFFFFFu;
     // SparsityEstimator::estimateMinimumColumnCover (SparsityEstimator.cpp:41-90), stream kind 1
@@ -364,10 +374,10 @@ __device__ void cl_reset(Cl &cl, const btg_gibbs_opts &o, Philox &prng) {
 
 // VariantClusterGenotyper::calcDiplotypeLogProb (VariantClusterGenotyper.cpp:597-666)
 __device__ double cl_dipl_log_prob(Cl &cl, const Tables &T, uint32_t s, uint32_t a, uint32_t b) {
-    double lp = 0;
-    if (b == NONE) lp += log(cl.freq[a]);
-    else if (a == b) lp += 2 * log(cl.freq[a]);
-    else lp += log(2.0) + log(cl.freq[a]) + log(cl.freq[b]);
+    double lp = 0;  // logf[] = log(freq[]) of this iteration (cl_sample_diplotypes)
+    if (b == NONE) lp += cl.logf[a];
+    else if (a == b) lp += 2 * cl.logf[a];
+    else lp += 0.6931471805599453 + cl.logf[a] + cl.logf[b];
     const size_t ci = (size_t)s * cl.Dall + cl.slot(a, b == NONE ? cl.H : b);
     double acc = cl.ucache[ci];
     if (acc != acc) {  // not cached yet
@@ -452,10 +462,10 @@ __device__ void cl_add_haplotype_stats(Cl &cl, uint32_t s, uint32_t which, uint3
         const uint32_t n = cl.kc_n[ci];
         const uint32_t ai = cl.alleleBase(v, s) + a;
         // AlleleKmerStats::addKmerStats (KmerStats.cpp:115-122): count, fraction (if any), mean (if any)
-        kstat_add(cl.as_n[ai * 3 + 0], cl.as_f[(ai * 3 + 0) * 2], cl.as_f[(ai * 3 + 0) * 2 + 1], (double)n);
+        cl.as_n[ai * 3 + 0]++; cl.as_f[ai * 3 + 0] += (double)n;
         if (n > 0) {
-            kstat_add(cl.as_n[ai * 3 + 1], cl.as_f[(ai * 3 + 1) * 2], cl.as_f[(ai * 3 + 1) * 2 + 1], cl.kc_f[2 * ci]);
-            kstat_add(cl.as_n[ai * 3 + 2], cl.as_f[(ai * 3 + 2) * 2], cl.as_f[(ai * 3 + 2) * 2 + 1], cl.kc_f[2 * ci + 1]);
+            cl.as_n[ai * 3 + 1]++; cl.as_f[ai * 3 + 1] += cl.kc_f[2 * ci];      // getFraction()
+            cl.as_n[ai * 3 + 2]++; cl.as_f[ai * 3 + 2] += cl.kc_f[2 * ci + 1];  // getMean()
         }
     }
 }
@@ -479,10 +489,15 @@ __device__ void cl_update_allele_stats(Cl &cl) {
                     for (uint64_t e = u.kmer_vh_off[cl.row0 + k]; e < u.kmer_vh_off[cl.row0 + k + 1]; e++) {
                         const uint32_t v = u.vh_var[e];
                         const uint8_t *bits = u.vh_bits + u.vh_bits_off[e];
-                        if (bits[da]) { const uint32_t ci = (s * 2 + 0) * cl.nvar + v; kstat_add(cl.kc_n[ci], cl.kc_f[2 * ci], cl.kc_f[2 * ci + 1], kc); }
-                        if (db != NONE && bits[db]) { const uint32_t ci = (s * 2 + 1) * cl.nvar + v; kstat_add(cl.kc_n[ci], cl.kc_f[2 * ci], cl.kc_f[2 * ci + 1], kc); }
+                        if (bits[da]) { const uint32_t ci = (s * 2 + 0) * cl.nvar + v; kc_add(cl.kc_n[ci], cl.kc_f[2 * ci], cl.kc_f[2 * ci + 1], kc); }
+                        if (db != NONE && bits[db]) { const uint32_t ci = (s * 2 + 1) * cl.nvar + v; kc_add(cl.kc_n[ci], cl.kc_f[2 * ci], cl.kc_f[2 * ci + 1], kc); }
                     }
                 }
+            }
+            // finalise: (#non-zero, sum) -> (fraction, mean)
+            for (uint32_t i = s * 2 * cl.nvar; i < (s + 1) * 2 * cl.nvar; i++) {
+                const uint32_t n = cl.kc_n[i];
+                if (n) { cl.kc_f[2 * i] = cl.kc_f[2 * i] / n; cl.kc_f[2 * i + 1] = cl.kc_f[2 * i + 1] / n; }
             }
         }
         if (da != NONE) cl_add_haplotype_stats(cl, s, 0, da);
@@ -492,6 +507,7 @@ __device__ void cl_update_allele_stats(Cl &cl) {
 
 // VariantClusterGenotyper::sampleDiplotypes (VariantClusterGenotyper.cpp:668-705)
 __device__ void cl_sample_diplotypes(Cl &cl, const Tables &T, const uint8_t *ploidy, bool collect, Philox &prng) {
+    for (uint32_t h = 0; h < cl.H; h++) if (cl.nz[h]) cl.logf[h] = log(cl.freq[h]);  // one log per haplotype per iteration
     for (uint32_t s = 0; s < cl.S; s++) {
         const uint32_t prev = cl.dipl[s];
         cl_sample_diplotype(cl, T, s, ploidy[s], prng);
@@ -506,7 +522,7 @@ __device__ void cl_sample_diplotypes(Cl &cl, const Tables &T, const uint8_t *plo
 
 // SparseFrequencyDistribution::updateCachedSimplexProbVector (FrequencyDistribution.cpp:143-196);
 // lgamma of the integer arguments comes from a table shared by all clusters
-__device__ uint32_t cl_simplex_vector(Cl &cl, uint32_t n_obs, uint32_t plus) {
+__device__ uint32_t cl_simplex_vector(Cl &cl, LaneArr<double> out, uint32_t n_obs, uint32_t plus) {
     const double *lg = cl.u->lgamma_int;
     const uint32_t H = cl.H;
     const double sparsity = cl.fmisc[0];
@@ -515,17 +531,17 @@ __device__ uint32_t cl_simplex_vector(Cl &cl, uint32_t n_obs, uint32_t plus) {
     double prob_t = lg[plus] - lg[n_obs + plus];
     double row_sum = 0 + prob_z + prob_t;
     uint32_t len = 0;
-    cl.simplex[len++] = row_sum;
+    out[len++] = row_sum;
     for (uint32_t j = plus + 1; j < H + 1; j++) {
         const double cardinal = lg[H - plus + 1] - (lg[j - plus + 1] + lg[H - j + 1]);
         prob_z = j * ls + (H - j) * l1s;
         prob_t = lg[j] - lg[n_obs + j];
         const double prob_eq = cardinal + prob_z + prob_t;
         row_sum += log(1 + exp(prob_eq - row_sum));
-        cl.simplex[len++] = row_sum;
-        if (doubleCompare(cl.simplex[len - 1], cl.simplex[len - 2])) break;
+        out[len++] = row_sum;
+        if (doubleCompare(out[len - 1], out[len - 2])) break;
     }
-    for (uint32_t i = 0; i < len; i++) cl.simplex[i] = exp(cl.simplex[i] - row_sum);
+    for (uint32_t i = 0; i < len; i++) out[i] = exp(out[i] - row_sum);
     return len;
 }
 
@@ -542,15 +558,30 @@ __device__ void cl_sample_frequencies(Cl &cl, Philox &fr) {
         } else {
             uint32_t plus = 0;
             for (uint32_t h = 0; h < H; h++) plus += cl.obs[h] > 0;
-            if (cl.misc[kSimplexNobs] != n_obs || cl.misc[kSimplexPlus] != plus) {
-                cl.misc[kSimplexLen] = cl_simplex_vector(cl, n_obs, plus);
-                cl.misc[kSimplexNobs] = n_obs;
-                cl.misc[kSimplexPlus] = plus;
+            // cached_simplex_prob_vectors (FrequencyDistribution.cpp:211-229): one vector per (n_obs, plus).  Small
+            // clusters keep a row per plus-count for the current n_obs; large ones only the most recent key.
+            LaneArr<double> vec = cl.simplex;
+            uint32_t len;
+            if (cl.has_simplex_tab) {
+                if (cl.misc[kSimplexNobs] != n_obs) {
+                    for (uint32_t p = 0; p < H; p++) cl.simplex_tab[p * (H + 1)] = 0;
+                    cl.misc[kSimplexNobs] = n_obs;
+                }
+                LaneArr<double> row = cl.simplex_tab + (size_t)(plus - 1) * (H + 1);
+                len = (uint32_t)row[0];
+                if (len == 0) { len = cl_simplex_vector(cl, row + 1, n_obs, plus); row[0] = (double)len; }
+                vec = row + 1;
+            } else {
+                if (cl.misc[kSimplexNobs] != n_obs || cl.misc[kSimplexPlus] != plus) {
+                    cl.misc[kSimplexLen] = cl_simplex_vector(cl, cl.simplex, n_obs, plus);
+                    cl.misc[kSimplexNobs] = n_obs;
+                    cl.misc[kSimplexPlus] = plus;
+                }
+                len = cl.misc[kSimplexLen];
             }
-            const uint32_t len = cl.misc[kSimplexLen];
             const double uu = fr.u01();
             uint32_t ub = 0;
-            while (ub < len && !(uu < cl.simplex[ub])) ub++;  // upper_bound
+            while (ub < len && !(uu < vec[ub])) ub++;  // upper_bound
             const uint32_t simplex_size = ub + plus;
             double norm = 0;
             // observed haplotypes, ascending index; nz[] marks membership of the (growing) plus set
@@ -641,9 +672,9 @@ __device__ void cl_summarise(Cl &cl, const btg_gibbs_opts &o, const uint8_t *plo
             const uint32_t ai0 = cl.alleleBase(v, s);
             for (uint32_t a = 0; a < nA; a++) {
                 const uint32_t ai = ai0 + a;
-                nak[a] = cl.as_n[ai * 3 + 0] ? (float)cl.as_f[(ai * 3 + 0) * 2 + 1] : -1.f;
-                fak[a] = cl.as_n[ai * 3 + 1] ? (float)cl.as_f[(ai * 3 + 1) * 2 + 1] : -1.f;
-                mac[a] = cl.as_n[ai * 3 + 2] ? (float)cl.as_f[(ai * 3 + 2) * 2 + 1] : -1.f;
+                nak[a] = cl.as_n[ai * 3 + 0] ? (float)(cl.as_f[ai * 3 + 0] / cl.as_n[ai * 3 + 0]) : -1.f;
+                fak[a] = cl.as_n[ai * 3 + 1] ? (float)(cl.as_f[ai * 3 + 1] / cl.as_n[ai * 3 + 1]) : -1.f;
+                mac[a] = cl.as_n[ai * 3 + 2] ? (float)(cl.as_f[ai * 3 + 2] / cl.as_n[ai * 3 + 2]) : -1.f;
             }
             for (uint32_t a = 0; a < n_all; a++) {
                 if (!floatCompare(app[a], 0)) {
@@ -678,7 +709,8 @@ __device__ void cl_summarise(Cl &cl, const btg_gibbs_opts &o, const uint8_t *plo
 }
 
 // InferenceEngine::estimateGenotypesCallback (InferenceEngine.cpp:278-333): one thread = one group, all chains
-__global__ void __launch_bounds__(64) k_estimate_genotypes(DevUnit du, Tables T, btg_gibbs_opts o, ResultView R) {
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(64, MIN_BLOCKS) k_estimate_genotypes(DevUnit du, Tables T, btg_gibbs_opts o, ResultView R) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= du.C) return;
     Cl cl;
@@ -1071,7 +1103,11 @@ int btg_estimate_genotypes_async(btg_unit *u, const btg_count_dist *cd, const bt
     if (!dr) { set_error("result allocation failed"); return BTG_ENOMEM; }
     Tables T{cd->genomic, cd->noise};
     if (u->du.C) {
-        k_estimate_genotypes<<<(u->du.C + 63) / 64, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R);
+        static const int occ = getenv("BTG_GIBBS_OCC") ? atoi(getenv("BTG_GIBBS_OCC")) : 8;
+        const unsigned grid = (u->du.C + 63) / 64;
+        if (occ >= 16) k_estimate_genotypes<16><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R);
+        else if (occ >= 12) k_estimate_genotypes<12><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R);
+        else k_estimate_genotypes<8><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R);
         BTG_LAUNCHED();
         BTG_CUDA(cudaGetLastError());
     }

@@ -46,9 +46,20 @@ BTG_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
     return (uint64_t)(((unsigned __int128)a * b) >> 64);
 #endif
 }
+#ifdef __CUDACC__
+// experiment knob (BTG_PROBE_MODE): which load flavour the single-byte Bloom probes use
+__device__ int g_probe_mode = 0;
+#endif
 BTG_HD uint8_t load_byte(const uint8_t *p) {
 #ifdef __CUDA_ARCH__
-    return __ldg(p);
+    unsigned v;
+    switch (g_probe_mode) {
+        case 1: asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(p)); return (uint8_t)v;
+        case 2: asm volatile("ld.global.ca.u8 %0, [%1];" : "=r"(v) : "l"(p)); return (uint8_t)v;
+        case 3: asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p)); return (uint8_t)v;
+        case 4: asm volatile("ld.global.cv.u8 %0, [%1];" : "=r"(v) : "l"(p)); return (uint8_t)v;
+        default: return __ldg(p);
+    }
 #else
     return *p;
 #endif

@@ -1,0 +1,582 @@
+// paths.cu — per-(cluster, sample) candidate-path search on the device.
+//
+// Replaces VariantClusterGraph::findSamplePaths + mergePaths / isPathsRedundant / filterPaths / addPathIndices
+// (src/bayesTyper/VariantClusterGraph.cpp:389-798), VariantClusterGraphPath::{addVertex,updateScore,getKmerScore,
+// getVertexScore,updateObservedCoveredVertices} (src/bayesTyper/VariantClusterGraphPath.cpp:46-225) and the driver
+// KmerCounter::findVariantClusterPaths (src/bayesTyper/KmerCounter.cpp:59-103).
+//
+// The north star asks for BIT-EXACT path enumeration, and the reference's result depends on the order in which
+// std::shuffle (libstdc++ 13: pairwise swaps drawn with Lemire's method from std::mt19937) leaves the candidate
+// paths before the greedy filter.  The kernel therefore carries a real mt19937 and the exact libstdc++ shuffle.
+//
+// Mapping: clusters are independent; one thread walks one cluster's vertex DP for the current sample (the
+// algorithm is a sequential dynamic programme over vertices), rolling each path's k-mer + ntHash incrementally
+// (kmer.cuh Roller) and probing the sample's Bloom filter in HBM for every completed k-mer.  Per-thread state
+// (path slots, lists, Mersenne state) lives in a scratch arena sized per cluster on the host.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "kmer.cuh"
+
+using namespace btg;
+
+struct btg_bloom;
+namespace btg_internal {
+BloomView bloom_view(const btg_bloom *b);  // bloom.cu
+}
+
+namespace {
+
+constexpr uint8_t kMinObserved = 2;   // min_observed_kmers (VariantClusterGraphPath.cpp:36)
+constexpr uint32_t kMinSamplePaths = 1;  // min_num_sample_paths (VariantClusterGraph.cpp:60)
+constexpr uint8_t kAbsent = 0xFF;
+
+struct DevGraphs {
+    uint32_t C;
+    const uint64_t *cl_vertex_off;  // [C+1]
+    const uint64_t *v_seq_off;      // [V+1]
+    const uint8_t *seq;             // nucleotide codes 0..3
+    const uint8_t *v_flags;         // bit0 is_first_nucleotides_redundant, bit1 is_disconnected
+    const uint64_t *v_in_off;       // [V+1]
+    const uint32_t *v_in_src;       // local ids, in_edges order
+    const uint32_t *v_max_target;   // [V] max(v, targets of v)   (visited_vertices, VariantClusterGraph.cpp:462-476)
+    const uint32_t *cl_group;       // group index of the cluster (seed)
+    const uint32_t *cl_idx;         // variant_cluster_idx within the group (seed)
+    // scratch layout per cluster
+    const uint64_t *scr_off;        // [C+1] byte offsets into scratch
+    const uint32_t *cl_pool;        // [C] number of path slots
+    const uint32_t *cl_tmp;         // [C] capacity of the merge list
+    uint8_t *scratch;
+    // results: best paths per cluster, merged over samples (best_paths_indices)
+    const uint64_t *best_off;       // [C+1] byte offsets into best (capacity rows x V bytes)
+    const uint32_t *best_cap;       // [C] capacity in paths
+    uint32_t *best_n;               // [C] current number of best paths
+    uint8_t *best;                  // path x vertex membership bytes
+    uint32_t *status;               // [C] 0 ok, 1 scratch overflow
+};
+
+// ---- std::mt19937 -------------------------------------------------------------------------------
+struct Mt19937 {
+    uint32_t *mt;  // [624]
+    uint32_t idx;
+    __device__ void seed(uint32_t s) {
+        mt[0] = s;
+        for (uint32_t i = 1; i < 624; i++) { s = 1812433253u * (s ^ (s >> 30)) + i; mt[i] = s; }
+        idx = 624;
+    }
+    __device__ void twist() {
+        for (uint32_t i = 0; i < 624; i++) {
+            const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+            mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        idx = 0;
+    }
+    __device__ uint32_t next() {
+        if (idx >= 624) twist();
+        uint32_t y = mt[idx++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+    // libstdc++ uniform_int_distribution<unsigned long>{0, range-1} on a 32-bit engine: Lemire (uniform_int_dist.h:250-274)
+    __device__ uint32_t below(uint32_t range) {
+        uint64_t product = (uint64_t)next() * range;
+        uint32_t low = (uint32_t)product;
+        if (low < range) {
+            const uint32_t threshold = (0u - range) % range;
+            while (low < threshold) { product = (uint64_t)next() * range; low = (uint32_t)product; }
+        }
+        return (uint32_t)(product >> 32);
+    }
+};
+
+// libstdc++ 13 std::shuffle (stl_algo.h): two swap positions per engine call
+__device__ void std_shuffle(uint16_t *a, uint32_t n, Mt19937 &g) {
+    if (n == 0) return;
+    uint32_t i = 1;
+    if ((n % 2) == 0) {
+        const uint32_t j = g.below(2);
+        const uint16_t t = a[i]; a[i] = a[j]; a[j] = t;
+        i++;
+    }
+    while (i != n) {
+        const uint32_t swap_range = i + 1;
+        const uint32_t x = g.below(swap_range * (swap_range + 1));  // __gen_two_uniform_ints(b0, b1): {x / b1, x % b1}
+        const uint32_t p0 = x / (swap_range + 1), p1 = x % (swap_range + 1);
+        uint16_t t = a[i]; a[i] = a[p0]; a[p0] = t; i++;
+        t = a[i]; a[i] = a[p1]; a[p1] = t; i++;
+    }
+}
+
+// ---- one cluster's working set -------------------------------------------------------------------
+struct PathHdr {        // 64 bytes, followed by V bytes of per-vertex state (kAbsent or num_observed_kmers 0..2)
+    uint64_t fhi, flo, rhi, rlo, F, R;
+    uint32_t filled, score_first, score_second, nverts;
+};
+
+struct Work {
+    const DevGraphs *g;
+    uint32_t c, V;
+    uint64_t v0;
+    uint32_t slot_bytes, pool, tmp_cap;
+    uint8_t *slots;       // pool x slot_bytes
+    uint16_t *lists;      // V x 32 slot ids
+    uint8_t *list_n;      // V
+    uint16_t *tmp;        // merge list
+    uint16_t *free_stack; // pool
+    uint32_t n_free;
+    uint8_t *covered;     // V (filterPaths' observed_covered_vertices)
+    uint32_t *mt;         // 624
+    bool overflow;
+
+    __device__ PathHdr *hdr(uint32_t s) const { return reinterpret_cast<PathHdr *>(slots + (size_t)s * slot_bytes); }
+    __device__ uint8_t *verts(uint32_t s) const { return slots + (size_t)s * slot_bytes + sizeof(PathHdr); }
+    __device__ uint32_t alloc() {
+        if (n_free == 0) { overflow = true; return 0; }
+        return free_stack[--n_free];
+    }
+    __device__ void release(uint32_t s) { free_stack[n_free++] = (uint16_t)s; }
+    __device__ uint32_t seq_len(uint32_t v) const { return (uint32_t)(g->v_seq_off[v0 + v + 1] - g->v_seq_off[v0 + v]); }
+    __device__ const uint8_t *seq(uint32_t v) const { return g->seq + g->v_seq_off[v0 + v]; }
+    __device__ bool disconnected(uint32_t v) const { return g->v_flags[v0 + v] & 2; }
+    __device__ bool first_redundant(uint32_t v) const { return g->v_flags[v0 + v] & 1; }
+};
+
+__device__ void copy_slot(Work &w, uint32_t dst, uint32_t src) {
+    const uint64_t *s = reinterpret_cast<const uint64_t *>(w.slots + (size_t)src * w.slot_bytes);
+    uint64_t *d = reinterpret_cast<uint64_t *>(w.slots + (size_t)dst * w.slot_bytes);
+    for (uint32_t i = 0; i < w.slot_bytes / 8; i++) d[i] = s[i];
+}
+
+// previous vertex of a path strictly below `v` (paths hold ascending vertex indices); V = none
+__device__ __forceinline__ uint32_t prev_vertex(const uint8_t *pv, uint32_t v) {
+    while (v > 0) { v--; if (pv[v] != kAbsent) return v; }
+    return 0xFFFFFFFFu;
+}
+__device__ __forceinline__ uint32_t last_vertex(const uint8_t *pv, uint32_t V) { return prev_vertex(pv, V); }
+
+// VariantClusterGraph::isPathsRedundant (VariantClusterGraph.cpp:534-629): both paths spell the same sequence with
+// disconnections at the same places, compared from the back
+__device__ bool paths_redundant(const Work &w, const uint8_t *p1, const uint8_t *p2) {
+    uint32_t v1 = last_vertex(p1, w.V), v2 = last_vertex(p2, w.V);
+    int64_t i1 = (int64_t)w.seq_len(v1) - 1, i2 = (int64_t)w.seq_len(v2) - 1;  // index of the next nucleotide to compare, -1 = vertex exhausted
+    bool d1 = false, d2 = false;
+    const uint32_t END = 0xFFFFFFFFu;
+    while (true) {
+        while (i1 < 0) {
+            if (w.disconnected(v1)) d1 = true;
+            v1 = prev_vertex(p1, v1);
+            if (v1 != END) i1 = (int64_t)w.seq_len(v1) - 1; else break;
+        }
+        while (i2 < 0) {
+            if (w.disconnected(v2)) d2 = true;
+            v2 = prev_vertex(p2, v2);
+            if (v2 != END) i2 = (int64_t)w.seq_len(v2) - 1; else break;
+        }
+        if (d1 != d2) return false;
+        d1 = d2 = false;
+        if (v1 == END || v2 == END) break;
+        if (v1 == v2 && i1 == i2) { i1 = -1; i2 = -1; }  // same vertex, same offset: identical from here to its start
+        const uint8_t *s1 = w.seq(v1), *s2 = w.seq(v2);
+        while (i1 >= 0 && i2 >= 0) {
+            if (s1[i1] != s2[i2]) return false;
+            i1--; i2--;
+        }
+    }
+    return v1 == END && v2 == END;
+}
+
+// VariantClusterGraph::mergePaths (VariantClusterGraph.cpp:484-532).  Paths are always copied into fresh slots;
+// a source list is released after its last consumer (the reference moves instead of copying there: same result).
+__device__ void merge_paths(Work &w, uint32_t &n_main, const uint16_t *input, uint32_t n_in) {
+    const uint32_t main_size = n_main;
+    for (uint32_t i = 0; i < n_in && !w.overflow; i++) {
+        const uint32_t in_slot = input[i];
+        const uint8_t *pin = w.verts(in_slot);
+        bool redundant = false;
+        for (uint32_t m = 0; m < main_size; m++) {
+            const uint32_t ms = w.tmp[m];
+            if (paths_redundant(w, w.verts(ms), pin)) {
+                if (w.hdr(ms)->nverts < w.hdr(in_slot)->nverts) copy_slot(w, ms, in_slot);  // keep the longer vertex list
+                redundant = true;
+                break;
+            }
+        }
+        if (!redundant) {
+            if (n_main >= w.tmp_cap) { w.overflow = true; return; }
+            const uint32_t s = w.alloc();
+            if (w.overflow) return;
+            copy_slot(w, s, in_slot);
+            w.tmp[n_main++] = (uint16_t)s;
+        }
+    }
+}
+
+// VariantClusterGraphPath::updateScore (VariantClusterGraphPath.cpp:89-130)
+__device__ void update_score(Work &w, PathHdr *h, uint8_t *pv, uint32_t cur_vertex, bool observed, uint32_t cur_len) {
+    if (observed) {
+        h->score_first++;
+        uint32_t v = cur_vertex;
+        if (cur_len > 1 || !w.first_redundant(v)) if (pv[v] < kMinObserved) pv[v]++;
+        v = prev_vertex(pv, v);
+        while (v != 0xFFFFFFFFu) {
+            if ((uint32_t)K <= cur_len || pv[v] == kMinObserved) break;
+            if (pv[v] < kMinObserved) pv[v]++;
+            cur_len += w.seq_len(v);
+            v = prev_vertex(pv, v);
+        }
+    }
+    h->score_second++;
+}
+
+// VariantClusterGraphPath::addVertex (VariantClusterGraphPath.cpp:46-87)
+__device__ void add_vertex(Work &w, uint32_t slot, uint32_t v, const BloomView &bloom) {
+    PathHdr *h = w.hdr(slot);
+    uint8_t *pv = w.verts(slot);
+    pv[v] = 0;
+    h->nverts++;
+    Roller r;
+    r.f.hi = h->fhi; r.f.lo = h->flo; r.r.hi = h->rhi; r.r.lo = h->rlo; r.F = h->F; r.R = h->R; r.filled = (int)h->filled;
+    const uint32_t len = w.seq_len(v);
+    if (w.disconnected(v)) {
+        if (len == 0) pv[v] = kMinObserved;
+        r.reset();
+    }
+    const uint8_t *s = w.seq(v);
+    for (uint32_t i = 0; i < len; i++) {
+        if (r.push(s[i])) update_score(w, h, pv, v, bloom_contains(bloom, r.canonical_hash()), i + 1);
+    }
+    h->fhi = r.f.hi; h->flo = r.f.lo; h->rhi = r.r.hi; h->rlo = r.r.lo; h->F = r.F; h->R = r.R; h->filled = (uint32_t)r.filled;
+}
+
+__device__ __forceinline__ double kmer_score(const PathHdr *h) {  // getKmerScore (…GraphPath.cpp:137-149)
+    return h->score_second > 0 ? h->score_first / static_cast<double>(h->score_second) : 1.0;
+}
+__host__ __device__ inline bool dbl_compare(double a, double b) {  // Utils.hpp:81-87
+    return (a == b) || (fabs(a - b) < fabs(a < b ? a : b) * 2.220446049250313e-16 * 100);
+}
+
+// getVertexScore / updateObservedCoveredVertices (…GraphPath.cpp:151-225)
+__device__ uint32_t vertex_score(const Work &w, const uint8_t *pv, bool is_complete) {
+    uint32_t score = 0;
+    for (uint32_t v = 0; v < w.V; v++) if (pv[v] == kMinObserved && !w.covered[v]) score++;
+    if (!is_complete) {
+        uint32_t v = last_vertex(pv, w.V), cur_len = 0;
+        while (v != 0xFFFFFFFFu) {
+            if ((uint32_t)(K - 1) <= cur_len || pv[v] == kMinObserved) break;
+            if (!w.covered[v]) score++;
+            cur_len += w.seq_len(v);
+            v = prev_vertex(pv, v);
+        }
+    }
+    return score;
+}
+__device__ void update_covered(Work &w, const uint8_t *pv, bool is_complete) {
+    for (uint32_t v = 0; v < w.V; v++) if (pv[v] == kMinObserved) w.covered[v] = 1;
+    if (!is_complete) {
+        uint32_t v = last_vertex(pv, w.V), cur_len = 0;
+        while (v != 0xFFFFFFFFu) {
+            if ((uint32_t)(K - 1) <= cur_len || pv[v] == kMinObserved) break;
+            w.covered[v] = 1;
+            cur_len += w.seq_len(v);
+            v = prev_vertex(pv, v);
+        }
+    }
+}
+
+// VariantClusterGraph::filterPaths (VariantClusterGraph.cpp:631-724): greedy selection in place; returns new size
+__device__ uint32_t filter_paths(Work &w, uint16_t *paths, uint32_t n, uint32_t max_paths, bool is_complete) {
+    if (!((n > max_paths) || (is_complete && n > kMinSamplePaths))) return n;
+    bool first_pass = true;
+    for (uint32_t v = 0; v < w.V; v++) w.covered[v] = 0;
+    uint32_t sorted_end = 0;
+    while (sorted_end != n) {
+        uint32_t best = sorted_end;
+        double best_k = kmer_score(w.hdr(paths[best]));
+        uint32_t best_v = vertex_score(w, w.verts(paths[best]), is_complete);
+        for (uint32_t i = sorted_end + 1; i < n; i++) {
+            const double ck = kmer_score(w.hdr(paths[i]));
+            const uint32_t cv = vertex_score(w, w.verts(paths[i]), is_complete);
+            if (first_pass) {
+                if (cv > 0) {
+                    if ((dbl_compare(ck, best_k) && cv > best_v) || ck > best_k || best_v == 0) { best = i; best_k = ck; best_v = cv; }
+                }
+            } else if (!is_complete || cv == w.hdr(paths[i])->nverts) {
+                if (ck > best_k) { best = i; best_k = ck; best_v = cv; }
+            }
+        }
+        if (first_pass) {
+            update_covered(w, w.verts(paths[best]), is_complete);
+        } else if (is_complete && sorted_end >= kMinSamplePaths && best_v < w.hdr(paths[best])->nverts) {
+            break;
+        }
+        if (sorted_end != best) { const uint16_t t = paths[sorted_end]; paths[sorted_end] = paths[best]; paths[best] = t; }
+        if (first_pass && best_v == 0) {
+            first_pass = false;
+            for (uint32_t v = 0; v < w.V; v++) w.covered[v] = 0;
+        } else {
+            sorted_end++;
+            if (sorted_end == max_paths) break;
+        }
+    }
+    for (uint32_t i = sorted_end; i < n; i++) w.release(paths[i]);
+    return sorted_end;
+}
+
+// redundancy between a stored best path (row of membership bytes) and a sample path: same predicate, the row
+// only needs != kAbsent semantics, which paths_redundant uses
+// VariantClusterGraph::addPathIndices (VariantClusterGraph.cpp:726-798)
+__device__ void add_path_indices(Work &w, const uint16_t *paths, uint32_t n) {
+    const DevGraphs &g = *w.g;
+    uint8_t *best = g.best + g.best_off[w.c];
+    uint32_t n_best = g.best_n[w.c];
+    const uint32_t cap = g.best_cap[w.c];
+    uint32_t redundant_mask_lo = 0;  // n <= 32
+    for (uint32_t b = 0; b < n_best; b++) {
+        uint8_t *row = best + (size_t)b * w.V;
+        uint32_t row_n = 0;
+        for (uint32_t v = 0; v < w.V; v++) row_n += row[v] != kAbsent;
+        for (uint32_t i = 0; i < n; i++) {
+            if (redundant_mask_lo & (1u << i)) continue;
+            const uint8_t *pv = w.verts(paths[i]);
+            if (paths_redundant(w, row, pv)) {
+                if (row_n < w.hdr(paths[i])->nverts)
+                    for (uint32_t v = 0; v < w.V; v++) row[v] = pv[v] != kAbsent ? 0 : kAbsent;
+                redundant_mask_lo |= 1u << i;
+                break;
+            }
+        }
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        if (!(redundant_mask_lo & (1u << i))) {
+            if (n_best >= cap) { w.overflow = true; break; }
+            const uint8_t *pv = w.verts(paths[i]);
+            uint8_t *row = best + (size_t)n_best * w.V;
+            for (uint32_t v = 0; v < w.V; v++) row[v] = pv[v] != kAbsent ? 0 : kAbsent;
+            n_best++;
+        }
+    }
+    g.best_n[w.c] = n_best;
+}
+
+// VariantClusterGraph::findSamplePaths (VariantClusterGraph.cpp:389-482), one thread per cluster
+__global__ void __launch_bounds__(64) k_find_sample_paths(DevGraphs g, BloomView bloom, uint32_t random_seed, uint32_t sample_idx, uint32_t max_paths) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.C) return;
+    Work w;
+    w.g = &g; w.c = c;
+    w.v0 = g.cl_vertex_off[c];
+    w.V = (uint32_t)(g.cl_vertex_off[c + 1] - w.v0);
+    w.pool = g.cl_pool[c]; w.tmp_cap = g.cl_tmp[c];
+    w.slot_bytes = (uint32_t)(sizeof(PathHdr) + ((w.V + 7) & ~7u));
+    uint8_t *p = g.scratch + g.scr_off[c];
+    w.mt = reinterpret_cast<uint32_t *>(p); p += 624 * 4;
+    w.slots = p; p += (size_t)w.pool * w.slot_bytes;
+    w.lists = reinterpret_cast<uint16_t *>(p); p += (size_t)w.V * 32 * 2;
+    w.tmp = reinterpret_cast<uint16_t *>(p); p += (size_t)((w.tmp_cap + 3) & ~3u) * 2;
+    w.free_stack = reinterpret_cast<uint16_t *>(p); p += (size_t)((w.pool + 3) & ~3u) * 2;
+    w.list_n = p; p += (w.V + 7) & ~7u;
+    w.covered = p;
+    w.overflow = false;
+    w.n_free = w.pool;
+    for (uint32_t i = 0; i < w.pool; i++) w.free_stack[i] = (uint16_t)(w.pool - 1 - i);
+    // seed = r + (g+1)(s+1) + cluster_idx (KmerCounter.cpp:65, VariantClusterGroup.cpp:142)
+    Mt19937 rng;
+    rng.mt = w.mt;
+    rng.seed(random_seed + (g.cl_group[c] + 1) * (sample_idx + 1) + g.cl_idx[c]);
+
+    for (uint32_t v = 0; v < w.V && !w.overflow; v++) {
+        uint32_t n = 0;
+        const uint64_t e0 = g.v_in_off[w.v0 + v], e1 = g.v_in_off[w.v0 + v + 1];
+        if (e0 == e1) {
+            const uint32_t s = w.alloc();
+            PathHdr *h = w.hdr(s);
+            h->fhi = h->flo = h->rhi = h->rlo = h->F = h->R = 0;
+            h->filled = h->score_first = h->score_second = h->nverts = 0;
+            uint8_t *pv = w.verts(s);
+            for (uint32_t i = 0; i < w.V; i++) pv[i] = kAbsent;
+            w.tmp[n++] = (uint16_t)s;
+        } else {
+            for (uint64_t e = e0; e < e1 && !w.overflow; e++) {
+                const uint32_t u = g.v_in_src[e];
+                merge_paths(w, n, w.lists + (size_t)u * 32, w.list_n[u]);
+                if (g.v_max_target[w.v0 + u] == v) {  // last consumer of u's paths
+                    for (uint32_t i = 0; i < w.list_n[u]; i++) w.release(w.lists[(size_t)u * 32 + i]);
+                    w.list_n[u] = 0;
+                }
+            }
+        }
+        if (w.overflow) break;
+        std_shuffle(w.tmp, n, rng);
+        for (uint32_t i = 0; i < n; i++) add_vertex(w, w.tmp[i], v, bloom);
+        n = filter_paths(w, w.tmp, n, max_paths, false);
+        for (uint32_t i = 0; i < n; i++) w.lists[(size_t)v * 32 + i] = w.tmp[i];
+        w.list_n[v] = (uint8_t)n;
+    }
+    if (!w.overflow) {
+        const uint32_t last = w.V - 1;
+        uint16_t *fin = w.lists + (size_t)last * 32;
+        const uint32_t n = filter_paths(w, fin, w.list_n[last], max_paths, true);
+        add_path_indices(w, fin, n);
+    }
+    if (w.overflow) g.status[c] = 1;
+}
+
+template <class T> T *upload(const T *h, size_t n, bool &ok) {
+    T *d = nullptr;
+    if (cudaMalloc(&d, (n ? n : 1) * sizeof(T)) != cudaSuccess) { ok = false; return nullptr; }
+    if (n && cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
+    return d;
+}
+
+}  // namespace
+
+struct btg_graphs {
+    DevGraphs g{};
+    std::vector<void *> allocs;
+    std::vector<uint64_t> h_best_off, h_vertex_off;
+    std::vector<uint32_t> h_best_cap;
+    uint32_t n_samples_cap = 0;
+};
+
+extern "C" {
+
+btg_graphs *btg_graphs_upload(const btg_graphs_desc *d, uint32_t max_samples, uint32_t max_sample_haplotypes) {
+    if (!ctx().ready) { set_error("btg_init() has not been called"); return nullptr; }
+    if (!d || max_samples == 0 || max_samples > BTG_MAX_SAMPLES || max_sample_haplotypes == 0 || max_sample_haplotypes > 32) {
+        set_error("bad graph descriptor (max_sample_haplotypes must be 1..32)");
+        return nullptr;
+    }
+    const uint32_t C = d->n_clusters;
+    const uint64_t Vtot = d->cl_vertex_off[C];
+    auto *gr = new btg_graphs();
+    bool ok = true;
+    auto keep = [&](auto *p) { gr->allocs.push_back((void *)p); return p; };
+    DevGraphs &g = gr->g;
+    g.C = C;
+    g.cl_vertex_off = keep(upload(d->cl_vertex_off, C + 1, ok));
+    g.v_seq_off = keep(upload(d->v_seq_off, Vtot + 1, ok));
+    g.seq = keep(upload(d->seq, d->v_seq_off[Vtot], ok));
+    g.v_flags = keep(upload(d->v_flags, Vtot, ok));
+    g.v_in_off = keep(upload(d->v_in_off, Vtot + 1, ok));
+    g.v_in_src = keep(upload(d->v_in_src, d->v_in_off[Vtot], ok));
+    g.cl_group = keep(upload(d->cl_group, C, ok));
+    g.cl_idx = keep(upload(d->cl_idx, C, ok));
+    // per-cluster sizing: simulate the candidate counts of the vertex DP (upper bounds)
+    std::vector<uint32_t> max_target(Vtot), pool(C), tmpc(C), best_cap(C);
+    std::vector<uint64_t> scr_off(C + 1, 0), best_off(C + 1, 0);
+    for (uint32_t c = 0; c < C; c++) {
+        const uint64_t v0 = d->cl_vertex_off[c];
+        const uint32_t V = (uint32_t)(d->cl_vertex_off[c + 1] - v0);
+        if (V == 0 || V > 60000) { set_error("cluster %u: unsupported vertex count %u", c, V); ok = false; break; }
+        for (uint32_t v = 0; v < V; v++) max_target[v0 + v] = v;
+        for (uint32_t v = 0; v < V; v++)
+            for (uint64_t e = d->v_in_off[v0 + v]; e < d->v_in_off[v0 + v + 1]; e++) {
+                const uint32_t u = d->v_in_src[e];
+                if (u >= v) { set_error("cluster %u: edge %u->%u is not topological", c, u, v); ok = false; }
+                else max_target[v0 + u] = std::max(max_target[v0 + u], v);
+            }
+        if (!ok) break;
+        std::vector<uint32_t> cnt(V, 0);
+        uint32_t need_pool = 1, need_tmp = 1;
+        for (uint32_t v = 0; v < V; v++) {
+            uint32_t pre = 0;
+            for (uint64_t e = d->v_in_off[v0 + v]; e < d->v_in_off[v0 + v + 1]; e++) pre += cnt[d->v_in_src[e]];
+            if (d->v_in_off[v0 + v] == d->v_in_off[v0 + v + 1]) pre = 1;
+            uint32_t alive = pre;
+            for (uint32_t u = 0; u < v; u++) if (max_target[v0 + u] >= v) alive += cnt[u];
+            need_pool = std::max(need_pool, alive);
+            need_tmp = std::max(need_tmp, pre);
+            cnt[v] = std::min(pre, max_sample_haplotypes);
+        }
+        if (need_pool > 60000) { set_error("cluster %u: candidate path pool too large (%u)", c, need_pool); ok = false; break; }
+        pool[c] = need_pool + 1;
+        tmpc[c] = need_tmp + 1;
+        best_cap[c] = max_sample_haplotypes * max_samples;
+        const uint64_t slot_bytes = sizeof(PathHdr) + ((V + 7) & ~7u);
+        uint64_t bytes = 624 * 4 + (uint64_t)pool[c] * slot_bytes + (uint64_t)V * 64 + (uint64_t)((tmpc[c] + 3) & ~3u) * 2 +
+                         (uint64_t)((pool[c] + 3) & ~3u) * 2 + 2 * (uint64_t)((V + 7) & ~7u);
+        scr_off[c + 1] = scr_off[c] + ((bytes + 15) & ~15ull);
+        best_off[c + 1] = best_off[c] + (uint64_t)best_cap[c] * V;
+    }
+    if (ok) {
+        g.v_max_target = keep(upload(max_target.data(), Vtot, ok));
+        g.scr_off = keep(upload(scr_off.data(), C + 1, ok));
+        g.cl_pool = keep(upload(pool.data(), C, ok));
+        g.cl_tmp = keep(upload(tmpc.data(), C, ok));
+        g.best_off = keep(upload(best_off.data(), C + 1, ok));
+        g.best_cap = keep(upload(best_cap.data(), C, ok));
+        uint8_t *scratch = nullptr, *best = nullptr;
+        uint32_t *best_n = nullptr, *status = nullptr;
+        ok = ok && cudaMalloc(&scratch, scr_off[C] + 16) == cudaSuccess;
+        ok = ok && cudaMalloc(&best, best_off[C] + 16) == cudaSuccess;
+        ok = ok && cudaMalloc(&best_n, (C + 1) * 4) == cudaSuccess && cudaMalloc(&status, (C + 1) * 4) == cudaSuccess;
+        keep(scratch); keep(best); keep(best_n); keep(status);
+        if (ok) {
+            cudaMemset(best_n, 0, (C + 1) * 4);
+            cudaMemset(status, 0, (C + 1) * 4);
+            cudaMemset(scratch, 0, scr_off[C] + 16);
+        }
+        g.scratch = scratch; g.best = best; g.best_n = best_n; g.status = status;
+    }
+    if (!ok) {
+        if (!*btg_last_error()) set_error("graph upload failed (%s)", cudaGetErrorString(cudaGetLastError()));
+        btg_graphs_free(gr);
+        return nullptr;
+    }
+    gr->h_best_off = best_off;
+    gr->h_best_cap = best_cap;
+    gr->h_vertex_off.assign(d->cl_vertex_off, d->cl_vertex_off + C + 1);
+    gr->n_samples_cap = max_samples;
+    return gr;
+}
+
+void btg_graphs_free(btg_graphs *gr) {
+    if (!gr) return;
+    cudaStreamSynchronize(ctx().stream);
+    for (void *p : gr->allocs) cudaFree(p);
+    delete gr;
+}
+
+int btg_find_sample_paths(btg_graphs *gr, const btg_bloom *sample_bloom, uint32_t sample_idx, uint32_t random_seed, uint32_t max_sample_haplotypes) {
+    BTG_REQUIRE_INIT();
+    if (!gr || !sample_bloom) { set_error("null argument"); return BTG_EINVAL; }
+    if (sample_idx >= gr->n_samples_cap) { set_error("sample index %u beyond the capacity given at upload (%u)", sample_idx, gr->n_samples_cap); return BTG_EINVAL; }
+    if (max_sample_haplotypes == 0 || max_sample_haplotypes > 32) { set_error("max_sample_haplotypes must be 1..32"); return BTG_EINVAL; }
+    if (gr->g.C == 0) return BTG_OK;
+    auto s = ctx().stream;
+    k_find_sample_paths<<<(gr->g.C + 63) / 64, 64, 0, s>>>(gr->g, btg_internal::bloom_view(sample_bloom), random_seed, sample_idx, max_sample_haplotypes);
+    BTG_LAUNCHED();
+    BTG_CUDA(cudaGetLastError());
+    BTG_CUDA(cudaStreamSynchronize(s));
+    std::vector<uint32_t> status(gr->g.C);
+    BTG_CUDA(cudaMemcpy(status.data(), gr->g.status, gr->g.C * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t c = 0; c < gr->g.C; c++)
+        if (status[c]) { set_error("cluster %u: path-search scratch overflow", c); return BTG_ESTATE; }
+    return BTG_OK;
+}
+
+int btg_get_best_paths(const btg_graphs *gr, uint32_t *n_paths_out, uint64_t *path_off_out, uint8_t *membership_out, uint64_t membership_bytes) {
+    BTG_REQUIRE_INIT();
+    if (!gr || !n_paths_out) { set_error("null argument"); return BTG_EINVAL; }
+    const uint32_t C = gr->g.C;
+    BTG_CUDA(cudaStreamSynchronize(ctx().stream));
+    BTG_CUDA(cudaMemcpy(n_paths_out, gr->g.best_n, C * 4, cudaMemcpyDeviceToHost));
+    if (!path_off_out) return BTG_OK;
+    path_off_out[0] = 0;
+    for (uint32_t c = 0; c < C; c++) path_off_out[c + 1] = path_off_out[c] + (uint64_t)n_paths_out[c] * (gr->h_vertex_off[c + 1] - gr->h_vertex_off[c]);
+    if (!membership_out) return BTG_OK;
+    if (membership_bytes < path_off_out[C]) { set_error("membership buffer too small"); return BTG_EINVAL; }
+    std::vector<uint8_t> all(gr->h_best_off[C]);
+    BTG_CUDA(cudaMemcpy(all.data(), gr->g.best, all.size(), cudaMemcpyDeviceToHost));
+    for (uint32_t c = 0; c < C; c++) {
+        const uint64_t n = path_off_out[c + 1] - path_off_out[c];
+        for (uint64_t i = 0; i < n; i++) membership_out[path_off_out[c] + i] = all[gr->h_best_off[c] + i] != kAbsent;
+    }
+    return BTG_OK;
+}
+
+}  // extern "C"

@@ -123,6 +123,36 @@ int btg_scan_sequence_dev(const char *seq_dev, size_t len, uint64_t *kmers_out_d
 int btg_scan_sequence_lookup_dev(const btg_bloom *b, const char *seq_dev, size_t len, uint8_t *hit_out_dev, void *stream);
 
 
+/* ======================= candidate-path search (k-mer match, hot loop A) ===================== *
+ * Replaces KmerCounter::findVariantClusterPaths (include/bayesTyper/KmerCounter.hpp:57,
+ * src/bayesTyper/KmerCounter.cpp:59-103) -> VariantClusterGroup::findSamplePaths ->
+ * VariantClusterGraph::findSamplePaths (src/bayesTyper/VariantClusterGraph.cpp:389-798).
+ * The graphs are the reference's boost::adjacency_list per cluster, CSR-flattened (vertices are
+ * already in topological = index order, VariantClusterGraph.cpp:433).                           */
+typedef struct btg_graphs_desc {
+    uint32_t n_clusters;
+    const uint64_t *cl_vertex_off;   /* [C+1] vertices per cluster */
+    const uint64_t *v_seq_off;       /* [V+1] -> seq */
+    const uint8_t *seq;              /* VariantClusterGraphVertex::sequence as one code (0..3) per nucleotide */
+    const uint8_t *v_flags;          /* [V] bit0 is_first_nucleotides_redundant, bit1 is_disconnected */
+    const uint64_t *v_in_off;        /* [V+1] -> v_in_src */
+    const uint32_t *v_in_src;        /* in-edge sources (cluster-local vertex ids), in boost::in_edges order */
+    const uint32_t *cl_group;        /* [C] index of the cluster's group in the unit (after the size sort) */
+    const uint32_t *cl_idx;          /* [C] variant_cluster_idx within its group */
+} btg_graphs_desc;
+
+typedef struct btg_graphs btg_graphs;
+btg_graphs *btg_graphs_upload(const btg_graphs_desc *desc, uint32_t max_samples, uint32_t max_sample_haplotypes);
+void btg_graphs_free(btg_graphs *g);
+/* one sample's pass (samples must be submitted in order 0..S-1: addPathIndices merges order-dependently,
+ * VariantClusterGraph.cpp:726-798).  seed of cluster c: random_seed + (group+1)*(sample_idx+1) + cluster_idx */
+int btg_find_sample_paths(btg_graphs *g, const btg_bloom *sample_bloom, uint32_t sample_idx, uint32_t random_seed,
+                          uint32_t max_sample_haplotypes);
+/* best_paths_indices: n_paths_out[C]; path_off_out[C+1] (prefix sums of n_paths*V, optional); membership_out
+ * (optional) one byte per (path, vertex), path-major                                             */
+int btg_get_best_paths(const btg_graphs *g, uint32_t *n_paths_out, uint64_t *path_off_out, uint8_t *membership_out,
+                       uint64_t membership_bytes);
+
 /* ======================= per-cluster Gibbs sampler =========================== *
  * Replaces InferenceEngine::{estimateNoise,estimateGenotypes,estimateNoiseAndGenotypes}
  * (include/bayesTyper/InferenceEngine.hpp:62-64, src/bayesTyper/InferenceEngine.cpp:135-472)

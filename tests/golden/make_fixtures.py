@@ -80,7 +80,37 @@ def make(name, workload, n_groups, seed=20190401, n_errors=20000):
         print(name, "groups", len(keep), "clusters", sub.Cn, "variants", sub.n_variants, "H max", int(sub.a["cl_nhap"].max()))
 
 
+def make_paths(name, workload, seed=20190401, n_errors=5000, max_hap=32):
+    """Path-search fixture: the reference's graphs (VariantClusterGraph ctor) and the best_paths_indices its
+    findVariantClusterPaths left after all samples.  The sample k-mer sets are NOT stored: the test regenerates
+    them with the same seeded generator and checks their checksum."""
+    import hashlib
+    with tempfile.TemporaryDirectory() as td:
+        spectra = synth.sample_spectra(workload, 4, n_errors)
+        wd = synth.write_workdir(workload, td, spectra=spectra)
+        subprocess.check_call([str(BTREF), "run", "--workdir", str(wd), "--threads", "4", "--seed", str(seed), "--dump-graphs",
+                               "--cluster-only", "--max-sample-haplotypes", str(max_hap)], stdout=subprocess.DEVNULL)
+        g = btd.read(Path(wd) / "ref_out" / "graphs.btd")
+    keep = ["group_cluster_off", "cluster_idx", "cl_vertex_off", "v_seq_off", "seq", "v_flags", "v_in_off", "v_in_src", "cl_path_off", "path_bits"]
+    pack = {"g." + k: g[k] for k in keep}
+    pack["meta.seed"] = np.array([seed], np.uint32)
+    pack["meta.max_hap"] = np.array([max_hap], np.uint32)
+    pack["meta.n_errors"] = np.array([n_errors], np.uint32)
+    pack["meta.kmer_sha"] = np.frombuffer(b"".join(hashlib.sha256(k.tobytes() + c.tobytes()).digest() for k, c in spectra), np.uint8)
+    btd.write(Path(__file__).parent / f"{name}.btd", pack)
+    nv = np.diff(g["cl_vertex_off"]); npaths = np.diff(g["cl_path_off"]) // np.maximum(nv, 1)
+    print(name, "clusters", len(nv), "max V", int(nv.max()), "paths hist", np.bincount(npaths.astype(int))[:12])
+
+
+PATH_WORKLOADS = {
+    "paths_snv_1s": lambda: synth.config_a(n_variants=1500, length=150_000),
+    "paths_mixed_3s": lambda: synth.small_mixed(900, 60_000, 3, seed=21),
+    "paths_dense_2s": lambda: synth.small_mixed(1500, 40_000, 2, seed=44, frac_indel=0.3),
+}
+
 if __name__ == "__main__":
+    for nm, fn in PATH_WORKLOADS.items():
+        make_paths(nm, fn(), max_hap=8 if nm == "paths_dense_2s" else 32)
     make("gibbs_snv_1s", synth.config_a(n_variants=1200, length=120_000), 160)
     make("gibbs_mixed_3s", synth.small_mixed(700, 60_000, 3, seed=21), 120)
     make("gibbs_chrx_2s", synth.small_mixed(400, 50_000, 2, seed=33, chrom="chrX"), 80)

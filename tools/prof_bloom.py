@@ -30,14 +30,18 @@ q[: nq // 2] = first
 q = q[torch.randperm(nq, device="cuda")].contiguous()
 hit = torch.zeros(nq, dtype=torch.uint8, device="cuda")
 torch.cuda.synchronize()
-for _ in range(3):
-    capi.check(lib.btg_bloom_lookup_dev(b, q.data_ptr(), nq, hit.data_ptr(), None))
-torch.cuda.synchronize()
-e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+import os
+modes = [int(x) for x in os.environ.get("MODES", "0").split(",")]
 s = torch.cuda.ExternalStream(lib.btg_get_stream())
-e0.record(s)
-for _ in range(5):
-    capi.check(lib.btg_bloom_lookup_dev(b, q.data_ptr(), nq, hit.data_ptr(), None))
-e1.record(s)
-s.synchronize()
-print("ms per lookup launch", e0.elapsed_time(e1) / 5, "hit rate", float(hit.float().mean()))
+for mode in modes:
+    lib.btg_debug_set_probe_mode(mode)
+    for _ in range(3):
+        capi.check(lib.btg_bloom_lookup_dev(b, q.data_ptr(), nq, hit.data_ptr(), None))
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(s)
+    for _ in range(5):
+        capi.check(lib.btg_bloom_lookup_dev(b, q.data_ptr(), nq, hit.data_ptr(), None))
+    e1.record(s)
+    s.synchronize()
+    print("mode", mode, "L2_FETCH", os.environ.get("BTG_L2_FETCH"), "ms per lookup launch", e0.elapsed_time(e1) / 5, "hit rate", float(hit.float().mean()), flush=True)
