@@ -29,3 +29,8 @@ def bind(L):
     L.btg_graphs_free.argtypes = [vp]
     L.btg_find_sample_paths.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32]
     L.btg_get_best_paths.argtypes = [vp, vp, vp, vp, C.c_uint64]
+    L.btg_walk_paths_dev.argtypes = [vp, C.c_int] + [vp] * 11 + [vp]
+    L.btg_path_alleles_dev.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.btg_table_lookup_dev.argtypes = [vp, vp, C.c_int64, vp, C.c_size_t, vp, vp]
+    L.btg_table_add_sample_kmers_dev.argtypes = [vp, vp, C.c_int64, vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, vp, vp, vp]
+    L.btg_table_scan_region_dev.argtypes = [vp, vp, C.c_int64, vp, C.c_size_t, C.c_int, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp]

@@ -1,0 +1,278 @@
+// table.cu — path k-mer enumeration and the exact k-mer count table (k-mer match, genotype side).
+//
+// Replaces, for the k-mers that can influence inference (the path k-mers of the unit):
+//   VariantClusterGraph::countPathKmers / classifyPathKmers / getHaplotypeCandidates' path walks
+//       src/bayesTyper/VariantClusterGraph.cpp:800-846, 848-939, 941-1135 (+ updateVariantPathIndices :1137-1184)
+//   KmerCounter::parseSampleKmersCallBack (sample k-mer stream -> counts)        src/bayesTyper/KmerCounter.cpp:388-429
+//   KmerCounter::countInterclusterKmersCallback (genome scan -> multiplicities)  src/bayesTyper/KmerCounter.cpp:291-334
+//   KmerCounts::{addSampleCount,addInterclusterMultiplicity}                     src/bayesTyper/KmerCounts.cpp:98-118,178-189
+//
+// The reference funnels every k-mer through an in-memory Bloom filter of the path k-mers and then a mutex-guarded
+// hash of vectors.  Filter false positives only ever create table entries that no path k-mer looks up, so the
+// device keeps an EXACT table instead: the distinct path k-mers as a sorted key array (built by the caller from
+// the emitted occurrences) that the 17 B/record sample stream and the 1 B/nt genome scan probe directly.
+// Keys are ordered as signed (w1, w0) pairs — the order torch.sort gives the host glue — and the kernels use the
+// same comparator.
+#include "common.cuh"
+#include "kmer.cuh"
+
+using namespace btg;
+
+namespace {
+
+constexpr uint32_t NONE16 = 0xFFFF;
+constexpr int kMaxRunning = 48;  // variants whose window covers the current k-mer (running_variants)
+
+struct PathWalkGraphs {
+    uint32_t C;
+    const uint64_t *cl_vertex_off, *v_seq_off;
+    const uint8_t *seq, *v_flags;
+    const uint16_t *v_var, *v_allele;   // variant_allele_idx (0xFFFF = none)
+    const uint64_t *v_refvar_off;
+    const uint16_t *v_refvar;           // reference_variant_indices
+    const uint64_t *cl_path_off;        // [C+1] first best path of each cluster (global path index)
+    const uint64_t *path_mem_off;       // [C+1] byte offset of the cluster's membership rows
+    const uint8_t *path_mem;            // path x vertex membership (1 = on path)
+    const uint32_t *path_cluster;       // [P] cluster of each path
+};
+
+struct Running { uint32_t var, allele, first, second; };
+
+// One best path: canonical k-mer of every window (reset at disconnected vertices) + which variants each window
+// covers.  EMIT = false: count only.
+template <bool EMIT>
+__global__ void __launch_bounds__(128) k_walk_paths(PathWalkGraphs g, uint64_t n_paths, uint32_t *__restrict__ n_occ, uint32_t *__restrict__ n_cov,
+                                                    const uint64_t *__restrict__ occ_off, const uint64_t *__restrict__ cov_off,
+                                                    int64_t *__restrict__ key_w0, int64_t *__restrict__ key_w1, uint32_t *__restrict__ occ_path,
+                                                    uint32_t *__restrict__ occ_nt, int64_t *__restrict__ cov_occ, uint16_t *__restrict__ cov_var,
+                                                    uint32_t *__restrict__ status) {
+    const uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (p >= n_paths) return;
+    const uint32_t c = g.path_cluster[p];
+    const uint64_t v0 = g.cl_vertex_off[c];
+    const uint32_t V = (uint32_t)(g.cl_vertex_off[c + 1] - v0);
+    const uint8_t *mem = g.path_mem + g.path_mem_off[c] + (p - g.cl_path_off[c]) * V;
+    Roller roll;
+    roll.reset();
+    Running run[kMaxRunning];
+    int n_run = 0;
+    uint32_t num_nt = 0, occ = 0, cov = 0;
+    uint64_t o_base = EMIT ? occ_off[p] : 0, c_base = EMIT ? cov_off[p] : 0;
+    bool overflow = false;
+    for (uint32_t v = 0; v < V; v++) {
+        if (!mem[v]) continue;
+        const uint64_t s0 = g.v_seq_off[v0 + v];
+        const uint32_t len = (uint32_t)(g.v_seq_off[v0 + v + 1] - s0);
+        const uint32_t var = g.v_var[v0 + v], allele = g.v_allele[v0 + v];
+        if (var != NONE16) {  // VariantClusterGraph.cpp:987-999
+            int f = -1;
+            for (int i = 0; i < n_run; i++) if (run[i].var == var && run[i].allele == allele) { f = i; break; }
+            if (f < 0) {
+                if (n_run == kMaxRunning) { overflow = true; break; }
+                f = n_run++;
+                run[f] = Running{var, allele, num_nt + (g.v_flags[v0 + v] & 1u), num_nt + K - 1};
+            }
+            run[f].second += len;
+        }
+        for (uint64_t e = g.v_refvar_off[v0 + v]; e < g.v_refvar_off[v0 + v + 1]; e++) {  // :1001-1012
+            const uint32_t rv = g.v_refvar[e];
+            for (int i = 0; i < n_run; i++) if (run[i].var == rv && run[i].allele == 0) { run[i].second += len; break; }
+        }
+        if (g.v_flags[v0 + v] & 2u) roll.reset();
+        for (uint32_t i = 0; i < len; i++) {
+            if (roll.push(g.seq[s0 + i])) {
+                // expire windows (updateVariantPathIndices :1141-1149), then record the covering variants
+                int w = 0;
+                for (int j = 0; j < n_run; j++) if (run[j].second > num_nt) run[w++] = run[j];
+                n_run = w;
+                if (EMIT) {
+                    const Kmer128 cn = roll.canonical();
+                    uint64_t w0, w1;
+                    to_boundary(cn, w0, w1);
+                    key_w0[o_base + occ] = (int64_t)w0;
+                    key_w1[o_base + occ] = (int64_t)w1;
+                    occ_path[o_base + occ] = (uint32_t)p;
+                    occ_nt[o_base + occ] = num_nt;
+                }
+                for (int j = 0; j < n_run; j++)
+                    if (run[j].first <= num_nt) {
+                        if (EMIT) { cov_occ[c_base + cov] = (int64_t)(o_base + occ); cov_var[c_base + cov] = (uint16_t)run[j].var; }
+                        cov++;
+                    }
+                occ++;
+            }
+            num_nt++;
+        }
+    }
+    if (overflow) status[c] = 2;
+    if (!EMIT) { n_occ[p] = occ; n_cov[p] = cov; }
+}
+
+// haplotype -> allele table: HaplotypeInfo::variant_allele_indices (VariantClusterGraph.cpp:983-992,1091-1098)
+__global__ void __launch_bounds__(128) k_path_alleles(PathWalkGraphs g, uint64_t n_paths, const uint64_t *__restrict__ cl_var_off,
+                                                      const uint16_t *__restrict__ var_nalleles, const uint64_t *__restrict__ hapvar_off,
+                                                      uint16_t *__restrict__ hap_alleles) {
+    const uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (p >= n_paths) return;
+    const uint32_t c = g.path_cluster[p];
+    const uint64_t v0 = g.cl_vertex_off[c];
+    const uint32_t V = (uint32_t)(g.cl_vertex_off[c + 1] - v0);
+    const uint32_t nvar = (uint32_t)(cl_var_off[c + 1] - cl_var_off[c]);
+    const uint8_t *mem = g.path_mem + g.path_mem_off[c] + (p - g.cl_path_off[c]) * V;
+    uint16_t *out = hap_alleles + hapvar_off[c] + (p - g.cl_path_off[c]) * nvar;
+    for (uint32_t i = 0; i < nvar; i++) out[i] = NONE16;
+    for (uint32_t v = 0; v < V; v++) {
+        if (!mem[v]) continue;
+        const uint32_t var = g.v_var[v0 + v];
+        if (var != NONE16 && !(g.v_flags[v0 + v] & 2u)) out[var] = g.v_allele[v0 + v];
+    }
+    for (uint32_t i = 0; i < nvar; i++) if (out[i] == NONE16) out[i] = var_nalleles[cl_var_off[c] + i] - 1;
+}
+
+// ---- exact table probes ------------------------------------------------------------------------
+__device__ __forceinline__ int64_t table_find(const int64_t *__restrict__ kw0, const int64_t *__restrict__ kw1, int64_t n, int64_t w0, int64_t w1) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const int64_t m1 = __ldg(kw1 + mid);
+        bool less;  // key[mid] < (w1, w0)
+        if (m1 != w1) less = m1 < w1;
+        else less = __ldg(kw0 + mid) < w0;
+        if (less) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n && __ldg(kw1 + lo) == w1 && __ldg(kw0 + lo) == w0) return lo;
+    return -1;
+}
+
+__device__ __forceinline__ void sat_add_u8(uint8_t *p, uint32_t add) {  // updateMultiplicity / addSampleCount (KmerCounts.cpp:161-189)
+    uint32_t *word = reinterpret_cast<uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~uintptr_t(3));
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+    uint32_t old = *word, assumed;
+    do {
+        assumed = old;
+        const uint32_t cur = (assumed >> sh) & 0xFFu;
+        const uint32_t nv = (255u - cur) <= add ? 255u : cur + add;
+        old = atomicCAS(word, assumed, (assumed & ~(0xFFu << sh)) | (nv << sh));
+    } while (old != assumed);
+}
+
+// KmerCounter::parseSampleKmersCallBack: one KMC record per thread (16 B k-mer + 1 B count streamed once)
+__global__ void __launch_bounds__(256) k_table_add_sample(const int64_t *__restrict__ kw0, const int64_t *__restrict__ kw1, int64_t n_keys,
+                                                          const longlong2 *__restrict__ kmers, const uint8_t *__restrict__ counts, size_t n,
+                                                          uint32_t S, uint32_t sample, uint8_t *table_counts, uint8_t *has_record) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const longlong2 k = __ldg(kmers + i);
+        const int64_t idx = table_find(kw0, kw1, n_keys, k.x, k.y);
+        if (idx >= 0) {
+            sat_add_u8(table_counts + (size_t)idx * S + sample, counts[i]);
+            has_record[idx] = 1;
+        }
+    }
+}
+
+// KmerCounter::countInterclusterKmersCallback: rolling scan of one region, probe, addInterclusterMultiplicity
+constexpr int kScanChunk = 64;
+__global__ void __launch_bounds__(256) k_table_scan_region(const int64_t *__restrict__ kw0, const int64_t *__restrict__ kw1, int64_t n_keys,
+                                                           const char *__restrict__ seq, size_t len, uint32_t is_decoy, uint32_t ploidy_f, uint32_t ploidy_m,
+                                                           uint8_t *ic, uint8_t *max_mult, uint8_t *decoy, uint8_t *has_record) {
+    const size_t nchunks = (len + kScanChunk - 1) / kScanChunk;
+    for (size_t ch = blockIdx.x * (size_t)blockDim.x + threadIdx.x; ch < nchunks; ch += (size_t)gridDim.x * blockDim.x) {
+        const size_t p0 = ch * kScanChunk, p1 = p0 + kScanChunk < len ? p0 + kScanChunk : len;
+        Roller roll;
+        roll.reset();
+        const size_t start = p0 >= (size_t)(K - 1) ? p0 - (K - 1) : 0;
+        for (size_t p = start; p < p1; p++) {
+            const unsigned c = nt_code(__ldg(seq + p));
+            bool complete = false;
+            if (c > 3) roll.reset(); else complete = roll.push(c);
+            if (complete && p >= p0) {
+                uint64_t w0, w1;
+                to_boundary(roll.canonical(), w0, w1);
+                const int64_t idx = table_find(kw0, kw1, n_keys, (int64_t)w0, (int64_t)w1);
+                if (idx >= 0) {
+                    has_record[idx] = 1;
+                    sat_add_u8(max_mult + idx, 1);  // max_haploid_multiplicity (KmerCounts.cpp:100)
+                    if (is_decoy) decoy[idx] = 1;
+                    else { sat_add_u8(ic + idx * 2, ploidy_f); sat_add_u8(ic + idx * 2 + 1, ploidy_m); }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_table_lookup(const int64_t *__restrict__ kw0, const int64_t *__restrict__ kw1, int64_t n_keys,
+                                                      const longlong2 *__restrict__ kmers, size_t n, int64_t *__restrict__ idx_out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const longlong2 k = __ldg(kmers + i);
+        idx_out[i] = table_find(kw0, kw1, n_keys, k.x, k.y);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// `g` fields are device pointers (the caller keeps graphs + best paths resident); see btgpu.h
+int btg_walk_paths_dev(const btg_pathwalk_desc *d, int emit, uint32_t *n_occ, uint32_t *n_cov, const uint64_t *occ_off, const uint64_t *cov_off,
+                       int64_t *key_w0, int64_t *key_w1, uint32_t *occ_path, uint32_t *occ_nt, int64_t *cov_occ, uint16_t *cov_var,
+                       uint32_t *status, void *stream) {
+    BTG_REQUIRE_INIT();
+    if (!d) { set_error("null argument"); return BTG_EINVAL; }
+    if (d->n_paths == 0) return BTG_OK;
+    PathWalkGraphs g{d->n_clusters, d->cl_vertex_off, d->v_seq_off, d->seq, d->v_flags, d->v_var, d->v_allele, d->v_refvar_off, d->v_refvar,
+                     d->cl_path_off, d->path_mem_off, d->path_mem, d->path_cluster};
+    const unsigned grid = (unsigned)((d->n_paths + 127) / 128);
+    if (emit) k_walk_paths<true><<<grid, 128, 0, pick_stream(stream)>>>(g, d->n_paths, n_occ, n_cov, occ_off, cov_off, key_w0, key_w1, occ_path, occ_nt, cov_occ, cov_var, status);
+    else k_walk_paths<false><<<grid, 128, 0, pick_stream(stream)>>>(g, d->n_paths, n_occ, n_cov, occ_off, cov_off, key_w0, key_w1, occ_path, occ_nt, cov_occ, cov_var, status);
+    BTG_LAUNCHED();
+    BTG_CUDA(cudaGetLastError());
+    return BTG_OK;
+}
+
+int btg_path_alleles_dev(const btg_pathwalk_desc *d, const uint64_t *cl_var_off, const uint16_t *var_nalleles, const uint64_t *hapvar_off,
+                         uint16_t *hap_alleles, void *stream) {
+    BTG_REQUIRE_INIT();
+    if (!d) { set_error("null argument"); return BTG_EINVAL; }
+    if (d->n_paths == 0) return BTG_OK;
+    PathWalkGraphs g{d->n_clusters, d->cl_vertex_off, d->v_seq_off, d->seq, d->v_flags, d->v_var, d->v_allele, d->v_refvar_off, d->v_refvar,
+                     d->cl_path_off, d->path_mem_off, d->path_mem, d->path_cluster};
+    k_path_alleles<<<(unsigned)((d->n_paths + 127) / 128), 128, 0, pick_stream(stream)>>>(g, d->n_paths, cl_var_off, var_nalleles, hapvar_off, hap_alleles);
+    BTG_LAUNCHED();
+    BTG_CUDA(cudaGetLastError());
+    return BTG_OK;
+}
+
+int btg_table_lookup_dev(const int64_t *key_w0, const int64_t *key_w1, int64_t n_keys, const uint64_t *kmers, size_t n, int64_t *idx_out, void *stream) {
+    BTG_REQUIRE_INIT();
+    if (n == 0) return BTG_OK;
+    k_table_lookup<<<btg_grid_for(n, 256, 8), 256, 0, pick_stream(stream)>>>(key_w0, key_w1, n_keys, (const longlong2 *)kmers, n, idx_out);
+    BTG_LAUNCHED();
+    BTG_CUDA(cudaGetLastError());
+    return BTG_OK;
+}
+
+int btg_table_add_sample_kmers_dev(const int64_t *key_w0, const int64_t *key_w1, int64_t n_keys, const uint64_t *kmers, const uint8_t *counts, size_t n,
+                                   uint32_t n_samples, uint32_t sample_idx, uint8_t *table_counts, uint8_t *has_record, void *stream) {
+    BTG_REQUIRE_INIT();
+    if (sample_idx >= n_samples) { set_error("sample index out of range"); return BTG_EINVAL; }
+    if (n == 0) return BTG_OK;
+    k_table_add_sample<<<btg_grid_for(n, 256, 8), 256, 0, pick_stream(stream)>>>(key_w0, key_w1, n_keys, (const longlong2 *)kmers, counts, n, n_samples,
+                                                                               sample_idx, table_counts, has_record);
+    BTG_LAUNCHED();
+    BTG_CUDA(cudaGetLastError());
+    return BTG_OK;
+}
+
+int btg_table_scan_region_dev(const int64_t *key_w0, const int64_t *key_w1, int64_t n_keys, const char *seq, size_t len, int is_decoy,
+                              uint32_t ploidy_female, uint32_t ploidy_male, uint8_t *ic, uint8_t *max_mult, uint8_t *decoy, uint8_t *has_record, void *stream) {
+    BTG_REQUIRE_INIT();
+    if (len == 0) return BTG_OK;
+    const size_t nchunks = (len + kScanChunk - 1) / kScanChunk;
+    k_table_scan_region<<<btg_grid_for(nchunks, 256, 4), 256, 0, pick_stream(stream)>>>(key_w0, key_w1, n_keys, seq, len, is_decoy ? 1u : 0u, ploidy_female,
+                                                                                       ploidy_male, ic, max_mult, decoy, has_record);
+    BTG_LAUNCHED();
+    BTG_CUDA(cudaGetLastError());
+    return BTG_OK;
+}
+
+}  // extern "C"

@@ -153,6 +153,56 @@ int btg_find_sample_paths(btg_graphs *g, const btg_bloom *sample_bloom, uint32_t
 int btg_get_best_paths(const btg_graphs *g, uint32_t *n_paths_out, uint64_t *path_off_out, uint8_t *membership_out,
                        uint64_t membership_bytes);
 
+/* ======================= path k-mers and the exact count table (k-mer match, hot loop B) ===== *
+ * Device-pointer entry points (suffix _dev): the host glue keeps graphs, best paths, sample k-mer
+ * streams and the table columns resident in HBM and composes these kernels (bayestyper_b200/
+ * kmer_pipeline.py mirrors KmerCounter's genotype-side stages: countPathKmers, countInterclusterKmers,
+ * parseSampleKmers, classifyPathKmers, include/bayesTyper/KmerCounter.hpp:61-67).
+ * Table keys: the distinct path k-mers, sorted ascending as SIGNED (w1, w0) pairs.              */
+typedef struct btg_pathwalk_desc {          /* every pointer is a device pointer */
+    uint32_t n_clusters;
+    uint64_t n_paths;                        /* best paths of all clusters, cluster-major */
+    const uint64_t *cl_vertex_off;           /* as btg_graphs_desc */
+    const uint64_t *v_seq_off;
+    const uint8_t *seq;
+    const uint8_t *v_flags;
+    const uint16_t *v_var;                   /* [V] VariantClusterGraphVertex::variant_allele_idx.first (0xFFFF none) */
+    const uint16_t *v_allele;                /* [V] .second */
+    const uint64_t *v_refvar_off;            /* [V+1] -> v_refvar: reference_variant_indices */
+    const uint16_t *v_refvar;
+    const uint64_t *cl_path_off;             /* [C+1] first path of each cluster */
+    const uint64_t *path_mem_off;            /* [C+1] byte offset of the cluster's rows in path_mem */
+    const uint8_t *path_mem;                 /* best_paths_indices: one byte per (path, vertex) */
+    const uint32_t *path_cluster;            /* [n_paths] */
+} btg_pathwalk_desc;
+
+/* Walks every best path (KmerPair reset at disconnected vertices) — the loop shared by countPathKmers,
+ * classifyPathKmers and getHaplotypeCandidates (VariantClusterGraph.cpp:800-1135).
+ * emit = 0: n_occ[p] / n_cov[p] = number of k-mer windows / (window, covered variant) pairs of path p.
+ * emit = 1: with occ_off / cov_off = exclusive prefix sums of those, writes per window the canonical k-mer
+ *           (key_w0, key_w1), its path and nucleotide index, and per pair (window id, variant): the
+ *           running_variants coverage of updateVariantPathIndices (:1137-1184).
+ * status[c] = 2 if a cluster exceeds the running-variant capacity.                             */
+int btg_walk_paths_dev(const btg_pathwalk_desc *d, int emit, uint32_t *n_occ, uint32_t *n_cov, const uint64_t *occ_off,
+                       const uint64_t *cov_off, int64_t *key_w0, int64_t *key_w1, uint32_t *occ_path, uint32_t *occ_nt,
+                       int64_t *cov_occ, uint16_t *cov_var, uint32_t *status, void *stream);
+/* HaplotypeInfo::variant_allele_indices of every best path (VariantClusterGraph.cpp:983-992,1091-1098) */
+int btg_path_alleles_dev(const btg_pathwalk_desc *d, const uint64_t *cl_var_off, const uint16_t *var_nalleles,
+                         const uint64_t *hapvar_off, uint16_t *hap_alleles, void *stream);
+/* KmerCountsHash::findKmer on a batch: index into the key arrays or -1 */
+int btg_table_lookup_dev(const int64_t *key_w0, const int64_t *key_w1, int64_t n_keys, const uint64_t *kmers, size_t n,
+                         int64_t *idx_out, void *stream);
+/* KmerCounter::parseSampleKmers for one batch of one sample (KmerCounter.cpp:388-429): for every (k-mer, count)
+ * record present in the table, counts[idx][sample] saturating-adds count (KmerCounts.cpp:178-189)          */
+int btg_table_add_sample_kmers_dev(const int64_t *key_w0, const int64_t *key_w1, int64_t n_keys, const uint64_t *kmers,
+                                   const uint8_t *counts, size_t n, uint32_t n_samples, uint32_t sample_idx,
+                                   uint8_t *table_counts, uint8_t *has_record, void *stream);
+/* KmerCounter::countInterclusterKmers for one region (KmerCounter.cpp:291-334): rolling scan, probe,
+ * KmerCounts::addInterclusterMultiplicity (KmerCounts.cpp:98-118). ic = [n_keys][2] (female, male)        */
+int btg_table_scan_region_dev(const int64_t *key_w0, const int64_t *key_w1, int64_t n_keys, const char *seq, size_t len,
+                              int is_decoy, uint32_t ploidy_female, uint32_t ploidy_male, uint8_t *ic, uint8_t *max_mult,
+                              uint8_t *decoy, uint8_t *has_record, void *stream);
+
 /* ======================= per-cluster Gibbs sampler =========================== *
  * Replaces InferenceEngine::{estimateNoise,estimateGenotypes,estimateNoiseAndGenotypes}
  * (include/bayesTyper/InferenceEngine.hpp:62-64, src/bayesTyper/InferenceEngine.cpp:135-472)

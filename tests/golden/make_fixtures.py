@@ -102,6 +102,39 @@ def make_paths(name, workload, seed=20190401, n_errors=5000, max_hap=32):
     print(name, "clusters", len(nv), "max V", int(nv.max()), "paths hist", np.bincount(npaths.astype(int))[:12])
 
 
+def make_pipeline(name, workload, seed=20190401, n_errors=3000):
+    """k-mer pipeline fixture: reference graphs + best paths + intercluster regions + multigroup Bloom in,
+    the reference's VariantClusterHaplotypes (classifyPathKmers + getHaplotypeCandidates output) out."""
+    import hashlib
+    with tempfile.TemporaryDirectory() as td:
+        spectra = synth.sample_spectra(workload, 4, n_errors)
+        wd = synth.write_workdir(workload, td, spectra=spectra)
+        subprocess.check_call([str(BTREF), "run", "--workdir", str(wd), "--threads", "1", "--seed", str(seed), "--dump-graphs", "--dump-haps",
+                               "--skip-genotype"], stdout=subprocess.DEVNULL)
+        out = Path(wd) / "ref_out"
+        g = btd.read(out / "graphs.btd"); h = btd.read(out / "haps.btd"); t = btd.read(out / "tables.btd")
+        regions = [ln.split("\t") for ln in (out / "bayestyper_cluster_data" / "intercluster_regions.txt.gz").read_text().splitlines()]
+        mg_meta = (out / "bayestyper_cluster_data" / "multigroup_kmers.bloomMeta").read_text().split()
+        mg_data = np.fromfile(out / "bayestyper_cluster_data" / "multigroup_kmers.bloomData", np.uint8)
+    pack = {"g." + k: v for k, v in g.items()}
+    pack.update({"h." + k: v for k, v in h.items()})
+    pack["t.nb_p_size"] = t["nb_p_size"]
+    pack["regions"] = np.array([[int(r[1]), int(r[2]), int(r[3])] for r in regions], np.int64).reshape(-1, 3)
+    pack["mg.meta"] = np.array([int(mg_meta[0]), int(mg_meta[1])], np.uint64)
+    pack["mg.data"] = mg_data
+    pack["meta.seed"] = np.array([seed], np.uint32)
+    pack["meta.n_errors"] = np.array([n_errors], np.uint32)
+    pack["meta.kmer_sha"] = np.frombuffer(b"".join(hashlib.sha256(k.tobytes() + c.tobytes()).digest() for k, c in spectra), np.uint8)
+    btd.write(Path(__file__).parent / f"{name}.btd", pack)
+    print(name, "clusters", len(g["cl_vertex_off"]) - 1, "rows", len(h["k_has_counts"]), "regions", len(regions), "multigroup n", mg_meta[0])
+
+
+PIPE_WORKLOADS = {
+    "pipe_snv_1s": lambda: synth.config_a(n_variants=500, length=50_000),
+    "pipe_mixed_3s": lambda: synth.small_mixed(350, 25_000, 3, seed=52),
+    "pipe_chrx_2s": lambda: synth.small_mixed(250, 20_000, 2, seed=61, chrom="chrX"),
+}
+
 PATH_WORKLOADS = {
     "paths_snv_1s": lambda: synth.config_a(n_variants=1500, length=150_000),
     "paths_mixed_3s": lambda: synth.small_mixed(900, 60_000, 3, seed=21),
@@ -109,6 +142,11 @@ PATH_WORKLOADS = {
 }
 
 if __name__ == "__main__":
+    import sys as _sys
+    if len(_sys.argv) > 1 and _sys.argv[1] == "pipe":
+        for nm, fn in PIPE_WORKLOADS.items():
+            make_pipeline(nm, fn())
+        _sys.exit(0)
     for nm, fn in PATH_WORKLOADS.items():
         make_paths(nm, fn(), max_hap=8 if nm == "paths_dense_2s" else 32)
     make("gibbs_snv_1s", synth.config_a(n_variants=1200, length=120_000), 160)
