@@ -1,0 +1,177 @@
+"""Host mirror of the stage order of `bayesTyper cluster` + `bayesTyper genotype`
+(src/bayesTyper/main.cpp:233-252 and :594-643) over the C ABI, for non-nested candidate sets.
+
+Every per-k-mer / per-cluster computation runs in libbtgpu kernels; this module only sequences
+them (like KmerCounter / InferenceEngine do in the reference) and moves arrays across the boundary.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+
+import numpy as np
+import torch
+
+from . import capi, engine, graph_builder, kmer_pipeline, unit as U
+
+K = 55
+
+
+class GraphsDesc(C.Structure):
+    _fields_ = [("n_clusters", C.c_uint32)] + [(n, C.c_void_p) for n in
+                ("cl_vertex_off", "v_seq_off", "seq", "v_flags", "v_in_off", "v_in_src", "cl_group", "cl_idx")]
+
+
+@dataclasses.dataclass
+class Options:
+    """Defaults of src/bayesTyper/main.cpp:125-137,378-403."""
+    random_seed: int = 20190401
+    max_sample_haplotypes: int = 32
+    gibbs_burn_in: int = 100
+    gibbs_samples: int = 250
+    n_chains: int = 20
+    kmer_subsampling_rate: float = 0.1
+    max_haplotype_variant_kmers: int = 500
+    noise_rate_prior: tuple = (1.0, 0.01)
+    min_genotype_posterior: float = 0.99
+    min_number_of_kmers: float = 1.0
+    disable_observed_kmers: bool = False
+    bloom_fpr: float = 0.001          # bayesTyperTools makeBloom default (src/bayesTyperTools/main.cpp:127)
+    max_parameter_kmers: int = 1_000_000
+
+
+def find_variant_cluster_paths(lib, graphs: dict, sample_blooms, opt: Options):
+    """KmerCounter::findVariantClusterPaths (KmerCounter.cpp:70-103): samples in order, one Bloom at a time."""
+    gco = graphs["group_cluster_off"]
+    keep = {
+        "cl_vertex_off": np.ascontiguousarray(graphs["cl_vertex_off"], np.uint64), "v_seq_off": np.ascontiguousarray(graphs["v_seq_off"], np.uint64),
+        "seq": np.ascontiguousarray(graphs["seq"], np.uint8), "v_flags": np.ascontiguousarray(graphs["v_flags"], np.uint8),
+        "v_in_off": np.ascontiguousarray(graphs["v_in_off"], np.uint64), "v_in_src": np.ascontiguousarray(graphs["v_in_src"], np.uint32),
+        "cl_group": np.repeat(np.arange(len(gco) - 1, dtype=np.uint32), np.diff(gco).astype(np.int64)),
+        "cl_idx": np.ascontiguousarray(graphs["cluster_idx"], np.uint32),
+    }
+    d = GraphsDesc()
+    d.n_clusters = len(keep["cl_vertex_off"]) - 1
+    for k, v in keep.items():
+        setattr(d, k, v.ctypes.data)
+    gr = capi.check(lib.btg_graphs_upload(C.addressof(d), len(sample_blooms), opt.max_sample_haplotypes), lib)
+    try:
+        for s, b in enumerate(sample_blooms):
+            capi.check(lib.btg_find_sample_paths(gr, b, s, opt.random_seed, opt.max_sample_haplotypes), lib)
+        n_paths = np.zeros(d.n_clusters, np.uint32)
+        off = np.zeros(d.n_clusters + 1, np.uint64)
+        capi.check(lib.btg_get_best_paths(gr, capi.ptr(n_paths), capi.ptr(off), None, 0), lib)
+        mem = np.zeros(int(off[-1]), np.uint8)
+        capi.check(lib.btg_get_best_paths(gr, capi.ptr(n_paths), capi.ptr(off), capi.ptr(mem), mem.size), lib)
+    finally:
+        lib.btg_graphs_free(gr)
+    return n_paths.astype(np.int64), mem
+
+
+def estimate_nb_parameters(pipe: kmer_pipeline.KmerPipeline, reference: bytes, regions, spectra_dev, genders, opt: Options, ploidy=(2, 2)):
+    """Parameter k-mers -> per-sample negative-binomial (p, size): the genotype-side half of
+    countInterclusterParameterKmers + calculateKmerStats + setGenomicCountDistributions
+    (KmerCounter.cpp:171-250, KmerHash.cpp:257-347, CountDistribution.cpp:66-141).
+    Parameter k-mers = inter-cluster reference k-mers that are not path k-mers, Bernoulli-subsampled to at most
+    3 x max_parameter_kmers and capped at max_parameter_kmers (the reference's draw order comes from mt19937 +
+    hash iteration order; here it is a seeded device permutation — same population, different sample)."""
+    lib, dev = pipe.lib, pipe.dev
+    with torch.cuda.stream(pipe.ext):
+        seq = np.frombuffer(reference, np.uint8)
+        parts = []
+        for a, b in regions:
+            parts.append(seq[a:b + 1]); parts.append(np.frombuffer(b"N", np.uint8))
+        buf = torch.from_numpy(np.concatenate(parts)).to(dev)
+        n = buf.numel()
+        km = torch.empty((n, 2), dtype=torch.int64, device=dev)
+        valid = torch.empty(n, dtype=torch.uint8, device=dev)
+        capi.check(lib.btg_scan_sequence_dev(buf.data_ptr(), n, km.data_ptr(), valid.data_ptr(), None), lib)
+        km = km[valid.to(torch.bool)]
+        # distinct k-mers + genomic multiplicity
+        o = torch.sort(km[:, 0], stable=True).indices
+        o = o[torch.sort(km[o, 1], stable=True).indices]
+        s = km[o]
+        new = torch.ones(len(s), dtype=torch.bool, device=dev)
+        new[1:] = (s[1:] != s[:-1]).any(1)
+        keys = s[new].contiguous()
+        occ = torch.diff(torch.cat([torch.nonzero(new).squeeze(1), torch.tensor([len(s)], device=dev)]))
+        idx = torch.empty(len(keys), dtype=torch.int64, device=dev)
+        capi.check(lib.btg_table_lookup_dev(pipe.kw0.data_ptr(), pipe.kw1.data_ptr(), pipe.n_keys, keys.data_ptr(), len(keys), idx.data_ptr(), None), lib)
+        not_path = idx < 0
+        keys, occ = keys[not_path], occ[not_path]
+        total = int(km.shape[0])
+        frac = min(1.0, 3.0 * opt.max_parameter_kmers / max(total, 1))
+        g = torch.Generator(device=dev).manual_seed(opt.random_seed)
+        sel = torch.rand(len(keys), device=dev, generator=g) < frac
+        keys, occ = keys[sel], occ[sel]
+        if len(keys) > opt.max_parameter_kmers:
+            perm = torch.randperm(len(keys), device=dev, generator=g)[:opt.max_parameter_kmers].sort().values
+            keys, occ = keys[perm], occ[perm]
+        kw0, kw1 = keys[:, 0].contiguous(), keys[:, 1].contiguous()
+        S = len(spectra_dev)
+        counts = torch.zeros((len(keys), S), dtype=torch.uint8, device=dev)
+        rec = torch.zeros(len(keys), dtype=torch.uint8, device=dev)
+        for si, (kd, cd_) in enumerate(spectra_dev):
+            capi.check(lib.btg_table_add_sample_kmers_dev(kw0.data_ptr(), kw1.data_ptr(), len(keys), kd.data_ptr(), cd_.data_ptr(), cd_.numel(), S, si,
+                                                          counts.data_ptr(), rec.data_ptr(), None), lib)
+        nb_p, nb_size, used = [], [], []
+        for si in range(S):
+            mult = torch.clamp(occ * ploidy[0 if genders[si] in ("F", 0) else 1], max=255)
+            hist = torch.bincount(mult, minlength=256)[1:33]            # max_nb_kmer_multiplicity = 32 (CountDistribution.cpp:42)
+            m = int(torch.argmax(hist)) + 1                             # first maximum, as the reference's strict '>' scan
+            c = counts[mult == m, si].to(torch.float64)
+            mean = float(c.mean()); var = float(c.var(unbiased=True))
+            p, size = C.c_double(), C.c_double()
+            lib.btg_nb_moments_to_parameters(mean, var, m, C.byref(p), C.byref(size))
+            nb_p.append(p.value); nb_size.append(size.value); used.append((m, int(hist[m - 1]), mean, var))
+    pipe.ext.synchronize()
+    return np.array(nb_p), np.array(nb_size), used
+
+
+def run(chrom: str, reference: bytes, variants, spectra, genders, opt: Options | None = None, nb_params=None, noise_rates=None):
+    """cluster + genotype for one contig and S samples; returns (graphs, unit, result arrays, info)."""
+    opt = opt or Options()
+    lib = capi.load()
+    S = len(spectra)
+    info = {}
+    graphs = graph_builder.build_unit_graphs(chrom, reference, variants)
+    regions = graph_builder.intercluster_regions(len(reference), variants)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    spectra_dev = [(torch.from_numpy(np.ascontiguousarray(k).view(np.int64)).to(dev), torch.from_numpy(np.ascontiguousarray(c)).to(dev)) for k, c in spectra]
+    torch.cuda.synchronize()
+    blooms = []
+    for kd, _ in spectra_dev:                                         # bayesTyperTools makeBloom
+        b = capi.check(lib.btg_bloom_create(kd.shape[0], opt.bloom_fpr, K), lib)
+        capi.check(lib.btg_bloom_insert_dev(b, kd.data_ptr(), kd.shape[0], None), lib)
+        blooms.append(b)
+    n_paths, mem = find_variant_cluster_paths(lib, graphs, blooms, opt)
+    for b in blooms:
+        lib.btg_bloom_free(b)
+    pipe = kmer_pipeline.KmerPipeline(graphs, n_paths, mem, S, genders)
+    info["n_path_kmers"] = pipe.enumerate_path_kmers()
+    male_ploidy = 1 if chrom.lower() in ("x", "chrx") else (1 if chrom.lower() in ("y", "chry") else 2)
+    female_ploidy = 0 if chrom.lower() in ("y", "chry") else 2
+    pipe.scan_regions(reference, regions, female_ploidy, male_ploidy, False)
+    for s, (kd, cdv) in enumerate(spectra_dev):
+        pipe.add_sample(s, kd, cdv)
+    ploidy = np.tile(np.array([female_ploidy if g in ("F", 0) else male_ploidy for g in genders], np.uint8), len(graphs["group_cluster_off"]) - 1)
+    unit = pipe.build_unit(multigroup_bloom=None, ploidy=ploidy)
+    if nb_params is None:
+        nb_p, nb_size, used = estimate_nb_parameters(pipe, reference, regions, spectra_dev, genders, opt, (female_ploidy, male_ploidy))
+        info["nb_fit"] = used
+    else:
+        nb_p, nb_size = nb_params
+    cd = engine.CountDistribution(nb_p, nb_size, opt.noise_rate_prior)
+    eng = engine.InferenceEngine(unit)
+    gopts = U.default_opts(seed=opt.random_seed, burn=opt.gibbs_burn_in, samples=opt.gibbs_samples, chains=opt.n_chains, rate=opt.kmer_subsampling_rate,
+                           max_hv=opt.max_haplotype_variant_kmers, min_gpp=opt.min_genotype_posterior, min_kmers=opt.min_number_of_kmers,
+                           min_frac=None if opt.disable_observed_kmers else U.min_fraction_observed(nb_p, nb_size))
+    if noise_rates is None:
+        info["noise_trace"] = eng.estimate_noise(cd, gopts)
+    else:
+        cd.set_noise_rates(noise_rates)
+    info["noise_rates"] = cd.noise_rates()
+    info["nb"] = (nb_p, nb_size)
+    res = eng.estimate_genotypes(cd, gopts)
+    eng.close(); cd.close()
+    return graphs, unit, res, info

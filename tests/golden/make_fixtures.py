@@ -129,6 +129,43 @@ def make_pipeline(name, workload, seed=20190401, n_errors=3000):
     print(name, "clusters", len(g["cl_vertex_off"]) - 1, "rows", len(h["k_has_counts"]), "regions", len(regions), "multigroup n", mg_meta[0])
 
 
+def make_e2e(name, workload, seed=20190401, n_errors=20000):
+    """End-to-end fixture: what the reference's cluster + genotype wrote for a workload (VCF fields, NB fit, noise rates)."""
+    with tempfile.TemporaryDirectory() as td:
+        spectra = synth.sample_spectra(workload, 4, n_errors)
+        wd = synth.write_workdir(workload, td, spectra=spectra)
+        subprocess.check_call([str(BTREF), "run", "--workdir", str(wd), "--threads", "8", "--seed", str(seed), "--dump-graphs"], stdout=subprocess.DEVNULL)
+        out = Path(wd) / "ref_out"
+        g = btd.read(out / "graphs.btd"); t = btd.read(out / "tables.btd")
+        _, rows = vcfio.read_vcf(out / "bayestyper.vcf")
+    S = len(spectra)
+    byid = {r["id"]: r for r in rows}
+    ids = [bytes(g["var_ids"][g["var_id_off"][i]:g["var_id_off"][i + 1]]).decode() for i in range(len(g["var_pos"]))]
+    nA = (1 + g["var_dep"].astype(np.int64) + g["var_nalt"]).astype(np.int64)
+    gt = np.zeros((len(ids), S, 2), np.uint16); gq = np.zeros((len(ids), S), np.uint32)
+    gpp_off = np.concatenate([[0], np.cumsum(S * nA * (nA + 1) // 2)]); gpp = np.zeros(int(gpp_off[-1]), np.float32)
+    for j, i in enumerate(ids):
+        nG = int(nA[j] * (nA[j] + 1) // 2)
+        for s_ in range(S):
+            sr = byid[i]["samples"][s_]
+            a = sr["GT"].replace("|", "/").split("/")
+            gt[j, s_, 0] = 0xFFFF if a[0] == "." else int(a[0])
+            gt[j, s_, 1] = (0xFFFF if a[1] == "." else int(a[1])) if len(a) > 1 else 0xFFFE
+            gq[j, s_] = sr.get("GQ", 0)
+            if "GPP" in sr:
+                gp = np.array(sr["GPP"], np.float32)
+                gpp[int(gpp_off[j]) + s_ * nG:int(gpp_off[j]) + s_ * nG + len(gp)] = gp
+    pack = {"ref.gt": gt.reshape(-1), "ref.gq": gq.reshape(-1), "ref.gpp": gpp, "ref.var_pos": g["var_pos"], "tab.nb_p_size": t["nb_p_size"],
+            "tab.noise_rates": t["noise_rates"], "meta.seed": np.array([seed], np.uint32), "meta.n_errors": np.array([n_errors], np.uint32)}
+    btd.write(Path(__file__).parent / f"{name}.btd", pack)
+    print(name, "variants", len(ids), "nb", t["nb_p_size"].tolist(), "noise", t["noise_rates"].tolist())
+
+
+E2E_WORKLOADS = {
+    "e2e_snv_1s": lambda: synth.config_a(n_variants=1500, length=150_000),
+    "e2e_mixed_3s": lambda: synth.small_mixed(800, 80_000, 3, seed=71),
+}
+
 PIPE_WORKLOADS = {
     "pipe_snv_1s": lambda: synth.config_a(n_variants=500, length=50_000),
     "pipe_mixed_3s": lambda: synth.small_mixed(350, 25_000, 3, seed=52),
@@ -146,6 +183,10 @@ if __name__ == "__main__":
     if len(_sys.argv) > 1 and _sys.argv[1] == "pipe":
         for nm, fn in PIPE_WORKLOADS.items():
             make_pipeline(nm, fn())
+        _sys.exit(0)
+    if len(_sys.argv) > 1 and _sys.argv[1] == "e2e":
+        for nm, fn in E2E_WORKLOADS.items():
+            make_e2e(nm, fn())
         _sys.exit(0)
     for nm, fn in PATH_WORKLOADS.items():
         make_paths(nm, fn(), max_hap=8 if nm == "paths_dense_2s" else 32)
