@@ -130,8 +130,22 @@ __global__ void __launch_bounds__(128) k_path_alleles(PathWalkGraphs g, uint64_t
 }
 
 // ---- exact table probes ------------------------------------------------------------------------
-__device__ __forceinline__ int64_t table_find(const int64_t *__restrict__ kw0, const int64_t *__restrict__ kw1, int64_t n, int64_t w0, int64_t w1) {
+// Optional prefix index (like KMC's prefix LUT): lut[b] = first key whose top `lut_bits` bits of the 46-bit word 1
+// equal b; narrows the binary search to the bucket (typically 1-2 keys) at the cost of one 8 B read.
+struct TableIndex {
+    const int64_t *lut;  // [2^lut_bits + 1] or nullptr
+    int shift;           // 46 - lut_bits
+};
+
+__device__ __forceinline__ int64_t table_find(const int64_t *__restrict__ kw0, const int64_t *__restrict__ kw1, int64_t n, int64_t w0, int64_t w1,
+                                              const TableIndex ix = TableIndex{nullptr, 0}) {
     int64_t lo = 0, hi = n;
+    if (ix.lut) {
+        const int64_t b = w1 >> ix.shift;
+        lo = __ldg(ix.lut + b);
+        hi = __ldg(ix.lut + b + 1);
+    }
+    const int64_t end = hi;
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
         const int64_t m1 = __ldg(kw1 + mid);
@@ -140,7 +154,7 @@ __device__ __forceinline__ int64_t table_find(const int64_t *__restrict__ kw0, c
         else less = __ldg(kw0 + mid) < w0;
         if (less) lo = mid + 1; else hi = mid;
     }
-    if (lo < n && __ldg(kw1 + lo) == w1 && __ldg(kw0 + lo) == w0) return lo;
+    if (lo < end && __ldg(kw1 + lo) == w1 && __ldg(kw0 + lo) == w0) return lo;
     return -1;
 }
 
@@ -159,10 +173,10 @@ __device__ __forceinline__ void sat_add_u8(uint8_t *p, uint32_t add) {  // updat
 // KmerCounter::parseSampleKmersCallBack: one KMC record per thread (16 B k-mer + 1 B count streamed once)
 __global__ void __launch_bounds__(256) k_table_add_sample(const int64_t *__restrict__ kw0, const int64_t *__restrict__ kw1, int64_t n_keys,
                                                           const longlong2 *__restrict__ kmers, const uint8_t *__restrict__ counts, size_t n,
-                                                          uint32_t S, uint32_t sample, uint8_t *table_counts, uint8_t *has_record) {
+                                                          uint32_t S, uint32_t sample, uint8_t *table_counts, uint8_t *has_record, TableIndex ix) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const longlong2 k = __ldg(kmers + i);
-        const int64_t idx = table_find(kw0, kw1, n_keys, k.x, k.y);
+        const int64_t idx = table_find(kw0, kw1, n_keys, k.x, k.y, ix);
         if (idx >= 0) {
             sat_add_u8(table_counts + (size_t)idx * S + sample, counts[i]);
             has_record[idx] = 1;
@@ -174,7 +188,7 @@ __global__ void __launch_bounds__(256) k_table_add_sample(const int64_t *__restr
 constexpr int kScanChunk = 64;
 __global__ void __launch_bounds__(256) k_table_scan_region(const int64_t *__restrict__ kw0, const int64_t *__restrict__ kw1, int64_t n_keys,
                                                            const char *__restrict__ seq, size_t len, uint32_t is_decoy, uint32_t ploidy_f, uint32_t ploidy_m,
-                                                           uint8_t *ic, uint8_t *max_mult, uint8_t *decoy, uint8_t *has_record) {
+                                                           uint8_t *ic, uint8_t *max_mult, uint8_t *decoy, uint8_t *has_record, TableIndex ix) {
     const size_t nchunks = (len + kScanChunk - 1) / kScanChunk;
     for (size_t ch = blockIdx.x * (size_t)blockDim.x + threadIdx.x; ch < nchunks; ch += (size_t)gridDim.x * blockDim.x) {
         const size_t p0 = ch * kScanChunk, p1 = p0 + kScanChunk < len ? p0 + kScanChunk : len;
@@ -188,7 +202,7 @@ __global__ void __launch_bounds__(256) k_table_scan_region(const int64_t *__rest
             if (complete && p >= p0) {
                 uint64_t w0, w1;
                 to_boundary(roll.canonical(), w0, w1);
-                const int64_t idx = table_find(kw0, kw1, n_keys, (int64_t)w0, (int64_t)w1);
+                const int64_t idx = table_find(kw0, kw1, n_keys, (int64_t)w0, (int64_t)w1, ix);
                 if (idx >= 0) {
                     has_record[idx] = 1;
                     sat_add_u8(max_mult + idx, 1);  // max_haploid_multiplicity (KmerCounts.cpp:100)
@@ -201,10 +215,10 @@ __global__ void __launch_bounds__(256) k_table_scan_region(const int64_t *__rest
 }
 
 __global__ void __launch_bounds__(256) k_table_lookup(const int64_t *__restrict__ kw0, const int64_t *__restrict__ kw1, int64_t n_keys,
-                                                      const longlong2 *__restrict__ kmers, size_t n, int64_t *__restrict__ idx_out) {
+                                                      const longlong2 *__restrict__ kmers, size_t n, int64_t *__restrict__ idx_out, TableIndex ix) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const longlong2 k = __ldg(kmers + i);
-        idx_out[i] = table_find(kw0, kw1, n_keys, k.x, k.y);
+        idx_out[i] = table_find(kw0, kw1, n_keys, k.x, k.y, ix);
     }
 }
 
@@ -242,10 +256,20 @@ int btg_path_alleles_dev(const btg_pathwalk_desc *d, const uint64_t *cl_var_off,
     return BTG_OK;
 }
 
+static TableIndex g_index{nullptr, 0};
+
+// Installs (or clears, lut = NULL) the prefix index used by the table probes that follow: lut[b] = index of the first
+// key whose word-1 top `lut_bits` bits (of 46) are >= b, for b in [0, 2^lut_bits]; built by the caller from the keys.
+int btg_table_set_index_dev(const int64_t *lut, int lut_bits) {
+    if (lut && (lut_bits < 1 || lut_bits > 30)) { set_error("lut_bits must be 1..30"); return BTG_EINVAL; }
+    g_index = TableIndex{lut, lut ? 2 * K - 64 - lut_bits : 0};
+    return BTG_OK;
+}
+
 int btg_table_lookup_dev(const int64_t *key_w0, const int64_t *key_w1, int64_t n_keys, const uint64_t *kmers, size_t n, int64_t *idx_out, void *stream) {
     BTG_REQUIRE_INIT();
     if (n == 0) return BTG_OK;
-    k_table_lookup<<<btg_grid_for(n, 256, 8), 256, 0, pick_stream(stream)>>>(key_w0, key_w1, n_keys, (const longlong2 *)kmers, n, idx_out);
+    k_table_lookup<<<btg_grid_for(n, 256, 8), 256, 0, pick_stream(stream)>>>(key_w0, key_w1, n_keys, (const longlong2 *)kmers, n, idx_out, g_index);
     BTG_LAUNCHED();
     BTG_CUDA(cudaGetLastError());
     return BTG_OK;
@@ -257,7 +281,7 @@ int btg_table_add_sample_kmers_dev(const int64_t *key_w0, const int64_t *key_w1,
     if (sample_idx >= n_samples) { set_error("sample index out of range"); return BTG_EINVAL; }
     if (n == 0) return BTG_OK;
     k_table_add_sample<<<btg_grid_for(n, 256, 8), 256, 0, pick_stream(stream)>>>(key_w0, key_w1, n_keys, (const longlong2 *)kmers, counts, n, n_samples,
-                                                                               sample_idx, table_counts, has_record);
+                                                                               sample_idx, table_counts, has_record, g_index);
     BTG_LAUNCHED();
     BTG_CUDA(cudaGetLastError());
     return BTG_OK;
@@ -269,7 +293,7 @@ int btg_table_scan_region_dev(const int64_t *key_w0, const int64_t *key_w1, int6
     if (len == 0) return BTG_OK;
     const size_t nchunks = (len + kScanChunk - 1) / kScanChunk;
     k_table_scan_region<<<btg_grid_for(nchunks, 256, 4), 256, 0, pick_stream(stream)>>>(key_w0, key_w1, n_keys, seq, len, is_decoy ? 1u : 0u, ploidy_female,
-                                                                                       ploidy_male, ic, max_mult, decoy, has_record);
+                                                                                       ploidy_male, ic, max_mult, decoy, has_record, g_index);
     BTG_LAUNCHED();
     BTG_CUDA(cudaGetLastError());
     return BTG_OK;

@@ -68,7 +68,7 @@ def find_variant_cluster_paths(lib, graphs: dict, sample_blooms, opt: Options):
     return n_paths.astype(np.int64), mem
 
 
-def estimate_nb_parameters(pipe: kmer_pipeline.KmerPipeline, reference: bytes, regions, spectra_dev, genders, opt: Options, ploidy=(2, 2)):
+def estimate_nb_parameters(pipe: kmer_pipeline.KmerPipeline, region_buf, spectra_dev, genders, opt: Options, ploidy=(2, 2)):
     """Parameter k-mers -> per-sample negative-binomial (p, size): the genotype-side half of
     countInterclusterParameterKmers + calculateKmerStats + setGenomicCountDistributions
     (KmerCounter.cpp:171-250, KmerHash.cpp:257-347, CountDistribution.cpp:66-141).
@@ -77,11 +77,7 @@ def estimate_nb_parameters(pipe: kmer_pipeline.KmerPipeline, reference: bytes, r
     hash iteration order; here it is a seeded device permutation — same population, different sample)."""
     lib, dev = pipe.lib, pipe.dev
     with torch.cuda.stream(pipe.ext):
-        seq = np.frombuffer(reference, np.uint8)
-        parts = []
-        for a, b in regions:
-            parts.append(seq[a:b + 1]); parts.append(np.frombuffer(b"N", np.uint8))
-        buf = torch.from_numpy(np.concatenate(parts)).to(dev)
+        buf = region_buf
         n = buf.numel()
         km = torch.empty((n, 2), dtype=torch.int64, device=dev)
         valid = torch.empty(n, dtype=torch.uint8, device=dev)
@@ -96,6 +92,7 @@ def estimate_nb_parameters(pipe: kmer_pipeline.KmerPipeline, reference: bytes, r
         keys = s[new].contiguous()
         occ = torch.diff(torch.cat([torch.nonzero(new).squeeze(1), torch.tensor([len(s)], device=dev)]))
         idx = torch.empty(len(keys), dtype=torch.int64, device=dev)
+        pipe.use_index()
         capi.check(lib.btg_table_lookup_dev(pipe.kw0.data_ptr(), pipe.kw1.data_ptr(), pipe.n_keys, keys.data_ptr(), len(keys), idx.data_ptr(), None), lib)
         not_path = idx < 0
         keys, occ = keys[not_path], occ[not_path]
@@ -111,6 +108,7 @@ def estimate_nb_parameters(pipe: kmer_pipeline.KmerPipeline, reference: bytes, r
         S = len(spectra_dev)
         counts = torch.zeros((len(keys), S), dtype=torch.uint8, device=dev)
         rec = torch.zeros(len(keys), dtype=torch.uint8, device=dev)
+        pipe.use_index(False)                       # the parameter k-mers are a second, un-indexed table
         for si, (kd, cd_) in enumerate(spectra_dev):
             capi.check(lib.btg_table_add_sample_kmers_dev(kw0.data_ptr(), kw1.data_ptr(), len(keys), kd.data_ptr(), cd_.data_ptr(), cd_.numel(), S, si,
                                                           counts.data_ptr(), rec.data_ptr(), None), lib)
@@ -128,36 +126,110 @@ def estimate_nb_parameters(pipe: kmer_pipeline.KmerPipeline, reference: bytes, r
     return np.array(nb_p), np.array(nb_size), used
 
 
-def run(chrom: str, reference: bytes, variants, spectra, genders, opt: Options | None = None, nb_params=None, noise_rates=None):
-    """cluster + genotype for one contig and S samples; returns (graphs, unit, result arrays, info)."""
+@dataclasses.dataclass
+class Inputs:
+    """Everything `cluster` + `genotype` read for one contig: host-side (the reference's files) ..."""
+    chrom: str
+    reference: bytes
+    variants: list
+    genders: list
+    spectra: list                      # per sample (kmers (n,2) uint64, counts (n,) uint8) numpy / pinned torch
+    blooms: list = None                # per sample (bytes uint8, num_kmers, num_bits) = <prefix>.bloomData/.bloomMeta; None = build
+    graphs: dict = None                # filled by prepare()
+    regions: list = None
+    # ... and optionally already resident in HBM
+    spectra_dev: list = None
+    blooms_dev: list = None
+    region_buf_dev: object = None
+
+    def prepare(self):
+        if self.graphs is None:
+            self.graphs = graph_builder.build_unit_graphs(self.chrom, self.reference, self.variants)
+            self.regions = graph_builder.intercluster_regions(len(self.reference), self.variants)
+        return self
+
+    def make_resident(self, lib, opt: "Options"):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if self.spectra_dev is None:
+            self.spectra_dev = [(_to_dev(k, np.int64, dev), _to_dev(c, np.uint8, dev)) for k, c in self.spectra]
+        torch.cuda.synchronize()
+        if self.blooms_dev is None:
+            self.blooms_dev = []
+            for kd, _ in self.spectra_dev:                             # bayesTyperTools makeBloom
+                b = capi.check(lib.btg_bloom_create(kd.shape[0], opt.bloom_fpr, K), lib)
+                capi.check(lib.btg_bloom_insert_dev(b, kd.data_ptr(), kd.shape[0], None), lib)
+                self.blooms_dev.append(b)
+        if self.region_buf_dev is None:
+            self.region_buf_dev = torch.from_numpy(_region_buffer(self.reference, self.regions)).to(dev)
+        torch.cuda.synchronize()
+        return self
+
+    def free(self, lib):
+        for b in self.blooms_dev or []:
+            lib.btg_bloom_free(b)
+        self.blooms_dev = None
+
+
+def _to_dev(a, dtype, dev):
+    if isinstance(a, torch.Tensor):
+        return a.to(dev, non_blocking=True)
+    a = np.ascontiguousarray(a)
+    return torch.from_numpy(a.view(dtype) if a.dtype != dtype else a).to(dev)
+
+
+def _region_buffer(reference: bytes, regions) -> np.ndarray:
+    seq = np.frombuffer(reference, np.uint8)
+    parts = []
+    sep = np.frombuffer(b"N", np.uint8)
+    for a, b in regions:
+        parts.append(seq[a:b + 1]); parts.append(sep)
+    return np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+
+
+def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rates=None, resident: bool = False, want_unit: bool = False):
+    """One pass of both hot paths: path search -> k-mer table -> haplotype candidates -> NB fit -> noise -> Gibbs.
+    resident=True uses the device copies made by Inputs.make_resident (the `value` leg of bench.py); otherwise every
+    input crosses the boundary from host memory inside this call (the `e2e` leg)."""
     opt = opt or Options()
     lib = capi.load()
-    S = len(spectra)
-    info = {}
-    graphs = graph_builder.build_unit_graphs(chrom, reference, variants)
-    regions = graph_builder.intercluster_regions(len(reference), variants)
+    inp.prepare()
+    S = len(inp.spectra) if inp.spectra is not None else len(inp.spectra_dev)
     dev = torch.device("cuda", torch.cuda.current_device())
-    spectra_dev = [(torch.from_numpy(np.ascontiguousarray(k).view(np.int64)).to(dev), torch.from_numpy(np.ascontiguousarray(c)).to(dev)) for k, c in spectra]
-    torch.cuda.synchronize()
-    blooms = []
-    for kd, _ in spectra_dev:                                         # bayesTyperTools makeBloom
-        b = capi.check(lib.btg_bloom_create(kd.shape[0], opt.bloom_fpr, K), lib)
-        capi.check(lib.btg_bloom_insert_dev(b, kd.data_ptr(), kd.shape[0], None), lib)
-        blooms.append(b)
-    n_paths, mem = find_variant_cluster_paths(lib, graphs, blooms, opt)
-    for b in blooms:
-        lib.btg_bloom_free(b)
-    pipe = kmer_pipeline.KmerPipeline(graphs, n_paths, mem, S, genders)
+    info = {}
+    own_blooms = False
+    if resident:
+        spectra_dev, blooms, region_buf = inp.spectra_dev, inp.blooms_dev, inp.region_buf_dev
+    else:
+        spectra_dev = [(_to_dev(k, np.int64, dev), _to_dev(c, np.uint8, dev)) for k, c in inp.spectra]
+        torch.cuda.synchronize()
+        own_blooms = True
+        if inp.blooms is not None:                                      # KmerBloom(prefix): load the sample filters
+            blooms = [capi.check(lib.btg_bloom_from_bytes(capi.ptr(b), nk, nb, K), lib) for b, nk, nb in inp.blooms]
+        else:
+            blooms = []
+            for kd, _ in spectra_dev:
+                b = capi.check(lib.btg_bloom_create(kd.shape[0], opt.bloom_fpr, K), lib)
+                capi.check(lib.btg_bloom_insert_dev(b, kd.data_ptr(), kd.shape[0], None), lib)
+                blooms.append(b)
+        region_buf = torch.from_numpy(_region_buffer(inp.reference, inp.regions)).to(dev)
+        torch.cuda.synchronize()
+    chrom = inp.chrom.lower()
+    male_ploidy = 1 if chrom in ("x", "chrx", "y", "chry") else 2
+    female_ploidy = 0 if chrom in ("y", "chry") else 2
+    n_paths, mem = find_variant_cluster_paths(lib, inp.graphs, blooms, opt)
+    if own_blooms:
+        for b in blooms:
+            lib.btg_bloom_free(b)
+    pipe = kmer_pipeline.KmerPipeline(inp.graphs, n_paths, mem, S, inp.genders)
     info["n_path_kmers"] = pipe.enumerate_path_kmers()
-    male_ploidy = 1 if chrom.lower() in ("x", "chrx") else (1 if chrom.lower() in ("y", "chry") else 2)
-    female_ploidy = 0 if chrom.lower() in ("y", "chry") else 2
-    pipe.scan_regions(reference, regions, female_ploidy, male_ploidy, False)
+    pipe.scan_buffer(region_buf, female_ploidy, male_ploidy, False)
     for s, (kd, cdv) in enumerate(spectra_dev):
         pipe.add_sample(s, kd, cdv)
-    ploidy = np.tile(np.array([female_ploidy if g in ("F", 0) else male_ploidy for g in genders], np.uint8), len(graphs["group_cluster_off"]) - 1)
+    G = len(inp.graphs["group_cluster_off"]) - 1
+    ploidy = np.tile(np.array([female_ploidy if g in ("F", 0) else male_ploidy for g in inp.genders], np.uint8), G)
     unit = pipe.build_unit(multigroup_bloom=None, ploidy=ploidy)
     if nb_params is None:
-        nb_p, nb_size, used = estimate_nb_parameters(pipe, reference, regions, spectra_dev, genders, opt, (female_ploidy, male_ploidy))
+        nb_p, nb_size, used = estimate_nb_parameters(pipe, region_buf, spectra_dev, inp.genders, opt, (female_ploidy, male_ploidy))
         info["nb_fit"] = used
     else:
         nb_p, nb_size = nb_params
@@ -167,11 +239,18 @@ def run(chrom: str, reference: bytes, variants, spectra, genders, opt: Options |
                            max_hv=opt.max_haplotype_variant_kmers, min_gpp=opt.min_genotype_posterior, min_kmers=opt.min_number_of_kmers,
                            min_frac=None if opt.disable_observed_kmers else U.min_fraction_observed(nb_p, nb_size))
     if noise_rates is None:
-        info["noise_trace"] = eng.estimate_noise(cd, gopts)
+        info["noise_trace"] = eng.estimate_noise(cd, gopts, want_trace=False)
     else:
         cd.set_noise_rates(noise_rates)
     info["noise_rates"] = cd.noise_rates()
     info["nb"] = (nb_p, nb_size)
     res = eng.estimate_genotypes(cd, gopts)
+    info["n_clusters"] = unit.Cn
     eng.close(); cd.close()
-    return graphs, unit, res, info
+    return (inp.graphs, unit if want_unit else None, res, info)
+
+
+def run(chrom: str, reference: bytes, variants, spectra, genders, opt: Options | None = None, nb_params=None, noise_rates=None):
+    """cluster + genotype for one contig and S samples from host inputs; returns (graphs, unit, result arrays, info)."""
+    inp = Inputs(chrom, reference, variants, list(genders), spectra)
+    return genotype(inp, opt, nb_params, noise_rates, resident=False, want_unit=True)

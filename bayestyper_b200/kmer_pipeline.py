@@ -138,6 +138,11 @@ class KmerPipeline:
         self.n_keys = int(self.kw0.numel())
         self.occ_key = torch.empty(N, dtype=torch.int64, device=d)
         self.occ_key[o] = key_of_sorted
+        # prefix index over word 1 (46 bits): ~1 key per bucket
+        self.lut_bits = int(min(24, max(8, np.ceil(np.log2(max(self.n_keys, 2))))))
+        buckets = self.kw1 >> (2 * K - 64 - self.lut_bits)
+        cnt = torch.bincount(buckets, minlength=1 << self.lut_bits)
+        self.lut = _excl_cumsum(cnt)
         S = self.S
         self.counts = torch.zeros((self.n_keys, S), dtype=torch.uint8, device=d)
         self.ic = torch.zeros((self.n_keys, 2), dtype=torch.uint8, device=d)
@@ -145,6 +150,10 @@ class KmerPipeline:
         self.decoy = torch.zeros(self.n_keys, dtype=torch.uint8, device=d)
         self.has_record = torch.zeros(self.n_keys, dtype=torch.uint8, device=d)
         return self.n_keys
+
+    def use_index(self, on: bool = True):
+        """(Re)install this table's prefix index in the library (the index is per-process state)."""
+        capi.check(self.lib.btg_table_set_index_dev(self.lut.data_ptr() if on else None, self.lut_bits if on else 0), self.lib)
 
     # ---- countInterclusterKmers -------------------------------------------------------------------------------
     @_on_library_stream
@@ -157,6 +166,16 @@ class KmerPipeline:
         if not parts:
             return
         buf = torch.from_numpy(np.concatenate(parts)).to(self.dev)
+        self._scan(buf, ploidy_female, ploidy_male, is_decoy)
+
+    @_on_library_stream
+    def scan_buffer(self, buf: torch.Tensor, ploidy_female: int = 2, ploidy_male: int = 2, is_decoy: bool = False):
+        """Same, on a resident buffer of regions separated by 'N'."""
+        if buf.numel():
+            self._scan(buf, ploidy_female, ploidy_male, is_decoy)
+
+    def _scan(self, buf, ploidy_female, ploidy_male, is_decoy):
+        self.use_index()
         capi.check(self.lib.btg_table_scan_region_dev(self.kw0.data_ptr(), self.kw1.data_ptr(), self.n_keys, buf.data_ptr(), buf.numel(), int(is_decoy),
                                                       ploidy_female, ploidy_male, self.ic.data_ptr(), self.max_mult.data_ptr(), self.decoy.data_ptr(),
                                                       self.has_record.data_ptr(), self.stream), self.lib)
@@ -164,6 +183,7 @@ class KmerPipeline:
     # ---- parseSampleKmers -------------------------------------------------------------------------------------
     @_on_library_stream
     def add_sample(self, sample_idx: int, kmers_dev: torch.Tensor, counts_dev: torch.Tensor):
+        self.use_index()
         capi.check(self.lib.btg_table_add_sample_kmers_dev(self.kw0.data_ptr(), self.kw1.data_ptr(), self.n_keys, kmers_dev.data_ptr(), counts_dev.data_ptr(),
                                                            counts_dev.numel(), self.S, sample_idx, self.counts.data_ptr(), self.has_record.data_ptr(),
                                                            self.stream), self.lib)

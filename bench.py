@@ -4,13 +4,14 @@
   python bench.py --gpus N --steps K --warmup W          our arm (libbtgpu, B200)
   python bench.py --impl reference ...                   the reference's own CPU code (oracle/_ref/btref)
 
-One "step" = one pass of the hot path over one synthetic batch of the named shape
-(configs[1]: 1 sample, chr22-like SNV+indel candidate set, ~300k variants, k=55):
-  k-mer match   path-k-mer Bloom build (a9) -> sample k-mer stream filtered through it (a11)
-                -> path k-mers probed in the sample Bloom (a7's innermost loop)
-  Gibbs         InferenceEngine::estimateGenotypes: 20 chains x (100 + 250) iterations per cluster (a15-a23)
-`value` times the step with every input already in HBM (CUDA events on the library stream);
-`e2e` times the same step through the host-buffer C ABI (H2D of k-mers + unit descriptors, D2H of results).
+One "step" = one pass of both hot paths over one synthetic batch of the named shape
+(configs[1]: 1 sample, chr22-like SNV+indel candidate set, ~300k variants, k=55), bayestyper_b200/driver.py:
+  k-mer match   findVariantClusterPaths (a7) -> path k-mer enumeration + exact table (a9, a12) -> genome scan (a10)
+                -> sample k-mer stream (a11) -> classify + haplotype candidates (a13, a14) -> NB fit (a18)
+  Gibbs         estimateNoise + estimateGenotypes: 20 chains x (100 + 250) iterations per cluster (a15-a23)
+`value` times the step with the sample k-mer set, sample Bloom and reference already in HBM (CUDA events on the
+library stream); `e2e` runs the same call with every input in host memory (H2D inside the timed region) and the
+results read back.
 N > 1 (torchrun): groups are independent -> every rank runs its own shard of the same size, no
 data-path collective ("weak"); time = max over ranks.
 """
@@ -88,33 +89,67 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # synthetic batch
 # ------------------------------------------------------------------------------------------------
-def build_batch(rank: int, scale: float):
-    """The chr22-like unit (structure enumerated on a 1/tile slice of the chromosome, tiled with
-    independently redrawn counts) + the k-mer sets the k-mer stages stream."""
-    from bayestyper_b200 import synth, synth_unit
-    tile = 10
-    n_var = int(30_000 * scale)
-    length = int(4_080_000 * scale)
-    ref = synth.random_reference(length, 11 + 1000 * rank)
-    var = synth.make_variants(ref, n_var, 12 + 1000 * rank, 0.075, 0.075)
-    g = synth.make_genotypes(len(var), 1, 13 + 1000 * rank)
-    w = synth.Workload("B", "chr22", ref, var, g, ["F"])
-    base = synth_unit.build_unit(w, seed=14 + 1000 * rank)
-    unit = synth_unit.tile_unit(base, tile, seed=15 + 1000 * rank)
-    return unit, tile * len(var)
-
-
-def random_kmers_torch(n, seed, device):
+def device_spectrum(lib, haplotypes, mean, var, seed, n_errors, dev):
+    """The sample's KMC-like k-mer spectrum, synthesised on the device (setup, untimed): canonical 55-mers of the
+    haplotypes (btg_scan_sequence_dev), distinct k-mers with copy number, NB(mean*copies, var*copies) counts."""
     import torch
-    g = torch.Generator(device=device).manual_seed(seed)
-    k = torch.empty((n, 2), dtype=torch.int64, device=device).random_(generator=g)
-    k[:, 1] &= (1 << 46) - 1
-    return k
+    from bayestyper_b200 import capi
+    chunks = []
+    for h in haplotypes:
+        t = torch.frombuffer(bytearray(h), dtype=torch.uint8).to(dev)
+        km = torch.empty((t.numel(), 2), dtype=torch.int64, device=dev)
+        valid = torch.empty(t.numel(), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        capi.check(lib.btg_scan_sequence_dev(t.data_ptr(), t.numel(), km.data_ptr(), valid.data_ptr(), None), lib)
+        torch.cuda.synchronize()
+        chunks.append(km[valid.to(torch.bool)])
+        del km, valid, t
+    km = torch.cat(chunks)
+    del chunks
+    o = torch.sort(km[:, 0], stable=True).indices
+    o = o[torch.sort(km[o, 1], stable=True).indices]
+    km = km[o]
+    del o
+    new = torch.ones(len(km), dtype=torch.bool, device=dev)
+    new[1:] = (km[1:] != km[:-1]).any(1)
+    first = torch.nonzero(new).squeeze(1)
+    copies = torch.diff(torch.cat([first, torch.tensor([len(km)], device=dev)])).to(torch.float64)
+    keys = km[new].contiguous()
+    del km, new
+    g = torch.Generator(device=dev).manual_seed(seed)
+    p = mean / var
+    size = mean * mean / (var - mean)
+    lam = torch._standard_gamma(size * copies, generator=g) * ((1 - p) / p)
+    counts = torch.clamp(torch.poisson(lam, generator=g), max=255).to(torch.uint8)
+    keep = counts > 0
+    keys, counts = keys[keep], counts[keep]
+    if n_errors:
+        err = torch.empty((n_errors, 2), dtype=torch.int64, device=dev).random_(generator=g)
+        err[:, 1] &= (1 << 46) - 1
+        keys = torch.cat([keys, err]); counts = torch.cat([counts, torch.ones(n_errors, dtype=torch.uint8, device=dev)])
+    return keys.contiguous(), counts.contiguous()
+
+
+def build_batch(lib, rank: int, scale: float, dev):
+    """configs[1]: chr22-like reference (10 Mb N + 40.8 Mb), ~300k SNV/indel candidates, 1 female sample at 30x."""
+    from bayestyper_b200 import driver, synth
+    n_var = max(200, int(300_000 * scale))
+    n_prefix = int(10_000_000 * scale)
+    length = int(40_800_000 * scale) + n_prefix
+    ref = synth.random_reference(length, 11 + 1000 * rank, n_prefix)
+    var = synth.make_variants(ref, n_var, 12 + 1000 * rank, 0.075, 0.075, lo=n_prefix + 55)
+    g = synth.make_genotypes(len(var), 1, 13 + 1000 * rank)
+    haps = [synth.apply_variants(ref, var, g[0, :, h]) for h in range(2)]
+    keys, counts = device_spectrum(lib, haps, 15.0, 25.0, 14 + 1000 * rank, int(500_000 * scale), dev)
+    inp = driver.Inputs("chr22", ref, var, ["F"], spectra=None)
+    inp.spectra_dev = [(keys, counts)]
+    inp.prepare()
+    return inp
 
 
 def run_ours(args):
     import torch
-    from bayestyper_b200 import capi, engine, unit as U
+    from bayestyper_b200 import capi, driver
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -128,52 +163,13 @@ def run_ours(args):
     capi.check(lib.btg_init(local_rank), lib)
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.ExternalStream(lib.btg_get_stream(), device=dev)
-    K = 55
+    opt = driver.Options(random_seed=20190401)
 
     t0 = time.time()
-    unit, n_variants = build_batch(rank, args.scale)
-    n_clusters = unit.Cn
-    n_path = int(unit.a["cl_kmer_off"][-1])                   # path k-mers (rows)
-    n_sample = int(80_000_000 * args.scale)                   # distinct 55-mers of a ~40.8 Mb diploid sample
-    setup_unit_s = time.time() - t0
-
-    # --- resident inputs --------------------------------------------------------------------
-    path_k = random_kmers_torch(n_path, 100 + rank, dev)
-    sample_k = random_kmers_torch(n_sample, 200 + rank, dev)
-    n_shared = min(n_path, n_sample) // 2
-    sample_k[:n_shared] = path_k[:n_shared]                   # half of the path k-mers are observed
-    sample_bloom = capi.check(lib.btg_bloom_create(n_sample, 1e-3, K), lib)
-    capi.check(lib.btg_bloom_insert_dev(sample_bloom, sample_k.data_ptr(), n_sample, None), lib)
-    hit_path = torch.zeros(n_path, dtype=torch.uint8, device=dev)
-    hit_sample = torch.zeros(n_sample, dtype=torch.uint8, device=dev)
-    probes = torch.zeros(n_sample, dtype=torch.uint8, device=dev)
-    nb_p, nb_size = np.array([0.6]), np.array([22.5])         # NB(mean 15, var 25) per haploid copy
-    cd = engine.CountDistribution(nb_p, nb_size)
-    cd.set_noise_rates([0.02])
-    opts = U.default_opts(seed=20190401, min_frac=U.min_fraction_observed(nb_p, nb_size), group_base=rank * unit.G)
-    eng = engine.InferenceEngine(unit)
-    res_struct, res_arrays = unit.alloc_result()
-    torch.cuda.synchronize()
-
-    sp = stream.cuda_stream
-
-    def kmer_stage(path_bloom, count_probes=False):
-        capi.check(lib.btg_tbloom_insert_dev(path_bloom, path_k.data_ptr(), n_path, sp), lib)
-        capi.check(lib.btg_tbloom_lookup_dev(path_bloom, sample_k.data_ptr(), n_sample, hit_sample.data_ptr(), sp), lib)
-        capi.check(lib.btg_bloom_lookup_dev(sample_bloom, path_k.data_ptr(), n_path, hit_path.data_ptr(), sp), lib)
-
-    def step_resident():
-        pb = capi.check(lib.btg_tbloom_create(n_path + 1_000_000, 1e-4, K), lib)
-        kmer_stage(pb)
-        capi.check(lib.btg_estimate_genotypes_async(eng.h, cd.h, C.addressof(opts), sp), lib)
-        return pb
-
-    # algorithmic bytes of the stream-filter kernel: 17 B per record + 32 B per executed probe
-    pb0 = capi.check(lib.btg_tbloom_create(n_path + 1_000_000, 1e-4, K), lib)
-    capi.check(lib.btg_tbloom_insert_dev(pb0, path_k.data_ptr(), n_path, sp), lib)
-    stream.synchronize()
-    probes_per_record = measure_tbloom_probes(lib, pb0, sample_k, dev)
-    lib.btg_tbloom_free(pb0)
+    inp = build_batch(lib, rank, args.scale, dev)
+    inp.make_resident(lib, opt)
+    setup_s = time.time() - t0
+    n_sample = int(inp.spectra_dev[0][0].shape[0])
 
     def barrier():
         torch.cuda.synchronize()
@@ -181,70 +177,50 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: device-resident step ------------------------------------------------------------
+    # ---- value: inputs resident in HBM -------------------------------------------------------------
+    info = None
     for _ in range(args.warmup):
-        pb = step_resident(); stream.synchronize(); lib.btg_tbloom_free(pb)
+        _, _, _, info = driver.genotype(inp, opt, resident=True)
+    n_clusters = info["n_clusters"] if info else None
     barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    kmer_ms, stream_ms = [], []
     lib.btg_launch_count_reset()
     with ClockSampler(local_rank) as clocks:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        pbs = []
-        marks = []
         for _ in range(args.steps):
-            a, b, c_, d = (torch.cuda.Event(enable_timing=True) for _ in range(4))
-            pb = capi.check(lib.btg_tbloom_create(n_path + 1_000_000, 1e-4, K), lib)
-            a.record(stream)
-            capi.check(lib.btg_tbloom_insert_dev(pb, path_k.data_ptr(), n_path, sp), lib)
-            b.record(stream)
-            capi.check(lib.btg_tbloom_lookup_dev(pb, sample_k.data_ptr(), n_sample, hit_sample.data_ptr(), sp), lib)
-            c_.record(stream)
-            capi.check(lib.btg_bloom_lookup_dev(sample_bloom, path_k.data_ptr(), n_path, hit_path.data_ptr(), sp), lib)
-            d.record(stream)
-            capi.check(lib.btg_estimate_genotypes_async(eng.h, cd.h, C.addressof(opts), sp), lib)
-            pbs.append(pb); marks.append((a, b, c_, d))
+            _, _, res, info = driver.genotype(inp, opt, resident=True)
         e1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
     launches = int(lib.btg_launch_count())
-    for pb in pbs:
-        lib.btg_tbloom_free(pb)
-    total_ms = e0.elapsed_time(e1)
-    stream_ms = [m[1].elapsed_time(m[2]) for m in marks]
-    kmer_ms = [m[0].elapsed_time(m[3]) for m in marks]
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    n_clusters = info["n_clusters"]
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     value = world * n_clusters / (ms_per_step / 1e3)
 
-    # ---- e2e: host buffers through the C ABI --------------------------------------------------------
-    h_path = torch.empty((n_path, 2), dtype=torch.int64, pin_memory=True); h_path.copy_(path_k)
-    h_sample = torch.empty((n_sample, 2), dtype=torch.int64, pin_memory=True); h_sample.copy_(sample_k)
-    h_hit_p = torch.empty(n_path, dtype=torch.uint8, pin_memory=True)
-    h_hit_s = torch.empty(n_sample, dtype=torch.uint8, pin_memory=True)
-    desc = unit.desc()
-    h2d = n_path * 16 * 2 + n_sample * 16 + sum(v.nbytes for v in unit.a.values())
-    d2h = n_path + n_sample + sum(v.nbytes for k, v in res_arrays.items() if k not in ("allele_off", "geno_off", "valt_off"))
-
-    def step_e2e():
-        pb = capi.check(lib.btg_tbloom_create(n_path + 1_000_000, 1e-4, K), lib)
-        capi.check(lib.btg_tbloom_insert(pb, h_path.data_ptr(), n_path), lib)
-        capi.check(lib.btg_tbloom_lookup(pb, h_sample.data_ptr(), n_sample, h_hit_s.data_ptr()), lib)
-        capi.check(lib.btg_bloom_lookup(sample_bloom, h_path.data_ptr(), n_path, h_hit_p.data_ptr()), lib)
-        lib.btg_tbloom_free(pb)
-        u = capi.check(lib.btg_unit_upload(C.addressof(desc)), lib)
-        capi.check(lib.btg_estimate_genotypes(u, cd.h, C.addressof(opts), C.addressof(res_struct)), lib)
-        lib.btg_unit_free(u)
-
-    step_e2e()
+    # ---- e2e: every input crosses the boundary from host memory inside the call --------------------------
+    keys_d, counts_d = inp.spectra_dev[0]
+    h_keys = torch.empty(keys_d.shape, dtype=torch.int64, pin_memory=True); h_keys.copy_(keys_d)
+    h_counts = torch.empty(counts_d.shape, dtype=torch.uint8, pin_memory=True); h_counts.copy_(counts_d)
+    nk, nb, nh = C.c_uint64(), C.c_uint64(), C.c_uint32()
+    lib.btg_bloom_info(inp.blooms_dev[0], C.byref(nk), C.byref(nb), C.byref(nh))
+    bloom_bytes = np.zeros((nb.value + 7) // 8, np.uint8)
+    capi.check(lib.btg_bloom_download(inp.blooms_dev[0], capi.ptr(bloom_bytes), bloom_bytes.size), lib)
+    host_inp = driver.Inputs(inp.chrom, inp.reference, inp.variants, inp.genders, spectra=[(h_keys, h_counts)],
+                             blooms=[(bloom_bytes, nk.value, nb.value)], graphs=inp.graphs, regions=inp.regions)
+    region_bytes = int(inp.region_buf_dev.numel())
+    h2d = h_keys.numel() * 8 + h_counts.numel() + bloom_bytes.size + region_bytes
+    torch.cuda.synchronize()
+    _, unit, res, _ = driver.genotype(host_inp, opt, resident=False, want_unit=True)      # warm-up; also sizes the unit traffic
+    h2d += 2 * sum(v.nbytes for v in unit.a.values())                                     # graphs + unit descriptors cross twice (down, up)
+    d2h = sum(v.nbytes for v in res.values()) + sum(v.nbytes for v in unit.a.values())
     barrier()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 2))
     t1 = time.perf_counter()
     for _ in range(e2e_steps):
-        step_e2e()
+        driver.genotype(host_inp, opt, resident=False)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t1) / e2e_steps
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -252,59 +228,89 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n_clusters / float(t.item())
 
-    # ---- roofline of the k-mer-match kernel --------------------------------------------------------
-    peak, peak_src = measured_peaks()
-    alg_bytes = n_sample * (17 + 32.0 * probes_per_record)
-    stream_kernel_ms = float(np.mean(stream_ms))
-    achieved = alg_bytes / (stream_kernel_ms / 1e3) / 1e9
-    gibbs_ms = ms_per_step - float(np.mean(kmer_ms))
+    # ---- stage breakdown + roofline of the k-mer-match stream kernel (measured live, CUDA events) ---------
+    stage_ms, roof = stage_breakdown(lib, inp, opt, stream, dev)
 
+    peak, peak_src = measured_peaks()
+    roof.update({"peak": peak, "unit": "GB/s", "frac": roof["achieved"] / peak, "peak_source": peak_src, "bound": "hbm", "traffic": None})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 (Gibbs log-likelihoods) / u64 (k-mer hashing)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clusters_per_gpu": n_clusters, "variants_per_gpu": int(unit.n_variants), "samples": unit.S,
-                   "path_kmers": n_path, "sample_kmers": n_sample, "gibbs": "20 chains x (100 burn-in + 250 samples)", "kmer_subsampling_rate": 0.1,
-                   "l2": "inputs exceed L2 (k-mer streams %.1f GB, Gibbs state > 126 MB)" % ((n_sample + n_path) * 16 / 1e9),
+        "config": {"workload": WORKLOAD, "clusters_per_gpu": n_clusters, "variants_per_gpu": len(inp.variants), "samples": 1,
+                   "reference_nt": len(inp.reference), "sample_kmers": n_sample, "path_kmers": info["n_path_kmers"],
+                   "step": "findVariantClusterPaths -> path k-mer table -> genome scan -> sample k-mer stream -> classify/haplotype candidates -> NB fit -> estimateNoise -> estimateGenotypes",
+                   "gibbs": "20 chains x (100 burn-in + 250 samples), k-mer subsampling 0.1",
+                   "l2": "inputs exceed L2 (sample k-mer stream %.2f GB, sample Bloom %.0f MB)" % (n_sample * 17 / 1e9, nb.value / 8e6),
                    "parallelism": "groups sharded across ranks, no collective" if world > 1 else "1 GPU", "scale": args.scale},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
-        "roofline": {"kernel": "k_tbloom_lookup (sample k-mer stream filtered through the path-k-mer Bloom, a11)", "bound": "hbm",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes, "probes_per_record": probes_per_record, "ms_per_launch": stream_kernel_ms},
-        "stage_ms": {"kmer_match": float(np.mean(kmer_ms)), "gibbs": gibbs_ms},
-        "setup_s": {"unit": setup_unit_s},
+        "roofline": roof,
+        "stage_ms": stage_ms,
+        "setup_s": setup_s,
     }
     if rank == 0:
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(args.cpu_variants, os.cpu_count() or 1)
         print(json.dumps(line), flush=True)
-    eng.close(); cd.close()
-    lib.btg_bloom_free(sample_bloom)
+    inp.free(lib)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def measure_tbloom_probes(lib, pb, sample_k, dev):
-    """Mean number of probes the reference's early-exit loop executes per streamed record: measured on a
-    1M-record sample with an equally loaded KmerBloom (same fpr) through btg_bloom_lookup_probes_dev."""
+def stage_breakdown(lib, inp, opt, stream, dev):
+    """One extra (untimed for `value`) pass with a synchronisation after every stage, and the isolated timing of the
+    stream kernel k_table_add_sample for the roofline object."""
     import torch
-    from bayestyper_b200 import capi
-    n = min(1_000_000, sample_k.shape[0])
-    sub_k, sub_b, nh = C.c_uint64(), C.c_uint64(), C.c_uint32()
-    lib.btg_tbloom_info(pb, C.byref(sub_k), C.byref(sub_b), C.byref(nh))
-    # an absent k-mer passes each probe with the filter's fill ratio f: E[probes] = sum_{i<nh} f^i
-    bits = np.zeros((65536, (sub_b.value + 7) // 8), np.uint8)
-    capi.check(lib.btg_tbloom_download(pb, bits.ctypes.data, bits.size), lib)
-    fill = float(np.unpackbits(bits[:256]).mean()) * (bits.shape[1] * 8) / sub_b.value
-    hit = torch.zeros(n, dtype=torch.uint8, device=dev)
-    capi.check(lib.btg_tbloom_lookup_dev(pb, sample_k.data_ptr(), n, hit.data_ptr(), None), lib)
+    from bayestyper_b200 import capi, driver, engine, kmer_pipeline, unit as U
+    out = {}
+
+    def timed(name, fn):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        out[name] = (time.perf_counter() - t) * 1e3
+        return r
+
+    n_paths, mem = timed("findVariantClusterPaths", lambda: driver.find_variant_cluster_paths(lib, inp.graphs, inp.blooms_dev, opt))
+    pipe = kmer_pipeline.KmerPipeline(inp.graphs, n_paths, mem, 1, inp.genders)
+    timed("countPathKmers(enumerate+sort)", pipe.enumerate_path_kmers)
+    timed("countInterclusterKmers(scan)", lambda: pipe.scan_buffer(inp.region_buf_dev, 2, 2, False))
+    kd, cdv = inp.spectra_dev[0]
+    timed("parseSampleKmers(stream)", lambda: pipe.add_sample(0, kd, cdv))
+    unit = timed("classify+getHaplotypeCandidates", lambda: pipe.build_unit(multigroup_bloom=None))
+    nb = timed("NB fit (parameter k-mers)", lambda: driver.estimate_nb_parameters(pipe, inp.region_buf_dev, inp.spectra_dev, inp.genders, opt))
+    cd = engine.CountDistribution(nb[0], nb[1])
+    eng = timed("unit upload", lambda: engine.InferenceEngine(unit))
+    gopts = U.default_opts(seed=opt.random_seed, min_frac=U.min_fraction_observed(nb[0], nb[1]))
+    timed("estimateNoise", lambda: eng.estimate_noise(cd, gopts, want_trace=False))
+    timed("estimateGenotypes", lambda: eng.estimate_genotypes(cd, gopts))
+    eng.close(); cd.close()
+    # roofline: the sample k-mer stream probing the exact path-k-mer table
+    pipe.use_index()
+    counts = torch.zeros_like(pipe.counts); rec = torch.zeros_like(pipe.has_record)
     torch.cuda.synchronize()
-    h = float(hit.float().mean())
-    miss_probes = sum(fill ** i for i in range(nh.value))
-    return h * nh.value + (1 - h) * miss_probes
+    n = kd.shape[0]
+    for _ in range(3):
+        capi.check(lib.btg_table_add_sample_kmers_dev(pipe.kw0.data_ptr(), pipe.kw1.data_ptr(), pipe.n_keys, kd.data_ptr(), cdv.data_ptr(), n, 1, 0, counts.data_ptr(), rec.data_ptr(), None), lib)
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        capi.check(lib.btg_table_add_sample_kmers_dev(pipe.kw0.data_ptr(), pipe.kw1.data_ptr(), pipe.n_keys, kd.data_ptr(), cdv.data_ptr(), n, 1, 0, counts.data_ptr(), rec.data_ptr(), None), lib)
+    e1.record(stream)
+    stream.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    hits = int(rec.sum())
+    alg = n * 17 + pipe.n_keys * 16 + hits * 1
+    roof = {"kernel": "k_table_add_sample (parseSampleKmers: sample k-mer stream probing the exact path-k-mer table, a11)",
+            "achieved": alg / (ms / 1e3) / 1e9, "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms,
+            "records": n, "table_keys": pipe.n_keys, "hits": hits,
+            "bytes_model": "17 B per record + 16 B per path k-mer + S B per hit (SURVEY.md section 8d, merge-join form)"}
+    return out, roof
 
 
 # ------------------------------------------------------------------------------------------------
@@ -329,7 +335,8 @@ def cpu_reference(n_variants: int, threads: int):
         wall = time.time() - t0
         tj = json.loads((Path(td) / "ref_out" / "timings.json").read_text())
     kmer_s = sum(tj.get(k, 0.0) for k in ("findVariantClusterPaths", "countPathMultigroupKmers", "countPathKmers", "countInterclusterKmers", "parseSampleKmers", "classifyPathKmers"))
-    return {"value": tj["clusters_genotyped"] / (tj["estimateGenotypes"] + kmer_s), "unit": UNIT, "cores": threads, "kind": "reference",
+    total_s = tj["estimateGenotypes"] + tj.get("estimateNoise", 0.0) + kmer_s
+    return {"value": tj["clusters_genotyped"] / total_s, "unit": UNIT, "cores": threads, "kind": "reference", "step_s": total_s,
             "sample": f"{len(var)} variants / {tj['num_clusters']} clusters of the same chr22-like shape through the reference's own stages "
                       f"(estimateGenotypes {tj['estimateGenotypes']:.2f} s, estimateNoise {tj.get('estimateNoise', 0):.2f} s, k-mer stages {kmer_s:.2f} s, wall {wall:.1f} s)",
             "clusters": tj["clusters_genotyped"], "estimateGenotypes_s": tj["estimateGenotypes"], "kmer_stages_s": kmer_s,
@@ -350,8 +357,8 @@ def run_reference(args):
             return
         if i >= args.warmup:
             vals.append(last)
-    value = float(np.mean([v["clusters"] / (v["estimateGenotypes_s"] + v["kmer_stages_s"]) for v in vals]))
-    ms = float(np.mean([(v["estimateGenotypes_s"] + v["kmer_stages_s"]) * 1e3 for v in vals]))
+    value = float(np.mean([v["clusters"] / v["step_s"] for v in vals]))
+    ms = float(np.mean([v["step_s"] * 1e3 for v in vals]))
     cb = dict(last); cb["value"] = value
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 / u64", "data": "synthetic",

@@ -189,6 +189,10 @@ int btg_walk_paths_dev(const btg_pathwalk_desc *d, int emit, uint32_t *n_occ, ui
 /* HaplotypeInfo::variant_allele_indices of every best path (VariantClusterGraph.cpp:983-992,1091-1098) */
 int btg_path_alleles_dev(const btg_pathwalk_desc *d, const uint64_t *cl_var_off, const uint16_t *var_nalleles,
                          const uint64_t *hapvar_off, uint16_t *hap_alleles, void *stream);
+/* Optional prefix index over the sorted keys (cf. the prefix LUT of a KMC database, external/kmc_api/kmc_file.cpp:236-290):
+ * lut[b] = index of the first key whose word-1 top lut_bits bits (of 46) are >= b, b in [0, 2^lut_bits]; NULL clears.
+ * Applies to the three table probes below until changed. */
+int btg_table_set_index_dev(const int64_t *lut, int lut_bits);
 /* KmerCountsHash::findKmer on a batch: index into the key arrays or -1 */
 int btg_table_lookup_dev(const int64_t *key_w0, const int64_t *key_w1, int64_t n_keys, const uint64_t *kmers, size_t n,
                          int64_t *idx_out, void *stream);

@@ -75,6 +75,7 @@ def test_haplotype_candidates_identical_to_reference(btg, name):
 
 def test_table_lookup_and_saturation(btg):
     """btg_table_lookup_dev / add_sample: hits, misses, duplicates saturate at 255 (KmerCounts.cpp:178-189)."""
+    capi.check(btg.btg_table_set_index_dev(None, 0), btg)
     rng = np.random.default_rng(3)
     keys = rng.integers(-2**63, 2**63 - 1, size=(5000, 2), dtype=np.int64)
     keys[:, 1] &= (1 << 46) - 1
@@ -98,5 +99,15 @@ def test_table_lookup_and_saturation(btg):
     capi.check(btg.btg_table_add_sample_kmers_dev(kw0.data_ptr(), kw1.data_ptr(), len(keys), dup.data_ptr(), cts.data_ptr(), 30, 3, 1, counts.data_ptr(), rec.data_ptr(), None), btg)
     capi.check(btg.btg_kmer_hash(capi.ptr(np.zeros((1, 2), np.uint64)), 1, capi.ptr(np.zeros(1, np.uint64))), btg)
     c = counts.cpu().numpy()
+    # same probes through a prefix index
+    bits = 10
+    lut = np.concatenate([[0], np.cumsum(np.bincount(keys[:, 1] >> (46 - bits), minlength=1 << bits))]).astype(np.int64)
+    lut_d = torch.from_numpy(lut).cuda(); idx2 = torch.zeros(len(q), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    capi.check(btg.btg_table_set_index_dev(lut_d.data_ptr(), bits), btg)
+    capi.check(btg.btg_table_lookup_dev(kw0.data_ptr(), kw1.data_ptr(), len(keys), qd.data_ptr(), len(q), idx2.data_ptr(), None), btg)
+    capi.check(btg.btg_kmer_hash(capi.ptr(np.zeros((1, 2), np.uint64)), 1, capi.ptr(np.zeros(1, np.uint64))), btg)
+    capi.check(btg.btg_table_set_index_dev(None, 0), btg)
+    assert (idx2.cpu().numpy() == exp).all()
     assert (c[:10, 1] == 255).all() and c[:10, [0, 2]].sum() == 0 and c[10:].sum() == 0
     assert rec.cpu().numpy()[:10].all() and not rec.cpu().numpy()[10:].any()
