@@ -25,8 +25,12 @@
 #include <type_traits>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "gibbs_rng.cuh"
+
+namespace cg = cooperative_groups;
 
 using namespace btg;
 
@@ -790,9 +794,8 @@ __global__ void __launch_bounds__(64) k_noise_iteration(DevUnit du, Tables T, bt
 // CountDistribution::sampleNoiseParameters / resetNoiseRates + updateNoiseCache, on the device so that the
 // iteration loop never synchronises with the host.  mode 0: reset from the prior; 1: posterior draw from hist;
 // 2: set to the accumulated mean.  One block; thread 0 draws, then all threads rebuild the Poisson rows.
-__global__ void k_noise_update(NoiseState ns, uint32_t S, float prior_shape, float prior_scale, uint32_t seed, int mode, int accumulate,
-                               double chain_label, double iter_label, double mean_div) {
-    __shared__ double sh_rates[BTG_MAX_SAMPLES];
+__device__ void noise_update_block(const NoiseState &ns, uint32_t S, float prior_shape, float prior_scale, uint32_t seed, int mode, int accumulate,
+                                   double chain_label, double iter_label, double mean_div, double *sh_rates) {
     if (threadIdx.x == 0) {
         Philox rng;
         rng.load(ns.rng, 0, seed, (uint64_t)-1, 0);
@@ -825,6 +828,67 @@ __global__ void k_noise_update(NoiseState ns, uint32_t S, float prior_shape, flo
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < S * 256u; i += blockDim.x) ns.noise_table[i] = noiseCountLogPmf(sh_rates[i >> 8], i & 255u);
+}
+
+__global__ void k_noise_update(NoiseState ns, uint32_t S, float prior_shape, float prior_scale, uint32_t seed, int mode, int accumulate,
+                               double chain_label, double iter_label, double mean_div) {
+    __shared__ double sh_rates[BTG_MAX_SAMPLES];
+    noise_update_block(ns, S, prior_shape, prior_scale, seed, mode, accumulate, chain_label, iter_label, mean_div, sh_rates);
+}
+
+// One whole chain of estimateNoise as ONE persistent cooperative kernel (InferenceEngine.cpp:191-253): every thread keeps its
+// clusters' state hot in L1 across the 350 iterations; the per-iteration "join + merge + sampleNoiseParameters" of the
+// reference (thread spawn/join per iteration, InferenceEngine.cpp:213-226) becomes two grid-wide barriers around block 0's
+// histogram -> Gamma draw -> Poisson-row rebuild.
+__global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg_gibbs_opts o, const uint32_t *sel, uint32_t n_sel, uint32_t chain,
+                                                       uint32_t iters, NoiseState ns, float prior_shape, float prior_scale, unsigned long long *hist) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh_rates[BTG_MAX_SAMPLES];
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    for (uint32_t i = tid; i < n_sel; i += nthreads) {  // initGenotypersCallback: fresh genotypers every chain
+        Cl cl;
+        cl.bind(du, sel[i]);
+        const uint64_t gidx = o.group_index_base + cl.g;
+        cl_construct(cl, o, gidx, chain);
+        Philox prng, fr;
+        prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, chain);
+        fr.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngFrequency, chain);
+        cl_reset(cl, o, prng);
+        prng.save(cl.misc, kRng0);
+        fr.save(cl.misc, kRng1);
+    }
+    if (blockIdx.x == 0 && ns.trace) noise_update_block(ns, du.S, prior_shape, prior_scale, o.random_seed, 3, 0, (double)chain, 0, 1, sh_rates);
+    grid.sync();
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (uint32_t it = 1; it <= iters; it++) {
+        for (uint32_t i = tid; i < n_sel; i += nthreads) {  // sampleGenotypesCallback
+            Cl cl;
+            cl.bind(du, sel[i]);
+            const uint64_t gidx = o.group_index_base + cl.g;
+            const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
+            Philox prng, fr;
+            prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+            fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
+            cl_sample_diplotypes(cl, T, ploidy, false, prng);
+            cl_sample_frequencies(cl, fr);
+            const uint32_t n_sub = cl.misc[kNSub];
+            for (uint32_t s = 0; s < cl.S; s++) {  // getNoiseCounts
+                const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
+                for (uint32_t j = 0; j < n_sub; j++) {
+                    const uint32_t k = cl.uniq_sub[j];
+                    if ((uint8_t)(cl.diplMult(k, da, db) + cl.ic(k, s)) == 0) atomicAdd(hist + s * 256u + cl.count(k, s), 1ULL);
+                }
+            }
+            for (uint32_t j = 0; j < cl.S * cl.Dall; j++) cl.ucache[j] = nan;  // clearGenotyperCache
+            prng.save(cl.misc, kRng0);
+            fr.save(cl.misc, kRng1);
+        }
+        __threadfence();
+        grid.sync();
+        if (blockIdx.x == 0) noise_update_block(ns, du.S, prior_shape, prior_scale, o.random_seed, 1, o.gibbs_burn_in < it, (double)chain, (double)it, 1, sh_rates);
+        __threadfence();
+        grid.sync();
+    }
 }
 
 __global__ void k_noise_rng_init(uint32_t *rng, uint32_t seed) {
@@ -1233,20 +1297,28 @@ int btg_estimate_noise(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *op
             std::sort(noise_groups.begin(), noise_groups.begin() + end);
             sel.clear();
             for (uint32_t i = 0; i < end; i++) sel.push_back((uint32_t)u->h_group_cluster_off[noise_groups[i]]);
+            std::sort(sel.begin(), sel.end(), [&](uint32_t a, uint32_t b) { return u->h_layout[a].pos < u->h_layout[b].pos; });  // neighbours share arena slots
             if (cudaMemcpyAsync(d_sel, sel.data(), sel.size() * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BTG_ECUDA; break; }
             cudaStreamSynchronize(s);  // sel is reused by the host next chain
             const uint32_t n_sel = (uint32_t)sel.size();
-            const uint32_t grid = (n_sel + 63) / 64;
-            if (n_sel) { k_noise_init<<<grid, 64, 0, s>>>(u->du, *opts, d_sel, n_sel, chain + 1); BTG_LAUNCHED(); }
-            // trace row "chain, 0": the rates the chain starts from (mode 3 = record, no draw)
-            if (ns.trace) {
-                k_noise_update<<<1, 256, 0, s>>>(ns, S, cd->prior_shape, cd->prior_scale, opts->random_seed, 3, 0, chain + 1, 0, 1);
+            if (n_sel) {
+                int per_sm = 0;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_noise_chain, 64, 0);
+                const uint32_t max_blocks = (uint32_t)std::max(1, per_sm) * (uint32_t)ctx().sm_count;
+                const uint32_t grid = std::min((n_sel + 63) / 64, max_blocks);
+                uint32_t chain_id = chain + 1, n_sel_arg = n_sel, iters_arg = iters;
+                float ps = cd->prior_shape, pc = cd->prior_scale;
+                btg_gibbs_opts o = *opts;
+                void *args[] = {&u->du, &T, &o, &d_sel, &n_sel_arg, &chain_id, &iters_arg, &ns, &ps, &pc, &hist};
+                cudaError_t e = cudaLaunchCooperativeKernel((void *)k_noise_chain, dim3(grid), dim3(64), args, 0, s);
                 BTG_LAUNCHED();
-            }
-            for (uint32_t it = 1; it <= iters; it++) {
-                if (n_sel) { k_noise_iteration<<<grid, 64, 0, s>>>(u->du, T, *opts, d_sel, n_sel, hist); BTG_LAUNCHED(); }
-                k_noise_update<<<1, 256, 0, s>>>(ns, S, cd->prior_shape, cd->prior_scale, opts->random_seed, 1, opts->gibbs_burn_in < it, chain + 1, it, 1);
-                BTG_LAUNCHED();
+                if (e != cudaSuccess) { set_error("cooperative launch failed: %s", cudaGetErrorString(e)); rc = BTG_ECUDA; break; }
+            } else {
+                if (ns.trace) { k_noise_update<<<1, 256, 0, s>>>(ns, S, cd->prior_shape, cd->prior_scale, opts->random_seed, 3, 0, chain + 1, 0, 1); BTG_LAUNCHED(); }
+                for (uint32_t it = 1; it <= iters; it++) {
+                    k_noise_update<<<1, 256, 0, s>>>(ns, S, cd->prior_shape, cd->prior_scale, opts->random_seed, 1, opts->gibbs_burn_in < it, chain + 1, it, 1);
+                    BTG_LAUNCHED();
+                }
             }
             // resetNoiseRates at the end of the chain (InferenceEngine.cpp:253); not a trace row
             k_noise_update<<<1, 256, 0, s>>>(ns_quiet, S, cd->prior_shape, cd->prior_scale, opts->random_seed, 0, 0, 0, 0, 1);

@@ -57,13 +57,40 @@ struct DevGraphs {
 };
 
 // ---- std::mt19937 -------------------------------------------------------------------------------
+// Bit-exact Mersenne Twister.  A cluster usually draws a handful of numbers, so the first kMtWindow outputs are
+// produced without materialising the 624-word state: output i < 227 only needs the seeded words mt[i], mt[i+1] and
+// mt[i+397], which come out of the (register-resident) seeding recurrence.  Only when a cluster draws more than that
+// is the full state built in the scratch arena and twisted the standard way.
+constexpr uint32_t kMtWindow = 24;
 struct Mt19937 {
-    uint32_t *mt;  // [624]
-    uint32_t idx;
-    __device__ void seed(uint32_t s) {
-        mt[0] = s;
-        for (uint32_t i = 1; i < 624; i++) { s = 1812433253u * (s ^ (s >> 30)) + i; mt[i] = s; }
-        idx = 624;
+    uint32_t *mt;      // [624] scratch, used only after the window is exhausted
+    uint32_t seed_value;
+    uint32_t consumed; // outputs handed out so far
+    uint32_t idx;      // position in the materialised state
+    bool windowed, full;
+    uint32_t wa[kMtWindow + 1], wb[kMtWindow];
+
+    __device__ void seed(uint32_t s) { seed_value = s; consumed = 0; idx = 624; windowed = false; full = false; }
+    __device__ void build_window() {
+        uint32_t x = seed_value;
+        wa[0] = x;
+        for (uint32_t i = 1; i < 397 + kMtWindow; i++) {
+            x = 1812433253u * (x ^ (x >> 30)) + i;
+            if (i <= kMtWindow) wa[i] = x;
+            if (i >= 397) wb[i - 397] = x;
+        }
+        windowed = true;
+    }
+    __device__ void materialise() {
+        uint32_t x = seed_value;
+        mt[0] = x;
+        for (uint32_t i = 1; i < 624; i++) { x = 1812433253u * (x ^ (x >> 30)) + i; mt[i] = x; }
+        for (uint32_t i = 0; i < 624; i++) {
+            const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+            mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        idx = consumed;  // the first `consumed` (< 624) outputs of this block were served from the window
+        full = true;
     }
     __device__ void twist() {
         for (uint32_t i = 0; i < 624; i++) {
@@ -72,14 +99,26 @@ struct Mt19937 {
         }
         idx = 0;
     }
-    __device__ uint32_t next() {
-        if (idx >= 624) twist();
-        uint32_t y = mt[idx++];
+    __device__ static uint32_t temper(uint32_t y) {
         y ^= y >> 11;
         y ^= (y << 7) & 0x9d2c5680u;
         y ^= (y << 15) & 0xefc60000u;
         y ^= y >> 18;
         return y;
+    }
+    __device__ uint32_t next() {
+        if (!full) {
+            if (consumed < kMtWindow) {
+                if (!windowed) build_window();
+                const uint32_t i = consumed++;
+                const uint32_t y = (wa[i] & 0x80000000u) | (wa[i + 1] & 0x7fffffffu);
+                return temper(wb[i] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u));
+            }
+            materialise();
+        }
+        if (idx >= 624) twist();
+        consumed++;
+        return temper(mt[idx++]);
     }
     // libstdc++ uniform_int_distribution<unsigned long>{0, range-1} on a 32-bit engine: Lemire (uniform_int_dist.h:250-274)
     __device__ uint32_t below(uint32_t range) {

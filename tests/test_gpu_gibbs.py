@@ -95,7 +95,7 @@ def test_estimate_noise_matches_oracle(btg):
     assert gtrace.shape == otrace.shape
     assert (gtrace[:, :2] == otrace[:, :2]).all()
     rel = np.abs(gtrace[:, 2:] - otrace[:, 2:]) / otrace[:, 2:]
-    assert rel.max() < 1e-9
+    assert rel.max() < 1e-9, (rel.max(), int(rel.argmax()), gtrace[int(rel.argmax()) // fx.S], otrace[int(rel.argmax()) // fx.S])
     assert np.abs(gcd.noise_rates() - ocd.noise_rates()).max() / ocd.noise_rates().max() < 1e-9
     eng.close()
 

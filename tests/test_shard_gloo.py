@@ -1,0 +1,71 @@
+"""The N>1 path on CPU (gloo, world_size 2): group sharding keeps every group's random streams (group_index_base),
+so the concatenation of the per-rank results equals the single-process result bit for bit; the noise rates travel
+by broadcast.  The per-rank compute stand-in is oracle-P (no GPU in this container)."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, str(ROOT))
+    import torch
+    import torch.distributed as dist
+    from bayestyper_b200 import shard
+    from tests import _oracle as O
+    from tests._fixtures import GibbsFixture
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fx = GibbsFixture("gibbs_mixed_3s")
+    rates = torch.zeros(fx.S, dtype=torch.float64)
+    if rank == 0:
+        rates[:] = torch.from_numpy(fx.tab["noise_rates"])
+    dist.broadcast(rates, 0)
+    sub, base = shard.shard(fx.unit, world, rank)
+    cd = O.OracleCountDist(fx.nb_p, fx.nb_size)
+    cd.set_noise_rates(rates.numpy())
+    res = O.oracle_estimate_genotypes(sub, cd, fx.opts(chains=2, burn=10, samples=30, group_base=base))
+    parts = [None] * world
+    dist.all_gather_object(parts, {k: res[k] for k in shard.RESULT_KEYS})
+    if rank == 0:
+        np.savez(Path(out_dir) / "sharded.npz", **shard.concat_results(parts))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_equals_single_process(tmp_path):
+    sys.path.insert(0, str(ROOT))
+    from bayestyper_b200 import shard
+    from tests import _oracle as O
+    from tests._fixtures import GibbsFixture
+    fx = GibbsFixture("gibbs_mixed_3s")
+    parts = shard.partition(fx.unit, 2)
+    assert parts[0][0] == 0 and parts[0][1] == parts[1][0] and parts[1][1] == fx.unit.G
+    cost = shard.group_costs(fx.unit)
+    c0, c1 = cost[parts[0][0]:parts[0][1]].sum(), cost[parts[1][0]:parts[1][1]].sum()
+    assert abs(c0 - c1) / (c0 + c1) < 0.25
+    mp.spawn(_worker, args=(2, 29517, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "sharded.npz")
+    cd = O.OracleCountDist(fx.nb_p, fx.nb_size)
+    cd.set_noise_rates(fx.tab["noise_rates"])
+    want = O.oracle_estimate_genotypes(fx.unit, cd, fx.opts(chains=2, burn=10, samples=30))
+    for k in shard.RESULT_KEYS:
+        assert (got[k] == want[k]).all(), k
+
+
+def test_partition_edge_cases():
+    sys.path.insert(0, str(ROOT))
+    from bayestyper_b200 import shard
+    from tests._fixtures import GibbsFixture
+    fx = GibbsFixture("gibbs_snv_1s")
+    for world in (1, 3, 8):
+        p = shard.partition(fx.unit, world)
+        assert p[0][0] == 0 and p[-1][1] == fx.unit.G
+        assert all(p[i][1] == p[i + 1][0] for i in range(world - 1))
+    empty = fx.unit.subset_groups(np.zeros(0, np.int64))
+    assert shard.partition(empty, 4) == [(0, 0)] * 4
