@@ -836,11 +836,54 @@ __global__ void k_noise_update(NoiseState ns, uint32_t S, float prior_shape, flo
     noise_update_block(ns, S, prior_shape, prior_scale, seed, mode, accumulate, chain_label, iter_label, mean_div, sh_rates);
 }
 
+// Warp-cooperative fill of the per-(sample, diplotype) k-mer log-likelihood cache for the current non-zero haplotypes:
+// entry e of the enumeration goes to lane e % 32, which sums over the k-mer subset in the same order as the
+// sequential code (so the cached value is bit-identical).  Used for large clusters in the lock-step noise chain,
+// where the slowest cluster sets the pace of every iteration.
+__device__ void cl_fill_cache_warp(Cl &cl, const Tables &T, const uint8_t *ploidy, uint32_t lane) {
+    const uint32_t H = cl.H, n_sub = cl.misc[kNSub];
+    for (uint32_t s = 0; s < cl.S; s++) {
+        const uint8_t pl = ploidy[s];
+        if (pl == 0) continue;
+        uint32_t e = 0;
+        for (uint32_t a = 0; a < H; a++) {
+            if (!cl.nz[a]) continue;
+            const uint32_t b_end = pl == 2 ? H : a + 1;
+            for (uint32_t b = a; b < b_end; b++) {
+                if (pl == 2 && !cl.nz[b]) continue;
+                if ((e++ & 31u) != lane) continue;
+                const uint32_t bb = pl == 2 ? b : NONE;
+                const size_t ci = (size_t)s * cl.Dall + cl.slot(a, bb == NONE ? H : bb);
+                if (cl.ucache[ci] == cl.ucache[ci]) continue;  // already cached
+                double acc = 0;
+                for (uint32_t i = 0; i < n_sub; i++) {
+                    const uint32_t k = cl.uniq_sub[i];
+                    acc += T.logProb(s, (uint8_t)(cl.diplMult(k, a, bb) + cl.ic(k, s)), cl.count(k, s));
+                }
+                cl.ucache[ci] = acc;
+            }
+        }
+    }
+}
+
+// one lock-step iteration of one cluster by a single thread (sampleGenotypesCallback body without the noise counts)
+__device__ void noise_iteration_thread(Cl &cl, const DevUnit &du, const Tables &T, const btg_gibbs_opts &o) {
+    const uint64_t gidx = o.group_index_base + cl.g;
+    const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
+    Philox prng, fr;
+    prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+    fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
+    cl_sample_diplotypes(cl, T, ploidy, false, prng);
+    cl_sample_frequencies(cl, fr);
+    prng.save(cl.misc, kRng0);
+    fr.save(cl.misc, kRng1);
+}
+
 // One whole chain of estimateNoise as ONE persistent cooperative kernel (InferenceEngine.cpp:191-253): every thread keeps its
 // clusters' state hot in L1 across the 350 iterations; the per-iteration "join + merge + sampleNoiseParameters" of the
 // reference (thread spawn/join per iteration, InferenceEngine.cpp:213-226) becomes two grid-wide barriers around block 0's
 // histogram -> Gamma draw -> Poisson-row rebuild.
-__global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg_gibbs_opts o, const uint32_t *sel, uint32_t n_sel, uint32_t chain,
+__global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg_gibbs_opts o, const uint32_t *sel, uint32_t n_sel, uint32_t n_big, uint32_t chain,
                                                        uint32_t iters, NoiseState ns, float prior_shape, float prior_scale, unsigned long long *hist) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh_rates[BTG_MAX_SAMPLES];
@@ -861,16 +904,32 @@ __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg
     grid.sync();
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     for (uint32_t it = 1; it <= iters; it++) {
-        for (uint32_t i = tid; i < n_sel; i += nthreads) {  // sampleGenotypesCallback
+        // sel[0 .. n_big): large clusters, one WARP each (cooperative cache fill, counts and cache clear; lane 0 samples)
+        for (uint32_t i = tid >> 5; i < n_big; i += nthreads >> 5) {
+            const uint32_t lane = tid & 31u;
             Cl cl;
             cl.bind(du, sel[i]);
-            const uint64_t gidx = o.group_index_base + cl.g;
             const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
-            Philox prng, fr;
-            prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
-            fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
-            cl_sample_diplotypes(cl, T, ploidy, false, prng);
-            cl_sample_frequencies(cl, fr);
+            cl_fill_cache_warp(cl, T, ploidy, lane);
+            __syncwarp();
+            if (lane == 0) noise_iteration_thread(cl, du, T, o);
+            __syncwarp();
+            const uint32_t n_sub = cl.misc[kNSub];
+            for (uint32_t s = 0; s < cl.S; s++) {  // getNoiseCounts
+                const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
+                for (uint32_t j = lane; j < n_sub; j += 32) {
+                    const uint32_t k = cl.uniq_sub[j];
+                    if ((uint8_t)(cl.diplMult(k, da, db) + cl.ic(k, s)) == 0) atomicAdd(hist + s * 256u + cl.count(k, s), 1ULL);
+                }
+            }
+            for (uint32_t j = lane; j < cl.S * cl.Dall; j += 32) cl.ucache[j] = nan;  // clearGenotyperCache
+            __syncwarp();
+        }
+        // sel[n_big .. n_sel): small clusters, one thread each
+        for (uint32_t i = n_big + tid; i < n_sel; i += nthreads) {  // sampleGenotypesCallback
+            Cl cl;
+            cl.bind(du, sel[i]);
+            noise_iteration_thread(cl, du, T, o);
             const uint32_t n_sub = cl.misc[kNSub];
             for (uint32_t s = 0; s < cl.S; s++) {  // getNoiseCounts
                 const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
@@ -880,8 +939,6 @@ __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg
                 }
             }
             for (uint32_t j = 0; j < cl.S * cl.Dall; j++) cl.ucache[j] = nan;  // clearGenotyperCache
-            prng.save(cl.misc, kRng0);
-            fr.save(cl.misc, kRng1);
         }
         __threadfence();
         grid.sync();
@@ -915,6 +972,7 @@ struct btg_unit {
     std::vector<uint64_t> h_group_cluster_off, h_cl_var_off;
     std::vector<ClusterLayout> h_layout;
     std::vector<SlotLayout> h_slots;
+    std::vector<uint32_t> h_fill_cost;  // table lookups of one full cache fill: S * D * n_uniq / 10
     uint64_t n_variants = 0, n_alleles_total = 0;
     uint32_t max_h = 0;
 };
@@ -1047,6 +1105,7 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
     du.valt_off = keep(upload(u->h_valt_off.data(), nvar + 1, ok));
     // arena layout + cost order
     u->h_layout.resize(C);
+    u->h_fill_cost.assign(C, 0);
     u->h_nhap.assign(d->cl_nhap, d->cl_nhap + C);
     u->h_group_cluster_off.assign(d->group_cluster_off, d->group_cluster_off + G + 1);
     u->h_cl_var_off.assign(d->cl_var_off, d->cl_var_off + C + 1);
@@ -1066,6 +1125,7 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
             L.n_alleles = nal;
             L.Dall = (H + 1) * (H + 2) / 2;
             dims[c] = Dims{H, K, nv, nu, nal, L.Dall};
+            u->h_fill_cost[c] = (uint32_t)std::min<uint64_t>(0xFFFFFFFFu, (uint64_t)S * ((uint64_t)H * (H + 1) / 2) * (nu / 10 + 1));
             cost[c] = (uint64_t)S * ((uint64_t)H * (H + 1) / 2) * 8 + nu + (uint64_t)H * K / 16;
             u->max_h = std::max(u->max_h, H);
         }
@@ -1297,7 +1357,14 @@ int btg_estimate_noise(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *op
             std::sort(noise_groups.begin(), noise_groups.begin() + end);
             sel.clear();
             for (uint32_t i = 0; i < end; i++) sel.push_back((uint32_t)u->h_group_cluster_off[noise_groups[i]]);
-            std::sort(sel.begin(), sel.end(), [&](uint32_t a, uint32_t b) { return u->h_layout[a].pos < u->h_layout[b].pos; });  // neighbours share arena slots
+            // large clusters first (one warp each in the chain kernel), then by position in the cost order (neighbours share arena slots)
+            auto is_big = [&](uint32_t c) { return u->h_fill_cost[c] > 384; };
+            std::sort(sel.begin(), sel.end(), [&](uint32_t a, uint32_t b) {
+                const bool ba = is_big(a), bb = is_big(b);
+                return ba != bb ? ba : u->h_layout[a].pos < u->h_layout[b].pos;
+            });
+            uint32_t n_big = 0;
+            while (n_big < sel.size() && is_big(sel[n_big])) n_big++;
             if (cudaMemcpyAsync(d_sel, sel.data(), sel.size() * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BTG_ECUDA; break; }
             cudaStreamSynchronize(s);  // sel is reused by the host next chain
             const uint32_t n_sel = (uint32_t)sel.size();
@@ -1305,11 +1372,12 @@ int btg_estimate_noise(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *op
                 int per_sm = 0;
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_noise_chain, 64, 0);
                 const uint32_t max_blocks = (uint32_t)std::max(1, per_sm) * (uint32_t)ctx().sm_count;
-                const uint32_t grid = std::min((n_sel + 63) / 64, max_blocks);
+                const uint32_t want_threads = n_big * 32 > n_sel - n_big ? n_big * 32 : n_sel - n_big;
+                const uint32_t grid = std::max(1u, std::min((want_threads + 63) / 64, max_blocks));
                 uint32_t chain_id = chain + 1, n_sel_arg = n_sel, iters_arg = iters;
                 float ps = cd->prior_shape, pc = cd->prior_scale;
                 btg_gibbs_opts o = *opts;
-                void *args[] = {&u->du, &T, &o, &d_sel, &n_sel_arg, &chain_id, &iters_arg, &ns, &ps, &pc, &hist};
+                void *args[] = {&u->du, &T, &o, &d_sel, &n_sel_arg, &n_big, &chain_id, &iters_arg, &ns, &ps, &pc, &hist};
                 cudaError_t e = cudaLaunchCooperativeKernel((void *)k_noise_chain, dim3(grid), dim3(64), args, 0, s);
                 BTG_LAUNCHED();
                 if (e != cudaSuccess) { set_error("cooperative launch failed: %s", cudaGetErrorString(e)); rc = BTG_ECUDA; break; }
