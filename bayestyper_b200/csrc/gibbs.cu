@@ -736,6 +736,15 @@ __global__ void __launch_bounds__(64, MIN_BLOCKS) k_estimate_genotypes(DevUnit d
     cl_summarise(cl, o, ploidy, R);
 }
 
+// VariantClusterGroup::collectGenotypes for every cluster (joint mode collects after all chains)
+__global__ void __launch_bounds__(64) k_summarise(DevUnit du, btg_gibbs_opts o, ResultView R) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= du.C) return;
+    Cl cl;
+    cl.bind(du, du.order[i]);
+    cl_summarise(cl, o, du.group_ploidy + (size_t)cl.g * du.S, R);
+}
+
 // ---- estimateNoise: lock-step iterations over the selected single-cluster groups ---------------
 struct NoiseState {
     uint64_t *hist;        // [S][256] CountAllocation (CountAllocation.cpp:34-57)
@@ -867,13 +876,13 @@ __device__ void cl_fill_cache_warp(Cl &cl, const Tables &T, const uint8_t *ploid
 }
 
 // one lock-step iteration of one cluster by a single thread (sampleGenotypesCallback body without the noise counts)
-__device__ void noise_iteration_thread(Cl &cl, const DevUnit &du, const Tables &T, const btg_gibbs_opts &o) {
+__device__ void noise_iteration_thread(Cl &cl, const DevUnit &du, const Tables &T, const btg_gibbs_opts &o, bool collect) {
     const uint64_t gidx = o.group_index_base + cl.g;
     const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
     Philox prng, fr;
     prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
     fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
-    cl_sample_diplotypes(cl, T, ploidy, false, prng);
+    cl_sample_diplotypes(cl, T, ploidy, collect, prng);
     cl_sample_frequencies(cl, fr);
     prng.save(cl.misc, kRng0);
     fr.save(cl.misc, kRng1);
@@ -883,8 +892,11 @@ __device__ void noise_iteration_thread(Cl &cl, const DevUnit &du, const Tables &
 // clusters' state hot in L1 across the 350 iterations; the per-iteration "join + merge + sampleNoiseParameters" of the
 // reference (thread spawn/join per iteration, InferenceEngine.cpp:213-226) becomes two grid-wide barriers around block 0's
 // histogram -> Gamma draw -> Poisson-row rebuild.
+// joint = 0: estimateNoise (fresh genotypers each chain, streams of chain `chain`, nothing collected)
+// joint = 1: estimateNoiseAndGenotypes (InferenceEngine.cpp:384-472): genotypers are constructed in the first chain only and
+//            persist (streams of chain 0), samples are collected after the burn-in
 __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg_gibbs_opts o, const uint32_t *sel, uint32_t n_sel, uint32_t n_big, uint32_t chain,
-                                                       uint32_t iters, NoiseState ns, float prior_shape, float prior_scale, unsigned long long *hist) {
+                                                       uint32_t iters, NoiseState ns, float prior_shape, float prior_scale, unsigned long long *hist, int joint) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh_rates[BTG_MAX_SAMPLES];
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
@@ -892,10 +904,16 @@ __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg
         Cl cl;
         cl.bind(du, sel[i]);
         const uint64_t gidx = o.group_index_base + cl.g;
-        cl_construct(cl, o, gidx, chain);
         Philox prng, fr;
-        prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, chain);
-        fr.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngFrequency, chain);
+        if (!joint || chain == 1) {
+            const uint32_t stream_chain = joint ? 0 : chain;
+            cl_construct(cl, o, gidx, stream_chain);
+            prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, stream_chain);
+            fr.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngFrequency, stream_chain);
+        } else {
+            prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+            fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
+        }
         cl_reset(cl, o, prng);
         prng.save(cl.misc, kRng0);
         fr.save(cl.misc, kRng1);
@@ -912,7 +930,7 @@ __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg
             const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
             cl_fill_cache_warp(cl, T, ploidy, lane);
             __syncwarp();
-            if (lane == 0) noise_iteration_thread(cl, du, T, o);
+            if (lane == 0) noise_iteration_thread(cl, du, T, o, joint && it > o.gibbs_burn_in);
             __syncwarp();
             const uint32_t n_sub = cl.misc[kNSub];
             for (uint32_t s = 0; s < cl.S; s++) {  // getNoiseCounts
@@ -929,7 +947,7 @@ __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg
         for (uint32_t i = n_big + tid; i < n_sel; i += nthreads) {  // sampleGenotypesCallback
             Cl cl;
             cl.bind(du, sel[i]);
-            noise_iteration_thread(cl, du, T, o);
+            noise_iteration_thread(cl, du, T, o, joint && it > o.gibbs_burn_in);
             const uint32_t n_sub = cl.misc[kNSub];
             for (uint32_t s = 0; s < cl.S; s++) {  // getNoiseCounts
                 const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
@@ -1285,13 +1303,33 @@ int btg_unit_cluster_tally(const btg_unit *u, uint32_t cluster, uint32_t *tally_
     return BTG_OK;
 }
 
+static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, double *trace_out, int joint);
+
 int btg_estimate_noise(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, double *trace_out) {
+    return noise_chains(u, cd, opts, trace_out, 0);
+}
+
+int btg_estimate_noise_and_genotypes(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, btg_genotype_result *out, double *trace_out) {
+    if (!out) { set_error("null argument"); return BTG_EINVAL; }
+    int rc = noise_chains(u, cd, opts, trace_out, 1);
+    if (rc != BTG_OK) return rc;
+    DevResult *dr = unit_result(u);
+    if (!dr) { set_error("result allocation failed"); return BTG_ENOMEM; }
+    if (u->du.C) {
+        k_summarise<<<(u->du.C + 63) / 64, 64, 0, ctx().stream>>>(u->du, *opts, dr->R);
+        BTG_LAUNCHED();
+        BTG_CUDA(cudaGetLastError());
+    }
+    return btg_unit_download_result(u, out, nullptr);
+}
+
+static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, double *trace_out, int joint) {
     BTG_REQUIRE_INIT();
     if (!u || !cd || !opts) { set_error("null argument"); return BTG_EINVAL; }
     if (cd->S != u->du.S) { set_error("count distribution / unit sample mismatch"); return BTG_EINVAL; }
     const uint32_t S = u->du.S, G = u->du.G;
     const uint32_t iters = (uint32_t)opts->gibbs_burn_in + opts->gibbs_samples;
-    const size_t trace_rows = (size_t)opts->n_chains * (iters + 1) + 1;
+    const size_t trace_rows = (size_t)opts->n_chains * (iters + 1) + (joint ? 0 : 1);
     auto s = ctx().stream;
     NoiseState ns{};
     unsigned long long *hist = nullptr;
@@ -1351,10 +1389,14 @@ int btg_estimate_noise(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *op
         const uint32_t noise_variants_batch_size = 100000;  // InferenceEngine.cpp:50
         std::vector<uint32_t> sel;
         for (uint32_t chain = 0; chain < opts->n_chains && rc == BTG_OK; chain++) {
-            for (size_t i = noise_groups.size(); i > 1; i--) std::swap(noise_groups[i - 1], noise_groups[engine.uniform_int((uint32_t)i)]);
             uint32_t end = 0, nvv = 0;
-            while (nvv < noise_variants_batch_size && end < noise_groups.size()) { nvv += group_variants(noise_groups[end]); end++; }
-            std::sort(noise_groups.begin(), noise_groups.begin() + end);
+            if (joint) {
+                end = (uint32_t)noise_groups.size();  // every group, every chain (InferenceEngine.cpp:407-408)
+            } else {
+                for (size_t i = noise_groups.size(); i > 1; i--) std::swap(noise_groups[i - 1], noise_groups[engine.uniform_int((uint32_t)i)]);
+                while (nvv < noise_variants_batch_size && end < noise_groups.size()) { nvv += group_variants(noise_groups[end]); end++; }
+                std::sort(noise_groups.begin(), noise_groups.begin() + end);
+            }
             sel.clear();
             for (uint32_t i = 0; i < end; i++) sel.push_back((uint32_t)u->h_group_cluster_off[noise_groups[i]]);
             // large clusters first (one warp each in the chain kernel), then by position in the cost order (neighbours share arena slots)
@@ -1377,7 +1419,7 @@ int btg_estimate_noise(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *op
                 uint32_t chain_id = chain + 1, n_sel_arg = n_sel, iters_arg = iters;
                 float ps = cd->prior_shape, pc = cd->prior_scale;
                 btg_gibbs_opts o = *opts;
-                void *args[] = {&u->du, &T, &o, &d_sel, &n_sel_arg, &n_big, &chain_id, &iters_arg, &ns, &ps, &pc, &hist};
+                void *args[] = {&u->du, &T, &o, &d_sel, &n_sel_arg, &n_big, &chain_id, &iters_arg, &ns, &ps, &pc, &hist, &joint};
                 cudaError_t e = cudaLaunchCooperativeKernel((void *)k_noise_chain, dim3(grid), dim3(64), args, 0, s);
                 BTG_LAUNCHED();
                 if (e != cudaSuccess) { set_error("cooperative launch failed: %s", cudaGetErrorString(e)); rc = BTG_ECUDA; break; }
@@ -1395,7 +1437,7 @@ int btg_estimate_noise(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *op
         }
         if (rc == BTG_OK) {
             // mean of the post-burn-in rates -> setNoiseRates (InferenceEngine.cpp:259-264); final trace row "0 0"
-            k_noise_update<<<1, 256, 0, s>>>(ns, S, cd->prior_shape, cd->prior_scale, opts->random_seed, 2, 0, 0, 0, (double)opts->gibbs_samples * opts->n_chains);
+            if (!joint) k_noise_update<<<1, 256, 0, s>>>(ns, S, cd->prior_shape, cd->prior_scale, opts->random_seed, 2, 0, 0, 0, (double)opts->gibbs_samples * opts->n_chains);
             BTG_LAUNCHED();
             if (trace_out) cudaMemcpyAsync(trace_out, ns.trace, trace_rows * (2 + S) * 8, cudaMemcpyDeviceToHost, s);
             cudaError_t e = cudaStreamSynchronize(s);

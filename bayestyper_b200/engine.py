@@ -68,6 +68,14 @@ class InferenceEngine:
         capi.check(self.lib.btg_estimate_noise(self.h, cd.h, C.addressof(opts), capi.ptr(trace) if want_trace else None), self.lib)
         return trace
 
+    def estimate_noise_and_genotypes(self, cd: CountDistribution, opts: GibbsOpts, want_trace: bool = True):
+        """InferenceEngine::estimateNoiseAndGenotypes (--noise-genotyping)."""
+        res, arrays = self.unit.alloc_result()
+        rows = opts.n_chains * (opts.gibbs_burn_in + opts.gibbs_samples + 1)
+        trace = np.zeros((rows, 2 + self.unit.S)) if want_trace else None
+        capi.check(self.lib.btg_estimate_noise_and_genotypes(self.h, cd.h, C.addressof(opts), C.addressof(res), capi.ptr(trace) if want_trace else None), self.lib)
+        return arrays, trace
+
     def cluster_tally(self, cluster: int) -> np.ndarray:
         H = int(self.unit.a["cl_nhap"][cluster])
         n = (H + 1) * (H + 2) // 2

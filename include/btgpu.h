@@ -331,6 +331,10 @@ int btg_unit_download_result(btg_unit *u, btg_genotype_result *out, void *stream
 /* InferenceEngine::estimateNoise (InferenceEngine.cpp:135-276): updates cd's noise rates; trace_out (optional)
  * receives the <prefix>_noise_parameters.txt rows: [n_chains*(iters+1)+1][2+S] doubles (chain, iteration, rates..) */
 int btg_estimate_noise(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, double *trace_out);
+/* InferenceEngine::estimateNoiseAndGenotypes (InferenceEngine.cpp:384-472, --noise-genotyping): all groups in lock-step, noise
+ * rates redrawn after every iteration, genotypers persisting across chains; trace rows: [n_chains*(iters+1)][2+S] */
+int btg_estimate_noise_and_genotypes(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, btg_genotype_result *out,
+                                     double *trace_out);
 /* raw diplotype tallies of one cluster (tests): [(H+1)(H+2)/2][S] uint32, pair (h1<=h2), index h2*(h2+1)/2+h1, H = "missing" */
 int btg_unit_cluster_tally(const btg_unit *u, uint32_t cluster, uint32_t *tally_out, uint64_t n);
 

@@ -734,6 +734,63 @@ int bto_estimate_noise(const btg_unit_desc *d, void *cd, const btg_gibbs_opts *o
     return 0;
 }
 
+
+// InferenceEngine::estimateNoiseAndGenotypes (InferenceEngine.cpp:384-472): every group advances in lock-step, the noise
+// rates are redrawn after EVERY iteration (burn-in and sampling alike) and the genotypers persist across chains (only
+// chain 0's seed is ever used: VariantClusterGroup::initGenotyper constructs once, InferenceEngine.cpp:70).
+int bto_estimate_noise_and_genotypes(const btg_unit_desc *d, void *cd, const btg_gibbs_opts *o, btg_genotype_result *out, double *trace_out) {
+    CountTables &T = *asTables(cd);
+    const uint32_t S = d->n_samples;
+    for (uint32_t g = 0; g < d->n_groups; g++)
+        if (d->group_cluster_off[g + 1] - d->group_cluster_off[g] != 1) return -1;
+    Philox noise_prng;
+    noise_prng.init(o->random_seed, (uint64_t)-1, 0, 4);
+    auto sampleGamma = [&](double shape, double scale) { return noise_prng.gamma(shape) * scale; };
+    auto resetNoiseRates = [&]() {
+        for (uint32_t s = 0; s < S; s++) T.noise_rates[s] = sampleGamma(T.prior_shape, T.prior_scale);
+        T.updateNoise();
+    };
+    resetNoiseRates();  // CountDistribution ctor
+    size_t row = 0;
+    auto trace = [&](double chain, double it) {
+        if (!trace_out) return;
+        double *r = trace_out + row * (2 + S);
+        r[0] = chain; r[1] = it;
+        for (uint32_t s = 0; s < S; s++) r[2 + s] = T.noise_rates[s];
+        row++;
+    };
+    std::vector<Genotyper> gts(d->n_groups);
+    for (uint32_t chain = 0; chain < o->n_chains; chain++) {
+        for (uint32_t g = 0; g < d->n_groups; g++) {
+            if (chain == 0) gts[g].init(d, o, (uint32_t)d->group_cluster_off[g], o->group_index_base + g, 0);
+            gts[g].reset();
+        }
+        trace(chain + 1, 0);
+        for (uint32_t it = 1; it <= (uint32_t)o->gibbs_burn_in + o->gibbs_samples; it++) {
+            std::vector<uint64_t> hist((size_t)S * 256, 0);
+            for (uint32_t g = 0; g < d->n_groups; g++) {
+                const uint8_t *ploidy = d->group_ploidy + (size_t)g * S;
+                gts[g].sampleDiplotypes(T, ploidy, it > o->gibbs_burn_in);
+                gts[g].sampleHaplotypeFrequencies();
+                gts[g].getNoiseCounts(hist);
+                for (auto &mc : gts[g].unique_cache) mc.clear();
+            }
+            for (uint32_t s = 0; s < S; s++) {
+                uint64_t n_obs = 0, sum = 0;
+                for (uint32_t i = 0; i < 256; i++) { n_obs += hist[(size_t)s * 256 + i]; sum += i * hist[(size_t)s * 256 + i]; }
+                const float shape_f = (float)T.prior_shape + (float)sum;
+                const float scale_f = (float)T.prior_scale / ((float)n_obs * (float)T.prior_scale + 1);
+                T.noise_rates[s] = sampleGamma(shape_f, scale_f);
+            }
+            T.updateNoise();
+            trace(chain + 1, it);
+        }
+        resetNoiseRates();
+    }
+    for (uint32_t g = 0; g < d->n_groups; g++) summarise(gts[g], d->group_ploidy + (size_t)g * S, out);
+    return 0;
+}
+
 void bto_count_dist_get_noise_rates(void *cd, double *out) {
     auto *t = asTables(cd);
     memcpy(out, t->noise_rates.data(), t->S * 8);

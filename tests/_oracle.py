@@ -118,6 +118,7 @@ def _bind_gibbs(L):
     L.bto_nb_moments_to_parameters.argtypes = [C.c_double, C.c_double, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.bto_estimate_genotypes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.bto_estimate_noise.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.bto_estimate_noise_and_genotypes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L._gibbs_bound = True
 
 
@@ -170,3 +171,15 @@ def oracle_estimate_noise(unit, cd: OracleCountDist, opts):
     rc = L.bto_estimate_noise(C.addressof(desc), cd.h, C.addressof(opts), trace.ctypes.data)
     assert rc == 0, rc
     return trace
+
+
+def oracle_estimate_noise_and_genotypes(unit, cd: OracleCountDist, opts):
+    L = load()
+    _bind_gibbs(L)
+    res, arrays = unit.alloc_result()
+    desc = unit.desc()
+    rows = opts.n_chains * (opts.gibbs_burn_in + opts.gibbs_samples + 1)
+    trace = np.zeros((rows, 2 + unit.S))
+    rc = L.bto_estimate_noise_and_genotypes(C.addressof(desc), cd.h, C.addressof(opts), C.addressof(res), trace.ctypes.data)
+    assert rc == 0, rc
+    return arrays, trace

@@ -22,10 +22,10 @@ from bayestyper_b200 import btd, synth, unit as U, vcfio  # noqa: E402
 BTREF = ROOT / "oracle" / "_ref" / "btref"
 
 
-def make(name, workload, n_groups, seed=20190401, n_errors=20000):
+def make(name, workload, n_groups, seed=20190401, n_errors=20000, extra_args=()):
     with tempfile.TemporaryDirectory() as td:
         wd = synth.write_workdir(workload, td, n_errors=n_errors)
-        subprocess.check_call([str(BTREF), "run", "--workdir", str(wd), "--threads", "8", "--seed", str(seed), "--dump-graphs", "--dump-haps"],
+        subprocess.check_call([str(BTREF), "run", "--workdir", str(wd), "--threads", "8", "--seed", str(seed), "--dump-graphs", "--dump-haps", *extra_args],
                               stdout=subprocess.DEVNULL)
         out = Path(wd) / "ref_out"
         g = btd.read(out / "graphs.btd"); h = btd.read(out / "haps.btd"); t = btd.read(out / "tables.btd")
@@ -183,6 +183,9 @@ if __name__ == "__main__":
     if len(_sys.argv) > 1 and _sys.argv[1] == "pipe":
         for nm, fn in PIPE_WORKLOADS.items():
             make_pipeline(nm, fn())
+        _sys.exit(0)
+    if len(_sys.argv) > 1 and _sys.argv[1] == "joint":
+        make("gibbs_joint_2s", synth.small_mixed(260, 24_000, 2, seed=83), 400, extra_args=("--noise-genotyping",))
         _sys.exit(0)
     if len(_sys.argv) > 1 and _sys.argv[1] == "e2e":
         for nm, fn in E2E_WORKLOADS.items():

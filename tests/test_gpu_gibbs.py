@@ -111,6 +111,25 @@ def test_multi_sample_noise(btg):
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["gibbs_snv_1s", "gibbs_chrx_2s"])
+def test_noise_genotyping_joint_mode_matches_oracle(btg, name):
+    """--noise-genotyping: InferenceEngine::estimateNoiseAndGenotypes (all groups in lock-step)."""
+    fx = GibbsFixture(name)
+    opts = fx.opts(chains=3, burn=20, samples=40)
+    ocd, gcd = _both(fx, opts)
+    ores, otrace = O.oracle_estimate_noise_and_genotypes(fx.unit, ocd, opts)
+    eng = engine.InferenceEngine(fx.unit)
+    gres, gtrace = eng.estimate_noise_and_genotypes(gcd, opts)
+    assert gtrace.shape == otrace.shape and (gtrace[:, :2] == otrace[:, :2]).all()
+    assert (np.abs(gtrace[:, 2:] - otrace[:, 2:]) / otrace[:, 2:]).max() < 1e-9
+    assert np.abs(gres["gpp"] - ores["gpp"]).max() <= GPP_TOL
+    for k in ("gt", "gq", "saf", "an", "ac"):
+        assert (gres[k] == ores[k]).all(), k
+    for k in ("nak", "fak", "mac", "app", "acp"):
+        assert np.abs(gres[k] - ores[k]).max() <= 1e-4, k
+    eng.close()
+
+
 def test_rejects_nested_groups_loudly(btg):
     fx = GibbsFixture("gibbs_snv_1s")
     a = dict(fx.unit.a)

@@ -83,3 +83,24 @@ def test_nb_moments():
         assert abs(g[0, m, c] - want) < 1e-12                                   # SURVEY §4 logPmf vectors
     L.bto_nb_moments_to_parameters(10.0, 5.0, 2, C.byref(p), C.byref(size))   # var < mean: p capped at 0.99
     assert abs(p.value - 0.99) < 1e-15
+
+
+def test_joint_noise_genotyping_statistically_equal_to_reference():
+    """--noise-genotyping (InferenceEngine::estimateNoiseAndGenotypes): the fixture holds every group of the reference run, so
+    the noise-rate trace is comparable in distribution, not only the calls."""
+    fx = GibbsFixture("gibbs_joint_2s")
+    cd = O.OracleCountDist(fx.nb_p, fx.nb_size)
+    res, trace = O.oracle_estimate_noise_and_genotypes(fx.unit, cd, fx.opts())
+    S = fx.S
+    gt_o, gt_r = res["gt"].reshape(-1, S, 2), fx.ref["gt"].reshape(-1, S, 2)
+    same = (gt_o == gt_r).all(axis=2)
+    assert same.mean() > 0.97
+    called_both = (gt_o[..., 0] != 0xFFFF) & (gt_r[..., 0] != 0xFFFF)
+    assert (~same & called_both).sum() <= max(1, int(0.004 * same.size))
+    assert np.abs(res["gpp"] - fx.ref["gpp"]).mean() < 4e-3
+    ref_tr = fx.noise_trace
+    assert trace.shape == ref_tr.shape
+    post_o = trace[trace[:, 1] > 100][:, 2:]
+    post_r = ref_tr[ref_tr[:, 1] > 100][:, 2:]
+    # posterior means of the per-sample noise rates agree within a few percent (7000 draws each)
+    assert np.abs(post_o.mean(0) / post_r.mean(0) - 1).max() < 0.1
