@@ -756,50 +756,6 @@ struct NoiseState {
     uint32_t *trace_row;
 };
 
-__global__ void __launch_bounds__(64) k_noise_init(DevUnit du, btg_gibbs_opts o, const uint32_t *sel, uint32_t n_sel, uint32_t chain) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_sel) return;
-    Cl cl;
-    cl.bind(du, sel[i]);
-    const uint64_t gidx = o.group_index_base + cl.g;
-    cl_construct(cl, o, gidx, chain);  // fresh genotypers every chain (InferenceEngine.cpp:60-75,240-251)
-    Philox prng, fr;
-    prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, chain);
-    fr.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngFrequency, chain);
-    cl_reset(cl, o, prng);
-    prng.save(cl.misc, kRng0);
-    fr.save(cl.misc, kRng1);
-}
-
-// sampleGenotypesCallback (InferenceEngine.cpp:77-98): one Gibbs iteration + noise-count histogram
-__global__ void __launch_bounds__(64) k_noise_iteration(DevUnit du, Tables T, btg_gibbs_opts o, const uint32_t *sel, uint32_t n_sel, unsigned long long *hist) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_sel) return;
-    Cl cl;
-    cl.bind(du, sel[i]);
-    const uint64_t gidx = o.group_index_base + cl.g;
-    const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
-    Philox prng, fr;
-    prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
-    fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
-    cl_sample_diplotypes(cl, T, ploidy, false, prng);
-    cl_sample_frequencies(cl, fr);
-    // VariantClusterGenotyper::getNoiseCounts (…Genotyper.cpp:757-779)
-    const uint32_t n_sub = cl.misc[kNSub];
-    for (uint32_t s = 0; s < cl.S; s++) {
-        const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
-        for (uint32_t j = 0; j < n_sub; j++) {
-            const uint32_t k = cl.uniq_sub[j];
-            if ((uint8_t)(cl.diplMult(k, da, db) + cl.ic(k, s)) == 0) atomicAdd(hist + s * 256u + cl.count(k, s), 1ULL);
-        }
-    }
-    // clearGenotyperCache: the Poisson table is about to change
-    const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    for (uint32_t j = 0; j < cl.S * cl.Dall; j++) cl.ucache[j] = nan;
-    prng.save(cl.misc, kRng0);
-    fr.save(cl.misc, kRng1);
-}
-
 // CountDistribution::sampleNoiseParameters / resetNoiseRates + updateNoiseCache, on the device so that the
 // iteration loop never synchronises with the host.  mode 0: reset from the prior; 1: posterior draw from hist;
 // 2: set to the accumulated mean.  One block; thread 0 draws, then all threads rebuild the Poisson rows.
