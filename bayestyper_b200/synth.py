@@ -108,7 +108,7 @@ def apply_variants(reference: bytes, variants: list, alleles: np.ndarray) -> byt
     parts = []
     cur = 0
     for v, a in zip(variants, alleles.tolist()):
-        if a == 0:
+        if a == 0 or v.pos < cur:      # inside an applied deletion: the allele is missing on this haplotype
             continue
         parts.append(reference[cur:v.pos])
         parts.append(v.alts[a - 1])
@@ -223,6 +223,44 @@ def small_mixed(n_variants: int, length: int, n_samples: int, seed: int, frac_in
     g = make_genotypes(len(var), n_samples, seed + 2, allele_freq=af)
     genders = ["F" if i % 2 == 0 else "M" for i in range(n_samples)]
     return Workload("mixed", chrom, ref, var, g, genders)
+
+
+def nested_sv(n_sv: int, length: int, n_samples: int, seed: int, sv_len=(150, 500), inner_rate: float = 0.012,
+              n_background: int = 0, chrom: str = "chr1", repeat_frac: float = 0.0) -> Workload:
+    """Large deletions with SNVs inside their span: the reference turns the inner variants into clusters
+    nested under the deletion's cluster (VariantFileParser.cpp:735-1000, has_dependency) and k-mers shared
+    between the clusters of such a group into multicluster k-mers (KmerCounts.cpp:137-160)."""
+    rng = np.random.default_rng(seed)
+    r = np.frombuffer(random_reference(length, seed), np.uint8).copy()
+    starts = np.sort(rng.choice(np.arange(2 * K, length - 2 * K - sv_len[1], 4 * sv_len[1]), size=n_sv, replace=False))
+    spans = []
+    for p in starts.tolist():
+        p += int(rng.integers(0, sv_len[1]))
+        ln = int(rng.integers(sv_len[0], sv_len[1]))
+        rep = ln >= 300 and rng.random() < repeat_frac
+        if rep:     # a 110-nt segment duplicated inside the deleted span: k-mers shared by clusters of ONE group
+            r[p + 150:p + 260] = r[p + 20:p + 130]
+        spans.append((p, ln, rep))
+    ref = r.tobytes()
+    var = []
+    for p, ln, rep in spans:
+        var.append(Variant(p, r[p:p + 1 + ln].tobytes(), [r[p:p + 1].tobytes()]))
+        inner = np.flatnonzero(rng.random(ln - 2) < inner_rate) + p + 2
+        if rep:
+            inner = np.array([p + 50, p + 230], np.int64)
+        for q in inner.tolist():
+            alt = _ACGT[(int(_CODE[r[q]]) + int(rng.integers(1, 4))) % 4]
+            var.append(Variant(q, r[q:q + 1].tobytes(), [bytes([alt])]))
+    if n_background:
+        taken = [(v.pos - K, v.pos + len(v.ref) + K) for v in var if len(v.ref) > 1]
+        for v in make_variants(ref, n_background, seed + 3, 0.05, 0.05, max_indel=20):
+            if not any(a <= v.pos <= b for a, b in taken):
+                var.append(v)
+    var.sort(key=lambda v: (v.pos, -len(v.ref)))
+    af = rng.beta(0.8, 0.8, len(var))
+    g = make_genotypes(len(var), n_samples, seed + 2, allele_freq=af)
+    genders = ["F" if i % 2 == 0 else "M" for i in range(n_samples)]
+    return Workload("nested", chrom, ref, var, g, genders)
 
 
 def sample_spectra(w: Workload, seed: int = 4, n_errors: int = 0):

@@ -172,5 +172,13 @@ def from_ref_dumps(haps: dict, graphs: dict, genders, ploidy=None) -> Unit:
     a["cl_nhap"] = np.diff(haps["cl_hap_off"]).astype(np.uint32)
     a["var_nalleles"] = (1 + graphs["var_dep"].astype(np.uint16) + graphs["var_nalt"]).astype(np.uint16)
     a["var_dep"] = graphs["var_dep"]
-    a["k_shared"] = np.full(len(haps["k_has_counts"]), 0xFFFFFFFF, np.uint32)
+    # multicluster k-mers (KmerCounts::has_multicluster_occ, bit 1 of k_flags): rows of different clusters holding the
+    # same k-mer share one KmerCounts record, hence one per-sample multiplicity (KmerCounts.cpp:205-224)
+    shared = np.full(len(haps["k_has_counts"]), 0xFFFFFFFF, np.uint32)
+    multi = np.flatnonzero((haps["k_flags"] & 2) != 0)
+    if len(multi):
+        words = haps["kmer_words"].reshape(-1, 2)[multi]
+        _, ids = np.unique(words, axis=0, return_inverse=True)
+        shared[multi] = ids.reshape(-1).astype(np.uint32)
+    a["k_shared"] = shared
     return Unit(a, S)

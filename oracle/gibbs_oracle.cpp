@@ -221,7 +221,11 @@ struct Genotyper {
     uint32_t num_hap_count = 0, num_missing_count = 0;
     std::map<std::pair<uint32_t, uint32_t>, std::vector<double> > simplex_cache;
     // VariantClusterGenotyper state
-    std::vector<std::map<Dipl, double> > unique_cache;
+    std::vector<std::map<Dipl, double> > unique_cache, multi_cache;
+    bool use_multi = false;
+    std::vector<uint8_t> sample_multi;  // sample_multicluster_kmer_multiplicities [multi_sub][S]
+    uint8_t *shared = nullptr;          // KmerCounts::multiplicities of the group-shared k-mer records [id][S]
+    uint64_t hap0 = 0;                  // index of this cluster's first haplotype in hap_nested_off
     std::vector<Dipl> dipl;
     std::map<Dipl, std::vector<uint32_t> > tally;
     struct StatsCache { bool update = true; std::vector<KStats> h1, h2; };
@@ -243,10 +247,25 @@ struct Genotyper {
         return r;
     }
     uint8_t uniqueMult(uint32_t k, const Dipl &dp, uint32_t s) const { return (uint8_t)(diplMult(k, dp) + ic(k, s)); }
+    // KmerCounts::getSampleMultiplicity of a multicluster k-mer (KmerCounts.cpp:205-224)
+    uint8_t &sharedMult(uint32_t k, uint32_t s) const { return shared[(size_t)d->k_shared[row0 + k] * S + s]; }
+    // VariantClusterHaplotypes::getMulticlusterKmerMultiplicity (VariantClusterHaplotypes.cpp:76-93)
+    uint8_t multiMult(uint32_t k, const Dipl &dp, const Dipl &prev, uint32_t s) const {
+        if (count(k, s) == 0) return (uint8_t)(diplMult(k, dp) + ic(k, s));
+        return (uint8_t)(sharedMult(k, s) - diplMult(k, prev) + diplMult(k, dp) + ic(k, s));
+    }
+    // VariantClusterHaplotypes::getPreviousMulticlusterKmerMultiplicity (VariantClusterHaplotypes.cpp:95-108)
+    uint8_t prevMultiMult(uint32_t sub, const Dipl &dp, const Dipl &prev, uint32_t s) const {
+        const uint32_t k = multi_sub[sub];
+        return (uint8_t)(sample_multi[(size_t)sub * S + s] - diplMult(k, prev) + diplMult(k, dp) + ic(k, s));
+    }
 
     // VariantClusterGenotyper ctor (VariantClusterGenotyper.cpp:59-106)
-    void init(const btg_unit_desc *desc, const btg_gibbs_opts *opts, uint32_t cluster, uint64_t group_index, uint32_t chain) {
+    void init(const btg_unit_desc *desc, const btg_gibbs_opts *opts, uint32_t cluster, uint64_t group_index, uint32_t chain,
+              uint8_t *shared_mult = nullptr, uint64_t first_haplotype = 0) {
         d = desc; o = opts; c = cluster;
+        shared = shared_mult;
+        hap0 = first_haplotype;
         S = d->n_samples;
         H = d->cl_nhap[c];
         row0 = d->cl_kmer_off[c];
@@ -259,6 +278,8 @@ struct Genotyper {
         uniq.assign(d->uniq_idx + d->cl_uniq_off[c], d->uniq_idx + d->cl_uniq_off[c + 1]);
         multi.assign(d->multi_idx + d->cl_multi_off[c], d->multi_idx + d->cl_multi_off[c + 1]);
         unique_cache.assign(S, std::map<Dipl, double>());
+        multi_cache.assign(S, std::map<Dipl, double>());
+        assert(multi.empty() || shared);
         dipl.assign(S, Dipl(NONE, NONE));
         stats_cache.assign(S, StatsCache());
         for (auto &sc : stats_cache) { sc.h1.assign(nvar, KStats()); sc.h2.assign(nvar, KStats()); }
@@ -325,11 +346,45 @@ struct Genotyper {
         for (auto k : uniq) if (prng.u01() < rate) if (!isMaxHapVarKmer(cnt, k)) uniq_sub.push_back(k);
         prng.shuffle(multi);
         for (auto k : multi) if (prng.u01() < rate) if (!isMaxHapVarKmer(cnt, k)) multi_sub.push_back(k);
+        sample_multi.assign(multi_sub.size() * (size_t)S, 0);
         for (auto &sc : stats_cache) sc.update = true;
-        for (auto &mcache : unique_cache) mcache.clear();
+        use_multi = false;
+        clearCache();
         resetFrequencies();
     }
-    // VariantClusterGenotyper::calcDiplotypeLogProb (VariantClusterGenotyper.cpp:597-666), unique k-mers only
+    void clearCache() {  // VariantClusterGenotyper::clearCache (…Genotyper.cpp:131-138)
+        for (auto &mcache : unique_cache) mcache.clear();
+        for (auto &mcache : multi_cache) mcache.clear();
+    }
+    // VariantClusterGenotyper::updateMulticlusterDiplotypeLogProb (…Genotyper.cpp:569-595): the cached terms of k-mers
+    // whose shared multiplicity was changed by another cluster of the group are replaced in place
+    void updateMulticlusterDiplotypeLogProb(const CountTables &T, uint32_t s) {
+        if (multi_cache[s].empty()) return;
+        for (uint32_t sub = 0; sub < multi_sub.size(); sub++) {
+            const uint32_t k = multi_sub[sub];
+            if (!(count(k, s) > 0 && sharedMult(k, s) != sample_multi[(size_t)sub * S + s])) continue;  // isMulticlusterKmerUpdated
+            for (auto &e : multi_cache[s]) {
+                e.second -= T.logProb(s, prevMultiMult(sub, e.first, dipl[s], s), count(k, s));
+                e.second += T.logProb(s, multiMult(k, e.first, dipl[s], s), count(k, s));
+            }
+        }
+    }
+    // VariantClusterHaplotypes::updateMulticlusterKmerMultiplicities (VariantClusterHaplotypes.cpp:197-233)
+    void updateMulticlusterKmerMultiplicities(const Dipl &dp, const Dipl &prev, uint32_t s) {
+        if (dp != prev) {
+            stats_cache[s].update = true;
+            for (auto k : multi) {
+                const uint8_t cur = diplMult(k, dp), old = diplMult(k, prev);
+                if (cur != old) { assert(old <= sharedMult(k, s)); sharedMult(k, s) -= old; sharedMult(k, s) += cur; }
+            }
+        }
+        for (uint32_t sub = 0; sub < multi_sub.size(); sub++) {
+            const uint32_t k = multi_sub[sub];
+            if (diplMult(k, dp) > 0 && count(k, s) > 0 && sharedMult(k, s) != sample_multi[(size_t)sub * S + s]) stats_cache[s].update = true;
+            sample_multi[(size_t)sub * S + s] = sharedMult(k, s);
+        }
+    }
+    // VariantClusterGenotyper::calcDiplotypeLogProb (VariantClusterGenotyper.cpp:597-666)
     double calcDiplotypeLogProb(const CountTables &T, uint32_t s, const Dipl &dp) {
         double lp = 0;
         if (dp.second == NONE) lp += std::log(freq[dp.first]);
@@ -342,6 +397,15 @@ struct Genotyper {
             ins.first->second = acc;
         }
         lp += ins.first->second;
+        if (use_multi) {
+            auto mins = multi_cache[s].emplace(dp, 0.0);
+            if (mins.second) {
+                double acc = 0;
+                for (auto k : multi_sub) acc += T.logProb(s, multiMult(k, dp, dipl[s], s), count(k, s));
+                mins.first->second = acc;
+            }
+            lp += mins.first->second;
+        }
         assert(std::isfinite(lp));
         return lp;
     }
@@ -393,8 +457,10 @@ struct Genotyper {
             else { allele_stats[v][s].addKmerStats(cache[v], a); last = v; }
         }
     }
-    // VariantClusterHaplotypes::updateAlleleKmerStats (VariantClusterHaplotypes.cpp:235-300), no nested clusters
-    void updateAlleleKmerStats() {
+    // VariantClusterHaplotypes::NestedVariantClusterInfo (VariantClusterHaplotypes.hpp:103-109)
+    struct NestedInfo { uint8_t ploidy; std::vector<KStats> stats; };
+    // VariantClusterHaplotypes::updateAlleleKmerStats (VariantClusterHaplotypes.cpp:235-300)
+    void updateAlleleKmerStats(const std::vector<NestedInfo> &nested) {
         for (uint32_t s = 0; s < S; s++) {
             const Dipl dp = dipl[s];
             auto &sc = stats_cache[s];
@@ -403,25 +469,59 @@ struct Genotyper {
                 for (uint32_t v = 0; v < nvar; v++) { sc.h1[v].reset(); sc.h2[v].reset(); }
                 if (dp.first != NONE)
                     for (auto k : uniq_sub) if (diplMult(k, dp) > 0) updateKmerStatsCache(k, dp, s, uniqueMult(k, dp, s));
+                if (dp.first != NONE)
+                    for (auto k : multi_sub) if (diplMult(k, dp) > 0) updateKmerStatsCache(k, dp, s, multiMult(k, dp, dp, s));
             }
             if (dp.first != NONE) addHaplotypeKmerStats(sc.h1, s, dp.first);
             if (dp.second != NONE) addHaplotypeKmerStats(sc.h2, s, dp.second);
+            for (auto &ks : nested[s].stats)  // addNestedHaplotypeKmerStats (VariantClusterHaplotypes.cpp:363-372)
+                for (uint32_t v = 0; v < nvar; v++) allele_stats[v][s].addKmerStats(ks, (uint16_t)(nalleles(v) - 1));
+        }
+    }
+    // VariantClusterGenotyper::updateNestedVariantClusterInfo / updateNestedPloidy / addNestedKmerStats (…Genotyper.cpp:140-206)
+    void updateNestedVariantClusterInfo(std::vector<NestedInfo> &nested, uint32_t child_cluster_idx) const {
+        uint64_t dep = d->cl_dep_off[c];
+        while (dep < d->cl_dep_off[c + 1] && d->dep_cluster[dep] != child_cluster_idx) dep++;
+        for (uint32_t s = 0; s < S; s++) {
+            for (int which = 0; which < 2; which++) {
+                const uint16_t h = which == 0 ? dipl[s].first : dipl[s].second;
+                if (h == NONE) continue;
+                const uint32_t *nb = d->hap_nested + d->hap_nested_off[hap0 + h], *ne = d->hap_nested + d->hap_nested_off[hap0 + h + 1];
+                if (std::binary_search(nb, ne, child_cluster_idx)) continue;
+                assert(nested[s].ploidy != 0);
+                nested[s].ploidy = nested[s].ploidy == 2 ? 1 : 0;
+                assert(dep < d->cl_dep_off[c + 1] && nested[s].stats.size() < 2);
+                uint32_t v = NONE;
+                for (uint64_t e = d->dep_var_off[dep]; e < d->dep_var_off[dep + 1]; e++) {
+                    const uint16_t nv = d->dep_var[e];
+                    if (!isMissing(nv, hapAllele(h, nv))) { v = nv; break; }
+                }
+                assert(v != NONE);
+                nested[s].stats.push_back(which == 0 ? stats_cache[s].h1[v] : stats_cache[s].h2[v]);
+            }
         }
     }
     // VariantClusterGenotyper::sampleDiplotypes (VariantClusterGenotyper.cpp:668-705)
-    void sampleDiplotypes(const CountTables &T, const uint8_t *ploidy, bool collect) {
+    void sampleDiplotypes(const CountTables &T, const std::vector<NestedInfo> &nested, bool collect) {
         std::vector<uint16_t> nzh;
         for (uint16_t h = 0; h < H; h++) if (nz[h]) nzh.push_back(h);
         for (uint32_t s = 0; s < S; s++) {
             const Dipl prev = dipl[s];
-            sampleDiplotype(nzh, T, s, ploidy[s]);
-            if (dipl[s] != prev) stats_cache[s].update = true;  // updateMulticlusterKmerMultiplicities, …Haplotypes.cpp:199-201
+            updateMulticlusterDiplotypeLogProb(T, s);
+            sampleDiplotype(nzh, T, s, nested[s].ploidy);
+            updateMulticlusterKmerMultiplicities(dipl[s], prev, s);
             if (collect) {
                 auto it = tally.emplace(dipl[s], std::vector<uint32_t>(S, 0)).first;
                 it->second[s]++;
             }
         }
-        if (collect) updateAlleleKmerStats();
+        if (collect) updateAlleleKmerStats(nested);
+        use_multi = !multi_sub.empty();
+    }
+    void sampleDiplotypes(const CountTables &T, const uint8_t *ploidy, bool collect) {  // a group of one cluster
+        std::vector<NestedInfo> top(S);
+        for (uint32_t s = 0; s < S; s++) top[s].ploidy = ploidy[s];
+        sampleDiplotypes(T, top, collect);
     }
     // SparseFrequencyDistribution::updateCachedSimplexProbVector (FrequencyDistribution.cpp:143-196)
     void simplexProbVector(std::vector<double> &vec, uint32_t n_obs, uint32_t plus_size) const {
@@ -488,6 +588,63 @@ struct Genotyper {
                 if (uniqueMult(k, dipl[s], s) == 0) hist[(size_t)s * 256 + count(k, s)]++;
     }
 };
+
+// VariantClusterGroup (VariantClusterGroup.cpp:47-260): the clusters of one group, the nested-cluster forest over them
+// and the shared multiplicity records of their multicluster k-mers
+struct Group {
+    const btg_unit_desc *d;
+    uint32_t g, S;
+    uint64_t c0;
+    std::vector<Genotyper> gts;
+    std::vector<uint32_t> src;
+    std::vector<std::vector<uint32_t> > out_edges;
+    void init(const btg_unit_desc *desc, const btg_gibbs_opts *o, uint32_t group, uint32_t chain, uint8_t *shared, const std::vector<uint64_t> &hap_start) {
+        d = desc; g = group; S = d->n_samples;
+        c0 = d->group_cluster_off[g];
+        const uint32_t n = (uint32_t)(d->group_cluster_off[g + 1] - c0);
+        gts.resize(n);
+        for (uint32_t i = 0; i < n; i++) gts[i].init(d, o, (uint32_t)(c0 + i), o->group_index_base + g, chain, shared, hap_start[c0 + i]);
+        src.assign(d->group_src + d->group_src_off[g], d->group_src + d->group_src_off[g + 1]);
+        out_edges.assign(n, std::vector<uint32_t>());
+        for (uint64_t e = d->group_edge_off[g]; e < d->group_edge_off[g + 1]; e++) out_edges[d->group_edge_src[e]].push_back(d->group_edge_dst[e]);
+    }
+    void reset() { for (auto &gt : gts) gt.reset(); }  // VariantClusterGroup::initGenotyper (…Group.cpp:175-186)
+    // VariantClusterGroup::shuffleBranchOrdering (…Group.cpp:208-218): cumulative, own stream (kind 3)
+    void shuffleBranchOrdering(const btg_gibbs_opts *o, uint32_t chain) {
+        Philox br;
+        br.init(o->random_seed, o->group_index_base + g, 0, 3, chain);
+        br.shuffle(src);
+        for (auto &e : out_edges) br.shuffle(e);
+    }
+    // VariantClusterGroup::estimateGenotypes / runGibbsSample (…Group.cpp:220-250)
+    void run(uint32_t v, const CountTables &T, const std::vector<Genotyper::NestedInfo> &nested, bool collect) {
+        gts[v].sampleDiplotypes(T, nested, collect);
+        gts[v].sampleHaplotypeFrequencies();
+        for (auto t : out_edges[v]) {
+            auto child = nested;
+            gts[v].updateNestedVariantClusterInfo(child, d->cluster_idx[c0 + t]);
+            run(t, T, child, collect);
+        }
+    }
+    void estimateGenotypes(const CountTables &T, bool collect) {
+        std::vector<Genotyper::NestedInfo> top(S);
+        for (uint32_t s = 0; s < S; s++) top[s].ploidy = d->group_ploidy[(size_t)g * S + s];
+        for (auto v : src) run(v, T, top, collect);
+    }
+};
+
+// index of each cluster's first haplotype in hap_nested_off, and the number of shared multiplicity records
+std::vector<uint64_t> haplotypeStarts(const btg_unit_desc *d) {
+    std::vector<uint64_t> h(d->n_clusters + 1, 0);
+    for (uint32_t c = 0; c < d->n_clusters; c++) h[c + 1] = h[c] + d->cl_nhap[c];
+    return h;
+}
+size_t sharedRecords(const btg_unit_desc *d) {
+    size_t n = 0;
+    const uint64_t rows = d->cl_kmer_off[d->n_clusters];
+    for (uint64_t r = 0; r < rows; r++) if (d->k_shared[r] != 0xFFFFFFFFu) n = std::max(n, (size_t)d->k_shared[r] + 1);
+    return n;
+}
 
 uint16_t hapToAllele(const Genotyper &g, uint16_t h, uint32_t v) { return h != NONE ? g.hapAllele(h, v) : g.nalleles(v) - 1; }  // …Genotyper.cpp:208-219
 
@@ -637,25 +794,27 @@ void bto_nb_moments_to_parameters(double mean, double var, uint32_t multiplicity
 int bto_estimate_genotypes(const btg_unit_desc *d, void *cd, const btg_gibbs_opts *o, btg_genotype_result *out,
                            uint32_t *tally_out, const uint64_t *tally_off) {
     const CountTables &T = *asTables(cd);
+    const std::vector<uint64_t> hap_start = haplotypeStarts(d);
+    std::vector<uint8_t> shared(sharedRecords(d) * (size_t)d->n_samples, 0);
     for (uint32_t g = 0; g < d->n_groups; g++) {
-        const uint64_t c0 = d->group_cluster_off[g], c1 = d->group_cluster_off[g + 1];
-        if (c1 - c0 != 1) return -1;  // nested cluster groups: not restated yet
-        const uint32_t c = (uint32_t)c0;
         const uint8_t *ploidy = d->group_ploidy + (size_t)g * d->n_samples;
-        Genotyper gt;
-        gt.init(d, o, c, o->group_index_base + g, 0);
+        Group grp;
+        grp.init(d, o, g, 0, shared.data(), hap_start);  // genotypers are constructed once and persist across chains
         for (uint32_t chain = 0; chain < o->n_chains; chain++) {
-            gt.reset();
-            for (uint32_t i = 0; i < o->gibbs_burn_in; i++) { gt.sampleDiplotypes(T, ploidy, false); gt.sampleHaplotypeFrequencies(); }
-            for (uint32_t i = 0; i < o->gibbs_samples; i++) { gt.sampleDiplotypes(T, ploidy, true); gt.sampleHaplotypeFrequencies(); }
+            grp.reset();
+            grp.shuffleBranchOrdering(o, chain);
+            for (uint32_t i = 0; i < o->gibbs_burn_in; i++) grp.estimateGenotypes(T, false);
+            for (uint32_t i = 0; i < o->gibbs_samples; i++) grp.estimateGenotypes(T, true);
         }
-        summarise(gt, ploidy, out);
-        if (tally_out) {
-            const uint32_t H = gt.H;
-            uint32_t *t = tally_out + tally_off[c];
-            for (auto &kv : gt.tally) {
-                uint32_t a = kv.first.first == NONE ? H : kv.first.first, b = kv.first.second == NONE ? H : kv.first.second;
-                for (uint32_t s = 0; s < d->n_samples; s++) t[((size_t)b * (b + 1) / 2 + a) * d->n_samples + s] = kv.second[s];
+        for (auto &gt : grp.gts) {  // collectGenotypes (…Group.cpp:262-278): every variant is summarised with the CHROMOSOME ploidy
+            summarise(gt, ploidy, out);
+            if (tally_out) {
+                const uint32_t H = gt.H;
+                uint32_t *t = tally_out + tally_off[gt.c];
+                for (auto &kv : gt.tally) {
+                    uint32_t a = kv.first.first == NONE ? H : kv.first.first, b = kv.first.second == NONE ? H : kv.first.second;
+                    for (uint32_t s = 0; s < d->n_samples; s++) t[((size_t)b * (b + 1) / 2 + a) * d->n_samples + s] = kv.second[s];
+                }
             }
         }
     }
@@ -711,7 +870,7 @@ int bto_estimate_noise(const btg_unit_desc *d, void *cd, const btg_gibbs_opts *o
                 gts[i].sampleDiplotypes(T, ploidy, false);
                 gts[i].sampleHaplotypeFrequencies();
                 gts[i].getNoiseCounts(hist);
-                for (auto &mc : gts[i].unique_cache) mc.clear();  // clearGenotyperCache
+                gts[i].clearCache();  // clearGenotyperCache
             }
             for (uint32_t s = 0; s < S; s++) {  // CountDistribution::sampleNoiseParameters (CountDistribution.cpp:173-200)
                 uint64_t n_obs = 0, sum = 0;
@@ -773,7 +932,7 @@ int bto_estimate_noise_and_genotypes(const btg_unit_desc *d, void *cd, const btg
                 gts[g].sampleDiplotypes(T, ploidy, it > o->gibbs_burn_in);
                 gts[g].sampleHaplotypeFrequencies();
                 gts[g].getNoiseCounts(hist);
-                for (auto &mc : gts[g].unique_cache) mc.clear();
+                gts[g].clearCache();
             }
             for (uint32_t s = 0; s < S; s++) {
                 uint64_t n_obs = 0, sum = 0;

@@ -42,7 +42,8 @@ def make(name, workload, n_groups, seed=20190401, n_errors=20000, extra_args=())
         un = U.from_ref_dumps(h, g, workload.genders, pl.reshape(-1))
         # keep a spread of groups: the largest ones and a stride through the rest
         rng = np.random.default_rng(7)
-        keep = np.unique(np.concatenate([np.arange(min(20, G)), rng.choice(G, size=min(n_groups, G), replace=False)]))
+        nested_groups = np.flatnonzero(np.diff(g["group_cluster_off"]) > 1)     # always keep every multi-cluster group
+        keep = np.unique(np.concatenate([np.arange(min(20, G)), nested_groups, rng.choice(G, size=min(n_groups, G), replace=False)]))
         sub = un.subset_groups(keep)
         _, rows = vcfio.read_vcf(out / "bayestyper.vcf")
         byid = {r["id"]: r for r in rows}
@@ -186,6 +187,10 @@ if __name__ == "__main__":
         _sys.exit(0)
     if len(_sys.argv) > 1 and _sys.argv[1] == "joint":
         make("gibbs_joint_2s", synth.small_mixed(260, 24_000, 2, seed=83), 400, extra_args=("--noise-genotyping",))
+        _sys.exit(0)
+    if len(_sys.argv) > 1 and _sys.argv[1] == "nested":
+        # deletions spanning SNVs (nested clusters, has_dependency) with duplicated segments (multicluster k-mers)
+        make("gibbs_nested_2s", synth.nested_sv(30, 120_000, 2, seed=5, n_background=300, sv_len=(150, 600), repeat_frac=0.6), 40)
         _sys.exit(0)
     if len(_sys.argv) > 1 and _sys.argv[1] == "e2e":
         for nm, fn in E2E_WORKLOADS.items():
