@@ -16,8 +16,10 @@
 // sorted by cost so that the 32 lanes of a warp carry similar work.  All arithmetic is f64 (the
 // reference's), table lookups go to the L2-resident log-pmf cache ([S][256][256] doubles).
 //
-// This file handles groups made of ONE cluster (no nested clusters, hence no multicluster k-mers);
-// btg_unit_upload rejects units that contain nested groups (explicit error, no fallback).
+// Groups made of ONE cluster (the bulk of any unit) run one thread per cluster in k_estimate_genotypes.  Groups
+// with nested clusters (VariantClusterGroup::runGibbsSample recursion, multicluster k-mers sharing a multiplicity
+// record) run one thread per GROUP in k_estimate_genotypes_nested, which walks the group's clusters in the
+// reference's depth-first order every iteration.  The joint noise mode still requires single-cluster groups.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -141,6 +143,7 @@ struct ClusterLayout {
 struct SlotLayout {
     uint64_t f64_off, u32_off, u8_off;  // element offsets of the slot in the three pools
     uint32_t H, K, nvar, n_uniq, n_alleles, Dall;  // per-lane capacities = max over the slot's clusters
+    uint32_t n_multi;                   // multicluster k-mers (0 for every slot of single-cluster groups)
 };
 template <class T> struct LaneArr {
     T *p;
@@ -172,12 +175,38 @@ struct DevUnit {
     uint32_t *u32_pool;
     uint8_t *u8_pool;
     const double *lgamma_int;
+    // nested groups / multicluster k-mers
+    uint32_t n_regular;          // order[0 .. n_regular): clusters of single-cluster groups
+    uint32_t n_nested_groups;
+    const uint32_t *nested_groups;
+    const uint32_t *k_shared;    // [rows] shared multiplicity record of a multicluster k-mer
+    const uint64_t *cl_multi_off;
+    const uint32_t *multi_idx;
+    const uint64_t *hap_start;   // [C+1] first haplotype of each cluster in hap_nested_off
+    const uint64_t *hap_nested_off;
+    const uint32_t *hap_nested;
+    const uint64_t *cl_dep_off;
+    const uint32_t *dep_cluster;
+    const uint64_t *dep_var_off;
+    const uint16_t *dep_var;
+    const uint64_t *group_src_off;
+    const uint32_t *group_src;
+    const uint64_t *cl_edge_off; // [C+1] out-edges of each cluster (CSR over clusters, targets = local indices)
+    const uint32_t *edge_dst;
+    uint32_t *src_mut, *edge_mut;        // branch orderings as shuffled so far (VariantClusterGroup::shuffleBranchOrdering)
+    uint32_t *dfs_order, *dfs_stack;     // [C] scratch of the group threads
+    uint8_t *shared_mult;                // [records][S] KmerCounts::multiplicities
+    const uint32_t *nest_slot;           // [C] index into the nested-info arrays, NONE for single-cluster groups
+    uint8_t *nest_pl, *nest_k;           // [slots][S] NestedVariantClusterInfo: nested_ploidy, number of nested_kmer_stats
+    uint32_t *nest_n;                    // [slots][S][2] KmerStats count
+    double *nest_f;                      // [slots][S][2][2] KmerStats (fraction, mean)
 };
 
 // arena sizes (elements) of one cluster — must match the pointer carving in Cl::bind
 constexpr uint32_t kSimplexTableMaxH = 32;
 struct ArenaSizes { uint64_t f64, u32, u8; };
-__host__ __device__ inline ArenaSizes arena_sizes(uint32_t S, uint32_t H, uint32_t K, uint32_t nvar, uint32_t n_uniq, uint32_t n_alleles, uint32_t Dall) {
+__host__ __device__ inline ArenaSizes arena_sizes(uint32_t S, uint32_t H, uint32_t K, uint32_t nvar, uint32_t n_uniq, uint32_t n_alleles, uint32_t Dall,
+                                                  uint32_t n_multi) {
     ArenaSizes a;
     a.f64 = (uint64_t)H * 2        /* freq, log(freq) */
           + (H + 1)                /* simplex prob vector (H > kSimplexTableMaxH: most recent key only) */
@@ -186,6 +215,7 @@ __host__ __device__ inline ArenaSizes arena_sizes(uint32_t S, uint32_t H, uint32
           + Dall                   /* cumulative log-probs of one draw */
           + (uint64_t)S * 2 * nvar * 2   /* k-mer stats cache (fraction, mean) */
           + (uint64_t)n_alleles * S * 3  /* allele k-mer stats: 3 sums (count, fraction, mean) */
+          + (n_multi ? (uint64_t)S * Dall : 0)  /* multicluster diplotype log-prob cache */
           + 2;                     /* sparsity, spare */
     a.u32 = (uint64_t)H            /* observation counts */
           + n_uniq * 2ull          /* unique k-mer order, subset */
@@ -194,24 +224,27 @@ __host__ __device__ inline ArenaSizes arena_sizes(uint32_t S, uint32_t H, uint32
           + (uint64_t)S * 2 * nvar /* k-mer stats cache counts */
           + (uint64_t)n_alleles * S * 3  /* allele stats counts */
           + S                      /* current diplotypes (first | second << 16) */
+          + n_multi * 2ull         /* multicluster k-mer order, subset */
           + 32;                    /* misc + rng states */
-    a.u8 = (uint64_t)H + K + S;    /* non-zero flags, uncovered rows, stats-cache update flags */
+    a.u8 = (uint64_t)H + K + S     /* non-zero flags, uncovered rows, stats-cache update flags */
+         + (uint64_t)n_multi * S;  /* sample_multicluster_kmer_multiplicities */
     a.u8 = (a.u8 + 7) & ~7ull;
     return a;
 }
 
-enum Misc { kNSub = 0, kNumHap = 1, kNumMissing = 2, kSimplexNobs = 3, kSimplexPlus = 4, kSimplexLen = 5, kSparse = 6, kCover = 7, kRng0 = 8, kRng1 = 16 };
+enum Misc { kNSub = 0, kNumHap = 1, kNumMissing = 2, kSimplexNobs = 3, kSimplexPlus = 4, kSimplexLen = 5, kSparse = 6, kCover = 7, kRng0 = 8, kRng1 = 16,
+            kNMultiSub = 24, kUseMulti = 25 };
 
 // per-cluster view
 struct Cl {
-    uint32_t S, H, K, nvar, n_uniq, Dall, n_alleles, c, g;
+    uint32_t S, H, K, nvar, n_uniq, Dall, n_alleles, c, g, n_multi;
     bool has_simplex_tab;
     uint64_t row0, var0;
     const DevUnit *u;
     const uint8_t *M;
-    LaneArr<double> freq, logf, simplex, simplex_tab, ucache, cum, kc_f, as_f, fmisc;
-    LaneArr<uint32_t> obs, uniq, uniq_sub, cnt, tally, kc_n, as_n, dipl, misc;
-    LaneArr<uint8_t> nz, uncovered, stats_update;
+    LaneArr<double> freq, logf, simplex, simplex_tab, ucache, cum, kc_f, as_f, mcache, fmisc;
+    LaneArr<uint32_t> obs, uniq, uniq_sub, cnt, tally, kc_n, as_n, dipl, multi, multi_sub, misc;
+    LaneArr<uint8_t> nz, uncovered, stats_update, sample_multi;
 
     __device__ void bind(const DevUnit &du, uint32_t cluster) {
         u = &du; c = cluster;
@@ -224,6 +257,7 @@ struct Cl {
         var0 = du.cl_var_off[c];
         nvar = (uint32_t)(du.cl_var_off[c + 1] - var0);
         n_uniq = (uint32_t)(du.cl_uniq_off[c + 1] - du.cl_uniq_off[c]);
+        n_multi = (uint32_t)(du.cl_multi_off[c + 1] - du.cl_multi_off[c]);
         Dall = L.Dall;
         n_alleles = L.n_alleles;
         M = du.mult + du.cl_mult_off[c];
@@ -239,6 +273,7 @@ struct Cl {
         cum = f; f = f + SL.Dall;
         kc_f = f; f = f + (uint64_t)S * 2 * SL.nvar * 2;
         as_f = f; f = f + (uint64_t)SL.n_alleles * S * 3;
+        mcache = f; f = f + (SL.n_multi ? (uint64_t)S * SL.Dall : 0);
         fmisc = f;
         LaneArr<uint32_t> w{du.u32_pool + SL.u32_off + lane};
         obs = w; w = w + SL.H;
@@ -249,11 +284,14 @@ struct Cl {
         kc_n = w; w = w + (uint64_t)S * 2 * SL.nvar;
         as_n = w; w = w + (uint64_t)SL.n_alleles * S * 3;
         dipl = w; w = w + S;
+        multi = w; w = w + SL.n_multi;
+        multi_sub = w; w = w + SL.n_multi;
         misc = w;
         LaneArr<uint8_t> b{du.u8_pool + SL.u8_off + lane};
         nz = b; b = b + SL.H;
         uncovered = b; b = b + SL.K;
-        stats_update = b;
+        stats_update = b; b = b + S;
+        sample_multi = b;
     }
     __device__ __forceinline__ uint8_t m(uint32_t k, uint32_t h) const { return M[(size_t)k * H + h]; }
     __device__ __forceinline__ uint8_t count(uint32_t k, uint32_t s) const { return u->k_has_counts[row0 + k] ? u->k_counts[(row0 + k) * S + s] : 0; }
@@ -271,6 +309,13 @@ struct Cl {
         if (a != NONE) r += m(k, a);
         if (b != NONE) r += m(k, b);
         return r;
+    }
+    // KmerCounts::getSampleMultiplicity of a multicluster k-mer (KmerCounts.cpp:205-224)
+    __device__ __forceinline__ uint8_t &sharedMult(uint32_t k, uint32_t s) const { return u->shared_mult[(size_t)u->k_shared[row0 + k] * S + s]; }
+    // VariantClusterHaplotypes::getMulticlusterKmerMultiplicity (VariantClusterHaplotypes.cpp:76-93); (pa, pb) = current diplotype
+    __device__ __forceinline__ uint8_t multiMult(uint32_t k, uint32_t a, uint32_t b, uint32_t pa, uint32_t pb, uint32_t s) const {
+        if (count(k, s) == 0) return (uint8_t)(diplMult(k, a, b) + ic(k, s));
+        return (uint8_t)(sharedMult(k, s) - diplMult(k, pa, pb) + diplMult(k, a, b) + ic(k, s));
     }
 };
 
@@ -309,6 +354,9 @@ __device__ void cl_construct(Cl &cl, const btg_gibbs_opts &o, uint64_t group_ind
     for (uint32_t i = 0; i < cl.n_alleles * S * 3; i++) { cl.as_n[i] = 0; cl.as_f[i] = 0; }
     for (int i = 0; i < 8; i++) cl.misc[i] = 0;
     cl.misc[kSimplexNobs] = 0xFFFFFFFFu;
+    cl.misc[kNMultiSub] = 0;
+    cl.misc[kUseMulti] = 0;
+    for (uint32_t i = 0; i < cl.n_multi; i++) cl.multi[i] = cl.u->multi_idx[cl.u->cl_multi_off[cl.c] + i];
     // SparsityEstimator::estimateMinimumColumnCover (SparsityEstimator.cpp:41-90), stream kind 1
     Philox sp;
     sp.init(o.random_seed, group_index, cl.u->cluster_idx[cl.c], kRngSparsity, chain);
@@ -356,6 +404,7 @@ __device__ bool cl_is_max_hap_var_kmer(Cl &cl, uint32_t k, uint32_t max_kmers) {
 }
 
 // VariantClusterGenotyper::reset + VariantClusterHaplotypes::sampleKmerSubset (…Genotyper.cpp:113-129, …Haplotypes.cpp:110-157)
+template <bool MC = false>
 __device__ void cl_reset(Cl &cl, const btg_gibbs_opts &o, Philox &prng) {
     const double rate = (double)o.kmer_subsampling_rate;
     for (uint32_t i = 0; i < cl.H * cl.nvar; i++) cl.cnt[i] = 0;
@@ -373,10 +422,75 @@ __device__ void cl_reset(Cl &cl, const btg_gibbs_opts &o, Philox &prng) {
     for (uint32_t s = 0; s < cl.S; s++) cl.stats_update[s] = 1;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     for (uint32_t i = 0; i < cl.S * cl.Dall; i++) cl.ucache[i] = nan;  // clear the per-sample diplotype caches
+    if constexpr (MC) {
+        if (cl.n_multi) {
+            for (uint32_t i = cl.n_multi; i > 1; i--) {
+                const uint32_t j = prng.uniform_int(i);
+                const uint32_t t = cl.multi[i - 1]; cl.multi[i - 1] = cl.multi[j]; cl.multi[j] = t;
+            }
+            uint32_t n_msub = 0;
+            for (uint32_t i = 0; i < cl.n_multi; i++) {
+                const uint32_t k = cl.multi[i];
+                if (prng.u01() < rate)
+                    if (!cl_is_max_hap_var_kmer(cl, k, o.max_haplotype_variant_kmers)) cl.multi_sub[n_msub++] = k;
+            }
+            cl.misc[kNMultiSub] = n_msub;
+            for (uint32_t i = 0; i < n_msub * cl.S; i++) cl.sample_multi[i] = 0;
+            for (uint32_t i = 0; i < cl.S * cl.Dall; i++) cl.mcache[i] = nan;
+        }
+        cl.misc[kUseMulti] = 0;
+    }
     cl_reset_frequencies(cl);
 }
 
+// VariantClusterGenotyper::updateMulticlusterDiplotypeLogProb (…Genotyper.cpp:569-595): cached terms of the k-mers whose
+// shared multiplicity another cluster of the group has changed are replaced in place (NaN = diplotype not cached)
+__device__ void cl_update_multi_log_prob(Cl &cl, const Tables &T, uint32_t s) {
+    const uint32_t n_msub = cl.misc[kNMultiSub], H = cl.H;
+    const uint32_t pa = cl.dipl[s] & 0xFFFFu, pb = cl.dipl[s] >> 16;
+    for (uint32_t sub = 0; sub < n_msub; sub++) {
+        const uint32_t k = cl.multi_sub[sub];
+        const uint8_t cnt = cl.count(k, s);
+        const uint8_t seen = cl.sample_multi[sub * cl.S + s];
+        if (!(cnt > 0 && cl.sharedMult(k, s) != seen)) continue;  // isMulticlusterKmerUpdated (…Haplotypes.cpp:180-195)
+        const uint8_t base_prev = (uint8_t)(seen - cl.diplMult(k, pa, pb) + cl.ic(k, s));
+        for (uint32_t b = 0; b <= H; b++) {
+            for (uint32_t a = 0; a <= b && a < H; a++) {
+                const size_t ci = (size_t)s * cl.Dall + cl.slot(a, b);
+                double v = cl.mcache[ci];
+                if (v != v) continue;
+                const uint32_t bb = b == H ? NONE : b;
+                v -= T.logProb(s, (uint8_t)(base_prev + cl.diplMult(k, a, bb)), cnt);  // getPreviousMulticlusterKmerMultiplicity
+                v += T.logProb(s, cl.multiMult(k, a, bb, pa, pb, s), cnt);
+                cl.mcache[ci] = v;
+            }
+        }
+    }
+}
+
+// VariantClusterHaplotypes::updateMulticlusterKmerMultiplicities (VariantClusterHaplotypes.cpp:197-233)
+__device__ void cl_update_multi_multiplicities(Cl &cl, uint32_t s, uint32_t prev) {
+    const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
+    if (cl.dipl[s] != prev) {
+        cl.stats_update[s] = 1;
+        const uint32_t pa = prev & 0xFFFFu, pb = prev >> 16;
+        for (uint32_t i = 0; i < cl.n_multi; i++) {
+            const uint32_t k = cl.multi[i];
+            const uint8_t cur = cl.diplMult(k, da, db), old = cl.diplMult(k, pa, pb);
+            if (cur != old) { uint8_t &m = cl.sharedMult(k, s); m = (uint8_t)(m - old + cur); }
+        }
+    }
+    const uint32_t n_msub = cl.misc[kNMultiSub];
+    for (uint32_t sub = 0; sub < n_msub; sub++) {
+        const uint32_t k = cl.multi_sub[sub];
+        const uint8_t m = cl.sharedMult(k, s);
+        if (cl.diplMult(k, da, db) > 0 && cl.count(k, s) > 0 && m != cl.sample_multi[sub * cl.S + s]) cl.stats_update[s] = 1;
+        cl.sample_multi[sub * cl.S + s] = m;
+    }
+}
+
 // VariantClusterGenotyper::calcDiplotypeLogProb (VariantClusterGenotyper.cpp:597-666)
+template <bool MC = false>
 __device__ double cl_dipl_log_prob(Cl &cl, const Tables &T, uint32_t s, uint32_t a, uint32_t b) {
     double lp = 0;  // logf[] = log(freq[]) of this iteration (cl_sample_diplotypes)
     if (b == NONE) lp += cl.logf[a];
@@ -393,7 +507,23 @@ __device__ double cl_dipl_log_prob(Cl &cl, const Tables &T, uint32_t s, uint32_t
         }
         cl.ucache[ci] = acc;
     }
-    return lp + acc;
+    lp += acc;
+    if constexpr (MC) {
+        if (cl.misc[kUseMulti]) {
+            double macc = cl.mcache[ci];
+            if (macc != macc) {
+                macc = 0;
+                const uint32_t n_msub = cl.misc[kNMultiSub], pa = cl.dipl[s] & 0xFFFFu, pb = cl.dipl[s] >> 16;
+                for (uint32_t i = 0; i < n_msub; i++) {
+                    const uint32_t k = cl.multi_sub[i];
+                    macc += T.logProb(s, cl.multiMult(k, a, b, pa, pb, s), cl.count(k, s));
+                }
+                cl.mcache[ci] = macc;
+            }
+            lp += macc;
+        }
+    }
+    return lp;
 }
 
 __device__ __forceinline__ void cl_increment(Cl &cl, uint32_t h) {  // HaplotypeFrequencyDistribution.cpp:114-126
@@ -403,6 +533,7 @@ __device__ __forceinline__ void cl_increment(Cl &cl, uint32_t h) {  // Haplotype
 }
 
 // VariantClusterGenotyper::sampleDiplotype (VariantClusterGenotyper.cpp:707-755) + LogDiscreteSampler (DiscreteSampler.cpp:106-126)
+template <bool MC = false>
 __device__ void cl_sample_diplotype(Cl &cl, const Tables &T, uint32_t s, uint8_t ploidy, Philox &prng) {
     uint32_t n = 0;
     double run = 0;
@@ -412,7 +543,7 @@ __device__ void cl_sample_diplotype(Cl &cl, const Tables &T, uint32_t s, uint8_t
             if (!cl.nz[a]) continue;
             for (uint32_t b = a; b < H; b++) {
                 if (!cl.nz[b]) continue;
-                const double lp = cl_dipl_log_prob(cl, T, s, a, b);
+                const double lp = cl_dipl_log_prob<MC>(cl, T, s, a, b);
                 run = n == 0 ? lp : logAddition(lp, run);
                 cl.cum[n++] = run;
             }
@@ -420,7 +551,7 @@ __device__ void cl_sample_diplotype(Cl &cl, const Tables &T, uint32_t s, uint8_t
     } else if (ploidy == 1) {
         for (uint32_t a = 0; a < H; a++) {
             if (!cl.nz[a]) continue;
-            const double lp = cl_dipl_log_prob(cl, T, s, a, NONE);
+            const double lp = cl_dipl_log_prob<MC>(cl, T, s, a, NONE);
             run = n == 0 ? lp : logAddition(lp, run);
             cl.cum[n++] = run;
         }
@@ -474,8 +605,20 @@ __device__ void cl_add_haplotype_stats(Cl &cl, uint32_t s, uint32_t which, uint3
     }
 }
 
-__device__ void cl_update_allele_stats(Cl &cl) {
+// updateKmerStatsCache (…Haplotypes.cpp:302-333)
+__device__ __forceinline__ void cl_stats_cache_add(Cl &cl, uint32_t k, uint32_t s, uint32_t da, uint32_t db, uint8_t mult) {
     const DevUnit &u = *cl.u;
+    const double kc = u.k_has_counts[cl.row0 + k] ? cl.count(k, s) / static_cast<double>(mult) : 0.0;
+    for (uint64_t e = u.kmer_vh_off[cl.row0 + k]; e < u.kmer_vh_off[cl.row0 + k + 1]; e++) {
+        const uint32_t v = u.vh_var[e];
+        const uint8_t *bits = u.vh_bits + u.vh_bits_off[e];
+        if (bits[da]) { const uint32_t ci = (s * 2 + 0) * cl.nvar + v; kc_add(cl.kc_n[ci], cl.kc_f[2 * ci], cl.kc_f[2 * ci + 1], kc); }
+        if (db != NONE && bits[db]) { const uint32_t ci = (s * 2 + 1) * cl.nvar + v; kc_add(cl.kc_n[ci], cl.kc_f[2 * ci], cl.kc_f[2 * ci + 1], kc); }
+    }
+}
+
+template <bool MC = false>
+__device__ void cl_update_allele_stats(Cl &cl) {
     for (uint32_t s = 0; s < cl.S; s++) {
         const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
         if (cl.stats_update[s]) {
@@ -487,14 +630,14 @@ __device__ void cl_update_allele_stats(Cl &cl) {
                     const uint32_t k = cl.uniq_sub[i];
                     const uint8_t dm = cl.diplMult(k, da, db);
                     if (dm == 0) continue;
-                    const uint8_t mult = (uint8_t)(dm + cl.ic(k, s));
-                    // updateKmerStatsCache (…Haplotypes.cpp:302-333)
-                    const double kc = u.k_has_counts[cl.row0 + k] ? cl.count(k, s) / static_cast<double>(mult) : 0.0;
-                    for (uint64_t e = u.kmer_vh_off[cl.row0 + k]; e < u.kmer_vh_off[cl.row0 + k + 1]; e++) {
-                        const uint32_t v = u.vh_var[e];
-                        const uint8_t *bits = u.vh_bits + u.vh_bits_off[e];
-                        if (bits[da]) { const uint32_t ci = (s * 2 + 0) * cl.nvar + v; kc_add(cl.kc_n[ci], cl.kc_f[2 * ci], cl.kc_f[2 * ci + 1], kc); }
-                        if (db != NONE && bits[db]) { const uint32_t ci = (s * 2 + 1) * cl.nvar + v; kc_add(cl.kc_n[ci], cl.kc_f[2 * ci], cl.kc_f[2 * ci + 1], kc); }
+                    cl_stats_cache_add(cl, k, s, da, db, (uint8_t)(dm + cl.ic(k, s)));
+                }
+                if constexpr (MC) {
+                    const uint32_t n_msub = cl.misc[kNMultiSub];
+                    for (uint32_t i = 0; i < n_msub; i++) {
+                        const uint32_t k = cl.multi_sub[i];
+                        if (cl.diplMult(k, da, db) == 0) continue;
+                        cl_stats_cache_add(cl, k, s, da, db, cl.multiMult(k, da, db, da, db, s));
                     }
                 }
             }
@@ -510,18 +653,22 @@ __device__ void cl_update_allele_stats(Cl &cl) {
 }
 
 // VariantClusterGenotyper::sampleDiplotypes (VariantClusterGenotyper.cpp:668-705)
+template <bool MC = false>
 __device__ void cl_sample_diplotypes(Cl &cl, const Tables &T, const uint8_t *ploidy, bool collect, Philox &prng) {
     for (uint32_t h = 0; h < cl.H; h++) if (cl.nz[h]) cl.logf[h] = log(cl.freq[h]);  // one log per haplotype per iteration
     for (uint32_t s = 0; s < cl.S; s++) {
         const uint32_t prev = cl.dipl[s];
-        cl_sample_diplotype(cl, T, s, ploidy[s], prng);
-        if (cl.dipl[s] != prev) cl.stats_update[s] = 1;  // …Haplotypes.cpp:199-201
+        if constexpr (MC) { if (cl.misc[kUseMulti]) cl_update_multi_log_prob(cl, T, s); }
+        cl_sample_diplotype<MC>(cl, T, s, ploidy[s], prng);
+        if constexpr (MC) cl_update_multi_multiplicities(cl, s, prev);
+        else if (cl.dipl[s] != prev) cl.stats_update[s] = 1;  // …Haplotypes.cpp:199-201
         if (collect) {
             const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
             cl.tally[(size_t)cl.slot(da == NONE ? cl.H : da, db == NONE ? cl.H : db) * cl.S + s]++;
         }
     }
-    if (collect) cl_update_allele_stats(cl);
+    if (collect) cl_update_allele_stats<MC>(cl);
+    if constexpr (MC) cl.misc[kUseMulti] = cl.misc[kNMultiSub] > 0;
 }
 
 // SparseFrequencyDistribution::updateCachedSimplexProbVector (FrequencyDistribution.cpp:143-196);
@@ -716,7 +863,7 @@ __device__ void cl_summarise(Cl &cl, const btg_gibbs_opts &o, const uint8_t *plo
 template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(64, MIN_BLOCKS) k_estimate_genotypes(DevUnit du, Tables T, btg_gibbs_opts o, ResultView R) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= du.C) return;
+    if (i >= du.n_regular) return;
     Cl cl;
     cl.bind(du, du.order[i]);
     const uint64_t gidx = o.group_index_base + cl.g;
@@ -734,6 +881,162 @@ __global__ void __launch_bounds__(64, MIN_BLOCKS) k_estimate_genotypes(DevUnit d
         }
     }
     cl_summarise(cl, o, ploidy, R);
+}
+
+
+// ---- groups with nested clusters ------------------------------------------------------------------
+// VariantClusterGenotyper::updateNestedVariantClusterInfo / updateNestedPloidy / addNestedKmerStats (…Genotyper.cpp:140-206):
+// `cl` is the parent that has just been sampled; the child's incoming info (slot nt) already holds a copy of the parent's own
+__device__ void cl_update_nested_info(Cl &cl, uint32_t nt, uint32_t child_cluster_idx) {
+    const DevUnit &u = *cl.u;
+    uint64_t dep = u.cl_dep_off[cl.c];
+    while (dep < u.cl_dep_off[cl.c + 1] && u.dep_cluster[dep] != child_cluster_idx) dep++;
+    for (uint32_t s = 0; s < cl.S; s++) {
+        for (uint32_t which = 0; which < 2; which++) {
+            const uint32_t h = which == 0 ? (cl.dipl[s] & 0xFFFFu) : (cl.dipl[s] >> 16);
+            if (h == NONE) continue;
+            bool contains = false;  // haplotype runs through the child cluster's position
+            for (uint64_t e = u.hap_nested_off[u.hap_start[cl.c] + h]; e < u.hap_nested_off[u.hap_start[cl.c] + h + 1]; e++)
+                if (u.hap_nested[e] == child_cluster_idx) { contains = true; break; }
+            if (contains) continue;
+            uint8_t &pl = u.nest_pl[(size_t)nt * cl.S + s];
+            pl = pl == 2 ? 1 : 0;
+            uint32_t v = NONE;
+            if (dep < u.cl_dep_off[cl.c + 1])
+                for (uint64_t e = u.dep_var_off[dep]; e < u.dep_var_off[dep + 1]; e++) {
+                    const uint32_t nv = u.dep_var[e];
+                    if (!cl.isMissing(nv, cl.hapAllele(h, nv))) { v = nv; break; }
+                }
+            uint8_t &k = u.nest_k[(size_t)nt * cl.S + s];
+            if (v == NONE || k >= 2) continue;  // the reference asserts both
+            const uint32_t ci = (s * 2 + which) * cl.nvar + v;
+            const size_t o = ((size_t)nt * cl.S + s) * 2 + k;
+            u.nest_n[o] = cl.kc_n[ci];
+            u.nest_f[2 * o] = cl.kc_f[2 * ci];
+            u.nest_f[2 * o + 1] = cl.kc_f[2 * ci + 1];
+            k++;
+        }
+    }
+}
+
+// VariantClusterHaplotypes::addNestedHaplotypeKmerStats (VariantClusterHaplotypes.cpp:363-372): the k-mer stats of the enclosing
+// allele(s) are booked on the "missing" allele of every variant of this cluster
+__device__ void cl_add_nested_stats(Cl &cl, uint32_t ns) {
+    const DevUnit &u = *cl.u;
+    for (uint32_t s = 0; s < cl.S; s++) {
+        const uint32_t nk = u.nest_k[(size_t)ns * cl.S + s];
+        for (uint32_t k = 0; k < nk; k++) {
+            const size_t o = ((size_t)ns * cl.S + s) * 2 + k;
+            const uint32_t n = u.nest_n[o];
+            for (uint32_t v = 0; v < cl.nvar; v++) {
+                const uint32_t ai = cl.alleleBase(v, s) + cl.nalleles(v) - 1;
+                cl.as_n[ai * 3 + 0]++; cl.as_f[ai * 3 + 0] += (double)n;
+                if (n > 0) {
+                    cl.as_n[ai * 3 + 1]++; cl.as_f[ai * 3 + 1] += u.nest_f[2 * o];
+                    cl.as_n[ai * 3 + 2]++; cl.as_f[ai * 3 + 2] += u.nest_f[2 * o + 1];
+                }
+            }
+        }
+    }
+}
+
+// InferenceEngine::estimateGenotypesCallback for a group with several clusters: one thread = one GROUP.  Per chain the branch
+// orderings are shuffled (cumulatively, VariantClusterGroup.cpp:208-218) and flattened into the depth-first order that
+// runGibbsSample's recursion (…Group.cpp:236-250) visits; every iteration walks that order, each cluster passing the
+// NestedVariantClusterInfo of its children on before they run.
+__global__ void __launch_bounds__(64) k_estimate_genotypes_nested(DevUnit du, Tables T, btg_gibbs_opts o, ResultView R) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= du.n_nested_groups) return;
+    const uint32_t g = du.nested_groups[i], S = du.S;
+    const uint64_t c0 = du.group_cluster_off[g];
+    const uint32_t n = (uint32_t)(du.group_cluster_off[g + 1] - c0);
+    const uint64_t gidx = o.group_index_base + g;
+    const uint8_t *ploidy = du.group_ploidy + (size_t)g * S;
+    const uint64_t s0 = du.group_src_off[g], s1 = du.group_src_off[g + 1];
+    const uint64_t e0 = du.cl_edge_off[c0], e1 = du.cl_edge_off[c0 + n];
+    for (uint64_t e = s0; e < s1; e++) du.src_mut[e] = du.group_src[e];
+    for (uint64_t e = e0; e < e1; e++) du.edge_mut[e] = du.edge_dst[e];
+    Cl cl;
+    for (uint32_t j = 0; j < n; j++) {  // VariantClusterGroup::initGenotyper: genotypers are constructed once
+        cl.bind(du, (uint32_t)(c0 + j));
+        cl_construct(cl, o, gidx, 0);
+        Philox prng, fr;
+        prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, 0);
+        fr.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngFrequency, 0);
+        prng.save(cl.misc, kRng0);
+        fr.save(cl.misc, kRng1);
+    }
+    const uint32_t iters = (uint32_t)o.gibbs_burn_in + o.gibbs_samples;
+    for (uint32_t chain = 0; chain < o.n_chains; chain++) {
+        for (uint32_t j = 0; j < n; j++) {
+            cl.bind(du, (uint32_t)(c0 + j));
+            Philox prng;
+            prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+            cl_reset<true>(cl, o, prng);
+            prng.save(cl.misc, kRng0);
+        }
+        {   // shuffleBranchOrdering: sources, then every vertex's out-edges in vertex order (stream kind 3)
+            Philox br;
+            br.init(o.random_seed, gidx, 0, kRngBranch, chain);
+            for (uint64_t m = s1 - s0; m > 1; m--) {
+                const uint32_t j = br.uniform_int((uint32_t)m);
+                const uint32_t t = du.src_mut[s0 + m - 1]; du.src_mut[s0 + m - 1] = du.src_mut[s0 + j]; du.src_mut[s0 + j] = t;
+            }
+            for (uint32_t v = 0; v < n; v++) {
+                const uint64_t b0 = du.cl_edge_off[c0 + v];
+                for (uint64_t m = du.cl_edge_off[c0 + v + 1] - b0; m > 1; m--) {
+                    const uint32_t j = br.uniform_int((uint32_t)m);
+                    const uint32_t t = du.edge_mut[b0 + m - 1]; du.edge_mut[b0 + m - 1] = du.edge_mut[b0 + j]; du.edge_mut[b0 + j] = t;
+                }
+            }
+        }
+        {   // depth-first pre-order of the forest
+            uint32_t top = 0, len = 0;
+            for (uint64_t e = s1; e > s0; e--) du.dfs_stack[c0 + top++] = du.src_mut[e - 1];
+            while (top > 0) {
+                const uint32_t v = du.dfs_stack[c0 + --top];
+                du.dfs_order[c0 + len++] = v;
+                for (uint64_t e = du.cl_edge_off[c0 + v + 1]; e > du.cl_edge_off[c0 + v]; e--) du.dfs_stack[c0 + top++] = du.edge_mut[e - 1];
+            }
+        }
+        for (uint64_t e = s0; e < s1; e++) {  // the info a source vertex receives: the chromosome ploidy, no enclosing allele
+            const uint32_t ns = du.nest_slot[c0 + du.src_mut[e]];
+            for (uint32_t s = 0; s < S; s++) { du.nest_pl[(size_t)ns * S + s] = ploidy[s]; du.nest_k[(size_t)ns * S + s] = 0; }
+        }
+        for (uint32_t it = 0; it < iters; it++) {
+            const bool collect = it >= o.gibbs_burn_in;
+            for (uint32_t pos = 0; pos < n; pos++) {
+                const uint32_t v = du.dfs_order[c0 + pos];
+                cl.bind(du, (uint32_t)(c0 + v));
+                const uint32_t ns = du.nest_slot[c0 + v];
+                Philox prng, fr;
+                prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+                fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
+                cl_sample_diplotypes<true>(cl, T, du.nest_pl + (size_t)ns * S, collect, prng);
+                if (collect) cl_add_nested_stats(cl, ns);
+                cl_sample_frequencies(cl, fr);
+                prng.save(cl.misc, kRng0);
+                fr.save(cl.misc, kRng1);
+                for (uint64_t e = du.cl_edge_off[c0 + v]; e < du.cl_edge_off[c0 + v + 1]; e++) {
+                    const uint32_t t = du.edge_mut[e], nt = du.nest_slot[c0 + t];
+                    for (uint32_t s = 0; s < S; s++) {
+                        du.nest_pl[(size_t)nt * S + s] = du.nest_pl[(size_t)ns * S + s];
+                        const uint32_t nk = du.nest_k[(size_t)ns * S + s];
+                        du.nest_k[(size_t)nt * S + s] = (uint8_t)nk;
+                        for (uint32_t k = 0; k < nk; k++) {
+                            const size_t a = ((size_t)ns * S + s) * 2 + k, b = ((size_t)nt * S + s) * 2 + k;
+                            du.nest_n[b] = du.nest_n[a]; du.nest_f[2 * b] = du.nest_f[2 * a]; du.nest_f[2 * b + 1] = du.nest_f[2 * a + 1];
+                        }
+                    }
+                    cl_update_nested_info(cl, nt, du.cluster_idx[c0 + t]);
+                }
+            }
+        }
+    }
+    for (uint32_t j = 0; j < n; j++) {  // collectGenotypes: every cluster is summarised with the chromosome ploidy
+        cl.bind(du, (uint32_t)(c0 + j));
+        cl_summarise(cl, o, ploidy, R);
+    }
 }
 
 // VariantClusterGroup::collectGenotypes for every cluster (joint mode collects after all chains)
@@ -947,7 +1250,7 @@ struct btg_unit {
     std::vector<ClusterLayout> h_layout;
     std::vector<SlotLayout> h_slots;
     std::vector<uint32_t> h_fill_cost;  // table lookups of one full cache fill: S * D * n_uniq / 10
-    uint64_t n_variants = 0, n_alleles_total = 0;
+    uint64_t n_variants = 0, n_alleles_total = 0, n_shared = 0;
     uint32_t max_h = 0;
 };
 
@@ -1030,12 +1333,6 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
     if (!ctx().ready) { set_error("btg_init() has not been called"); return nullptr; }
     if (!d || d->n_samples == 0 || d->n_samples > BTG_MAX_SAMPLES) { set_error("bad unit descriptor"); return nullptr; }
     const uint32_t S = d->n_samples, G = d->n_groups, C = d->n_clusters;
-    for (uint32_t g = 0; g < G; g++)
-        if (d->group_cluster_off[g + 1] - d->group_cluster_off[g] != 1) {
-            set_error("group %u has %llu clusters: nested variant-cluster groups are not supported by this build", g,
-                      (unsigned long long)(d->group_cluster_off[g + 1] - d->group_cluster_off[g]));
-            return nullptr;
-        }
     auto *u = new btg_unit();
     bool ok = true;
     auto keep = [&](auto *p) { u->allocs.push_back((void *)p); return p; };
@@ -1064,6 +1361,81 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
     du.hap_alleles = keep(upload(d->hap_alleles, d->cl_hapvar_off[C], ok));
     du.var_nalleles = keep(upload(d->var_nalleles, nvar, ok));
     du.var_dep = keep(upload(d->var_dep, nvar, ok));
+    // nested groups and multicluster k-mers
+    {
+        const uint64_t n_multi = d->cl_multi_off[C];
+        uint64_t n_hap = 0, n_shared = 0;
+        std::vector<uint64_t> hap_start(C + 1, 0);
+        for (uint32_t c = 0; c < C; c++) hap_start[c + 1] = hap_start[c] + d->cl_nhap[c];
+        n_hap = hap_start[C];
+        for (uint32_t c = 0; c < C && ok; c++)
+            for (uint64_t i = d->cl_multi_off[c]; i < d->cl_multi_off[c + 1]; i++) {
+                const uint64_t r = d->cl_kmer_off[c] + d->multi_idx[i];
+                if (d->k_shared[r] == 0xFFFFFFFFu || !d->k_has_counts[r]) { set_error("cluster %u: multicluster k-mer row %llu has no shared count record (k_shared)", c, (unsigned long long)r); ok = false; break; }
+                n_shared = std::max<uint64_t>(n_shared, (uint64_t)d->k_shared[r] + 1);
+            }
+        du.k_shared = keep(upload(d->k_shared, rows, ok));
+        du.cl_multi_off = keep(upload(d->cl_multi_off, C + 1, ok));
+        du.multi_idx = keep(upload(d->multi_idx, n_multi, ok));
+        du.hap_start = keep(upload(hap_start.data(), C + 1, ok));
+        du.hap_nested_off = keep(upload(d->hap_nested_off, n_hap + 1, ok));
+        du.hap_nested = keep(upload(d->hap_nested, d->hap_nested_off[n_hap], ok));
+        du.cl_dep_off = keep(upload(d->cl_dep_off, C + 1, ok));
+        const uint64_t n_dep = d->cl_dep_off[C];
+        du.dep_cluster = keep(upload(d->dep_cluster, n_dep, ok));
+        du.dep_var_off = keep(upload(d->dep_var_off, n_dep + 1, ok));
+        du.dep_var = keep(upload(d->dep_var, d->dep_var_off[n_dep], ok));
+        du.group_src_off = keep(upload(d->group_src_off, G + 1, ok));
+        du.group_src = keep(upload(d->group_src, d->group_src_off[G], ok));
+        // out-edges as a CSR over clusters, each vertex's targets in the order given (VariantClusterGroup.cpp:94-104)
+        std::vector<uint64_t> cl_edge_off(C + 1, 0);
+        const uint64_t n_edges = d->group_edge_off[G];
+        std::vector<uint32_t> edge_dst(n_edges);
+        std::vector<uint32_t> nested_groups, nest_slot(C, 0xFFFFFFFFu);
+        uint32_t n_nest = 0;
+        for (uint32_t g = 0; g < G && ok; g++) {
+            const uint64_t c0 = d->group_cluster_off[g], n = d->group_cluster_off[g + 1] - c0;
+            if (n == 0) { set_error("group %u has no cluster", g); ok = false; break; }
+            for (uint64_t e = d->group_edge_off[g]; e < d->group_edge_off[g + 1]; e++) {
+                if (d->group_edge_src[e] >= n || d->group_edge_dst[e] >= n) { set_error("group %u: edge %llu out of range", g, (unsigned long long)e); ok = false; break; }
+                cl_edge_off[c0 + d->group_edge_src[e] + 1]++;
+            }
+            for (uint64_t e = d->group_src_off[g]; e < d->group_src_off[g + 1]; e++)
+                if (d->group_src[e] >= n) { set_error("group %u: source vertex out of range", g); ok = false; break; }
+            if (n > 1) {
+                nested_groups.push_back(g);
+                for (uint64_t c = c0; c < c0 + n; c++) nest_slot[c] = n_nest++;
+                if (d->group_edge_off[g + 1] - d->group_edge_off[g] + (d->group_src_off[g + 1] - d->group_src_off[g]) != n) {
+                    set_error("group %u: %llu clusters need a forest of %llu sources + edges", g, (unsigned long long)n, (unsigned long long)n); ok = false; break;
+                }
+            }
+        }
+        for (uint32_t c = 0; c < C; c++) cl_edge_off[c + 1] += cl_edge_off[c];
+        if (ok) {
+            std::vector<uint64_t> fill(cl_edge_off.begin(), cl_edge_off.end() - 1);
+            for (uint32_t g = 0; g < G; g++) {
+                const uint64_t c0 = d->group_cluster_off[g];
+                for (uint64_t e = d->group_edge_off[g]; e < d->group_edge_off[g + 1]; e++) edge_dst[fill[c0 + d->group_edge_src[e]]++] = d->group_edge_dst[e];
+            }
+        }
+        du.cl_edge_off = keep(upload(cl_edge_off.data(), C + 1, ok));
+        du.edge_dst = keep(upload(edge_dst.data(), n_edges, ok));
+        du.nested_groups = keep(upload(nested_groups.data(), nested_groups.size(), ok));
+        du.n_nested_groups = (uint32_t)nested_groups.size();
+        du.nest_slot = keep(upload(nest_slot.data(), C, ok));
+        auto dmalloc = [&](auto *&dst, size_t n) {
+            void *p = nullptr;
+            if (cudaMalloc(&p, (n ? n : 1) * sizeof(*dst)) != cudaSuccess) { ok = false; dst = nullptr; return; }
+            u->allocs.push_back(p);
+            dst = static_cast<std::remove_reference_t<decltype(dst)>>(p);
+        };
+        dmalloc(du.src_mut, d->group_src_off[G]); dmalloc(du.edge_mut, n_edges);
+        dmalloc(du.dfs_order, nested_groups.empty() ? 0 : C); dmalloc(du.dfs_stack, nested_groups.empty() ? 0 : C);
+        dmalloc(du.shared_mult, n_shared * S);
+        dmalloc(du.nest_pl, (size_t)n_nest * S); dmalloc(du.nest_k, (size_t)n_nest * S);
+        dmalloc(du.nest_n, (size_t)n_nest * S * 2); dmalloc(du.nest_f, (size_t)n_nest * S * 4);
+        u->n_shared = n_shared;
+    }
     // result offsets
     u->n_variants = nvar;
     u->h_valt_off.assign(nvar + 1, 0);
@@ -1083,7 +1455,7 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
     u->h_nhap.assign(d->cl_nhap, d->cl_nhap + C);
     u->h_group_cluster_off.assign(d->group_cluster_off, d->group_cluster_off + G + 1);
     u->h_cl_var_off.assign(d->cl_var_off, d->cl_var_off + C + 1);
-    struct Dims { uint32_t H, K, nv, nu, nal, Dall; };
+    struct Dims { uint32_t H, K, nv, nu, nal, Dall, nm; };
     std::vector<Dims> dims(C);
     std::vector<uint64_t> cost(C);
     for (uint32_t g = 0; g < G; g++) {
@@ -1098,7 +1470,8 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
             L.group = g;
             L.n_alleles = nal;
             L.Dall = (H + 1) * (H + 2) / 2;
-            dims[c] = Dims{H, K, nv, nu, nal, L.Dall};
+            const uint32_t nm = (uint32_t)(d->cl_multi_off[c + 1] - d->cl_multi_off[c]);
+            dims[c] = Dims{H, K, nv, nu, nal, L.Dall, nm};
             u->h_fill_cost[c] = (uint32_t)std::min<uint64_t>(0xFFFFFFFFu, (uint64_t)S * ((uint64_t)H * (H + 1) / 2) * (nu / 10 + 1));
             cost[c] = (uint64_t)S * ((uint64_t)H * (H + 1) / 2) * 8 + nu + (uint64_t)H * K / 16;
             u->max_h = std::max(u->max_h, H);
@@ -1106,7 +1479,14 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
     }
     std::vector<uint32_t> order(C);
     std::iota(order.begin(), order.end(), 0u);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
+    // clusters of single-cluster groups first (one thread each), then the clusters of nested groups (one thread per group)
+    auto is_nested = [&](uint32_t c) { const uint32_t g = u->h_layout[c].group; return d->group_cluster_off[g + 1] - d->group_cluster_off[g] > 1; };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        const bool na = is_nested(a), nb = is_nested(b);
+        return na != nb ? nb : cost[a] > cost[b];
+    });
+    du.n_regular = 0;
+    while (du.n_regular < C && !is_nested(order[du.n_regular])) du.n_regular++;
     // one arena slot per warp of the cost order, sized by the largest cluster in it
     const uint32_t n_slots = (C + 31) / 32;
     u->h_slots.assign(n_slots ? n_slots : 1, SlotLayout{});
@@ -1118,8 +1498,9 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
             u->h_layout[order[i]].pos = i;
             SL.H = std::max(SL.H, D.H); SL.K = std::max(SL.K, D.K); SL.nvar = std::max(SL.nvar, D.nv);
             SL.n_uniq = std::max(SL.n_uniq, D.nu); SL.n_alleles = std::max(SL.n_alleles, D.nal); SL.Dall = std::max(SL.Dall, D.Dall);
+            SL.n_multi = std::max(SL.n_multi, D.nm);
         }
-        const ArenaSizes a = arena_sizes(S, SL.H, SL.K, SL.nvar, SL.n_uniq, SL.n_alleles, SL.Dall);
+        const ArenaSizes a = arena_sizes(S, SL.H, SL.K, SL.nvar, SL.n_uniq, SL.n_alleles, SL.Dall, SL.n_multi);
         SL.f64_off = f64_total; SL.u32_off = u32_total; SL.u8_off = u8_total;
         f64_total += a.f64 * 32; u32_total += a.u32 * 32; u8_total += a.u8 * 32;
     }
@@ -1200,9 +1581,16 @@ int btg_estimate_genotypes_async(btg_unit *u, const btg_count_dist *cd, const bt
     DevResult *dr = unit_result(u);
     if (!dr) { set_error("result allocation failed"); return BTG_ENOMEM; }
     Tables T{cd->genomic, cd->noise};
-    if (u->du.C) {
+    if (u->du.n_nested_groups) {
+        // KmerCounts::multiplicities start at zero in a fresh run (KmerCounts.hpp:100)
+        BTG_CUDA(cudaMemsetAsync(u->du.shared_mult, 0, (size_t)u->n_shared * u->du.S, pick_stream(stream)));
+        k_estimate_genotypes_nested<<<(u->du.n_nested_groups + 63) / 64, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R);
+        BTG_LAUNCHED();
+        BTG_CUDA(cudaGetLastError());
+    }
+    if (u->du.n_regular) {
         static const int occ = getenv("BTG_GIBBS_OCC") ? atoi(getenv("BTG_GIBBS_OCC")) : 8;
-        const unsigned grid = (u->du.C + 63) / 64;
+        const unsigned grid = (u->du.n_regular + 63) / 64;
         if (occ >= 16) k_estimate_genotypes<16><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R);
         else if (occ >= 12) k_estimate_genotypes<12><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R);
         else k_estimate_genotypes<8><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R);
@@ -1284,6 +1672,7 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
     if (!u || !cd || !opts) { set_error("null argument"); return BTG_EINVAL; }
     if (cd->S != u->du.S) { set_error("count distribution / unit sample mismatch"); return BTG_EINVAL; }
     const uint32_t S = u->du.S, G = u->du.G;
+    if (joint && u->du.n_nested_groups) { set_error("the joint noise-genotyping mode does not support nested variant-cluster groups in this build (%u groups)", u->du.n_nested_groups); return BTG_EINVAL; }
     const uint32_t iters = (uint32_t)opts->gibbs_burn_in + opts->gibbs_samples;
     const size_t trace_rows = (size_t)opts->n_chains * (iters + 1) + (joint ? 0 : 1);
     auto s = ctx().stream;

@@ -130,16 +130,40 @@ def test_noise_genotyping_joint_mode_matches_oracle(btg, name):
     eng.close()
 
 
-def test_rejects_nested_groups_loudly(btg):
+def test_malformed_group_forest_rejected_loudly(btg):
+    """A multi-cluster group needs sources + edges forming a forest over its clusters (VariantClusterGroup.cpp:47-107)."""
     fx = GibbsFixture("gibbs_snv_1s")
     a = dict(fx.unit.a)
     gco = a["group_cluster_off"].copy()
-    a["group_cluster_off"] = np.concatenate([gco[:1], gco[2:]])      # merge the first two groups
+    a["group_cluster_off"] = np.concatenate([gco[:1], gco[2:]])      # merge the first two groups, drop one source
     a["group_ploidy"] = a["group_ploidy"][fx.S:]
-    a["group_src_off"] = a["group_src_off"][:-1]; a["group_edge_off"] = a["group_edge_off"][:-1]
+    a["group_src_off"] = np.concatenate([a["group_src_off"][:1], a["group_src_off"][2:] - 1])
+    a["group_src"] = a["group_src"][1:]
+    a["group_edge_off"] = a["group_edge_off"][:-1]
     bad = U.Unit(a, fx.S)
-    with pytest.raises(Exception, match="nested"):
+    with pytest.raises(Exception, match="forest"):
         engine.InferenceEngine(bad)
+
+
+def test_joint_mode_rejects_nested_groups_loudly(btg):
+    fx = GibbsFixture("gibbs_nested_2s")
+    _, gcd = _both(fx, None)
+    eng = engine.InferenceEngine(fx.unit)
+    with pytest.raises(Exception, match="nested"):
+        eng.estimate_noise_and_genotypes(gcd, fx.opts(chains=1, burn=2, samples=2))
+    eng.close()
+
+
+def test_nested_unit_noise_estimation_uses_single_cluster_groups_only(btg):
+    """InferenceEngine::estimateNoise draws from groups of ONE cluster (InferenceEngine.cpp:144-151)."""
+    fx = GibbsFixture("gibbs_nested_2s")
+    opts = fx.opts(chains=2, burn=20, samples=30)
+    ocd, gcd = _both(fx, opts)
+    otrace = O.oracle_estimate_noise(fx.unit, ocd, opts)
+    eng = engine.InferenceEngine(fx.unit)
+    gtrace = eng.estimate_noise(gcd, opts)
+    assert np.abs(gtrace - otrace).max() <= 1e-9 * max(1.0, np.abs(otrace).max())
+    eng.close()
 
 
 def test_empty_unit(btg):
