@@ -188,6 +188,48 @@ class KmerPipeline:
                                                            counts_dev.numel(), self.S, sample_idx, self.counts.data_ptr(), self.has_record.data_ptr(),
                                                            self.stream), self.lib)
 
+    def _nested_tables(self):
+        """HaplotypeInfo::nested_variant_cluster_indices and nested_variant_cluster_dependency
+        (VariantClusterGraph.cpp:1006-1010, 1112-1133).  Only clusters holding a vertex that stands for a nested
+        cluster contribute, so this is a short host loop over those clusters."""
+        g = self.g
+        v_nested = np.asarray(g["v_nested"], np.uint32)
+        cvo, cpo = np.asarray(g["cl_vertex_off"], np.int64), np.asarray(g["cl_path_off"], np.int64)
+        hap_nested_off = np.zeros(self.P + 1, np.uint64)
+        cl_dep_off = np.zeros(self.C + 1, np.uint64)
+        nested_parts, dep_cluster, dep_var_off, dep_var = [], [], [0], []
+        marked = np.flatnonzero(v_nested != 0xFFFFFFFF)
+        if len(marked):
+            path_start = np.concatenate([[0], np.cumsum(self.n_paths.astype(np.int64))])
+            hap_len = np.zeros(self.P, np.int64)
+            per_hap = {}
+            for c in np.unique(np.searchsorted(cvo, marked, side="right") - 1):
+                v0, v1 = cvo[c], cvo[c + 1]
+                nv = v1 - v0
+                bits = np.asarray(g["path_bits"][cpo[c]:cpo[c + 1]], np.uint8).reshape(-1, nv)
+                nest = v_nested[v0:v1]
+                has = nest != 0xFFFFFFFF
+                for p in range(bits.shape[0]):
+                    lst = np.sort(nest[has & (bits[p] != 0)])
+                    per_hap[path_start[c] + p] = lst
+                    hap_len[path_start[c] + p] = len(lst)
+                deps = {}
+                for v in np.flatnonzero(has):
+                    vars_ = []
+                    if g["v_var"][v0 + v] != 0xFFFF:
+                        vars_.append(int(g["v_var"][v0 + v]))
+                    vars_ += [int(x) for x in g["v_refvar"][g["v_refvar_off"][v0 + v]:g["v_refvar_off"][v0 + v + 1]]]
+                    deps[int(nest[v])] = sorted(vars_, reverse=True)
+                for key in sorted(deps):
+                    dep_cluster.append(key); dep_var += deps[key]; dep_var_off.append(len(dep_var))
+                cl_dep_off[c + 1] = len(deps)
+            hap_nested_off[1:] = np.cumsum(hap_len)
+            nested_parts = [per_hap[h] for h in sorted(per_hap)]
+        cl_dep_off = np.cumsum(cl_dep_off).astype(np.uint64)
+        hap_nested = np.concatenate(nested_parts).astype(np.uint32) if nested_parts else np.zeros(0, np.uint32)
+        return (hap_nested_off, hap_nested, cl_dep_off, np.asarray(dep_cluster, np.uint32), np.asarray(dep_var_off, np.uint64),
+                np.asarray(dep_var, np.uint16))
+
     # ---- classifyPathKmers + getHaplotypeCandidates -----------------------------------------------------------
     @_on_library_stream
     def build_unit(self, multigroup_bloom=None, var_nalleles=None, var_dep=None, ploidy=None) -> Unit:
@@ -278,6 +320,10 @@ class KmerPipeline:
         capi.check(self.lib.btg_path_alleles_dev(C.addressof(self.desc), cl_var_off.data_ptr(), vna.data_ptr(), hapvar_off.data_ptr(), hap_alleles.data_ptr(),
                                                  self.stream), self.lib)
         self.ext.synchronize()
+        # multicluster k-mers of one group share a KmerCounts record: one id per such key (KmerCounts.cpp:205-224)
+        shared_id = torch.cumsum(multicluster.to(torch.int64), 0) - 1
+        k_shared = torch.where(is_multi, shared_id[k_key], torch.full_like(k_key, 0xFFFFFFFF))
+        hap_nested_off, hap_nested, cl_dep_off, dep_cluster, dep_var_off, dep_var = self._nested_tables()
         G = len(g["group_cluster_off"]) - 1
         cpu = lambda t, dt: t.cpu().numpy().astype(dt) if t.dtype != torch.int16 else t.cpu().numpy().view(np.uint16)
         a = {
@@ -289,16 +335,15 @@ class KmerPipeline:
             "cl_kmer_off": cpu(cl_kmer_off, np.uint64), "cl_var_off": g["cl_var_off"], "cl_mult_off": cpu(cl_mult_off, np.uint64),
             "mult": cpu(mult, np.uint8), "k_has_counts": cpu(rec[k_key], np.uint8),
             "k_counts": cpu(self.counts[k_key].reshape(-1), np.uint8), "k_ic": cpu(self.ic[k_key].reshape(-1), np.uint8),
-            "k_shared": np.full(Rk, 0xFFFFFFFF, np.uint32),
+            "k_shared": cpu(k_shared, np.uint32),
             "cl_uniq_off": cpu(_excl_cumsum(cl_uniq), np.uint64), "uniq_idx": cpu(local_row[uniq_rows], np.uint32),
             "cl_multi_off": cpu(_excl_cumsum(cl_multi), np.uint64), "multi_idx": cpu(local_row[multi_rows], np.uint32),
             "kmer_vh_off": cpu(_excl_cumsum(kmer_vh), np.uint64), "vh_var": cpu(e_var, np.uint16),
             "vh_bits_off": cpu(vh_bits_off, np.uint64), "vh_bits": cpu(vh_bits, np.uint8),
             "cl_hapvar_off": cpu(hapvar_off, np.uint64), "hap_alleles": cpu(hap_alleles[:-1], np.uint16),
             "var_nalleles": np.asarray(var_nalleles, np.uint16), "var_dep": np.asarray(var_dep, np.uint8),
-            "hap_nested_off": np.zeros(self.P + 1, np.uint64), "hap_nested": np.zeros(0, np.uint32),
-            "cl_dep_off": np.zeros(self.C + 1, np.uint64), "dep_cluster": np.zeros(0, np.uint32),
-            "dep_var_off": np.zeros(1, np.uint64), "dep_var": np.zeros(0, np.uint16),
+            "hap_nested_off": hap_nested_off, "hap_nested": hap_nested,
+            "cl_dep_off": cl_dep_off, "dep_cluster": dep_cluster, "dep_var_off": dep_var_off, "dep_var": dep_var,
         }
         u = Unit(a, self.S)
         u.kmer_words = np.stack([self.kw0[k_key].cpu().numpy().view(np.uint64), self.kw1[k_key].cpu().numpy().view(np.uint64)], 1)

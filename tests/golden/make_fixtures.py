@@ -171,12 +171,14 @@ PIPE_WORKLOADS = {
     "pipe_snv_1s": lambda: synth.config_a(n_variants=500, length=50_000),
     "pipe_mixed_3s": lambda: synth.small_mixed(350, 25_000, 3, seed=52),
     "pipe_chrx_2s": lambda: synth.small_mixed(250, 20_000, 2, seed=61, chrom="chrX"),
+    "pipe_nested_2s": lambda: synth.nested_sv(12, 50_000, 2, seed=9, n_background=120, sv_len=(150, 600), repeat_frac=0.6),
 }
 
 PATH_WORKLOADS = {
     "paths_snv_1s": lambda: synth.config_a(n_variants=1500, length=150_000),
     "paths_mixed_3s": lambda: synth.small_mixed(900, 60_000, 3, seed=21),
     "paths_dense_2s": lambda: synth.small_mixed(1500, 40_000, 2, seed=44, frac_indel=0.3),
+    "paths_nested_2s": lambda: synth.nested_sv(20, 80_000, 2, seed=13, n_background=200, sv_len=(150, 600), repeat_frac=0.5),
 }
 
 if __name__ == "__main__":
@@ -187,6 +189,10 @@ if __name__ == "__main__":
         _sys.exit(0)
     if len(_sys.argv) > 1 and _sys.argv[1] == "joint":
         make("gibbs_joint_2s", synth.small_mixed(260, 24_000, 2, seed=83), 400, extra_args=("--noise-genotyping",))
+        _sys.exit(0)
+    if len(_sys.argv) > 1 and _sys.argv[1] == "nested-kmer":
+        make_pipeline("pipe_nested_2s", PIPE_WORKLOADS["pipe_nested_2s"]())
+        make_paths("paths_nested_2s", PATH_WORKLOADS["paths_nested_2s"]())
         _sys.exit(0)
     if len(_sys.argv) > 1 and _sys.argv[1] == "nested":
         # deletions spanning SNVs (nested clusters, has_dependency) with duplicated segments (multicluster k-mers)

@@ -71,6 +71,19 @@ def test_haplotype_candidates_identical_to_reference(btg, name):
     # flags of the table entries that have records
     fl = h["k_flags"]
     assert ((fl & 2) != 0).sum() == len(a["multi_idx"])
+    # nested clusters: per-haplotype nested cluster lists and the dependency map (VariantClusterGraph.cpp:1006-1010, 1112-1133)
+    for k in ("hap_nested_off", "hap_nested", "cl_dep_off", "dep_cluster", "dep_var_off", "dep_var"):
+        assert (a[k] == h[k]).all(), k
+    # multicluster rows: one shared record per k-mer, exactly on the rows the reference flags
+    sh = a["k_shared"] != 0xFFFFFFFF
+    assert (sh == ((fl & 2) != 0)).all()
+    if sh.any():
+        words = u.kmer_words[sh]
+        ids = a["k_shared"][sh]
+        by_id = {}
+        for wd, i in zip(map(bytes, words), ids.tolist()):
+            assert by_id.setdefault(i, wd) == wd
+        assert len(set(by_id.values())) == len(by_id)
 
 
 def test_table_lookup_and_saturation(btg):
