@@ -35,4 +35,6 @@ def bind(L):
     L.btg_table_add_sample_kmers_dev.argtypes = [vp, vp, C.c_int64, vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, vp, vp, vp]
     L.btg_table_scan_region_dev.argtypes = [vp, vp, C.c_int64, vp, C.c_size_t, C.c_int, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp]
     L.btg_table_set_index_dev.argtypes = [vp, C.c_int]
+    L.btg_table_keys_from_kmers_dev.argtypes = [vp, C.c_size_t, vp, vp, vp]
+    L.btg_table_keys_to_kmers_dev.argtypes = [vp, vp, C.c_size_t, vp, vp]
     L.btg_estimate_noise_and_genotypes.argtypes = [vp, vp, vp, vp, vp]

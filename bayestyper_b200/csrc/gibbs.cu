@@ -1050,7 +1050,8 @@ __global__ void __launch_bounds__(64) k_summarise(DevUnit du, btg_gibbs_opts o, 
 
 // ---- estimateNoise: lock-step iterations over the selected single-cluster groups ---------------
 struct NoiseState {
-    uint64_t *hist;        // [S][256] CountAllocation (CountAllocation.cpp:34-57)
+    uint64_t *hist;        // [S][2] sufficient statistics (n_obs, sum of counts) of the CountAllocation histogram
+                           // (CountAllocation.cpp:34-57, CountDistribution::calcCountSuffStats :188-200) — the only thing read from it
     double *rates;         // [S] current noise rates (device copy owned by the count dist)
     double *noise_table;   // [S][256]
     double *mean_rates;    // [S]
@@ -1072,8 +1073,8 @@ __device__ void noise_update_block(const NoiseState &ns, uint32_t S, float prior
             if (mode == 0) {
                 r = rng.gamma((double)prior_shape) * (double)prior_scale;  // CountDistribution.cpp:163-171,202-213
             } else if (mode == 1) {
-                unsigned long long n_obs = 0, sum = 0;  // calcCountSuffStats (CountDistribution.cpp:188-200)
-                for (uint32_t i = 0; i < 256; i++) { const unsigned long long c = ns.hist[s * 256 + i]; n_obs += c; sum += i * c; ns.hist[s * 256 + i] = 0; }
+                const unsigned long long n_obs = ns.hist[s * 2], sum = ns.hist[s * 2 + 1];  // calcCountSuffStats (CountDistribution.cpp:188-200)
+                ns.hist[s * 2] = 0; ns.hist[s * 2 + 1] = 0;
                 const float shape_f = prior_shape + (float)sum;                                   // float arithmetic as in the
                 const float scale_f = prior_scale / ((float)n_obs * prior_scale + 1);             // reference (CountDistribution.cpp:182)
                 r = rng.gamma((double)shape_f) * (double)scale_f;
@@ -1158,6 +1159,9 @@ __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg
                                                        uint32_t iters, NoiseState ns, float prior_shape, float prior_scale, unsigned long long *hist, int joint) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sh_rates[BTG_MAX_SAMPLES];
+    // getNoiseCounts of the block's clusters: only (n_obs, sum) per sample are ever read from the merged CountAllocation,
+    // so they are summed in shared memory and leave the block as <= 2S global atomics per iteration
+    __shared__ unsigned long long sh_stat[BTG_MAX_SAMPLES * 2];
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     for (uint32_t i = tid; i < n_sel; i += nthreads) {  // initGenotypersCallback: fresh genotypers every chain
         Cl cl;
@@ -1181,6 +1185,8 @@ __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg
     grid.sync();
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     for (uint32_t it = 1; it <= iters; it++) {
+        if (threadIdx.x < 2 * du.S) sh_stat[threadIdx.x] = 0;
+        __syncthreads();
         // sel[0 .. n_big): large clusters, one WARP each (cooperative cache fill, counts and cache clear; lane 0 samples)
         for (uint32_t i = tid >> 5; i < n_big; i += nthreads >> 5) {
             const uint32_t lane = tid & 31u;
@@ -1194,10 +1200,12 @@ __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg
             const uint32_t n_sub = cl.misc[kNSub];
             for (uint32_t s = 0; s < cl.S; s++) {  // getNoiseCounts
                 const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
+                uint32_t n0 = 0, c0 = 0;
                 for (uint32_t j = lane; j < n_sub; j += 32) {
                     const uint32_t k = cl.uniq_sub[j];
-                    if ((uint8_t)(cl.diplMult(k, da, db) + cl.ic(k, s)) == 0) atomicAdd(hist + s * 256u + cl.count(k, s), 1ULL);
+                    if ((uint8_t)(cl.diplMult(k, da, db) + cl.ic(k, s)) == 0) { n0++; c0 += cl.count(k, s); }
                 }
+                if (n0) { atomicAdd(sh_stat + 2 * s, (unsigned long long)n0); atomicAdd(sh_stat + 2 * s + 1, (unsigned long long)c0); }
             }
             for (uint32_t j = lane; j < cl.S * cl.Dall; j += 32) cl.ucache[j] = nan;  // clearGenotyperCache
             __syncwarp();
@@ -1210,13 +1218,17 @@ __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg
             const uint32_t n_sub = cl.misc[kNSub];
             for (uint32_t s = 0; s < cl.S; s++) {  // getNoiseCounts
                 const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
+                uint32_t n0 = 0, c0 = 0;
                 for (uint32_t j = 0; j < n_sub; j++) {
                     const uint32_t k = cl.uniq_sub[j];
-                    if ((uint8_t)(cl.diplMult(k, da, db) + cl.ic(k, s)) == 0) atomicAdd(hist + s * 256u + cl.count(k, s), 1ULL);
+                    if ((uint8_t)(cl.diplMult(k, da, db) + cl.ic(k, s)) == 0) { n0++; c0 += cl.count(k, s); }
                 }
+                if (n0) { atomicAdd(sh_stat + 2 * s, (unsigned long long)n0); atomicAdd(sh_stat + 2 * s + 1, (unsigned long long)c0); }
             }
             for (uint32_t j = 0; j < cl.S * cl.Dall; j++) cl.ucache[j] = nan;  // clearGenotyperCache
         }
+        __syncthreads();
+        if (threadIdx.x < 2 * du.S && sh_stat[threadIdx.x]) atomicAdd(hist + threadIdx.x, sh_stat[threadIdx.x]);
         __threadfence();
         grid.sync();
         if (blockIdx.x == 0) noise_update_block(ns, du.S, prior_shape, prior_scale, o.random_seed, 1, o.gibbs_burn_in < it, (double)chain, (double)it, 1, sh_rates);
@@ -1681,7 +1693,7 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
     uint32_t *d_sel = nullptr;
     std::vector<void *> tmp;
     auto dalloc = [&](size_t bytes) { void *p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 8) != cudaSuccess) return (void *)nullptr; tmp.push_back(p); cudaMemsetAsync(p, 0, bytes ? bytes : 8, s); return p; };
-    hist = (unsigned long long *)dalloc((size_t)S * 256 * 8);
+    hist = (unsigned long long *)dalloc((size_t)S * 2 * 8);
     ns.hist = (uint64_t *)hist;
     ns.rates = cd->rates;
     ns.noise_table = cd->noise;

@@ -11,8 +11,11 @@
 // hash of vectors.  Filter false positives only ever create table entries that no path k-mer looks up, so the
 // device keeps an EXACT table instead: the distinct path k-mers as a sorted key array (built by the caller from
 // the emitted occurrences) that the 17 B/record sample stream and the 1 B/nt genome scan probe directly.
-// Keys are ordered as signed (w1, w0) pairs — the order torch.sort gives the host glue — and the kernels use the
-// same comparator.
+// Keys are kept in the internal MSB-first form of kmer.cuh (V = hi:lo, nucleotide 0 on top), ascending, i.e. in
+// lexicographic order of the k-mer strings — the order in which a KMC database stores its records
+// (external/kmc_api/kmc_file.cpp:428-515: prefix LUT, then sorted suffixes), so a sample's stream walks the table
+// front to back.  The two key columns are signed 64-bit for the host glue's sort: key_hi = hi (46 bits, >= 0) and
+// key_lo = lo ^ 2^63 (biased, so that signed order == unsigned order of lo).
 #include "common.cuh"
 #include "kmer.cuh"
 
@@ -21,6 +24,12 @@ using namespace btg;
 namespace {
 
 constexpr uint32_t NONE16 = 0xFFFF;
+constexpr uint64_t kLoBias = 0x8000000000000000ULL;  // key_lo = lo ^ kLoBias
+
+struct TableKey { int64_t lo, hi; };  // (key_lo, key_hi) of one k-mer
+__device__ __forceinline__ TableKey key_of(const Kmer128 &v) { return TableKey{(int64_t)(v.lo ^ kLoBias), (int64_t)v.hi}; }
+// a packed k-mer in the boundary layout (the ABI's 2 x uint64) -> table key
+__device__ __forceinline__ TableKey key_of_boundary(int64_t w0, int64_t w1) { return key_of(from_boundary((uint64_t)w0, (uint64_t)w1)); }
 constexpr int kMaxRunning = 48;  // variants whose window covers the current k-mer (running_variants)
 
 struct PathWalkGraphs {
@@ -87,10 +96,8 @@ __global__ void __launch_bounds__(128) k_walk_paths(PathWalkGraphs g, uint64_t n
                 n_run = w;
                 if (EMIT) {
                     const Kmer128 cn = roll.canonical();
-                    uint64_t w0, w1;
-                    to_boundary(cn, w0, w1);
-                    key_w0[o_base + occ] = (int64_t)w0;
-                    key_w1[o_base + occ] = (int64_t)w1;
+                    key_w0[o_base + occ] = (int64_t)(cn.lo ^ kLoBias);
+                    key_w1[o_base + occ] = (int64_t)cn.hi;
                     occ_path[o_base + occ] = (uint32_t)p;
                     occ_nt[o_base + occ] = num_nt;
                 }
@@ -130,8 +137,9 @@ __global__ void __launch_bounds__(128) k_path_alleles(PathWalkGraphs g, uint64_t
 }
 
 // ---- exact table probes ------------------------------------------------------------------------
-// Optional prefix index (like KMC's prefix LUT): lut[b] = first key whose top `lut_bits` bits of the 46-bit word 1
-// equal b; narrows the binary search to the bucket (typically 1-2 keys) at the cost of one 8 B read.
+// Optional prefix index (like KMC's prefix LUT): lut[b] = first key whose top `lut_bits` bits of the 46-bit key_hi
+// (= the first lut_bits/2 nucleotides) are >= b; narrows the search to the bucket (typically 1-2 keys) at the cost of
+// one 8 B read.
 struct TableIndex {
     const int64_t *lut;  // [2^lut_bits + 1] or nullptr
     int shift;           // 46 - lut_bits
@@ -170,17 +178,75 @@ __device__ __forceinline__ void sat_add_u8(uint8_t *p, uint32_t add) {  // updat
     } while (old != assumed);
 }
 
-// KmerCounter::parseSampleKmersCallBack: one KMC record per thread (16 B k-mer + 1 B count streamed once)
-__global__ void __launch_bounds__(256) k_table_add_sample(const int64_t *__restrict__ kw0, const int64_t *__restrict__ kw1, int64_t n_keys,
+// KmerCounter::parseSampleKmersCallBack: the sample's (k-mer, count) records stream past the table once (17 B/record).
+// Every thread keeps R records in flight: R coalesced 16 B record loads, R prefix-index reads, R first-key reads are
+// issued back to back before anything is compared, so a record costs three DRAM latencies (index -> key -> count
+// update) shared with R-1 others instead of the ~6 of a dependent binary search.  With a KMC-ordered stream
+// neighbouring lanes read neighbouring index entries and keys (the stream and the table are sorted alike), so the
+// table and its index cross the memory bus about once: traffic ~ the algorithmic 17 B/record + 16 B/key.
+// Buckets longer than kLinear keys (no index installed, or a skewed table) fall back to the binary search.
+constexpr int kStreamR = 4;
+constexpr int kLinear = 4;
+__global__ void __launch_bounds__(256, 4) k_table_add_sample(const int64_t *__restrict__ kw0, const int64_t *__restrict__ kw1, int64_t n_keys,
                                                           const longlong2 *__restrict__ kmers, const uint8_t *__restrict__ counts, size_t n,
                                                           uint32_t S, uint32_t sample, uint8_t *table_counts, uint8_t *has_record, TableIndex ix) {
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    for (size_t base = blockIdx.x * (size_t)blockDim.x + threadIdx.x; base < n; base += nthreads * kStreamR) {
+        TableKey q[kStreamR];
+        int64_t lo[kStreamR], hi[kStreamR], k0[kStreamR], k1[kStreamR];
+#pragma unroll
+        for (int r = 0; r < kStreamR; r++) {
+            const size_t i = base + (size_t)r * nthreads;
+            if (i < n) { const longlong2 k = __ldg(kmers + i); q[r] = key_of_boundary(k.x, k.y); lo[r] = 0; hi[r] = n_keys; }
+            else { q[r] = TableKey{0, 0}; lo[r] = 0; hi[r] = 0; }
+        }
+        if (ix.lut) {
+#pragma unroll
+            for (int r = 0; r < kStreamR; r++)
+                if (hi[r]) { const int64_t b = q[r].hi >> ix.shift; lo[r] = __ldg(ix.lut + b); hi[r] = __ldg(ix.lut + b + 1); }
+        }
+#pragma unroll
+        for (int r = 0; r < kStreamR; r++) {
+            const bool small = hi[r] - lo[r] <= kLinear && lo[r] < hi[r];
+            k1[r] = small ? __ldg(kw1 + lo[r]) : 0;
+            k0[r] = small ? __ldg(kw0 + lo[r]) : 0;
+        }
+#pragma unroll
+        for (int r = 0; r < kStreamR; r++) {
+            if (lo[r] >= hi[r]) continue;
+            int64_t idx = -1;
+            if (hi[r] - lo[r] <= kLinear) {
+                int64_t p = lo[r], a1 = k1[r], a0 = k0[r];
+                for (;;) {
+                    if (a1 == q[r].hi && a0 == q[r].lo) { idx = p; break; }
+                    if (a1 > q[r].hi || (a1 == q[r].hi && a0 > q[r].lo) || ++p >= hi[r]) break;
+                    a1 = __ldg(kw1 + p); a0 = __ldg(kw0 + p);
+                }
+            } else {
+                idx = table_find(kw0 + lo[r], kw1 + lo[r], hi[r] - lo[r], q[r].lo, q[r].hi);
+                if (idx >= 0) idx += lo[r];
+            }
+            if (idx >= 0) {
+                sat_add_u8(table_counts + (size_t)idx * S + sample, counts[base + (size_t)r * nthreads]);
+                has_record[idx] = 1;
+            }
+        }
+    }
+}
+
+// table keys <-> packed k-mers in the ABI's boundary layout
+__global__ void __launch_bounds__(256) k_keys_from_kmers(const longlong2 *__restrict__ kmers, size_t n, int64_t *__restrict__ kw0, int64_t *__restrict__ kw1) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const longlong2 k = __ldg(kmers + i);
-        const int64_t idx = table_find(kw0, kw1, n_keys, k.x, k.y, ix);
-        if (idx >= 0) {
-            sat_add_u8(table_counts + (size_t)idx * S + sample, counts[i]);
-            has_record[idx] = 1;
-        }
+        const TableKey q = key_of_boundary(k.x, k.y);
+        kw0[i] = q.lo; kw1[i] = q.hi;
+    }
+}
+__global__ void __launch_bounds__(256) k_keys_to_kmers(const int64_t *__restrict__ kw0, const int64_t *__restrict__ kw1, size_t n, longlong2 *__restrict__ kmers) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t w0, w1;
+        to_boundary(Kmer128{(uint64_t)kw1[i], (uint64_t)kw0[i] ^ kLoBias}, w0, w1);
+        kmers[i] = longlong2{(long long)w0, (long long)w1};
     }
 }
 
@@ -200,9 +266,8 @@ __global__ void __launch_bounds__(256) k_table_scan_region(const int64_t *__rest
             bool complete = false;
             if (c > 3) roll.reset(); else complete = roll.push(c);
             if (complete && p >= p0) {
-                uint64_t w0, w1;
-                to_boundary(roll.canonical(), w0, w1);
-                const int64_t idx = table_find(kw0, kw1, n_keys, (int64_t)w0, (int64_t)w1, ix);
+                const TableKey q = key_of(roll.canonical());
+                const int64_t idx = table_find(kw0, kw1, n_keys, q.lo, q.hi, ix);
                 if (idx >= 0) {
                     has_record[idx] = 1;
                     sat_add_u8(max_mult + idx, 1);  // max_haploid_multiplicity (KmerCounts.cpp:100)
@@ -218,7 +283,8 @@ __global__ void __launch_bounds__(256) k_table_lookup(const int64_t *__restrict_
                                                       const longlong2 *__restrict__ kmers, size_t n, int64_t *__restrict__ idx_out, TableIndex ix) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const longlong2 k = __ldg(kmers + i);
-        idx_out[i] = table_find(kw0, kw1, n_keys, k.x, k.y, ix);
+        const TableKey q = key_of_boundary(k.x, k.y);
+        idx_out[i] = table_find(kw0, kw1, n_keys, q.lo, q.hi, ix);
     }
 }
 
@@ -266,6 +332,24 @@ int btg_table_set_index_dev(const int64_t *lut, int lut_bits) {
     return BTG_OK;
 }
 
+int btg_table_keys_from_kmers_dev(const uint64_t *kmers, size_t n, int64_t *key_lo, int64_t *key_hi, void *stream) {
+    BTG_REQUIRE_INIT();
+    if (n == 0) return BTG_OK;
+    k_keys_from_kmers<<<btg_grid_for(n, 256, 8), 256, 0, pick_stream(stream)>>>((const longlong2 *)kmers, n, key_lo, key_hi);
+    BTG_LAUNCHED();
+    BTG_CUDA(cudaGetLastError());
+    return BTG_OK;
+}
+
+int btg_table_keys_to_kmers_dev(const int64_t *key_lo, const int64_t *key_hi, size_t n, uint64_t *kmers, void *stream) {
+    BTG_REQUIRE_INIT();
+    if (n == 0) return BTG_OK;
+    k_keys_to_kmers<<<btg_grid_for(n, 256, 8), 256, 0, pick_stream(stream)>>>(key_lo, key_hi, n, (longlong2 *)kmers);
+    BTG_LAUNCHED();
+    BTG_CUDA(cudaGetLastError());
+    return BTG_OK;
+}
+
 int btg_table_lookup_dev(const int64_t *key_w0, const int64_t *key_w1, int64_t n_keys, const uint64_t *kmers, size_t n, int64_t *idx_out, void *stream) {
     BTG_REQUIRE_INIT();
     if (n == 0) return BTG_OK;
@@ -280,7 +364,7 @@ int btg_table_add_sample_kmers_dev(const int64_t *key_w0, const int64_t *key_w1,
     BTG_REQUIRE_INIT();
     if (sample_idx >= n_samples) { set_error("sample index out of range"); return BTG_EINVAL; }
     if (n == 0) return BTG_OK;
-    k_table_add_sample<<<btg_grid_for(n, 256, 8), 256, 0, pick_stream(stream)>>>(key_w0, key_w1, n_keys, (const longlong2 *)kmers, counts, n, n_samples,
+    k_table_add_sample<<<btg_grid_for((n + kStreamR - 1) / kStreamR, 256, 4), 256, 0, pick_stream(stream)>>>(key_w0, key_w1, n_keys, (const longlong2 *)kmers, counts, n, n_samples,
                                                                                sample_idx, table_counts, has_record, g_index);
     BTG_LAUNCHED();
     BTG_CUDA(cudaGetLastError());

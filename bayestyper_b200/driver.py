@@ -83,34 +83,39 @@ def estimate_nb_parameters(pipe: kmer_pipeline.KmerPipeline, region_buf, spectra
         valid = torch.empty(n, dtype=torch.uint8, device=dev)
         capi.check(lib.btg_scan_sequence_dev(buf.data_ptr(), n, km.data_ptr(), valid.data_ptr(), None), lib)
         km = km[valid.to(torch.bool)]
-        # distinct k-mers + genomic multiplicity
-        o = torch.sort(km[:, 0], stable=True).indices
-        o = o[torch.sort(km[o, 1], stable=True).indices]
-        s = km[o]
-        new = torch.ones(len(s), dtype=torch.bool, device=dev)
-        new[1:] = (s[1:] != s[:-1]).any(1)
-        keys = s[new].contiguous()
-        occ = torch.diff(torch.cat([torch.nonzero(new).squeeze(1), torch.tensor([len(s)], device=dev)]))
+        # distinct k-mers + genomic multiplicity (as table keys: lexicographic order)
+        n_valid = km.shape[0]
+        k_lo = torch.empty(n_valid, dtype=torch.int64, device=dev)
+        k_hi = torch.empty(n_valid, dtype=torch.int64, device=dev)
+        capi.check(lib.btg_table_keys_from_kmers_dev(km.data_ptr(), n_valid, k_lo.data_ptr(), k_hi.data_ptr(), None), lib)
+        o = torch.sort(k_lo, stable=True).indices
+        o = o[torch.sort(k_hi[o], stable=True).indices]
+        s_lo, s_hi = k_lo[o], k_hi[o]
+        new = torch.ones(n_valid, dtype=torch.bool, device=dev)
+        new[1:] = (s_lo[1:] != s_lo[:-1]) | (s_hi[1:] != s_hi[:-1])
+        keys = km[o][new].contiguous()                              # packed k-mers of the distinct keys, key order
+        kw0, kw1 = s_lo[new].contiguous(), s_hi[new].contiguous()
+        occ = torch.diff(torch.cat([torch.nonzero(new).squeeze(1), torch.tensor([n_valid], device=dev)]))
         idx = torch.empty(len(keys), dtype=torch.int64, device=dev)
         pipe.use_index()
         capi.check(lib.btg_table_lookup_dev(pipe.kw0.data_ptr(), pipe.kw1.data_ptr(), pipe.n_keys, keys.data_ptr(), len(keys), idx.data_ptr(), None), lib)
         not_path = idx < 0
-        keys, occ = keys[not_path], occ[not_path]
+        kw0, kw1, occ = kw0[not_path], kw1[not_path], occ[not_path]
         total = int(km.shape[0])
         frac = min(1.0, 3.0 * opt.max_parameter_kmers / max(total, 1))
         g = torch.Generator(device=dev).manual_seed(opt.random_seed)
-        sel = torch.rand(len(keys), device=dev, generator=g) < frac
-        keys, occ = keys[sel], occ[sel]
-        if len(keys) > opt.max_parameter_kmers:
-            perm = torch.randperm(len(keys), device=dev, generator=g)[:opt.max_parameter_kmers].sort().values
-            keys, occ = keys[perm], occ[perm]
-        kw0, kw1 = keys[:, 0].contiguous(), keys[:, 1].contiguous()
+        sel = torch.rand(len(occ), device=dev, generator=g) < frac
+        kw0, kw1, occ = kw0[sel], kw1[sel], occ[sel]
+        if len(occ) > opt.max_parameter_kmers:
+            perm = torch.randperm(len(occ), device=dev, generator=g)[:opt.max_parameter_kmers].sort().values
+            kw0, kw1, occ = kw0[perm], kw1[perm], occ[perm]
+        kw0, kw1 = kw0.contiguous(), kw1.contiguous()
         S = len(spectra_dev)
-        counts = torch.zeros((len(keys), S), dtype=torch.uint8, device=dev)
-        rec = torch.zeros(len(keys), dtype=torch.uint8, device=dev)
+        counts = torch.zeros((len(occ), S), dtype=torch.uint8, device=dev)
+        rec = torch.zeros(len(occ), dtype=torch.uint8, device=dev)
         pipe.use_index(False)                       # the parameter k-mers are a second, un-indexed table
         for si, (kd, cd_) in enumerate(spectra_dev):
-            capi.check(lib.btg_table_add_sample_kmers_dev(kw0.data_ptr(), kw1.data_ptr(), len(keys), kd.data_ptr(), cd_.data_ptr(), cd_.numel(), S, si,
+            capi.check(lib.btg_table_add_sample_kmers_dev(kw0.data_ptr(), kw1.data_ptr(), len(occ), kd.data_ptr(), cd_.data_ptr(), cd_.numel(), S, si,
                                                           counts.data_ptr(), rec.data_ptr(), None), lib)
         nb_p, nb_size, used = [], [], []
         for si in range(S):

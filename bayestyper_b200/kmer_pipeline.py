@@ -126,7 +126,7 @@ class KmerPipeline:
         if int(status.max()) != 0:
             raise capi.BtgError("path walk: running-variant capacity exceeded in cluster %d" % int(torch.nonzero(status)[0]))
         self.NC = NC
-        # distinct keys, ascending signed (w1, w0)
+        # distinct keys, ascending (key_hi, key_lo) = lexicographic k-mer order (the order of a KMC database)
         o = torch.sort(self.w0, stable=True).indices
         o = o[torch.sort(self.w1[o], stable=True).indices]
         s0, s1 = self.w0[o], self.w1[o]
@@ -138,7 +138,7 @@ class KmerPipeline:
         self.n_keys = int(self.kw0.numel())
         self.occ_key = torch.empty(N, dtype=torch.int64, device=d)
         self.occ_key[o] = key_of_sorted
-        # prefix index over word 1 (46 bits): ~1 key per bucket
+        # prefix index over key_hi (46 bits = the first 23 nucleotides): ~1 key per bucket
         self.lut_bits = int(min(24, max(8, np.ceil(np.log2(max(self.n_keys, 2))))))
         buckets = self.kw1 >> (2 * K - 64 - self.lut_bits)
         cnt = torch.bincount(buckets, minlength=1 << self.lut_bits)
@@ -258,7 +258,7 @@ class KmerPipeline:
         max_hap = torch.clamp(self.max_mult[:nk].to(torch.int64) + sum_max, max=255)
         multicluster = rec & (n_cl >= 2)
         if multigroup_bloom is not None:
-            keys = torch.stack([self.kw0, self.kw1], 1).contiguous()
+            keys = self.key_kmers()
             hit = torch.zeros(nk, dtype=torch.uint8, device=d)
             capi.check(self.lib.btg_bloom_lookup_dev(multigroup_bloom, keys.data_ptr(), nk, hit.data_ptr(), self.stream), self.lib)
             multigroup = hit.to(torch.bool)
@@ -346,5 +346,12 @@ class KmerPipeline:
             "cl_dep_off": cl_dep_off, "dep_cluster": dep_cluster, "dep_var_off": dep_var_off, "dep_var": dep_var,
         }
         u = Unit(a, self.S)
-        u.kmer_words = np.stack([self.kw0[k_key].cpu().numpy().view(np.uint64), self.kw1[k_key].cpu().numpy().view(np.uint64)], 1)
+        u.kmer_words = self.key_kmers(k_key).cpu().numpy().view(np.uint64)
         return u
+
+    def key_kmers(self, idx=None):
+        """Table keys (all, or those at `idx`) as packed k-mers in the ABI's boundary layout, (n, 2) int64 on the device."""
+        lo, hi = (self.kw0, self.kw1) if idx is None else (self.kw0[idx].contiguous(), self.kw1[idx].contiguous())
+        out = torch.empty((lo.numel(), 2), dtype=torch.int64, device=self.dev)
+        capi.check(self.lib.btg_table_keys_to_kmers_dev(lo.data_ptr(), hi.data_ptr(), lo.numel(), out.data_ptr(), self.stream), self.lib)
+        return out

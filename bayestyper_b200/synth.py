@@ -175,6 +175,28 @@ def unique_kmers(kmers: np.ndarray):
     return s[idx], mult
 
 
+def _rev2_64(x: np.ndarray) -> np.ndarray:
+    """Reverse the order of the 32 2-bit groups of each uint64."""
+    x = ((x >> np.uint64(2)) & np.uint64(0x3333333333333333)) | ((x & np.uint64(0x3333333333333333)) << np.uint64(2))
+    x = ((x >> np.uint64(4)) & np.uint64(0x0F0F0F0F0F0F0F0F)) | ((x & np.uint64(0x0F0F0F0F0F0F0F0F)) << np.uint64(4))
+    return x.byteswap()
+
+
+def lexicographic_words(kmers: np.ndarray):
+    """(hi, lo) of V = sum_i code(nt_i) << 2*(K-1-i) for packed k-mers in the boundary layout: integer order of V is
+    the lexicographic order of the k-mer strings."""
+    pad = np.uint64(128 - 2 * K)
+    r0, r1 = _rev2_64(np.ascontiguousarray(kmers[:, 0])), _rev2_64(np.ascontiguousarray(kmers[:, 1]))
+    return r0 >> pad, (r0 << (np.uint64(64) - pad)) | (r1 >> pad)
+
+
+def kmc_order(kmers: np.ndarray) -> np.ndarray:
+    """Permutation that puts packed k-mers in the record order of a KMC database: lexicographic, A<C<G<T from
+    nucleotide 0 (external/kmc_api/kmc_file.cpp:428-515: prefix LUT over the leading nucleotides, sorted suffixes)."""
+    hi, lo = lexicographic_words(kmers)
+    return np.lexsort((lo, hi))
+
+
 def nb_counts(rng, copies: np.ndarray, mean: float, var: float) -> np.ndarray:
     """NB(mean*copies, var*copies) draws, saturated at 255 (KmerCounts.cpp:178-189)."""
     p = mean / var
@@ -195,7 +217,8 @@ def sample_kmer_counts(haplotypes: list, seed: int, mean: float, var: float, n_e
         err[:, 1] &= np.uint64((1 << (2 * K - 64)) - 1)
         uniq = np.concatenate([uniq, err])
         counts = np.concatenate([counts, np.ones(n_errors, np.uint8)])
-    return np.ascontiguousarray(uniq), np.ascontiguousarray(counts)
+    o = kmc_order(uniq)                    # a KMC database lists its records in lexicographic k-mer order
+    return np.ascontiguousarray(uniq[o]), np.ascontiguousarray(counts[o])
 
 
 # ---- configs ---------------------------------------------------------------------------------

@@ -127,7 +127,15 @@ def device_spectrum(lib, haplotypes, mean, var, seed, n_errors, dev):
         err = torch.empty((n_errors, 2), dtype=torch.int64, device=dev).random_(generator=g)
         err[:, 1] &= (1 << 46) - 1
         keys = torch.cat([keys, err]); counts = torch.cat([counts, torch.ones(n_errors, dtype=torch.uint8, device=dev)])
-    return keys.contiguous(), counts.contiguous()
+    # a KMC database lists its records in lexicographic k-mer order (kmc_file.cpp:428-515): put the spectrum in that order
+    keys = keys.contiguous()
+    k_lo = torch.empty(len(keys), dtype=torch.int64, device=dev); k_hi = torch.empty_like(k_lo)
+    torch.cuda.synchronize()
+    capi.check(lib.btg_table_keys_from_kmers_dev(keys.data_ptr(), len(keys), k_lo.data_ptr(), k_hi.data_ptr(), None), lib)
+    capi.check(lib.btg_kmer_hash(capi.ptr(np.zeros((1, 2), np.uint64)), 1, capi.ptr(np.zeros(1, np.uint64))), lib)   # library-stream sync
+    o = torch.sort(k_lo, stable=True).indices
+    o = o[torch.sort(k_hi[o], stable=True).indices]
+    return keys[o].contiguous(), counts[o].contiguous()
 
 
 def build_batch(lib, rank: int, scale: float, dev):

@@ -158,7 +158,11 @@ int btg_get_best_paths(const btg_graphs *g, uint32_t *n_paths_out, uint64_t *pat
  * streams and the table columns resident in HBM and composes these kernels (bayestyper_b200/
  * kmer_pipeline.py mirrors KmerCounter's genotype-side stages: countPathKmers, countInterclusterKmers,
  * parseSampleKmers, classifyPathKmers, include/bayesTyper/KmerCounter.hpp:61-67).
- * Table keys: the distinct path k-mers, sorted ascending as SIGNED (w1, w0) pairs.              */
+ * Table keys: the distinct path k-mers in lexicographic order of their strings (A<C<G<T from nucleotide 0) — the
+ * order of the records of a KMC database (external/kmc_api/kmc_file.cpp:428-515), so a sample's stream walks the
+ * table front to back.  A key is the k-mer as the 110-bit integer V = sum_i code(nt_i) << 2*(54-i), split into two
+ * signed 64-bit columns for sorting: key_hi = V >> 64 (46 bits) and key_lo = (V & (2^64-1)) ^ 2^63; keys ascend
+ * by (key_hi, key_lo).  btg_table_keys_{from,to}_kmers_dev convert from / to the ABI's packed k-mers.        */
 typedef struct btg_pathwalk_desc {          /* every pointer is a device pointer */
     uint32_t n_clusters;
     uint64_t n_paths;                        /* best paths of all clusters, cluster-major */
@@ -180,30 +184,35 @@ typedef struct btg_pathwalk_desc {          /* every pointer is a device pointer
  * classifyPathKmers and getHaplotypeCandidates (VariantClusterGraph.cpp:800-1135).
  * emit = 0: n_occ[p] / n_cov[p] = number of k-mer windows / (window, covered variant) pairs of path p.
  * emit = 1: with occ_off / cov_off = exclusive prefix sums of those, writes per window the canonical k-mer
- *           (key_w0, key_w1), its path and nucleotide index, and per pair (window id, variant): the
+ *           as a table key (key_lo, key_hi), its path and nucleotide index, and per pair (window id, variant): the
  *           running_variants coverage of updateVariantPathIndices (:1137-1184).
  * status[c] = 2 if a cluster exceeds the running-variant capacity.                             */
 int btg_walk_paths_dev(const btg_pathwalk_desc *d, int emit, uint32_t *n_occ, uint32_t *n_cov, const uint64_t *occ_off,
-                       const uint64_t *cov_off, int64_t *key_w0, int64_t *key_w1, uint32_t *occ_path, uint32_t *occ_nt,
+                       const uint64_t *cov_off, int64_t *key_lo, int64_t *key_hi, uint32_t *occ_path, uint32_t *occ_nt,
                        int64_t *cov_occ, uint16_t *cov_var, uint32_t *status, void *stream);
+/* packed k-mers (2 x uint64 each) <-> table key columns */
+int btg_table_keys_from_kmers_dev(const uint64_t *kmers, size_t n, int64_t *key_lo, int64_t *key_hi, void *stream);
+int btg_table_keys_to_kmers_dev(const int64_t *key_lo, const int64_t *key_hi, size_t n, uint64_t *kmers, void *stream);
 /* HaplotypeInfo::variant_allele_indices of every best path (VariantClusterGraph.cpp:983-992,1091-1098) */
 int btg_path_alleles_dev(const btg_pathwalk_desc *d, const uint64_t *cl_var_off, const uint16_t *var_nalleles,
                          const uint64_t *hapvar_off, uint16_t *hap_alleles, void *stream);
 /* Optional prefix index over the sorted keys (cf. the prefix LUT of a KMC database, external/kmc_api/kmc_file.cpp:236-290):
- * lut[b] = index of the first key whose word-1 top lut_bits bits (of 46) are >= b, b in [0, 2^lut_bits]; NULL clears.
+ * lut[b] = index of the first key whose key_hi top lut_bits bits (of 46; the first lut_bits/2 nucleotides) are >= b,
+ * b in [0, 2^lut_bits]; NULL clears.
  * Applies to the three table probes below until changed. */
 int btg_table_set_index_dev(const int64_t *lut, int lut_bits);
 /* KmerCountsHash::findKmer on a batch: index into the key arrays or -1 */
-int btg_table_lookup_dev(const int64_t *key_w0, const int64_t *key_w1, int64_t n_keys, const uint64_t *kmers, size_t n,
+int btg_table_lookup_dev(const int64_t *key_lo, const int64_t *key_hi, int64_t n_keys, const uint64_t *kmers, size_t n,
                          int64_t *idx_out, void *stream);
 /* KmerCounter::parseSampleKmers for one batch of one sample (KmerCounter.cpp:388-429): for every (k-mer, count)
- * record present in the table, counts[idx][sample] saturating-adds count (KmerCounts.cpp:178-189)          */
-int btg_table_add_sample_kmers_dev(const int64_t *key_w0, const int64_t *key_w1, int64_t n_keys, const uint64_t *kmers,
+ * record present in the table, counts[idx][sample] saturating-adds count (KmerCounts.cpp:178-189).  Any record order
+ * is accepted; the order of a KMC database (= the table's) is the fast one.                                 */
+int btg_table_add_sample_kmers_dev(const int64_t *key_lo, const int64_t *key_hi, int64_t n_keys, const uint64_t *kmers,
                                    const uint8_t *counts, size_t n, uint32_t n_samples, uint32_t sample_idx,
                                    uint8_t *table_counts, uint8_t *has_record, void *stream);
 /* KmerCounter::countInterclusterKmers for one region (KmerCounter.cpp:291-334): rolling scan, probe,
  * KmerCounts::addInterclusterMultiplicity (KmerCounts.cpp:98-118). ic = [n_keys][2] (female, male)        */
-int btg_table_scan_region_dev(const int64_t *key_w0, const int64_t *key_w1, int64_t n_keys, const char *seq, size_t len,
+int btg_table_scan_region_dev(const int64_t *key_lo, const int64_t *key_hi, int64_t n_keys, const char *seq, size_t len,
                               int is_decoy, uint32_t ploidy_female, uint32_t ploidy_male, uint8_t *ic, uint8_t *max_mult,
                               uint8_t *decoy, uint8_t *has_record, void *stream);
 

@@ -86,41 +86,83 @@ def test_haplotype_candidates_identical_to_reference(btg, name):
         assert len(set(by_id.values())) == len(by_id)
 
 
+def _sync(btg):
+    capi.check(btg.btg_kmer_hash(capi.ptr(np.zeros((1, 2), np.uint64)), 1, capi.ptr(np.zeros(1, np.uint64))), btg)  # syncs the library stream
+
+
+def _random_kmers(rng, n):
+    km = rng.integers(0, 2**64, size=(n, 2), dtype=np.uint64)
+    km[:, 1] &= np.uint64((1 << 46) - 1)
+    return km
+
+
 def test_table_lookup_and_saturation(btg):
-    """btg_table_lookup_dev / add_sample: hits, misses, duplicates saturate at 255 (KmerCounts.cpp:178-189)."""
+    """btg_table_keys_*, btg_table_lookup_dev / add_sample: key order = lexicographic k-mer order (KMC record order), hits,
+    misses, duplicates saturate at 255 (KmerCounts.cpp:178-189); with and without a prefix index, sorted and shuffled streams."""
+    from bayestyper_b200 import synth
     capi.check(btg.btg_table_set_index_dev(None, 0), btg)
     rng = np.random.default_rng(3)
-    keys = rng.integers(-2**63, 2**63 - 1, size=(5000, 2), dtype=np.int64)
-    keys[:, 1] &= (1 << 46) - 1
-    o = np.lexsort((keys[:, 0], keys[:, 1]))
-    keys = keys[o]
-    kw0 = torch.from_numpy(keys[:, 0].copy()).cuda(); kw1 = torch.from_numpy(keys[:, 1].copy()).cuda()
-    q = np.concatenate([keys[::7], rng.integers(-2**63, 2**63 - 1, size=(300, 2), dtype=np.int64)])
-    q[-300:, 1] &= (1 << 46) - 1
-    qd = torch.from_numpy(q).cuda()
+    km = _random_kmers(rng, 5000)
+    km = km[synth.kmc_order(km)]                                            # the order a KMC database lists them in
+    kmd = torch.from_numpy(km.view(np.int64)).cuda()
+    kw0 = torch.empty(len(km), dtype=torch.int64, device="cuda"); kw1 = torch.empty_like(kw0)
+    torch.cuda.synchronize()
+    capi.check(btg.btg_table_keys_from_kmers_dev(kmd.data_ptr(), len(km), kw0.data_ptr(), kw1.data_ptr(), None), btg)
+    _sync(btg)
+    lo, hi = kw0.cpu().numpy(), kw1.cpu().numpy()
+    assert (np.lexsort((lo, hi)) == np.arange(len(km))).all(), "table key order is not the lexicographic k-mer order"
+    ehi, elo = synth.lexicographic_words(km)
+    assert (hi.view(np.uint64) == ehi).all() and ((lo.view(np.uint64) ^ np.uint64(1 << 63)) == elo).all()
+    back = torch.empty_like(kmd)
+    capi.check(btg.btg_table_keys_to_kmers_dev(kw0.data_ptr(), kw1.data_ptr(), len(km), back.data_ptr(), None), btg)
+    _sync(btg)
+    assert (back.cpu().numpy().view(np.uint64) == km).all()
+    q = np.concatenate([km[::7], _random_kmers(rng, 300)])
+    qd = torch.from_numpy(q.view(np.int64)).cuda()
     idx = torch.zeros(len(q), dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()
-    capi.check(btg.btg_table_lookup_dev(kw0.data_ptr(), kw1.data_ptr(), len(keys), qd.data_ptr(), len(q), idx.data_ptr(), None), btg)
-    exp = np.concatenate([np.arange(0, len(keys), 7), -np.ones(300, np.int64)])
-    capi.check(btg.btg_kmer_hash(capi.ptr(np.zeros((1, 2), np.uint64)), 1, capi.ptr(np.zeros(1, np.uint64))), btg)  # syncs the library stream
+    capi.check(btg.btg_table_lookup_dev(kw0.data_ptr(), kw1.data_ptr(), len(km), qd.data_ptr(), len(q), idx.data_ptr(), None), btg)
+    exp = np.concatenate([np.arange(0, len(km), 7), -np.ones(300, np.int64)])
+    _sync(btg)
     assert (idx.cpu().numpy() == exp).all()
-    counts = torch.zeros((len(keys), 3), dtype=torch.uint8, device="cuda")
-    rec = torch.zeros(len(keys), dtype=torch.uint8, device="cuda")
-    dup = torch.from_numpy(np.concatenate([keys[:10]] * 3)).cuda()          # each of 10 k-mers three times
-    cts = torch.full((30,), 100, dtype=torch.uint8, device="cuda")
-    torch.cuda.synchronize()
-    capi.check(btg.btg_table_add_sample_kmers_dev(kw0.data_ptr(), kw1.data_ptr(), len(keys), dup.data_ptr(), cts.data_ptr(), 30, 3, 1, counts.data_ptr(), rec.data_ptr(), None), btg)
-    capi.check(btg.btg_kmer_hash(capi.ptr(np.zeros((1, 2), np.uint64)), 1, capi.ptr(np.zeros(1, np.uint64))), btg)
-    c = counts.cpu().numpy()
-    # same probes through a prefix index
+
+    def stream(records, cts, n_samples, sample, use_lut_bits):
+        counts = torch.zeros((len(km), n_samples), dtype=torch.uint8, device="cuda")
+        rec = torch.zeros(len(km), dtype=torch.uint8, device="cuda")
+        rd = torch.from_numpy(records.view(np.int64)).cuda(); cd_ = torch.from_numpy(cts).cuda()
+        lut_d = None
+        if use_lut_bits:
+            lut = np.concatenate([[0], np.cumsum(np.bincount(hi >> (46 - use_lut_bits), minlength=1 << use_lut_bits))]).astype(np.int64)
+            lut_d = torch.from_numpy(lut).cuda()
+        torch.cuda.synchronize()
+        capi.check(btg.btg_table_set_index_dev(lut_d.data_ptr() if use_lut_bits else None, use_lut_bits), btg)
+        capi.check(btg.btg_table_add_sample_kmers_dev(kw0.data_ptr(), kw1.data_ptr(), len(km), rd.data_ptr(), cd_.data_ptr(), len(cts), n_samples, sample,
+                                                      counts.data_ptr(), rec.data_ptr(), None), btg)
+        _sync(btg)
+        capi.check(btg.btg_table_set_index_dev(None, 0), btg)
+        return counts.cpu().numpy(), rec.cpu().numpy()
+
+    dup = np.concatenate([km[:10]] * 3)                                      # each of 10 k-mers three times
+    for bits in (0, 4, 10, 16):                                              # no index / long buckets (binary search) / short buckets (linear)
+        c, r = stream(dup, np.full(30, 100, np.uint8), 3, 1, bits)
+        assert (c[:10, 1] == 255).all() and c[:10, [0, 2]].sum() == 0 and c[10:].sum() == 0
+        assert r[:10].all() and not r[10:].any()
+    # a whole "database": every third key present + misses, KMC-ordered and shuffled, ragged length (not a multiple of the batch)
+    recs = np.concatenate([km[::3], _random_kmers(rng, 2001)])
+    cts = rng.integers(1, 255, size=len(recs)).astype(np.uint8)
+    expc = np.zeros(len(km), np.uint8); expc[::3] = cts[:len(km[::3])]
+    o = synth.kmc_order(recs)
+    for order in (o, rng.permutation(len(recs))):
+        for bits in (0, 12):
+            c, r = stream(np.ascontiguousarray(recs[order]), np.ascontiguousarray(cts[order]), 1, 0, bits)
+            assert (c[:, 0] == expc).all() and (r == (expc > 0)).all()
+    # through a prefix index: lookups
     bits = 10
-    lut = np.concatenate([[0], np.cumsum(np.bincount(keys[:, 1] >> (46 - bits), minlength=1 << bits))]).astype(np.int64)
+    lut = np.concatenate([[0], np.cumsum(np.bincount(hi >> (46 - bits), minlength=1 << bits))]).astype(np.int64)
     lut_d = torch.from_numpy(lut).cuda(); idx2 = torch.zeros(len(q), dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()
     capi.check(btg.btg_table_set_index_dev(lut_d.data_ptr(), bits), btg)
-    capi.check(btg.btg_table_lookup_dev(kw0.data_ptr(), kw1.data_ptr(), len(keys), qd.data_ptr(), len(q), idx2.data_ptr(), None), btg)
-    capi.check(btg.btg_kmer_hash(capi.ptr(np.zeros((1, 2), np.uint64)), 1, capi.ptr(np.zeros(1, np.uint64))), btg)
+    capi.check(btg.btg_table_lookup_dev(kw0.data_ptr(), kw1.data_ptr(), len(km), qd.data_ptr(), len(q), idx2.data_ptr(), None), btg)
+    _sync(btg)
     capi.check(btg.btg_table_set_index_dev(None, 0), btg)
     assert (idx2.cpu().numpy() == exp).all()
-    assert (c[:10, 1] == 255).all() and c[:10, [0, 2]].sum() == 0 and c[10:].sum() == 0
-    assert rec.cpu().numpy()[:10].all() and not rec.cpu().numpy()[10:].any()
