@@ -71,6 +71,18 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_host(force: bool = False) -> Path:
+    """g++ build of the C++ host program over the C ABI (host/btgenotype.cpp, include/btgpu.hpp)."""
+    src = ROOT / "host" / "btgenotype.cpp"
+    exe = ROOT / "host" / "btgenotype"
+    deps = [src, ROOT / "include" / "btgpu.hpp", ROOT / "include" / "btgpu.h", LIB]
+    if not force and _newer(exe, deps):
+        return exe
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I", str(ROOT / "include"), str(src), "-L", str(LIBDIR), "-lbtgpu",
+                           "-Wl,-rpath,$ORIGIN/../bayestyper_b200/lib", "-o", str(exe)])
+    return exe
+
+
 def build_oracle(force: bool = False) -> Path:
     """gcc build of the CPU restatement (test infrastructure; see oracle/README.md)."""
     odir = ROOT / "oracle"
@@ -81,4 +93,5 @@ def build_oracle(force: bool = False) -> Path:
 if __name__ == "__main__":
     v = "-v" in sys.argv
     print(build_lib(force="-f" in sys.argv, verbose=v))
+    print(build_host())
     print(build_oracle())

@@ -38,3 +38,10 @@ def bind(L):
     L.btg_table_keys_from_kmers_dev.argtypes = [vp, C.c_size_t, vp, vp, vp]
     L.btg_table_keys_to_kmers_dev.argtypes = [vp, vp, C.c_size_t, vp, vp]
     L.btg_estimate_noise_and_genotypes.argtypes = [vp, vp, vp, vp, vp]
+    L.btg_comm_create.restype = vp
+    L.btg_comm_create.argtypes = [C.c_uint32, C.c_uint32, vp]
+    L.btg_comm_connect.argtypes = [vp, vp]
+    L.btg_comm_free.argtypes = [vp]
+    L.btg_comm_free.restype = None
+    L.btg_estimate_noise_sharded.argtypes = [vp, vp, vp, vp, vp]
+    L.btg_estimate_noise_and_genotypes_sharded.argtypes = [vp, vp, vp, vp, vp, vp]

@@ -31,6 +31,7 @@
 
 #include "common.cuh"
 #include "gibbs_rng.cuh"
+#include "comm.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -227,7 +228,8 @@ __host__ __device__ inline ArenaSizes arena_sizes(uint32_t S, uint32_t H, uint32
           + n_multi * 2ull         /* multicluster k-mer order, subset */
           + 32;                    /* misc + rng states */
     a.u8 = (uint64_t)H + K + S     /* non-zero flags, uncovered rows, stats-cache update flags */
-         + (uint64_t)n_multi * S;  /* sample_multicluster_kmer_multiplicities */
+         + (uint64_t)n_multi * S   /* sample_multicluster_kmer_multiplicities */
+         + (uint64_t)n_uniq * (H + S + 2);  /* k-mer tile of the current subsample: multiplicities, counts, (F, M) inter-cluster multiplicity */
     a.u8 = (a.u8 + 7) & ~7ull;
     return a;
 }
@@ -244,7 +246,7 @@ struct Cl {
     const uint8_t *M;
     LaneArr<double> freq, logf, simplex, simplex_tab, ucache, cum, kc_f, as_f, mcache, fmisc;
     LaneArr<uint32_t> obs, uniq, uniq_sub, cnt, tally, kc_n, as_n, dipl, multi, multi_sub, misc;
-    LaneArr<uint8_t> nz, uncovered, stats_update, sample_multi;
+    LaneArr<uint8_t> nz, uncovered, stats_update, sample_multi, tile_m, tile_c, tile_ic;
 
     __device__ void bind(const DevUnit &du, uint32_t cluster) {
         u = &du; c = cluster;
@@ -291,7 +293,19 @@ struct Cl {
         nz = b; b = b + SL.H;
         uncovered = b; b = b + SL.K;
         stats_update = b; b = b + S;
-        sample_multi = b;
+        sample_multi = b; b = b + (uint64_t)SL.n_multi * S;
+        tile_m = b; b = b + (uint64_t)SL.n_uniq * SL.H;
+        tile_c = b; b = b + (uint64_t)SL.n_uniq * S;
+        tile_ic = b;
+    }
+    // k-mer tile (lock-step modes, where the diplotype caches are cleared every iteration): row i holds everything the
+    // likelihood reads about the i-th k-mer of the current subsample, so the per-iteration gathers touch three compact
+    // lane-interleaved byte arrays instead of five scattered unit arrays
+    __device__ __forceinline__ uint8_t tileDiplMult(uint32_t i, uint32_t a, uint32_t b) const {
+        uint8_t r = 0;
+        if (a != NONE) r += tile_m[i * H + a];
+        if (b != NONE) r += tile_m[i * H + b];
+        return r;
     }
     __device__ __forceinline__ uint8_t m(uint32_t k, uint32_t h) const { return M[(size_t)k * H + h]; }
     __device__ __forceinline__ uint8_t count(uint32_t k, uint32_t s) const { return u->k_has_counts[row0 + k] ? u->k_counts[(row0 + k) * S + s] : 0; }
@@ -404,7 +418,7 @@ __device__ bool cl_is_max_hap_var_kmer(Cl &cl, uint32_t k, uint32_t max_kmers) {
 }
 
 // VariantClusterGenotyper::reset + VariantClusterHaplotypes::sampleKmerSubset (…Genotyper.cpp:113-129, …Haplotypes.cpp:110-157)
-template <bool MC = false>
+template <bool MC = false, bool TILE = false>
 __device__ void cl_reset(Cl &cl, const btg_gibbs_opts &o, Philox &prng) {
     const double rate = (double)o.kmer_subsampling_rate;
     for (uint32_t i = 0; i < cl.H * cl.nvar; i++) cl.cnt[i] = 0;
@@ -419,6 +433,16 @@ __device__ void cl_reset(Cl &cl, const btg_gibbs_opts &o, Philox &prng) {
             if (!cl_is_max_hap_var_kmer(cl, k, o.max_haplotype_variant_kmers)) cl.uniq_sub[n_sub++] = k;
     }
     cl.misc[kNSub] = n_sub;
+    if constexpr (TILE) {
+        for (uint32_t i = 0; i < n_sub; i++) {
+            const uint32_t k = cl.uniq_sub[i];
+            const bool has = cl.u->k_has_counts[cl.row0 + k];
+            for (uint32_t h = 0; h < cl.H; h++) cl.tile_m[i * cl.H + h] = cl.m(k, h);
+            for (uint32_t s = 0; s < cl.S; s++) cl.tile_c[i * cl.S + s] = has ? cl.u->k_counts[(cl.row0 + k) * cl.S + s] : 0;
+            cl.tile_ic[i * 2] = has ? cl.u->k_ic[(cl.row0 + k) * 2] : 0;
+            cl.tile_ic[i * 2 + 1] = has ? cl.u->k_ic[(cl.row0 + k) * 2 + 1] : 0;
+        }
+    }
     for (uint32_t s = 0; s < cl.S; s++) cl.stats_update[s] = 1;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     for (uint32_t i = 0; i < cl.S * cl.Dall; i++) cl.ucache[i] = nan;  // clear the per-sample diplotype caches
@@ -490,7 +514,7 @@ __device__ void cl_update_multi_multiplicities(Cl &cl, uint32_t s, uint32_t prev
 }
 
 // VariantClusterGenotyper::calcDiplotypeLogProb (VariantClusterGenotyper.cpp:597-666)
-template <bool MC = false>
+template <bool MC = false, bool TILE = false>
 __device__ double cl_dipl_log_prob(Cl &cl, const Tables &T, uint32_t s, uint32_t a, uint32_t b) {
     double lp = 0;  // logf[] = log(freq[]) of this iteration (cl_sample_diplotypes)
     if (b == NONE) lp += cl.logf[a];
@@ -501,9 +525,15 @@ __device__ double cl_dipl_log_prob(Cl &cl, const Tables &T, uint32_t s, uint32_t
     if (acc != acc) {  // not cached yet
         acc = 0;
         const uint32_t n_sub = cl.misc[kNSub];
-        for (uint32_t i = 0; i < n_sub; i++) {
-            const uint32_t k = cl.uniq_sub[i];
-            acc += T.logProb(s, (uint8_t)(cl.diplMult(k, a, b) + cl.ic(k, s)), cl.count(k, s));
+        if constexpr (TILE) {
+            const uint32_t g = cl.u->sample_gender[s];
+            for (uint32_t i = 0; i < n_sub; i++)
+                acc += T.logProb(s, (uint8_t)(cl.tileDiplMult(i, a, b) + cl.tile_ic[i * 2 + g]), cl.tile_c[i * cl.S + s]);
+        } else {
+            for (uint32_t i = 0; i < n_sub; i++) {
+                const uint32_t k = cl.uniq_sub[i];
+                acc += T.logProb(s, (uint8_t)(cl.diplMult(k, a, b) + cl.ic(k, s)), cl.count(k, s));
+            }
         }
         cl.ucache[ci] = acc;
     }
@@ -533,7 +563,7 @@ __device__ __forceinline__ void cl_increment(Cl &cl, uint32_t h) {  // Haplotype
 }
 
 // VariantClusterGenotyper::sampleDiplotype (VariantClusterGenotyper.cpp:707-755) + LogDiscreteSampler (DiscreteSampler.cpp:106-126)
-template <bool MC = false>
+template <bool MC = false, bool TILE = false>
 __device__ void cl_sample_diplotype(Cl &cl, const Tables &T, uint32_t s, uint8_t ploidy, Philox &prng) {
     uint32_t n = 0;
     double run = 0;
@@ -543,7 +573,7 @@ __device__ void cl_sample_diplotype(Cl &cl, const Tables &T, uint32_t s, uint8_t
             if (!cl.nz[a]) continue;
             for (uint32_t b = a; b < H; b++) {
                 if (!cl.nz[b]) continue;
-                const double lp = cl_dipl_log_prob<MC>(cl, T, s, a, b);
+                const double lp = cl_dipl_log_prob<MC, TILE>(cl, T, s, a, b);
                 run = n == 0 ? lp : logAddition(lp, run);
                 cl.cum[n++] = run;
             }
@@ -551,7 +581,7 @@ __device__ void cl_sample_diplotype(Cl &cl, const Tables &T, uint32_t s, uint8_t
     } else if (ploidy == 1) {
         for (uint32_t a = 0; a < H; a++) {
             if (!cl.nz[a]) continue;
-            const double lp = cl_dipl_log_prob<MC>(cl, T, s, a, NONE);
+            const double lp = cl_dipl_log_prob<MC, TILE>(cl, T, s, a, NONE);
             run = n == 0 ? lp : logAddition(lp, run);
             cl.cum[n++] = run;
         }
@@ -653,13 +683,13 @@ __device__ void cl_update_allele_stats(Cl &cl) {
 }
 
 // VariantClusterGenotyper::sampleDiplotypes (VariantClusterGenotyper.cpp:668-705)
-template <bool MC = false>
+template <bool MC = false, bool TILE = false>
 __device__ void cl_sample_diplotypes(Cl &cl, const Tables &T, const uint8_t *ploidy, bool collect, Philox &prng) {
     for (uint32_t h = 0; h < cl.H; h++) if (cl.nz[h]) cl.logf[h] = log(cl.freq[h]);  // one log per haplotype per iteration
     for (uint32_t s = 0; s < cl.S; s++) {
         const uint32_t prev = cl.dipl[s];
         if constexpr (MC) { if (cl.misc[kUseMulti]) cl_update_multi_log_prob(cl, T, s); }
-        cl_sample_diplotype<MC>(cl, T, s, ploidy[s], prng);
+        cl_sample_diplotype<MC, TILE>(cl, T, s, ploidy[s], prng);
         if constexpr (MC) cl_update_multi_multiplicities(cl, s, prev);
         else if (cl.dipl[s] != prev) cl.stats_update[s] = 1;  // …Haplotypes.cpp:199-201
         if (collect) {
@@ -861,26 +891,33 @@ __device__ void cl_summarise(Cl &cl, const btg_gibbs_opts &o, const uint8_t *plo
 
 // InferenceEngine::estimateGenotypesCallback (InferenceEngine.cpp:278-333): one thread = one group, all chains
 template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(64, MIN_BLOCKS) k_estimate_genotypes(DevUnit du, Tables T, btg_gibbs_opts o, ResultView R) {
+__global__ void __launch_bounds__(64, MIN_BLOCKS) k_estimate_genotypes(DevUnit du, Tables T, btg_gibbs_opts o, ResultView R, int reconverge) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= du.n_regular) return;
+    // no early return: every lane of the warp reaches the __syncwarp()s below.  The 32 clusters of a warp are neighbours in the
+    // cost order and do nearly the same work per iteration, but data-dependent branches (rejection loops, sparse / dense
+    // frequency draws, 2 or 3 live diplotypes) let the lanes drift apart, and without a reconvergence point at the loop
+    // back-edges they never meet again (18 of 32 lanes active in profiles/r1b_gibbs_ncu_full.txt)
+    const bool live = i < du.n_regular;
     Cl cl;
-    cl.bind(du, du.order[i]);
+    cl.bind(du, du.order[live ? i : 0]);
     const uint64_t gidx = o.group_index_base + cl.g;
     const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
-    cl_construct(cl, o, gidx, 0);
     Philox prng, fr;
     prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, 0);
     fr.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngFrequency, 0);
+    if (live) cl_construct(cl, o, gidx, 0);
     for (uint32_t chain = 0; chain < o.n_chains; chain++) {
-        cl_reset(cl, o, prng);
+        if (live) cl_reset(cl, o, prng);
+        if (reconverge) __syncwarp();
         const uint32_t iters = (uint32_t)o.gibbs_burn_in + o.gibbs_samples;
         for (uint32_t it = 0; it < iters; it++) {
-            cl_sample_diplotypes(cl, T, ploidy, it >= o.gibbs_burn_in, prng);
-            cl_sample_frequencies(cl, fr);
+            if (live) cl_sample_diplotypes(cl, T, ploidy, it >= o.gibbs_burn_in, prng);
+            if (reconverge) __syncwarp();
+            if (live) cl_sample_frequencies(cl, fr);
+            if (reconverge) __syncwarp();
         }
     }
-    cl_summarise(cl, o, ploidy, R);
+    if (live) cl_summarise(cl, o, ploidy, R);
 }
 
 
@@ -1058,7 +1095,29 @@ struct NoiseState {
     double *trace;         // rows of (chain, iteration, rates...) or nullptr
     uint32_t *rng;         // persisted Philox state of CountDistribution::prng (kind 4)
     uint32_t *trace_row;
+    const double *lg;      // lg[i] = lgamma((double)i), i < n_lg (the Poisson rows need lgamma(count + 1) of integers only)
+    uint32_t n_lg;
 };
+
+// noiseCountLogPmf with log(rate) hoisted and lgamma of the integer argument read from the table (same values, same order of
+// operations as poissonLogProb: value * log(rate) - rate - lgamma(value + 1))
+__device__ __forceinline__ double poissonLogProbT(uint32_t value, double rate, double log_rate, const double *lg, uint32_t n_lg) {
+    return value * log_rate - rate - (value + 1 < n_lg ? lg[value + 1] : lgamma((double)(value + 1)));
+}
+__device__ double noiseCountLogPmfT(double rate, double log_rate, uint32_t c, const double *lg, uint32_t n_lg) {
+    double v = poissonLogProbT(c, rate, log_rate, lg, n_lg);
+    if (c == 255) {
+        uint32_t limit = c;
+        double prev;
+        do {
+            limit++;
+            prev = v;
+            v = logAddition(v, poissonLogProbT(limit, rate, log_rate, lg, n_lg));
+            if (v > 0) { v = 0; break; }
+        } while (!doubleCompare(prev, v));
+    }
+    return v;
+}
 
 // CountDistribution::sampleNoiseParameters / resetNoiseRates + updateNoiseCache, on the device so that the
 // iteration loop never synchronises with the host.  mode 0: reset from the prior; 1: posterior draw from hist;
@@ -1096,7 +1155,14 @@ __device__ void noise_update_block(const NoiseState &ns, uint32_t S, float prior
         }
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < S * 256u; i += blockDim.x) ns.noise_table[i] = noiseCountLogPmf(sh_rates[i >> 8], i & 255u);
+    if (ns.lg) {
+        __shared__ double sh_log_rates[BTG_MAX_SAMPLES];
+        if (threadIdx.x < S) sh_log_rates[threadIdx.x] = log(sh_rates[threadIdx.x]);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < S * 256u; i += blockDim.x) ns.noise_table[i] = noiseCountLogPmfT(sh_rates[i >> 8], sh_log_rates[i >> 8], i & 255u, ns.lg, ns.n_lg);
+    } else {
+        for (uint32_t i = threadIdx.x; i < S * 256u; i += blockDim.x) ns.noise_table[i] = noiseCountLogPmf(sh_rates[i >> 8], i & 255u);
+    }
 }
 
 __global__ void k_noise_update(NoiseState ns, uint32_t S, float prior_shape, float prior_scale, uint32_t seed, int mode, int accumulate,
@@ -1109,26 +1175,27 @@ __global__ void k_noise_update(NoiseState ns, uint32_t S, float prior_shape, flo
 // entry e of the enumeration goes to lane e % 32, which sums over the k-mer subset in the same order as the
 // sequential code (so the cached value is bit-identical).  Used for large clusters in the lock-step noise chain,
 // where the slowest cluster sets the pace of every iteration.
-__device__ void cl_fill_cache_warp(Cl &cl, const Tables &T, const uint8_t *ploidy, uint32_t lane) {
+// A cluster may be shared by `parts` warps (anywhere in the grid): entries are dealt to them in rounds of 32.
+__device__ void cl_fill_cache_warp(Cl &cl, const Tables &T, const uint8_t *ploidy, uint32_t lane, uint32_t part, uint32_t parts) {
     const uint32_t H = cl.H, n_sub = cl.misc[kNSub];
+    uint32_t e = 0;
     for (uint32_t s = 0; s < cl.S; s++) {
         const uint8_t pl = ploidy[s];
         if (pl == 0) continue;
-        uint32_t e = 0;
         for (uint32_t a = 0; a < H; a++) {
             if (!cl.nz[a]) continue;
             const uint32_t b_end = pl == 2 ? H : a + 1;
             for (uint32_t b = a; b < b_end; b++) {
                 if (pl == 2 && !cl.nz[b]) continue;
-                if ((e++ & 31u) != lane) continue;
+                const uint32_t mine = e++;
+                if ((mine & 31u) != lane || ((mine >> 5) % parts) != part) continue;
                 const uint32_t bb = pl == 2 ? b : NONE;
                 const size_t ci = (size_t)s * cl.Dall + cl.slot(a, bb == NONE ? H : bb);
                 if (cl.ucache[ci] == cl.ucache[ci]) continue;  // already cached
                 double acc = 0;
-                for (uint32_t i = 0; i < n_sub; i++) {
-                    const uint32_t k = cl.uniq_sub[i];
-                    acc += T.logProb(s, (uint8_t)(cl.diplMult(k, a, bb) + cl.ic(k, s)), cl.count(k, s));
-                }
+                const uint32_t g = cl.u->sample_gender[s];
+                for (uint32_t i = 0; i < n_sub; i++)
+                    acc += T.logProb(s, (uint8_t)(cl.tileDiplMult(i, a, bb) + cl.tile_ic[i * 2 + g]), cl.tile_c[i * cl.S + s]);
                 cl.ucache[ci] = acc;
             }
         }
@@ -1142,7 +1209,7 @@ __device__ void noise_iteration_thread(Cl &cl, const DevUnit &du, const Tables &
     Philox prng, fr;
     prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
     fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
-    cl_sample_diplotypes(cl, T, ploidy, collect, prng);
+    cl_sample_diplotypes<false, true>(cl, T, ploidy, collect, prng);
     cl_sample_frequencies(cl, fr);
     prng.save(cl.misc, kRng0);
     fr.save(cl.misc, kRng1);
@@ -1156,8 +1223,10 @@ __device__ void noise_iteration_thread(Cl &cl, const DevUnit &du, const Tables &
 // joint = 1: estimateNoiseAndGenotypes (InferenceEngine.cpp:384-472): genotypers are constructed in the first chain only and
 //            persist (streams of chain 0), samples are collected after the burn-in
 __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg_gibbs_opts o, const uint32_t *sel, uint32_t n_sel, uint32_t n_big, uint32_t chain,
-                                                       uint32_t iters, NoiseState ns, float prior_shape, float prior_scale, unsigned long long *hist, int joint) {
+                                                       uint32_t iters, NoiseState ns, float prior_shape, float prior_scale, unsigned long long *hist, int joint,
+                                                       PeerExchange px, const uint32_t *fill_tasks, uint32_t n_fill_tasks) {
     cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned long long sh_tot[kMailRow];
     __shared__ double sh_rates[BTG_MAX_SAMPLES];
     // getNoiseCounts of the block's clusters: only (n_obs, sum) per sample are ever read from the merged CountAllocation,
     // so they are summed in shared memory and leave the block as <= 2S global atomics per iteration
@@ -1177,7 +1246,7 @@ __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg
             prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
             fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
         }
-        cl_reset(cl, o, prng);
+        cl_reset<false, true>(cl, o, prng);
         prng.save(cl.misc, kRng0);
         fr.save(cl.misc, kRng1);
     }
@@ -1187,24 +1256,29 @@ __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg
     for (uint32_t it = 1; it <= iters; it++) {
         if (threadIdx.x < 2 * du.S) sh_stat[threadIdx.x] = 0;
         __syncthreads();
-        // sel[0 .. n_big): large clusters, one WARP each (cooperative cache fill, counts and cache clear; lane 0 samples)
+        // phase A: the diplotype caches of the large clusters sel[0 .. n_big) are filled by the whole grid: fill task t =
+        // (cluster, part, parts) gives one warp every parts-th round of 32 cache entries of that cluster, so the slowest
+        // cluster no longer sets the pace of the iteration with a single warp
+        for (uint32_t t = tid >> 5; t < n_fill_tasks; t += nthreads >> 5) {
+            Cl cl;
+            cl.bind(du, sel[fill_tasks[3 * t]]);
+            cl_fill_cache_warp(cl, T, du.group_ploidy + (size_t)cl.g * du.S, tid & 31u, fill_tasks[3 * t + 1], fill_tasks[3 * t + 2]);
+        }
+        if (n_fill_tasks) { __threadfence(); grid.sync(); }
+        // phase B: sel[0 .. n_big): one WARP each (lane 0 samples from the filled cache; counts and cache clear by all lanes)
         for (uint32_t i = tid >> 5; i < n_big; i += nthreads >> 5) {
             const uint32_t lane = tid & 31u;
             Cl cl;
             cl.bind(du, sel[i]);
-            const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
-            cl_fill_cache_warp(cl, T, ploidy, lane);
-            __syncwarp();
             if (lane == 0) noise_iteration_thread(cl, du, T, o, joint && it > o.gibbs_burn_in);
             __syncwarp();
             const uint32_t n_sub = cl.misc[kNSub];
             for (uint32_t s = 0; s < cl.S; s++) {  // getNoiseCounts
                 const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
                 uint32_t n0 = 0, c0 = 0;
-                for (uint32_t j = lane; j < n_sub; j += 32) {
-                    const uint32_t k = cl.uniq_sub[j];
-                    if ((uint8_t)(cl.diplMult(k, da, db) + cl.ic(k, s)) == 0) { n0++; c0 += cl.count(k, s); }
-                }
+                const uint32_t g = du.sample_gender[s];
+                for (uint32_t j = lane; j < n_sub; j += 32)
+                    if ((uint8_t)(cl.tileDiplMult(j, da, db) + cl.tile_ic[j * 2 + g]) == 0) { n0++; c0 += cl.tile_c[j * cl.S + s]; }
                 if (n0) { atomicAdd(sh_stat + 2 * s, (unsigned long long)n0); atomicAdd(sh_stat + 2 * s + 1, (unsigned long long)c0); }
             }
             for (uint32_t j = lane; j < cl.S * cl.Dall; j += 32) cl.ucache[j] = nan;  // clearGenotyperCache
@@ -1219,10 +1293,9 @@ __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg
             for (uint32_t s = 0; s < cl.S; s++) {  // getNoiseCounts
                 const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
                 uint32_t n0 = 0, c0 = 0;
-                for (uint32_t j = 0; j < n_sub; j++) {
-                    const uint32_t k = cl.uniq_sub[j];
-                    if ((uint8_t)(cl.diplMult(k, da, db) + cl.ic(k, s)) == 0) { n0++; c0 += cl.count(k, s); }
-                }
+                const uint32_t g = du.sample_gender[s];
+                for (uint32_t j = 0; j < n_sub; j++)
+                    if ((uint8_t)(cl.tileDiplMult(j, da, db) + cl.tile_ic[j * 2 + g]) == 0) { n0++; c0 += cl.tile_c[j * cl.S + s]; }
                 if (n0) { atomicAdd(sh_stat + 2 * s, (unsigned long long)n0); atomicAdd(sh_stat + 2 * s + 1, (unsigned long long)c0); }
             }
             for (uint32_t j = 0; j < cl.S * cl.Dall; j++) cl.ucache[j] = nan;  // clearGenotyperCache
@@ -1231,7 +1304,15 @@ __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg
         if (threadIdx.x < 2 * du.S && sh_stat[threadIdx.x]) atomicAdd(hist + threadIdx.x, sh_stat[threadIdx.x]);
         __threadfence();
         grid.sync();
-        if (blockIdx.x == 0) noise_update_block(ns, du.S, prior_shape, prior_scale, o.random_seed, 1, o.gibbs_burn_in < it, (double)chain, (double)it, 1, sh_rates);
+        if (blockIdx.x == 0) {
+            if (px.world > 1) {  // sharded unit: add up the ranks' statistics over peer memory (comm.cuh) before the draw
+                if (threadIdx.x < 2 * du.S) sh_tot[threadIdx.x] = hist[threadIdx.x];
+                peer_allreduce_block(px, px.seq0 + it, sh_tot, 2 * du.S);
+                if (threadIdx.x < 2 * du.S) hist[threadIdx.x] = sh_tot[threadIdx.x];
+                __syncthreads();
+            }
+            noise_update_block(ns, du.S, prior_shape, prior_scale, o.random_seed, 1, o.gibbs_burn_in < it, (double)chain, (double)it, 1, sh_rates);
+        }
         __threadfence();
         grid.sync();
     }
@@ -1602,10 +1683,11 @@ int btg_estimate_genotypes_async(btg_unit *u, const btg_count_dist *cd, const bt
     }
     if (u->du.n_regular) {
         static const int occ = getenv("BTG_GIBBS_OCC") ? atoi(getenv("BTG_GIBBS_OCC")) : 8;
+        const int reconverge = getenv("BTG_GIBBS_SYNC") ? atoi(getenv("BTG_GIBBS_SYNC")) : 1;
         const unsigned grid = (u->du.n_regular + 63) / 64;
-        if (occ >= 16) k_estimate_genotypes<16><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R);
-        else if (occ >= 12) k_estimate_genotypes<12><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R);
-        else k_estimate_genotypes<8><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R);
+        if (occ >= 16) k_estimate_genotypes<16><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R, reconverge);
+        else if (occ >= 12) k_estimate_genotypes<12><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R, reconverge);
+        else k_estimate_genotypes<8><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R, reconverge);
         BTG_LAUNCHED();
         BTG_CUDA(cudaGetLastError());
     }
@@ -1659,15 +1741,24 @@ int btg_unit_cluster_tally(const btg_unit *u, uint32_t cluster, uint32_t *tally_
     return BTG_OK;
 }
 
-static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, double *trace_out, int joint);
+static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, double *trace_out, int joint);
 
 int btg_estimate_noise(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, double *trace_out) {
-    return noise_chains(u, cd, opts, trace_out, 0);
+    return noise_chains(u, cd, opts, nullptr, trace_out, 0);
+}
+
+int btg_estimate_noise_sharded(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, double *trace_out) {
+    return noise_chains(u, cd, opts, sh, trace_out, 0);
 }
 
 int btg_estimate_noise_and_genotypes(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, btg_genotype_result *out, double *trace_out) {
+    return btg_estimate_noise_and_genotypes_sharded(u, cd, opts, nullptr, out, trace_out);
+}
+
+int btg_estimate_noise_and_genotypes_sharded(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, btg_genotype_result *out,
+                                             double *trace_out) {
     if (!out) { set_error("null argument"); return BTG_EINVAL; }
-    int rc = noise_chains(u, cd, opts, trace_out, 1);
+    int rc = noise_chains(u, cd, opts, sh, trace_out, 1);
     if (rc != BTG_OK) return rc;
     DevResult *dr = unit_result(u);
     if (!dr) { set_error("result allocation failed"); return BTG_ENOMEM; }
@@ -1679,9 +1770,17 @@ int btg_estimate_noise_and_genotypes(btg_unit *u, btg_count_dist *cd, const btg_
     return btg_unit_download_result(u, out, nullptr);
 }
 
-static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, double *trace_out, int joint) {
+static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, double *trace_out, int joint) {
     BTG_REQUIRE_INIT();
     if (!u || !cd || !opts) { set_error("null argument"); return BTG_EINVAL; }
+    btg_comm *comm = sh ? sh->comm : nullptr;
+    const uint32_t world = comm ? comm->world : 1;
+    if (sh && (!sh->group_n_clusters || !sh->group_n_variants || opts->group_index_base + u->du.G > sh->n_groups_total)) {
+        set_error("bad shard descriptor: this rank's groups [%llu, %llu) do not fit the %llu groups of the unit", (unsigned long long)opts->group_index_base,
+                  (unsigned long long)(opts->group_index_base + u->du.G), (unsigned long long)(sh ? sh->n_groups_total : 0));
+        return BTG_EINVAL;
+    }
+    if (comm && !comm->connected) { set_error("communicator is not connected (btg_comm_connect)"); return BTG_ESTATE; }
     if (cd->S != u->du.S) { set_error("count distribution / unit sample mismatch"); return BTG_EINVAL; }
     const uint32_t S = u->du.S, G = u->du.G;
     if (joint && u->du.n_nested_groups) { set_error("the joint noise-genotyping mode does not support nested variant-cluster groups in this build (%u groups)", u->du.n_nested_groups); return BTG_EINVAL; }
@@ -1690,7 +1789,8 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
     auto s = ctx().stream;
     NoiseState ns{};
     unsigned long long *hist = nullptr;
-    uint32_t *d_sel = nullptr;
+    uint32_t *d_sel = nullptr, *d_tasks = nullptr;
+    size_t tasks_cap = 0;
     std::vector<void *> tmp;
     auto dalloc = [&](size_t bytes) { void *p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 8) != cudaSuccess) return (void *)nullptr; tmp.push_back(p); cudaMemsetAsync(p, 0, bytes ? bytes : 8, s); return p; };
     hist = (unsigned long long *)dalloc((size_t)S * 2 * 8);
@@ -1700,6 +1800,9 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
     ns.mean_rates = (double *)dalloc(S * 8);
     ns.trace = trace_out ? (double *)dalloc(trace_rows * (2 + S) * 8) : nullptr;
     ns.rng = (uint32_t *)dalloc(8 * 4);
+    const uint32_t n_lg = 1024;
+    double *lg_tab = (double *)dalloc(n_lg * 8);
+    ns.lg = lg_tab; ns.n_lg = n_lg;
     ns.trace_row = (uint32_t *)dalloc(4);
     d_sel = (uint32_t *)dalloc((size_t)G * 4);
     int rc = BTG_OK;
@@ -1727,24 +1830,41 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
             uint32_t uniform_int(uint32_t n) { return (uint32_t)(((uint64_t)next() * n) >> 32); }
         } engine;
         engine.init(opts->random_seed);
-        std::vector<uint32_t> noise_groups;  // single-cluster groups (InferenceEngine.cpp:144-151)
-        for (uint32_t g = 0; g < G; g++)
-            if (u->h_group_cluster_off[g + 1] - u->h_group_cluster_off[g] == 1) noise_groups.push_back(g);
+        // single-cluster groups (InferenceEngine.cpp:144-151) of the WHOLE unit: with a shard descriptor every rank walks the
+        // same global list with the same engine stream, so the selection does not depend on the sharding
+        const uint64_t base = sh ? opts->group_index_base : 0;
+        std::vector<uint32_t> noise_groups;
+        if (sh) {
+            for (uint64_t g = 0; g < sh->n_groups_total; g++) if (sh->group_n_clusters[g] == 1) noise_groups.push_back((uint32_t)g);
+        } else {
+            for (uint32_t g = 0; g < G; g++)
+                if (u->h_group_cluster_off[g + 1] - u->h_group_cluster_off[g] == 1) noise_groups.push_back(g);
+        }
         auto group_variants = [&](uint32_t g) {
+            if (sh) return sh->group_n_variants[g];
             uint64_t n = 0;
             for (uint64_t c = u->h_group_cluster_off[g]; c < u->h_group_cluster_off[g + 1]; c++) n += u->h_cl_var_off[c + 1] - u->h_cl_var_off[c];
             return (uint32_t)n;
         };
+        PeerExchange px{};
+        px.world = world; px.rank = comm ? comm->rank : 0;
+        if (comm) {
+            for (uint32_t r = 0; r < world; r++) px.mail[r] = comm->peers[r];
+            px.error = comm->error;
+            const char *tmo = getenv("BTG_PEER_TIMEOUT_MS");
+            px.timeout_ns = (tmo ? strtoull(tmo, nullptr, 10) : 20000ull) * 1000000ull;
+        }
         Tables T{cd->genomic, cd->noise};
         k_noise_rng_init<<<1, 1, 0, s>>>(ns.rng, opts->random_seed);
         BTG_LAUNCHED();
+        if (lg_tab) { k_lgamma_int<<<(n_lg + 127) / 128, 128, 0, s>>>(lg_tab, n_lg); BTG_LAUNCHED(); } else ns.lg = nullptr;
         NoiseState ns_quiet = ns;  // same state, no trace row
         ns_quiet.trace = nullptr;
         // CountDistribution ctor draws the initial rates (CountDistribution.cpp:62)
         k_noise_update<<<1, 256, 0, s>>>(ns_quiet, S, cd->prior_shape, cd->prior_scale, opts->random_seed, 0, 0, 0, 0, 1);
         BTG_LAUNCHED();
         const uint32_t noise_variants_batch_size = 100000;  // InferenceEngine.cpp:50
-        std::vector<uint32_t> sel;
+        std::vector<uint32_t> sel, tasks;
         for (uint32_t chain = 0; chain < opts->n_chains && rc == BTG_OK; chain++) {
             uint32_t end = 0, nvv = 0;
             if (joint) {
@@ -1755,28 +1875,47 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
                 std::sort(noise_groups.begin(), noise_groups.begin() + end);
             }
             sel.clear();
-            for (uint32_t i = 0; i < end; i++) sel.push_back((uint32_t)u->h_group_cluster_off[noise_groups[i]]);
+            for (uint32_t i = 0; i < end; i++) {
+                const uint64_t g = noise_groups[i];
+                if (g >= base && g < base + G) sel.push_back((uint32_t)u->h_group_cluster_off[g - base]);  // this rank's share
+            }
             // large clusters first (one warp each in the chain kernel), then by position in the cost order (neighbours share arena slots)
-            auto is_big = [&](uint32_t c) { return u->h_fill_cost[c] > 384; };
+            const uint32_t big_cost = getenv("BTG_NOISE_BIG") ? (uint32_t)atoi(getenv("BTG_NOISE_BIG")) : 128u;
+            auto is_big = [&](uint32_t c) { return u->h_fill_cost[c] > big_cost; };
             std::sort(sel.begin(), sel.end(), [&](uint32_t a, uint32_t b) {
                 const bool ba = is_big(a), bb = is_big(b);
                 return ba != bb ? ba : u->h_layout[a].pos < u->h_layout[b].pos;
             });
             uint32_t n_big = 0;
             while (n_big < sel.size() && is_big(sel[n_big])) n_big++;
+            // fill tasks: a large cluster gets one warp per 32 cache entries (S x diplotypes, upper bound), at most 64
+            tasks.clear();
+            for (uint32_t i = 0; i < n_big; i++) {
+                const uint64_t H = u->h_nhap[sel[i]], entries = (uint64_t)S * (H * (H + 1) / 2);
+                const uint32_t parts = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (entries + 31) / 32));
+                for (uint32_t p = 0; p < parts; p++) { tasks.push_back(i); tasks.push_back(p); tasks.push_back(parts); }
+            }
+            if (tasks.size() > tasks_cap) {
+                if (d_tasks) cudaFree(d_tasks);
+                tasks_cap = tasks.size() * 2;
+                if (cudaMalloc(&d_tasks, tasks_cap * 4) != cudaSuccess) { d_tasks = nullptr; tasks_cap = 0; rc = BTG_ENOMEM; set_error("fill task allocation failed"); break; }
+            }
+            if (!tasks.empty() && cudaMemcpyAsync(d_tasks, tasks.data(), tasks.size() * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BTG_ECUDA; break; }
             if (cudaMemcpyAsync(d_sel, sel.data(), sel.size() * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BTG_ECUDA; break; }
             cudaStreamSynchronize(s);  // sel is reused by the host next chain
             const uint32_t n_sel = (uint32_t)sel.size();
-            if (n_sel) {
+            if (n_sel || world > 1) {  // a rank with nothing selected still takes part in every exchange
                 int per_sm = 0;
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_noise_chain, 64, 0);
                 const uint32_t max_blocks = (uint32_t)std::max(1, per_sm) * (uint32_t)ctx().sm_count;
-                const uint32_t want_threads = n_big * 32 > n_sel - n_big ? n_big * 32 : n_sel - n_big;
+                const uint32_t want_threads = std::max<uint32_t>({n_big * 32u, n_sel - n_big, (uint32_t)(tasks.size() / 3) * 32u});
                 const uint32_t grid = std::max(1u, std::min((want_threads + 63) / 64, max_blocks));
                 uint32_t chain_id = chain + 1, n_sel_arg = n_sel, iters_arg = iters;
                 float ps = cd->prior_shape, pc = cd->prior_scale;
                 btg_gibbs_opts o = *opts;
-                void *args[] = {&u->du, &T, &o, &d_sel, &n_sel_arg, &n_big, &chain_id, &iters_arg, &ns, &ps, &pc, &hist, &joint};
+                if (comm) { px.seq0 = comm->seq; comm->seq += iters; }
+                uint32_t n_tasks = (uint32_t)(tasks.size() / 3);
+                void *args[] = {&u->du, &T, &o, &d_sel, &n_sel_arg, &n_big, &chain_id, &iters_arg, &ns, &ps, &pc, &hist, &joint, &px, &d_tasks, &n_tasks};
                 cudaError_t e = cudaLaunchCooperativeKernel((void *)k_noise_chain, dim3(grid), dim3(64), args, 0, s);
                 BTG_LAUNCHED();
                 if (e != cudaSuccess) { set_error("cooperative launch failed: %s", cudaGetErrorString(e)); rc = BTG_ECUDA; break; }
@@ -1799,12 +1938,18 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
             if (trace_out) cudaMemcpyAsync(trace_out, ns.trace, trace_rows * (2 + S) * 8, cudaMemcpyDeviceToHost, s);
             cudaError_t e = cudaStreamSynchronize(s);
             if (e != cudaSuccess) { set_error("noise estimation failed: %s", cudaGetErrorString(e)); rc = BTG_ECUDA; }
+            if (rc == BTG_OK && comm && world > 1) {
+                uint32_t flag = 0;
+                cudaMemcpy(&flag, comm->error, 4, cudaMemcpyDeviceToHost);
+                if (flag) { set_error("peer exchange timed out waiting for rank %u (a rank failed or left the lock-step)", flag - 1); cudaMemset(comm->error, 0, 4); rc = BTG_ECUDA; }
+            }
         } else {
             set_error("noise estimation failed: %s", cudaGetErrorString(cudaGetLastError()));
         }
     }
     cudaStreamSynchronize(s);
     for (void *p : tmp) cudaFree(p);
+    if (d_tasks) cudaFree(d_tasks);
     return rc;
 }
 

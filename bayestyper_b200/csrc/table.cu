@@ -178,59 +178,152 @@ __device__ __forceinline__ void sat_add_u8(uint8_t *p, uint32_t add) {  // updat
     } while (old != assumed);
 }
 
-// KmerCounter::parseSampleKmersCallBack: the sample's (k-mer, count) records stream past the table once (17 B/record).
-// Every thread keeps R records in flight: R coalesced 16 B record loads, R prefix-index reads, R first-key reads are
-// issued back to back before anything is compared, so a record costs three DRAM latencies (index -> key -> count
-// update) shared with R-1 others instead of the ~6 of a dependent binary search.  With a KMC-ordered stream
-// neighbouring lanes read neighbouring index entries and keys (the stream and the table are sorted alike), so the
-// table and its index cross the memory bus about once: traffic ~ the algorithmic 17 B/record + 16 B/key.
-// Buckets longer than kLinear keys (no index installed, or a skewed table) fall back to the binary search.
-constexpr int kStreamR = 4;
-constexpr int kLinear = 4;
-__global__ void __launch_bounds__(256, 4) k_table_add_sample(const int64_t *__restrict__ kw0, const int64_t *__restrict__ kw1, int64_t n_keys,
+// several saturating byte adds that fall into the same aligned 32-bit word are applied by ONE lane in one CAS loop: with
+// S < 4 neighbouring keys share a word, and a warp walking the table front to back would otherwise collide with itself
+__device__ __forceinline__ void sat_add_u8_warp(bool has, uint8_t *p, uint32_t add) {
+    const unsigned active = __ballot_sync(0xFFFFFFFFu, has);
+    if (!has) return;
+    uint32_t *word = reinterpret_cast<uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~uintptr_t(3));
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+    const unsigned peers = __match_any_sync(active, reinterpret_cast<unsigned long long>(word));
+    const int leader = __ffs(peers) - 1;
+    uint32_t shs[4], adds[4];  // at most 4 bytes per word
+    int n = 0;
+    for (unsigned m = peers; m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        const uint32_t v = __shfl_sync(peers, (add << 8) | sh, src);
+        if (n < 4) { shs[n] = v & 0xFFu; adds[n] = v >> 8; }
+        n++;
+    }
+    if ((int)(threadIdx.x & 31u) != leader) return;
+    if (n > 4) n = 4;  // cannot happen: distinct lanes of one group address distinct (key, sample) bytes
+    uint32_t old = *word, assumed;
+    do {
+        assumed = old;
+        uint32_t nw = assumed;
+        for (int i = 0; i < n; i++) {
+            const uint32_t cur = (nw >> shs[i]) & 0xFFu;
+            const uint32_t nv = (255u - cur) <= adds[i] ? 255u : cur + adds[i];
+            nw = (nw & ~(0xFFu << shs[i])) | (nv << shs[i]);
+        }
+        old = atomicCAS(word, assumed, nw);
+    } while (old != assumed);
+}
+
+// KmerCounter::parseSampleKmersCallBack as a tiled merge-join: the sample's (k-mer, count) records stream past the table
+// once (17 B/record).  A warp takes a tile of 128 consecutive records (coalesced 16 B loads), reduces their prefix-index
+// buckets to [bmin, bmax] and stages the table keys of that bucket range — with a KMC-ordered stream a few dozen
+// consecutive keys — in shared memory with coalesced loads.  Every record is then located by a branch-free
+// lower-bound search in shared memory with a warp-uniform trip count (no divergence, no dependent global loads), its
+// count is accumulated per key in shared memory, and the tile's keys are updated in the table by one coalesced pass.
+// Traffic = records + keys + index ends once = the algorithmic 17 B/record + 16 B/key.  Tiles whose bucket range
+// exceeds kTileKeys keys (unsorted or sparse stream, no index) probe the table directly, record by record.
+constexpr int kTileLanes = 4;                    // records per lane and tile -> 128 records per warp tile
+constexpr int kTileKeys = 256;                   // staged keys per tile
+constexpr int kStreamWarps = 8;                  // warps per CTA
+__global__ void __launch_bounds__(kStreamWarps * 32) k_table_add_sample(const int64_t *__restrict__ kw0, const int64_t *__restrict__ kw1, int64_t n_keys,
                                                           const longlong2 *__restrict__ kmers, const uint8_t *__restrict__ counts, size_t n,
                                                           uint32_t S, uint32_t sample, uint8_t *table_counts, uint8_t *has_record, TableIndex ix) {
-    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
-    for (size_t base = blockIdx.x * (size_t)blockDim.x + threadIdx.x; base < n; base += nthreads * kStreamR) {
-        TableKey q[kStreamR];
-        int64_t lo[kStreamR], hi[kStreamR], k0[kStreamR], k1[kStreamR];
+    __shared__ int64_t s_hi[kStreamWarps][kTileKeys];
+    __shared__ int64_t s_lo[kStreamWarps][kTileKeys];
+    __shared__ uint32_t s_acc[kStreamWarps][kTileKeys];
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const size_t n_tiles = (n + 32 * kTileLanes - 1) / (32 * kTileLanes);
+    const size_t warp_id = (size_t)blockIdx.x * kStreamWarps + w, n_warps = (size_t)gridDim.x * kStreamWarps;
+    for (size_t tile = warp_id; tile < n_tiles; tile += n_warps) {  // warp-uniform trip count
+        const size_t r0 = tile * (32 * kTileLanes);
+        TableKey q[kTileLanes];
+        bool valid[kTileLanes];
+        uint32_t bmin = 0xFFFFFFFFu, bmax = 0;
 #pragma unroll
-        for (int r = 0; r < kStreamR; r++) {
-            const size_t i = base + (size_t)r * nthreads;
-            if (i < n) { const longlong2 k = __ldg(kmers + i); q[r] = key_of_boundary(k.x, k.y); lo[r] = 0; hi[r] = n_keys; }
-            else { q[r] = TableKey{0, 0}; lo[r] = 0; hi[r] = 0; }
+        for (int j = 0; j < kTileLanes; j++) {
+            const size_t i = r0 + (size_t)j * 32 + lane;
+            valid[j] = i < n;
+            if (valid[j]) {
+                const longlong2 k = __ldg(kmers + i);
+                q[j] = key_of_boundary(k.x, k.y);
+                if (ix.lut) { const uint32_t b = (uint32_t)(q[j].hi >> ix.shift); bmin = min(bmin, b); bmax = max(bmax, b); }
+            } else q[j] = TableKey{0, 0};
         }
+        int64_t t0 = 0, t1 = n_keys;
         if (ix.lut) {
-#pragma unroll
-            for (int r = 0; r < kStreamR; r++)
-                if (hi[r]) { const int64_t b = q[r].hi >> ix.shift; lo[r] = __ldg(ix.lut + b); hi[r] = __ldg(ix.lut + b + 1); }
+            bmin = __reduce_min_sync(0xFFFFFFFFu, bmin);
+            bmax = __reduce_max_sync(0xFFFFFFFFu, bmax);
+            int64_t v = 0;
+            if (lane == 0) v = __ldg(ix.lut + bmin); else if (lane == 1) v = __ldg(ix.lut + bmax + 1);
+            t0 = __shfl_sync(0xFFFFFFFFu, v, 0);
+            t1 = __shfl_sync(0xFFFFFFFFu, v, 1);
         }
+        const int64_t nk = t1 - t0;
+        if (nk < kTileKeys) {
+            uint32_t top = 1;
+            while ((int64_t)top <= nk) top <<= 1;  // warp-uniform; the search below covers top - 1 >= nk slots
+            for (uint32_t i = lane; i < top; i += 32) {  // slots past the last key hold +inf: no bound checks in the search
+                const bool in = (int64_t)i < nk;
+                s_hi[w][i] = in ? __ldg(kw1 + t0 + i) : INT64_MAX;
+                s_lo[w][i] = in ? __ldg(kw0 + t0 + i) : INT64_MAX;
+                s_acc[w][i] = 0;
+            }
+            __syncwarp();
 #pragma unroll
-        for (int r = 0; r < kStreamR; r++) {
-            const bool small = hi[r] - lo[r] <= kLinear && lo[r] < hi[r];
-            k1[r] = small ? __ldg(kw1 + lo[r]) : 0;
-            k0[r] = small ? __ldg(kw0 + lo[r]) : 0;
-        }
+            for (int j = 0; j < kTileLanes; j++) {
+                // lower bound on key_hi alone (the first 23 nucleotides); ties on key_hi are walked linearly
+                uint32_t pos = 0;
+                for (uint32_t step = top >> 1; step; step >>= 1)
+                    if (s_hi[w][pos + step - 1] < q[j].hi) pos += step;
+                while (s_hi[w][pos] == q[j].hi && s_lo[w][pos] < q[j].lo) pos++;  // s_hi[top - 1] = +inf ends the walk
+                if (valid[j] && s_hi[w][pos] == q[j].hi && s_lo[w][pos] == q[j].lo)
+                    atomicAdd(&s_acc[w][pos], (uint32_t)counts[r0 + (size_t)j * 32 + lane]);
+            }
+            __syncwarp();
+            if (S == 1) {
+                // one lane per aligned 32-bit word of the count column (4 consecutive keys): no collisions inside the warp
+                const int64_t w_first = t0 >> 2, w_last = (t1 - 1) >> 2;
+                for (int64_t wd = w_first + lane; wd <= w_last; wd += 32) {
+                    uint32_t add[4];
+                    bool any = false;
 #pragma unroll
-        for (int r = 0; r < kStreamR; r++) {
-            if (lo[r] >= hi[r]) continue;
-            int64_t idx = -1;
-            if (hi[r] - lo[r] <= kLinear) {
-                int64_t p = lo[r], a1 = k1[r], a0 = k0[r];
-                for (;;) {
-                    if (a1 == q[r].hi && a0 == q[r].lo) { idx = p; break; }
-                    if (a1 > q[r].hi || (a1 == q[r].hi && a0 > q[r].lo) || ++p >= hi[r]) break;
-                    a1 = __ldg(kw1 + p); a0 = __ldg(kw0 + p);
+                    for (int bt = 0; bt < 4; bt++) {
+                        const int64_t i = wd * 4 + bt - t0;
+                        add[bt] = (i >= 0 && i < nk) ? min(s_acc[w][i], 255u) : 0u;
+                        if (add[bt]) { any = true; has_record[t0 + i] = 1; }
+                    }
+                    if (!any) continue;
+                    uint32_t *word = reinterpret_cast<uint32_t *>(table_counts) + wd;  // cudaMalloc'd column: 4-byte aligned
+                    uint32_t old = *word, assumed;
+                    do {
+                        assumed = old;
+                        uint32_t nw = 0;
+#pragma unroll
+                        for (int bt = 0; bt < 4; bt++) {
+                            const uint32_t cur = (assumed >> (8 * bt)) & 0xFFu;
+                            nw |= ((255u - cur) <= add[bt] ? 255u : cur + add[bt]) << (8 * bt);
+                        }
+                        old = atomicCAS(word, assumed, nw);
+                    } while (old != assumed);
                 }
             } else {
-                idx = table_find(kw0 + lo[r], kw1 + lo[r], hi[r] - lo[r], q[r].lo, q[r].hi);
-                if (idx >= 0) idx += lo[r];
+                for (int64_t i0 = 0; i0 < nk; i0 += 32) {  // one coalesced pass over the tile's keys
+                    const int64_t i = i0 + lane;
+                    const uint32_t add = i < nk ? s_acc[w][i] : 0;
+                    if (add) has_record[t0 + i] = 1;
+                    uint8_t *p = table_counts + (size_t)(t0 + (i < nk ? i : 0)) * S + sample;
+                    if (S >= 4) { if (add) sat_add_u8(p, add > 255u ? 255u : add); }   // distinct keys, distinct words
+                    else sat_add_u8_warp(add != 0, p, add > 255u ? 255u : add);
+                }
             }
-            if (idx >= 0) {
-                sat_add_u8(table_counts + (size_t)idx * S + sample, counts[base + (size_t)r * nthreads]);
-                has_record[idx] = 1;
+        } else {
+#pragma unroll
+            for (int j = 0; j < kTileLanes; j++) {
+                if (!valid[j]) continue;
+                const int64_t idx = table_find(kw0, kw1, n_keys, q[j].lo, q[j].hi, ix);
+                if (idx >= 0) {
+                    sat_add_u8(table_counts + (size_t)idx * S + sample, counts[r0 + (size_t)j * 32 + lane]);
+                    has_record[idx] = 1;
+                }
             }
         }
+        __syncwarp();
     }
 }
 
@@ -363,8 +456,9 @@ int btg_table_add_sample_kmers_dev(const int64_t *key_w0, const int64_t *key_w1,
                                    uint32_t n_samples, uint32_t sample_idx, uint8_t *table_counts, uint8_t *has_record, void *stream) {
     BTG_REQUIRE_INIT();
     if (sample_idx >= n_samples) { set_error("sample index out of range"); return BTG_EINVAL; }
+    if (reinterpret_cast<uintptr_t>(table_counts) & 3u) { set_error("table_counts must be 4-byte aligned"); return BTG_EINVAL; }
     if (n == 0) return BTG_OK;
-    k_table_add_sample<<<btg_grid_for((n + kStreamR - 1) / kStreamR, 256, 4), 256, 0, pick_stream(stream)>>>(key_w0, key_w1, n_keys, (const longlong2 *)kmers, counts, n, n_samples,
+    k_table_add_sample<<<btg_grid_for((n + kTileLanes - 1) / kTileLanes, kStreamWarps * 32, 5), kStreamWarps * 32, 0, pick_stream(stream)>>>(key_w0, key_w1, n_keys, (const longlong2 *)kmers, counts, n, n_samples,
                                                                                sample_idx, table_counts, has_record, g_index);
     BTG_LAUNCHED();
     BTG_CUDA(cudaGetLastError());

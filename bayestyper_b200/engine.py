@@ -62,18 +62,28 @@ class InferenceEngine:
         capi.check(self.lib.btg_estimate_genotypes(self.h, cd.h, C.addressof(opts), C.addressof(res)), self.lib)
         return arrays
 
-    def estimate_noise(self, cd: CountDistribution, opts: GibbsOpts, want_trace: bool = True):
+    def estimate_noise(self, cd: CountDistribution, opts: GibbsOpts, want_trace: bool = True, shard=None):
+        """InferenceEngine::estimateNoise.  shard = btg_shard_desc (shard.shard_desc) when this engine holds one rank's
+        groups of a larger unit: the selection and the noise draws are then those of the whole unit."""
         rows = opts.n_chains * (opts.gibbs_burn_in + opts.gibbs_samples + 1) + 1
         trace = np.zeros((rows, 2 + self.unit.S)) if want_trace else None
-        capi.check(self.lib.btg_estimate_noise(self.h, cd.h, C.addressof(opts), capi.ptr(trace) if want_trace else None), self.lib)
+        tp = capi.ptr(trace) if want_trace else None
+        if shard is None:
+            capi.check(self.lib.btg_estimate_noise(self.h, cd.h, C.addressof(opts), tp), self.lib)
+        else:
+            capi.check(self.lib.btg_estimate_noise_sharded(self.h, cd.h, C.addressof(opts), C.addressof(shard), tp), self.lib)
         return trace
 
-    def estimate_noise_and_genotypes(self, cd: CountDistribution, opts: GibbsOpts, want_trace: bool = True):
+    def estimate_noise_and_genotypes(self, cd: CountDistribution, opts: GibbsOpts, want_trace: bool = True, shard=None):
         """InferenceEngine::estimateNoiseAndGenotypes (--noise-genotyping)."""
         res, arrays = self.unit.alloc_result()
         rows = opts.n_chains * (opts.gibbs_burn_in + opts.gibbs_samples + 1)
         trace = np.zeros((rows, 2 + self.unit.S)) if want_trace else None
-        capi.check(self.lib.btg_estimate_noise_and_genotypes(self.h, cd.h, C.addressof(opts), C.addressof(res), capi.ptr(trace) if want_trace else None), self.lib)
+        tp = capi.ptr(trace) if want_trace else None
+        if shard is None:
+            capi.check(self.lib.btg_estimate_noise_and_genotypes(self.h, cd.h, C.addressof(opts), C.addressof(res), tp), self.lib)
+        else:
+            capi.check(self.lib.btg_estimate_noise_and_genotypes_sharded(self.h, cd.h, C.addressof(opts), C.addressof(shard), C.addressof(res), tp), self.lib)
         return arrays, trace
 
     def cluster_tally(self, cluster: int) -> np.ndarray:

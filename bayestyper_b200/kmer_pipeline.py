@@ -87,6 +87,7 @@ class KmerPipeline:
         path_mem_off = np.concatenate([[0], np.cumsum(n_paths * V)]).astype(np.int64)
         assert path_mem_off[-1] == len(path_mem)
         self.cl_path_off = cl_path_off
+        self.path_mem_host, self.path_mem_off_host = np.asarray(path_mem, np.uint8), path_mem_off
         self.t["cl_path_off"] = torch.from_numpy(cl_path_off).to(d)
         self.t["path_mem_off"] = torch.from_numpy(path_mem_off).to(d)
         self.t["path_mem"] = torch.from_numpy(np.ascontiguousarray(path_mem, np.uint8)).to(d)
@@ -193,8 +194,8 @@ class KmerPipeline:
         (VariantClusterGraph.cpp:1006-1010, 1112-1133).  Only clusters holding a vertex that stands for a nested
         cluster contribute, so this is a short host loop over those clusters."""
         g = self.g
-        v_nested = np.asarray(g["v_nested"], np.uint32)
-        cvo, cpo = np.asarray(g["cl_vertex_off"], np.int64), np.asarray(g["cl_path_off"], np.int64)
+        v_nested = np.asarray(g["v_nested"], np.uint32) if "v_nested" in g else np.zeros(0, np.uint32)
+        cvo = np.asarray(g["cl_vertex_off"], np.int64)
         hap_nested_off = np.zeros(self.P + 1, np.uint64)
         cl_dep_off = np.zeros(self.C + 1, np.uint64)
         nested_parts, dep_cluster, dep_var_off, dep_var = [], [], [0], []
@@ -206,7 +207,7 @@ class KmerPipeline:
             for c in np.unique(np.searchsorted(cvo, marked, side="right") - 1):
                 v0, v1 = cvo[c], cvo[c + 1]
                 nv = v1 - v0
-                bits = np.asarray(g["path_bits"][cpo[c]:cpo[c + 1]], np.uint8).reshape(-1, nv)
+                bits = self.path_mem_host[self.path_mem_off_host[c]:self.path_mem_off_host[c + 1]].reshape(-1, nv)
                 nest = v_nested[v0:v1]
                 has = nest != 0xFFFFFFFF
                 for p in range(bits.shape[0]):

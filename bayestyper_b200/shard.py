@@ -1,8 +1,12 @@
 """Multi-GPU sharding of an inference unit: variant-cluster GROUPS are independent, so each rank
 genotypes a contiguous, cost-balanced block of groups with its global group indices (seeds unchanged) and the
-results are concatenated in rank order.  No data-path collective in the default mode; the S noise rates estimated
-on rank 0 are broadcast (S doubles)."""
+results are concatenated in rank order.  The default mode (estimateGenotypes) has no data-path exchange.  The
+lock-step modes (estimateNoise, estimateNoiseAndGenotypes) exchange the per-sample (n_obs, sum) of the noise counts
+once per iteration inside the chain kernel, over peer mailboxes (csrc/comm.cuh); this module only carries the
+64-byte mailbox handles between the ranks (torch.distributed, any backend) and describes the whole unit to the library."""
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 
@@ -46,3 +50,66 @@ RESULT_KEYS = ("gt", "gq", "gpp", "app", "nak", "fak", "mac", "saf", "ploidy", "
 def concat_results(parts):
     """Concatenate per-rank result dicts (rank order == group order)."""
     return {k: np.concatenate([p[k] for p in parts]) for k in RESULT_KEYS}
+
+
+HANDLE_BYTES = 64
+
+
+class ShardDesc(C.Structure):
+    _fields_ = [("comm", C.c_void_p), ("n_groups_total", C.c_uint64), ("group_n_clusters", C.c_void_p), ("group_n_variants", C.c_void_p)]
+
+
+class Comm:
+    """btg_comm: this rank's mailbox + the peers' mappings.  `allgather(bytes) -> [bytes per rank]` is the host transport
+    for the handles; `Comm.torch(world, rank)` uses torch.distributed (gloo or nccl)."""
+
+    def __init__(self, world: int, rank: int, allgather=None):
+        from . import capi
+        self.lib = capi.load()
+        self.world, self.rank = world, rank
+        mine = np.zeros(HANDLE_BYTES, np.uint8)
+        self.h = capi.check(self.lib.btg_comm_create(world, rank, capi.ptr(mine)), self.lib)
+        if world > 1:
+            handles = allgather(mine.tobytes())
+            assert len(handles) == world and all(len(b) == HANDLE_BYTES for b in handles)
+            buf = np.frombuffer(b"".join(handles), np.uint8).copy()
+            capi.check(self.lib.btg_comm_connect(self.h, capi.ptr(buf)), self.lib)
+
+    @classmethod
+    def torch(cls, world: int, rank: int):
+        import torch.distributed as dist
+
+        def allgather(b: bytes):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        return cls(world, rank, allgather)
+
+    def close(self):
+        if self.h:
+            self.lib.btg_comm_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def group_tables(unit: Unit):
+    """(clusters per group, variants per group) of a unit — what every rank must know about the WHOLE unit."""
+    a = unit.a
+    gco = np.asarray(a["group_cluster_off"], np.int64)
+    nvar = np.diff(np.asarray(a["cl_var_off"], np.int64))
+    n_cl = np.diff(gco).astype(np.uint32)
+    csum = np.concatenate([[0], np.cumsum(nvar)])
+    return n_cl, (csum[gco[1:]] - csum[gco[:-1]]).astype(np.uint32)
+
+
+def shard_desc(whole: Unit, comm: Comm | None):
+    """btg_shard_desc of the whole unit for the lock-step entry points; returns (struct, keep-alive tuple)."""
+    n_cl, n_var = group_tables(whole)
+    n_cl, n_var = np.ascontiguousarray(n_cl), np.ascontiguousarray(n_var)
+    d = ShardDesc(comm.h if comm is not None else None, len(n_cl), n_cl.ctypes.data, n_var.ctypes.data)
+    return d, (n_cl, n_var, comm)

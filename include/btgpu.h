@@ -344,6 +344,29 @@ int btg_estimate_noise(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *op
  * rates redrawn after every iteration, genotypers persisting across chains; trace rows: [n_chains*(iters+1)][2+S] */
 int btg_estimate_noise_and_genotypes(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, btg_genotype_result *out,
                                      double *trace_out);
+/* ---- one inference unit sharded over several GPUs (one rank per process and GPU) ----------
+ * Groups are independent, so a rank uploads the groups [group_index_base, group_index_base + n_groups) of the unit as
+ * its btg_unit and keeps the reference's per-group seeds through btg_gibbs_opts.group_index_base.  btg_estimate_genotypes
+ * needs nothing else.  The lock-step modes (estimateNoise, estimateNoiseAndGenotypes) merge every thread's
+ * CountAllocation once per iteration (InferenceEngine.cpp:226-229,445-448); across ranks that merge is the per-sample
+ * (n_obs, sum) pair written into every peer's mailbox over NVLink from inside the chain kernel, after which all ranks
+ * draw the same noise rates from the shared CountDistribution stream.  Results equal the single-GPU run bit for bit.
+ * A communicator owns this rank's mailbox; the 64-byte handles are exchanged by the host (any transport).          */
+#define BTG_COMM_HANDLE_BYTES 64
+typedef struct btg_comm btg_comm;
+btg_comm *btg_comm_create(uint32_t world, uint32_t rank, uint8_t *handle_out /* [BTG_COMM_HANDLE_BYTES] */);
+int btg_comm_connect(btg_comm *c, const uint8_t *all_handles /* [world][BTG_COMM_HANDLE_BYTES], rank order */);
+void btg_comm_free(btg_comm *c);
+typedef struct btg_shard_desc {
+    btg_comm *comm;                    /* NULL = this rank holds the whole unit */
+    uint64_t n_groups_total;           /* groups of the whole unit */
+    const uint32_t *group_n_clusters;  /* [n_groups_total] clusters per group (estimateNoise uses single-cluster groups, InferenceEngine.cpp:144-151) */
+    const uint32_t *group_n_variants;  /* [n_groups_total] variants per group (the 100,000-variant batch, InferenceEngine.cpp:50,183-189) */
+} btg_shard_desc;
+int btg_estimate_noise_sharded(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *shard, double *trace_out);
+int btg_estimate_noise_and_genotypes_sharded(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *shard,
+                                             btg_genotype_result *out, double *trace_out);
+
 /* raw diplotype tallies of one cluster (tests): [(H+1)(H+2)/2][S] uint32, pair (h1<=h2), index h2*(h2+1)/2+h1, H = "missing" */
 int btg_unit_cluster_tally(const btg_unit *u, uint32_t cluster, uint32_t *tally_out, uint64_t n);
 

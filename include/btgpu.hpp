@@ -1,0 +1,164 @@
+// btgpu.hpp — C++ host mirror of the reference's stage objects over the C ABI (include/btgpu.h).
+//
+// The reference is C++ whose seams are ordinary classes.  These header-only RAII adaptors keep
+// the reference's class and method names and argument meaning, and turn the ABI's error codes into exceptions
+// (the reference prints to cerr and calls exit(1), e.g. src/kmerBloom/KmerBloom.cpp:67-71):
+//
+//   btg::KmerBloom          ≡ KmerBloom<55>          include/kmerBloom/KmerBloom.hpp:48-77
+//   btg::CountDistribution  ≡ CountDistribution      include/bayesTyper/CountDistribution.hpp:44-90
+//   btg::InferenceUnit      ≡ the VariantClusterHaplotypes of an InferenceUnit (flat descriptors)
+//   btg::InferenceEngine    ≡ InferenceEngine        include/bayesTyper/InferenceEngine.hpp:56-98
+//
+// There is no CPU implementation behind any of it: every method is one or two libbtgpu calls.
+#pragma once
+#include <bitset>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "btgpu.h"
+
+namespace btg {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+inline void check(int rc) {
+    if (rc != BTG_OK) throw Error(btg_last_error());
+}
+template <class T> inline T *check_ptr(T *p) {
+    if (!p) throw Error(btg_last_error());
+    return p;
+}
+
+// one per process and GPU (src/bayesTyper/main.cpp:80 is where the reference would call it)
+struct Library {
+    explicit Library(int device = 0) { check(btg_init(device)); }
+    ~Library() { btg_shutdown(); }
+    Library(const Library &) = delete;
+    Library &operator=(const Library &) = delete;
+};
+
+class KmerBloom {
+    btg_bloom *b_;
+
+  public:
+    static constexpr int kmer_size = BTG_KMER_SIZE;
+    using Kmer = std::bitset<2 * BTG_KMER_SIZE>;  // memory layout == the ABI's packed k-mer (two 64-bit words)
+    static_assert(sizeof(Kmer) == 16, "std::bitset<110> must be two 64-bit words");
+
+    KmerBloom(uint64_t num_kmers, float false_positive_rate) : b_(check_ptr(btg_bloom_create(num_kmers, false_positive_rate, kmer_size))) {}
+    explicit KmerBloom(const std::string &prefix) : b_(check_ptr(btg_bloom_load(prefix.c_str(), kmer_size))) {}
+    ~KmerBloom() { btg_bloom_free(b_); }
+    KmerBloom(const KmerBloom &) = delete;
+    KmerBloom &operator=(const KmerBloom &) = delete;
+
+    void save(const std::string &prefix) const { check(btg_bloom_save(b_, prefix.c_str())); }
+    // batched addKmer(bitset) / lookup(bitset) (KmerBloom.cpp:178-200)
+    void addKmers(const std::vector<Kmer> &kmers) { check(btg_bloom_insert(b_, reinterpret_cast<const uint64_t *>(kmers.data()), kmers.size())); }
+    std::vector<uint8_t> lookup(const std::vector<Kmer> &kmers) const {
+        std::vector<uint8_t> hit(kmers.size());
+        check(btg_bloom_lookup(b_, reinterpret_cast<const uint64_t *>(kmers.data()), kmers.size(), hit.data()));
+        return hit;
+    }
+    const btg_bloom *handle() const { return b_; }
+};
+
+class CountDistribution {
+    btg_count_dist *cd_;
+    uint32_t n_samples_;
+
+  public:
+    // ctor + setGenomicCountDistributions (CountDistribution.cpp:51-141): per-sample NB (p, size) of one haploid copy
+    CountDistribution(const std::vector<double> &nb_p, const std::vector<double> &nb_size, float prior_shape = 1.0f, float prior_scale = 0.01f)
+        : cd_(nullptr), n_samples_((uint32_t)nb_p.size()) {
+        if (nb_p.size() != nb_size.size()) throw Error("CountDistribution: p / size length mismatch");
+        cd_ = check_ptr(btg_count_dist_create(n_samples_, nb_p.data(), nb_size.data(), prior_shape, prior_scale));
+    }
+    ~CountDistribution() { btg_count_dist_free(cd_); }
+    CountDistribution(const CountDistribution &) = delete;
+    CountDistribution &operator=(const CountDistribution &) = delete;
+
+    void setNoiseRates(const std::vector<double> &rates) {  // CountDistribution.cpp:153-161
+        if (rates.size() != n_samples_) throw Error("setNoiseRates: wrong number of samples");
+        check(btg_count_dist_set_noise_rates(cd_, rates.data()));
+    }
+    std::vector<double> getNoiseRates() const {
+        std::vector<double> r(n_samples_);
+        check(btg_count_dist_get_noise_rates(cd_, r.data()));
+        return r;
+    }
+    uint32_t numSamples() const { return n_samples_; }
+    btg_count_dist *handle() const { return cd_; }
+};
+
+// result arrays of one unit: the fields of `Genotypes` (include/bayesTyper/Genotypes.hpp:46-99), flat
+struct GenotypeArrays {
+    std::vector<uint64_t> allele_off, geno_off, valt_off;
+    std::vector<uint16_t> gt, saf, hc;
+    std::vector<uint32_t> gq, an, ac;
+    std::vector<float> gpp, app, nak, fak, mac, af, acp;
+    std::vector<uint8_t> ploidy, anc;
+    btg_genotype_result view;
+
+    GenotypeArrays(uint32_t S, const uint16_t *var_nalleles, uint64_t n_variants) {
+        allele_off.assign(1, 0); geno_off.assign(1, 0); valt_off.assign(1, 0);
+        for (uint64_t v = 0; v < n_variants; v++) {
+            const uint64_t nA = var_nalleles[v];
+            allele_off.push_back(allele_off.back() + S * nA);
+            geno_off.push_back(geno_off.back() + S * (nA * (nA + 1) / 2));
+            valt_off.push_back(valt_off.back() + nA);
+        }
+        const uint64_t nall = allele_off.back(), ngen = geno_off.back(), nalt = valt_off.back();
+        gt.resize(n_variants * S * 2); gq.resize(n_variants * S); gpp.resize(ngen); app.resize(nall); nak.resize(nall); fak.resize(nall); mac.resize(nall);
+        saf.resize(nall); ploidy.resize(n_variants * S); an.resize(n_variants); ac.resize(nalt); af.resize(nalt); acp.resize(nalt); anc.resize(nalt);
+        hc.resize(n_variants);
+        view = btg_genotype_result{n_variants, allele_off.data(), geno_off.data(), gt.data(), gq.data(), gpp.data(), app.data(), nak.data(), fak.data(),
+                                   mac.data(), saf.data(), ploidy.data(), an.data(), valt_off.data(), ac.data(), af.data(), acp.data(), anc.data(), hc.data()};
+    }
+};
+
+class InferenceUnit {
+    btg_unit *u_;
+    uint32_t n_samples_;
+    std::vector<uint16_t> var_nalleles_;
+
+  public:
+    explicit InferenceUnit(const btg_unit_desc &d) : u_(check_ptr(btg_unit_upload(&d))), n_samples_(d.n_samples) {
+        var_nalleles_.assign(d.var_nalleles, d.var_nalleles + d.cl_var_off[d.n_clusters]);
+    }
+    ~InferenceUnit() { btg_unit_free(u_); }
+    InferenceUnit(const InferenceUnit &) = delete;
+    InferenceUnit &operator=(const InferenceUnit &) = delete;
+    btg_unit *handle() const { return u_; }
+    uint32_t numSamples() const { return n_samples_; }
+    GenotypeArrays allocResult() const { return GenotypeArrays(n_samples_, var_nalleles_.data(), var_nalleles_.size()); }
+};
+
+class InferenceEngine {
+    btg_gibbs_opts opts_;
+
+  public:
+    explicit InferenceEngine(const btg_gibbs_opts &opts) : opts_(opts) {}
+    // InferenceEngine::estimateNoise (InferenceEngine.cpp:135-276); returns the rows of <prefix>_noise_parameters.txt
+    std::vector<double> estimateNoise(CountDistribution *cd, InferenceUnit *unit) const {
+        const size_t rows = (size_t)opts_.n_chains * (opts_.gibbs_burn_in + opts_.gibbs_samples + 1) + 1;
+        std::vector<double> trace(rows * (2 + unit->numSamples()));
+        check(btg_estimate_noise(unit->handle(), cd->handle(), &opts_, trace.data()));
+        return trace;
+    }
+    // InferenceEngine::estimateGenotypes (InferenceEngine.cpp:278-382)
+    void estimateGenotypes(InferenceUnit *unit, const CountDistribution &cd, GenotypeArrays *out) const {
+        check(btg_estimate_genotypes(unit->handle(), cd.handle(), &opts_, &out->view));
+    }
+    // InferenceEngine::estimateNoiseAndGenotypes (InferenceEngine.cpp:384-472, --noise-genotyping)
+    std::vector<double> estimateNoiseAndGenotypes(InferenceUnit *unit, CountDistribution *cd, GenotypeArrays *out) const {
+        const size_t rows = (size_t)opts_.n_chains * (opts_.gibbs_burn_in + opts_.gibbs_samples + 1);
+        std::vector<double> trace(rows * (2 + unit->numSamples()));
+        check(btg_estimate_noise_and_genotypes(unit->handle(), cd->handle(), &opts_, &out->view, trace.data()));
+        return trace;
+    }
+};
+
+}  // namespace btg

@@ -69,3 +69,22 @@ def test_partition_edge_cases():
         assert all(p[i][1] == p[i + 1][0] for i in range(world - 1))
     empty = fx.unit.subset_groups(np.zeros(0, np.int64))
     assert shard.partition(empty, 4) == [(0, 0)] * 4
+
+
+def test_group_tables_describe_the_whole_unit():
+    """What every rank hands to the lock-step entry points (btg_shard_desc): clusters and variants per group."""
+    sys.path.insert(0, str(ROOT))
+    from bayestyper_b200 import shard
+    from tests._fixtures import GibbsFixture
+    for name in ("gibbs_mixed_3s", "gibbs_nested_2s"):
+        fx = GibbsFixture(name)
+        n_cl, n_var = shard.group_tables(fx.unit)
+        a = fx.unit.a
+        gco, cvo = a["group_cluster_off"].astype(np.int64), a["cl_var_off"].astype(np.int64)
+        assert len(n_cl) == fx.unit.G and n_cl.sum() == fx.unit.Cn and n_var.sum() == cvo[-1]
+        for g in (0, fx.unit.G // 2, fx.unit.G - 1):
+            assert n_cl[g] == gco[g + 1] - gco[g]
+            assert n_var[g] == cvo[gco[g + 1]] - cvo[gco[g]]
+        # the shards tile the group axis, so group_index_base + local index addresses these tables
+        parts = shard.partition(fx.unit, 3)
+        assert sum(hi - lo for lo, hi in parts) == fx.unit.G
