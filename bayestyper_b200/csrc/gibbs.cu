@@ -35,6 +35,12 @@
 
 namespace cg = cooperative_groups;
 
+// -DBTG_NOISE_TIMING=1 compiles per-cluster timers into the chain kernel (slowest cluster per iteration, clock sums of the
+// sub-steps); they cost registers, so the default build only keeps block 0's four phase laps (BTG_NOISE_PHASES=1 at run time)
+#ifndef BTG_NOISE_TIMING
+#define BTG_NOISE_TIMING 0
+#endif
+
 using namespace btg;
 
 namespace {
@@ -51,7 +57,7 @@ __host__ __device__ inline bool floatCompare(float a, float b) {  // Utils.hpp:8
 }
 __host__ __device__ inline bool floatLess(float a, float b) { return (a < b) && !floatCompare(a, b); }
 __device__ __forceinline__ double logAddition(double a, double b) {  // Utils.hpp:105-124
-    return a < b ? b + log1p(exp(a - b)) : a + log1p(exp(b - a));
+    return a < b ? b + m_log1p(m_exp(a - b)) : a + m_log1p(m_exp(b - a));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -152,6 +158,16 @@ template <class T> struct LaneArr {
     __device__ __forceinline__ LaneArr<T> operator+(size_t i) const { return LaneArr<T>{p + i * 32}; }
 };
 
+// k-mer tile accessor: lane-interleaved (stride 32) for clusters that run one per thread — the 32 clusters of a warp
+// read one sector per element — and dense (stride 1) for the large clusters that a whole warp works on, where all lanes
+// read the same row and an interleaved layout would cost one sector per byte
+struct TileArr {
+    uint8_t *p;
+    uint32_t stride;
+    __device__ __forceinline__ uint8_t &operator[](uint32_t i) const { return p[(size_t)i * stride]; }
+};
+constexpr uint32_t kBigFillCost = 128;  // table lookups per cache fill above which a cluster is "large" (warp-cooperative)
+
 struct DevUnit {
     uint32_t S, G, C;
     const uint8_t *sample_gender, *group_ploidy;
@@ -176,6 +192,8 @@ struct DevUnit {
     uint32_t *u32_pool;
     uint8_t *u8_pool;
     const double *lgamma_int;
+    const uint64_t *big_tile_off;  // [C] offset of the cluster's dense tile in big_tile_pool, ~0 for one-thread clusters
+    uint8_t *big_tile_pool;
     // nested groups / multicluster k-mers
     uint32_t n_regular;          // order[0 .. n_regular): clusters of single-cluster groups
     uint32_t n_nested_groups;
@@ -246,7 +264,8 @@ struct Cl {
     const uint8_t *M;
     LaneArr<double> freq, logf, simplex, simplex_tab, ucache, cum, kc_f, as_f, mcache, fmisc;
     LaneArr<uint32_t> obs, uniq, uniq_sub, cnt, tally, kc_n, as_n, dipl, multi, multi_sub, misc;
-    LaneArr<uint8_t> nz, uncovered, stats_update, sample_multi, tile_m, tile_c, tile_ic;
+    LaneArr<uint8_t> nz, uncovered, stats_update, sample_multi;
+    TileArr tile_m, tile_c, tile_ic;
 
     __device__ void bind(const DevUnit &du, uint32_t cluster) {
         u = &du; c = cluster;
@@ -294,9 +313,17 @@ struct Cl {
         uncovered = b; b = b + SL.K;
         stats_update = b; b = b + S;
         sample_multi = b; b = b + (uint64_t)SL.n_multi * S;
-        tile_m = b; b = b + (uint64_t)SL.n_uniq * SL.H;
-        tile_c = b; b = b + (uint64_t)SL.n_uniq * S;
-        tile_ic = b;
+        const uint64_t dense = du.big_tile_off[c];
+        if (dense != ~0ull) {
+            uint8_t *t = du.big_tile_pool + dense;
+            tile_m = TileArr{t, 1}; t += (size_t)n_uniq * H;
+            tile_c = TileArr{t, 1}; t += (size_t)n_uniq * S;
+            tile_ic = TileArr{t, 1};
+        } else {
+            tile_m = TileArr{b.p, 32}; b = b + (uint64_t)SL.n_uniq * SL.H;
+            tile_c = TileArr{b.p, 32}; b = b + (uint64_t)SL.n_uniq * S;
+            tile_ic = TileArr{b.p, 32};
+        }
     }
     // k-mer tile (lock-step modes, where the diplotype caches are cleared every iteration): row i holds everything the
     // likelihood reads about the i-th k-mer of the current subsample, so the per-iteration gathers touch three compact
@@ -347,18 +374,104 @@ __device__ __forceinline__ void kc_add(uint32_t &n, double &nonzero, double &sum
 struct Tables {
     const double *genomic;  // [S][256][256]
     const double *noise;    // [S][256]
+    // address of the table entry (no branch between the byte loads that produce (m, c) and the gather, so the gathers of
+    // consecutive k-mers can be in flight together)
+    __device__ __forceinline__ const double *entry(uint32_t s, uint8_t m, uint8_t c) const {
+        return m == 0 ? noise + s * 256u + c : genomic + ((size_t)s * 256 + m) * 256 + c;
+    }
     __device__ __forceinline__ double logProb(uint32_t s, uint8_t m, uint8_t c) const {  // CountDistribution.cpp:255-265
-        return m == 0 ? __ldg(noise + s * 256u + c) : __ldg(genomic + ((size_t)s * 256 + m) * 256 + c);
+        return *entry(s, m, c);
     }
 };
 
+// Sum over the k-mer tile of one (sample, diplotype) cache entry, in subsample order (bit-identical to the sequential
+// loop): the (multiplicity, count) bytes of eight k-mers are read first, then their eight table entries are gathered
+// together, then added in order — eight L2 round trips overlap instead of queueing behind each other.
+__device__ __forceinline__ const double *tile_term(const Cl &cl, const Tables &T, uint32_t s, uint32_t g, uint32_t a, uint32_t b, uint32_t i) {
+    return T.entry(s, (uint8_t)(cl.tileDiplMult(i, a, b) + cl.tile_ic[i * 2 + g]), cl.tile_c[i * cl.S + s]);
+}
+__device__ __forceinline__ double tile_entry_sum(const Cl &cl, const Tables &T, uint32_t s, uint32_t a, uint32_t b, uint32_t n_sub) {
+    const uint32_t g = cl.u->sample_gender[s];
+    double acc = 0;
+    uint32_t i = 0;
+    for (; i + 8 <= n_sub; i += 8) {
+        const double *p0 = tile_term(cl, T, s, g, a, b, i), *p1 = tile_term(cl, T, s, g, a, b, i + 1), *p2 = tile_term(cl, T, s, g, a, b, i + 2),
+                     *p3 = tile_term(cl, T, s, g, a, b, i + 3), *p4 = tile_term(cl, T, s, g, a, b, i + 4), *p5 = tile_term(cl, T, s, g, a, b, i + 5),
+                     *p6 = tile_term(cl, T, s, g, a, b, i + 6), *p7 = tile_term(cl, T, s, g, a, b, i + 7);
+        const double v0 = *(p0), v1 = *(p1), v2 = *(p2), v3 = *(p3), v4 = *(p4), v5 = *(p5), v6 = *(p6), v7 = *(p7);
+        acc += v0; acc += v1; acc += v2; acc += v3; acc += v4; acc += v5; acc += v6; acc += v7;
+    }
+    for (; i < n_sub; i++) acc += *(tile_term(cl, T, s, g, a, b, i));
+    return acc;
+}
+
+// Row-major fill of ALL cache entries of a one-thread cluster with at most 4 live haplotypes (<= 10 diplotypes): the
+// tile is walked once per sample and every k-mer updates all diplotype sums, so the gathers of one k-mer (up to 10,
+// independent) are in flight together and each tile byte is read once instead of once per diplotype.  Every entry is
+// still the sum of its terms in subsample order.  Used where the caches are cleared every iteration (lock-step modes).
+__device__ __forceinline__ bool cl_fill_cache_rows(Cl &cl, const Tables &T, const uint8_t *ploidy) {
+    const uint32_t H = cl.H, n_sub = cl.misc[kNSub];
+    uint32_t hs0 = 0, hs1 = 0, hs2 = 0, hs3 = 0, n = 0;
+    for (uint32_t h = 0; h < H; h++)
+        if (cl.nz[h]) {
+            if (n == 0) hs0 = h; else if (n == 1) hs1 = h; else if (n == 2) hs2 = h; else if (n == 3) hs3 = h; else return false;
+            n++;
+        }
+    for (uint32_t s = 0; s < cl.S; s++) {
+        const uint8_t pl = ploidy[s];
+        if (pl == 0) continue;
+        const uint32_t g = cl.u->sample_gender[s];
+        // pair slots: (0,0) (0,1) (0,2) (0,3) (1,1) (1,2) (1,3) (2,2) (2,3) (3,3)
+        double a00 = 0, a01 = 0, a02 = 0, a03 = 0, a11 = 0, a12 = 0, a13 = 0, a22 = 0, a23 = 0, a33 = 0;
+        for (uint32_t i = 0; i < n_sub; i++) {
+            const uint8_t c = cl.tile_c[i * cl.S + s];
+            const uint8_t base = cl.tile_ic[i * 2 + g];
+            const uint8_t m0 = cl.tile_m[i * H + hs0];
+            const uint8_t m1 = n > 1 ? cl.tile_m[i * H + hs1] : 0, m2 = n > 2 ? cl.tile_m[i * H + hs2] : 0, m3 = n > 3 ? cl.tile_m[i * H + hs3] : 0;
+            if (pl == 2) {
+                const double *p00 = T.entry(s, (uint8_t)(m0 + m0 + base), c), *p01 = T.entry(s, (uint8_t)(m0 + m1 + base), c),
+                             *p02 = T.entry(s, (uint8_t)(m0 + m2 + base), c), *p03 = T.entry(s, (uint8_t)(m0 + m3 + base), c),
+                             *p11 = T.entry(s, (uint8_t)(m1 + m1 + base), c), *p12 = T.entry(s, (uint8_t)(m1 + m2 + base), c),
+                             *p13 = T.entry(s, (uint8_t)(m1 + m3 + base), c), *p22 = T.entry(s, (uint8_t)(m2 + m2 + base), c),
+                             *p23 = T.entry(s, (uint8_t)(m2 + m3 + base), c), *p33 = T.entry(s, (uint8_t)(m3 + m3 + base), c);
+                const double v00 = *(p00);
+                double v01 = 0, v02 = 0, v03 = 0, v11 = 0, v12 = 0, v13 = 0, v22 = 0, v23 = 0, v33 = 0;
+                if (n > 1) { v01 = *(p01); v11 = *(p11); }
+                if (n > 2) { v02 = *(p02); v12 = *(p12); v22 = *(p22); }
+                if (n > 3) { v03 = *(p03); v13 = *(p13); v23 = *(p23); v33 = *(p33); }
+                a00 += v00; a01 += v01; a02 += v02; a03 += v03; a11 += v11; a12 += v12; a13 += v13; a22 += v22; a23 += v23; a33 += v33;
+            } else {
+                const double v0 = *(T.entry(s, (uint8_t)(m0 + base), c));
+                double v1 = 0, v2 = 0, v3 = 0;
+                if (n > 1) v1 = *(T.entry(s, (uint8_t)(m1 + base), c));
+                if (n > 2) v2 = *(T.entry(s, (uint8_t)(m2 + base), c));
+                if (n > 3) v3 = *(T.entry(s, (uint8_t)(m3 + base), c));
+                a00 += v0; a11 += v1; a22 += v2; a33 += v3;
+            }
+        }
+        const size_t cb = (size_t)s * cl.Dall;
+        if (pl == 2) {
+            cl.ucache[cb + cl.slot(hs0, hs0)] = a00;
+            if (n > 1) { cl.ucache[cb + cl.slot(hs0, hs1)] = a01; cl.ucache[cb + cl.slot(hs1, hs1)] = a11; }
+            if (n > 2) { cl.ucache[cb + cl.slot(hs0, hs2)] = a02; cl.ucache[cb + cl.slot(hs1, hs2)] = a12; cl.ucache[cb + cl.slot(hs2, hs2)] = a22; }
+            if (n > 3) { cl.ucache[cb + cl.slot(hs0, hs3)] = a03; cl.ucache[cb + cl.slot(hs1, hs3)] = a13; cl.ucache[cb + cl.slot(hs2, hs3)] = a23; cl.ucache[cb + cl.slot(hs3, hs3)] = a33; }
+        } else {  // haploid entries live in the (h, "missing") slots
+            cl.ucache[cb + cl.slot(hs0, H)] = a00;
+            if (n > 1) cl.ucache[cb + cl.slot(hs1, H)] = a11;
+            if (n > 2) cl.ucache[cb + cl.slot(hs2, H)] = a22;
+            if (n > 3) cl.ucache[cb + cl.slot(hs3, H)] = a33;
+        }
+    }
+    return true;
+}
+
 // ---- VariantClusterGenotyper ctor: sparsity estimate + frequency reset ------------------------
-__device__ void cl_reset_frequencies(Cl &cl) {  // FrequencyDistribution.cpp:46-51,104-115
+__device__ __forceinline__ void cl_reset_frequencies(Cl &cl) {  // FrequencyDistribution.cpp:46-51,104-115
     const double f0 = 1 / static_cast<double>(cl.H);
     for (uint32_t h = 0; h < cl.H; h++) { cl.obs[h] = 0; cl.freq[h] = f0; cl.nz[h] = 1; }
 }
 
-__device__ void cl_construct(Cl &cl, const btg_gibbs_opts &o, uint64_t group_index, uint32_t chain) {
+__device__ __forceinline__ void cl_construct(Cl &cl, const btg_gibbs_opts &o, uint64_t group_index, uint32_t chain) {
     const uint32_t H = cl.H, K = cl.K, S = cl.S;
     const uint32_t *src = cl.u->uniq_idx + cl.u->cl_uniq_off[cl.c];
     for (uint32_t i = 0; i < cl.n_uniq; i++) cl.uniq[i] = src[i];
@@ -405,7 +518,7 @@ __device__ void cl_construct(Cl &cl, const btg_gibbs_opts &o, uint64_t group_ind
 }
 
 // VariantClusterHaplotypes::isMaxHaplotypeVariantKmer (VariantClusterHaplotypes.cpp:159-178)
-__device__ bool cl_is_max_hap_var_kmer(Cl &cl, uint32_t k, uint32_t max_kmers) {
+__device__ __forceinline__ bool cl_is_max_hap_var_kmer(Cl &cl, uint32_t k, uint32_t max_kmers) {
     bool is_max = true;
     const DevUnit &u = *cl.u;
     for (uint64_t e = u.kmer_vh_off[cl.row0 + k]; e < u.kmer_vh_off[cl.row0 + k + 1]; e++) {
@@ -419,7 +532,7 @@ __device__ bool cl_is_max_hap_var_kmer(Cl &cl, uint32_t k, uint32_t max_kmers) {
 
 // VariantClusterGenotyper::reset + VariantClusterHaplotypes::sampleKmerSubset (…Genotyper.cpp:113-129, …Haplotypes.cpp:110-157)
 template <bool MC = false, bool TILE = false>
-__device__ void cl_reset(Cl &cl, const btg_gibbs_opts &o, Philox &prng) {
+__device__ __forceinline__ void cl_reset(Cl &cl, const btg_gibbs_opts &o, Philox &prng) {
     const double rate = (double)o.kmer_subsampling_rate;
     for (uint32_t i = 0; i < cl.H * cl.nvar; i++) cl.cnt[i] = 0;
     for (uint32_t i = cl.n_uniq; i > 1; i--) {  // Fisher-Yates from the back
@@ -469,7 +582,7 @@ __device__ void cl_reset(Cl &cl, const btg_gibbs_opts &o, Philox &prng) {
 
 // VariantClusterGenotyper::updateMulticlusterDiplotypeLogProb (…Genotyper.cpp:569-595): cached terms of the k-mers whose
 // shared multiplicity another cluster of the group has changed are replaced in place (NaN = diplotype not cached)
-__device__ void cl_update_multi_log_prob(Cl &cl, const Tables &T, uint32_t s) {
+__device__ __forceinline__ void cl_update_multi_log_prob(Cl &cl, const Tables &T, uint32_t s) {
     const uint32_t n_msub = cl.misc[kNMultiSub], H = cl.H;
     const uint32_t pa = cl.dipl[s] & 0xFFFFu, pb = cl.dipl[s] >> 16;
     for (uint32_t sub = 0; sub < n_msub; sub++) {
@@ -493,7 +606,7 @@ __device__ void cl_update_multi_log_prob(Cl &cl, const Tables &T, uint32_t s) {
 }
 
 // VariantClusterHaplotypes::updateMulticlusterKmerMultiplicities (VariantClusterHaplotypes.cpp:197-233)
-__device__ void cl_update_multi_multiplicities(Cl &cl, uint32_t s, uint32_t prev) {
+__device__ __forceinline__ void cl_update_multi_multiplicities(Cl &cl, uint32_t s, uint32_t prev) {
     const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
     if (cl.dipl[s] != prev) {
         cl.stats_update[s] = 1;
@@ -515,7 +628,7 @@ __device__ void cl_update_multi_multiplicities(Cl &cl, uint32_t s, uint32_t prev
 
 // VariantClusterGenotyper::calcDiplotypeLogProb (VariantClusterGenotyper.cpp:597-666)
 template <bool MC = false, bool TILE = false>
-__device__ double cl_dipl_log_prob(Cl &cl, const Tables &T, uint32_t s, uint32_t a, uint32_t b) {
+__device__ __forceinline__ double cl_dipl_log_prob(Cl &cl, const Tables &T, uint32_t s, uint32_t a, uint32_t b) {
     double lp = 0;  // logf[] = log(freq[]) of this iteration (cl_sample_diplotypes)
     if (b == NONE) lp += cl.logf[a];
     else if (a == b) lp += 2 * cl.logf[a];
@@ -526,9 +639,7 @@ __device__ double cl_dipl_log_prob(Cl &cl, const Tables &T, uint32_t s, uint32_t
         acc = 0;
         const uint32_t n_sub = cl.misc[kNSub];
         if constexpr (TILE) {
-            const uint32_t g = cl.u->sample_gender[s];
-            for (uint32_t i = 0; i < n_sub; i++)
-                acc += T.logProb(s, (uint8_t)(cl.tileDiplMult(i, a, b) + cl.tile_ic[i * 2 + g]), cl.tile_c[i * cl.S + s]);
+            acc = tile_entry_sum(cl, T, s, a, b, n_sub);
         } else {
             for (uint32_t i = 0; i < n_sub; i++) {
                 const uint32_t k = cl.uniq_sub[i];
@@ -564,7 +675,7 @@ __device__ __forceinline__ void cl_increment(Cl &cl, uint32_t h) {  // Haplotype
 
 // VariantClusterGenotyper::sampleDiplotype (VariantClusterGenotyper.cpp:707-755) + LogDiscreteSampler (DiscreteSampler.cpp:106-126)
 template <bool MC = false, bool TILE = false>
-__device__ void cl_sample_diplotype(Cl &cl, const Tables &T, uint32_t s, uint8_t ploidy, Philox &prng) {
+__device__ __forceinline__ void cl_sample_diplotype(Cl &cl, const Tables &T, uint32_t s, uint8_t ploidy, Philox &prng) {
     uint32_t n = 0;
     double run = 0;
     const uint32_t H = cl.H;
@@ -588,7 +699,7 @@ __device__ void cl_sample_diplotype(Cl &cl, const Tables &T, uint32_t s, uint8_t
     } else {
         cl.cum[n++] = 0;
     }
-    const double x = log(prng.u01()) + run;
+    const double x = m_log(prng.u01()) + run;
     uint32_t idx = 0;
     if (n > 1) {  // upper_bound
         uint32_t lo = 0, hi = n;
@@ -617,7 +728,7 @@ __device__ void cl_sample_diplotype(Cl &cl, const Tables &T, uint32_t s, uint8_t
 }
 
 // VariantClusterHaplotypes::updateAlleleKmerStats (VariantClusterHaplotypes.cpp:235-372), single-cluster groups
-__device__ void cl_add_haplotype_stats(Cl &cl, uint32_t s, uint32_t which, uint32_t h) {  // addHaplotypeKmerStats
+__device__ __forceinline__ void cl_add_haplotype_stats(Cl &cl, uint32_t s, uint32_t which, uint32_t h) {  // addHaplotypeKmerStats
     uint32_t last = NONE;
     for (uint32_t v = 0; v < cl.nvar; v++) {
         const uint16_t a = cl.hapAllele(h, v);
@@ -648,7 +759,7 @@ __device__ __forceinline__ void cl_stats_cache_add(Cl &cl, uint32_t k, uint32_t 
 }
 
 template <bool MC = false>
-__device__ void cl_update_allele_stats(Cl &cl) {
+__device__ __forceinline__ void cl_update_allele_stats(Cl &cl) {
     for (uint32_t s = 0; s < cl.S; s++) {
         const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
         if (cl.stats_update[s]) {
@@ -684,8 +795,8 @@ __device__ void cl_update_allele_stats(Cl &cl) {
 
 // VariantClusterGenotyper::sampleDiplotypes (VariantClusterGenotyper.cpp:668-705)
 template <bool MC = false, bool TILE = false>
-__device__ void cl_sample_diplotypes(Cl &cl, const Tables &T, const uint8_t *ploidy, bool collect, Philox &prng) {
-    for (uint32_t h = 0; h < cl.H; h++) if (cl.nz[h]) cl.logf[h] = log(cl.freq[h]);  // one log per haplotype per iteration
+__device__ __forceinline__ void cl_sample_diplotypes(Cl &cl, const Tables &T, const uint8_t *ploidy, bool collect, Philox &prng) {
+    for (uint32_t h = 0; h < cl.H; h++) if (cl.nz[h]) cl.logf[h] = m_log(cl.freq[h]);  // one log per haplotype per iteration
     for (uint32_t s = 0; s < cl.S; s++) {
         const uint32_t prev = cl.dipl[s];
         if constexpr (MC) { if (cl.misc[kUseMulti]) cl_update_multi_log_prob(cl, T, s); }
@@ -703,7 +814,7 @@ __device__ void cl_sample_diplotypes(Cl &cl, const Tables &T, const uint8_t *plo
 
 // SparseFrequencyDistribution::updateCachedSimplexProbVector (FrequencyDistribution.cpp:143-196);
 // lgamma of the integer arguments comes from a table shared by all clusters
-__device__ uint32_t cl_simplex_vector(Cl &cl, LaneArr<double> out, uint32_t n_obs, uint32_t plus) {
+__device__ __forceinline__ uint32_t cl_simplex_vector(Cl &cl, LaneArr<double> out, uint32_t n_obs, uint32_t plus) {
     const double *lg = cl.u->lgamma_int;
     const uint32_t H = cl.H;
     const double sparsity = cl.fmisc[0];
@@ -728,7 +839,7 @@ __device__ uint32_t cl_simplex_vector(Cl &cl, LaneArr<double> out, uint32_t n_ob
 
 // VariantClusterGenotyper::sampleHaplotypeFrequencies (…Genotyper.cpp:781-785) ->
 // (Sparse)FrequencyDistribution::sampleFrequencies (FrequencyDistribution.cpp:75-94,209-304)
-__device__ void cl_sample_frequencies(Cl &cl, Philox &fr) {
+__device__ __forceinline__ void cl_sample_frequencies(Cl &cl, Philox &fr) {
     const uint32_t H = cl.H;
     const uint32_t n_obs = cl.misc[kNumHap];
     if (n_obs > 0) {
@@ -796,7 +907,7 @@ struct ResultView {
     uint32_t *an, *ac; float *af, *acp; uint8_t *anc; uint16_t *hc;
 };
 
-__device__ void cl_summarise(Cl &cl, const btg_gibbs_opts &o, const uint8_t *ploidy, const ResultView &R) {
+__device__ __forceinline__ void cl_summarise(Cl &cl, const btg_gibbs_opts &o, const uint8_t *ploidy, const ResultView &R) {
     const uint32_t S = cl.S, H = cl.H;
     for (uint32_t v = 0; v < cl.nvar; v++) {
         const uint64_t gv = cl.var0 + v;
@@ -924,7 +1035,7 @@ __global__ void __launch_bounds__(64, MIN_BLOCKS) k_estimate_genotypes(DevUnit d
 // ---- groups with nested clusters ------------------------------------------------------------------
 // VariantClusterGenotyper::updateNestedVariantClusterInfo / updateNestedPloidy / addNestedKmerStats (…Genotyper.cpp:140-206):
 // `cl` is the parent that has just been sampled; the child's incoming info (slot nt) already holds a copy of the parent's own
-__device__ void cl_update_nested_info(Cl &cl, uint32_t nt, uint32_t child_cluster_idx) {
+__device__ __forceinline__ void cl_update_nested_info(Cl &cl, uint32_t nt, uint32_t child_cluster_idx) {
     const DevUnit &u = *cl.u;
     uint64_t dep = u.cl_dep_off[cl.c];
     while (dep < u.cl_dep_off[cl.c + 1] && u.dep_cluster[dep] != child_cluster_idx) dep++;
@@ -958,7 +1069,7 @@ __device__ void cl_update_nested_info(Cl &cl, uint32_t nt, uint32_t child_cluste
 
 // VariantClusterHaplotypes::addNestedHaplotypeKmerStats (VariantClusterHaplotypes.cpp:363-372): the k-mer stats of the enclosing
 // allele(s) are booked on the "missing" allele of every variant of this cluster
-__device__ void cl_add_nested_stats(Cl &cl, uint32_t ns) {
+__device__ __forceinline__ void cl_add_nested_stats(Cl &cl, uint32_t ns) {
     const DevUnit &u = *cl.u;
     for (uint32_t s = 0; s < cl.S; s++) {
         const uint32_t nk = u.nest_k[(size_t)ns * cl.S + s];
@@ -1097,6 +1208,7 @@ struct NoiseState {
     uint32_t *trace_row;
     const double *lg;      // lg[i] = lgamma((double)i), i < n_lg (the Poisson rows need lgamma(count + 1) of integers only)
     uint32_t n_lg;
+    unsigned long long *phase_ns;  // optional (BTG_NOISE_PHASES=1): time block 0 spends in [fill, sample, exchange+update, release] per chain
 };
 
 // noiseCountLogPmf with log(rate) hoisted and lgamma of the integer argument read from the table (same values, same order of
@@ -1176,7 +1288,7 @@ __global__ void k_noise_update(NoiseState ns, uint32_t S, float prior_shape, flo
 // sequential code (so the cached value is bit-identical).  Used for large clusters in the lock-step noise chain,
 // where the slowest cluster sets the pace of every iteration.
 // A cluster may be shared by `parts` warps (anywhere in the grid): entries are dealt to them in rounds of 32.
-__device__ void cl_fill_cache_warp(Cl &cl, const Tables &T, const uint8_t *ploidy, uint32_t lane, uint32_t part, uint32_t parts) {
+__device__ __forceinline__ void cl_fill_cache_warp(Cl &cl, const Tables &T, const uint8_t *ploidy, uint32_t lane, uint32_t part, uint32_t parts) {
     const uint32_t H = cl.H, n_sub = cl.misc[kNSub];
     uint32_t e = 0;
     for (uint32_t s = 0; s < cl.S; s++) {
@@ -1192,18 +1304,14 @@ __device__ void cl_fill_cache_warp(Cl &cl, const Tables &T, const uint8_t *ploid
                 const uint32_t bb = pl == 2 ? b : NONE;
                 const size_t ci = (size_t)s * cl.Dall + cl.slot(a, bb == NONE ? H : bb);
                 if (cl.ucache[ci] == cl.ucache[ci]) continue;  // already cached
-                double acc = 0;
-                const uint32_t g = cl.u->sample_gender[s];
-                for (uint32_t i = 0; i < n_sub; i++)
-                    acc += T.logProb(s, (uint8_t)(cl.tileDiplMult(i, a, bb) + cl.tile_ic[i * 2 + g]), cl.tile_c[i * cl.S + s]);
-                cl.ucache[ci] = acc;
+                cl.ucache[ci] = tile_entry_sum(cl, T, s, a, bb, n_sub);
             }
         }
     }
 }
 
 // one lock-step iteration of one cluster by a single thread (sampleGenotypesCallback body without the noise counts)
-__device__ void noise_iteration_thread(Cl &cl, const DevUnit &du, const Tables &T, const btg_gibbs_opts &o, bool collect) {
+__device__ __forceinline__ void noise_iteration_thread(Cl &cl, const DevUnit &du, const Tables &T, const btg_gibbs_opts &o, bool collect) {
     const uint64_t gidx = o.group_index_base + cl.g;
     const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
     Philox prng, fr;
@@ -1215,6 +1323,36 @@ __device__ void noise_iteration_thread(Cl &cl, const DevUnit &du, const Tables &
     fr.save(cl.misc, kRng1);
 }
 
+// Grid-wide barrier of the persistent chain kernel (all blocks are co-resident: cooperative launch).  One thread per block
+// arrives on a counter and then polls a generation word WITH BACK-OFF.  cooperative_groups' grid.sync() polls without
+// pause: with ~1200 blocks waiting for the few warps that still work, the polls queue up on the one L2 slice that holds the
+// barrier word and every load of the working warps that maps to that slice waits behind them (measured: ~50 us of fixed cost
+// per phase and 0.5 us per dependent load, profiles/r1_noise_chain_phases.txt).
+struct GridBarrier {
+    unsigned int *count, *gen;
+};
+__device__ __forceinline__ void grid_barrier(const GridBarrier &b) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int g;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(b.gen) : "memory");
+        __threadfence();  // this block's writes are visible before its arrival
+        if (atomicAdd(b.count, 1u) == gridDim.x - 1) {
+            *b.count = 0;
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(b.gen), "r"(g + 1) : "memory");
+        } else {
+            unsigned int now, ns_sleep = 64;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(b.gen) : "memory");
+                if (now != g) break;
+                __nanosleep(ns_sleep);
+                if (ns_sleep < 1024) ns_sleep *= 2;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // One whole chain of estimateNoise as ONE persistent cooperative kernel (InferenceEngine.cpp:191-253): every thread keeps its
 // clusters' state hot in L1 across the 350 iterations; the per-iteration "join + merge + sampleNoiseParameters" of the
 // reference (thread spawn/join per iteration, InferenceEngine.cpp:213-226) becomes two grid-wide barriers around block 0's
@@ -1222,10 +1360,9 @@ __device__ void noise_iteration_thread(Cl &cl, const DevUnit &du, const Tables &
 // joint = 0: estimateNoise (fresh genotypers each chain, streams of chain `chain`, nothing collected)
 // joint = 1: estimateNoiseAndGenotypes (InferenceEngine.cpp:384-472): genotypers are constructed in the first chain only and
 //            persist (streams of chain 0), samples are collected after the burn-in
-__global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg_gibbs_opts o, const uint32_t *sel, uint32_t n_sel, uint32_t n_big, uint32_t chain,
+__global__ void __launch_bounds__(256, 2) k_noise_chain(DevUnit du, Tables T, btg_gibbs_opts o, const uint32_t *sel, uint32_t n_sel, uint32_t n_big, uint32_t chain,
                                                        uint32_t iters, NoiseState ns, float prior_shape, float prior_scale, unsigned long long *hist, int joint,
-                                                       PeerExchange px, const uint32_t *fill_tasks, uint32_t n_fill_tasks) {
-    cg::grid_group grid = cg::this_grid();
+                                                       PeerExchange px, const uint32_t *fill_tasks, uint32_t n_fill_tasks, GridBarrier gb) {
     __shared__ unsigned long long sh_tot[kMailRow];
     __shared__ double sh_rates[BTG_MAX_SAMPLES];
     // getNoiseCounts of the block's clusters: only (n_obs, sum) per sample are ever read from the merged CountAllocation,
@@ -1251,26 +1388,91 @@ __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg
         fr.save(cl.misc, kRng1);
     }
     if (blockIdx.x == 0 && ns.trace) noise_update_block(ns, du.S, prior_shape, prior_scale, o.random_seed, 3, 0, (double)chain, 0, 1, sh_rates);
-    grid.sync();
+    grid_barrier(gb);
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
+#if BTG_NOISE_TIMING
+    unsigned long long sub_acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // per-thread clock sums of the one-thread sub-steps, flushed once at the end
+#endif
+    const bool timing = ns.phase_ns && blockIdx.x == 0 && threadIdx.x == 0;
+    unsigned long long t_prev = timing ? global_timer_ns() : 0;
+    auto lap = [&](int phase) {
+        if (timing) { const unsigned long long t = global_timer_ns(); ns.phase_ns[phase] += t - t_prev; t_prev = t; }
+    };
     for (uint32_t it = 1; it <= iters; it++) {
         if (threadIdx.x < 2 * du.S) sh_stat[threadIdx.x] = 0;
         __syncthreads();
         // phase A: the diplotype caches of the large clusters sel[0 .. n_big) are filled by the whole grid: fill task t =
         // (cluster, part, parts) gives one warp every parts-th round of 32 cache entries of that cluster, so the slowest
         // cluster no longer sets the pace of the iteration with a single warp
-        for (uint32_t t = tid >> 5; t < n_fill_tasks; t += nthreads >> 5) {
+        // (tasks are dealt from the LAST warp downwards: the one-thread clusters below occupy the first threads of the grid)
+        for (uint32_t t = (nthreads >> 5) - 1 - (tid >> 5); t < n_fill_tasks; t += nthreads >> 5) {
+            const unsigned long long t_in = BTG_NOISE_TIMING && ns.phase_ns ? global_timer_ns() : 0;
             Cl cl;
             cl.bind(du, sel[fill_tasks[3 * t]]);
             cl_fill_cache_warp(cl, T, du.group_ploidy + (size_t)cl.g * du.S, tid & 31u, fill_tasks[3 * t + 1], fill_tasks[3 * t + 2]);
+            if (BTG_NOISE_TIMING && ns.phase_ns) { const unsigned long long v = ((global_timer_ns() - t_in) << 32) | cl.c; atomicMax(ns.phase_ns + 4, v); atomicMax(ns.phase_ns + 8 + 3 * (it - 1), v); }
         }
-        if (n_fill_tasks) { __threadfence(); grid.sync(); }
+        // ... while the one-thread clusters sel[n_big .. n_sel) take their whole step in the same phase (they do not depend on the
+        // fill tasks): the warps that hold no fill task are not idle at the barrier while the large caches are filled
+        for (uint32_t i = n_big + tid; i < n_sel; i += nthreads) {  // sampleGenotypesCallback
+            const unsigned long long t_in = BTG_NOISE_TIMING && ns.phase_ns ? global_timer_ns() : 0;
+#if BTG_NOISE_TIMING
+            const bool sub = ns.phase_ns != nullptr;
+            long long ck = sub ? clock64() : 0;
+            auto tick = [&](int k) { if (sub) { const long long now = clock64(); sub_acc[k] += (unsigned int)(now - ck); ck = now; } };
+#else
+            auto tick = [](int) {};
+#endif
+            Cl cl;
+            cl.bind(du, sel[i]);
+            tick(0);
+            const uint8_t *ploidy_i = du.group_ploidy + (size_t)cl.g * du.S;
+            cl_fill_cache_rows(cl, T, ploidy_i);  // > 4 live haplotypes: entries are filled on demand
+            tick(1);
+            {
+                const uint64_t gidx = o.group_index_base + cl.g;
+                Philox prng, fr;
+                prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+                fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
+                tick(2);
+                cl_sample_diplotypes<false, true>(cl, T, ploidy_i, joint && it > o.gibbs_burn_in, prng);
+                tick(3);
+                cl_sample_frequencies(cl, fr);
+                tick(4);
+                prng.save(cl.misc, kRng0);
+                fr.save(cl.misc, kRng1);
+                tick(5);
+            }
+#if BTG_NOISE_TIMING
+            if (sub) sub_acc[8]++;
+#endif
+            if (BTG_NOISE_TIMING && ns.phase_ns) { const unsigned long long v = ((global_timer_ns() - t_in) << 32) | cl.c; atomicMax(ns.phase_ns + 6, v); atomicMax(ns.phase_ns + 8 + 3 * (it - 1) + 2, v); }
+            const uint32_t n_sub = cl.misc[kNSub];
+            for (uint32_t s = 0; s < cl.S; s++) {  // getNoiseCounts
+                const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
+                uint32_t n0 = 0, c0 = 0;
+                const uint32_t g = du.sample_gender[s];
+#pragma unroll 4
+                for (uint32_t j = 0; j < n_sub; j++) {
+                    const uint8_t mm = (uint8_t)(cl.tileDiplMult(j, da, db) + cl.tile_ic[j * 2 + g]), cc = cl.tile_c[j * cl.S + s];
+                    n0 += mm == 0; c0 += mm == 0 ? cc : 0u;
+                }
+                if (n0) { atomicAdd(sh_stat + 2 * s, (unsigned long long)n0); atomicAdd(sh_stat + 2 * s + 1, (unsigned long long)c0); }
+            }
+            tick(6);
+            for (uint32_t j = 0; j < cl.S * cl.Dall; j++) cl.ucache[j] = nan;  // clearGenotyperCache
+            tick(7);
+        }
+        if (n_fill_tasks) grid_barrier(gb);
+        lap(0);
         // phase B: sel[0 .. n_big): one WARP each (lane 0 samples from the filled cache; counts and cache clear by all lanes)
         for (uint32_t i = tid >> 5; i < n_big; i += nthreads >> 5) {
             const uint32_t lane = tid & 31u;
+            const unsigned long long t_in = BTG_NOISE_TIMING && ns.phase_ns ? global_timer_ns() : 0;
             Cl cl;
             cl.bind(du, sel[i]);
             if (lane == 0) noise_iteration_thread(cl, du, T, o, joint && it > o.gibbs_burn_in);
+            if (BTG_NOISE_TIMING && ns.phase_ns && lane == 0) { const unsigned long long v = ((global_timer_ns() - t_in) << 32) | cl.c; atomicMax(ns.phase_ns + 5, v); atomicMax(ns.phase_ns + 8 + 3 * (it - 1) + 1, v); }
             __syncwarp();
             const uint32_t n_sub = cl.misc[kNSub];
             for (uint32_t s = 0; s < cl.S; s++) {  // getNoiseCounts
@@ -1284,26 +1486,10 @@ __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg
             for (uint32_t j = lane; j < cl.S * cl.Dall; j += 32) cl.ucache[j] = nan;  // clearGenotyperCache
             __syncwarp();
         }
-        // sel[n_big .. n_sel): small clusters, one thread each
-        for (uint32_t i = n_big + tid; i < n_sel; i += nthreads) {  // sampleGenotypesCallback
-            Cl cl;
-            cl.bind(du, sel[i]);
-            noise_iteration_thread(cl, du, T, o, joint && it > o.gibbs_burn_in);
-            const uint32_t n_sub = cl.misc[kNSub];
-            for (uint32_t s = 0; s < cl.S; s++) {  // getNoiseCounts
-                const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
-                uint32_t n0 = 0, c0 = 0;
-                const uint32_t g = du.sample_gender[s];
-                for (uint32_t j = 0; j < n_sub; j++)
-                    if ((uint8_t)(cl.tileDiplMult(j, da, db) + cl.tile_ic[j * 2 + g]) == 0) { n0++; c0 += cl.tile_c[j * cl.S + s]; }
-                if (n0) { atomicAdd(sh_stat + 2 * s, (unsigned long long)n0); atomicAdd(sh_stat + 2 * s + 1, (unsigned long long)c0); }
-            }
-            for (uint32_t j = 0; j < cl.S * cl.Dall; j++) cl.ucache[j] = nan;  // clearGenotyperCache
-        }
         __syncthreads();
         if (threadIdx.x < 2 * du.S && sh_stat[threadIdx.x]) atomicAdd(hist + threadIdx.x, sh_stat[threadIdx.x]);
-        __threadfence();
-        grid.sync();
+        grid_barrier(gb);
+        lap(1);
         if (blockIdx.x == 0) {
             if (px.world > 1) {  // sharded unit: add up the ranks' statistics over peer memory (comm.cuh) before the draw
                 if (threadIdx.x < 2 * du.S) sh_tot[threadIdx.x] = hist[threadIdx.x];
@@ -1313,9 +1499,14 @@ __global__ void __launch_bounds__(64, 8) k_noise_chain(DevUnit du, Tables T, btg
             }
             noise_update_block(ns, du.S, prior_shape, prior_scale, o.random_seed, 1, o.gibbs_burn_in < it, (double)chain, (double)it, 1, sh_rates);
         }
-        __threadfence();
-        grid.sync();
+        lap(2);
+        grid_barrier(gb);
+        lap(3);
     }
+#if BTG_NOISE_TIMING
+    if (ns.phase_ns && sub_acc[8])
+        for (int k = 0; k < 9; k++) atomicAdd(ns.phase_ns + 8 + 3 * (size_t)iters + k, sub_acc[k]);
+#endif
 }
 
 __global__ void k_noise_rng_init(uint32_t *rng, uint32_t seed) {
@@ -1597,6 +1788,15 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
         SL.f64_off = f64_total; SL.u32_off = u32_total; SL.u8_off = u8_total;
         f64_total += a.f64 * 32; u32_total += a.u32 * 32; u8_total += a.u8 * 32;
     }
+    std::vector<uint64_t> tile_off(C ? C : 1, ~0ull);
+    uint64_t tile_total = 0;
+    for (uint32_t c = 0; c < C; c++)
+        if (u->h_fill_cost[c] > kBigFillCost) { tile_off[c] = tile_total; tile_total += ((uint64_t)dims[c].nu * (dims[c].H + S + 2) + 31) & ~31ull; }
+    du.big_tile_off = keep(upload(tile_off.data(), C, ok));
+    uint8_t *tile_pool = nullptr;
+    ok = ok && cudaMalloc(&tile_pool, tile_total + 32) == cudaSuccess;
+    keep(tile_pool);
+    du.big_tile_pool = tile_pool;
     du.layout = keep(upload(u->h_layout.data(), C, ok));
     du.slots = keep(upload(u->h_slots.data(), u->h_slots.size(), ok));
     du.order = keep(upload(order.data(), C, ok));
@@ -1800,6 +2000,11 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
     ns.mean_rates = (double *)dalloc(S * 8);
     ns.trace = trace_out ? (double *)dalloc(trace_rows * (2 + S) * 8) : nullptr;
     ns.rng = (uint32_t *)dalloc(8 * 4);
+    GridBarrier gb{};
+    gb.count = (unsigned int *)dalloc(256);   // count and generation in separate 128-byte lines
+    gb.gen = gb.count ? gb.count + 32 : nullptr;
+    const bool want_phases = getenv("BTG_NOISE_PHASES") && atoi(getenv("BTG_NOISE_PHASES"));
+    ns.phase_ns = want_phases ? (unsigned long long *)dalloc((8 + 3 * (size_t)iters + 16) * 8) : nullptr;  // [4 phases, 3 maxima, spare][iteration][3 maxima]
     const uint32_t n_lg = 1024;
     double *lg_tab = (double *)dalloc(n_lg * 8);
     ns.lg = lg_tab; ns.n_lg = n_lg;
@@ -1880,8 +2085,7 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
                 if (g >= base && g < base + G) sel.push_back((uint32_t)u->h_group_cluster_off[g - base]);  // this rank's share
             }
             // large clusters first (one warp each in the chain kernel), then by position in the cost order (neighbours share arena slots)
-            const uint32_t big_cost = getenv("BTG_NOISE_BIG") ? (uint32_t)atoi(getenv("BTG_NOISE_BIG")) : 128u;
-            auto is_big = [&](uint32_t c) { return u->h_fill_cost[c] > big_cost; };
+            auto is_big = [&](uint32_t c) { return u->h_fill_cost[c] > kBigFillCost; };  // the clusters with a dense tile
             std::sort(sel.begin(), sel.end(), [&](uint32_t a, uint32_t b) {
                 const bool ba = is_big(a), bb = is_big(b);
                 return ba != bb ? ba : u->h_layout[a].pos < u->h_layout[b].pos;
@@ -1905,18 +2109,22 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
             cudaStreamSynchronize(s);  // sel is reused by the host next chain
             const uint32_t n_sel = (uint32_t)sel.size();
             if (n_sel || world > 1) {  // a rank with nothing selected still takes part in every exchange
+                // (a shared-memory window of the log-pmf tables was tried and made the fill slower: the chain is bound by instruction issue
+                //  at 16 warps/SM, not by the gathers — profiles/r1_noise_chain_phases.txt)
+                const size_t smem = 0;
+                const uint32_t bs = 256;
                 int per_sm = 0;
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_noise_chain, 64, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_noise_chain, bs, smem);
                 const uint32_t max_blocks = (uint32_t)std::max(1, per_sm) * (uint32_t)ctx().sm_count;
                 const uint32_t want_threads = std::max<uint32_t>({n_big * 32u, n_sel - n_big, (uint32_t)(tasks.size() / 3) * 32u});
-                const uint32_t grid = std::max(1u, std::min((want_threads + 63) / 64, max_blocks));
+                const uint32_t grid = std::max(1u, std::min((want_threads + bs - 1) / bs, max_blocks));
                 uint32_t chain_id = chain + 1, n_sel_arg = n_sel, iters_arg = iters;
                 float ps = cd->prior_shape, pc = cd->prior_scale;
                 btg_gibbs_opts o = *opts;
                 if (comm) { px.seq0 = comm->seq; comm->seq += iters; }
                 uint32_t n_tasks = (uint32_t)(tasks.size() / 3);
-                void *args[] = {&u->du, &T, &o, &d_sel, &n_sel_arg, &n_big, &chain_id, &iters_arg, &ns, &ps, &pc, &hist, &joint, &px, &d_tasks, &n_tasks};
-                cudaError_t e = cudaLaunchCooperativeKernel((void *)k_noise_chain, dim3(grid), dim3(64), args, 0, s);
+                void *args[] = {&u->du, &T, &o, &d_sel, &n_sel_arg, &n_big, &chain_id, &iters_arg, &ns, &ps, &pc, &hist, &joint, &px, &d_tasks, &n_tasks, &gb};
+                cudaError_t e = cudaLaunchCooperativeKernel((void *)k_noise_chain, dim3(grid), dim3(bs), args, smem, s);
                 BTG_LAUNCHED();
                 if (e != cudaSuccess) { set_error("cooperative launch failed: %s", cudaGetErrorString(e)); rc = BTG_ECUDA; break; }
             } else {
@@ -1938,6 +2146,48 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
             if (trace_out) cudaMemcpyAsync(trace_out, ns.trace, trace_rows * (2 + S) * 8, cudaMemcpyDeviceToHost, s);
             cudaError_t e = cudaStreamSynchronize(s);
             if (e != cudaSuccess) { set_error("noise estimation failed: %s", cudaGetErrorString(e)); rc = BTG_ECUDA; }
+            if (rc == BTG_OK && ns.phase_ns) {
+                unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                cudaMemcpy(ph, ns.phase_ns, sizeof ph, cudaMemcpyDeviceToHost);
+                if (BTG_NOISE_TIMING) {
+                    unsigned long long sub[16];
+                    cudaMemcpy(sub, ns.phase_ns + 8 + 3 * (size_t)iters, sizeof sub, cudaMemcpyDeviceToHost);
+                    const char *nm[8] = {"bind", "fill rows", "rng load", "sample diplotypes", "sample frequencies", "rng save", "noise counts", "clear cache"};
+                    if (sub[8]) {
+                        fprintf(stderr, "[btgpu]   one-thread clusters, mean cycles per cluster-iteration:");
+                        for (int k = 0; k < 8; k++) fprintf(stderr, " %s %.0f;", nm[k], (double)sub[k] / (double)sub[8]);
+                        fprintf(stderr, "\n");
+                    }
+                }
+                const char *what[3] = {"fill task", "large-cluster owner", "one-thread cluster"};
+                if (BTG_NOISE_TIMING) {   // per-iteration maxima (accumulated over the chains by atomicMax): median over iterations and the cluster that is most often the slowest
+                    std::vector<unsigned long long> it_max(3 * (size_t)iters);
+                    cudaMemcpy(it_max.data(), ns.phase_ns + 8, it_max.size() * 8, cudaMemcpyDeviceToHost);
+                    for (int k = 0; k < 3; k++) {
+                        std::vector<double> us;
+                        std::vector<uint32_t> who;
+                        for (uint32_t i = 10; i < iters; i++) { us.push_back((it_max[3 * i + k] >> 32) / 1e3); who.push_back((uint32_t)(it_max[3 * i + k] & 0xFFFFFFFFu)); }
+                        if (us.empty()) continue;
+                        std::vector<double> sorted_us = us;
+                        std::sort(sorted_us.begin(), sorted_us.end());
+                        std::sort(who.begin(), who.end());
+                        uint32_t best = who[0], best_n = 0, run = 0;
+                        for (size_t i = 0; i < who.size(); i++) { run = (i && who[i] == who[i - 1]) ? run + 1 : 1; if (run > best_n) { best_n = run; best = who[i]; } }
+                        fprintf(stderr, "[btgpu]   per-iteration slowest %s: median %.1f us, p90 %.1f us; most often cluster %u (%u of %zu iterations; H %u, variants %llu, fill cost %u)\n",
+                                what[k], sorted_us[sorted_us.size() / 2], sorted_us[sorted_us.size() * 9 / 10], best, best_n, who.size(), best < u->du.C ? u->h_nhap[best] : 0,
+                                best < u->du.C ? (unsigned long long)(u->h_cl_var_off[best + 1] - u->h_cl_var_off[best]) : 0ull, best < u->du.C ? u->h_fill_cost[best] : 0);
+                    }
+                }
+                for (int k = 0; k < 3 && BTG_NOISE_TIMING; k++) {
+                    const uint32_t c = (uint32_t)(ph[4 + k] & 0xFFFFFFFFu);
+                    if (ph[4 + k] && c < u->du.C)
+                        fprintf(stderr, "[btgpu]   slowest %s: %.1f us, cluster %u (H %u, variants %llu, fill cost %u)\n", what[k], (ph[4 + k] >> 32) / 1e3, c, u->h_nhap[c],
+                                (unsigned long long)(u->h_cl_var_off[c + 1] - u->h_cl_var_off[c]), u->h_fill_cost[c]);
+                }
+                const double n_it = (double)opts->n_chains * iters;
+                fprintf(stderr, "[btgpu] noise chain phases, us per iteration (block 0): fill %.1f  sample %.1f  exchange+update %.1f  release %.1f\n",
+                        ph[0] / n_it / 1e3, ph[1] / n_it / 1e3, ph[2] / n_it / 1e3, ph[3] / n_it / 1e3);
+            }
             if (rc == BTG_OK && comm && world > 1) {
                 uint32_t flag = 0;
                 cudaMemcpy(&flag, comm->error, 4, cudaMemcpyDeviceToHost);

@@ -1,0 +1,10 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r1k_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r1k_pytest.log
+tail -4 gpurun_out/r1k_pytest.log
+timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/r1k_bench.json 2> gpurun_out/r1k_bench.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r1k_bench_reference.json 2> gpurun_out/r1k_bench_reference.err; echo "ref rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_table_add_sample -s 2 -c 1 -o gpurun_out/r1k_stream_full -f python tools/prof_stream.py > gpurun_out/r1k_ncu_stream.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r1k_launches.csv python bench.py --steps 1 --warmup 1 --timed-only > gpurun_out/r1k_launches.log 2>&1
+timeout 120 python tools/prof_stream.py > gpurun_out/r1k_stream.txt 2>&1
+ls -la gpurun_out | grep r1k
