@@ -4,12 +4,13 @@ is missing or no B200 is visible, loading / btg_init fails loudly."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
-LIB_PATH = ROOT / "bayestyper_b200" / "lib" / "libbtgpu.so"
+LIB_PATH = Path(os.environ["BTG_LIB"]) if os.environ.get("BTG_LIB") else ROOT / "bayestyper_b200" / "lib" / "libbtgpu.so"   # BTG_LIB: build variants for experiments
 
 u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
 u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")

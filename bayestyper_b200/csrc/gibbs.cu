@@ -26,6 +26,7 @@
 #include <numeric>
 #include <type_traits>
 #include <vector>
+#include <chrono>
 
 #include <cooperative_groups.h>
 
@@ -56,7 +57,7 @@ __host__ __device__ inline bool floatCompare(float a, float b) {  // Utils.hpp:8
     return (a == b) || (fabsf(a - b) < fabsf(a < b ? a : b) * kFloatEps100);
 }
 __host__ __device__ inline bool floatLess(float a, float b) { return (a < b) && !floatCompare(a, b); }
-__device__ __forceinline__ double logAddition(double a, double b) {  // Utils.hpp:105-124
+BTG_LEAF double logAddition(double a, double b) {  // Utils.hpp:105-124
     return a < b ? b + m_log1p(m_exp(a - b)) : a + m_log1p(m_exp(b - a));
 }
 
@@ -166,7 +167,10 @@ struct TileArr {
     uint32_t stride;
     __device__ __forceinline__ uint8_t &operator[](uint32_t i) const { return p[(size_t)i * stride]; }
 };
-constexpr uint32_t kBigFillCost = 128;  // table lookups per cache fill above which a cluster is "large" (warp-cooperative)
+constexpr uint32_t kBigFillCost = 128;
+constexpr uint32_t kChainSplit = 20;      // virtual threads of a chain-split cluster (chain c runs on thread c % kChainSplit)
+constexpr uint32_t kSplitFillCost = 64;   // clusters above this fill cost are chain-split in the default mode (sweep: profiles/r1_gibbs_tail.txt)
+constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 
 struct DevUnit {
     uint32_t S, G, C;
@@ -196,6 +200,11 @@ struct DevUnit {
     uint8_t *big_tile_pool;
     // nested groups / multicluster k-mers
     uint32_t n_regular;          // order[0 .. n_regular): clusters of single-cluster groups
+    // chain-split clusters: large single-cluster groups whose chains run as kChainSplit independent threads (default mode)
+    uint32_t n_split;
+    const uint32_t *split_cluster;   // [n_split] cluster
+    const uint32_t *split_pos;       // [n_split][kChainSplit] arena position of virtual thread v (v = 0: the cluster's own position)
+    const uint32_t *split_of;        // [C] index into split_cluster or NONE32
     uint32_t n_nested_groups;
     const uint32_t *nested_groups;
     const uint32_t *k_shared;    // [rows] shared multiplicity record of a multicluster k-mer
@@ -267,9 +276,10 @@ struct Cl {
     LaneArr<uint8_t> nz, uncovered, stats_update, sample_multi;
     TileArr tile_m, tile_c, tile_ic;
 
-    __device__ void bind(const DevUnit &du, uint32_t cluster) {
+    __device__ void bind(const DevUnit &du, uint32_t cluster, uint32_t pos_override = 0xFFFFFFFFu) {
         u = &du; c = cluster;
-        const ClusterLayout L = du.layout[c];
+        ClusterLayout L = du.layout[c];
+        if (pos_override != 0xFFFFFFFFu) L.pos = pos_override;
         g = L.group;
         S = du.S;
         H = du.cl_nhap[c];
@@ -531,9 +541,13 @@ __device__ __forceinline__ bool cl_is_max_hap_var_kmer(Cl &cl, uint32_t k, uint3
 }
 
 // VariantClusterGenotyper::reset + VariantClusterHaplotypes::sampleKmerSubset (…Genotyper.cpp:113-129, …Haplotypes.cpp:110-157)
-template <bool MC = false, bool TILE = false>
+template <bool MC = false, bool TILE = false, bool FRESH = false>
 __device__ __forceinline__ void cl_reset(Cl &cl, const btg_gibbs_opts &o, Philox &prng) {
     const double rate = (double)o.kmer_subsampling_rate;
+    if constexpr (FRESH) {  // chains are independent in the default mode: every chain shuffles the original order
+        const uint32_t *src = cl.u->uniq_idx + cl.u->cl_uniq_off[cl.c];
+        for (uint32_t i = 0; i < cl.n_uniq; i++) cl.uniq[i] = src[i];
+    }
     for (uint32_t i = 0; i < cl.H * cl.nvar; i++) cl.cnt[i] = 0;
     for (uint32_t i = cl.n_uniq; i > 1; i--) {  // Fisher-Yates from the back
         const uint32_t j = prng.uniform_int(i);
@@ -675,23 +689,32 @@ __device__ __forceinline__ void cl_increment(Cl &cl, uint32_t h) {  // Haplotype
 
 // VariantClusterGenotyper::sampleDiplotype (VariantClusterGenotyper.cpp:707-755) + LogDiscreteSampler (DiscreteSampler.cpp:106-126)
 template <bool MC = false, bool TILE = false>
-__device__ __forceinline__ void cl_sample_diplotype(Cl &cl, const Tables &T, uint32_t s, uint8_t ploidy, Philox &prng) {
+__device__ __forceinline__ void cl_sample_diplotype(Cl &cl, const Tables &T, uint32_t s, uint8_t ploidy, Philox &prng, uint64_t nzm) {
     uint32_t n = 0;
     double run = 0;
     const uint32_t H = cl.H;
+    // next haplotype >= from with a non-zero frequency (H if none).  For H <= 64 the flags arrive as the bit mask nzm, so the
+    // pair enumeration visits only live pairs instead of testing H^2/2 flags in the arena (a cluster with 16 haplotypes of
+    // which 4 are live: 10 steps instead of 136 loads); the order of enumeration is unchanged.
+    const bool use_mask = H <= 64;
+    auto next = [&](uint32_t from) -> uint32_t {
+        if (use_mask) {
+            const uint64_t m = from < 64 ? nzm >> from : 0;
+            return m ? from + (uint32_t)__ffsll((long long)m) - 1 : H;
+        }
+        while (from < H && !cl.nz[from]) from++;
+        return from;
+    };
     if (ploidy == 2) {
-        for (uint32_t a = 0; a < H; a++) {
-            if (!cl.nz[a]) continue;
-            for (uint32_t b = a; b < H; b++) {
-                if (!cl.nz[b]) continue;
+        for (uint32_t a = next(0); a < H; a = next(a + 1)) {
+            for (uint32_t b = a; b < H; b = next(b + 1)) {
                 const double lp = cl_dipl_log_prob<MC, TILE>(cl, T, s, a, b);
                 run = n == 0 ? lp : logAddition(lp, run);
                 cl.cum[n++] = run;
             }
         }
     } else if (ploidy == 1) {
-        for (uint32_t a = 0; a < H; a++) {
-            if (!cl.nz[a]) continue;
+        for (uint32_t a = next(0); a < H; a = next(a + 1)) {
             const double lp = cl_dipl_log_prob<MC, TILE>(cl, T, s, a, NONE);
             run = n == 0 ? lp : logAddition(lp, run);
             cl.cum[n++] = run;
@@ -710,17 +733,15 @@ __device__ __forceinline__ void cl_sample_diplotype(Cl &cl, const Tables &T, uin
     uint32_t da = NONE, db = NONE;
     if (ploidy == 2) {
         uint32_t i = 0;
-        for (uint32_t a = 0; a < H && da == NONE; a++) {
-            if (!cl.nz[a]) continue;
-            for (uint32_t b = a; b < H; b++) {
-                if (!cl.nz[b]) continue;
+        for (uint32_t a = next(0); a < H && da == NONE; a = next(a + 1)) {
+            for (uint32_t b = a; b < H; b = next(b + 1)) {
                 if (i == idx) { da = a; db = b; break; }
                 i++;
             }
         }
     } else if (ploidy == 1) {
         uint32_t i = 0;
-        for (uint32_t a = 0; a < H; a++) { if (!cl.nz[a]) continue; if (i == idx) { da = a; break; } i++; }
+        for (uint32_t a = next(0); a < H; a = next(a + 1)) { if (i == idx) { da = a; break; } i++; }
     }
     cl.dipl[s] = (da & 0xFFFFu) | (db << 16);
     cl_increment(cl, da);
@@ -796,11 +817,13 @@ __device__ __forceinline__ void cl_update_allele_stats(Cl &cl) {
 // VariantClusterGenotyper::sampleDiplotypes (VariantClusterGenotyper.cpp:668-705)
 template <bool MC = false, bool TILE = false>
 __device__ __forceinline__ void cl_sample_diplotypes(Cl &cl, const Tables &T, const uint8_t *ploidy, bool collect, Philox &prng) {
-    for (uint32_t h = 0; h < cl.H; h++) if (cl.nz[h]) cl.logf[h] = m_log(cl.freq[h]);  // one log per haplotype per iteration
+    uint64_t nzm = 0;  // non-zero flags of the first 64 haplotypes as a bit mask
+    for (uint32_t h = 0; h < cl.H; h++)
+        if (cl.nz[h]) { cl.logf[h] = m_log(cl.freq[h]); if (h < 64) nzm |= 1ull << h; }  // one log per haplotype per iteration
     for (uint32_t s = 0; s < cl.S; s++) {
         const uint32_t prev = cl.dipl[s];
         if constexpr (MC) { if (cl.misc[kUseMulti]) cl_update_multi_log_prob(cl, T, s); }
-        cl_sample_diplotype<MC, TILE>(cl, T, s, ploidy[s], prng);
+        cl_sample_diplotype<MC, TILE>(cl, T, s, ploidy[s], prng, nzm);
         if constexpr (MC) cl_update_multi_multiplicities(cl, s, prev);
         else if (cl.dipl[s] != prev) cl.stats_update[s] = 1;  // …Haplotypes.cpp:199-201
         if (collect) {
@@ -818,7 +841,7 @@ __device__ __forceinline__ uint32_t cl_simplex_vector(Cl &cl, LaneArr<double> ou
     const double *lg = cl.u->lgamma_int;
     const uint32_t H = cl.H;
     const double sparsity = cl.fmisc[0];
-    const double ls = log(sparsity), l1s = log(1 - sparsity);
+    const double ls = m_log(sparsity), l1s = m_log(1 - sparsity);
     double prob_z = plus * ls + (H - plus) * l1s;
     double prob_t = lg[plus] - lg[n_obs + plus];
     double row_sum = 0 + prob_z + prob_t;
@@ -829,11 +852,11 @@ __device__ __forceinline__ uint32_t cl_simplex_vector(Cl &cl, LaneArr<double> ou
         prob_z = j * ls + (H - j) * l1s;
         prob_t = lg[j] - lg[n_obs + j];
         const double prob_eq = cardinal + prob_z + prob_t;
-        row_sum += log(1 + exp(prob_eq - row_sum));
+        row_sum += m_log(1 + m_exp(prob_eq - row_sum));
         out[len++] = row_sum;
         if (doubleCompare(out[len - 1], out[len - 2])) break;
     }
-    for (uint32_t i = 0; i < len; i++) out[i] = exp(out[i] - row_sum);
+    for (uint32_t i = 0; i < len; i++) out[i] = m_exp(out[i] - row_sum);
     return len;
 }
 
@@ -846,7 +869,7 @@ __device__ __forceinline__ void cl_sample_frequencies(Cl &cl, Philox &fr) {
         if (!cl.misc[kSparse]) {
             double norm = 0;
             for (uint32_t h = 0; h < H; h++) { const double f = fr.gamma(cl.obs[h] + 1.0); cl.freq[h] = f; norm += f; cl.obs[h] = 0; }
-            for (uint32_t h = 0; h < H; h++) cl.freq[h] /= norm;
+            for (uint32_t h = 0; h < H; h++) cl.freq[h] = m_div(cl.freq[h], norm);
         } else {
             uint32_t plus = 0;
             for (uint32_t h = 0; h < H; h++) plus += cl.obs[h] > 0;
@@ -891,7 +914,7 @@ __device__ __forceinline__ void cl_sample_frequencies(Cl &cl, Philox &fr) {
                 plus++; n_zero--;
             }
             for (uint32_t h = 0; h < H; h++) {
-                if (cl.nz[h]) cl.freq[h] /= norm; else cl.freq[h] = 0;
+                if (cl.nz[h]) cl.freq[h] = m_div(cl.freq[h], norm); else cl.freq[h] = 0;
                 cl.obs[h] = 0;
             }
         }
@@ -1001,34 +1024,82 @@ __device__ __forceinline__ void cl_summarise(Cl &cl, const btg_gibbs_opts &o, co
 }
 
 // InferenceEngine::estimateGenotypesCallback (InferenceEngine.cpp:278-333): one thread = one group, all chains
+// Chains of one cluster are independent in this mode: every chain re-keys the cluster's two random streams with its chain
+// index, shuffles the original k-mer order and starts from reset frequencies; tallies and allele statistics are sums over
+// chains.  (The reference keeps ONE mt19937 running through all chains of a genotyper, InferenceEngine.cpp:292-306 — a
+// property of its generator, not of the model; oracle-P follows the per-chain contract.)  That lets the few large clusters,
+// which otherwise set the kernel's tail (one thread: 1.3 s while the mean thread takes 0.16 s, profiles/r1_gibbs_tail.txt), run
+// their chains on kChainSplit threads with private arena positions; k_merge_split adds the pieces up and summarises.
 template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(64, MIN_BLOCKS) k_estimate_genotypes(DevUnit du, Tables T, btg_gibbs_opts o, ResultView R, int reconverge) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    // no early return: every lane of the warp reaches the __syncwarp()s below.  The 32 clusters of a warp are neighbours in the
-    // cost order and do nearly the same work per iteration, but data-dependent branches (rejection loops, sparse / dense
-    // frequency draws, 2 or 3 live diplotypes) let the lanes drift apart, and without a reconvergence point at the loop
-    // back-edges they never meet again (18 of 32 lanes active in profiles/r1b_gibbs_ncu_full.txt)
-    const bool live = i < du.n_regular;
+__global__ void __launch_bounds__(64, MIN_BLOCKS) k_estimate_genotypes(DevUnit du, Tables T, btg_gibbs_opts o, ResultView R, int reconverge, unsigned long long *dbg) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long t_in = dbg ? global_timer_ns() : 0;
+    // no early return: every lane of the warp reaches the __syncwarp()s below
+    const uint32_t n_virtual = du.n_split * kChainSplit;
+    bool live;
+    uint32_t cluster = 0, pos = NONE32, chain0 = 0, chain_step = 1;
+    bool split = false;
+    if (t < n_virtual) {  // the large clusters first: their blocks start before everything else
+        const uint32_t j = t / kChainSplit, v = t % kChainSplit;
+        cluster = du.split_cluster[j];
+        pos = du.split_pos[(size_t)j * kChainSplit + v];
+        chain0 = v; chain_step = kChainSplit;
+        split = true; live = true;
+    } else {
+        const uint32_t i = t - n_virtual;
+        live = i < du.n_regular;
+        cluster = du.order[live ? i : 0];
+        if (live && du.split_of[cluster] != NONE32) live = false;  // handled above
+    }
     Cl cl;
-    cl.bind(du, du.order[live ? i : 0]);
+    cl.bind(du, cluster, pos);
     const uint64_t gidx = o.group_index_base + cl.g;
     const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
     Philox prng, fr;
     prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, 0);
     fr.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngFrequency, 0);
     if (live) cl_construct(cl, o, gidx, 0);
-    for (uint32_t chain = 0; chain < o.n_chains; chain++) {
-        if (live) cl_reset(cl, o, prng);
+    const uint32_t iters = (uint32_t)o.gibbs_burn_in + o.gibbs_samples;
+    // warp-uniform trip count (lanes of split clusters take fewer chains; they idle through the rest)
+    for (uint32_t round = 0; round < o.n_chains; round++) {
+        const uint32_t chain = chain0 + round * chain_step;
+        const bool run = live && chain < o.n_chains;
+        if (run) {
+            prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, chain);
+            fr.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngFrequency, chain);
+            cl_reset<false, false, true>(cl, o, prng);
+        }
         if (reconverge) __syncwarp();
-        const uint32_t iters = (uint32_t)o.gibbs_burn_in + o.gibbs_samples;
+        if (__all_sync(0xFFFFFFFFu, !run)) continue;  // nothing left for this warp in this round
         for (uint32_t it = 0; it < iters; it++) {
-            if (live) cl_sample_diplotypes(cl, T, ploidy, it >= o.gibbs_burn_in, prng);
+            if (run) cl_sample_diplotypes(cl, T, ploidy, it >= o.gibbs_burn_in, prng);
             if (reconverge) __syncwarp();
-            if (live) cl_sample_frequencies(cl, fr);
+            if (run) cl_sample_frequencies(cl, fr);
             if (reconverge) __syncwarp();
         }
     }
-    if (live) cl_summarise(cl, o, ploidy, R);
+    if (live && !split) cl_summarise(cl, o, ploidy, R);
+    if (dbg && live) {  // BTG_GIBBS_TIMING=1: slowest thread and the sum of all per-thread times
+        const unsigned long long dt = global_timer_ns() - t_in;
+        atomicMax(dbg, (dt << 32) | cl.c);
+        atomicAdd(dbg + 1, dt);
+        if (cl.H > 4) atomicAdd(dbg + 2, dt);
+    }
+}
+
+// chain-split clusters: add the tallies and allele statistics of the virtual threads 1.. into thread 0's arena position
+// (ascending order, so the f64 sums are reproducible) and summarise
+__global__ void __launch_bounds__(64) k_merge_split(DevUnit du, btg_gibbs_opts o, ResultView R) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= du.n_split) return;
+    Cl cl, part;
+    cl.bind(du, du.split_cluster[j]);
+    for (uint32_t v = 1; v < kChainSplit; v++) {
+        part.bind(du, du.split_cluster[j], du.split_pos[(size_t)j * kChainSplit + v]);
+        for (uint32_t i = 0; i < cl.Dall * cl.S; i++) cl.tally[i] += part.tally[i];
+        for (uint32_t i = 0; i < cl.n_alleles * cl.S * 3; i++) { cl.as_n[i] += part.as_n[i]; cl.as_f[i] += part.as_f[i]; }
+    }
+    cl_summarise(cl, o, du.group_ploidy + (size_t)cl.g * du.S, R);
 }
 
 
@@ -1620,6 +1691,15 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
     auto *u = new btg_unit();
     bool ok = true;
     auto keep = [&](auto *p) { u->allocs.push_back((void *)p); return p; };
+    const bool up_timing = getenv("BTG_UPLOAD_TIMING") != nullptr;
+    auto up_t0 = std::chrono::steady_clock::now();
+    auto up_lap = [&](const char *what) {
+        if (!up_timing) return;
+        cudaDeviceSynchronize();
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[btgpu] unit upload: %s %.1f ms\n", what, std::chrono::duration<double, std::milli>(now - up_t0).count());
+        up_t0 = now;
+    };
     const uint64_t rows = d->cl_kmer_off[C], nvar = d->cl_var_off[C], n_vh = d->kmer_vh_off[rows];
     DevUnit &du = u->du;
     du.S = S; du.G = G; du.C = C;
@@ -1740,6 +1820,7 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
     u->h_group_cluster_off.assign(d->group_cluster_off, d->group_cluster_off + G + 1);
     u->h_cl_var_off.assign(d->cl_var_off, d->cl_var_off + C + 1);
     struct Dims { uint32_t H, K, nv, nu, nal, Dall, nm; };
+    up_lap("descriptor arrays -> device");
     std::vector<Dims> dims(C);
     std::vector<uint64_t> cost(C);
     for (uint32_t g = 0; g < G; g++) {
@@ -1771,15 +1852,27 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
     });
     du.n_regular = 0;
     while (du.n_regular < C && !is_nested(order[du.n_regular])) du.n_regular++;
-    // one arena slot per warp of the cost order, sized by the largest cluster in it
-    const uint32_t n_slots = (C + 31) / 32;
+    // chain-split clusters (default mode): large clusters of single-cluster groups get kChainSplit arena positions; the extra
+    // positions follow the C regular ones
+    const uint32_t split_cost = getenv("BTG_SPLIT_COST") ? (uint32_t)strtoul(getenv("BTG_SPLIT_COST"), nullptr, 10) : kSplitFillCost;  // tests: 0 splits everything
+    std::vector<uint32_t> split_cluster, split_of(C ? C : 1, NONE32);
+    for (uint32_t i = 0; i < du.n_regular; i++)
+        if (u->h_fill_cost[order[i]] > split_cost) { split_of[order[i]] = (uint32_t)split_cluster.size(); split_cluster.push_back(order[i]); }
+    const uint32_t n_split = (uint32_t)split_cluster.size();
+    std::vector<uint32_t> ext_cluster(order);  // cluster at every arena position
+    std::vector<uint32_t> split_pos((size_t)n_split * kChainSplit + 1, NONE32);
+    for (uint32_t j = 0; j < n_split; j++)
+        for (uint32_t v = 1; v < kChainSplit; v++) { split_pos[(size_t)j * kChainSplit + v] = (uint32_t)ext_cluster.size(); ext_cluster.push_back(split_cluster[j]); }
+    const uint32_t n_pos = (uint32_t)ext_cluster.size();
+    // one arena slot per warp of the position order, sized by the largest cluster in it
+    const uint32_t n_slots = (n_pos + 31) / 32;
     u->h_slots.assign(n_slots ? n_slots : 1, SlotLayout{});
     uint64_t f64_total = 0, u32_total = 0, u8_total = 0;
     for (uint32_t w = 0; w < n_slots; w++) {
         SlotLayout &SL = u->h_slots[w];
-        for (uint32_t i = w * 32; i < std::min<uint64_t>(C, (uint64_t)w * 32 + 32); i++) {
-            const Dims &D = dims[order[i]];
-            u->h_layout[order[i]].pos = i;
+        for (uint32_t i = w * 32; i < std::min<uint64_t>(n_pos, (uint64_t)w * 32 + 32); i++) {
+            const Dims &D = dims[ext_cluster[i]];
+            if (i < C) u->h_layout[order[i]].pos = i;
             SL.H = std::max(SL.H, D.H); SL.K = std::max(SL.K, D.K); SL.nvar = std::max(SL.nvar, D.nv);
             SL.n_uniq = std::max(SL.n_uniq, D.nu); SL.n_alleles = std::max(SL.n_alleles, D.nal); SL.Dall = std::max(SL.Dall, D.Dall);
             SL.n_multi = std::max(SL.n_multi, D.nm);
@@ -1797,6 +1890,12 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
     ok = ok && cudaMalloc(&tile_pool, tile_total + 32) == cudaSuccess;
     keep(tile_pool);
     du.big_tile_pool = tile_pool;
+    up_lap("host layout");
+    for (uint32_t j = 0; j < n_split; j++) split_pos[(size_t)j * kChainSplit] = u->h_layout[split_cluster[j]].pos;
+    du.n_split = n_split;
+    du.split_cluster = keep(upload(split_cluster.data(), n_split, ok));
+    du.split_pos = keep(upload(split_pos.data(), (size_t)n_split * kChainSplit, ok));
+    du.split_of = keep(upload(split_of.data(), C, ok));
     du.layout = keep(upload(u->h_layout.data(), C, ok));
     du.slots = keep(upload(u->h_slots.data(), u->h_slots.size(), ok));
     du.order = keep(upload(order.data(), C, ok));
@@ -1808,6 +1907,7 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
     ok = ok && cudaMalloc(&lg, n_lg * sizeof(double)) == cudaSuccess;
     keep(f64_pool); keep(u32_pool); keep(u8_pool); keep(lg);
     du.f64_pool = f64_pool; du.u32_pool = u32_pool; du.u8_pool = u8_pool; du.lgamma_int = lg;
+    up_lap("arena allocation");
     if (ok) {
         k_lgamma_int<<<(n_lg + 127) / 128, 128, 0, ctx().stream>>>(lg, n_lg);
         BTG_LAUNCHED();
@@ -1884,12 +1984,28 @@ int btg_estimate_genotypes_async(btg_unit *u, const btg_count_dist *cd, const bt
     if (u->du.n_regular) {
         static const int occ = getenv("BTG_GIBBS_OCC") ? atoi(getenv("BTG_GIBBS_OCC")) : 8;
         const int reconverge = getenv("BTG_GIBBS_SYNC") ? atoi(getenv("BTG_GIBBS_SYNC")) : 1;
-        const unsigned grid = (u->du.n_regular + 63) / 64;
-        if (occ >= 16) k_estimate_genotypes<16><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R, reconverge);
-        else if (occ >= 12) k_estimate_genotypes<12><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R, reconverge);
-        else k_estimate_genotypes<8><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R, reconverge);
+        const unsigned grid = (u->du.n_regular + u->du.n_split * kChainSplit + 63) / 64;
+        unsigned long long *dbg = nullptr;
+        if (getenv("BTG_GIBBS_TIMING")) { cudaMalloc(&dbg, 32); cudaMemset(dbg, 0, 32); }
+        if (occ >= 16) k_estimate_genotypes<16><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R, reconverge, dbg);
+        else if (occ >= 12) k_estimate_genotypes<12><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R, reconverge, dbg);
+        else k_estimate_genotypes<8><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R, reconverge, dbg);
         BTG_LAUNCHED();
         BTG_CUDA(cudaGetLastError());
+        if (u->du.n_split) {
+            k_merge_split<<<(u->du.n_split + 63) / 64, 64, 0, pick_stream(stream)>>>(u->du, *opts, dr->R);
+            BTG_LAUNCHED();
+            BTG_CUDA(cudaGetLastError());
+        }
+        if (dbg) {
+            unsigned long long h[4];
+            cudaStreamSynchronize(pick_stream(stream));
+            cudaMemcpy(h, dbg, 32, cudaMemcpyDeviceToHost);
+            cudaFree(dbg);
+            const uint32_t c = (uint32_t)(h[0] & 0xFFFFFFFFu);
+            fprintf(stderr, "[btgpu] k_estimate_genotypes: slowest thread %.1f ms (cluster %u, H %u, fill cost %u); mean thread %.2f ms over %u clusters; clusters with H > 4 hold %.1f %% of the thread time\n",
+                    (h[0] >> 32) / 1e6, c, c < u->du.C ? u->h_nhap[c] : 0, c < u->du.C ? u->h_fill_cost[c] : 0, h[1] / 1e6 / std::max(1u, u->du.n_regular), u->du.n_regular, 100.0 * h[2] / std::max<unsigned long long>(1, h[1]));
+        }
     }
     return BTG_OK;
 }

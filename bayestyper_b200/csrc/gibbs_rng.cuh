@@ -14,11 +14,14 @@
 
 namespace btg {
 
-// The sampler kernels inline every call, including libm's f64 log/exp/log1p/cos (60-150 instructions each) and the ten
-// Philox rounds at every call site.  BTG_OUTLINE=1 keeps these leaf functions out of line (scalar arguments in registers,
-// no state spilled) to test whether instruction fetch limits the kernels; it does not (see below), so inlining stays.
+// The sampler kernels would inline every call, including libm's f64 log/exp/log1p/cos/pow (60-300 instructions each) and
+// the ten Philox rounds at every call site: k_estimate_genotypes was 15.1k SASS instructions with a hot loop of ~63 KB, and
+// at full occupancy (16 warps per SM, each at a different point of the loop) it stalled on instruction fetch
+// (no_instruction = 16 of 23 stall cycles per issue, profiles/r1_gibbs_full_occupancy_ncu_full.txt).  Keeping these leaf
+// functions out of line (scalar arguments in registers, no state spilled) runs the same arithmetic 1.4x faster there
+// (161k clusters: 730 ms -> 529 ms); with few resident warps it is ~5 % slower.  BTG_OUTLINE=0 restores full inlining.
 #ifndef BTG_OUTLINE
-#define BTG_OUTLINE 0   /* measured on B200: outlining shrinks k_estimate_genotypes 15.1k -> 11.6k SASS but runs 5 % slower */
+#define BTG_OUTLINE 1
 #endif
 #if BTG_OUTLINE
 #define BTG_LEAF __device__ __noinline__
@@ -29,6 +32,9 @@ BTG_LEAF double m_log(double x) { return log(x); }
 BTG_LEAF double m_exp(double x) { return exp(x); }
 BTG_LEAF double m_log1p(double x) { return log1p(x); }
 BTG_LEAF double m_cos(double x) { return cos(x); }
+BTG_LEAF double m_pow(double x, double y) { return pow(x, y); }
+BTG_LEAF double m_sqrt(double x) { return sqrt(x); }
+BTG_LEAF double m_div(double x, double y) { return x / y; }
 BTG_LEAF uint4 philox4x32_10(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
@@ -80,7 +86,7 @@ struct Philox {
     __device__ __forceinline__ uint32_t uniform_int(uint32_t n) { return __umulhi(next(), n); }
     __device__ __forceinline__ double normal() {
         const double u1 = u01(), u2 = u01();
-        return sqrt(-2.0 * m_log(u1)) * m_cos(6.283185307179586476925286766559 * u2);
+        return m_sqrt(-2.0 * m_log(u1)) * m_cos(6.283185307179586476925286766559 * u2);
     }
     // Marsaglia-Tsang, scale 1
     __device__ double gamma(double a) {
@@ -88,12 +94,12 @@ struct Philox {
         if (a < 1.0) {
             // gamma(a) = gamma(a+1) * U^(1/a); the gamma(a+1) draw comes first
             const double g = gamma_ge1(a + 1.0);
-            return g * pow(u01(), 1.0 / a);
+            return g * m_pow(u01(), m_div(1.0, a));
         }
         return boost * gamma_ge1(a);
     }
     __device__ double gamma_ge1(double a) {
-        const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+        const double d = a - 1.0 / 3.0, c = m_div(1.0, m_sqrt(9.0 * d));
         for (;;) {
             const double x = normal();
             double v = 1.0 + c * x;

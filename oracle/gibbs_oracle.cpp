@@ -801,6 +801,15 @@ int bto_estimate_genotypes(const btg_unit_desc *d, void *cd, const btg_gibbs_opt
         Group grp;
         grp.init(d, o, g, 0, shared.data(), hap_start);  // genotypers are constructed once and persist across chains
         for (uint32_t chain = 0; chain < o->n_chains; chain++) {
+            if (grp.gts.size() == 1) {
+                // stream contract of the default mode for single-cluster groups (csrc/gibbs.cu, k_estimate_genotypes): chains are
+                // independent — each chain re-keys the genotyper's two streams with its index and shuffles the original k-mer
+                // order.  (The reference keeps one mt19937 running through all chains, InferenceEngine.cpp:292-306.)
+                Genotyper &gt = grp.gts[0];
+                gt.prng.init(o->random_seed, o->group_index_base + g, d->cluster_idx[gt.c], 0, chain);
+                gt.prng_freq.init(o->random_seed, o->group_index_base + g, d->cluster_idx[gt.c], 2, chain);
+                gt.uniq.assign(d->uniq_idx + d->cl_uniq_off[gt.c], d->uniq_idx + d->cl_uniq_off[gt.c + 1]);
+            }
             grp.reset();
             grp.shuffleBranchOrdering(o, chain);
             for (uint32_t i = 0; i < o->gibbs_burn_in; i++) grp.estimateGenotypes(T, false);

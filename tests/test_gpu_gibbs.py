@@ -62,6 +62,29 @@ def test_estimate_genotypes_matches_oracle(btg, name):
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["gibbs_mixed_3s", "gibbs_chrx_2s"])
+@pytest.mark.parametrize("split_cost", ["0", "4000000000"])
+def test_chain_split_is_invisible(btg, name, split_cost, monkeypatch):
+    """Default mode: the chains of a cluster are independent, so a cluster whose chains run on 20 threads with private state
+    (every cluster with BTG_SPLIT_COST=0, none with a huge threshold) gives the tallies of the sequential oracle."""
+    monkeypatch.setenv("BTG_SPLIT_COST", split_cost)
+    fx = GibbsFixture(name)
+    opts = fx.opts(chains=23, burn=5, samples=12)          # more chains than virtual threads: thread v runs chains v and v + 20
+    ocd, gcd = _both(fx, opts)
+    ores, otally = O.oracle_estimate_genotypes(fx.unit, ocd, opts, want_tally=True)
+    eng = engine.InferenceEngine(fx.unit)
+    gres = eng.estimate_genotypes(gcd, opts)
+    toff = fx.unit.tally_offsets()
+    for c in range(fx.unit.Cn):
+        assert (eng.cluster_tally(c).reshape(-1) == otally[int(toff[c]):int(toff[c + 1])]).all(), c
+    assert np.abs(gres["gpp"] - ores["gpp"]).max() <= GPP_TOL
+    for k in ("gt", "gq", "saf", "an", "ac"):
+        assert (gres[k] == ores[k]).all(), k
+    for k in ("nak", "fak", "mac"):
+        assert np.abs(gres[k] - ores[k]).max() <= 1e-4, k
+    eng.close()
+
+
 def test_seed_and_shard_invariance(btg):
     """Per-group streams: a group's result does not depend on which other groups share the launch
     (the reference's determinism contract, README.md:9), and changes with the seed."""

@@ -1,0 +1,6 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r1n_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r1n_pytest.log
+tail -4 gpurun_out/r1n_pytest.log
+timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/r1n_bench.json 2> gpurun_out/r1n_bench.err; echo "bench rc=$?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r1n_launches.csv python bench.py --steps 1 --warmup 1 --timed-only > gpurun_out/r1n_launches.log 2>&1
