@@ -1413,11 +1413,15 @@ __device__ __forceinline__ void grid_barrier(const GridBarrier &b) {
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(b.gen), "r"(g + 1) : "memory");
         } else {
             unsigned int now, ns_sleep = 64;
+            const unsigned long long t0 = global_timer_ns();
             for (;;) {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(b.gen) : "memory");
                 if (now != g) break;
                 __nanosleep(ns_sleep);
                 if (ns_sleep < 1024) ns_sleep *= 2;
+                // never hang the GPU: if the grid is not co-resident (it always is: cooperative launch) give up after 60 s; the
+                // host sees the flag in the generation word's neighbour and reports an error
+                if (ns_sleep == 1024 && global_timer_ns() - t0 > 60000000000ull) { atomicExch(b.gen + 1, 1u); break; }
             }
         }
     }
@@ -1431,7 +1435,10 @@ __device__ __forceinline__ void grid_barrier(const GridBarrier &b) {
 // joint = 0: estimateNoise (fresh genotypers each chain, streams of chain `chain`, nothing collected)
 // joint = 1: estimateNoiseAndGenotypes (InferenceEngine.cpp:384-472): genotypers are constructed in the first chain only and
 //            persist (streams of chain 0), samples are collected after the burn-in
-__global__ void __launch_bounds__(256, 2) k_noise_chain(DevUnit du, Tables T, btg_gibbs_opts o, const uint32_t *sel, uint32_t n_sel, uint32_t n_big, uint32_t chain,
+#ifndef BTG_NOISE_MINBLOCKS
+#define BTG_NOISE_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(256, BTG_NOISE_MINBLOCKS) k_noise_chain(DevUnit du, Tables T, btg_gibbs_opts o, const uint32_t *sel, uint32_t n_sel, uint32_t n_big, uint32_t chain,
                                                        uint32_t iters, NoiseState ns, float prior_shape, float prior_scale, unsigned long long *hist, int joint,
                                                        PeerExchange px, const uint32_t *fill_tasks, uint32_t n_fill_tasks, GridBarrier gb) {
     __shared__ unsigned long long sh_tot[kMailRow];
@@ -1580,10 +1587,27 @@ __global__ void __launch_bounds__(256, 2) k_noise_chain(DevUnit du, Tables T, bt
 #endif
 }
 
-__global__ void k_noise_rng_init(uint32_t *rng, uint32_t seed) {
+__global__ void k_noise_rng_init(uint32_t *rng, uint32_t seed, uint32_t chain = 0) {
     Philox r;
-    r.init(seed, (uint64_t)-1, 0, kRngNoise);
+    r.init(seed, (uint64_t)-1, 0, kRngNoise, chain);
     r.save(rng, 0);
+}
+
+// estimateNoise, end: mean of the post-burn-in rates of all chains (added up in chain order) -> setNoiseRates
+// (InferenceEngine.cpp:259-264), Poisson rows rebuilt, final trace row "0 0"
+__global__ void k_noise_finish(const double *chain_means /* [n_chains][S] sums */, uint32_t n_chains, uint32_t S, double div, double *rates, double *noise_table,
+                               double *trace_row) {
+    __shared__ double sh[BTG_MAX_SAMPLES];
+    if (threadIdx.x < S) {
+        double acc = 0;
+        for (uint32_t b = 0; b < n_chains; b++) acc += chain_means[(size_t)b * S + threadIdx.x];
+        const double r = acc / div;
+        rates[threadIdx.x] = r;
+        sh[threadIdx.x] = r;
+        if (trace_row) { trace_row[0] = 0; trace_row[1] = 0; trace_row[2 + threadIdx.x] = r; }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < S * 256u; i += blockDim.x) noise_table[i] = noiseCountLogPmf(sh[i >> 8], i & 255u);
 }
 
 template <class T> T *upload(const T *h, size_t n, bool &ok) {
@@ -1607,6 +1631,10 @@ struct btg_unit {
     std::vector<uint32_t> h_fill_cost;  // table lookups of one full cache fill: S * D * n_uniq / 10
     uint64_t n_variants = 0, n_alleles_total = 0, n_shared = 0;
     uint32_t max_h = 0;
+    // sizes of the mutable arena pools, and shadow copies of them: estimateNoise runs several chains at once, each on its own
+    // arena (shadow_du[k] = du with private pools; the descriptors are shared)
+    uint64_t f64_total = 0, u32_total = 0, u8_total = 0, tile_total = 0;
+    std::vector<DevUnit> shadow_du;
 };
 
 void btg_unit_free_result(btg_unit *u);
@@ -1906,6 +1934,7 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
     const uint32_t n_lg = u->max_h + 2 * S + 4;
     ok = ok && cudaMalloc(&lg, n_lg * sizeof(double)) == cudaSuccess;
     keep(f64_pool); keep(u32_pool); keep(u8_pool); keep(lg);
+    u->f64_total = f64_total; u->u32_total = u32_total; u->u8_total = u8_total; u->tile_total = tile_total;
     du.f64_pool = f64_pool; du.u32_pool = u32_pool; du.u8_pool = u8_pool; du.lgamma_int = lg;
     up_lap("arena allocation");
     if (ok) {
@@ -2058,13 +2087,14 @@ int btg_unit_cluster_tally(const btg_unit *u, uint32_t cluster, uint32_t *tally_
 }
 
 static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, double *trace_out, int joint);
+static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, double *trace_out);
 
 int btg_estimate_noise(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, double *trace_out) {
-    return noise_chains(u, cd, opts, nullptr, trace_out, 0);
+    return estimate_noise_concurrent(u, cd, opts, nullptr, trace_out);
 }
 
 int btg_estimate_noise_sharded(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, double *trace_out) {
-    return noise_chains(u, cd, opts, sh, trace_out, 0);
+    return estimate_noise_concurrent(u, cd, opts, sh, trace_out);
 }
 
 int btg_estimate_noise_and_genotypes(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, btg_genotype_result *out, double *trace_out) {
@@ -2084,6 +2114,239 @@ int btg_estimate_noise_and_genotypes_sharded(btg_unit *u, btg_count_dist *cd, co
         BTG_CUDA(cudaGetLastError());
     }
     return btg_unit_download_result(u, out, nullptr);
+}
+
+
+// the engine's own stream (InferenceEngine.cpp:174) lives on the host: Fisher-Yates with the same Philox recipe as the device
+struct HostEnginePhilox {
+    uint32_t key[2], ctr[4], buf[4]; int pos;
+    void init(uint32_t seed) { key[0] = seed; key[1] = 0; ctr[0] = ctr[1] = ctr[2] = 0; ctr[3] = kRngEngine; pos = 4; }
+    uint32_t next() {
+        if (pos == 4) {
+            uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]}, k[2] = {key[0], key[1]};
+            for (int r = 0; r < 10; r++) {
+                const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+                const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k[0], n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k[1], n3 = (uint32_t)p0;
+                c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+                k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+            }
+            for (int i = 0; i < 4; i++) buf[i] = c[i];
+            if (++ctr[0] == 0) ++ctr[1];
+            pos = 0;
+        }
+        return buf[pos++];
+    }
+    uint32_t uniform_int(uint32_t n) { return (uint32_t)(((uint64_t)next() * n) >> 32); }
+};
+
+// shadow arenas for chains that run at the same time: shadow 0 is the unit's own arena
+static uint32_t ensure_shadows(btg_unit *u, uint32_t want) {
+    if (u->shadow_du.empty()) u->shadow_du.push_back(u->du);
+    while (u->shadow_du.size() < want) {
+        double *f = nullptr; uint32_t *w = nullptr; uint8_t *b = nullptr, *t = nullptr;
+        const bool ok = cudaMalloc(&f, (u->f64_total + 1) * sizeof(double)) == cudaSuccess && cudaMalloc(&w, (u->u32_total + 1) * sizeof(uint32_t)) == cudaSuccess &&
+                        cudaMalloc(&b, u->u8_total + 8) == cudaSuccess && cudaMalloc(&t, u->tile_total + 32) == cudaSuccess;
+        if (!ok) { cudaFree(f); cudaFree(w); cudaFree(b); cudaFree(t); cudaGetLastError(); break; }  // fewer concurrent chains
+        for (void *p : {(void *)f, (void *)w, (void *)b, (void *)t}) u->allocs.push_back(p);
+        DevUnit d = u->du;
+        d.f64_pool = f; d.u32_pool = w; d.u8_pool = b; d.big_tile_pool = t;
+        u->shadow_du.push_back(d);
+    }
+    return (uint32_t)std::min<size_t>(want, u->shadow_du.size());
+}
+
+// InferenceEngine::estimateNoise (InferenceEngine.cpp:135-276).  The chains are independent under this library's stream contract
+// (fresh genotypers per chain as in the reference, InferenceEngine.cpp:240-251; the noise rates of chain c come from their own
+// stream, kind 4 / chain c + 1, starting with the prior draw), so several chains run AT THE SAME TIME: each is one persistent
+// cooperative k_noise_chain on its own CUDA stream, arena and noise state, with a share of the SMs (BTG_NOISE_CONCURRENCY = K).
+// Measured (profiles/r1_noise_chain_phases.txt): K = 4 or 8 chains side by side take as long as one after the other — an iteration
+// costs (clusters per thread) x (slowest lane's step), so a chain on 1/K of the SMs is K times slower — hence the default K = 1;
+// the per-chain contract is what makes the results independent of K.
+static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, double *trace_out) {
+    BTG_REQUIRE_INIT();
+    if (!u || !cd || !opts) { set_error("null argument"); return BTG_EINVAL; }
+    btg_comm *comm = sh ? sh->comm : nullptr;
+    const uint32_t world = comm ? comm->world : 1;
+    if (sh && (!sh->group_n_clusters || !sh->group_n_variants || opts->group_index_base + u->du.G > sh->n_groups_total)) {
+        set_error("bad shard descriptor: this rank's groups [%llu, %llu) do not fit the %llu groups of the unit", (unsigned long long)opts->group_index_base,
+                  (unsigned long long)(opts->group_index_base + u->du.G), (unsigned long long)(sh ? sh->n_groups_total : 0));
+        return BTG_EINVAL;
+    }
+    if (comm && !comm->connected) { set_error("communicator is not connected (btg_comm_connect)"); return BTG_ESTATE; }
+    if (cd->S != u->du.S) { set_error("count distribution / unit sample mismatch"); return BTG_EINVAL; }
+    const uint32_t S = u->du.S, G = u->du.G, n_chains = opts->n_chains;
+    const uint32_t iters = (uint32_t)opts->gibbs_burn_in + opts->gibbs_samples;
+    const size_t row_len = 2 + S, trace_rows = (size_t)n_chains * (iters + 1) + 1;
+    auto s0 = ctx().stream;
+    const bool want_phases = getenv("BTG_NOISE_PHASES") && atoi(getenv("BTG_NOISE_PHASES"));
+    // one mailbox per communicator: a sharded unit runs its chains one after the other (the exchange is inside the kernel)
+    uint32_t K = world > 1 || want_phases ? 1u : (uint32_t)std::max(1, getenv("BTG_NOISE_CONCURRENCY") ? atoi(getenv("BTG_NOISE_CONCURRENCY")) : 1);
+    K = ensure_shadows(u, std::min(K, std::max(1u, n_chains)));
+    int rc = BTG_OK;
+    std::vector<void *> tmp;
+    auto dalloc = [&](size_t bytes) { void *p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 8) != cudaSuccess) { rc = BTG_ENOMEM; return (void *)nullptr; } tmp.push_back(p); cudaMemsetAsync(p, 0, bytes ? bytes : 8, s0); return p; };
+    // per-chain state, one allocation each: [n_chains][...]
+    const size_t nc = std::max(1u, n_chains);
+    auto *d_hist = (unsigned long long *)dalloc(nc * 2 * S * 8);
+    auto *d_rates = (double *)dalloc(nc * S * 8);
+    auto *d_tables = (double *)dalloc(nc * S * 256 * 8);
+    auto *d_means = (double *)dalloc(nc * S * 8);
+    auto *d_rng = (uint32_t *)dalloc(nc * 8 * 4);
+    auto *d_rows = (uint32_t *)dalloc(nc * 4);
+    auto *d_bar = (unsigned int *)dalloc(nc * 256);
+    auto *d_trace = trace_out ? (double *)dalloc(trace_rows * row_len * 8) : nullptr;
+    const uint32_t n_lg = 1024;
+    auto *lg_tab = (double *)dalloc(n_lg * 8);
+    unsigned long long *d_phase = want_phases ? (unsigned long long *)dalloc((8 + 3 * (size_t)iters + 16) * 8) : nullptr;
+    std::vector<cudaStream_t> streams(K, nullptr);
+    cudaEvent_t ev_ready = nullptr;
+    std::vector<std::vector<uint32_t>> sels(n_chains), tasks(n_chains);
+    std::vector<uint32_t> n_bigs(n_chains, 0);
+    uint32_t *d_sel = nullptr, *d_tasks = nullptr;
+    if (rc == BTG_OK) {
+        // ---- group selection of every chain (InferenceEngine.cpp:174-189), on the host, in chain order ----
+        HostEnginePhilox engine;
+        engine.init(opts->random_seed);
+        const uint64_t base = sh ? opts->group_index_base : 0;
+        std::vector<uint32_t> noise_groups;  // single-cluster groups of the WHOLE unit (InferenceEngine.cpp:144-151)
+        if (sh) { for (uint64_t g = 0; g < sh->n_groups_total; g++) if (sh->group_n_clusters[g] == 1) noise_groups.push_back((uint32_t)g); }
+        else { for (uint32_t g = 0; g < G; g++) if (u->h_group_cluster_off[g + 1] - u->h_group_cluster_off[g] == 1) noise_groups.push_back(g); }
+        auto group_variants = [&](uint32_t g) {
+            if (sh) return sh->group_n_variants[g];
+            uint64_t n = 0;
+            for (uint64_t c = u->h_group_cluster_off[g]; c < u->h_group_cluster_off[g + 1]; c++) n += u->h_cl_var_off[c + 1] - u->h_cl_var_off[c];
+            return (uint32_t)n;
+        };
+        const uint32_t noise_variants_batch_size = 100000;  // InferenceEngine.cpp:50
+        auto is_big = [&](uint32_t c) { return u->h_fill_cost[c] > kBigFillCost; };  // the clusters with a dense tile
+        size_t sel_total = 0, task_total = 0;
+        for (uint32_t b = 0; b < n_chains; b++) {
+            uint32_t end = 0, nvv = 0;
+            for (size_t i = noise_groups.size(); i > 1; i--) std::swap(noise_groups[i - 1], noise_groups[engine.uniform_int((uint32_t)i)]);
+            while (nvv < noise_variants_batch_size && end < noise_groups.size()) { nvv += group_variants(noise_groups[end]); end++; }
+            std::sort(noise_groups.begin(), noise_groups.begin() + end);
+            auto &sel = sels[b];
+            for (uint32_t i = 0; i < end; i++) {
+                const uint64_t g = noise_groups[i];
+                if (g >= base && g < base + G) sel.push_back((uint32_t)u->h_group_cluster_off[g - base]);  // this rank's share
+            }
+            // large clusters first (fill tasks + one warp each), then by position in the cost order (neighbours share arena slots)
+            std::sort(sel.begin(), sel.end(), [&](uint32_t a, uint32_t c) {
+                const bool ba = is_big(a), bc = is_big(c);
+                return ba != bc ? ba : u->h_layout[a].pos < u->h_layout[c].pos;
+            });
+            uint32_t n_big = 0;
+            while (n_big < sel.size() && is_big(sel[n_big])) n_big++;
+            n_bigs[b] = n_big;
+            for (uint32_t i = 0; i < n_big; i++) {  // a large cluster gets one warp per 32 cache entries (upper bound), at most 64
+                const uint64_t H = u->h_nhap[sel[i]], entries = (uint64_t)S * (H * (H + 1) / 2);
+                const uint32_t parts = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (entries + 31) / 32));
+                for (uint32_t p = 0; p < parts; p++) { tasks[b].push_back(i); tasks[b].push_back(p); tasks[b].push_back(parts); }
+            }
+            sel_total += sel.size(); task_total += tasks[b].size();
+        }
+        d_sel = (uint32_t *)dalloc(sel_total * 4);
+        d_tasks = (uint32_t *)dalloc(task_total * 4);
+    }
+    if (rc == BTG_OK) {
+        for (auto &st : streams) if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) rc = BTG_ECUDA;
+        if (cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming) != cudaSuccess) rc = BTG_ECUDA;
+    }
+    if (rc == BTG_OK) {
+        k_lgamma_int<<<(n_lg + 127) / 128, 128, 0, s0>>>(lg_tab, n_lg);
+        BTG_LAUNCHED();
+        cudaEventRecord(ev_ready, s0);  // allocations zeroed, tables of cd complete
+        PeerExchange px{};
+        px.world = world; px.rank = comm ? comm->rank : 0;
+        if (comm) {
+            for (uint32_t r = 0; r < world; r++) px.mail[r] = comm->peers[r];
+            px.error = comm->error;
+            const char *tmo = getenv("BTG_PEER_TIMEOUT_MS");
+            px.timeout_ns = (tmo ? strtoull(tmo, nullptr, 10) : 20000ull) * 1000000ull;
+        }
+        const uint32_t bs = 256;
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_noise_chain, bs, 0);
+        const uint32_t capacity = (uint32_t)std::max(1, per_sm) * (uint32_t)ctx().sm_count;
+        const uint32_t max_blocks = std::max(1u, (K > 1 ? capacity - capacity / 16 : capacity) / K);  // this chain's share of the SMs (a few block slots stay free)
+        size_t sel_off = 0, task_off = 0;
+        for (auto &st : streams) cudaStreamWaitEvent(st, ev_ready, 0);
+        for (uint32_t b = 0; b < n_chains && rc == BTG_OK; b++) {
+            const uint32_t k = b % K;
+            cudaStream_t st = streams[k];
+            NoiseState ns{};
+            ns.hist = (uint64_t *)(d_hist + (size_t)b * 2 * S);
+            ns.rates = d_rates + (size_t)b * S;
+            ns.noise_table = d_tables + (size_t)b * S * 256;
+            ns.mean_rates = d_means + (size_t)b * S;
+            ns.trace = d_trace ? d_trace + (size_t)b * (iters + 1) * row_len : nullptr;
+            ns.rng = d_rng + (size_t)b * 8;
+            ns.trace_row = d_rows + b;
+            ns.lg = lg_tab; ns.n_lg = n_lg;
+            ns.phase_ns = d_phase;
+            GridBarrier gb{d_bar + (size_t)b * 64, d_bar + (size_t)b * 64 + 32};
+            uint32_t *sel_b = d_sel + sel_off, *tasks_b = d_tasks + task_off;
+            if (!sels[b].empty() && cudaMemcpyAsync(sel_b, sels[b].data(), sels[b].size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = BTG_ECUDA; break; }
+            if (!tasks[b].empty() && cudaMemcpyAsync(tasks_b, tasks[b].data(), tasks[b].size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = BTG_ECUDA; break; }
+            sel_off += sels[b].size(); task_off += tasks[b].size();
+            // this chain's noise stream, and its first draw: the rates of the prior (CountDistribution.cpp:62,163-171)
+            k_noise_rng_init<<<1, 1, 0, st>>>(ns.rng, opts->random_seed, b + 1);
+            BTG_LAUNCHED();
+            NoiseState ns_quiet = ns;
+            ns_quiet.trace = nullptr;
+            k_noise_update<<<1, 256, 0, st>>>(ns_quiet, S, cd->prior_shape, cd->prior_scale, opts->random_seed, 0, 0, 0, 0, 1);
+            BTG_LAUNCHED();
+            Tables T{cd->genomic, ns.noise_table};
+            uint32_t n_sel = (uint32_t)sels[b].size(), n_big = n_bigs[b], n_tasks = (uint32_t)(tasks[b].size() / 3), chain_id = b + 1, iters_arg = iters;
+            const uint32_t want_threads = std::max<uint32_t>({n_big * 32u, n_sel - n_big, n_tasks * 32u, 1u});
+            const uint32_t grid = std::max(1u, std::min((want_threads + bs - 1) / bs, max_blocks));
+            float ps = cd->prior_shape, pc = cd->prior_scale;
+            btg_gibbs_opts o = *opts;
+            int joint = 0;
+            unsigned long long *hist = (unsigned long long *)ns.hist;
+            if (comm) { px.seq0 = comm->seq; comm->seq += iters; }
+            DevUnit du_k = u->shadow_du[k];
+            void *args[] = {&du_k, &T, &o, &sel_b, &n_sel, &n_big, &chain_id, &iters_arg, &ns, &ps, &pc, &hist, &joint, &px, &tasks_b, &n_tasks, &gb};
+            cudaError_t e = cudaLaunchCooperativeKernel((void *)k_noise_chain, dim3(grid), dim3(bs), args, 0, st);
+            BTG_LAUNCHED();
+            if (e != cudaSuccess) { set_error("cooperative launch failed: %s", cudaGetErrorString(e)); rc = BTG_ECUDA; break; }
+        }
+        // join the chain streams, then: mean of the post-burn-in rates -> setNoiseRates, final trace row "0 0"
+        for (auto &st : streams) { cudaEvent_t ev; if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) { cudaEventRecord(ev, st); cudaStreamWaitEvent(s0, ev, 0); cudaEventDestroy(ev); } }
+        if (rc == BTG_OK) {
+            k_noise_finish<<<1, 256, 0, s0>>>(d_means, n_chains, S, (double)opts->gibbs_samples * n_chains, cd->rates, cd->noise,
+                                              d_trace ? d_trace + (trace_rows - 1) * row_len : nullptr);
+            BTG_LAUNCHED();
+            if (trace_out) cudaMemcpyAsync(trace_out, d_trace, trace_rows * row_len * 8, cudaMemcpyDeviceToHost, s0);
+        }
+        cudaError_t e = cudaStreamSynchronize(s0);
+        for (auto &st : streams) if (st) { cudaError_t e2 = cudaStreamSynchronize(st); if (e == cudaSuccess) e = e2; }
+        if (e != cudaSuccess && rc == BTG_OK) { set_error("noise estimation failed: %s", cudaGetErrorString(e)); rc = BTG_ECUDA; }
+        if (rc == BTG_OK && comm && world > 1) {
+            uint32_t flag = 0;
+            cudaMemcpy(&flag, comm->error, 4, cudaMemcpyDeviceToHost);
+            if (flag) { set_error("peer exchange timed out waiting for rank %u (a rank failed or left the lock-step)", flag - 1); cudaMemset(comm->error, 0, 4); rc = BTG_ECUDA; }
+        }
+        if (rc == BTG_OK) {
+            std::vector<unsigned int> bar(nc * 64);
+            cudaMemcpy(bar.data(), d_bar, bar.size() * 4, cudaMemcpyDeviceToHost);
+            for (size_t b = 0; b < nc; b++) if (bar[b * 64 + 33]) { set_error("grid barrier of chain %zu timed out (grid not co-resident)", b); rc = BTG_ECUDA; break; }
+        }
+        if (rc == BTG_OK && d_phase) {
+            unsigned long long ph[4] = {0, 0, 0, 0};
+            cudaMemcpy(ph, d_phase, sizeof ph, cudaMemcpyDeviceToHost);
+            const double n_it = (double)n_chains * iters;
+            fprintf(stderr, "[btgpu] noise chain phases, us per iteration (block 0, chains one after the other): fill+one-thread %.1f  large owners %.1f  exchange+update %.1f  release %.1f\n",
+                    ph[0] / n_it / 1e3, ph[1] / n_it / 1e3, ph[2] / n_it / 1e3, ph[3] / n_it / 1e3);
+        }
+    } else if (rc != BTG_OK && !*btg_last_error()) {
+        set_error("noise estimation allocation failed");
+    }
+    cudaStreamSynchronize(s0);
+    for (auto &st : streams) if (st) cudaStreamDestroy(st);
+    if (ev_ready) cudaEventDestroy(ev_ready);
+    for (void *p : tmp) cudaFree(p);
+    return rc;
 }
 
 static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, double *trace_out, int joint) {

@@ -851,7 +851,9 @@ int bto_estimate_noise(const btg_unit_desc *d, void *cd, const btg_gibbs_opts *o
         for (uint32_t s = 0; s < S; s++) T.noise_rates[s] = sampleGamma(T.prior_shape, T.prior_scale);
         T.updateNoise();
     };
-    resetNoiseRates();  // CountDistribution ctor (CountDistribution.cpp:62)
+    // Stream contract (csrc/gibbs.cu, estimate_noise_concurrent): the chains of estimateNoise are independent — chain c draws its noise
+    // rates from its own stream (kind 4, chain c + 1), starting with the prior draw that the reference takes from the running
+    // CountDistribution stream in the ctor / at the end of the previous chain (CountDistribution.cpp:62, InferenceEngine.cpp:253).
     std::vector<double> mean_rates(S, 0);
     size_t row = 0;
     auto trace = [&](double chain, double it) {
@@ -866,6 +868,8 @@ int bto_estimate_noise(const btg_unit_desc *d, void *cd, const btg_gibbs_opts *o
         uint32_t end = 0, nv = 0;
         while (nv < noise_variants_batch_size && end < noise_groups.size()) { nv += groupVariants(noise_groups[end]); end++; }
         std::sort(noise_groups.begin(), noise_groups.begin() + end);
+        noise_prng.init(o->random_seed, (uint64_t)-1, 0, 4, chain + 1);
+        resetNoiseRates();
         std::vector<Genotyper> gts(end);
         for (uint32_t i = 0; i < end; i++) {  // initGenotypersCallback (InferenceEngine.cpp:60-75): fresh genotypers per chain
             gts[i].init(d, o, (uint32_t)d->group_cluster_off[noise_groups[i]], o->group_index_base + noise_groups[i], chain + 1);
@@ -893,7 +897,6 @@ int bto_estimate_noise(const btg_unit_desc *d, void *cd, const btg_gibbs_opts *o
             trace(chain + 1, it);
             if (o->gibbs_burn_in < it) for (uint32_t s = 0; s < S; s++) mean_rates[s] += T.noise_rates[s];
         }
-        resetNoiseRates();
     }
     for (uint32_t s = 0; s < S; s++) mean_rates[s] /= (double)o->gibbs_samples * o->n_chains;
     T.noise_rates = mean_rates;
