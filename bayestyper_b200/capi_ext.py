@@ -17,6 +17,8 @@ def bind(L):
     L.btg_count_dist_free.argtypes = [vp]
     L.btg_unit_upload.restype = vp
     L.btg_unit_upload.argtypes = [vp]
+    L.btg_unit_upload_dev.restype = vp
+    L.btg_unit_upload_dev.argtypes = [vp, vp, C.c_uint64, C.c_uint64]
     L.btg_unit_free.argtypes = [vp]
     L.btg_estimate_genotypes.argtypes = [vp, vp, vp, vp]
     L.btg_estimate_noise.argtypes = [vp, vp, vp, vp]

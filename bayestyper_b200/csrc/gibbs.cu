@@ -27,6 +27,7 @@
 #include <type_traits>
 #include <vector>
 #include <chrono>
+#include <functional>
 
 #include <cooperative_groups.h>
 
@@ -1359,23 +1360,42 @@ __global__ void k_noise_update(NoiseState ns, uint32_t S, float prior_shape, flo
 // sequential code (so the cached value is bit-identical).  Used for large clusters in the lock-step noise chain,
 // where the slowest cluster sets the pace of every iteration.
 // A cluster may be shared by `parts` warps (anywhere in the grid): entries are dealt to them in rounds of 32.
+// With many k-mers per entry (n_sub >= 16) the roles turn: the warp takes its entries one at a time, the 32 lanes gather 32
+// TERMS of the entry at once, and the terms are then added in subsample order through shuffles — the sum is still the
+// sequential one, but an entry costs n_sub/32 gather rounds instead of n_sub dependent gathers in one lane (the slowest
+// fill task of an iteration was a lane walking ~60 k-mers: 214 us, profiles/r1_noise_chain_phases.txt).
 __device__ __forceinline__ void cl_fill_cache_warp(Cl &cl, const Tables &T, const uint8_t *ploidy, uint32_t lane, uint32_t part, uint32_t parts) {
     const uint32_t H = cl.H, n_sub = cl.misc[kNSub];
+    const bool by_terms = n_sub >= 16;
     uint32_t e = 0;
     for (uint32_t s = 0; s < cl.S; s++) {
         const uint8_t pl = ploidy[s];
         if (pl == 0) continue;
+        const uint32_t g = cl.u->sample_gender[s];
         for (uint32_t a = 0; a < H; a++) {
             if (!cl.nz[a]) continue;
             const uint32_t b_end = pl == 2 ? H : a + 1;
             for (uint32_t b = a; b < b_end; b++) {
                 if (pl == 2 && !cl.nz[b]) continue;
                 const uint32_t mine = e++;
-                if ((mine & 31u) != lane || ((mine >> 5) % parts) != part) continue;
                 const uint32_t bb = pl == 2 ? b : NONE;
                 const size_t ci = (size_t)s * cl.Dall + cl.slot(a, bb == NONE ? H : bb);
-                if (cl.ucache[ci] == cl.ucache[ci]) continue;  // already cached
-                cl.ucache[ci] = tile_entry_sum(cl, T, s, a, bb, n_sub);
+                if (by_terms) {  // warp-uniform control flow from here on
+                    if ((mine % parts) != part) continue;
+                    if (cl.ucache[ci] == cl.ucache[ci]) continue;  // already cached (same address in every lane)
+                    double acc = 0;
+                    for (uint32_t base = 0; base < n_sub; base += 32) {
+                        const uint32_t i = base + lane;
+                        const double v = i < n_sub ? *tile_term(cl, T, s, g, a, bb, i) : 0.0;
+                        const uint32_t m = n_sub - base < 32 ? n_sub - base : 32;
+                        for (uint32_t j = 0; j < m; j++) acc += __shfl_sync(0xFFFFFFFFu, v, j);  // in subsample order
+                    }
+                    if (lane == 0) cl.ucache[ci] = acc;
+                } else {
+                    if ((mine & 31u) != lane || ((mine >> 5) % parts) != part) continue;
+                    if (cl.ucache[ci] == cl.ucache[ci]) continue;  // already cached
+                    cl.ucache[ci] = tile_entry_sum(cl, T, s, a, bb, n_sub);
+                }
             }
         }
     }
@@ -1447,6 +1467,7 @@ __global__ void __launch_bounds__(256, BTG_NOISE_MINBLOCKS) k_noise_chain(DevUni
     // so they are summed in shared memory and leave the block as <= 2S global atomics per iteration
     __shared__ unsigned long long sh_stat[BTG_MAX_SAMPLES * 2];
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    const unsigned long long t_start = ns.phase_ns && blockIdx.x == 0 && threadIdx.x == 0 ? global_timer_ns() : 0;
     for (uint32_t i = tid; i < n_sel; i += nthreads) {  // initGenotypersCallback: fresh genotypers every chain
         Cl cl;
         cl.bind(du, sel[i]);
@@ -1467,6 +1488,7 @@ __global__ void __launch_bounds__(256, BTG_NOISE_MINBLOCKS) k_noise_chain(DevUni
     }
     if (blockIdx.x == 0 && ns.trace) noise_update_block(ns, du.S, prior_shape, prior_scale, o.random_seed, 3, 0, (double)chain, 0, 1, sh_rates);
     grid_barrier(gb);
+    if (t_start) ns.phase_ns[7] += global_timer_ns() - t_start;  // construct + reset of every selected cluster
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
 #if BTG_NOISE_TIMING
     unsigned long long sub_acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // per-thread clock sums of the one-thread sub-steps, flushed once at the end
@@ -1712,9 +1734,21 @@ void btg_count_dist_free(btg_count_dist *cd) {
 }
 
 // ---- unit -------------------------------------------------------------------------------------
-btg_unit *btg_unit_upload(const btg_unit_desc *d) {
+btg_unit *btg_unit_upload(const btg_unit_desc *d) { return btg_unit_upload_dev(d, nullptr, 0, 0); }
+
+btg_unit *btg_unit_upload_dev(const btg_unit_desc *d, const btg_unit_desc *dev, uint64_t n_vh_dev, uint64_t n_vh_bits_dev) {
     if (!ctx().ready) { set_error("btg_init() has not been called"); return nullptr; }
     if (!d || d->n_samples == 0 || d->n_samples > BTG_MAX_SAMPLES) { set_error("bad unit descriptor"); return nullptr; }
+    // row-level arrays may come from the device (dev->field != NULL): device-to-device copy instead of a host round trip
+    auto from = [&](auto host_ptr, auto dev_ptr, size_t n, bool &ok_flag) {
+        using T = std::remove_cv_t<std::remove_pointer_t<decltype(host_ptr)>>;
+        if (!dev_ptr) return upload(host_ptr, n, ok_flag);
+        T *p = nullptr;
+        if (cudaMalloc(&p, (n ? n : 1) * sizeof(T)) != cudaSuccess) { ok_flag = false; return (T *)nullptr; }
+        if (n && cudaMemcpyAsync(p, dev_ptr, n * sizeof(T), cudaMemcpyDeviceToDevice, ctx().stream) != cudaSuccess) ok_flag = false;
+        return p;
+    };
+#define BTG_DEVF(f) (dev ? dev->f : nullptr)
     const uint32_t S = d->n_samples, G = d->n_groups, C = d->n_clusters;
     auto *u = new btg_unit();
     bool ok = true;
@@ -1728,7 +1762,7 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
         fprintf(stderr, "[btgpu] unit upload: %s %.1f ms\n", what, std::chrono::duration<double, std::milli>(now - up_t0).count());
         up_t0 = now;
     };
-    const uint64_t rows = d->cl_kmer_off[C], nvar = d->cl_var_off[C], n_vh = d->kmer_vh_off[rows];
+    const uint64_t rows = d->cl_kmer_off[C], nvar = d->cl_var_off[C], n_vh = BTG_DEVF(kmer_vh_off) ? n_vh_dev : d->kmer_vh_off[rows];
     DevUnit &du = u->du;
     du.S = S; du.G = G; du.C = C;
     du.sample_gender = keep(upload(d->sample_gender, S, ok));
@@ -1739,18 +1773,18 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
     du.cl_kmer_off = keep(upload(d->cl_kmer_off, C + 1, ok));
     du.cl_var_off = keep(upload(d->cl_var_off, C + 1, ok));
     du.cl_mult_off = keep(upload(d->cl_mult_off, C + 1, ok));
-    du.mult = keep(upload(d->mult, d->cl_mult_off[C], ok));
-    du.k_has_counts = keep(upload(d->k_has_counts, rows, ok));
-    du.k_counts = keep(upload(d->k_counts, rows * S, ok));
-    du.k_ic = keep(upload(d->k_ic, rows * 2, ok));
+    du.mult = keep(from(d->mult, BTG_DEVF(mult), d->cl_mult_off[C], ok));
+    du.k_has_counts = keep(from(d->k_has_counts, BTG_DEVF(k_has_counts), rows, ok));
+    du.k_counts = keep(from(d->k_counts, BTG_DEVF(k_counts), rows * S, ok));
+    du.k_ic = keep(from(d->k_ic, BTG_DEVF(k_ic), rows * 2, ok));
     du.cl_uniq_off = keep(upload(d->cl_uniq_off, C + 1, ok));
-    du.uniq_idx = keep(upload(d->uniq_idx, d->cl_uniq_off[C], ok));
-    du.kmer_vh_off = keep(upload(d->kmer_vh_off, rows + 1, ok));
-    du.vh_var = keep(upload(d->vh_var, n_vh, ok));
-    du.vh_bits_off = keep(upload(d->vh_bits_off, n_vh + 1, ok));
-    du.vh_bits = keep(upload(d->vh_bits, d->vh_bits_off[n_vh], ok));
+    du.uniq_idx = keep(from(d->uniq_idx, BTG_DEVF(uniq_idx), d->cl_uniq_off[C], ok));
+    du.kmer_vh_off = keep(from(d->kmer_vh_off, BTG_DEVF(kmer_vh_off), rows + 1, ok));
+    du.vh_var = keep(from(d->vh_var, BTG_DEVF(vh_var), n_vh, ok));
+    du.vh_bits_off = keep(from(d->vh_bits_off, BTG_DEVF(vh_bits_off), n_vh + 1, ok));
+    du.vh_bits = keep(from(d->vh_bits, BTG_DEVF(vh_bits), BTG_DEVF(vh_bits_off) ? n_vh_bits_dev : d->vh_bits_off[n_vh], ok));
     du.cl_hapvar_off = keep(upload(d->cl_hapvar_off, C + 1, ok));
-    du.hap_alleles = keep(upload(d->hap_alleles, d->cl_hapvar_off[C], ok));
+    du.hap_alleles = keep(from(d->hap_alleles, BTG_DEVF(hap_alleles), d->cl_hapvar_off[C], ok));
     du.var_nalleles = keep(upload(d->var_nalleles, nvar, ok));
     du.var_dep = keep(upload(d->var_dep, nvar, ok));
     // nested groups and multicluster k-mers
@@ -1760,13 +1794,17 @@ btg_unit *btg_unit_upload(const btg_unit_desc *d) {
         std::vector<uint64_t> hap_start(C + 1, 0);
         for (uint32_t c = 0; c < C; c++) hap_start[c + 1] = hap_start[c] + d->cl_nhap[c];
         n_hap = hap_start[C];
+        if (n_multi && (BTG_DEVF(k_shared) || BTG_DEVF(k_has_counts))) {
+            set_error("units with multicluster k-mers must pass k_shared and k_has_counts as host arrays (they are validated on the host)");
+            ok = false;
+        }
         for (uint32_t c = 0; c < C && ok; c++)
             for (uint64_t i = d->cl_multi_off[c]; i < d->cl_multi_off[c + 1]; i++) {
                 const uint64_t r = d->cl_kmer_off[c] + d->multi_idx[i];
                 if (d->k_shared[r] == 0xFFFFFFFFu || !d->k_has_counts[r]) { set_error("cluster %u: multicluster k-mer row %llu has no shared count record (k_shared)", c, (unsigned long long)r); ok = false; break; }
                 n_shared = std::max<uint64_t>(n_shared, (uint64_t)d->k_shared[r] + 1);
             }
-        du.k_shared = keep(upload(d->k_shared, rows, ok));
+        du.k_shared = keep(from(d->k_shared, BTG_DEVF(k_shared), rows, ok));
         du.cl_multi_off = keep(upload(d->cl_multi_off, C + 1, ok));
         du.multi_idx = keep(upload(d->multi_idx, n_multi, ok));
         du.hap_start = keep(upload(hap_start.data(), C + 1, ok));
@@ -2203,6 +2241,8 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
     std::vector<std::vector<uint32_t>> sels(n_chains), tasks(n_chains);
     std::vector<uint32_t> n_bigs(n_chains, 0);
     uint32_t *d_sel = nullptr, *d_tasks = nullptr;
+    size_t sel_cap = 0, task_cap = 0;
+    std::function<void(uint32_t)> select_chain;  // group selection of chain b (host; chains in order: the engine stream is sequential)
     if (rc == BTG_OK) {
         // ---- group selection of every chain (InferenceEngine.cpp:174-189), on the host, in chain order ----
         HostEnginePhilox engine;
@@ -2219,8 +2259,16 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
         };
         const uint32_t noise_variants_batch_size = 100000;  // InferenceEngine.cpp:50
         auto is_big = [&](uint32_t c) { return u->h_fill_cost[c] > kBigFillCost; };  // the clusters with a dense tile
-        size_t sel_total = 0, task_total = 0;
-        for (uint32_t b = 0; b < n_chains; b++) {
+        // upper bounds per chain: every local single-cluster group selected; every large cluster with its maximal number of fill tasks
+        for (uint32_t g = 0; g < G; g++) {
+            if (u->h_group_cluster_off[g + 1] - u->h_group_cluster_off[g] != 1) continue;
+            const uint32_t c = (uint32_t)u->h_group_cluster_off[g];
+            sel_cap++;
+            if (is_big(c)) task_cap += 3 * (size_t)std::min<uint64_t>(64, std::max<uint64_t>(1, ((uint64_t)S * ((uint64_t)u->h_nhap[c] * (u->h_nhap[c] + 1) / 2) + 3) / 4));
+        }
+        d_sel = (uint32_t *)dalloc(std::max<size_t>(1, sel_cap) * nc * 4);
+        d_tasks = (uint32_t *)dalloc(std::max<size_t>(1, task_cap) * nc * 4);
+        select_chain = [&, base, noise_groups, engine, group_variants, is_big, noise_variants_batch_size](uint32_t b) mutable {
             uint32_t end = 0, nvv = 0;
             for (size_t i = noise_groups.size(); i > 1; i--) std::swap(noise_groups[i - 1], noise_groups[engine.uniform_int((uint32_t)i)]);
             while (nvv < noise_variants_batch_size && end < noise_groups.size()) { nvv += group_variants(noise_groups[end]); end++; }
@@ -2240,13 +2288,12 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
             n_bigs[b] = n_big;
             for (uint32_t i = 0; i < n_big; i++) {  // a large cluster gets one warp per 32 cache entries (upper bound), at most 64
                 const uint64_t H = u->h_nhap[sel[i]], entries = (uint64_t)S * (H * (H + 1) / 2);
-                const uint32_t parts = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (entries + 31) / 32));
+                // entry-parallel fill: 32 entries per warp; term-parallel fill (>= 16 k-mers per entry expected): 4 entries per warp
+                const bool by_terms = (u->h_fill_cost[sel[i]] / std::max<uint64_t>(1, entries)) >= 16;
+                const uint32_t parts = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, by_terms ? (entries + 3) / 4 : (entries + 31) / 32));
                 for (uint32_t p = 0; p < parts; p++) { tasks[b].push_back(i); tasks[b].push_back(p); tasks[b].push_back(parts); }
             }
-            sel_total += sel.size(); task_total += tasks[b].size();
-        }
-        d_sel = (uint32_t *)dalloc(sel_total * 4);
-        d_tasks = (uint32_t *)dalloc(task_total * 4);
+        };
     }
     if (rc == BTG_OK) {
         for (auto &st : streams) if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) rc = BTG_ECUDA;
@@ -2269,9 +2316,9 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_noise_chain, bs, 0);
         const uint32_t capacity = (uint32_t)std::max(1, per_sm) * (uint32_t)ctx().sm_count;
         const uint32_t max_blocks = std::max(1u, (K > 1 ? capacity - capacity / 16 : capacity) / K);  // this chain's share of the SMs (a few block slots stay free)
-        size_t sel_off = 0, task_off = 0;
         for (auto &st : streams) cudaStreamWaitEvent(st, ev_ready, 0);
         for (uint32_t b = 0; b < n_chains && rc == BTG_OK; b++) {
+            select_chain(b);  // while the previous chains run on the device
             const uint32_t k = b % K;
             cudaStream_t st = streams[k];
             NoiseState ns{};
@@ -2285,10 +2332,9 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
             ns.lg = lg_tab; ns.n_lg = n_lg;
             ns.phase_ns = d_phase;
             GridBarrier gb{d_bar + (size_t)b * 64, d_bar + (size_t)b * 64 + 32};
-            uint32_t *sel_b = d_sel + sel_off, *tasks_b = d_tasks + task_off;
+            uint32_t *sel_b = d_sel + (size_t)b * std::max<size_t>(1, sel_cap), *tasks_b = d_tasks + (size_t)b * std::max<size_t>(1, task_cap);
             if (!sels[b].empty() && cudaMemcpyAsync(sel_b, sels[b].data(), sels[b].size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = BTG_ECUDA; break; }
             if (!tasks[b].empty() && cudaMemcpyAsync(tasks_b, tasks[b].data(), tasks[b].size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = BTG_ECUDA; break; }
-            sel_off += sels[b].size(); task_off += tasks[b].size();
             // this chain's noise stream, and its first draw: the rates of the prior (CountDistribution.cpp:62,163-171)
             k_noise_rng_init<<<1, 1, 0, st>>>(ns.rng, opts->random_seed, b + 1);
             BTG_LAUNCHED();
@@ -2333,11 +2379,11 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
             for (size_t b = 0; b < nc; b++) if (bar[b * 64 + 33]) { set_error("grid barrier of chain %zu timed out (grid not co-resident)", b); rc = BTG_ECUDA; break; }
         }
         if (rc == BTG_OK && d_phase) {
-            unsigned long long ph[4] = {0, 0, 0, 0};
+            unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             cudaMemcpy(ph, d_phase, sizeof ph, cudaMemcpyDeviceToHost);
             const double n_it = (double)n_chains * iters;
-            fprintf(stderr, "[btgpu] noise chain phases, us per iteration (block 0, chains one after the other): fill+one-thread %.1f  large owners %.1f  exchange+update %.1f  release %.1f\n",
-                    ph[0] / n_it / 1e3, ph[1] / n_it / 1e3, ph[2] / n_it / 1e3, ph[3] / n_it / 1e3);
+            fprintf(stderr, "[btgpu] noise chain phases, us per iteration (block 0, chains one after the other): fill+one-thread %.1f  large owners %.1f  exchange+update %.1f  release %.1f; construct+reset %.2f ms per chain\n",
+                    ph[0] / n_it / 1e3, ph[1] / n_it / 1e3, ph[2] / n_it / 1e3, ph[3] / n_it / 1e3, ph[7] / 1e6 / std::max(1u, n_chains));
         }
     } else if (rc != BTG_OK && !*btg_last_error()) {
         set_error("noise estimation allocation failed");
@@ -2475,7 +2521,9 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
             tasks.clear();
             for (uint32_t i = 0; i < n_big; i++) {
                 const uint64_t H = u->h_nhap[sel[i]], entries = (uint64_t)S * (H * (H + 1) / 2);
-                const uint32_t parts = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (entries + 31) / 32));
+                // entry-parallel fill: 32 entries per warp; term-parallel fill (>= 16 k-mers per entry expected): 4 entries per warp
+                const bool by_terms = (u->h_fill_cost[sel[i]] / std::max<uint64_t>(1, entries)) >= 16;
+                const uint32_t parts = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, by_terms ? (entries + 3) / 4 : (entries + 31) / 32));
                 for (uint32_t p = 0; p < parts; p++) { tasks.push_back(i); tasks.push_back(p); tasks.push_back(parts); }
             }
             if (tasks.size() > tasks_cap) {

@@ -54,6 +54,7 @@ struct DevGraphs {
     uint32_t *best_n;               // [C] current number of best paths
     uint8_t *best;                  // path x vertex membership bytes
     uint32_t *status;               // [C] 0 ok, 1 scratch overflow
+    const uint32_t *order;          // [C] clusters sorted by (vertices, sequence length): the 32 clusters of a warp have the same shape
 };
 
 // ---- std::mt19937 -------------------------------------------------------------------------------
@@ -403,8 +404,11 @@ __device__ void add_path_indices(Work &w, const uint16_t *paths, uint32_t n) {
 
 // VariantClusterGraph::findSamplePaths (VariantClusterGraph.cpp:389-482), one thread per cluster
 __global__ void __launch_bounds__(64) k_find_sample_paths(DevGraphs g, BloomView bloom, uint32_t random_seed, uint32_t sample_idx, uint32_t max_paths) {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g.C) return;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.C) return;
+    // thread -> cluster through the shape order: neighbours along the genome differ in vertex count and sequence length and
+    // would keep 8 of 32 lanes busy (profiles/r1_find_sample_paths_ncu_full.txt)
+    const uint32_t c = g.order[t];
     Work w;
     w.g = &g; w.c = c;
     w.v0 = g.cl_vertex_off[c];
@@ -542,6 +546,14 @@ btg_graphs *btg_graphs_upload(const btg_graphs_desc *d, uint32_t max_samples, ui
         best_off[c + 1] = best_off[c] + (uint64_t)best_cap[c] * V;
     }
     if (ok) {
+        std::vector<uint32_t> order(C);
+        for (uint32_t c = 0; c < C; c++) order[c] = c;
+        auto shape = [&](uint32_t c) {
+            const uint64_t v0 = d->cl_vertex_off[c], v1 = d->cl_vertex_off[c + 1];
+            return std::make_pair((uint64_t)(v1 - v0), (uint64_t)(d->v_seq_off[v1] - d->v_seq_off[v0]));
+        };
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return shape(a) > shape(b); });  // largest first
+        g.order = keep(upload(order.data(), C, ok));
         g.v_max_target = keep(upload(max_target.data(), Vtot, ok));
         g.scr_off = keep(upload(scr_off.data(), C + 1, ok));
         g.cl_pool = keep(upload(pool.data(), C, ok));

@@ -232,7 +232,8 @@ def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rate
         pipe.add_sample(s, kd, cdv)
     G = len(inp.graphs["group_cluster_off"]) - 1
     ploidy = np.tile(np.array([female_ploidy if g in ("F", 0) else male_ploidy for g in inp.genders], np.uint8), G)
-    unit = pipe.build_unit(multigroup_bloom=None, ploidy=ploidy)
+    # row-level unit arrays stay in HBM unless the caller wants the unit on the host (tests, fixtures)
+    unit = pipe.build_unit(multigroup_bloom=None, ploidy=ploidy, device_resident=not want_unit)
     if nb_params is None:
         nb_p, nb_size, used = estimate_nb_parameters(pipe, region_buf, spectra_dev, inp.genders, opt, (female_ploidy, male_ploidy))
         info["nb_fit"] = used

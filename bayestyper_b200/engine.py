@@ -55,7 +55,12 @@ class InferenceEngine:
         self.lib = capi.load()
         self.unit = unit
         self._desc = unit.desc()
-        self.h = capi.check(self.lib.btg_unit_upload(C.addressof(self._desc)), self.lib)
+        dd = unit.dev_desc() if getattr(unit, "dev", None) else None
+        if dd is None:
+            self.h = capi.check(self.lib.btg_unit_upload(C.addressof(self._desc)), self.lib)
+        else:   # row-level arrays stay in HBM: device-to-device copies instead of a host round trip
+            self._dev_desc, n_vh, n_vh_bits = dd
+            self.h = capi.check(self.lib.btg_unit_upload_dev(C.addressof(self._desc), C.addressof(self._dev_desc), n_vh, n_vh_bits), self.lib)
 
     def estimate_genotypes(self, cd: CountDistribution, opts: GibbsOpts) -> dict:
         res, arrays = self.unit.alloc_result()

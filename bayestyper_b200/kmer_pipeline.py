@@ -233,7 +233,7 @@ class KmerPipeline:
 
     # ---- classifyPathKmers + getHaplotypeCandidates -----------------------------------------------------------
     @_on_library_stream
-    def build_unit(self, multigroup_bloom=None, var_nalleles=None, var_dep=None, ploidy=None) -> Unit:
+    def build_unit(self, multigroup_bloom=None, var_nalleles=None, var_dep=None, ploidy=None, device_resident: bool = False) -> Unit:
         d, g = self.dev, self.g
         N = self.occ_key.numel()
         occ_cluster = self.t["path_cluster"].to(torch.int64)[self.occ_path.to(torch.int64)]
@@ -327,6 +327,18 @@ class KmerPipeline:
         hap_nested_off, hap_nested, cl_dep_off, dep_cluster, dep_var_off, dep_var = self._nested_tables()
         G = len(g["group_cluster_off"]) - 1
         cpu = lambda t, dt: t.cpu().numpy().astype(dt) if t.dtype != torch.int16 else t.cpu().numpy().view(np.uint16)
+        n_multi = int(multi_rows.numel())
+        dev = None
+        if device_resident and n_multi == 0:
+            # the row-level arrays stay in HBM (btg_unit_upload_dev copies them device to device); bit patterns = the ABI's dtypes
+            dev = {
+                "mult": mult.contiguous(), "k_has_counts": rec[k_key].to(torch.uint8).contiguous(),
+                "k_counts": self.counts[k_key].reshape(-1).contiguous(), "k_ic": self.ic[k_key].reshape(-1).contiguous(),
+                "k_shared": k_shared.to(torch.int32).contiguous(), "uniq_idx": local_row[uniq_rows].to(torch.int32).contiguous(),
+                "kmer_vh_off": _excl_cumsum(kmer_vh).contiguous(), "vh_var": e_var.to(torch.int16).contiguous(),
+                "vh_bits_off": vh_bits_off.contiguous(), "vh_bits": vh_bits.contiguous(), "hap_alleles": hap_alleles[:-1].contiguous(),
+            }
+            self.ext.synchronize()
         a = {
             "sample_gender": np.array([0 if x in ("F", 0) else 1 for x in self.genders], np.uint8),
             "group_ploidy": np.full(G * self.S, 2, np.uint8) if ploidy is None else np.asarray(ploidy, np.uint8),
@@ -334,20 +346,25 @@ class KmerPipeline:
             "group_edge_off": g["group_edge_off"], "group_edge_src": g["group_edge_src"], "group_edge_dst": g["group_edge_dst"],
             "cluster_idx": g["cluster_idx"], "cl_nhap": self.n_paths.astype(np.uint32),
             "cl_kmer_off": cpu(cl_kmer_off, np.uint64), "cl_var_off": g["cl_var_off"], "cl_mult_off": cpu(cl_mult_off, np.uint64),
-            "mult": cpu(mult, np.uint8), "k_has_counts": cpu(rec[k_key], np.uint8),
-            "k_counts": cpu(self.counts[k_key].reshape(-1), np.uint8), "k_ic": cpu(self.ic[k_key].reshape(-1), np.uint8),
-            "k_shared": cpu(k_shared, np.uint32),
-            "cl_uniq_off": cpu(_excl_cumsum(cl_uniq), np.uint64), "uniq_idx": cpu(local_row[uniq_rows], np.uint32),
+            "cl_uniq_off": cpu(_excl_cumsum(cl_uniq), np.uint64),
             "cl_multi_off": cpu(_excl_cumsum(cl_multi), np.uint64), "multi_idx": cpu(local_row[multi_rows], np.uint32),
-            "kmer_vh_off": cpu(_excl_cumsum(kmer_vh), np.uint64), "vh_var": cpu(e_var, np.uint16),
-            "vh_bits_off": cpu(vh_bits_off, np.uint64), "vh_bits": cpu(vh_bits, np.uint8),
-            "cl_hapvar_off": cpu(hapvar_off, np.uint64), "hap_alleles": cpu(hap_alleles[:-1], np.uint16),
+            "cl_hapvar_off": cpu(hapvar_off, np.uint64),
             "var_nalleles": np.asarray(var_nalleles, np.uint16), "var_dep": np.asarray(var_dep, np.uint8),
             "hap_nested_off": hap_nested_off, "hap_nested": hap_nested,
             "cl_dep_off": cl_dep_off, "dep_cluster": dep_cluster, "dep_var_off": dep_var_off, "dep_var": dep_var,
         }
-        u = Unit(a, self.S)
-        u.kmer_words = self.key_kmers(k_key).cpu().numpy().view(np.uint64)
+        if dev is None:
+            a.update({
+                "mult": cpu(mult, np.uint8), "k_has_counts": cpu(rec[k_key], np.uint8),
+                "k_counts": cpu(self.counts[k_key].reshape(-1), np.uint8), "k_ic": cpu(self.ic[k_key].reshape(-1), np.uint8),
+                "k_shared": cpu(k_shared, np.uint32), "uniq_idx": cpu(local_row[uniq_rows], np.uint32),
+                "kmer_vh_off": cpu(_excl_cumsum(kmer_vh), np.uint64), "vh_var": cpu(e_var, np.uint16),
+                "vh_bits_off": cpu(vh_bits_off, np.uint64), "vh_bits": cpu(vh_bits, np.uint8),
+                "hap_alleles": cpu(hap_alleles[:-1], np.uint16),
+            })
+        u = Unit(a, self.S, dev)
+        if dev is None:
+            u.kmer_words = self.key_kmers(k_key).cpu().numpy().view(np.uint64)
         return u
 
     def key_kmers(self, idx=None):

@@ -70,9 +70,17 @@ def min_fraction_observed(nb_p, nb_size, beta: float = 0.275):
 class Unit:
     """Flat haplotype-candidate descriptors of an inference unit (numpy arrays + ctypes view)."""
 
-    def __init__(self, arrays: dict, n_samples: int):
+    # row-level arrays that btg_unit_upload_dev accepts as device pointers
+    DEVICE_FIELDS = ("mult", "k_has_counts", "k_counts", "k_ic", "k_shared", "uniq_idx", "kmer_vh_off", "vh_var", "vh_bits_off", "vh_bits", "hap_alleles")
+
+    def __init__(self, arrays: dict, n_samples: int, dev: dict | None = None):
+        """dev: optional {field: torch tensor on the device} for DEVICE_FIELDS (same bit patterns as the numpy dtypes); those
+        fields may then be absent from `arrays` and are materialised on the host only when `host()` is called."""
         self.a = {}
+        self.dev = dict(dev) if dev else None
         for name, dt in _DESC_FIELDS:
+            if self.dev is not None and name in self.dev and name not in arrays:
+                continue
             self.a[name] = np.ascontiguousarray(arrays[name], dt)
         self.S = n_samples
         self.G = len(self.a["group_cluster_off"]) - 1
@@ -83,8 +91,27 @@ class Unit:
         d = UnitDesc()
         d.n_samples, d.n_groups, d.n_clusters = self.S, self.G, self.Cn
         for name, _ in _DESC_FIELDS:
-            setattr(d, name, self.a[name].ctypes.data)
+            setattr(d, name, self.a[name].ctypes.data if name in self.a else None)
         return d
+
+    def dev_desc(self):
+        """(UnitDesc of device pointers, n_vh, n_vh_bits) for btg_unit_upload_dev, or None for a host-only unit."""
+        if not self.dev:
+            return None
+        d = UnitDesc()
+        for name in self.DEVICE_FIELDS:
+            if name in self.dev:
+                setattr(d, name, self.dev[name].data_ptr())
+        return d, int(self.dev["vh_var"].numel()), int(self.dev["vh_bits"].numel())
+
+    def host(self) -> "Unit":
+        """Materialise device-resident fields on the host (tests, fixtures, sharding)."""
+        if self.dev:
+            dt = dict(_DESC_FIELDS)
+            for name, t in self.dev.items():
+                if name not in self.a:
+                    self.a[name] = np.ascontiguousarray(t.cpu().numpy().view(dt[name]).reshape(-1))
+        return self
 
     # ---- sizes of the result arrays -----------------------------------------------------------
     def alloc_result(self):

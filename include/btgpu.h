@@ -291,6 +291,12 @@ typedef struct btg_unit_desc {
 
 typedef struct btg_unit btg_unit;
 btg_unit *btg_unit_upload(const btg_unit_desc *desc);
+/* The same for callers that built the row-level arrays on the device (the k-mer stages do): every non-NULL pointer in `dev`
+ * is a DEVICE pointer that replaces the host array of the same name in `desc` (which may then be NULL) — for these fields only:
+ * mult, k_has_counts, k_counts, k_ic, k_shared, uniq_idx, kmer_vh_off, vh_var, vh_bits_off, vh_bits, hap_alleles.
+ * n_vh / n_vh_bits are the lengths of vh_var / vh_bits (the host cannot read kmer_vh_off[rows] / vh_bits_off[n_vh] then).
+ * Units with multicluster k-mers keep k_shared and k_has_counts on the host (they are validated there).  dev = NULL: as above. */
+btg_unit *btg_unit_upload_dev(const btg_unit_desc *desc, const btg_unit_desc *dev, uint64_t n_vh, uint64_t n_vh_bits);
 void btg_unit_free(btg_unit *u);
 
 /* the options InferenceEngine / Filters read (src/bayesTyper/main.cpp:389-403) */
