@@ -1950,7 +1950,7 @@ btg_unit *btg_unit_upload_dev(const btg_unit_desc *d, const btg_unit_desc *dev, 
     std::vector<uint64_t> tile_off(C ? C : 1, ~0ull);
     uint64_t tile_total = 0;
     for (uint32_t c = 0; c < C; c++)
-        if (u->h_fill_cost[c] > kBigFillCost) { tile_off[c] = tile_total; tile_total += ((uint64_t)dims[c].nu * (dims[c].H + S + 2) + 31) & ~31ull; }
+        if (u->h_fill_cost[c] > (uint64_t)kBigFillCost * S) { tile_off[c] = tile_total; tile_total += ((uint64_t)dims[c].nu * (dims[c].H + S + 2) + 31) & ~31ull; }
     du.big_tile_off = keep(upload(tile_off.data(), C, ok));
     uint8_t *tile_pool = nullptr;
     ok = ok && cudaMalloc(&tile_pool, tile_total + 32) == cudaSuccess;
@@ -2258,7 +2258,7 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
             return (uint32_t)n;
         };
         const uint32_t noise_variants_batch_size = 100000;  // InferenceEngine.cpp:50
-        auto is_big = [&](uint32_t c) { return u->h_fill_cost[c] > kBigFillCost; };  // the clusters with a dense tile
+        auto is_big = [&](uint32_t c) { return u->h_fill_cost[c] > (uint64_t)kBigFillCost * S; };  // the clusters with a dense tile: cost PER SAMPLE (a one-thread cluster walks its samples in turn)
         // upper bounds per chain: every local single-cluster group selected; every large cluster with its maximal number of fill tasks
         for (uint32_t g = 0; g < G; g++) {
             if (u->h_group_cluster_off[g + 1] - u->h_group_cluster_off[g] != 1) continue;
@@ -2510,7 +2510,7 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
                 if (g >= base && g < base + G) sel.push_back((uint32_t)u->h_group_cluster_off[g - base]);  // this rank's share
             }
             // large clusters first (one warp each in the chain kernel), then by position in the cost order (neighbours share arena slots)
-            auto is_big = [&](uint32_t c) { return u->h_fill_cost[c] > kBigFillCost; };  // the clusters with a dense tile
+            auto is_big = [&](uint32_t c) { return u->h_fill_cost[c] > (uint64_t)kBigFillCost * S; };  // the clusters with a dense tile: cost PER SAMPLE (a one-thread cluster walks its samples in turn)
             std::sort(sel.begin(), sel.end(), [&](uint32_t a, uint32_t b) {
                 const bool ba = is_big(a), bb = is_big(b);
                 return ba != bb ? ba : u->h_layout[a].pos < u->h_layout[b].pos;
