@@ -528,6 +528,78 @@ __device__ __forceinline__ void cl_construct(Cl &cl, const btg_gibbs_opts &o, ui
     cl_reset_frequencies(cl);
 }
 
+// cl_construct by a whole warp (large clusters of the lock-step chain, where the slowest constructor holds every chain's first
+// barrier: 18 ms per chain, profiles/r1_noise_chain_phases.txt): lanes take haplotypes for the column sums of the greedy cover and
+// rows / array elements for everything else; the picks and the random draws are those of the sequential code.
+__device__ __forceinline__ void cl_construct_warp(Cl &cl, const btg_gibbs_opts &o, uint64_t group_index, uint32_t chain, uint32_t lane) {
+    const uint32_t H = cl.H, K = cl.K, S = cl.S, FULL = 0xFFFFFFFFu;
+    const uint32_t *src = cl.u->uniq_idx + cl.u->cl_uniq_off[cl.c];
+    for (uint32_t i = lane; i < cl.n_uniq; i += 32) cl.uniq[i] = src[i];
+    for (uint32_t i = lane; i < cl.Dall * S; i += 32) cl.tally[i] = 0;
+    for (uint32_t s = lane; s < S; s += 32) { cl.dipl[s] = 0xFFFFFFFFu; cl.stats_update[s] = 1; }
+    for (uint32_t i = lane; i < S * 2 * cl.nvar; i += 32) { cl.kc_n[i] = 0; cl.kc_f[2 * i] = 0; cl.kc_f[2 * i + 1] = 0; }
+    for (uint32_t i = lane; i < cl.n_alleles * S * 3; i += 32) { cl.as_n[i] = 0; cl.as_f[i] = 0; }
+    if (lane < 8) cl.misc[lane] = 0;
+    __syncwarp();
+    if (lane == 0) { cl.misc[kSimplexNobs] = 0xFFFFFFFFu; cl.misc[kNMultiSub] = 0; cl.misc[kUseMulti] = 0; }
+    for (uint32_t i = lane; i < cl.n_multi; i += 32) cl.multi[i] = cl.u->multi_idx[cl.u->cl_multi_off[cl.c] + i];
+    // SparsityEstimator::estimateMinimumColumnCover (SparsityEstimator.cpp:41-90), stream kind 1 (lane 0 draws)
+    Philox sp;
+    sp.init(o.random_seed, group_index, cl.u->cluster_idx[cl.c], kRngSparsity, chain);
+    uint32_t n_part = 0;
+    for (uint32_t k = lane; k < K; k += 32) { const uint8_t un = cl.u->k_has_counts[cl.row0 + k]; cl.uncovered[k] = un; n_part += un; }
+    uint32_t n_unc = __reduce_add_sync(FULL, n_part);
+    __syncwarp();
+    uint32_t cover = 0;
+    while (n_unc > 0) {  // warp-uniform
+        uint32_t mx = 0;
+        for (uint32_t hb = 0; hb < H; hb += 32) {  // column cover of haplotype hb + lane over the uncovered rows
+            const uint32_t h = hb + lane;
+            uint32_t col = 0;
+            if (h < H) {
+                for (uint32_t k = 0; k < K; k++) if (cl.uncovered[k]) col += cl.m(k, h);
+                cl.cnt[h] = col;
+            }
+            mx = max(mx, __reduce_max_sync(FULL, col));
+        }
+        __syncwarp();
+        uint32_t ties = 0;
+        for (uint32_t hb = 0; hb < H; hb += 32) ties += __popc(__ballot_sync(FULL, hb + lane < H && cl.cnt[hb + lane] == mx));
+        // DiscreteSampler with unit weights (DiscreteSampler.cpp:61-87): u * n against cum = 1..n
+        uint32_t idx = 0;
+        if (lane == 0) {
+            const double x = sp.u01() * (double)ties;
+            if (ties > 1) while (idx + 1 < ties && !(x < (double)(idx + 1))) idx++;
+        }
+        idx = __shfl_sync(FULL, idx, 0);
+        uint32_t pick = 0;
+        bool found = false;
+        for (uint32_t hb = 0; hb < H; hb += 32) {  // the idx-th haplotype (ascending) whose column cover is the maximum
+            const uint32_t bal = __ballot_sync(FULL, hb + lane < H && cl.cnt[hb + lane] == mx);
+            const uint32_t n = __popc(bal);
+            if (!found) {
+                if (idx < n) { pick = hb + __fns(bal, 0, idx + 1); found = true; }
+                else idx -= n;
+            }
+        }
+        cover++;
+        uint32_t removed = 0;
+        for (uint32_t k = lane; k < K; k += 32) if (cl.uncovered[k] && cl.m(k, pick)) { cl.uncovered[k] = 0; removed++; }
+        n_unc -= __reduce_add_sync(FULL, removed);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        cl.misc[kCover] = cover;
+        cl.misc[kSparse] = cover > 0;
+        if (cover > 0) {  // SparseFrequencyDistribution ctor (FrequencyDistribution.cpp:97-103)
+            const double sp_in = cover / static_cast<double>(H), cap = 1 - 2.220446049250313e-16 * 100;
+            cl.fmisc[0] = sp_in < cap ? sp_in : cap;
+        } else cl.fmisc[0] = 0;
+        cl_reset_frequencies(cl);
+    }
+    __syncwarp();
+}
+
 // VariantClusterHaplotypes::isMaxHaplotypeVariantKmer (VariantClusterHaplotypes.cpp:159-178)
 __device__ __forceinline__ bool cl_is_max_hap_var_kmer(Cl &cl, uint32_t k, uint32_t max_kmers) {
     bool is_max = true;
@@ -1468,7 +1540,28 @@ __global__ void __launch_bounds__(256, BTG_NOISE_MINBLOCKS) k_noise_chain(DevUni
     __shared__ unsigned long long sh_stat[BTG_MAX_SAMPLES * 2];
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
     const unsigned long long t_start = ns.phase_ns && blockIdx.x == 0 && threadIdx.x == 0 ? global_timer_ns() : 0;
-    for (uint32_t i = tid; i < n_sel; i += nthreads) {  // initGenotypersCallback: fresh genotypers every chain
+    for (uint32_t i = tid >> 5; i < n_big; i += nthreads >> 5) {  // large clusters: constructed by a warp, reset by its lane 0
+        Cl cl;
+        cl.bind(du, sel[i]);
+        const uint64_t gidx = o.group_index_base + cl.g;
+        const uint32_t stream_chain = joint ? 0 : chain;
+        if (!joint || chain == 1) cl_construct_warp(cl, o, gidx, stream_chain, tid & 31u);
+        if ((tid & 31u) == 0) {
+            Philox prng, fr;
+            if (!joint || chain == 1) {
+                prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, stream_chain);
+                fr.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngFrequency, stream_chain);
+            } else {
+                prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+                fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
+            }
+            cl_reset<false, true>(cl, o, prng);
+            prng.save(cl.misc, kRng0);
+            fr.save(cl.misc, kRng1);
+        }
+        __syncwarp();
+    }
+    for (uint32_t i = n_big + tid; i < n_sel; i += nthreads) {  // initGenotypersCallback: fresh genotypers every chain
         Cl cl;
         cl.bind(du, sel[i]);
         const uint64_t gidx = o.group_index_base + cl.g;
