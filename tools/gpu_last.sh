@@ -1,2 +1,1 @@
-timeout 300 python -m pytest tests/test_gpu_gibbs.py tests/test_gpu_shard.py tests/test_host_cpp.py -m gpu -q -x 2>&1 | tail -3
-BTG_NOISE_PHASES=1 BIGS=128 timeout 200 python tools/prof_real.py 0.33 2>&1 | grep -E "phases|estimateNoise"
+mkdir -p gpurun_out; timeout 170 python bench.py --steps 3 --warmup 3 > gpurun_out/r1s_bench.json 2> gpurun_out/r1s_bench.err; echo "bench rc=$?"
