@@ -197,3 +197,40 @@ def test_empty_unit(btg):
     res = eng.estimate_genotypes(gcd, fx.opts())
     assert res["gpp"].size == 0
     eng.close()
+
+
+def test_large_clusters_take_the_cooperative_paths_and_match_oracle(btg):
+    """A synthetic unit dense enough for clusters with up to 9 haplotype candidates and 600 k-mers (6 samples): in the lock-step
+    chain these take the warp paths (dense k-mer tiles, grid-wide fill tasks, term-parallel fills for >= 16 k-mers per entry,
+    warp-cooperative construct), in the default mode the chain split.  Noise trace and diplotype tallies must equal the
+    sequential CPU restatement."""
+    from bayestyper_b200 import synth, synth_unit
+    w = synth.small_mixed(260, 20000, 6, 77, 0.15)
+    unit = synth_unit.build_unit(w, seed=3, max_cluster_variants=6)
+    H = unit.a["cl_nhap"].astype(np.int64)
+    nu = np.diff(unit.a["cl_uniq_off"].astype(np.int64))
+    per_sample_cost = (H * (H + 1) // 2) * (nu // 10 + 1)
+    assert ((per_sample_cost > 128) & (nu // 10 >= 16)).sum() >= 20 and H.max() >= 8, "workload no longer exercises the large-cluster paths"
+    nb_p, nb_size = [0.6] * unit.S, [22.5] * unit.S
+    opts = U.default_opts(min_frac=U.min_fraction_observed(nb_p, nb_size), chains=3, burn=5, samples=10)
+    ocd = O.OracleCountDist(nb_p, nb_size)
+    gcd = engine.CountDistribution(nb_p, nb_size)
+    eng = engine.InferenceEngine(unit)
+    otrace = O.oracle_estimate_noise(unit, ocd, opts)
+    gtrace = eng.estimate_noise(gcd, opts)
+    assert (gtrace[:, :2] == otrace[:, :2]).all()
+    assert (np.abs(gtrace[:, 2:] - otrace[:, 2:]) / otrace[:, 2:]).max() < 1e-9
+    gcd.set_noise_rates(ocd.noise_rates())
+    ores, otally = O.oracle_estimate_genotypes(unit, ocd, opts, want_tally=True)
+    gres = eng.estimate_genotypes(gcd, opts)
+    toff = unit.tally_offsets()
+    bad = [c for c in range(unit.Cn) if not (eng.cluster_tally(c).reshape(-1) == otally[int(toff[c]):int(toff[c + 1])]).all()]
+    assert not bad, f"clusters with different tallies: {bad[:10]}"
+    assert np.abs(gres["gpp"] - ores["gpp"]).max() <= GPP_TOL and (gres["gt"] == ores["gt"]).all()
+    # the joint mode on the same unit (all groups have one cluster)
+    ocd2 = O.OracleCountDist(nb_p, nb_size); gcd2 = engine.CountDistribution(nb_p, nb_size)
+    jres_o, jtrace_o = O.oracle_estimate_noise_and_genotypes(unit, ocd2, opts)
+    jres_g, jtrace_g = eng.estimate_noise_and_genotypes(gcd2, opts)
+    assert (np.abs(jtrace_g[:, 2:] - jtrace_o[:, 2:]) / jtrace_o[:, 2:]).max() < 1e-9
+    assert np.abs(jres_g["gpp"] - jres_o["gpp"]).max() <= GPP_TOL and (jres_g["gt"] == jres_o["gt"]).all()
+    eng.close(); gcd.close(); gcd2.close()
