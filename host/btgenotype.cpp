@@ -4,7 +4,7 @@
 //   btgenotype <unit.btd> <out.btd> [--device D] [--random-seed R] [--gibbs-burn-in B] [--gibbs-samples N]
 //              [--number-of-gibbs-chains C] [--kmer-subsampling-rate F] [--max-haplotype-variant-kmers M]
 //              [--noise-genotyping] [--noise-rates r0,r1,...] [--min-genotype-posterior P] [--min-number-of-kmers K]
-//              [--disable-observed-kmers]
+//              [--disable-observed-kmers] [--vcf out.vcf]
 //
 // Option names and defaults are the reference's (main.cpp:378-403).  <unit.btd> is the BTD1 named-array container
 // (bayestyper_b200/btd.py) holding the btg_unit_desc arrays as "unit.<field>", "meta.n_samples" and the per-sample
@@ -21,51 +21,11 @@
 
 #include "btgpu.hpp"
 
+#include "vcf_desc.hpp"
+
 namespace {
 
-struct Array {
-    uint8_t dtype = 0;  // 0 u8, 1 u16, 2 u32, 3 u64, 4 i32, 5 f32, 6 f64, 7 i64
-    std::vector<uint64_t> dims;
-    std::vector<uint8_t> bytes;
-    template <class T> const T *as() const { return reinterpret_cast<const T *>(bytes.data()); }
-    uint64_t count() const { uint64_t n = 1; for (auto d : dims) n *= d; return n; }
-};
-const size_t kItem[8] = {1, 2, 4, 8, 4, 4, 8, 8};
-
-std::map<std::string, Array> read_btd(const std::string &path) {
-    std::ifstream f(path, std::ios::binary);
-    if (!f) throw btg::Error("cannot open " + path);
-    std::vector<char> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-    if (buf.size() < 4 || memcmp(buf.data(), "BTD1", 4) != 0) throw btg::Error(path + ": not a BTD1 file");
-    std::map<std::string, Array> out;
-    size_t off = 4;
-    auto need = [&](size_t n) { if (off + n > buf.size()) throw btg::Error(path + ": truncated"); };
-    while (off < buf.size()) {
-        need(4); uint32_t nl; memcpy(&nl, &buf[off], 4); off += 4;
-        need(nl); std::string name(&buf[off], nl); off += nl;
-        need(2); Array a; a.dtype = (uint8_t)buf[off]; const uint8_t nd = (uint8_t)buf[off + 1]; off += 2;
-        if (a.dtype > 7) throw btg::Error(path + ": bad dtype");
-        need(8ull * nd); a.dims.resize(nd); memcpy(a.dims.data(), &buf[off], 8ull * nd); off += 8ull * nd;
-        const size_t nb = a.count() * kItem[a.dtype];
-        need(nb); a.bytes.assign(buf.begin() + off, buf.begin() + off + nb); off += nb;
-        out.emplace(name, std::move(a));
-    }
-    return out;
-}
-
-struct BtdWriter {
-    std::ofstream f;
-    explicit BtdWriter(const std::string &path) : f(path, std::ios::binary) { if (!f) throw btg::Error("cannot write " + path); f.write("BTD1", 4); }
-    template <class T> void put(const std::string &name, uint8_t dtype, const T *data, std::vector<uint64_t> dims) {
-        const uint32_t nl = (uint32_t)name.size();
-        f.write((const char *)&nl, 4); f.write(name.data(), nl);
-        const uint8_t hd[2] = {dtype, (uint8_t)dims.size()};
-        f.write((const char *)hd, 2); f.write((const char *)dims.data(), 8 * dims.size());
-        uint64_t n = 1; for (auto d : dims) n *= d;
-        f.write((const char *)data, n * sizeof(T));
-    }
-    template <class T> void put(const std::string &name, uint8_t dtype, const std::vector<T> &v) { put(name, dtype, v.data(), {(uint64_t)v.size()}); }
-};
+using namespace btd;
 
 template <class T> const T *field(const std::map<std::string, Array> &m, const std::string &name, uint8_t dtype, uint64_t *n = nullptr) {
     auto it = m.find("unit." + name);
@@ -83,6 +43,7 @@ int main(int argc, char **argv) {
         int device = 0;
         bool joint = false, disable_observed = false;
         std::vector<double> fixed_rates;
+        std::string vcf_path;
         btg_gibbs_opts o{};
         o.random_seed = 20190401; o.gibbs_burn_in = 100; o.gibbs_samples = 250; o.n_chains = 20;       // main.cpp:389-403
         o.kmer_subsampling_rate = 0.1f; o.max_haplotype_variant_kmers = 500; o.min_genotype_posterior = 0.99f; o.min_number_of_kmers = 1.0f;
@@ -100,6 +61,7 @@ int main(int argc, char **argv) {
             else if (a == "--min-number-of-kmers") o.min_number_of_kmers = std::stof(val());
             else if (a == "--noise-genotyping") joint = true;
             else if (a == "--disable-observed-kmers") disable_observed = true;
+            else if (a == "--vcf") vcf_path = val();
             else if (a == "--noise-rates") { std::stringstream ss(val()); std::string t; while (std::getline(ss, t, ',')) fixed_rates.push_back(std::stod(t)); }
             else throw btg::Error("unknown option " + a);
         }
@@ -157,6 +119,13 @@ int main(int argc, char **argv) {
         w.put("acp", 5, res.acp); w.put("anc", 0, res.anc); w.put("hc", 1, res.hc);
         w.put("noise_rates", 6, rates);
         if (!trace.empty()) w.put("noise_trace", 6, trace.data(), {(uint64_t)(trace.size() / (2 + S)), (uint64_t)(2 + S)});
+        if (!vcf_path.empty()) {  // GenotypeWriter (include/btgpu_vcf.hpp): needs the "vcf.*" description of the unit's variants, in unit order
+            const vcfdesc::Description vd = vcfdesc::load(in, S);
+            if (vd.variants.size() != res.view.n_variants) throw btg::Error("the vcf.* description does not cover the unit's variants");
+            std::ofstream vout(vcf_path);
+            if (!vout) throw btg::Error("cannot write " + vcf_path);
+            btg::writeVcf(vout, vd.header, vd.variants, vd.contigs, res.view, S);
+        }
         std::cout << "btgenotype: " << d.n_clusters << " clusters, " << res.view.n_variants << " variants, " << S << " samples; noise rates";
         for (double r : rates) std::cout << ' ' << r;
         std::cout << std::endl;

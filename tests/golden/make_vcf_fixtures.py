@@ -1,0 +1,40 @@
+"""Golden VCFs written by the REFERENCE's own GenotypeWriter (oracle-R: oracle/_ref/btref compiles src/bayesTyper/GenotypeWriter.cpp
+in place) on small seeded workloads: diploid and chrX (haploid males).  (A chrY-only genome makes the reference abort: a female sample has no genomic
+k-mers to fit, CountDistribution.cpp:115; the no-genotype sample format is covered by a synthetic case in tests/test_vcf_writer.py.)  Run in the build
+container (needs /root/reference):  python tests/golden/make_vcf_fixtures.py"""
+import gzip
+import re
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent.parent
+sys.path.insert(0, str(ROOT))
+from bayestyper_b200 import synth  # noqa: E402
+
+VCF_WORKLOADS = {
+    "vcf_mixed_3s": lambda: synth.small_mixed(160, 16_000, 3, seed=81),
+    "vcf_chrx_2s": lambda: synth.small_mixed(90, 9_000, 2, seed=82, chrom="chrX"),
+}
+
+
+def main():
+    btref = ROOT / "oracle" / "_ref" / "btref"
+    for name, mk in VCF_WORKLOADS.items():
+        w = mk()
+        with tempfile.TemporaryDirectory() as td:
+            wd = synth.write_workdir(w, td, n_errors=2000)
+            subprocess.check_call([str(btref), "run", "--workdir", str(wd), "--threads", "4", "--seed", "20190401"], stdout=subprocess.DEVNULL)
+            txt = (Path(wd) / "ref_out" / "bayestyper.vcf").read_text()
+        txt = txt.replace(str(td), "/WORKDIR")          # the temporary directory appears in ##reference and the option lines
+        out = ROOT / "tests" / "golden" / f"{name}.vcf.gz"
+        with gzip.GzipFile(out, "wb", mtime=0) as f:
+            f.write(txt.encode())
+        body = [l for l in txt.splitlines() if not l.startswith("#")]
+        print(name, "genders", w.genders, "records", len(body), "bytes", out.stat().st_size, "ploidy-0 samples", sum(l.count("\t:.:.:.:.:.:.") for l in body),
+              "haploid GT", sum(bool(re.search(r"\t\d:", l)) for l in body))
+
+
+if __name__ == "__main__":
+    main()
