@@ -145,3 +145,39 @@ def test_sample_without_genotype_and_filters(tmp_path):
     assert r.returncode == 0, r.stderr
     got = (tmp_path / "out.vcf").read_text().splitlines()
     assert got[-1] == rec
+
+
+@pytest.mark.parametrize("name", list(VCF_WORKLOADS))
+def test_description_from_graph_builder_reproduces_the_reference_vcf(tmp_path, name):
+    """End to end on the host side: clusters built by graph_builder -> vcf_desc.describe (ids, positions, trimmed alleles, VCS / VCR /
+    VCGS / VCGR in unit order) + the reference's numbers reordered into unit order -> btvcf == the reference's file."""
+    from bayestyper_b200 import graph_builder, vcf_desc
+    exe = _build_btvcf()
+    want = gzip.open(GOLD / f"{name}.vcf.gz", "rt").read()
+    w = VCF_WORKLOADS[name]()
+    graphs = graph_builder.build_unit_graphs(w.chrom, w.reference, w.variants)
+    head = [l for l in want.splitlines() if l.startswith("#")]
+    opt = [l + "\n" for l in head if l.startswith("##BayesTyperOptions")]
+    genome = [l for l in head if l.startswith("##reference=file:")][0][len("##reference=file:"):]
+    desc = vcf_desc.describe(w.chrom, w.reference, w.variants, graphs, head[-1].split("\t")[9:], genome, opt[0], opt[1])
+    # the reference's numbers, parsed in file order, moved to unit order (match by id)
+    by_file = _arrays_from_vcf(want, w.reference, False)
+    file_ids = [bytes(by_file["vcf.ids"][int(a):int(b)]).decode() for a, b in zip(by_file["vcf.ids_off"][:-1], by_file["vcf.ids_off"][1:])]
+    unit_ids = [bytes(desc["vcf.ids"][int(a):int(b)]).decode() for a, b in zip(desc["vcf.ids_off"][:-1], desc["vcf.ids_off"][1:])]
+    assert sorted(file_ids) == sorted(unit_ids)
+    where = {v: i for i, v in enumerate(file_ids)}
+    perm = np.array([where[v] for v in unit_ids])
+    S = len(head[-1].split("\t")) - 9
+    nA = (1 + np.diff(by_file["vcf.alt_off"].astype(np.int64)) + by_file["vcf.has_dependency"]).astype(np.int64)
+    def take(arr, width):          # per-variant blocks of `width[v]` entries
+        off = np.concatenate([[0], np.cumsum(width)])
+        return np.concatenate([arr[off[v]:off[v + 1]] for v in perm])
+    out = {}
+    for k, wdt in (("gt", np.full(len(nA), 2 * S)), ("gq", np.full(len(nA), S)), ("ploidy", np.full(len(nA), S)), ("an", np.ones(len(nA), int)), ("hc", np.ones(len(nA), int)),
+                   ("gpp", S * nA * (nA + 1) // 2), ("app", S * nA), ("nak", S * nA), ("fak", S * nA), ("mac", S * nA), ("saf", S * nA), ("ac", nA), ("af", nA), ("acp", nA), ("anc", nA)):
+        out[k] = take(by_file[k], np.asarray(wdt, np.int64))
+    vcf_desc.write_vcf(tmp_path / "out.vcf", out, desc, S)          # the call a user of the Python mirror makes
+    gl, wl = (tmp_path / "out.vcf").read_text().splitlines(), want.splitlines()
+    assert len(gl) == len(wl)
+    for a, b in zip(gl, wl):
+        assert a == b or (not b.startswith("#") and _qual_tolerant_equal(a, b)), f"\n got: {a[:300]}\nwant: {b[:300]}"
