@@ -73,13 +73,17 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
 
 def build_host(force: bool = False) -> Path:
     """g++ build of the C++ host programs over the C ABI: host/btgenotype (Gibbs stage order, links libbtgpu.so) and host/btvcf
-    (GenotypeWriter, host-only)."""
+    (GenotypeWriter, host-only), host/btkmc (KMC database listing, makeBloom)."""
     hdrs = [ROOT / "include" / "btgpu.hpp", ROOT / "include" / "btgpu.h", ROOT / "include" / "btgpu_vcf.hpp", ROOT / "host" / "btd.hpp", ROOT / "host" / "vcf_desc.hpp"]
     inc = ["-I", str(ROOT / "include"), "-I", str(ROOT / "host")]
     exe = ROOT / "host" / "btgenotype"
     if force or not _newer(exe, [ROOT / "host" / "btgenotype.cpp", LIB, *hdrs]):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", *inc, str(ROOT / "host" / "btgenotype.cpp"), "-L", str(LIBDIR), "-lbtgpu",
                                "-Wl,-rpath,$ORIGIN/../bayestyper_b200/lib", "-o", str(exe)])
+    kmc = ROOT / "host" / "btkmc"
+    if force or not _newer(kmc, [ROOT / "host" / "btkmc.cpp", ROOT / "include" / "btgpu_kmc.hpp", LIB, *hdrs]):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", *inc, str(ROOT / "host" / "btkmc.cpp"), "-L", str(LIBDIR), "-lbtgpu",
+                               "-Wl,-rpath,$ORIGIN/../bayestyper_b200/lib", "-o", str(kmc)])
     vcf = ROOT / "host" / "btvcf"
     if force or not _newer(vcf, [ROOT / "host" / "btvcf.cpp", *hdrs]):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", *inc, str(ROOT / "host" / "btvcf.cpp"), "-o", str(vcf)])

@@ -70,6 +70,7 @@
 #include "NegativeBinomialDistribution.hpp"
 #include "InferenceEngine.hpp"
 #include "GenotypeWriter.hpp"
+#include "kmc_file.h"
 #include "Filters.hpp"
 #undef private
 #undef protected
@@ -681,9 +682,25 @@ finish:
     return 0;
 }
 
+// btref kmc-list --db <kmc_prefix>: every (k-mer, count) the reference's vendored KMC API lists (CKMCFile::OpenForListing /
+// ReadNextKmer, the calls of KmerCounter::parseSampleKmers and MakeBloom::kmc2bloomThreaded), as "<k-mer>\t<count>" lines, preceded
+// by one "#info" line.  Pins include/btgpu_kmc.hpp and bayestyper_b200/kmcio.py (tests/test_kmc.py).
+static int cmdKmcList(const Args & a) {
+    CKMCFile db;
+    if (!db.OpenForListing(a.str("db", ""))) { cerr << "cannot open KMC database " << a.str("db", "") << endl; return 1; }
+    CKMCFileInfo info;
+    db.Info(info);
+    cout << "#info kmer_length " << info.kmer_length << " mode " << info.mode << " counter_size " << info.counter_size << " lut_prefix_length " << info.lut_prefix_length
+         << " min_count " << info.min_count << " max_count " << info.max_count << " total_kmers " << info.total_kmers << " both_strands " << info.both_strands << "\n";
+    CKmerAPI kmer(info.kmer_length);
+    uint32 count;
+    while (db.ReadNextKmer(kmer, count)) cout << kmer.to_string() << "\t" << count << "\n";
+    return 0;
+}
+
 int main(int argc, char ** argv) {
     if (argc < 2) {
-        cerr << "usage: btref <kat|bloom|run> [--key value ...]" << endl;
+        cerr << "usage: btref <kat|bloom|run|kmc-list> [--key value ...]" << endl;
         return 2;
     }
     const string cmd = argv[1];
@@ -691,6 +708,7 @@ int main(int argc, char ** argv) {
     if (cmd == "kat") return cmdKat();
     if (cmd == "bloom") return cmdBloom(a);
     if (cmd == "run") return cmdRun(a);
+    if (cmd == "kmc-list") return cmdKmcList(a);
     cerr << "unknown command " << cmd << endl;
     return 2;
 }

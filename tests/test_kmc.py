@@ -1,0 +1,84 @@
+"""KMC databases: include/btgpu_kmc.hpp (the reader the host programs use) and
+bayestyper_b200/kmcio.py (KMC1 / KMC2 writers for the synthetic samples) against the REFERENCE's vendored KMC API 2.3.0
+(CKMCFile::OpenForListing / ReadNextKmer, driven by `btref kmc-list`): the API must list exactly the k-mers and counts that were
+written, and btkmc must list exactly what the API lists, in the same order.  CPU only."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from bayestyper_b200 import kmcio, synth
+
+ROOT = Path(__file__).resolve().parent.parent
+BTREF = ROOT / "oracle" / "_ref" / "btref"
+K = 55
+
+
+def _build_btkmc():
+    from bayestyper_b200 import build
+    build.build_host()
+    return ROOT / "host" / "btkmc"
+
+
+def _strings(kmers):
+    codes = kmcio._codes(np.ascontiguousarray(kmers, np.uint64).reshape(-1, 2), K)
+    return ["".join("ACGT"[c] for c in row) for row in codes]
+
+
+def _spectrum(n, seed):
+    rng = np.random.default_rng(seed)
+    seq = bytes(rng.choice(list(b"ACGT"), n + K - 1).astype(np.uint8))
+    km = np.unique(synth.canonical_kmers(seq), axis=0)
+    counts = rng.integers(1, 256, size=len(km)).astype(np.uint32)
+    counts[:5] = [1, 255, 2, 254, 128]
+    return km, counts
+
+
+def _listing(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return [l for l in r.stdout.splitlines() if not l.startswith("#")]
+
+
+@pytest.mark.parametrize("layout,p,counter_size", [("kmc1", 7, 1), ("kmc1", 3, 2), ("kmc2", 7, 1), ("kmc2", 11, 4)])
+def test_reader_and_writers_agree_with_the_reference_api(tmp_path, layout, p, counter_size):
+    exe = _build_btkmc()
+    km, counts = _spectrum(6000, 5)
+    if counter_size > 1:
+        counts = counts * np.uint32(37)                      # counts beyond one byte
+    db = tmp_path / "sample"
+    maxc = int(counts.max())
+    if layout == "kmc1":
+        kmcio.write_kmc1(db, km, counts, lut_prefix_length=p, counter_size=counter_size, max_count=maxc)
+        o = synth.kmc_order(km)
+        want = [f"{s}\t{c}" for s, c in zip(_strings(km[o]), counts[o])]   # a KMC1 database lists in lexicographic order
+    else:
+        lk, lc = kmcio.write_kmc2(db, km, counts, lut_prefix_length=p, counter_size=counter_size, max_count=maxc, n_bins=8 if p < 11 else 2, seed=3)
+        want = [f"{s}\t{c}" for s, c in zip(_strings(lk), lc)]             # KMC2: bin by bin, each bin sorted
+    mine = _listing([str(exe), "list", str(db)])
+    assert mine == want
+    if BTREF.exists():                                       # the reference's own reader (build container; absent on the GPU box)
+        ref = _listing([str(BTREF), "kmc-list", "--db", str(db)])
+        assert ref == want, "the reference's KMC API does not list what kmcio wrote"
+        assert mine == ref
+    info = subprocess.run([str(exe), "info", str(db)], capture_output=True, text=True).stdout
+    assert f"kmer_length {K}" in info and f"total_kmers {len(km)}" in info and f"lut_prefix_length {p}" in info
+
+
+def test_count_window_and_errors(tmp_path):
+    """ReadNextKmer skips records outside [min_count, max_count] (kmc_file.cpp:509-513); broken files fail loudly."""
+    exe = _build_btkmc()
+    km, counts = _spectrum(2000, 9)
+    db = tmp_path / "w"
+    kmcio.write_kmc1(db, km, counts, min_count=3, max_count=200)
+    o = synth.kmc_order(km)
+    keep = (counts[o] >= 3) & (counts[o] <= 200)
+    want = [f"{s}\t{c}" for s, c in zip(np.array(_strings(km[o]))[keep], counts[o][keep])]
+    assert _listing([str(exe), "list", str(db)]) == want
+    if BTREF.exists():
+        assert _listing([str(BTREF), "kmc-list", "--db", str(db)]) == want
+    (tmp_path / "bad.kmc_pre").write_bytes(b"KMCPxxxxKMCX")
+    (tmp_path / "bad.kmc_suf").write_bytes(b"KMCSKMCS")
+    r = subprocess.run([str(exe), "list", str(tmp_path / "bad")], capture_output=True, text=True)
+    assert r.returncode == 1 and "not a KMC file" in r.stderr
