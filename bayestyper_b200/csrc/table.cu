@@ -12,9 +12,9 @@
 // device keeps an EXACT table instead: the distinct path k-mers as a sorted key array (built by the caller from
 // the emitted occurrences) that the 17 B/record sample stream and the 1 B/nt genome scan probe directly.
 // Keys are kept in the internal MSB-first form of kmer.cuh (V = hi:lo, nucleotide 0 on top), ascending, i.e. in
-// lexicographic order of the k-mer strings — the order in which a KMC database stores its records
-// (external/kmc_api/kmc_file.cpp:428-515: prefix LUT, then sorted suffixes), so a sample's stream walks the table
-// front to back.  The two key columns are signed 64-bit for the host glue's sort: key_hi = hi (46 bits, >= 0) and
+// lexicographic order of the k-mer strings — the order in which a KMC1 database lists its records
+// (external/kmc_api/kmc_file.cpp:428-515: prefix LUT, then sorted suffixes; a KMC2 database lists signature bin by
+// signature bin, each bin in this order), so a sample's stream walks the table front to back (once per bin).  The two key columns are signed 64-bit for the host glue's sort: key_hi = hi (46 bits, >= 0) and
 // key_lo = lo ^ 2^63 (biased, so that signed order == unsigned order of lo).
 #include "common.cuh"
 #include "kmer.cuh"

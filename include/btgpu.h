@@ -159,8 +159,8 @@ int btg_get_best_paths(const btg_graphs *g, uint32_t *n_paths_out, uint64_t *pat
  * kmer_pipeline.py mirrors KmerCounter's genotype-side stages: countPathKmers, countInterclusterKmers,
  * parseSampleKmers, classifyPathKmers, include/bayesTyper/KmerCounter.hpp:61-67).
  * Table keys: the distinct path k-mers in lexicographic order of their strings (A<C<G<T from nucleotide 0) — the
- * order of the records of a KMC database (external/kmc_api/kmc_file.cpp:428-515), so a sample's stream walks the
- * table front to back.  A key is the k-mer as the 110-bit integer V = sum_i code(nt_i) << 2*(54-i), split into two
+ * order of the records of a KMC1 database (external/kmc_api/kmc_file.cpp:428-515; KMC2: of every signature bin), so a
+ * sample's stream walks the table front to back.  A key is the k-mer as the 110-bit integer V = sum_i code(nt_i) << 2*(54-i), split into two
  * signed 64-bit columns for sorting: key_hi = V >> 64 (46 bits) and key_lo = (V & (2^64-1)) ^ 2^63; keys ascend
  * by (key_hi, key_lo).  btg_table_keys_{from,to}_kmers_dev convert from / to the ABI's packed k-mers.        */
 typedef struct btg_pathwalk_desc {          /* every pointer is a device pointer */
