@@ -248,7 +248,11 @@ def run_ours(args):
     stage_ms, roof = stage_breakdown(lib, inp, opt, stream, dev)
 
     peak, peak_src = measured_peaks()
-    roof.update({"peak": peak, "unit": "GB/s", "frac": roof["achieved"] / peak, "peak_source": peak_src, "bound": "hbm", "traffic": None})
+    roof.update({"peak": peak, "unit": "GB/s", "frac": roof["achieved"] / peak, "peak_source": peak_src, "bound": "hbm", "traffic": None,
+                 # no ncu capture of THIS launch; the same kernel on tools/prof_stream.py's 40.6 M records / 21.0 M keys moved 1.15 GB of DRAM
+                 # traffic for 1.04 GB of algorithmic bytes (profiles/r1_stream_tiled_ncu_full.txt): no wasted re-reads
+                 "traffic_reference": {"profile": "profiles/r1_stream_tiled_ncu_full.txt", "dram_bytes": 1150482000, "algorithmic_bytes": 1038973086,
+                                       "workload": "tools/prof_stream.py: 40,620,727 records, 21,000,000 keys"}})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
