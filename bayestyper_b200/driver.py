@@ -191,7 +191,27 @@ def _region_buffer(reference: bytes, regions) -> np.ndarray:
     return np.concatenate(parts) if parts else np.zeros(0, np.uint8)
 
 
-def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rates=None, resident: bool = False, want_unit: bool = False):
+def inputs_from_kmc(chrom: str, reference: bytes, variants, samples) -> Inputs:
+    """Inputs for one contig from the files `bayesTyper genotype` reads per sample: samples = [(id, gender, kmc_prefix)] as in
+    <samples>.tsv (Sample.cpp:38-70); the KMC databases (KMC1 or KMC2) are read with kmcio.read_kmc, and a <kmc_prefix>.bloomMeta /
+    .bloomData pair written by makeBloom is used when present (otherwise the filter is built on the device)."""
+    from pathlib import Path
+
+    from . import kmcio
+    spectra, blooms, genders = [], [], []
+    for _, gender, prefix in samples:
+        km, ct, _info = kmcio.read_kmc(prefix)
+        spectra.append((km, np.minimum(ct, 255).astype(np.uint8)))          # addSampleCount saturates at 255 (KmerCounts.cpp:178-189)
+        genders.append("F" if str(gender).upper().startswith("F") else "M")
+        meta = Path(str(prefix) + ".bloomMeta")
+        if meta.exists():
+            n, bits, _k = (int(x) for x in meta.read_text().split())
+            blooms.append((np.fromfile(str(prefix) + ".bloomData", np.uint8), n, bits))
+    return Inputs(chrom, reference, variants, genders, spectra, blooms=blooms if len(blooms) == len(samples) else None)
+
+
+def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rates=None, resident: bool = False, want_unit: bool = False,
+             vcf_out=None, sample_names=None):
     """One pass of both hot paths: path search -> k-mer table -> haplotype candidates -> NB fit -> noise -> Gibbs.
     resident=True uses the device copies made by Inputs.make_resident (the `value` leg of bench.py); otherwise every
     input crosses the boundary from host memory inside this call (the `e2e` leg)."""
@@ -253,6 +273,10 @@ def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rate
     res = eng.estimate_genotypes(cd, gopts)
     info["n_clusters"] = unit.Cn
     eng.close(); cd.close()
+    if vcf_out is not None:   # GenotypeWriter (include/btgpu_vcf.hpp through host/btvcf): the result arrays are in unit order, so is the description
+        from . import vcf_desc
+        names = list(sample_names) if sample_names is not None else [f"S{i + 1}" for i in range(S)]
+        vcf_desc.write_vcf(vcf_out, res, vcf_desc.describe(inp.chrom, inp.reference, inp.variants, inp.graphs, names), S)
     return (inp.graphs, unit if want_unit else None, res, info)
 
 

@@ -84,3 +84,54 @@ def write_kmc2(prefix, kmers: np.ndarray, counts: np.ndarray, k: int = K, lut_pr
     with open(str(prefix) + ".kmc_suf", "wb") as f:
         f.write(b"KMCS" + _records(codes, counts, lut_prefix_length, counter_size) + b"KMCS")
     return kmers, counts                                           # in listing order
+
+
+def read_kmc(prefix):
+    """(kmers (n, 2) uint64 in the C ABI's layout, counts (n,) uint32, info dict) of a KMC1 / KMC2 database in listing order, with the
+    database's [min_count, max_count] window applied — the numpy twin of include/btgpu_kmc.hpp (CKMCFile::OpenForListing / ReadNextKmer,
+    external/kmc_api/kmc_file.cpp:66-99,177-292,428-515), for the Python mirror's sample loading."""
+    pre = open(str(prefix) + ".kmc_pre", "rb").read()
+    if len(pre) < 8 or pre[:4] != b"KMCP" or pre[-4:] != b"KMCP":
+        raise ValueError(f"{prefix}.kmc_pre: not a KMC file (marker)")
+    end = len(pre) - 4
+    version = struct.unpack_from("<I", pre, end - 8)[0]
+    header_offset = pre[end - 4]
+    h = end - 4 - header_offset
+    if version == 0x200:
+        k, mode, counter_size, p, sig_len, min_count, max_count, total, flag = struct.unpack_from("<7IQB", pre, h)
+        lut_bytes = h - ((4 ** sig_len + 1) * 4) - 4 - 8
+    elif version == 0:
+        d0, d1, d2, d3, d4 = struct.unpack_from("<5Q", pre, h)
+        k, mode, counter_size, p = d0 & 0xFFFFFFFF, d0 >> 32, d1 & 0xFFFFFFFF, d1 >> 32
+        min_count, max_count, total, flag = d2 & 0xFFFFFFFF, (d2 >> 32) + (d4 & 0xFFFFFFFF00000000), d3, int((d4 & 0xF) == 1)
+        lut_bytes = h - 4
+    else:
+        raise ValueError("unsupported KMC database version")
+    if mode != 0:
+        raise ValueError("KMC databases with quality-aware counters (mode 1) are not supported")
+    lut = np.frombuffer(pre, np.uint64, lut_bytes // 8, 4).astype(np.int64)
+    suf = np.fromfile(str(prefix) + ".kmc_suf", np.uint8)
+    if len(suf) < 8 or bytes(suf[:4]) != b"KMCS" or bytes(suf[-4:]) != b"KMCS":
+        raise ValueError(f"{prefix}.kmc_suf: not a KMC file (marker)")
+    sb = (k - p) // 4
+    rec = suf[4:4 + total * (sb + counter_size)].reshape(total, sb + counter_size)
+    counts = np.zeros(total, np.uint64)
+    for b in range(counter_size):
+        counts |= rec[:, sb + b].astype(np.uint64) << np.uint64(8 * b)
+    # prefix of record r = (index of the last LUT entry <= r) mod 4^p  (LUT entries are starts; empty prefixes repeat a start)
+    starts = np.append(lut, total + 1)
+    prefix_index = np.searchsorted(starts, np.arange(total), side="right") - 1
+    pv = prefix_index % (4 ** p)
+    kmers = np.zeros((total, 2), np.uint64)
+    nt = 0
+    for i in range(p):
+        code = ((pv >> (2 * (p - 1 - i))) & 3).astype(np.uint64)
+        kmers[:, nt >> 5] |= code << np.uint64(2 * (nt & 31)); nt += 1
+    for b in range(sb):
+        for sft in (6, 4, 2, 0):
+            code = ((rec[:, b] >> sft) & 3).astype(np.uint64)
+            kmers[:, nt >> 5] |= code << np.uint64(2 * (nt & 31)); nt += 1
+    keep = (counts >= min_count) & (counts <= max_count)
+    info = {"kmer_length": int(k), "counter_size": int(counter_size), "lut_prefix_length": int(p), "min_count": int(min_count), "max_count": int(max_count),
+            "total_kmers": int(total), "both_strands": not flag, "kmc_version": int(version)}
+    return np.ascontiguousarray(kmers[keep]), counts[keep].astype(np.uint32), info

@@ -62,6 +62,8 @@ def test_reader_and_writers_agree_with_the_reference_api(tmp_path, layout, p, co
         ref = _listing([str(BTREF), "kmc-list", "--db", str(db)])
         assert ref == want, "the reference's KMC API does not list what kmcio wrote"
         assert mine == ref
+    rk, rc, rinfo = kmcio.read_kmc(db)                       # the numpy twin used by the Python mirror
+    assert [f"{s}\t{c}" for s, c in zip(_strings(rk), rc)] == want and rinfo["total_kmers"] == len(km)
     info = subprocess.run([str(exe), "info", str(db)], capture_output=True, text=True).stdout
     assert f"kmer_length {K}" in info and f"total_kmers {len(km)}" in info and f"lut_prefix_length {p}" in info
 
@@ -76,6 +78,8 @@ def test_count_window_and_errors(tmp_path):
     keep = (counts[o] >= 3) & (counts[o] <= 200)
     want = [f"{s}\t{c}" for s, c in zip(np.array(_strings(km[o]))[keep], counts[o][keep])]
     assert _listing([str(exe), "list", str(db)]) == want
+    rk, rc, _ = kmcio.read_kmc(db)
+    assert [f"{s}\t{c}" for s, c in zip(_strings(rk), rc)] == want
     if BTREF.exists():
         assert _listing([str(BTREF), "kmc-list", "--db", str(db)]) == want
     (tmp_path / "bad.kmc_pre").write_bytes(b"KMCPxxxxKMCX")
