@@ -74,7 +74,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
 def build_host(force: bool = False) -> Path:
     """g++ build of the C++ host programs over the C ABI: host/btgenotype (Gibbs stage order, links libbtgpu.so) and host/btvcf
     (GenotypeWriter, host-only), host/btkmc (KMC database listing, makeBloom)."""
-    hdrs = [ROOT / "include" / "btgpu.hpp", ROOT / "include" / "btgpu.h", ROOT / "include" / "btgpu_vcf.hpp", ROOT / "host" / "btd.hpp", ROOT / "host" / "vcf_desc.hpp"]
+    hdrs = [ROOT / "include" / "btgpu.hpp", ROOT / "include" / "btgpu.h", ROOT / "include" / "btgpu_vcf.hpp", ROOT / "include" / "btgpu_params.hpp", ROOT / "host" / "btd.hpp", ROOT / "host" / "vcf_desc.hpp"]
     inc = ["-I", str(ROOT / "include"), "-I", str(ROOT / "host")]
     exe = ROOT / "host" / "btgenotype"
     if force or not _newer(exe, [ROOT / "host" / "btgenotype.cpp", LIB, *hdrs]):

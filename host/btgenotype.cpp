@@ -4,7 +4,7 @@
 //   btgenotype <unit.btd> <out.btd> [--device D] [--random-seed R] [--gibbs-burn-in B] [--gibbs-samples N]
 //              [--number-of-gibbs-chains C] [--kmer-subsampling-rate F] [--max-haplotype-variant-kmers M]
 //              [--noise-genotyping] [--noise-rates r0,r1,...] [--min-genotype-posterior P] [--min-number-of-kmers K]
-//              [--disable-observed-kmers] [--vcf out.vcf]
+//              [--disable-observed-kmers] [--vcf out.vcf] [--output-prefix P]
 //
 // Option names and defaults are the reference's (main.cpp:378-403).  <unit.btd> is the BTD1 named-array container
 // (bayestyper_b200/btd.py) holding the btg_unit_desc arrays as "unit.<field>", "meta.n_samples" and the per-sample
@@ -21,6 +21,7 @@
 
 #include "btgpu.hpp"
 
+#include "btgpu_params.hpp"
 #include "vcf_desc.hpp"
 
 namespace {
@@ -43,7 +44,7 @@ int main(int argc, char **argv) {
         int device = 0;
         bool joint = false, disable_observed = false;
         std::vector<double> fixed_rates;
-        std::string vcf_path;
+        std::string vcf_path, out_prefix;
         btg_gibbs_opts o{};
         o.random_seed = 20190401; o.gibbs_burn_in = 100; o.gibbs_samples = 250; o.n_chains = 20;       // main.cpp:389-403
         o.kmer_subsampling_rate = 0.1f; o.max_haplotype_variant_kmers = 500; o.min_genotype_posterior = 0.99f; o.min_number_of_kmers = 1.0f;
@@ -62,6 +63,7 @@ int main(int argc, char **argv) {
             else if (a == "--noise-genotyping") joint = true;
             else if (a == "--disable-observed-kmers") disable_observed = true;
             else if (a == "--vcf") vcf_path = val();
+            else if (a == "--output-prefix" || a == "-o") out_prefix = val();
             else if (a == "--noise-rates") { std::stringstream ss(val()); std::string t; while (std::getline(ss, t, ',')) fixed_rates.push_back(std::stod(t)); }
             else throw btg::Error("unknown option " + a);
         }
@@ -119,6 +121,15 @@ int main(int argc, char **argv) {
         w.put("acp", 5, res.acp); w.put("anc", 0, res.anc); w.put("hc", 1, res.hc);
         w.put("noise_rates", 6, rates);
         if (!trace.empty()) w.put("noise_trace", 6, trace.data(), {(uint64_t)(trace.size() / (2 + S)), (uint64_t)(2 + S)});
+        if (!out_prefix.empty()) {  // <prefix>_genomic_parameters.txt, <prefix>_noise_parameters.txt (and <prefix>.vcf when the variants are described)
+            std::vector<std::string> names;
+            if (in.count("vcf.sample_names")) names = vcfdesc::strings(in, "vcf.sample_names");
+            else for (uint32_t s = 0; s < S; s++) names.push_back("S" + std::to_string(s + 1));
+            std::ofstream gp(out_prefix + "_genomic_parameters.txt");
+            btg::writeGenomicParameters(gp, names, p.data(), size.data());
+            if (!trace.empty()) { std::ofstream np(out_prefix + "_noise_parameters.txt"); btg::writeNoiseParameters(np, names, trace.data(), trace.size() / (2 + S)); }
+            if (vcf_path.empty() && vcfdesc::present(in)) vcf_path = out_prefix + ".vcf";
+        }
         if (!vcf_path.empty()) {  // GenotypeWriter (include/btgpu_vcf.hpp): needs the "vcf.*" description of the unit's variants, in unit order
             const vcfdesc::Description vd = vcfdesc::load(in, S);
             if (vd.variants.size() != res.view.n_variants) throw btg::Error("the vcf.* description does not cover the unit's variants");

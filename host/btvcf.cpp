@@ -11,6 +11,7 @@
 //   genome_filename, graph_options_header, genotype_options_header (byte arrays).
 #include <iostream>
 
+#include "btgpu_params.hpp"
 #include "vcf_desc.hpp"
 
 int main(int argc, char **argv) {
@@ -34,6 +35,21 @@ int main(int argc, char **argv) {
         std::ofstream out(argv[2]);
         if (!out) throw btg::Error(std::string("cannot write ") + argv[2]);
         btg::writeVcf(out, d.header, d.variants, d.contigs, res.view, S);
+        // optional companions: "noise_trace" [rows][2 + S] and "tab.nb_p_size" [S][2] -> <out minus .vcf>_noise_parameters.txt / _genomic_parameters.txt
+        std::string stem = argv[2];
+        if (stem.size() > 4 && stem.substr(stem.size() - 4) == ".vcf") stem = stem.substr(0, stem.size() - 4);
+        if (in.count("noise_trace")) {
+            const btd::Array &t = need(in, "noise_trace", 6);
+            std::ofstream np(stem + "_noise_parameters.txt");
+            btg::writeNoiseParameters(np, d.sample_names, t.as<double>(), t.count() / (2 + S));
+        }
+        if (in.count("tab.nb_p_size")) {
+            const btd::Array &t = need(in, "tab.nb_p_size", 6);
+            std::vector<double> p(S), size(S);
+            for (uint32_t s = 0; s < S; s++) { p[s] = t.as<double>()[2 * s]; size[s] = t.as<double>()[2 * s + 1]; }
+            std::ofstream gp(stem + "_genomic_parameters.txt");
+            btg::writeGenomicParameters(gp, d.sample_names, p.data(), size.data());
+        }
         std::cout << "btvcf: wrote " << nv << " variants, " << S << " samples to " << argv[2] << std::endl;
         return 0;
     } catch (const std::exception &e) {

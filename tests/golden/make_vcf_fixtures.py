@@ -27,6 +27,10 @@ def main():
             wd = synth.write_workdir(w, td, n_errors=2000)
             subprocess.check_call([str(btref), "run", "--workdir", str(wd), "--threads", "4", "--seed", "20190401"], stdout=subprocess.DEVNULL)
             txt = (Path(wd) / "ref_out" / "bayestyper.vcf").read_text()
+            if name == "vcf_chrx_2s":   # the two parameter files of the same run (tests/test_vcf_writer.py::test_parameter_files_reproduce_the_reference)
+                (ROOT / "tests" / "golden" / "params_chrx_2s_genomic.txt").write_text((Path(wd) / "ref_out" / "bayestyper_genomic_parameters.txt").read_text())
+                with gzip.GzipFile(ROOT / "tests" / "golden" / "params_chrx_2s_noise.txt.gz", "wb", mtime=0) as f:
+                    f.write((Path(wd) / "ref_out" / "bayestyper_noise_parameters.txt").read_bytes())
         txt = txt.replace(str(td), "/WORKDIR")          # the temporary directory appears in ##reference and the option lines
         out = ROOT / "tests" / "golden" / f"{name}.vcf.gz"
         with gzip.GzipFile(out, "wb", mtime=0) as f:

@@ -181,3 +181,28 @@ def test_description_from_graph_builder_reproduces_the_reference_vcf(tmp_path, n
     assert len(gl) == len(wl)
     for a, b in zip(gl, wl):
         assert a == b or (not b.startswith("#") and _qual_tolerant_equal(a, b)), f"\n got: {a[:300]}\nwant: {b[:300]}"
+
+
+def test_parameter_files_reproduce_the_reference(tmp_path):
+    """<out>_noise_parameters.txt and <out>_genomic_parameters.txt (include/btgpu_params.hpp) byte for byte against the files the
+    reference wrote for the chrX fixture (oracle-R run of make_vcf_fixtures.py; InferenceEngine.cpp:165-172,205,229,266,
+    CountDistribution.cpp:70-78,128-137), given the reference's numbers."""
+    exe = _build_btvcf()
+    noise = gzip.open(GOLD / "params_chrx_2s_noise.txt.gz", "rt").read()
+    genomic = (GOLD / "params_chrx_2s_genomic.txt").read_text()
+    rows = [l.split("\t") for l in noise.splitlines()[1:]]
+    trace = np.array([[float(x) for x in r] for r in rows], np.float64)
+    gm = [l.split("\t") for l in genomic.splitlines()[1:]]
+    mean, var = np.array([float(x[1]) for x in gm]), np.array([float(x[2]) for x in gm])
+    nb_p = mean / var
+    nb_size = mean * nb_p / (1 - nb_p)                       # mean = size (1 - p) / p
+    want_vcf = gzip.open(GOLD / "vcf_chrx_2s.vcf.gz", "rt").read()
+    w = VCF_WORKLOADS["vcf_chrx_2s"]()
+    a = _arrays_from_vcf(want_vcf, w.reference, False)
+    a["noise_trace"] = trace
+    a["tab.nb_p_size"] = np.stack([nb_p, nb_size], 1)
+    btd.write(tmp_path / "in.btd", a)
+    r = subprocess.run([str(exe), str(tmp_path / "in.btd"), str(tmp_path / "out.vcf")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "out_noise_parameters.txt").read_text() == noise
+    assert (tmp_path / "out_genomic_parameters.txt").read_text() == genomic
