@@ -166,3 +166,42 @@ def test_table_lookup_and_saturation(btg):
     _sync(btg)
     capi.check(btg.btg_table_set_index_dev(None, 0), btg)
     assert (idx2.cpu().numpy() == exp).all()
+
+
+def test_stream_full_size_properties(btg):
+    """The sample-stream kernel at a size the tiled path dominates (2 M keys, 6 M records), through size-independent properties: the
+    table after a KMC-ordered stream equals the table after the same records shuffled (order independence), the number of keys
+    with a record equals the number of distinct present records, and the sum of the counts equals the sum over present records."""
+    from bayestyper_b200 import synth
+    rng = np.random.default_rng(11)
+    n_keys, n_hit, n_miss = 2_000_000, 2_400_000, 3_600_000
+    km = _random_kmers(rng, n_keys)
+    km = km[synth.kmc_order(km)]
+    kmd = torch.from_numpy(km.view(np.int64)).cuda()
+    kw0 = torch.empty(n_keys, dtype=torch.int64, device="cuda"); kw1 = torch.empty_like(kw0)
+    torch.cuda.synchronize()
+    capi.check(btg.btg_table_keys_from_kmers_dev(kmd.data_ptr(), n_keys, kw0.data_ptr(), kw1.data_ptr(), None), btg)
+    _sync(btg)
+    hi = kw1.cpu().numpy()
+    bits = 20
+    lut = np.concatenate([[0], np.cumsum(np.bincount(hi >> (46 - bits), minlength=1 << bits))]).astype(np.int64)
+    lut_d = torch.from_numpy(lut).cuda()
+    pick = rng.integers(0, n_keys, size=n_hit)                       # present records, with repeats (saturating adds)
+    recs = np.concatenate([km[pick], _random_kmers(rng, n_miss)])
+    cts = rng.integers(1, 40, size=len(recs)).astype(np.uint8)
+    expect = np.minimum(np.bincount(pick, weights=cts[:n_hit].astype(np.float64), minlength=n_keys), 255).astype(np.uint8)
+    tables = []
+    for order in (synth.kmc_order(recs), rng.permutation(len(recs))):
+        rd = torch.from_numpy(np.ascontiguousarray(recs[order]).view(np.int64)).cuda(); cd_ = torch.from_numpy(np.ascontiguousarray(cts[order])).cuda()
+        counts = torch.zeros(n_keys, dtype=torch.uint8, device="cuda"); rec = torch.zeros(n_keys, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        capi.check(btg.btg_table_set_index_dev(lut_d.data_ptr(), bits), btg)
+        capi.check(btg.btg_table_add_sample_kmers_dev(kw0.data_ptr(), kw1.data_ptr(), n_keys, rd.data_ptr(), cd_.data_ptr(), len(recs), 1, 0, counts.data_ptr(),
+                                                      rec.data_ptr(), None), btg)
+        _sync(btg)
+        capi.check(btg.btg_table_set_index_dev(None, 0), btg)
+        tables.append((counts.cpu().numpy(), rec.cpu().numpy()))
+    (c0, r0), (c1, r1) = tables
+    assert (c0 == c1).all() and (r0 == r1).all(), "the table depends on the order of the stream"
+    assert int(r0.sum()) == len(np.unique(pick)) and int(c0.astype(np.int64).sum()) == int(expect.astype(np.int64).sum())
+    assert (c0 == expect).all()
