@@ -86,3 +86,29 @@ def test_count_window_and_errors(tmp_path):
     (tmp_path / "bad.kmc_suf").write_bytes(b"KMCSKMCS")
     r = subprocess.run([str(exe), "list", str(tmp_path / "bad")], capture_output=True, text=True)
     assert r.returncode == 1 and "not a KMC file" in r.stderr
+
+
+def test_driver_inputs_from_kmc_files(tmp_path, oracle):
+    """driver.inputs_from_kmc: the per-sample files `bayesTyper genotype` reads (<samples>.tsv rows: id, gender, KMC prefix; the KMC
+    database; the .bloomMeta / .bloomData pair of makeBloom) become the Python mirror's Inputs without touching the GPU."""
+    from bayestyper_b200 import driver
+    from tests import _oracle as O
+    km, counts = _spectrum(3000, 21)
+    counts = np.minimum(counts * 3, 700).astype(np.uint32)            # some counts beyond 255: addSampleCount saturates
+    kmcio.write_kmc2(tmp_path / "S1", km, counts, counter_size=2, max_count=700, n_bins=4, seed=1)
+    kmcio.write_kmc1(tmp_path / "S2", km[::2], counts[::2], counter_size=2, max_count=700)
+    m = oracle.bto_bloom_num_bits(len(km), 1e-3)
+    nh = oracle.bto_bloom_num_hashes(m, len(km))
+    bits = O.bloom_build(np.ascontiguousarray(km), m, nh)
+    (tmp_path / "S1.bloomMeta").write_text(f"{len(km)}\t{m}\t{K}\n")
+    bits.tofile(tmp_path / "S1.bloomData")
+    ref = b"ACGT" * 100
+    inp = driver.inputs_from_kmc("chr1", ref, [], [("S1", "Female", tmp_path / "S1"), ("S2", "M", tmp_path / "S2")])
+    assert inp.genders == ["F", "M"] and inp.blooms is None            # S2 has no filter files: filters are built on the device
+    (k1, c1), (k2, c2) = inp.spectra
+    want = {tuple(k): min(int(c), 255) for k, c in zip(km.tolist(), counts.tolist())}
+    assert len(k1) == len(km) and all(want[tuple(k)] == int(c) for k, c in zip(k1.tolist(), c1.tolist()))
+    assert len(k2) == len(km[::2]) and c1.dtype == np.uint8 and int(c1.max()) == 255
+    inp1 = driver.inputs_from_kmc("chr1", ref, [], [("S1", "F", tmp_path / "S1")])
+    (b, n, nbits), = inp1.blooms
+    assert n == len(km) and nbits == m and (b == bits).all()
