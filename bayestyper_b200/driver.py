@@ -150,7 +150,7 @@ class Inputs:
     def prepare(self):
         if self.graphs is None:
             self.graphs = graph_builder.build_unit_graphs(self.chrom, self.reference, self.variants)
-            self.regions = graph_builder.intercluster_regions(len(self.reference), self.variants)
+            self.regions = [(int(a), int(b)) for a, b in self.graphs["regions"]]
         return self
 
     def make_resident(self, lib, opt: "Options"):

@@ -1,6 +1,6 @@
 """The "vcf.*" description that the VCF writer (include/btgpu_vcf.hpp, host/btvcf, host/btgenotype --vcf) needs next to the result
 arrays: per variant of the unit, in unit order, what the reference keeps in VariantInfo and in the cluster fields of Genotypes
-(VCS / VCR / VCGS / VCGR).  Built from graph_builder's output for non-nested candidate sets (every group is one cluster)."""
+(VCS / VCR / VCGS / VCGR).  Built from graph_builder's output (groups of several clusters included)."""
 from __future__ import annotations
 
 import numpy as np
@@ -14,12 +14,7 @@ def _strs(items):
 
 def unit_variant_order(graphs: dict) -> np.ndarray:
     """Index into the caller's (position-sorted) variant list for every variant of the unit, in unit order."""
-    sizes_unit = np.diff(np.asarray(graphs["cl_var_off"], np.int64))
-    order = np.asarray(graphs["cluster_order"], np.int64)
-    size_of = np.zeros(len(order), np.int64)
-    size_of[order] = sizes_unit
-    start = np.concatenate([[0], np.cumsum(size_of)])
-    return np.concatenate([np.arange(start[c], start[c] + size_of[c]) for c in order]) if len(order) else np.zeros(0, np.int64)
+    return np.asarray(graphs["var_input_idx"], np.int64)
 
 
 def describe(chrom: str, reference: bytes, variants, graphs: dict, sample_names, genome_filename: str = "", graph_options_header: str = "",
@@ -35,7 +30,14 @@ def describe(chrom: str, reference: bytes, variants, graphs: dict, sample_names,
     alt_bytes = bytes(np.asarray(graphs["alt_seq"], np.uint8))
     n_var = len(pos)
     vcs = np.zeros(n_var, np.uint32)
+    vcgs = np.zeros(n_var, np.uint32)
     vcr = [None] * n_var
+    vcgr = [None] * n_var
+    gco = np.asarray(graphs["group_cluster_off"], np.int64)
+    for g in range(len(gco) - 1):                                                                    # VariantClusterGroup::region, number of clusters
+        v0, v1 = cvo[gco[g]], cvo[gco[g + 1]]
+        vcgs[v0:v1] = gco[g + 1] - gco[g]
+        vcgr[v0:v1] = [f"{chrom}:{int(graphs['group_start'][g])}-{int(graphs['group_end'][g])}"] * (v1 - v0)
     for c in range(len(cvo) - 1):
         v0, v1 = cvo[c], cvo[c + 1]
         end = max(pos[v] - 1 + reflen[vao[v]:vao[v + 1]].max() - 1 for v in range(v0, v1)) + 1       # 1-based end of the cluster's reference span
@@ -53,7 +55,7 @@ def describe(chrom: str, reference: bytes, variants, graphs: dict, sample_names,
     a["vcf.genotype_options_header"] = np.frombuffer(genotype_options_header.encode(), np.uint8).copy()
     a["vcf.ids"], a["vcf.ids_off"] = _strs([ids[i] for i in vorder])
     a["vcf.vcr"], a["vcf.vcr_off"] = _strs(vcr)
-    a["vcf.vcgr"], a["vcf.vcgr_off"] = _strs(vcr)                      # one cluster per group
+    a["vcf.vcgr"], a["vcf.vcgr_off"] = _strs(vcgr)
     a["vcf.alt_seq"], a["vcf.alt_seq_off"] = _strs([alt_bytes[aso[i]:aso[i + 1]] for i in range(len(reflen))])
     a["vcf.alt_aco"], a["vcf.alt_aco_off"] = _strs([""] * len(reflen))  # no ACO attribute in the candidate sets handled here
     a["vcf.alt_ref_length"] = reflen.astype(np.uint32)
@@ -62,7 +64,7 @@ def describe(chrom: str, reference: bytes, variants, graphs: dict, sample_names,
     a["vcf.position"] = pos.astype(np.uint32)
     a["vcf.has_dependency"] = np.asarray(graphs["var_dep"], np.uint8)
     a["vcf.vcs"] = vcs
-    a["vcf.vcgs"] = np.ones(n_var, np.uint32)
+    a["vcf.vcgs"] = vcgs
     return a
 
 

@@ -102,10 +102,11 @@ inline void vcfRecord(std::ostream &os, const VcfVariant &v, uint64_t vi, const 
         os << v.alt_alleles[a].sequence << chrom.substr(v.position + v.alt_alleles[a].ref_length - 1, max_ref - v.alt_alleles[a].ref_length);
     }
     if (v.has_dependency) os << ",*";
-    // writeQualityAndFilter: max_alt_allele_call_probability = max ACP over the alternative alleles
+    // writeQualityAndFilter: max_alt_allele_call_probability = max ACP over the alternative alleles, the missing ('*') allele
+    // of a dependent variant not among them (VariantClusterGenotyper.cpp:509-513)
     const uint64_t o = r.valt_off[vi];
     float max_acp = 0;
-    for (uint32_t a = 1; a < nA; a++) max_acp = std::max(max_acp, r.acp[o + a]);
+    for (uint32_t a = 1; a <= v.alt_alleles.size(); a++) max_acp = std::max(max_acp, r.acp[o + a]);
     if (floatCompare(max_acp, 1)) os << "\t99";
     else if (floatCompare(max_acp, 0)) os << "\t0";
     else os << "\t" << -10 * std::log10(1 - max_acp);

@@ -16,12 +16,16 @@ from bayestyper_b200 import synth  # noqa: E402
 VCF_WORKLOADS = {
     "vcf_mixed_3s": lambda: synth.small_mixed(160, 16_000, 3, seed=81),
     "vcf_chrx_2s": lambda: synth.small_mixed(90, 9_000, 2, seed=82, chrom="chrX"),
+    # deletions with variants inside: groups of several clusters (VCGS > 1, VCGR != VCR) and '*' alleles on dependent variants
+    "vcf_nested_2s": lambda: synth.nested_sv(5, 14_000, 2, seed=83, n_background=40, sv_len=(150, 500)),
 }
 
 
-def main():
+def main(only=None):
     btref = ROOT / "oracle" / "_ref" / "btref"
     for name, mk in VCF_WORKLOADS.items():
+        if only and name not in only:
+            continue
         w = mk()
         with tempfile.TemporaryDirectory() as td:
             wd = synth.write_workdir(w, td, n_errors=2000)
@@ -41,4 +45,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:])

@@ -8,29 +8,21 @@ from tests._fixtures import GOLD
 from tests.golden.make_fixtures import PIPE_WORKLOADS
 
 
-def test_overlapping_variants_rejected_loudly():
-    """Nested clusters need VariantFileParser's dependency bookkeeping (VariantFileParser.cpp:735-1000), which stays
-    with the reference (SURVEY §8 out of scope): the builder says so instead of producing a wrong graph.  The GPU
-    stages themselves take the reference's nested graphs (tests/test_gpu_pipeline.py[pipe_nested_2s])."""
-    w = PIPE_WORKLOADS["pipe_nested_2s"]()
-    with pytest.raises(ValueError, match="nested"):
-        graph_builder.build_unit_graphs(w.chrom, w.reference, w.variants)
-
-
-@pytest.mark.parametrize("name", [n for n in PIPE_WORKLOADS if "nested" not in n])
+@pytest.mark.parametrize("name", list(PIPE_WORKLOADS))
 def test_graphs_identical_to_reference(name):
     d = btd.read(GOLD / f"{name}.btd")
     g = {k[2:]: v for k, v in d.items() if k.startswith("g.")}
     w = PIPE_WORKLOADS[name]()
     b = graph_builder.build_unit_graphs(w.chrom, w.reference, w.variants)
     for k in ("group_cluster_off", "cl_vertex_off", "cl_var_off", "v_seq_off", "seq", "v_flags", "v_var", "v_allele", "v_nested",
-              "v_in_off", "v_in_src", "var_pos", "var_dep", "var_nalt", "alt_reflen", "alt_seq", "v_refvar_off", "cluster_idx"):
+              "v_in_off", "v_in_src", "var_pos", "var_dep", "var_nalt", "alt_reflen", "alt_seq", "v_refvar_off", "cluster_idx",
+              "group_nvar", "group_src_off", "group_src", "group_edge_off", "group_edge_src", "group_edge_dst"):
         assert len(b[k]) == len(g[k]), k
         assert (b[k] == g[k]).all(), k
     # reference_variant_indices come out of an unordered_set: compare as sets per vertex
     for v in range(len(g["v_flags"])):
         a0, a1 = int(g["v_refvar_off"][v]), int(g["v_refvar_off"][v + 1])
         assert set(b["v_refvar"][a0:a1].tolist()) == set(g["v_refvar"][a0:a1].tolist())
-    regs = graph_builder.intercluster_regions(len(w.reference), w.variants)
+    regs = graph_builder.intercluster_regions(w.chrom, w.reference, w.variants)
     ref_regs = sorted((int(a), int(bb)) for dec, a, bb in d["regions"])
     assert sorted(regs) == ref_regs
