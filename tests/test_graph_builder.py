@@ -26,3 +26,74 @@ def test_graphs_identical_to_reference(name):
     regs = graph_builder.intercluster_regions(w.chrom, w.reference, w.variants)
     ref_regs = sorted((int(a), int(bb)) for dec, a, bb in d["regions"])
     assert sorted(regs) == ref_regs
+
+
+def test_unordered_container_order_matches_the_toolchain(tmp_path):
+    """stdhash_order.UnorderedUInt against std::unordered_set<unsigned> of this toolchain's libstdc++ (the containers whose
+    iteration order the reference's cluster order, merge survivor and dependency-edge order come from)."""
+    import random
+    import shutil
+    import subprocess
+    from bayestyper_b200.stdhash_order import UnorderedUInt
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    src = tmp_path / "probe.cpp"
+    src.write_text("""
+#include <unordered_set>
+#include <cstdio>
+int main() { std::unordered_set<unsigned> s; char op; unsigned k;
+  while (std::scanf(" %c", &op) == 1) {
+    if (op == 'i') { if (std::scanf("%u", &k) == 1) s.insert(k); }
+    else if (op == 'e') { if (std::scanf("%u", &k) == 1) s.erase(k); }
+    else if (op == 'n') { s = std::unordered_set<unsigned>(); }
+    else if (op == 'p') { for (auto x : s) std::printf("%u ", x); std::printf("\\n"); } } }
+""")
+    subprocess.check_call(["g++", "-O1", "-o", str(tmp_path / "probe"), str(src)])
+    rnd = random.Random(5)
+    ops, want = [], []
+    for _ in range(200):
+        ops.append("n")
+        u, keys = UnorderedUInt(), []
+        for _ in range(rnd.randint(1, 150)):
+            if keys and rnd.random() < 0.25:
+                k = rnd.choice(keys); keys.remove(k); u.erase(k); ops.append(f"e {k}")
+            else:
+                k = rnd.randint(0, rnd.choice([20, 200, 5000]))
+                if u.insert(k):
+                    keys.append(k)
+                ops.append(f"i {k}")
+            if rnd.random() < 0.2:
+                ops.append("p"); want.append(" ".join(map(str, u)))
+        ops.append("p"); want.append(" ".join(map(str, u)))
+    got = subprocess.run([str(tmp_path / "probe")], input="\n".join(ops), capture_output=True, text=True).stdout.splitlines()
+    assert [g.strip() for g in got] == want
+
+
+def test_adversarial_candidate_sets_identical_to_reference():
+    """Nested / overlapping / bridging deletions, multi-allelic variants with several reference spans, '*' alleles, copy-number
+    insertions in front of tandem repeats, N runs, excluded variants: graphs, groups, dependency edges and intercluster regions
+    the REFERENCE built (tools/fuzz_graph_builder.py --write-golden, oracle-R) against graph_builder on the stored cases."""
+    from bayestyper_b200 import synth
+    d = btd.read(GOLD / "graphs_adversarial.btd")
+    n = int(d["meta.n_cases"][0])
+    assert n >= 20
+    n_multi = 0
+    for c in range(n):
+        ref = bytes(d[f"c{c}.reference"])
+        alleles = bytes(d[f"c{c}.alleles"]).split(b"\n")
+        var = []
+        for p, al in zip(d[f"c{c}.var_pos"].tolist(), alleles):
+            t = al.split(b",")
+            var.append(synth.Variant(int(p), t[0], t[1:]))
+        b = graph_builder.build_unit_graphs("chrF", ref, var)
+        g = {k[len(f"c{c}.g."):]: v for k, v in d.items() if k.startswith(f"c{c}.g.")}
+        for k in g:
+            if k == "v_refvar":
+                continue
+            assert len(b[k]) == len(g[k]) and (np.asarray(b[k]) == g[k]).all(), (c, k)
+        for v in range(len(g["v_flags"])):
+            a0, a1 = int(g["v_refvar_off"][v]), int(g["v_refvar_off"][v + 1])
+            assert set(b["v_refvar"][a0:a1].tolist()) == set(g["v_refvar"][a0:a1].tolist())
+        assert sorted((int(x), int(y)) for x, y in b["regions"]) == sorted((int(x), int(y)) for x, y in d[f"c{c}.regions"])
+        n_multi += int((np.diff(g["group_cluster_off"].astype(np.int64)) > 1).sum())
+    assert n_multi >= 20          # the stored cases do exercise groups of several clusters
