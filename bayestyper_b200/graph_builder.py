@@ -93,10 +93,10 @@ def copy_number_variant_length(allele: bytes, chrom: bytes, start: int, k: int =
 
 class _Variant:
     """VariantCluster::Variant (include/bayesTyper/VariantCluster.hpp:56-71) plus the index into the caller's list."""
-    __slots__ = ("input_idx", "has_dependency", "num_redundant", "alts")
+    __slots__ = ("input_idx", "has_dependency", "num_redundant", "alts", "aco")
 
     def __init__(self, input_idx, has_dependency):
-        self.input_idx, self.has_dependency, self.num_redundant, self.alts = input_idx, has_dependency, None, []
+        self.input_idx, self.has_dependency, self.num_redundant, self.alts, self.aco = input_idx, has_dependency, None, [], []
 
 
 class _Cluster:
@@ -209,7 +209,8 @@ def parse_variants(chrom: str, reference: bytes, variants, k: int = K, max_allel
                    copy_number_variant_threshold: float = 0.5):
     """VariantFileParser::parseVariants for one contig (VariantFileParser.cpp:241-545).
 
-    variants: objects with .pos (0-based), .ref (bytes), .alts (list of bytes), sorted by position.
+    variants: objects with .pos (0-based), .ref (bytes), .alts (list of bytes), optionally .id and .aco (per alternative allele
+    call-set origin), sorted by position.
     Returns (groups, regions): every group an UnorderedUInt cluster index -> _Cluster, in file order; regions the inclusive
     (start, end) intercluster stretches of at least k nucleotides."""
     chrom_up = reference.upper()
@@ -250,6 +251,7 @@ def parse_variants(chrom: str, reference: bytes, variants, k: int = K, max_allel
             raise ValueError(f"duplicate alternative alleles at position {pos + 1}")
         if pos + len(ref) > n:
             raise ValueError(f"variant at position {pos + 1} runs past the end of the contig")
+        origins = getattr(v, "aco", None) or [""] * len(alts)               # INFO ACO, one per alternative allele ('*' dropped above)
         pairs = [_right_trim(ref, a) for a in alts]
         excluded = chrom_up[pos:pos + len(ref)] != ref or pos < k - 1
         included = []
@@ -271,6 +273,7 @@ def parse_variants(chrom: str, reference: bytes, variants, k: int = K, max_allel
             li = _left_identical(r, a)
             var.num_redundant = li if var.num_redundant is None else min(var.num_redundant, li)
             var.alts.append((len(r), a))
+            var.aco.append(origins[i])
             after = pos + len(r)
             cnv = max(copy_number_variant_length(r, chrom_up, after, k, copy_number_variant_threshold),
                       copy_number_variant_length(a, chrom_up, after, k, copy_number_variant_threshold))
@@ -449,7 +452,7 @@ def build_unit_graphs(chrom: str, reference: bytes, variants, k: int = K, max_al
     # group order: number of variants desc, then region string desc (VariantClusterGroupCompare, VariantClusterGroup.cpp:278-291)
     order = sorted(range(len(built)), key=lambda i: (-built[i][5], _neg_str(f"{chrom}:{built[i][3]}-{built[i][4]}")))
     out = {k_: [] for k_ in ("seq", "v_flags", "v_var", "v_allele", "v_nested", "v_refvar", "v_in_src", "var_pos", "var_dep", "var_nalt",
-                             "alt_reflen", "var_input_idx", "cluster_idx", "group_src", "group_edge_src", "group_edge_dst", "group_nvar",
+                             "alt_reflen", "alt_aco", "var_input_idx", "cluster_idx", "group_src", "group_edge_src", "group_edge_dst", "group_nvar",
                              "group_start", "group_end")}
     cl_vertex_off, v_seq_off, v_in_off, v_refvar_off, cl_var_off, var_alt_off, alt_seq_off = [0], [0], [0], [0], [0], [0], [0]
     group_cluster_off, group_src_off, group_edge_off = [0], [0], [0]
@@ -477,6 +480,7 @@ def build_unit_graphs(chrom: str, reference: bytes, variants, k: int = K, max_al
             for p, var in zip(sorted(cl.variants), cvars):
                 out["var_pos"].append(p + 1); out["var_dep"].append(int(var.has_dependency)); out["var_nalt"].append(len(var.alts))
                 out["var_input_idx"].append(var.input_idx)
+                out["alt_aco"].extend(var.aco)
                 for rl, a in var.alts:
                     out["alt_reflen"].append(rl); alt_seq += a; alt_seq_off.append(len(alt_seq))
                 var_alt_off.append(len(out["alt_reflen"]))
@@ -497,7 +501,7 @@ def build_unit_graphs(chrom: str, reference: bytes, variants, k: int = K, max_al
         "var_pos": np.array(out["var_pos"], np.uint32), "var_dep": np.array(out["var_dep"], np.uint8), "var_nalt": np.array(out["var_nalt"], np.uint16),
         "var_alt_off": np.array(var_alt_off, np.uint64), "alt_reflen": np.array(out["alt_reflen"], np.uint32),
         "alt_seq_off": np.array(alt_seq_off, np.uint64), "alt_seq": np.frombuffer(bytes(alt_seq), np.uint8),
-        "var_input_idx": np.array(out["var_input_idx"], np.int64),
+        "var_input_idx": np.array(out["var_input_idx"], np.int64), "alt_aco": list(out["alt_aco"]),
         "group_start": np.array(out["group_start"], np.uint32), "group_end": np.array(out["group_end"], np.uint32),
         "regions": np.array(regions, np.int64).reshape(-1, 2),
     }

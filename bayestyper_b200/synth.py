@@ -26,6 +26,8 @@ class Variant:
     pos: int          # 0-based position of REF[0]
     ref: bytes
     alts: list        # list[bytes]
+    id: str = None    # VCF ID (write_workdir writes v<index> when unset)
+    aco: list = None  # per alternative allele call-set origin (INFO ACO), optional
 
 
 @dataclasses.dataclass
@@ -315,7 +317,8 @@ def write_workdir(w: Workload, wd, spectra=None, seed: int = 4, n_errors: int = 
     with open(wd / "variants.vcf", "w") as f:
         f.write("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
         for i, v in enumerate(w.variants):
-            f.write(f"{w.chrom}\t{v.pos + 1}\tv{i}\t{v.ref.decode()}\t{','.join(a.decode() for a in v.alts)}\t.\t.\t.\n")
+            info = "ACO=" + ",".join(v.aco) if v.aco else "."
+            f.write(f"{w.chrom}\t{v.pos + 1}\t{v.id or f'v{i}'}\t{v.ref.decode()}\t{','.join(a.decode() for a in v.alts)}\t.\t.\t{info}\n")
     spectra = spectra if spectra is not None else sample_spectra(w, seed, n_errors)
     with open(wd / "samples.tsv", "w") as f:
         for s, (km, ct) in enumerate(spectra):

@@ -21,7 +21,9 @@ def describe(chrom: str, reference: bytes, variants, graphs: dict, sample_names,
              genotype_options_header: str = "", ids=None) -> dict:
     """BTD1 arrays "vcf.*" (see host/btvcf.cpp).  ids: per input variant (default v<index>, the ids synth.write_workdir writes)."""
     vorder = unit_variant_order(graphs)
-    ids = [f"v{i}" for i in range(len(variants))] if ids is None else list(ids)
+    if ids is None:                                                     # the candidates' own ids, else the ids synth.write_workdir writes
+        ids = [getattr(v, "id", None) or f"v{i}" for i, v in enumerate(variants)]
+    ids = list(ids)
     cvo = np.asarray(graphs["cl_var_off"], np.int64)
     pos = np.asarray(graphs["var_pos"], np.int64)                       # 1-based
     vao = np.asarray(graphs["var_alt_off"], np.int64)
@@ -57,7 +59,7 @@ def describe(chrom: str, reference: bytes, variants, graphs: dict, sample_names,
     a["vcf.vcr"], a["vcf.vcr_off"] = _strs(vcr)
     a["vcf.vcgr"], a["vcf.vcgr_off"] = _strs(vcgr)
     a["vcf.alt_seq"], a["vcf.alt_seq_off"] = _strs([alt_bytes[aso[i]:aso[i + 1]] for i in range(len(reflen))])
-    a["vcf.alt_aco"], a["vcf.alt_aco_off"] = _strs([""] * len(reflen))  # no ACO attribute in the candidate sets handled here
+    a["vcf.alt_aco"], a["vcf.alt_aco_off"] = _strs(graphs.get("alt_aco") or [""] * len(reflen))
     a["vcf.alt_ref_length"] = reflen.astype(np.uint32)
     a["vcf.alt_off"] = vao.astype(np.uint64)
     a["vcf.contig"] = np.zeros(n_var, np.uint32)

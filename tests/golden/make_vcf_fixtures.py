@@ -13,11 +13,21 @@ ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 from bayestyper_b200 import synth  # noqa: E402
 
+def _nested_with_origins():
+    """Deletions with variants inside; every third variant carries ids / ACO call-set origins of its own."""
+    w = synth.nested_sv(5, 14_000, 2, seed=83, n_background=40, sv_len=(150, 500))
+    for i, v in enumerate(w.variants):
+        if i % 3 == 0:
+            v.id = f"rs{1000 + i}"
+            v.aco = [("gatk:platypus", "manta", "gatk")[(i // 3 + a) % 3] for a in range(len(v.alts))]
+    return w
+
+
 VCF_WORKLOADS = {
     "vcf_mixed_3s": lambda: synth.small_mixed(160, 16_000, 3, seed=81),
     "vcf_chrx_2s": lambda: synth.small_mixed(90, 9_000, 2, seed=82, chrom="chrX"),
     # deletions with variants inside: groups of several clusters (VCGS > 1, VCGR != VCR) and '*' alleles on dependent variants
-    "vcf_nested_2s": lambda: synth.nested_sv(5, 14_000, 2, seed=83, n_background=40, sv_len=(150, 500)),
+    "vcf_nested_2s": _nested_with_origins,
 }
 
 

@@ -97,3 +97,29 @@ def test_adversarial_candidate_sets_identical_to_reference():
         assert sorted((int(x), int(y)) for x, y in b["regions"]) == sorted((int(x), int(y)) for x, y in d[f"c{c}.regions"])
         n_multi += int((np.diff(g["group_cluster_off"].astype(np.int64)) > 1).sum())
     assert n_multi >= 20          # the stored cases do exercise groups of several clusters
+
+
+def test_candidate_vcf_and_fasta_readers(tmp_path):
+    """The files `bayesTyper cluster` takes (VariantFileParser.cpp:67-167, Chromosomes.cpp:72-117) read back into the same candidate set:
+    ids, ACO origins, '.vcf.gz', and the graphs built from the files equal the graphs built from the in-memory workload."""
+    import gzip
+    from bayestyper_b200 import synth, vcfio
+    from tests.golden.make_vcf_fixtures import VCF_WORKLOADS
+    w = VCF_WORKLOADS["vcf_nested_2s"]()
+    km = synth.unique_kmers(synth.canonical_kmers(w.reference[:300]))[0]
+    wd = synth.write_workdir(w, tmp_path, spectra=[(km, np.ones(len(km), np.uint8))] * 2)
+    genome = vcfio.read_fasta(wd / "genome.fa")
+    assert list(genome) == [w.chrom] and genome[w.chrom] == w.reference
+    (tmp_path / "variants.vcf.gz").write_bytes(gzip.compress((wd / "variants.vcf").read_bytes()))
+    for name in ("variants.vcf", "variants.vcf.gz"):
+        cand = vcfio.read_candidates(tmp_path / name)
+        assert list(cand) == [w.chrom] and len(cand[w.chrom]) == len(w.variants)
+        for i, (c, v) in enumerate(zip(cand[w.chrom], w.variants)):
+            assert (c.pos, c.ref, c.alts, c.id, c.aco) == (v.pos, v.ref, v.alts, v.id or f"v{i}", v.aco)
+    a = graph_builder.build_unit_graphs(w.chrom, genome[w.chrom], cand[w.chrom])
+    b = graph_builder.build_unit_graphs(w.chrom, w.reference, w.variants)
+    for k in b:
+        assert (np.asarray(a[k]) == np.asarray(b[k])).all() if not isinstance(b[k], list) else a[k] == b[k], k
+    assert any(a["alt_aco"]) and (np.diff(a["group_cluster_off"].astype(np.int64)) > 1).any()
+    with pytest.raises(ValueError, match="vcf"):
+        vcfio.read_candidates(tmp_path / "genome.fa")
