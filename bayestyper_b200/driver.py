@@ -12,7 +12,7 @@ import dataclasses
 import numpy as np
 import torch
 
-from . import capi, engine, graph_builder, kmer_pipeline, unit as U
+from . import capi, engine, graph_builder, kmer_pipeline, ploidy as ploidy_rules, unit as U
 
 K = 55
 
@@ -38,6 +38,7 @@ class Options:
     disable_observed_kmers: bool = False
     bloom_fpr: float = 0.001          # bayesTyperTools makeBloom default (src/bayesTyperTools/main.cpp:127)
     max_parameter_kmers: int = 1_000_000
+    chromosome_ploidy_file: str = None   # --chromosome-ploidy-file (ChromosomePloidy.cpp:96-180); default: human X / Y rules by name
 
 
 def find_variant_cluster_paths(lib, graphs: dict, sample_blooms, opt: Options):
@@ -238,9 +239,7 @@ def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rate
                 blooms.append(b)
         region_buf = torch.from_numpy(_region_buffer(inp.reference, inp.regions)).to(dev)
         torch.cuda.synchronize()
-    chrom = inp.chrom.lower()
-    male_ploidy = 1 if chrom in ("x", "chrx", "y", "chry") else 2
-    female_ploidy = 0 if chrom in ("y", "chry") else 2
+    female_ploidy, male_ploidy = ploidy_rules.ChromosomePloidy([inp.chrom], inp.genders, opt.chromosome_ploidy_file).gender_ploidy(inp.chrom)
     n_paths, mem = find_variant_cluster_paths(lib, inp.graphs, blooms, opt)
     if own_blooms:
         for b in blooms:
