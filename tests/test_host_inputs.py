@@ -43,3 +43,41 @@ def test_ploidy_file(tmp_path):
     p.write_text("chr1 2 2\n")
     with pytest.raises(ValueError, match="three tab-separated"):
         ploidy.ChromosomePloidy(["chr1"], ["F"], p)
+
+
+def test_cluster_data_files_of_the_reference(tmp_path):
+    """`<out>_cluster_data/intercluster_regions.txt.gz` and `parameter_kmers.fa.gz` as the reference's cluster stage wrote them
+    (tests/golden/make_cluster_data_fixture.py, oracle-R) read back; the regions equal graph_builder's; every parameter k-mer is a
+    canonical k-mer of an intercluster region; writing reproduces the files' content."""
+    import gzip
+    import shutil
+
+    import numpy as np
+
+    from bayestyper_b200 import cluster_data, graph_builder, synth
+    from tests._fixtures import GOLD
+    from tests.golden.make_fixtures import PIPE_WORKLOADS
+    w = PIPE_WORKLOADS["pipe_mixed_3s"]()
+    for name in ("intercluster_regions.txt.gz", "parameter_kmers.fa.gz"):
+        shutil.copy(GOLD / f"cluster_data_mixed_3s.{name}", tmp_path / name)
+    regions = cluster_data.read_intercluster_regions(tmp_path / "intercluster_regions")
+    mine = graph_builder.intercluster_regions(w.chrom, w.reference, w.variants)
+    assert sorted((a, b) for _, _, a, b in regions) == sorted(mine)
+    assert all(c == w.chrom and d is False for c, d, _, _ in regions)
+    lengths = [b - a for _, _, a, b in regions]
+    assert lengths == sorted(lengths, reverse=True)
+    cluster_data.write_intercluster_regions(tmp_path / "again", [(w.chrom, False, a, b) for a, b in mine])
+    again = cluster_data.read_intercluster_regions(tmp_path / "again")
+    assert [b - a for _, _, a, b in again] == lengths and sorted(again) == sorted(regions)
+
+    km = cluster_data.read_parameter_kmers(tmp_path / "parameter_kmers")
+    assert km.shape == (400, 2)
+    pool = np.concatenate([synth.canonical_kmers(w.reference[a:b + 1]) for a, b in mine])
+    as_void = lambda x: np.ascontiguousarray(x).view([("a", np.uint64), ("b", np.uint64)]).ravel()
+    assert np.isin(as_void(km), as_void(pool)).all()
+    cluster_data.write_parameter_kmers(tmp_path / "pk_again", km)
+    assert gzip.open(tmp_path / "pk_again.fa.gz").read() == gzip.open(tmp_path / "parameter_kmers.fa.gz").read()
+    assert cluster_data.write_parameter_kmers(tmp_path / "capped", km, max_kmers=10) == 10
+    assert len(cluster_data.read_parameter_kmers(tmp_path / "capped")) == 10
+    with pytest.raises(ValueError, match="ACGT"):
+        cluster_data.strings_to_kmers(np.frombuffer(b"N" * 55, np.uint8))
