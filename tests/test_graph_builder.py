@@ -123,3 +123,14 @@ def test_candidate_vcf_and_fasta_readers(tmp_path):
     assert any(a["alt_aco"]) and (np.diff(a["group_cluster_off"].astype(np.int64)) > 1).any()
     with pytest.raises(ValueError, match="vcf"):
         vcfio.read_candidates(tmp_path / "genome.fa")
+
+
+def test_unit_order_of_the_end_to_end_fixtures():
+    """The variants of the unit, in unit order, as the reference's run listed them (e2e fixtures, staged nested case included):
+    what the GPU end-to-end test asserts first, checked here without a GPU."""
+    from tests.golden.make_fixtures import E2E_NEXT_WORKLOADS, E2E_WORKLOADS
+    for name, mk in {**E2E_WORKLOADS, **E2E_NEXT_WORKLOADS}.items():
+        d = btd.read(GOLD / f"{name}.btd")
+        w = mk()
+        g = graph_builder.build_unit_graphs(w.chrom, w.reference, w.variants)
+        assert (g["var_pos"] == d["ref.var_pos"]).all(), name
