@@ -9,8 +9,7 @@ the reference; tests/test_graph_builder.py checks it array by array against what
 deletions included).  Orders that the reference takes from `std::unordered_map` / `unordered_set` iteration are reproduced with
 `stdhash_order.UnorderedUInt`.
 
-Not restated: the split of a candidate set into several inference units (`min_unit_variants`, one unit here), decoy contigs and
-contigs absent from the genome (one contig per call), and the ACO attribute.
+Not restated: the split of a candidate set into several inference units (`min_unit_variants`: one unit here).
 """
 from __future__ import annotations
 
@@ -428,13 +427,8 @@ def build_cluster_graph(chrom_codes: np.ndarray, variants, contained=(), k: int 
     return g
 
 
-def build_unit_graphs(chrom: str, reference: bytes, variants, k: int = K, max_allele_length: int = 500000,
-                      copy_number_variant_threshold: float = 0.5) -> dict:
-    """Variant-cluster groups sorted like main.cpp:247, as the CSR arrays of graphs.btd / btg_graphs_desc.
-
-    variants: objects with .pos (0-based), .ref (bytes), .alts (list of bytes), sorted by position.  On top of the arrays the
-    reference's graphs hold, `var_input_idx` maps every variant of the unit back to the caller's list, and `group_start` /
-    `group_end` carry the 1-based region of every group (VariantClusterGroup::region)."""
+def _build_contig(chrom, reference, variants, k, max_allele_length, copy_number_variant_threshold):
+    """The groups of one contig, unsorted: (contig, nucleotide codes, clusters, sources, out_edges, start, end, variants)."""
     codes = _CODE[np.frombuffer(reference, np.uint8)]
     groups, regions = parse_variants(chrom, reference, variants, k, max_allele_length, copy_number_variant_threshold)
     built = []
@@ -448,9 +442,63 @@ def build_unit_graphs(chrom: str, reference: bytes, variants, k: int = K, max_al
             out_edges[slot[container]].append(slot[inner])
         start = min(cl.left for cl in clusters) + 1
         end = max(cl.right for cl in clusters) + 1
-        built.append((clusters, sources, out_edges, start, end, sum(len(cl.variants) for cl in clusters)))
-    # group order: number of variants desc, then region string desc (VariantClusterGroupCompare, VariantClusterGroup.cpp:278-291)
-    order = sorted(range(len(built)), key=lambda i: (-built[i][5], _neg_str(f"{chrom}:{built[i][3]}-{built[i][4]}")))
+        built.append((chrom, codes, clusters, sources, out_edges, start, end, sum(len(cl.variants) for cl in clusters)))
+    return built, regions
+
+
+def build_unit_graphs(chrom: str, reference: bytes, variants, k: int = K, max_allele_length: int = 500000,
+                      copy_number_variant_threshold: float = 0.5) -> dict:
+    """Variant-cluster groups of one contig sorted like main.cpp:247, as the CSR arrays of graphs.btd / btg_graphs_desc.
+
+    variants: objects with .pos (0-based), .ref (bytes), .alts (list of bytes), sorted by position.  On top of the arrays the
+    reference's graphs hold, `var_input_idx` maps every variant of the unit back to the caller's list, and `group_start` /
+    `group_end` carry the 1-based region of every group (VariantClusterGroup::region)."""
+    built, regions = _build_contig(chrom, reference, variants, k, max_allele_length, copy_number_variant_threshold)
+    out = _emit(built, k)
+    del out["_order"]
+    out["regions"] = np.array(regions, np.int64).reshape(-1, 2)
+    return out
+
+
+def build_genome_graphs(genome: dict, candidates: dict, decoys=(), k: int = K, max_allele_length: int = 500000,
+                        copy_number_variant_threshold: float = 0.5) -> dict:
+    """The unit of a whole genome: genome = contig -> sequence (FASTA order, decoy contigs included), candidates = contig ->
+    position-sorted variants (VCF order), decoys = names of the decoy contigs.
+
+    Like the reference, variants on decoy contigs are dropped (VariantFileParser.cpp:332-341) and a variant on a contig that
+    the genome does not hold is an error (the reference asserts in Chromosomes::isDecoy, Chromosomes.cpp:145); every contig contributes its intercluster regions — a contig without usable variants as one
+    region, decoy contigs flagged (:273-280,512-536) — and the groups of all contigs are sorted together (main.cpp:247).
+    On top of build_unit_graphs' arrays: `contig_names`, `group_contig` / `var_contig` (index into contig_names; `var_input_idx` is the
+    index into that contig's candidate list) and `regions` as (contig index, is_decoy, start, end) rows."""
+    names = list(genome)
+    index = {n: i for i, n in enumerate(names)}
+    decoys = set(decoys)
+    built, regions, visited = [], [], set()
+    for chrom, variants in candidates.items():
+        if chrom not in genome:
+            raise ValueError(f'variants on contig "{chrom}", which the genome does not hold')
+        if chrom in decoys:
+            continue
+        visited.add(chrom)
+        b, r = _build_contig(chrom, genome[chrom], variants, k, max_allele_length, copy_number_variant_threshold)
+        built.extend(b)
+        regions.extend((index[chrom], 0, x, y) for x, y in r)
+    for chrom in names:
+        if chrom not in visited and len(genome[chrom]) >= k:
+            regions.append((index[chrom], int(chrom in decoys), 0, len(genome[chrom]) - 1))
+    out = _emit(built, k)
+    group_contig = np.array([index[built[i][0]] for i in out.pop("_order")], np.uint32)
+    out["contig_names"] = names
+    out["group_contig"] = group_contig
+    out["var_contig"] = np.repeat(group_contig, np.diff(out["cl_var_off"][out["group_cluster_off"].astype(np.int64)].astype(np.int64)))
+    out["regions"] = np.array(regions, np.int64).reshape(-1, 4)
+    return out
+
+
+def _emit(built, k):
+    """Groups in the unit's order (number of variants desc, then region string desc: VariantClusterGroupCompare,
+    VariantClusterGroup.cpp:278-291) as CSR arrays."""
+    order = sorted(range(len(built)), key=lambda i: (-built[i][7], _neg_str(f"{built[i][0]}:{built[i][5]}-{built[i][6]}")))
     out = {k_: [] for k_ in ("seq", "v_flags", "v_var", "v_allele", "v_nested", "v_refvar", "v_in_src", "var_pos", "var_dep", "var_nalt",
                              "alt_reflen", "alt_aco", "var_input_idx", "cluster_idx", "group_src", "group_edge_src", "group_edge_dst", "group_nvar",
                              "group_start", "group_end")}
@@ -458,7 +506,7 @@ def build_unit_graphs(chrom: str, reference: bytes, variants, k: int = K, max_al
     group_cluster_off, group_src_off, group_edge_off = [0], [0], [0]
     alt_seq = bytearray()
     for gi in order:
-        clusters, sources, out_edges, start, end, nvar = built[gi]
+        _chrom, codes, clusters, sources, out_edges, start, end, nvar = built[gi]
         out["group_nvar"].append(nvar); out["group_start"].append(start); out["group_end"].append(end)
         out["group_src"].extend(sources); group_src_off.append(len(out["group_src"]))
         for u, targets in enumerate(out_edges):
@@ -503,7 +551,7 @@ def build_unit_graphs(chrom: str, reference: bytes, variants, k: int = K, max_al
         "alt_seq_off": np.array(alt_seq_off, np.uint64), "alt_seq": np.frombuffer(bytes(alt_seq), np.uint8),
         "var_input_idx": np.array(out["var_input_idx"], np.int64), "alt_aco": list(out["alt_aco"]),
         "group_start": np.array(out["group_start"], np.uint32), "group_end": np.array(out["group_end"], np.uint32),
-        "regions": np.array(regions, np.int64).reshape(-1, 2),
+        "_order": order,
     }
 
 

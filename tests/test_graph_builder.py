@@ -134,3 +134,31 @@ def test_unit_order_of_the_end_to_end_fixtures():
         w = mk()
         g = graph_builder.build_unit_graphs(w.chrom, w.reference, w.variants)
         assert (g["var_pos"] == d["ref.var_pos"]).all(), name
+
+
+def test_genome_of_several_contigs_identical_to_reference():
+    """build_genome_graphs on a genome with several contigs, a contig without variants, decoy contigs (one with variants, which are
+    dropped) against the unit the REFERENCE built (tools/fuzz_genome_builder.py --write-golden, oracle-R with --decoy-file): groups
+    of all contigs sorted together, contig per group, intercluster regions with the decoy flag."""
+    from bayestyper_b200 import synth
+    d = btd.read(GOLD / "graphs_genome.btd")
+    names = bytes(d["meta.contigs"]).decode().split("\n")
+    n_decoys = int(d["meta.n_decoys"][0])
+    genome = {n: bytes(d[f"seq.{n}"]) for n in names}
+    cand = {}
+    for n in bytes(d["meta.cand_contigs"]).decode().split("\n"):
+        alleles = bytes(d[f"cand.{n}.alleles"]).split(b"\n")
+        cand[n] = [synth.Variant(int(p), al.split(b",")[0], al.split(b",")[1:]) for p, al in zip(d[f"cand.{n}.pos"].tolist(), alleles)]
+    b = graph_builder.build_genome_graphs(genome, cand, decoys=names[-n_decoys:])
+    for k, v in d.items():
+        if k.startswith("g.") and k[2:] not in ("v_refvar", "chroms", "chrom_off"):
+            assert len(b[k[2:]]) == len(v) and (np.asarray(b[k[2:]]) == v).all(), k
+    chroms = bytes(d["g.chroms"])
+    ref_names = [chroms[int(a):int(c)].decode() for a, c in zip(d["g.chrom_off"][:-1], d["g.chrom_off"][1:])]
+    assert ref_names == [b["contig_names"][i] for i in b["group_contig"]] and len(set(ref_names)) >= 2
+    want = sorted(tuple(ln.split("\t")) for ln in bytes(d["regions"]).decode().split("\n"))
+    got = sorted((b["contig_names"][c], str(int(f)), str(int(x)), str(int(y))) for c, f, x, y in b["regions"])
+    assert got == want and any(r[1] == "1" for r in want)
+    assert len(b["var_contig"]) == len(b["var_pos"])
+    with pytest.raises(ValueError, match="does not hold"):
+        graph_builder.build_genome_graphs(genome, {"chrGone": [synth.Variant(80, b"A", [b"C"])]})
