@@ -39,13 +39,18 @@ def _arrays_from_vcf(text: str, reference: bytes, trim: bool):
     S = len(samples)
     opt = [l + "\n" for l in head if l.startswith("##BayesTyperOptions")]
     genome = [l for l in head if l.startswith("##reference=file:")][0][len("##reference=file:"):]
-    contig = [l for l in head if l.startswith("##contig")][0]
-    cname = contig.split("ID=")[1].split(",")[0]
+    cnames = [l.split("ID=")[1].split(",")[0] for l in head if l.startswith("##contig")]
+    if isinstance(reference, dict):             # several contigs: name -> sequence, the ones missing from the header are decoys
+        cnames += [n for n in reference if n not in cnames]
+        seqs = [reference[n] for n in cnames]
+    else:
+        seqs = [reference]
+    n_header = sum(l.startswith("##contig") for l in head)
     a = {"meta.n_samples": np.array([S], np.uint32)}
     a["vcf.sample_names"], a["vcf.sample_names_off"] = _strs(samples)
-    a["vcf.contig_names"], a["vcf.contig_names_off"] = _strs([cname])
-    a["vcf.contig_seq"], a["vcf.contig_seq_off"] = _strs([reference])
-    a["vcf.contig_decoy"] = np.zeros(1, np.uint8)
+    a["vcf.contig_names"], a["vcf.contig_names_off"] = _strs(cnames)
+    a["vcf.contig_seq"], a["vcf.contig_seq_off"] = _strs(seqs)
+    a["vcf.contig_decoy"] = np.array([0] * n_header + [1] * (len(cnames) - n_header), np.uint8)
     a["vcf.genome_filename"] = np.frombuffer(genome.encode(), np.uint8).copy()
     a["vcf.graph_options_header"] = np.frombuffer(opt[0].encode(), np.uint8).copy()
     a["vcf.genotype_options_header"] = np.frombuffer(opt[1].encode(), np.uint8).copy()
@@ -94,7 +99,7 @@ def _arrays_from_vcf(text: str, reference: bytes, trim: bool):
     a["vcf.alt_seq"], a["vcf.alt_seq_off"] = _strs(alt_seq)
     a["vcf.alt_aco"], a["vcf.alt_aco_off"] = _strs(alt_aco)
     a["vcf.alt_ref_length"] = np.array(alt_len, np.uint32); a["vcf.alt_off"] = np.array(alt_off, np.uint64)
-    a["vcf.contig"] = np.zeros(len(body), np.uint32); a["vcf.position"] = np.array(pos, np.uint32); a["vcf.has_dependency"] = np.array(dep, np.uint8)
+    a["vcf.contig"] = np.array([cnames.index(t[0]) for t in body], np.uint32); a["vcf.position"] = np.array(pos, np.uint32); a["vcf.has_dependency"] = np.array(dep, np.uint8)
     a["vcf.vcs"] = np.array(vcs, np.uint32); a["vcf.vcgs"] = np.array(vcgs, np.uint32)
     for k, v, dt in (("gt", gt, np.uint16), ("gq", gq, np.uint32), ("gpp", gpp, np.float32), ("app", app, np.float32), ("nak", nak, np.float32), ("fak", fak, np.float32),
                      ("mac", mac, np.float32), ("saf", saf, np.uint16), ("ploidy", ploidy, np.uint8), ("an", an, np.uint32), ("ac", ac, np.uint32), ("af", af, np.float32),
@@ -129,6 +134,74 @@ def test_writer_reproduces_the_reference_vcf(tmp_path, name, trim):
             assert not b.startswith("#") and _qual_tolerant_equal(a, b), f"\n got: {a[:300]}\nwant: {b[:300]}"
             n_qual += 1
     assert n_qual <= len(wl) // 20, "too many QUAL last-digit differences"
+
+
+def _genome_fixture():
+    from tests.golden.make_vcf_genome_fixture import genome_workload
+    parts, empty, decoys = genome_workload()
+    genome = {n: w.reference for n, w in parts.items()}
+    genome[empty[0]] = empty[1]
+    return parts, genome, decoys
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_writer_reproduces_the_reference_vcf_of_a_genome(tmp_path, shuffle):
+    """Several contigs (FASTA order chr2, chr1, chrX, a contig without variants) and a decoy: `##contig` lines, record order and
+    per-contig ploidy as the reference wrote them (tests/golden/make_vcf_genome_fixture.py).  shuffle=True hands the variants over in
+    a scrambled order: the writer, like GenotypeWriter::finalise, sorts them itself."""
+    exe = _build_btvcf()
+    want = gzip.open(GOLD / "vcf_genome_2s.vcf.gz", "rt").read()
+    _, genome, decoys = _genome_fixture()
+    if shuffle:
+        lines = want.splitlines()
+        body = [l for l in lines if not l.startswith("#")]
+        np.random.default_rng(3).shuffle(body)
+        text = "\n".join([l for l in lines if l.startswith("#")] + body) + "\n"
+    else:
+        text = want
+    btd.write(tmp_path / "in.btd", _arrays_from_vcf(text, {**genome, **decoys}, True))
+    r = subprocess.run([str(exe), str(tmp_path / "in.btd"), str(tmp_path / "out.vcf")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    gl, wl = (tmp_path / "out.vcf").read_text().splitlines(), want.splitlines()
+    assert len(gl) == len(wl)
+    for a, b in zip(gl, wl):
+        assert a == b or (not b.startswith("#") and _qual_tolerant_equal(a, b)), f"\n got: {a[:300]}\nwant: {b[:300]}"
+
+
+def test_description_of_a_genome_from_graph_builder_reproduces_the_reference_vcf(tmp_path):
+    """build_genome_graphs -> vcf_desc.describe_genome (contig per variant, ids, VCR / VCGR with the contig's name, decoy flag) + the
+    reference's numbers moved into unit order -> btvcf == the reference's file."""
+    from bayestyper_b200 import graph_builder, vcf_desc
+    _build_btvcf()
+    want = gzip.open(GOLD / "vcf_genome_2s.vcf.gz", "rt").read()
+    parts, genome, decoys = _genome_fixture()
+    full = {**genome, **decoys}
+    cand = {n: w.variants for n, w in parts.items()}
+    graphs = graph_builder.build_genome_graphs(full, cand, decoys=list(decoys))
+    head = [l for l in want.splitlines() if l.startswith("#")]
+    opt = [l + "\n" for l in head if l.startswith("##BayesTyperOptions")]
+    genome_file = [l for l in head if l.startswith("##reference=file:")][0][len("##reference=file:"):]
+    S = len(head[-1].split("\t")) - 9
+    desc = vcf_desc.describe_genome(full, cand, graphs, head[-1].split("\t")[9:], list(decoys), genome_file, opt[0], opt[1])
+    by_file = _arrays_from_vcf(want, full, False)
+    file_ids = [bytes(by_file["vcf.ids"][int(a):int(b)]).decode() for a, b in zip(by_file["vcf.ids_off"][:-1], by_file["vcf.ids_off"][1:])]
+    unit_ids = [bytes(desc["vcf.ids"][int(a):int(b)]).decode() for a, b in zip(desc["vcf.ids_off"][:-1], desc["vcf.ids_off"][1:])]
+    assert sorted(file_ids) == sorted(unit_ids)
+    where = {v: i for i, v in enumerate(file_ids)}
+    perm = np.array([where[v] for v in unit_ids])
+    nA = (1 + np.diff(by_file["vcf.alt_off"].astype(np.int64)) + by_file["vcf.has_dependency"]).astype(np.int64)
+    def take(arr, width):
+        off = np.concatenate([[0], np.cumsum(width)])
+        return np.concatenate([arr[off[v]:off[v + 1]] for v in perm])
+    out = {}
+    for k, wdt in (("gt", np.full(len(nA), 2 * S)), ("gq", np.full(len(nA), S)), ("ploidy", np.full(len(nA), S)), ("an", np.ones(len(nA), int)), ("hc", np.ones(len(nA), int)),
+                   ("gpp", S * nA * (nA + 1) // 2), ("app", S * nA), ("nak", S * nA), ("fak", S * nA), ("mac", S * nA), ("saf", S * nA), ("ac", nA), ("af", nA), ("acp", nA), ("anc", nA)):
+        out[k] = take(by_file[k], np.asarray(wdt, np.int64))
+    vcf_desc.write_vcf(tmp_path / "out.vcf", out, desc, S)
+    gl, wl = (tmp_path / "out.vcf").read_text().splitlines(), want.splitlines()
+    assert len(gl) == len(wl)
+    for a, b in zip(gl, wl):
+        assert a == b or (not b.startswith("#") and _qual_tolerant_equal(a, b)), f"\n got: {a[:300]}\nwant: {b[:300]}"
 
 
 def test_sample_without_genotype_and_filters(tmp_path):
