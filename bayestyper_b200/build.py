@@ -73,7 +73,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
 
 def build_host(force: bool = False) -> Path:
     """g++ build of the C++ host programs over the C ABI: host/btgenotype (Gibbs stage order, links libbtgpu.so) and host/btvcf
-    (GenotypeWriter, host-only), host/btkmc (KMC database listing, makeBloom)."""
+    (GenotypeWriter, host-only), host/btkmc (KMC database listing, makeBloom), host/btcluster (cluster / group / graph construction, host-only)."""
     hdrs = [ROOT / "include" / "btgpu.hpp", ROOT / "include" / "btgpu.h", ROOT / "include" / "btgpu_vcf.hpp", ROOT / "include" / "btgpu_params.hpp", ROOT / "host" / "btd.hpp", ROOT / "host" / "vcf_desc.hpp"]
     inc = ["-I", str(ROOT / "include"), "-I", str(ROOT / "host")]
     exe = ROOT / "host" / "btgenotype"
@@ -87,6 +87,9 @@ def build_host(force: bool = False) -> Path:
     vcf = ROOT / "host" / "btvcf"
     if force or not _newer(vcf, [ROOT / "host" / "btvcf.cpp", *hdrs]):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", *inc, str(ROOT / "host" / "btvcf.cpp"), "-o", str(vcf)])
+    clu = ROOT / "host" / "btcluster"
+    if force or not _newer(clu, [ROOT / "host" / "btcluster.cpp", ROOT / "include" / "btgpu_cluster.hpp", *hdrs]):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", *inc, str(ROOT / "host" / "btcluster.cpp"), "-lz", "-o", str(clu)])
     return exe
 
 

@@ -214,6 +214,7 @@ def parse_variants(chrom: str, reference: bytes, variants, k: int = K, max_allel
     (start, end) intercluster stretches of at least k nucleotides."""
     chrom_up = reference.upper()
     n = len(reference)
+    copy_number_variant_threshold = float(np.float32(copy_number_variant_threshold))      # the option is a float in the reference
     groups, regions = [], []
     group, merge_sets, flanks = UnorderedUInt(), [], {}
     dependencies = set()

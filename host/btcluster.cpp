@@ -1,0 +1,149 @@
+// btcluster — the host-side front end of `bayesTyper cluster`: genome FASTA (+ decoy FASTA) and candidate VCF in, the unit's variant
+// clusters, groups and graphs out as a BTD1 file with the keys of bayestyper_b200/graph_builder.build_genome_graphs
+// (include/btgpu_cluster.hpp does the work; file reading follows Chromosomes::parseFasta, Chromosomes.cpp:72-117, and
+// VariantFileParser's line reader, VariantFileParser.cpp:67-167: CHROM POS ID REF ALT and INFO ACO, `.vcf` or `.vcf.gz`).
+//
+//   btcluster <genome.fa> <candidates.vcf[.gz]> <out.btd> [--decoy <decoy.fa>] [--max-allele-length N] [--copy-number-variant-threshold X]
+#include <zlib.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+
+#include "btd.hpp"
+#include "btgpu_cluster.hpp"
+
+using btg::cluster::Candidate;
+
+static bool readLine(gzFile f, std::string &line) {
+    line.clear();
+    char buf[1 << 16];
+    while (gzgets(f, buf, sizeof buf)) {
+        line += buf;
+        if (!line.empty() && line.back() == '\n') { line.pop_back(); if (!line.empty() && line.back() == '\r') line.pop_back(); return true; }
+    }
+    return !line.empty();
+}
+
+static void readFasta(const std::string &path, bool decoy, std::vector<std::string> &names, std::vector<std::string> &seqs, std::vector<uint8_t> &flags) {
+    gzFile f = gzopen(path.c_str(), "rb");
+    if (!f) throw btg::Error("cannot open " + path);
+    std::string line;
+    bool any = false;
+    while (readLine(f, line)) {
+        if (!line.empty() && line[0] == '>') {
+            const size_t e = line.find_first_of("\t ");
+            std::string name = line.substr(1, e == std::string::npos ? std::string::npos : e - 1);
+            if (name.empty()) throw btg::Error(path + ": empty contig name");
+            for (auto &n : names) if (n == name) throw btg::Error(path + ": contig " + name + " appears twice");
+            names.push_back(name); seqs.emplace_back(); flags.push_back(decoy);
+            any = true;
+        } else {
+            if (!any) throw btg::Error(path + " does not start with a '>' line");
+            seqs.back() += line;
+        }
+    }
+    gzclose(f);
+}
+
+static std::vector<std::string> split(const std::string &s, char sep) {
+    std::vector<std::string> out;
+    size_t a = 0;
+    while (true) {
+        const size_t b = s.find(sep, a);
+        out.push_back(s.substr(a, b == std::string::npos ? std::string::npos : b - a));
+        if (b == std::string::npos) break;
+        a = b + 1;
+    }
+    return out;
+}
+
+static std::vector<std::pair<std::string, std::vector<Candidate>>> readCandidates(const std::string &path) {
+    const bool gz = path.size() > 7 && path.compare(path.size() - 7, 7, ".vcf.gz") == 0;
+    if (!gz && !(path.size() > 4 && path.compare(path.size() - 4, 4, ".vcf") == 0)) throw btg::Error("variant file needs to end in .vcf or .vcf.gz");
+    gzFile f = gzopen(path.c_str(), "rb");
+    if (!f) throw btg::Error("cannot open " + path);
+    std::vector<std::pair<std::string, std::vector<Candidate>>> out;
+    std::string line;
+    bool header = false;
+    while (readLine(f, line)) {
+        if (line.empty()) continue;
+        if (line[0] == '#') {
+            if (line.compare(0, 6, "#CHROM") == 0) {
+                if (std::count(line.begin(), line.end(), '\t') + 1 < 8) throw btg::Error("variant file header has fewer than 8 columns");
+                header = true;
+            }
+            continue;
+        }
+        if (!header) throw btg::Error("variant file has no #CHROM header line");
+        auto t = split(line, '\t');
+        if (t.size() < 8) throw btg::Error("variant line with fewer than 8 columns");
+        if (t[3].find(',') != std::string::npos) throw btg::Error("REF holds several alleles");
+        Candidate c;
+        c.pos = (uint32_t)std::stoul(t[1]) - 1; c.id = t[2]; c.ref = t[3]; c.alts = split(t[4], ',');
+        for (auto &kv : split(t[7], ';'))
+            if (kv.compare(0, 4, "ACO=") == 0) {
+                c.aco = split(kv.substr(4), ',');
+                if (c.aco.size() != c.alts.size()) throw btg::Error("ACO lists a different number of origins than there are alternative alleles at " + t[0] + ":" + t[1]);
+                break;
+            }
+        if (out.empty() || out.back().first != t[0]) {
+            for (auto &cv : out) if (cv.first == t[0]) throw btg::Error("variants need to be sorted by contig; variants on contig \"" + t[0] + "\" are unordered");
+            out.emplace_back(t[0], std::vector<Candidate>());
+        }
+        out.back().second.push_back(std::move(c));
+    }
+    gzclose(f);
+    return out;
+}
+
+int main(int argc, char **argv) {
+    try {
+        if (argc < 4) { std::fprintf(stderr, "usage: btcluster <genome.fa> <candidates.vcf[.gz]> <out.btd> [--decoy <decoy.fa>] [--max-allele-length N] [--copy-number-variant-threshold X]\n"); return 2; }
+        btg::cluster::Options opt;
+        std::string decoy;
+        for (int i = 4; i + 1 < argc; i += 2) {
+            if (!std::strcmp(argv[i], "--decoy")) decoy = argv[i + 1];
+            else if (!std::strcmp(argv[i], "--max-allele-length")) opt.max_allele_length = (uint32_t)std::stoul(argv[i + 1]);
+            else if (!std::strcmp(argv[i], "--copy-number-variant-threshold")) opt.copy_number_variant_threshold = (float)std::stod(argv[i + 1]);
+            else throw btg::Error(std::string("unknown option ") + argv[i]);
+        }
+        std::vector<std::string> names, seqs;
+        std::vector<uint8_t> flags;
+        readFasta(argv[1], false, names, seqs, flags);
+        if (!decoy.empty()) readFasta(decoy, true, names, seqs, flags);
+        auto cand = readCandidates(argv[2]);
+        const auto t0 = std::chrono::steady_clock::now();
+        auto g = btg::cluster::buildGenomeGraphs(names, seqs, flags, cand, opt);
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        btd::BtdWriter w(argv[3]);
+        std::string joined;
+        for (size_t i = 0; i < names.size(); i++) { if (i) joined += '\n'; joined += names[i]; }
+        w.put("contig_names", 0, (const uint8_t *)joined.data(), {(uint64_t)joined.size()});
+        w.put("group_cluster_off", 3, g.group_cluster_off); w.put("group_nvar", 2, g.group_nvar);
+        w.put("group_src_off", 3, g.group_src_off); w.put("group_src", 2, g.group_src);
+        w.put("group_edge_off", 3, g.group_edge_off); w.put("group_edge_src", 2, g.group_edge_src); w.put("group_edge_dst", 2, g.group_edge_dst);
+        w.put("group_start", 2, g.group_start); w.put("group_end", 2, g.group_end); w.put("group_contig", 2, g.group_contig);
+        w.put("cluster_idx", 2, g.cluster_idx);
+        w.put("cl_vertex_off", 3, g.cl_vertex_off); w.put("cl_var_off", 3, g.cl_var_off);
+        w.put("v_seq_off", 3, g.v_seq_off); w.put("seq", 0, g.seq); w.put("v_flags", 0, g.v_flags); w.put("v_var", 1, g.v_var); w.put("v_allele", 1, g.v_allele);
+        w.put("v_nested", 2, g.v_nested); w.put("v_refvar_off", 3, g.v_refvar_off); w.put("v_refvar", 1, g.v_refvar);
+        w.put("v_in_off", 3, g.v_in_off); w.put("v_in_src", 2, g.v_in_src);
+        w.put("var_pos", 2, g.var_pos); w.put("var_dep", 0, g.var_dep); w.put("var_nalt", 1, g.var_nalt); w.put("var_contig", 2, g.var_contig);
+        w.put("var_input_idx", 7, g.var_input_idx); w.put("var_alt_off", 3, g.var_alt_off); w.put("alt_reflen", 2, g.alt_reflen);
+        w.put("alt_seq_off", 3, g.alt_seq_off); w.put("alt_seq", 0, (const uint8_t *)g.alt_seq.data(), {(uint64_t)g.alt_seq.size()});
+        w.put("alt_aco_off", 3, g.alt_aco_off); w.put("alt_aco", 0, (const uint8_t *)g.alt_aco.data(), {(uint64_t)g.alt_aco.size()});
+        w.put("var_id_off", 3, g.var_id_off); w.put("var_ids", 0, (const uint8_t *)g.var_ids.data(), {(uint64_t)g.var_ids.size()});
+        std::vector<int64_t> regions;
+        for (auto &r : g.regions) { regions.push_back(r.contig); regions.push_back(r.decoy); regions.push_back(r.start); regions.push_back(r.end); }
+        w.put("regions", 7, regions.data(), {(uint64_t)g.regions.size(), 4});
+        std::fprintf(stderr, "btcluster: %zu variants as %zu clusters in %zu groups, %zu intercluster regions (%.3f s)\n", g.var_pos.size(), g.cluster_idx.size(),
+                     g.group_nvar.size(), g.regions.size(), dt);
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "btcluster: %s\n", e.what());
+        return 1;
+    }
+}
