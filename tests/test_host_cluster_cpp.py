@@ -117,3 +117,21 @@ def test_origins_ids_and_errors(tmp_path):
     assert r.returncode == 1 and "does not hold" in r.stderr
     r = subprocess.run([str(_exe()), str(tmp_path / "genome.fa"), str(tmp_path / "genome.fa"), str(tmp_path / "o.btd")], capture_output=True, text=True)
     assert r.returncode == 1 and ".vcf" in r.stderr
+
+
+def test_native_builder_behind_the_python_interface():
+    from tests.golden.make_vcf_genome_fixture import genome_workload
+    parts, empty, decoys = genome_workload()
+    genome = {n: w.reference for n, w in parts.items()}
+    genome[empty[0]] = empty[1]
+    full = {**genome, **decoys}
+    cand = {n: w.variants for n, w in parts.items()}
+    a = graph_builder.build_genome_graphs(full, cand, decoys=list(decoys))
+    b = graph_builder.build_genome_graphs_native(full, cand, decoys=list(decoys))
+    for k, v in a.items():
+        if isinstance(v, list):
+            assert b[k] == v, k
+        else:
+            assert np.asarray(b[k]).dtype == np.asarray(v).dtype and (np.asarray(b[k]) == np.asarray(v)).all(), k
+    with pytest.raises(ValueError, match="sorted by position"):
+        graph_builder.build_genome_graphs_native({"c": b"A" * 300}, {"c": [synth.Variant(100, b"A", [b"C"]), synth.Variant(90, b"A", [b"C"])]})
