@@ -210,12 +210,13 @@ def parse_variants(chrom: str, reference: bytes, variants, k: int = K, max_allel
 
     variants: objects with .pos (0-based), .ref (bytes), .alts (list of bytes), optionally .id and .aco (per alternative allele
     call-set origin), sorted by position.
-    Returns (groups, regions): every group an UnorderedUInt cluster index -> _Cluster, in file order; regions the inclusive
-    (start, end) intercluster stretches of at least k nucleotides."""
+    Returns (groups, regions, breaks): every group an UnorderedUInt cluster index -> _Cluster, in file order; regions the inclusive
+    (start, end) intercluster stretches of at least k nucleotides; breaks[i] says whether an inference unit may end in front of
+    variant i (it lies at least k past the end of the running group, :286)."""
     chrom_up = reference.upper()
     n = len(reference)
     copy_number_variant_threshold = float(np.float32(copy_number_variant_threshold))      # the option is a float in the reference
-    groups, regions = [], []
+    groups, regions, breaks = [], [], []
     group, merge_sets, flanks = UnorderedUInt(), [], {}
     dependencies = set()
     prev_pos, prev_var_end, group_end = None, -1, -1
@@ -237,6 +238,7 @@ def parse_variants(chrom: str, reference: bytes, variants, k: int = K, max_allel
         if prev_pos is not None and pos < prev_pos:
             raise ValueError(f"variants need to be sorted by position: {prev_pos + 1} is before {pos + 1}")
         dependencies = {d for d in dependencies if d >= pos}
+        breaks.append(pos - group_end >= k)
         prev_pos = pos
         ref = bytes(v.ref).upper()
         alts = [bytes(a).upper() for a in v.alts]
@@ -284,7 +286,7 @@ def parse_variants(chrom: str, reference: bytes, variants, k: int = K, max_allel
     flush()
     if prev_var_end + 1 <= n - 1:
         add_region(prev_var_end + 1, n - 1)
-    return groups, regions
+    return groups, regions, breaks
 
 
 def _group_dependencies(group):
@@ -431,7 +433,7 @@ def build_cluster_graph(chrom_codes: np.ndarray, variants, contained=(), k: int 
 def _build_contig(chrom, reference, variants, k, max_allele_length, copy_number_variant_threshold):
     """The groups of one contig, unsorted: (contig, nucleotide codes, clusters, sources, out_edges, start, end, variants)."""
     codes = _CODE[np.frombuffer(reference, np.uint8)]
-    groups, regions = parse_variants(chrom, reference, variants, k, max_allele_length, copy_number_variant_threshold)
+    groups, regions, breaks = parse_variants(chrom, reference, variants, k, max_allele_length, copy_number_variant_threshold)
     built = []
     for group in groups:
         deps = _group_dependencies(group)
@@ -444,7 +446,7 @@ def _build_contig(chrom, reference, variants, k, max_allele_length, copy_number_
         start = min(cl.left for cl in clusters) + 1
         end = max(cl.right for cl in clusters) + 1
         built.append((chrom, codes, clusters, sources, out_edges, start, end, sum(len(cl.variants) for cl in clusters)))
-    return built, regions
+    return built, regions, breaks
 
 
 def build_unit_graphs(chrom: str, reference: bytes, variants, k: int = K, max_allele_length: int = 500000,
@@ -454,10 +456,41 @@ def build_unit_graphs(chrom: str, reference: bytes, variants, k: int = K, max_al
     variants: objects with .pos (0-based), .ref (bytes), .alts (list of bytes), sorted by position.  On top of the arrays the
     reference's graphs hold, `var_input_idx` maps every variant of the unit back to the caller's list, and `group_start` /
     `group_end` carry the 1-based region of every group (VariantClusterGroup::region)."""
-    built, regions = _build_contig(chrom, reference, variants, k, max_allele_length, copy_number_variant_threshold)
+    built, regions, _ = _build_contig(chrom, reference, variants, k, max_allele_length, copy_number_variant_threshold)
     out = _emit(built, k)
     del out["_order"]
     out["regions"] = np.array(regions, np.int64).reshape(-1, 2)
+    return out
+
+
+def _build_genome(genome, candidates, decoys, k, max_allele_length, copy_number_variant_threshold):
+    """Groups of all contigs (unsorted, file order), regions as (contig index, is_decoy, start, end) and, per candidate contig,
+    the unit break flags of its variants."""
+    names = list(genome)
+    index = {n: i for i, n in enumerate(names)}
+    decoys = set(decoys)
+    built, regions, visited, breaks = [], [], set(), {}
+    for chrom, variants in candidates.items():
+        if chrom not in genome:
+            raise ValueError(f'variants on contig "{chrom}", which the genome does not hold')
+        if chrom in decoys:
+            breaks[chrom] = [v.pos + 1 >= k for v in variants]          # the running group end is -1 on a contig without clusters
+            continue
+        visited.add(chrom)
+        b, r, breaks[chrom] = _build_contig(chrom, genome[chrom], variants, k, max_allele_length, copy_number_variant_threshold)
+        built.extend(b)
+        regions.extend((index[chrom], 0, x, y) for x, y in r)
+    for chrom in names:
+        if chrom not in visited and len(genome[chrom]) >= k:
+            regions.append((index[chrom], int(chrom in decoys), 0, len(genome[chrom]) - 1))
+    return names, index, built, regions, breaks
+
+
+def _finish_genome(out, names, index, built):
+    group_contig = np.array([index[built[i][0]] for i in out.pop("_order")], np.uint32)
+    out["contig_names"] = names
+    out["group_contig"] = group_contig
+    out["var_contig"] = np.repeat(group_contig, np.diff(out["cl_var_off"][out["group_cluster_off"].astype(np.int64)].astype(np.int64)))
     return out
 
 
@@ -467,33 +500,42 @@ def build_genome_graphs(genome: dict, candidates: dict, decoys=(), k: int = K, m
     position-sorted variants (VCF order), decoys = names of the decoy contigs.
 
     Like the reference, variants on decoy contigs are dropped (VariantFileParser.cpp:332-341) and a variant on a contig that
-    the genome does not hold is an error (the reference asserts in Chromosomes::isDecoy, Chromosomes.cpp:145); every contig contributes its intercluster regions — a contig without usable variants as one
+    the genome does not hold is an error (the reference asserts in Chromosomes::isDecoy, Chromosomes.cpp:145); every contig
+    contributes its intercluster regions — a contig without usable variants as one
     region, decoy contigs flagged (:273-280,512-536) — and the groups of all contigs are sorted together (main.cpp:247).
     On top of build_unit_graphs' arrays: `contig_names`, `group_contig` / `var_contig` (index into contig_names; `var_input_idx` is the
     index into that contig's candidate list) and `regions` as (contig index, is_decoy, start, end) rows."""
-    names = list(genome)
-    index = {n: i for i, n in enumerate(names)}
-    decoys = set(decoys)
-    built, regions, visited = [], [], set()
-    for chrom, variants in candidates.items():
-        if chrom not in genome:
-            raise ValueError(f'variants on contig "{chrom}", which the genome does not hold')
-        if chrom in decoys:
-            continue
-        visited.add(chrom)
-        b, r = _build_contig(chrom, genome[chrom], variants, k, max_allele_length, copy_number_variant_threshold)
-        built.extend(b)
-        regions.extend((index[chrom], 0, x, y) for x, y in r)
-    for chrom in names:
-        if chrom not in visited and len(genome[chrom]) >= k:
-            regions.append((index[chrom], int(chrom in decoys), 0, len(genome[chrom]) - 1))
-    out = _emit(built, k)
-    group_contig = np.array([index[built[i][0]] for i in out.pop("_order")], np.uint32)
-    out["contig_names"] = names
-    out["group_contig"] = group_contig
-    out["var_contig"] = np.repeat(group_contig, np.diff(out["cl_var_off"][out["group_cluster_off"].astype(np.int64)].astype(np.int64)))
+    names, index, built, regions, _ = _build_genome(genome, candidates, decoys, k, max_allele_length, copy_number_variant_threshold)
+    out = _finish_genome(_emit(built, k), names, index, built)
     out["regions"] = np.array(regions, np.int64).reshape(-1, 4)
     return out
+
+
+def build_genome_units(genome: dict, candidates: dict, decoys=(), min_unit_variants: int = 5_000_000, k: int = K, max_allele_length: int = 500000,
+                       copy_number_variant_threshold: float = 0.5):
+    """The inference units `bayesTyper cluster` splits a candidate set into (main.cpp:219,233-247; VariantFileParser.cpp:286-290):
+    floor(variants / min_unit_variants) units (at least one) of ceil(variants / units) variant lines each — excluded lines count —
+    every unit running on to the next variant that lies at least k past the end of its group.  Returns (list of per-unit arrays as
+    build_genome_graphs gives them, regions of the whole genome)."""
+    names, index, built, regions, breaks = _build_genome(genome, candidates, decoys, k, max_allele_length, copy_number_variant_threshold)
+    total = sum(len(v) for v in candidates.values())
+    n_units = max(1, int(np.floor(np.float32(total) / np.float32(min_unit_variants))))
+    per_unit = int(np.ceil(np.float32(total) / np.float32(n_units)))
+    unit_of, unit, count = {}, 0, 0
+    for chrom, variants in candidates.items():
+        for i in range(len(variants)):
+            if count >= per_unit and breaks[chrom][i]:
+                unit, count = unit + 1, 0
+            count += 1
+            unit_of[(chrom, i)] = unit
+    per_unit_built = [[] for _ in range(unit + 1)]
+    for b in built:
+        first = min(v.input_idx for cl in b[2] for v in cl.variants.values())
+        per_unit_built[unit_of[(b[0], first)]].append(b)
+    if any(not bu for bu in per_unit_built):            # the reference asserts that every unit gains clusters (VariantFileParser.cpp:216-218)
+        raise ValueError("an inference unit holds no usable variant (only excluded or decoy lines): raise min_unit_variants")
+    units = [_finish_genome(_emit(bu, k), names, index, bu) for bu in per_unit_built]
+    return units, np.array(regions, np.int64).reshape(-1, 4)
 
 
 def _emit(built, k):

@@ -685,6 +685,41 @@ finish:
 // btref kmc-list --db <kmc_prefix>: every (k-mer, count) the reference's vendored KMC API lists (CKMCFile::OpenForListing /
 // ReadNextKmer, the calls of KmerCounter::parseSampleKmers and MakeBloom::kmc2bloomThreaded), as "<k-mer>\t<count>" lines, preceded
 // by one "#info" line.  Pins include/btgpu_kmc.hpp and bayestyper_b200/kmcio.py (tests/test_kmc.py).
+// `cluster`'s unit loop (main.cpp:206-247) without the k-mer stages: the variant-cluster groups of every inference unit the
+// reference's parser forms for --min-unit-variants, plus the intercluster regions it accumulated over all units
+static int cmdUnits(const Args & a) {
+    const string wd = a.str("workdir", ".");
+    const string out_dir = wd + "/" + a.str("out", "ref_out");
+    mkdir(out_dir.c_str(), 0755);
+    OptionsContainer copt("cluster", BT_VERSION, "00/00/0000 00:00:00");
+    copt.parseValue<string>("variant-file", wd + "/variants.vcf");
+    setCommonOptions(copt, a, wd, out_dir + "/bayestyper");
+    copt.parseValue<uint>("min-number-of-unit-variants", (uint) a.num("min-unit-variants", 5000000));
+    copt.parseValue<uint>("max-allele-length", 500000);
+    copt.parseValue<float>("copy-number-variant-threshold", 0.5);
+    Chromosomes chromosomes(copt.getValue<string>("genome-file"), false);
+    chromosomes.addFasta(copt.getValue<string>("decoy-file"), true);
+    chromosomes.convertToUpper();
+    VariantFileParser variant_file_parser(copt);
+    const uint num_variants = variant_file_parser.getNumberOfVariants();
+    const uint num_units = max(uint(1), static_cast<uint>(floor(num_variants / static_cast<float>(copt.getValue<uint>("min-number-of-unit-variants")))));
+    bool parsed = false;
+    uint unit_idx = 1;
+    for (; unit_idx < (num_units + 1); unit_idx++) {
+        assert(!parsed);
+        InferenceUnit unit(unit_idx);
+        parsed = variant_file_parser.constructVariantClusterGroups(&unit, ceil(num_variants / static_cast<float>(num_units)), chromosomes);
+        sort(unit.variant_cluster_groups.begin(), unit.variant_cluster_groups.end(), VariantClusterGroupCompare);
+        dumpGraphs(out_dir + "/graphs_unit_" + to_string(unit_idx) + ".btd", unit);
+        if (parsed) break;
+    }
+    assert(parsed);
+    variant_file_parser.sortInterclusterRegions();
+    variant_file_parser.writeInterclusterRegions(out_dir + "/intercluster_regions");
+    cout << "units " << unit_idx << " of " << num_units << endl;
+    return 0;
+}
+
 static int cmdKmcList(const Args & a) {
     CKMCFile db;
     if (!db.OpenForListing(a.str("db", ""))) { cerr << "cannot open KMC database " << a.str("db", "") << endl; return 1; }
@@ -708,6 +743,7 @@ int main(int argc, char ** argv) {
     if (cmd == "kat") return cmdKat();
     if (cmd == "bloom") return cmdBloom(a);
     if (cmd == "run") return cmdRun(a);
+    if (cmd == "units") return cmdUnits(a);
     if (cmd == "kmc-list") return cmdKmcList(a);
     cerr << "unknown command " << cmd << endl;
     return 2;

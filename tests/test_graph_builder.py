@@ -162,3 +162,32 @@ def test_genome_of_several_contigs_identical_to_reference():
     assert len(b["var_contig"]) == len(b["var_pos"])
     with pytest.raises(ValueError, match="does not hold"):
         graph_builder.build_genome_graphs(genome, {"chrGone": [synth.Variant(80, b"A", [b"C"])]})
+
+
+def test_inference_units_identical_to_reference():
+    """The split of a candidate set into inference units (main.cpp:219,233-247; VariantFileParser.cpp:286-290) against the units the
+    REFERENCE's parser formed for the same --min-number-of-unit-variants (tools/fuzz_genome_builder.py --units --write-golden; oracle-R's
+    `btref units` runs the reference's own unit loop)."""
+    from bayestyper_b200 import synth
+    d = btd.read(GOLD / "graphs_units.btd")
+    names = bytes(d["meta.contigs"]).decode().split("\n")
+    n_decoys = int(d["meta.n_decoys"][0])
+    genome = {n: bytes(d[f"seq.{n}"]) for n in names}
+    cand = {}
+    for n in bytes(d["meta.cand_contigs"]).decode().split("\n"):
+        alleles = bytes(d[f"cand.{n}.alleles"]).split(b"\n")
+        cand[n] = [synth.Variant(int(p), al.split(b",")[0], al.split(b",")[1:]) for p, al in zip(d[f"cand.{n}.pos"].tolist(), alleles)]
+    units, regions = graph_builder.build_genome_units(genome, cand, decoys=names[-n_decoys:], min_unit_variants=int(d["meta.min_unit_variants"][0]))
+    assert len(units) == int(d["meta.n_units"][0]) >= 3
+    for u, b in enumerate(units):
+        for k in ("var_pos", "cluster_idx", "group_nvar", "group_cluster_off", "seq", "v_in_src"):
+            assert len(b[k]) == len(d[f"u{u}.{k}"]) and (np.asarray(b[k]) == d[f"u{u}.{k}"]).all(), (u, k)
+        chroms = bytes(d[f"u{u}.chroms"])
+        ref_names = [chroms[int(a):int(c)].decode() for a, c in zip(d[f"u{u}.chrom_off"][:-1], d[f"u{u}.chrom_off"][1:])]
+        assert ref_names == [b["contig_names"][i] for i in b["group_contig"]]
+    one, regions_one = graph_builder.build_genome_units(genome, cand, decoys=names[-n_decoys:], min_unit_variants=10**9)
+    whole = graph_builder.build_genome_graphs(genome, cand, decoys=names[-n_decoys:])
+    assert len(one) == 1 and (one[0]["var_pos"] == whole["var_pos"]).all() and (regions_one == whole["regions"]).all() and (regions == regions_one).all()
+    assert sum(len(b["var_pos"]) for b in units) == len(whole["var_pos"])
+    with pytest.raises(ValueError, match="no usable variant"):
+        graph_builder.build_genome_units(genome, cand, decoys=names[-n_decoys:], min_unit_variants=1)

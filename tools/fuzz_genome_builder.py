@@ -70,6 +70,37 @@ def reference_run(genome, decoys, cand):
     return g, regions, None
 
 
+def reference_units(genome, decoys, cand, min_unit_variants):
+    """btref units: the groups of every inference unit + the regions of the whole run."""
+    with tempfile.TemporaryDirectory() as td:
+        wd = Path(td)
+        with open(wd / "genome.fa", "wb") as f:
+            for n, s in genome.items():
+                f.write(b">" + n.encode() + b"\n" + s + b"\n")
+        with open(wd / "decoy.fa", "wb") as f:
+            for n, s in decoys.items():
+                f.write(b">" + n.encode() + b"\n" + s + b"\n")
+        with open(wd / "variants.vcf", "w") as f:
+            f.write("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
+            for n, var in cand.items():
+                for i, v in enumerate(var):
+                    f.write(f"{n}\t{v.pos + 1}\t{n}_{i}\t{v.ref.decode()}\t{','.join(a.decode() for a in v.alts)}\t.\t.\t.\n")
+        (wd / "samples.tsv").write_text("S1\tF\tnone\n")
+        r = subprocess.run([str(F.BTREF), "units", "--workdir", str(wd), "--threads", "2", "--min-unit-variants", str(min_unit_variants),
+                            "--decoy-file", str(wd / "decoy.fa")], capture_output=True, text=True)
+        if r.returncode != 0:
+            return None, None, (r.stderr or r.stdout)[-400:]
+        units = []
+        i = 1
+        while (wd / "ref_out" / f"graphs_unit_{i}.btd").exists():
+            units.append(btd.read(wd / "ref_out" / f"graphs_unit_{i}.btd"))
+            i += 1
+        raw = (wd / "ref_out" / "intercluster_regions.txt.gz").read_bytes()
+        txt = gzip.decompress(raw).decode() if raw[:2] == b"\x1f\x8b" else raw.decode()
+        regions = sorted((t[0], int(t[1]), int(t[2]), int(t[3])) for t in (ln.split("\t") for ln in txt.splitlines()))
+    return units, regions, None
+
+
 def compare(g, regions, b):
     for k in F.KEYS:
         if len(b[k]) != len(g[k]) or not (np.asarray(b[k]) == np.asarray(g[k])).all():
@@ -90,8 +121,52 @@ def main():
     ap.add_argument("--cases", type=int, default=10)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--write-golden", action="store_true")
+    ap.add_argument("--units", action="store_true", help="compare the split into inference units (btref units) instead")
     a = ap.parse_args()
     n_bad = 0
+    if a.units:
+        for c in range(a.cases):
+            seed = a.seed * 100 + c
+            genome, decoys, cand = genome_case(seed)
+            total = sum(len(v) for v in cand.values())
+            for min_unit in (max(1, total // 7), max(1, total // 3), total + 5):
+                ref_units, regions, err = reference_units(genome, decoys, cand, min_unit)
+                if ref_units is None:
+                    try:
+                        graph_builder.build_genome_units({**genome, **decoys}, cand, decoys=list(decoys), min_unit_variants=min_unit)
+                        verdict = "builder built it: MISMATCH"
+                        n_bad += 1
+                    except ValueError as e:
+                        verdict = f"builder refuses too ({e})"
+                    print(f"case {seed} min_unit {min_unit}: reference aborted ({err.strip().splitlines()[-1][-90:] if err.strip() else '?'}); {verdict}")
+                    continue
+                mine, mine_regions = graph_builder.build_genome_units({**genome, **decoys}, cand, decoys=list(decoys), min_unit_variants=min_unit)
+                bad = None if len(mine) == len(ref_units) else f"number of units {len(mine)} vs {len(ref_units)}"
+                for u, (g, b) in enumerate(zip(ref_units, mine)):
+                    b = dict(b); b["regions"] = mine_regions
+                    bad = bad or compare(g, regions, b)
+                print(f"case {seed} min_unit {min_unit}: {'MISMATCH: ' + str(bad) if bad else 'identical'} ({len(ref_units)} units, "
+                      f"{[len(g['cluster_idx']) for g in ref_units]} clusters)")
+                n_bad += bool(bad)
+                if a.write_golden and not bad and c == 0 and len(ref_units) >= 3:
+                    pack = {"meta.contigs": np.frombuffer("\n".join(list(genome) + list(decoys)).encode(), np.uint8), "meta.n_decoys": np.array([len(decoys)], np.uint32),
+                            "meta.cand_contigs": np.frombuffer("\n".join(cand).encode(), np.uint8), "meta.min_unit_variants": np.array([min_unit], np.uint32),
+                            "meta.n_units": np.array([len(ref_units)], np.uint32)}
+                    for n, s_ in {**genome, **decoys}.items():
+                        pack[f"seq.{n}"] = np.frombuffer(s_, np.uint8)
+                    for n, var in cand.items():
+                        pack[f"cand.{n}.pos"] = np.array([v.pos for v in var], np.int64)
+                        pack[f"cand.{n}.alleles"] = np.frombuffer(b"\n".join(b",".join([v.ref] + v.alts) for v in var), np.uint8)
+                    for u, g in enumerate(ref_units):
+                        for k_ in ("var_pos", "cluster_idx", "group_nvar", "group_cluster_off", "seq", "v_in_src", "chrom_off"):
+                            pack[f"u{u}.{k_}"] = np.asarray(g[k_])
+                        ch = g["chroms"]
+                        pack[f"u{u}.chroms"] = np.frombuffer(ch.encode() if isinstance(ch, str) else bytes(ch), np.uint8)
+                    btd.write(ROOT / "tests" / "golden" / "graphs_units.btd", pack)
+                    print("wrote tests/golden/graphs_units.btd")
+                    a.write_golden = False
+        print(f"{a.cases} cases, {n_bad} bad")
+        return 1 if n_bad else 0
     for c in range(a.cases):
         seed = a.seed * 100 + c
         genome, decoys, cand = genome_case(seed)
