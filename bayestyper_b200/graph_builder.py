@@ -9,7 +9,10 @@ the reference; tests/test_graph_builder.py checks it array by array against what
 deletions included).  Orders that the reference takes from `std::unordered_map` / `unordered_set` iteration are reproduced with
 `stdhash_order.UnorderedUInt`.
 
-Not restated: the split of a candidate set into several inference units (`min_unit_variants`: one unit here).
+One behaviour of the reference is deliberately not reproduced: when an inference unit ends exactly in front of the first variant of a
+new contig, the reference's next unit compares that variant's position with the last position of the PREVIOUS contig and exits with
+"Variants need to be sorted by position" (VariantFileParser.cpp:283-293 runs before prev_position is updated, :268 sees equal contig
+names on re-entry); build_genome_units simply starts the unit there.
 """
 from __future__ import annotations
 

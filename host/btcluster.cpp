@@ -3,7 +3,8 @@
 // (include/btgpu_cluster.hpp does the work; file reading follows Chromosomes::parseFasta, Chromosomes.cpp:72-117, and
 // VariantFileParser's line reader, VariantFileParser.cpp:67-167: CHROM POS ID REF ALT and INFO ACO, `.vcf` or `.vcf.gz`).
 //
-//   btcluster <genome.fa> <candidates.vcf[.gz]> <out.btd> [--decoy <decoy.fa>] [--max-allele-length N] [--copy-number-variant-threshold X]
+//   btcluster <genome.fa> <candidates.vcf[.gz]> <out.btd> [--decoy <decoy.fa>] [--min-unit-variants N] [--max-allele-length N] [--copy-number-variant-threshold X]
+// With --min-unit-variants the inference units go to <out>_unit_<i>.btd (i = 1..), as the reference's <prefix>_unit_<i>/ directories.
 #include <zlib.h>
 
 #include <chrono>
@@ -101,11 +102,13 @@ static std::vector<std::pair<std::string, std::vector<Candidate>>> readCandidate
 
 int main(int argc, char **argv) {
     try {
-        if (argc < 4) { std::fprintf(stderr, "usage: btcluster <genome.fa> <candidates.vcf[.gz]> <out.btd> [--decoy <decoy.fa>] [--max-allele-length N] [--copy-number-variant-threshold X]\n"); return 2; }
+        if (argc < 4) { std::fprintf(stderr, "usage: btcluster <genome.fa> <candidates.vcf[.gz]> <out.btd> [--decoy <decoy.fa>] [--min-unit-variants N] [--max-allele-length N] [--copy-number-variant-threshold X]\n"); return 2; }
         btg::cluster::Options opt;
         std::string decoy;
+        uint32_t min_unit = 0;          // 0: one unit
         for (int i = 4; i + 1 < argc; i += 2) {
             if (!std::strcmp(argv[i], "--decoy")) decoy = argv[i + 1];
+            else if (!std::strcmp(argv[i], "--min-unit-variants")) min_unit = (uint32_t)std::stoul(argv[i + 1]);
             else if (!std::strcmp(argv[i], "--max-allele-length")) opt.max_allele_length = (uint32_t)std::stoul(argv[i + 1]);
             else if (!std::strcmp(argv[i], "--copy-number-variant-threshold")) opt.copy_number_variant_threshold = (float)std::stod(argv[i + 1]);
             else throw btg::Error(std::string("unknown option ") + argv[i]);
@@ -116,31 +119,40 @@ int main(int argc, char **argv) {
         if (!decoy.empty()) readFasta(decoy, true, names, seqs, flags);
         auto cand = readCandidates(argv[2]);
         const auto t0 = std::chrono::steady_clock::now();
-        auto g = btg::cluster::buildGenomeGraphs(names, seqs, flags, cand, opt);
+        std::vector<btg::cluster::Graphs> units;
+        if (min_unit) units = btg::cluster::buildGenomeUnits(names, seqs, flags, cand, min_unit, opt);
+        else units.push_back(btg::cluster::buildGenomeGraphs(names, seqs, flags, cand, opt));
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        btd::BtdWriter w(argv[3]);
         std::string joined;
         for (size_t i = 0; i < names.size(); i++) { if (i) joined += '\n'; joined += names[i]; }
-        w.put("contig_names", 0, (const uint8_t *)joined.data(), {(uint64_t)joined.size()});
-        w.put("group_cluster_off", 3, g.group_cluster_off); w.put("group_nvar", 2, g.group_nvar);
-        w.put("group_src_off", 3, g.group_src_off); w.put("group_src", 2, g.group_src);
-        w.put("group_edge_off", 3, g.group_edge_off); w.put("group_edge_src", 2, g.group_edge_src); w.put("group_edge_dst", 2, g.group_edge_dst);
-        w.put("group_start", 2, g.group_start); w.put("group_end", 2, g.group_end); w.put("group_contig", 2, g.group_contig);
-        w.put("cluster_idx", 2, g.cluster_idx);
-        w.put("cl_vertex_off", 3, g.cl_vertex_off); w.put("cl_var_off", 3, g.cl_var_off);
-        w.put("v_seq_off", 3, g.v_seq_off); w.put("seq", 0, g.seq); w.put("v_flags", 0, g.v_flags); w.put("v_var", 1, g.v_var); w.put("v_allele", 1, g.v_allele);
-        w.put("v_nested", 2, g.v_nested); w.put("v_refvar_off", 3, g.v_refvar_off); w.put("v_refvar", 1, g.v_refvar);
-        w.put("v_in_off", 3, g.v_in_off); w.put("v_in_src", 2, g.v_in_src);
-        w.put("var_pos", 2, g.var_pos); w.put("var_dep", 0, g.var_dep); w.put("var_nalt", 1, g.var_nalt); w.put("var_contig", 2, g.var_contig);
-        w.put("var_input_idx", 7, g.var_input_idx); w.put("var_alt_off", 3, g.var_alt_off); w.put("alt_reflen", 2, g.alt_reflen);
-        w.put("alt_seq_off", 3, g.alt_seq_off); w.put("alt_seq", 0, (const uint8_t *)g.alt_seq.data(), {(uint64_t)g.alt_seq.size()});
-        w.put("alt_aco_off", 3, g.alt_aco_off); w.put("alt_aco", 0, (const uint8_t *)g.alt_aco.data(), {(uint64_t)g.alt_aco.size()});
-        w.put("var_id_off", 3, g.var_id_off); w.put("var_ids", 0, (const uint8_t *)g.var_ids.data(), {(uint64_t)g.var_ids.size()});
-        std::vector<int64_t> regions;
-        for (auto &r : g.regions) { regions.push_back(r.contig); regions.push_back(r.decoy); regions.push_back(r.start); regions.push_back(r.end); }
-        w.put("regions", 7, regions.data(), {(uint64_t)g.regions.size(), 4});
-        std::fprintf(stderr, "btcluster: %zu variants as %zu clusters in %zu groups, %zu intercluster regions (%.3f s)\n", g.var_pos.size(), g.cluster_idx.size(),
-                     g.group_nvar.size(), g.regions.size(), dt);
+        std::string stem = argv[3];
+        if (stem.size() > 4 && stem.compare(stem.size() - 4, 4, ".btd") == 0) stem.resize(stem.size() - 4);
+        size_t n_var = 0, n_cl = 0, n_gr = 0;
+        for (size_t u = 0; u < units.size(); u++) {
+            const auto &g = units[u];
+            btd::BtdWriter w(min_unit ? stem + "_unit_" + std::to_string(u + 1) + ".btd" : std::string(argv[3]));
+            w.put("contig_names", 0, (const uint8_t *)joined.data(), {(uint64_t)joined.size()});
+            w.put("group_cluster_off", 3, g.group_cluster_off); w.put("group_nvar", 2, g.group_nvar);
+            w.put("group_src_off", 3, g.group_src_off); w.put("group_src", 2, g.group_src);
+            w.put("group_edge_off", 3, g.group_edge_off); w.put("group_edge_src", 2, g.group_edge_src); w.put("group_edge_dst", 2, g.group_edge_dst);
+            w.put("group_start", 2, g.group_start); w.put("group_end", 2, g.group_end); w.put("group_contig", 2, g.group_contig);
+            w.put("cluster_idx", 2, g.cluster_idx);
+            w.put("cl_vertex_off", 3, g.cl_vertex_off); w.put("cl_var_off", 3, g.cl_var_off);
+            w.put("v_seq_off", 3, g.v_seq_off); w.put("seq", 0, g.seq); w.put("v_flags", 0, g.v_flags); w.put("v_var", 1, g.v_var); w.put("v_allele", 1, g.v_allele);
+            w.put("v_nested", 2, g.v_nested); w.put("v_refvar_off", 3, g.v_refvar_off); w.put("v_refvar", 1, g.v_refvar);
+            w.put("v_in_off", 3, g.v_in_off); w.put("v_in_src", 2, g.v_in_src);
+            w.put("var_pos", 2, g.var_pos); w.put("var_dep", 0, g.var_dep); w.put("var_nalt", 1, g.var_nalt); w.put("var_contig", 2, g.var_contig);
+            w.put("var_input_idx", 7, g.var_input_idx); w.put("var_alt_off", 3, g.var_alt_off); w.put("alt_reflen", 2, g.alt_reflen);
+            w.put("alt_seq_off", 3, g.alt_seq_off); w.put("alt_seq", 0, (const uint8_t *)g.alt_seq.data(), {(uint64_t)g.alt_seq.size()});
+            w.put("alt_aco_off", 3, g.alt_aco_off); w.put("alt_aco", 0, (const uint8_t *)g.alt_aco.data(), {(uint64_t)g.alt_aco.size()});
+            w.put("var_id_off", 3, g.var_id_off); w.put("var_ids", 0, (const uint8_t *)g.var_ids.data(), {(uint64_t)g.var_ids.size()});
+            std::vector<int64_t> regions;      // of the whole genome: with the first unit
+            for (auto &r : units.front().regions) { regions.push_back(r.contig); regions.push_back(r.decoy); regions.push_back(r.start); regions.push_back(r.end); }
+            w.put("regions", 7, regions.data(), {(uint64_t)units.front().regions.size(), 4});
+            n_var += g.var_pos.size(); n_cl += g.cluster_idx.size(); n_gr += g.group_nvar.size();
+        }
+        std::fprintf(stderr, "btcluster: %zu variants as %zu clusters in %zu groups and %zu unit(s), %zu intercluster regions (%.3f s)\n", n_var, n_cl, n_gr, units.size(),
+                     units.front().regions.size(), dt);
         return 0;
     } catch (const std::exception &e) {
         std::fprintf(stderr, "btcluster: %s\n", e.what());

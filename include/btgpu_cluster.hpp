@@ -205,7 +205,7 @@ inline void mergeClusters(Group &group, MergeSets &merge_sets) {
     }
 }
 
-struct ContigResult { std::vector<Group> groups; std::vector<std::pair<uint32_t, uint32_t>> regions; };
+struct ContigResult { std::vector<Group> groups; std::vector<std::pair<uint32_t, uint32_t>> regions; std::vector<uint8_t> breaks; };
 
 inline ContigResult parseContig(const std::string &reference, const std::vector<Candidate> &variants, const Options &o) {
     const uint32_t k = o.k;
@@ -227,6 +227,7 @@ inline ContigResult parseContig(const std::string &reference, const std::vector<
         const int64_t pos = v.pos;
         if (pos < prev_pos) throw std::runtime_error("variants need to be sorted by position: " + std::to_string(prev_pos + 1) + " is before " + std::to_string(pos + 1));
         while (!dependencies.empty() && int64_t(*dependencies.begin()) < pos) dependencies.erase(dependencies.begin());
+        out.breaks.push_back(pos - group_end >= int64_t(k));      // an inference unit may end in front of this variant
         prev_pos = pos;
         const std::string ref = upper(v.ref);
         std::vector<std::string> alts;
@@ -434,25 +435,35 @@ struct BuiltGroup {
 
 }  // namespace detail
 
-// The unit of a genome: contigs in FASTA order (decoys included, flagged), candidates per contig in VCF order.
-// Variants on decoy contigs are dropped; a variant on a contig the genome does not hold is an error (Chromosomes.cpp:145).
-inline Graphs buildGenomeGraphs(const std::vector<std::string> &contig_names, const std::vector<std::string> &contig_seqs, const std::vector<uint8_t> &contig_decoy,
-                                const std::vector<std::pair<std::string, std::vector<Candidate>>> &candidates, const Options &o = Options()) {
-    using namespace detail;
+namespace detail {
+
+struct GenomeParse {
+    std::vector<std::vector<Group>> keep;      // owns the clusters
+    std::vector<BuiltGroup> built;             // file order
+    std::vector<int64_t> first_variant;        // per built group: smallest input index among its variants
+    std::vector<Region> regions;
+    std::vector<std::vector<uint8_t>> breaks;  // per candidate contig, per variant line
+};
+
+inline GenomeParse parseGenome(const std::vector<std::string> &contig_names, const std::vector<std::string> &contig_seqs, const std::vector<uint8_t> &contig_decoy,
+                               const std::vector<std::pair<std::string, std::vector<Candidate>>> &candidates, const Options &o) {
     std::unordered_map<std::string, uint32_t> index;
     for (uint32_t i = 0; i < contig_names.size(); i++) index.emplace(contig_names[i], i);
-    Graphs g;
-    std::vector<std::vector<Group>> keep;      // owns the clusters
-    std::vector<BuiltGroup> built;
+    GenomeParse p;
     std::vector<bool> visited(contig_names.size(), false);
     for (auto &cv : candidates) {
         auto it = index.find(cv.first);
         if (it == index.end()) throw std::runtime_error("variants on contig \"" + cv.first + "\", which the genome does not hold");
         const uint32_t c = it->second;
-        if (contig_decoy[c]) continue;
+        if (contig_decoy[c]) {      // dropped; the running group end is -1 on a contig without clusters
+            p.breaks.emplace_back();
+            for (auto &v : cv.second) p.breaks.back().push_back(v.pos + 1 >= o.k);
+            continue;
+        }
         visited[c] = true;
         ContigResult r = parseContig(contig_seqs[c], cv.second, o);
-        for (auto &reg : r.regions) g.regions.push_back({c, false, reg.first, reg.second});
+        p.breaks.push_back(std::move(r.breaks));
+        for (auto &reg : r.regions) p.regions.push_back({c, false, reg.first, reg.second});
         for (auto &group : r.groups) {
             auto deps = groupDependencies(group);
             BuiltGroup b;
@@ -463,17 +474,27 @@ inline Graphs buildGenomeGraphs(const std::vector<std::string> &contig_names, co
             b.out_edges.resize(b.clusters.size());
             for (auto &d : deps) b.out_edges[slot.at(d.second)].push_back(slot.at(d.first));
             b.start = kNone32; b.end = 0; b.n_variants = 0;
-            for (Cluster *cl : b.clusters) { b.start = std::min(b.start, cl->left + 1); b.end = std::max(b.end, cl->right + 1); b.n_variants += (uint32_t)cl->variants.size(); }
+            int64_t first = std::numeric_limits<int64_t>::max();
+            for (Cluster *cl : b.clusters) {
+                b.start = std::min(b.start, cl->left + 1); b.end = std::max(b.end, cl->right + 1); b.n_variants += (uint32_t)cl->variants.size();
+                for (auto &pv : cl->variants) first = std::min(first, pv.second.input_idx);
+            }
             b.region = contig_names[c] + ":" + std::to_string(b.start) + "-" + std::to_string(b.end);
-            built.push_back(std::move(b));
+            p.built.push_back(std::move(b));
+            p.first_variant.push_back(first);
         }
-        keep.push_back(std::move(r.groups));
+        p.keep.push_back(std::move(r.groups));
     }
     for (uint32_t c = 0; c < contig_names.size(); c++)
-        if (!visited[c] && contig_seqs[c].size() >= o.k) g.regions.push_back({c, contig_decoy[c] != 0, 0, (uint32_t)contig_seqs[c].size() - 1});
+        if (!visited[c] && contig_seqs[c].size() >= o.k) p.regions.push_back({c, contig_decoy[c] != 0, 0, (uint32_t)contig_seqs[c].size() - 1});
+    return p;
+}
+
+// groups `which` of the parse, in the unit's order, as flat arrays
+inline Graphs emitUnit(const GenomeParse &p, std::vector<uint32_t> order, const std::vector<std::string> &contig_seqs, const Options &o) {
+    const auto &built = p.built;
+    Graphs g;
     // VariantClusterGroupCompare: number of variants desc, then region string desc
-    std::vector<uint32_t> order(built.size());
-    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
         if (built[a].n_variants != built[b].n_variants) return built[a].n_variants > built[b].n_variants;
         return built[a].region > built[b].region;
@@ -506,6 +527,55 @@ inline Graphs buildGenomeGraphs(const std::vector<std::string> &contig_names, co
         g.group_cluster_off.push_back(g.cluster_idx.size());
     }
     return g;
+}
+
+}  // namespace detail
+
+// The unit of a genome: contigs in FASTA order (decoys included, flagged), candidates per contig in VCF order.
+// Variants on decoy contigs are dropped; a variant on a contig the genome does not hold is an error (Chromosomes.cpp:145).
+inline Graphs buildGenomeGraphs(const std::vector<std::string> &contig_names, const std::vector<std::string> &contig_seqs, const std::vector<uint8_t> &contig_decoy,
+                                const std::vector<std::pair<std::string, std::vector<Candidate>>> &candidates, const Options &o = Options()) {
+    detail::GenomeParse p = detail::parseGenome(contig_names, contig_seqs, contig_decoy, candidates, o);
+    std::vector<uint32_t> all(p.built.size());
+    for (uint32_t i = 0; i < all.size(); i++) all[i] = i;
+    Graphs g = detail::emitUnit(p, all, contig_seqs, o);
+    g.regions = p.regions;
+    return g;
+}
+
+// The inference units `bayesTyper cluster` splits a candidate set into (main.cpp:219,233-247; VariantFileParser.cpp:286-290):
+// floor(variants / min_unit_variants) units (at least one) of ceil(variants / units) variant lines each — excluded lines count —
+// every unit running on to the next variant that lies at least k past the end of its group.  regions (of the whole genome) go to
+// the first unit's `regions`.
+inline std::vector<Graphs> buildGenomeUnits(const std::vector<std::string> &contig_names, const std::vector<std::string> &contig_seqs,
+                                            const std::vector<uint8_t> &contig_decoy, const std::vector<std::pair<std::string, std::vector<Candidate>>> &candidates,
+                                            uint32_t min_unit_variants, const Options &o = Options()) {
+    detail::GenomeParse p = detail::parseGenome(contig_names, contig_seqs, contig_decoy, candidates, o);
+    uint64_t total = 0;
+    for (auto &cv : candidates) total += cv.second.size();
+    const uint32_t n_units = std::max<uint32_t>(1, (uint32_t)std::floor((float)total / (float)min_unit_variants));
+    const uint32_t per_unit = (uint32_t)std::ceil((float)total / (float)n_units);
+    // unit of every variant line, file order
+    std::vector<std::vector<uint32_t>> unit_of(candidates.size());
+    uint32_t unit = 0, count = 0;
+    for (size_t c = 0; c < candidates.size(); c++)
+        for (size_t i = 0; i < candidates[c].second.size(); i++) {
+            if (count >= per_unit && p.breaks[c][i]) { unit++; count = 0; }
+            count++;
+            unit_of[c].push_back(unit);
+        }
+    std::unordered_map<std::string, size_t> cand_index;
+    for (size_t c = 0; c < candidates.size(); c++) cand_index.emplace(candidates[c].first, c);
+    std::vector<std::vector<uint32_t>> members(unit + 1);
+    for (uint32_t gi = 0; gi < p.built.size(); gi++)
+        members[unit_of[cand_index.at(contig_names[p.built[gi].contig])][(size_t)p.first_variant[gi]]].push_back(gi);
+    std::vector<Graphs> units;
+    for (auto &m : members) {
+        if (m.empty()) throw std::runtime_error("an inference unit holds no usable variant (only excluded or decoy lines): raise --min-unit-variants");
+        units.push_back(detail::emitUnit(p, m, contig_seqs, o));
+    }
+    units.front().regions = p.regions;
+    return units;
 }
 
 }  // namespace cluster

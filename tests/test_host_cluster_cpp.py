@@ -135,3 +135,33 @@ def test_native_builder_behind_the_python_interface():
             assert np.asarray(b[k]).dtype == np.asarray(v).dtype and (np.asarray(b[k]) == np.asarray(v)).all(), k
     with pytest.raises(ValueError, match="sorted by position"):
         graph_builder.build_genome_graphs_native({"c": b"A" * 300}, {"c": [synth.Variant(100, b"A", [b"C"]), synth.Variant(90, b"A", [b"C"])]})
+
+
+def test_inference_units_identical_to_reference(tmp_path):
+    d = btd.read(GOLD / "graphs_units.btd")
+    names = bytes(d["meta.contigs"]).decode().split("\n")
+    n_decoys = int(d["meta.n_decoys"][0])
+    seqs = {n: bytes(d[f"seq.{n}"]) for n in names}
+    cand = {}
+    for n in bytes(d["meta.cand_contigs"]).decode().split("\n"):
+        alleles = bytes(d[f"cand.{n}.alleles"]).split(b"\n")
+        cand[n] = [synth.Variant(int(p), al.split(b",")[0], al.split(b",")[1:]) for p, al in zip(d[f"cand.{n}.pos"].tolist(), alleles)]
+    _write_fasta(tmp_path / "genome.fa", {n: seqs[n] for n in names[:-n_decoys]})
+    _write_fasta(tmp_path / "decoy.fa", {n: seqs[n] for n in names[-n_decoys:]})
+    _write_vcf(tmp_path / "c.vcf", cand)
+    r = subprocess.run([str(_exe()), str(tmp_path / "genome.fa"), str(tmp_path / "c.vcf"), str(tmp_path / "out.btd"), "--decoy", str(tmp_path / "decoy.fa"),
+                        "--min-unit-variants", str(int(d["meta.min_unit_variants"][0]))], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    n_units = int(d["meta.n_units"][0])
+    assert not (tmp_path / f"out_unit_{n_units + 1}.btd").exists()
+    py_units, py_regions = graph_builder.build_genome_units(seqs, cand, decoys=names[-n_decoys:], min_unit_variants=int(d["meta.min_unit_variants"][0]))
+    for u in range(n_units):
+        b = btd.read(tmp_path / f"out_unit_{u + 1}.btd")
+        for k in ("var_pos", "cluster_idx", "group_nvar", "group_cluster_off", "seq", "v_in_src"):
+            assert len(b[k]) == len(d[f"u{u}.{k}"]) and (np.asarray(b[k]) == d[f"u{u}.{k}"]).all(), (u, k)
+        for k in KEYS + ("group_contig", "var_contig", "var_input_idx"):
+            assert (np.asarray(b[k]) == np.asarray(py_units[u][k])).all(), (u, k)
+        assert (b["regions"] == py_regions).all()
+    r = subprocess.run([str(_exe()), str(tmp_path / "genome.fa"), str(tmp_path / "c.vcf"), str(tmp_path / "o2.btd"), "--decoy", str(tmp_path / "decoy.fa"),
+                        "--min-unit-variants", "1"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no usable variant" in r.stderr
