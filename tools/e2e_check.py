@@ -1,7 +1,9 @@
 """End-to-end check of a staged fixture on a GPU box: tests/golden/make_fixtures.py E2E_NEXT_WORKLOADS -> driver.run -> the
 reference's calls (same statistical bars as tests/test_gpu_e2e.py).  A case that is green here moves to E2E_WORKLOADS.
 
-    gpurun --timeout 600 -- 'python tools/e2e_check.py e2e_nested_2s'
+    gpurun --timeout 600 -- 'python tools/e2e_check.py e2e_nested_2s; python tools/e2e_check.py genome'
+
+`genome` runs the staged whole-genome composition (bayestyper_b200/driver_genome.py) on the multi-contig fixture.
 """
 from __future__ import annotations
 
@@ -48,5 +50,51 @@ def main(name):
     return 0 if ok else 1
 
 
+def main_genome():
+    """driver_genome.genotype_genome on the multi-contig fixture against the calls in the reference's VCF (tests/golden/vcf_genome_2s.vcf.gz)."""
+    import gzip
+
+    from bayestyper_b200 import driver_genome, vcfio
+    from tests.golden.make_vcf_genome_fixture import GENDERS, genome_workload, sample_spectra
+    parts, empty, decoys = genome_workload()
+    genome = {n: w.reference for n, w in parts.items()}
+    genome[empty[0]] = empty[1]
+    cand = {n: w.variants for n, w in parts.items()}
+    inp = driver_genome.GenomeInputs({**genome, **decoys}, cand, list(GENDERS), sample_spectra(parts, decoys), decoys=tuple(decoys))
+    out_vcf = ROOT / "gpurun_out" / "genome_check.vcf"
+    out_vcf.parent.mkdir(exist_ok=True)
+    graphs, res, info = driver_genome.genotype_genome(inp, driver.Options(random_seed=20190401), vcf_out=out_vcf, sample_names=["S1", "S2"])
+    tmp = ROOT / "gpurun_out" / "genome_ref.vcf"
+    tmp.write_bytes(gzip.open(ROOT / "tests" / "golden" / "vcf_genome_2s.vcf.gz").read())
+    _, ref_rows = vcfio.read_vcf(tmp)
+    _, got_rows = vcfio.read_vcf(out_vcf)
+    ok = True
+
+    def check(cond, what):
+        nonlocal ok
+        print(("ok   " if cond else "FAIL ") + what)
+        ok = ok and bool(cond)
+
+    check([(r["chrom"], r["pos"], r["id"], r["ref"], r["alt"]) for r in got_rows] == [(r["chrom"], r["pos"], r["id"], r["ref"], r["alt"]) for r in ref_rows],
+          f"same records in the same order ({len(ref_rows)})")
+    n = same = hard = 0
+    dgpp = []
+    for a, b in zip(got_rows, ref_rows):
+        check_info = all(a["info"].get(k) == b["info"].get(k) for k in ("VCS", "VCR", "VCGS", "VCGR"))
+        ok = ok and check_info
+        for sa, sb in zip(a["samples"], b["samples"]):
+            n += 1
+            same += sa["GT"] == sb["GT"]
+            hard += sa["GT"] != sb["GT"] and "." not in sa["GT"] and "." not in sb["GT"]
+            if "GPP" in sa and "GPP" in sb and len(sa["GPP"]) == len(sb["GPP"]):
+                dgpp.append(np.abs(np.array(sa["GPP"]) - np.array(sb["GPP"])).max())
+    check(same / n > 0.98, f"GT agreement {same / n:.4f} (haploid chrX male calls included)")
+    check(hard <= max(2, int(0.003 * n)), f"hard disagreements {hard}")
+    check(np.mean(dgpp) < 3e-3, f"mean max|dGPP| {np.mean(dgpp):.2e}")
+    print("nb", info["nb"], "noise", info["noise_rates"])
+    return 0 if ok else 1
+
+
 if __name__ == "__main__":
-    sys.exit(main(sys.argv[1] if len(sys.argv) > 1 else "e2e_nested_2s"))
+    name = sys.argv[1] if len(sys.argv) > 1 else "e2e_nested_2s"
+    sys.exit(main_genome() if name == "genome" else main(name))
