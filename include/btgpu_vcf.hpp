@@ -52,6 +52,9 @@ namespace vcf_detail {
 inline bool floatCompare(float a, float b) {  // Utils.hpp:89-95
     return (a == b) || (std::fabs(a - b) < std::fabs(a < b ? a : b) * (1.1920929e-07f * 100));
 }
+// the reference holds the genome in upper case (Chromosomes::convertToUpper, main.cpp:213): REF and the allele suffixes taken from a
+// soft-masked contig are written in upper case
+inline std::string upperCase(std::string s) { for (auto &c : s) if (c >= 'a' && c <= 'z') c = char(c - 'a' + 'A'); return s; }
 template <class T> void field(std::ostream &os, const T *v, size_t n) {  // writeAlleleField
     for (size_t i = 0; i < n; i++) { if (i) os << ","; os << v[i]; }
 }
@@ -96,10 +99,10 @@ inline void vcfRecord(std::ostream &os, const VcfVariant &v, uint64_t vi, const 
     using namespace vcf_detail;
     const std::string &chrom = contigs[v.contig].sequence;
     const uint32_t nA = v.numberOfAlleles(), max_ref = v.maxReferenceLength();
-    os << contigs[v.contig].name << "\t" << v.position << "\t" << v.id << "\t" << chrom.substr(v.position - 1, max_ref) << "\t";
+    os << contigs[v.contig].name << "\t" << v.position << "\t" << v.id << "\t" << upperCase(chrom.substr(v.position - 1, max_ref)) << "\t";
     for (size_t a = 0; a < v.alt_alleles.size(); a++) {  // writeAlleleSequences
         if (a) os << ",";
-        os << v.alt_alleles[a].sequence << chrom.substr(v.position + v.alt_alleles[a].ref_length - 1, max_ref - v.alt_alleles[a].ref_length);
+        os << v.alt_alleles[a].sequence << upperCase(chrom.substr(v.position + v.alt_alleles[a].ref_length - 1, max_ref - v.alt_alleles[a].ref_length));
     }
     if (v.has_dependency) os << ",*";
     // writeQualityAndFilter: max_alt_allele_call_probability = max ACP over the alternative alleles, the missing ('*') allele

@@ -204,6 +204,20 @@ def test_description_of_a_genome_from_graph_builder_reproduces_the_reference_vcf
         assert a == b or (not b.startswith("#") and _qual_tolerant_equal(a, b)), f"\n got: {a[:300]}\nwant: {b[:300]}"
 
 
+def test_soft_masked_genome_is_written_in_upper_case(tmp_path):
+    """The reference upper-cases the genome on loading (Chromosomes::convertToUpper): a soft-masked contig gives the same file."""
+    exe = _build_btvcf()
+    want = gzip.open(GOLD / "vcf_mixed_3s.vcf.gz", "rt").read()
+    w = VCF_WORKLOADS["vcf_mixed_3s"]()
+    masked = bytearray(w.reference)
+    masked[1000:9000] = bytes(masked[1000:9000]).lower()
+    btd.write(tmp_path / "in.btd", _arrays_from_vcf(want, bytes(masked), True))
+    r = subprocess.run([str(exe), str(tmp_path / "in.btd"), str(tmp_path / "out.vcf")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for a, b in zip((tmp_path / "out.vcf").read_text().splitlines(), want.splitlines()):
+        assert a == b or (not b.startswith("#") and _qual_tolerant_equal(a, b)), f"\n got: {a[:200]}\nwant: {b[:200]}"
+
+
 def test_sample_without_genotype_and_filters(tmp_path):
     """Ploidy 0 (e.g. a female on chrY) prints the reference's ':.:.:.:.:.:.' (GenotypeWriter.cpp:58,319); AN = 0 gives FILTER AN0;
     a dependent variant gets the '*' allele and ACO '.' (GenotypeWriter.cpp:170-173,250-253)."""

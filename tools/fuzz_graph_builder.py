@@ -117,6 +117,17 @@ def adversarial_case(seed: int, length: int = 6000):
                     rr, _ = graph_builder._right_trim(v.ref, a)
                     if v.pos + len(rr) - 1 + K <= length:
                         ends.append(v.pos + len(rr) - 1)
+    if seed % 3 == 0:                                                           # soft-masked stretches and lower-case alleles
+        rb = bytearray(r)
+        for _ in range(int(rng.integers(1, 6))):
+            p = int(rng.integers(0, length - 300)); q = p + int(rng.integers(20, 300))
+            rb[p:q] = bytes(rb[p:q]).lower()
+        r = bytes(rb)
+        for v in out:
+            if rng.random() < 0.3:
+                v.ref = v.ref.lower()
+            if rng.random() < 0.3:
+                v.alts = [a.lower() for a in v.alts]
     return "chrF", r, out
 
 
