@@ -4,6 +4,7 @@
 // VariantFileParser's line reader, VariantFileParser.cpp:67-167: CHROM POS ID REF ALT and INFO ACO, `.vcf` or `.vcf.gz`).
 //
 //   btcluster <genome.fa> <candidates.vcf[.gz]> <out.btd> [--decoy <decoy.fa>] [--min-unit-variants N] [--max-allele-length N] [--copy-number-variant-threshold X]
+// --regions-prefix P also writes P.txt.gz, the reference's <out>_cluster_data/intercluster_regions.txt.gz.
 // With --min-unit-variants the inference units go to <out>_unit_<i>.btd (i = 1..), as the reference's <prefix>_unit_<i>/ directories.
 #include <zlib.h>
 
@@ -102,12 +103,13 @@ static std::vector<std::pair<std::string, std::vector<Candidate>>> readCandidate
 
 int main(int argc, char **argv) {
     try {
-        if (argc < 4) { std::fprintf(stderr, "usage: btcluster <genome.fa> <candidates.vcf[.gz]> <out.btd> [--decoy <decoy.fa>] [--min-unit-variants N] [--max-allele-length N] [--copy-number-variant-threshold X]\n"); return 2; }
+        if (argc < 4) { std::fprintf(stderr, "usage: btcluster <genome.fa> <candidates.vcf[.gz]> <out.btd> [--decoy <decoy.fa>] [--min-unit-variants N] [--regions-prefix P] [--max-allele-length N] [--copy-number-variant-threshold X]\n"); return 2; }
         btg::cluster::Options opt;
-        std::string decoy;
+        std::string decoy, regions_prefix;
         uint32_t min_unit = 0;          // 0: one unit
         for (int i = 4; i + 1 < argc; i += 2) {
             if (!std::strcmp(argv[i], "--decoy")) decoy = argv[i + 1];
+            else if (!std::strcmp(argv[i], "--regions-prefix")) regions_prefix = argv[i + 1];
             else if (!std::strcmp(argv[i], "--min-unit-variants")) min_unit = (uint32_t)std::stoul(argv[i + 1]);
             else if (!std::strcmp(argv[i], "--max-allele-length")) opt.max_allele_length = (uint32_t)std::stoul(argv[i + 1]);
             else if (!std::strcmp(argv[i], "--copy-number-variant-threshold")) opt.copy_number_variant_threshold = (float)std::stod(argv[i + 1]);
@@ -150,6 +152,16 @@ int main(int argc, char **argv) {
             for (auto &r : units.front().regions) { regions.push_back(r.contig); regions.push_back(r.decoy); regions.push_back(r.start); regions.push_back(r.end); }
             w.put("regions", 7, regions.data(), {(uint64_t)units.front().regions.size(), 4});
             n_var += g.var_pos.size(); n_cl += g.cluster_idx.size(); n_gr += g.group_nvar.size();
+        }
+        if (!regions_prefix.empty()) {
+            // <prefix>.txt.gz as VariantFileParser::sortInterclusterRegions + writeInterclusterRegions leave it (VariantFileParser.cpp:59-65,1181-1212):
+            // the same std::sort over the same sequence of regions with the same comparison, so regions of equal length come out in the same order
+            std::vector<btg::cluster::Region> regs = units.front().regions;
+            std::sort(regs.begin(), regs.end(), [](const btg::cluster::Region &a, const btg::cluster::Region &b) { return (a.end - a.start) > (b.end - b.start); });
+            gzFile out = gzopen((regions_prefix + ".txt.gz").c_str(), "wb");
+            if (!out) throw btg::Error("cannot write " + regions_prefix + ".txt.gz");
+            for (auto &r : regs) gzprintf(out, "%s\t%d\t%u\t%u\n", names[r.contig].c_str(), int(r.decoy), r.start, r.end);
+            gzclose(out);
         }
         std::fprintf(stderr, "btcluster: %zu variants as %zu clusters in %zu groups and %zu unit(s), %zu intercluster regions (%.3f s)\n", n_var, n_cl, n_gr, units.size(),
                      units.front().regions.size(), dt);

@@ -165,3 +165,20 @@ def test_inference_units_identical_to_reference(tmp_path):
     r = subprocess.run([str(_exe()), str(tmp_path / "genome.fa"), str(tmp_path / "c.vcf"), str(tmp_path / "o2.btd"), "--decoy", str(tmp_path / "decoy.fa"),
                         "--min-unit-variants", "1"], capture_output=True, text=True)
     assert r.returncode == 1 and "no usable variant" in r.stderr
+
+
+def test_intercluster_regions_file_equals_the_reference_file(tmp_path):
+    """btcluster --regions-prefix against <out>_cluster_data/intercluster_regions.txt.gz of the reference's cluster stage
+    (tests/golden/make_cluster_data_fixture.py): same lines in the same order, regions of equal length included."""
+    from tests.golden.make_fixtures import PIPE_WORKLOADS
+    w = PIPE_WORKLOADS["pipe_mixed_3s"]()
+    _write_fasta(tmp_path / "genome.fa", {w.chrom: w.reference})
+    _write_vcf(tmp_path / "c.vcf", {w.chrom: w.variants})
+    r = subprocess.run([str(_exe()), str(tmp_path / "genome.fa"), str(tmp_path / "c.vcf"), str(tmp_path / "out.btd"), "--regions-prefix", str(tmp_path / "intercluster_regions")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    want = gzip.open(GOLD / "cluster_data_mixed_3s.intercluster_regions.txt.gz").read()
+    got = gzip.open(tmp_path / "intercluster_regions.txt.gz").read()
+    lengths = [int(l.split(b"\t")[3]) - int(l.split(b"\t")[2]) for l in want.splitlines()]
+    assert len(set(lengths)) < len(lengths)          # the fixture does hold ties
+    assert got == want
