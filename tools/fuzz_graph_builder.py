@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--cases", type=int, default=40)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--write-golden", action="store_true")
+    ap.add_argument("--native", action="store_true", help="also run host/btcluster (include/btgpu_cluster.hpp) on every case")
     a = ap.parse_args()
     golden = {}
     n_bad = n_ref_abort = 0
@@ -188,6 +189,11 @@ def main():
             print(f"case {seed}: builder raised '{mine_err}' where the reference built {len(g['cluster_idx'])} clusters")
             continue
         bad = compare(g, regions, b)
+        if not bad and a.native:
+            nb = graph_builder.build_genome_graphs_native({chrom: ref}, {chrom: var})
+            nb["regions"] = nb["regions"][:, 2:]
+            bad = compare(g, regions, nb)
+            bad = bad and "native:" + bad
         gsz = np.diff(g["group_cluster_off"].astype(np.int64))
         stats["groups"] += len(gsz); stats["nested_groups"] += int((gsz > 1).sum()); stats["clusters"] += int(gsz.sum())
         stats["max_group"] = max(stats["max_group"], int(gsz.max())); stats["deps"] += len(g["group_edge_src"])
