@@ -9,3 +9,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
 ncu --set full --clock-control none --import-source on -k regex:k_table_add_sample -s 2 -c 1 -o gpurun_out/stream_full -f python tools/prof_stream.py
 BTG_NOISE_PHASES=1 BTG_GIBBS_TIMING=1 python tools/prof_real.py 0.33
 # 2 GPUs: gpurun --gpus 2 -- 'python -m pytest tests/test_gpu_shard.py -q; python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29571 tools/prof_shard.py 0.33'
+# staged in round 1 without a GPU: run these first in round 2
+#   python tools/e2e_check.py e2e_nested_2s > gpurun_out/e2e_nested.log 2>&1      # nested candidate set end to end
+#   python tools/e2e_check.py genome > gpurun_out/e2e_genome.log 2>&1             # several contigs + decoy + haploid chrX (driver_genome)
+#   host/btkmc makebloom <kmc prefix> 0.001                                       # makeBloom on the device
