@@ -147,10 +147,15 @@ class Inputs:
     spectra_dev: list = None
     blooms_dev: list = None
     region_buf_dev: object = None
+    native_builder: bool = False       # cluster construction through host/btcluster (same arrays, ~15x faster) instead of graph_builder.py
 
     def prepare(self):
         if self.graphs is None:
-            self.graphs = graph_builder.build_unit_graphs(self.chrom, self.reference, self.variants)
+            if self.native_builder:
+                self.graphs = graph_builder.build_genome_graphs_native({self.chrom: self.reference}, {self.chrom: self.variants})
+                self.graphs["regions"] = self.graphs["regions"][:, 2:]
+            else:
+                self.graphs = graph_builder.build_unit_graphs(self.chrom, self.reference, self.variants)
             self.regions = [(int(a), int(b)) for a, b in self.graphs["regions"]]
         return self
 

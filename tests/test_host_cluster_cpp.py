@@ -182,3 +182,17 @@ def test_intercluster_regions_file_equals_the_reference_file(tmp_path):
     lengths = [int(l.split(b"\t")[3]) - int(l.split(b"\t")[2]) for l in want.splitlines()]
     assert len(set(lengths)) < len(lengths)          # the fixture does hold ties
     assert got == want
+
+
+def test_driver_inputs_with_the_native_builder():
+    from bayestyper_b200 import driver
+    from tests.golden.make_fixtures import E2E_WORKLOADS
+    w = E2E_WORKLOADS["e2e_mixed_3s"]()
+    a = driver.Inputs(w.chrom, w.reference, w.variants, list(w.genders), spectra=None).prepare()
+    b = driver.Inputs(w.chrom, w.reference, w.variants, list(w.genders), spectra=None, native_builder=True).prepare()
+    assert a.regions == b.regions
+    for k, v in a.graphs.items():
+        if isinstance(v, list):
+            assert b.graphs[k] == v, k
+        else:
+            assert (np.asarray(b.graphs[k]) == np.asarray(v)).all(), k
