@@ -138,7 +138,8 @@ def _cluster_variant(var, pos, ends, flanks, group, merge_sets, k):
                     raise AssertionError("unreachable in the reference: an end position is never closer to an earlier flank than the start")
             elif pos < key < e:
                 overlap(cl)
-    # the reference keeps `second` in a std::set of pointers: allocation order, taken here as creation order
+    # the reference keeps `second` in a std::set of POINTERS and feeds the merge set in that order: with two or more extra clusters the
+    # surviving index depends on malloc's placement of the clusters; creation order is the deterministic choice made here
     second.sort(key=lambda c: c.idx)
     if first is None:
         cl = _Cluster(len(group), pos, ends[-1])

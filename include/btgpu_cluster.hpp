@@ -151,7 +151,8 @@ inline void clusterVariant(Variant &&var, uint32_t pos, const std::vector<uint32
         }
         ++it;
     }
-    // the reference keeps these in a std::set of pointers (allocation order): creation order is taken here
+    // the reference keeps these in a std::set of POINTERS and feeds the merge set in that order: with two or more extra clusters the
+    // surviving index depends on malloc's placement of the clusters; creation order is the deterministic choice made here
     std::sort(second.begin(), second.end(), [](Cluster *a, Cluster *b) { return a->idx < b->idx; });
     const uint32_t last_end = ends.back();
     if (!first) {
