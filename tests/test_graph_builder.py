@@ -69,15 +69,18 @@ int main() { std::unordered_set<unsigned> s; char op; unsigned k;
     assert [g.strip() for g in got] == want
 
 
-def test_adversarial_candidate_sets_identical_to_reference():
+@pytest.mark.parametrize("golden, min_cases, min_multi, min_largest", [("graphs_adversarial", 20, 20, 2), ("graphs_deep", 10, 10, 14)])
+def test_adversarial_candidate_sets_identical_to_reference(golden, min_cases, min_multi, min_largest):
     """Nested / overlapping / bridging deletions, multi-allelic variants with several reference spans, '*' alleles, copy-number
     insertions in front of tandem repeats, N runs, excluded variants: graphs, groups, dependency edges and intercluster regions
-    the REFERENCE built (tools/fuzz_graph_builder.py --write-golden, oracle-R) against graph_builder on the stored cases."""
+    the REFERENCE built (tools/fuzz_graph_builder.py --write-golden, oracle-R) against graph_builder on the stored cases.
+    graphs_deep: deletions nested four levels deep, groups of up to 20 clusters (the reference's unordered_map of clusters rehashes past
+    13 and 29 entries: stdhash_order has to follow)."""
     from bayestyper_b200 import synth
-    d = btd.read(GOLD / "graphs_adversarial.btd")
+    d = btd.read(GOLD / f"{golden}.btd")
     n = int(d["meta.n_cases"][0])
-    assert n >= 20
-    n_multi = 0
+    assert n >= min_cases
+    n_multi = largest = 0
     for c in range(n):
         ref = bytes(d[f"c{c}.reference"])
         alleles = bytes(d[f"c{c}.alleles"]).split(b"\n")
@@ -96,7 +99,8 @@ def test_adversarial_candidate_sets_identical_to_reference():
             assert set(b["v_refvar"][a0:a1].tolist()) == set(g["v_refvar"][a0:a1].tolist())
         assert sorted((int(x), int(y)) for x, y in b["regions"]) == sorted((int(x), int(y)) for x, y in d[f"c{c}.regions"])
         n_multi += int((np.diff(g["group_cluster_off"].astype(np.int64)) > 1).sum())
-    assert n_multi >= 20          # the stored cases do exercise groups of several clusters
+        largest = max(largest, int(np.diff(g["group_cluster_off"].astype(np.int64)).max()))
+    assert n_multi >= min_multi and largest >= min_largest          # the stored cases do exercise groups of several clusters
 
 
 def test_candidate_vcf_and_fasta_readers(tmp_path):

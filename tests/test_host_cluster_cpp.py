@@ -56,8 +56,9 @@ def _run(tmp_path, genome, cand, decoys=None, gz=False):
     return btd.read(tmp_path / "out.btd")
 
 
-def test_adversarial_candidate_sets_identical_to_reference(tmp_path):
-    d = btd.read(GOLD / "graphs_adversarial.btd")
+@pytest.mark.parametrize("golden", ["graphs_adversarial", "graphs_deep"])
+def test_adversarial_candidate_sets_identical_to_reference(tmp_path, golden):
+    d = btd.read(GOLD / f"{golden}.btd")
     for c in range(int(d["meta.n_cases"][0])):
         ref = bytes(d[f"c{c}.reference"])
         alleles = bytes(d[f"c{c}.alleles"]).split(b"\n")

@@ -131,6 +131,37 @@ def adversarial_case(seed: int, length: int = 6000):
     return "chrF", r, out
 
 
+def deep_case(seed: int, length: int = 12000):
+    """Deletions inside deletions inside deletions (up to four levels) with SNVs at the bottom: groups of 10+ clusters, which takes the
+    reference's unordered_map of clusters past its first rehash, and variants that overlap three or more clusters at once."""
+    rng = np.random.default_rng(seed)
+    r = synth.random_reference(length, seed + 100)
+    var = {}
+
+    def put(p, ref, alts):
+        if p not in var and 60 < p and p + len(ref) < length - 60:
+            var[p] = synth.Variant(p, ref, alts)
+
+    def fill(lo, hi, depth):
+        if hi - lo < 250 or depth > 3:
+            for p in rng.integers(lo + 60, max(lo + 61, hi - 60), size=int(rng.integers(0, 3))).tolist():
+                put(int(p), r[p:p + 1], [ACGT[(ACGT.index(r[p]) + 1) % 4:][:1]])
+            return
+        cuts = np.sort(rng.integers(lo + 70, hi - 70, size=2 * int(rng.integers(1, 4))))
+        for a, b in zip(cuts[0::2].tolist(), cuts[1::2].tolist()):
+            if b - a > 120:
+                put(a, r[a:a + 1 + b - a], [r[a:a + 1]])
+                fill(a, b, depth + 1)
+            else:
+                put(a, r[a:a + 1], [ACGT[(ACGT.index(r[a]) + 1) % 4:][:1]])
+
+    for _ in range(3):
+        a = int(rng.integers(200, length - 4000)); ln = int(rng.integers(1500, 3500))
+        put(a, r[a:a + 1 + ln], [r[a:a + 1]])
+        fill(a, a + ln, 1)
+    return "chrF", r, [var[p] for p in sorted(var)]
+
+
 def reference_graphs(chrom, reference, variants):
     w = synth.Workload("fuzz", chrom, reference, variants, np.zeros((1, len(variants), 2), np.int64), ["F"])
     km = synth.unique_kmers(synth.canonical_kmers(reference[:400].replace(b"N", b"A")))[0]
@@ -166,6 +197,9 @@ def main():
     ap.add_argument("--cases", type=int, default=40)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--write-golden", action="store_true")
+    ap.add_argument("--deep", action="store_true", help="deep-nesting cases (deep_case) instead of the mixed adversarial ones; a mismatch in "
+                    "cluster_idx / group_src there is the allocator-dependent overlap-set order of the reference (DESIGN.md §7)")
+    ap.add_argument("--golden-name", default="graphs_adversarial")
     ap.add_argument("--native", action="store_true", help="also run host/btcluster (include/btgpu_cluster.hpp) on every case")
     a = ap.parse_args()
     golden = {}
@@ -173,7 +207,7 @@ def main():
     stats = dict(groups=0, nested_groups=0, clusters=0, max_group=0, deps=0)
     for c in range(a.cases):
         seed = a.seed * 1000 + c
-        chrom, ref, var = adversarial_case(seed)
+        chrom, ref, var = (deep_case if a.deep else adversarial_case)(seed)
         g, regions, err = reference_graphs(chrom, ref, var)
         try:
             b = graph_builder.build_unit_graphs(chrom, ref, var)
@@ -212,8 +246,8 @@ def main():
     print(f"{a.cases} cases: {n_bad} mismatches, {n_ref_abort} reference aborts; reference built {stats}")
     if a.write_golden:
         golden["meta.n_cases"] = np.array([len([k for k in golden if k.endswith('.reference')])], np.uint32)
-        btd.write(ROOT / "tests" / "golden" / "graphs_adversarial.btd", golden)
-        print("wrote tests/golden/graphs_adversarial.btd", golden["meta.n_cases"][0], "cases")
+        btd.write(ROOT / "tests" / "golden" / f"{a.golden_name}.btd", golden)
+        print(f"wrote tests/golden/{a.golden_name}.btd", golden["meta.n_cases"][0], "cases")
     return 1 if n_bad else 0
 
 
