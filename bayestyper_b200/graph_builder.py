@@ -634,6 +634,8 @@ def build_genome_graphs_native(genome: dict, candidates: dict, decoys=(), k: int
         raise ValueError("the native builder is compiled for k = 55")
     build.build_host()
     exe = Path(build.ROOT) / "host" / "btcluster"
+    if not exe.exists():
+        raise RuntimeError("host/btcluster is not built (needs g++ and zlib); use build_genome_graphs")
     decoys = set(decoys)
     with tempfile.TemporaryDirectory() as td:
         td = Path(td)
