@@ -7,7 +7,11 @@
 //   key     = (random_seed, uint32(group_index + 1))
 //   counter = (n_lo, n_hi, cluster_idx_in_group, kind | chain << 8)
 // which keeps the reference's determinism contract (results independent of how groups are
-// scheduled or sharded).  The exact draw recipes are part of the parity contract with
+// scheduled or sharded).  n counts the blocks a stream consumes in sequence (n_hi = 0 in practice).  The one draw
+// that the model allows to be taken side by side — the diplotype of sample s in the t-th sampleDiplotypes call of
+// a genotyper since its stream was keyed (VariantClusterGenotyper.cpp:668-705: the loop over samples only adds up
+// haplotype counts) — owns its own block instead: counter = (t, 1 + s, cluster_idx, kind | chain << 8), so it
+// does not depend on the order in which the samples are visited (one thread walking them, or one lane each).  The exact draw recipes are part of the parity contract with
 // oracle/gibbs_oracle.cpp and are documented in DESIGN.md §RNG.
 #pragma once
 #include <cstdint>
@@ -24,9 +28,9 @@ namespace btg {
 #define BTG_OUTLINE 1
 #endif
 #if BTG_OUTLINE
-#define BTG_LEAF __device__ __noinline__
+#define BTG_LEAF static __device__ __noinline__
 #else
-#define BTG_LEAF __device__ __forceinline__
+#define BTG_LEAF static __device__ __forceinline__
 #endif
 BTG_LEAF double m_log(double x) { return log(x); }
 BTG_LEAF double m_exp(double x) { return exp(x); }
@@ -55,6 +59,7 @@ struct Philox {
     uint32_t c0, c1, c2, c3;  // counter
     uint32_t b0, b1, b2, b3;  // current block
     uint32_t pos;             // next word of the block (4 = exhausted)
+    uint32_t t_draw;          // sampleDiplotypes calls since the stream was keyed (addresses the per-sample draw blocks)
 
     __device__ __forceinline__ void init(uint32_t seed, uint64_t group_index, uint32_t cluster_idx, uint32_t kind, uint32_t chain = 0) {
         key0 = seed;
@@ -64,6 +69,13 @@ struct Philox {
         c3 = kind | (chain << 8);
         pos = 4;
         b0 = b1 = b2 = b3 = 0;
+        t_draw = 0;
+    }
+    // the diplotype draw of sample s in the current sampleDiplotypes call: own counter block (t_draw, 1 + s), words x0:x1
+    __device__ __forceinline__ double u01_draw(uint32_t s) const {
+        const uint4 b = philox4x32_10(t_draw, 1u + s, c2, c3, key0, key1);
+        const uint64_t x = ((uint64_t)b.x << 32) | b.y;
+        return ((double)(x >> 11) + 0.5) * (1.0 / 9007199254740992.0);
     }
     __device__ __forceinline__ void refill() {
         const uint4 b = philox4x32_10(c0, c1, c2, c3, key0, key1);
@@ -114,11 +126,11 @@ struct Philox {
     // persist / restore (noise modes run one iteration per launch)
     // A: anything indexable (plain pointer or a lane-interleaved accessor)
     template <class A> __device__ __forceinline__ void save(A p, uint32_t o) const {
-        p[o + 0] = c0; p[o + 1] = c1; p[o + 2] = b0; p[o + 3] = b1; p[o + 4] = b2; p[o + 5] = b3; p[o + 6] = pos; p[o + 7] = c3;
+        p[o + 0] = c0; p[o + 1] = c1; p[o + 2] = b0; p[o + 3] = b1; p[o + 4] = b2; p[o + 5] = b3; p[o + 6] = pos; p[o + 7] = c3; p[o + 8] = t_draw;
     }
     template <class A> __device__ __forceinline__ void load(A p, uint32_t o, uint32_t seed, uint64_t group_index, uint32_t cluster_idx) {
         key0 = seed; key1 = (uint32_t)(group_index + 1); c2 = cluster_idx;
-        c0 = p[o + 0]; c1 = p[o + 1]; b0 = p[o + 2]; b1 = p[o + 3]; b2 = p[o + 4]; b3 = p[o + 5]; pos = p[o + 6]; c3 = p[o + 7];
+        c0 = p[o + 0]; c1 = p[o + 1]; b0 = p[o + 2]; b1 = p[o + 3]; b2 = p[o + 4]; b3 = p[o + 5]; pos = p[o + 6]; c3 = p[o + 7]; t_draw = p[o + 8];
     }
 };
 

@@ -1,5 +1,12 @@
 // gibbs_oracle.cpp — "oracle-P": CPU restatement of the reference's per-cluster Gibbs
-// sampler, drawing from the SAME counter-based Philox streams as the CUDA kernels.
+// sampler.  ONE restatement, TWO draw sources (bto_set_rng_mode):
+//   mode 0 (Philox)  — the SAME counter-based streams as the CUDA kernels: the GPU must reproduce its tallies exactly;
+//   mode 1 (mt19937) — std::mt19937 + the libstdc++ distributions, seeds, running-stream semantics and unordered-container
+//                      walks of the reference: oracle-P must then reproduce the REFERENCE's
+//                      diplotype tallies / noise trace exactly (tests/test_ref_parity_exact.py, against oracle-R dumps).
+// The two modes share every line below except the bodies of struct Rng and the few `if (mt())` branches that
+// express the reference's stream ownership (one engine running through all chains) against this library's
+// per-chain / per-sample stream addressing.
 //
 // TEST INFRASTRUCTURE ONLY (see kmer_oracle.c).  It follows the reference function by
 // function (citations are file:line under /root/reference) with std containers, and is
@@ -30,8 +37,10 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <random>
 #include <set>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../include/btgpu.h"
@@ -40,10 +49,16 @@ namespace {
 
 const uint16_t NONE = 0xFFFF;  // Utils::ushort_overflow
 
+int g_rng_mode = 0;                          // 0 = Philox (the kernels' streams), 1 = mt19937 (the reference's)
+const uint64_t *g_group_index = nullptr;     // optional: index of every group of the descriptor in the FULL unit (seeds)
+inline bool mt() { return g_rng_mode == 1; }
+inline uint64_t groupIndex(const btg_gibbs_opts *o, uint32_t g) { return g_group_index ? g_group_index[g] : o->group_index_base + g; }
+
 // ------------------------------------------------------------------ Philox4x32-10
 struct Philox {
     uint32_t key[2], ctr[4], buf[4];
     int pos;
+    uint32_t t_draw;  // sampleDiplotypes calls since the stream was keyed
     void init(uint32_t seed, uint64_t group_index, uint32_t cluster_idx, uint32_t kind, uint32_t chain = 0) {
         key[0] = seed;
         key[1] = (uint32_t)(group_index + 1);
@@ -51,6 +66,22 @@ struct Philox {
         ctr[2] = cluster_idx;
         ctr[3] = kind | (chain << 8);
         pos = 4;
+        t_draw = 0;
+    }
+    static void block(uint32_t *c, uint32_t k0, uint32_t k1) {
+        uint32_t k[2] = {k0, k1};
+        for (int r = 0; r < 10; r++) {
+            round(c, k);
+            k[0] += 0x9E3779B9u;
+            k[1] += 0xBB67AE85u;
+        }
+    }
+    // the diplotype draw of sample s in the current sampleDiplotypes call owns the block (t_draw, 1 + s): words x0:x1
+    double u01_draw(uint32_t s) const {
+        uint32_t c[4] = {t_draw, 1u + s, ctr[2], ctr[3]};
+        block(c, key[0], key[1]);
+        uint64_t x = ((uint64_t)c[0] << 32) | c[1];
+        return ((double)(x >> 11) + 0.5) * (1.0 / 9007199254740992.0);
     }
     static void round(uint32_t *c, const uint32_t *k) {
         const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
@@ -102,6 +133,72 @@ struct Philox {
         for (size_t i = a.size(); i > 1; i--) std::swap(a[i - 1], a[uniform_int((uint32_t)i)]);
     }
 };
+
+// ------------------------------------------------------------------ one random stream, either draw source
+// mt19937 seeds: genotyper / sparsity estimator / frequency distribution r + (g+1)(chain+1) + c
+// (InferenceEngine.cpp:70, VariantClusterGroup.cpp:181, VariantClusterGenotyper.cpp:61,100,105 — three engines, one seed),
+// branch shuffle r + (g+1)(chain+1) (InferenceEngine.cpp:71,295), CountDistribution and the engine's own stream r
+// (CountDistribution.cpp:53, InferenceEngine.cpp:174).
+struct Rng {
+    Philox ph;
+    std::mt19937 eng;
+    std::gamma_distribution<double> gamma_dist;  // a member in the reference too (FrequencyDistribution.hpp, CountDistribution.hpp): its
+                                                 // normal_distribution keeps a spare value between calls
+    void init(uint32_t seed, uint64_t group_index, uint32_t cluster_idx, uint32_t kind, uint32_t chain = 0) {
+        ph.init(seed, group_index, cluster_idx, kind, chain);
+        if (mt()) {
+            uint32_t sd = seed;
+            if (kind <= 3) sd += (uint32_t)(group_index + 1) * (chain + 1);
+            if (kind <= 2) sd += cluster_idx;
+            eng = std::mt19937(sd);
+            gamma_dist = std::gamma_distribution<double>();
+        }
+    }
+    double canonical() { return std::generate_canonical<double, std::numeric_limits<double>::digits>(eng); }
+    double u01() { return mt() ? canonical() : ph.u01(); }
+    // LogDiscreteSampler::sample's uniform for sample s (DiscreteSampler.cpp:120-126): the reference takes it from the running engine
+    double u01_draw(uint32_t s) { return mt() ? canonical() : ph.u01_draw(s); }
+    void draws_done() { ph.t_draw++; }
+    bool bernoulli(float rate) {  // VariantClusterHaplotypes.cpp:118,124
+        if (mt()) { std::bernoulli_distribution d(rate); return d(eng); }
+        return ph.u01() < (double)rate;
+    }
+    uint32_t uniform_int(uint32_t n) {  // FrequencyDistribution.cpp:253-254
+        if (mt()) { std::uniform_int_distribution<> d(0, (int)n - 1); return (uint32_t)d(eng); }
+        return ph.uniform_int(n);
+    }
+    double gamma(double shape, double scale = 1) {  // FrequencyDistribution.cpp:79-84,236-248, CountDistribution.cpp:202-213
+        if (mt()) { gamma_dist.param(std::gamma_distribution<double>::param_type(shape, scale)); return gamma_dist(eng); }
+        return ph.gamma(shape) * scale;
+    }
+    template <class T> void shuffle(std::vector<T> &a) {
+        if (mt()) std::shuffle(a.begin(), a.end(), eng); else ph.shuffle(a);
+    }
+};
+
+// boost::hash<pair<ushort, ushort>> as oracle-R's shim defines it (oracle/ref_build/shim/boost/functional/hash.hpp): fixes the
+// walk order of diplotype_sampling_frequencies (VariantClusterGenotyper.hpp:112) in the mt19937 mode
+struct PairHash {
+    size_t operator()(const std::pair<uint16_t, uint16_t> &p) const {
+        size_t seed = 0;
+        seed ^= std::hash<uint16_t>()(p.first) + 0x9e3779b9 + (seed << 6) + (seed >> 2);
+        seed ^= std::hash<uint16_t>()(p.second) + 0x9e3779b9 + (seed << 6) + (seed >> 2);
+        return seed;
+    }
+};
+// walk of an unordered container: the reference's own order (same libstdc++, same history of insertions) in the mt19937 mode,
+// ascending otherwise (the kernels walk ascending indices)
+template <class Map> std::vector<typename Map::key_type> walkKeys(const Map &m) {
+    std::vector<typename Map::key_type> v;
+    for (auto &kv : m) v.push_back(kv.first);
+    if (!mt()) std::sort(v.begin(), v.end());
+    return v;
+}
+template <class Set> std::vector<typename Set::key_type> walk(const Set &s) {
+    std::vector<typename Set::key_type> v(s.begin(), s.end());
+    if (!mt()) std::sort(v.begin(), v.end());
+    return v;
+}
 
 // ------------------------------------------------------------------ Utils.hpp:81-124
 const double double_precision = std::numeric_limits<double>::epsilon();
@@ -209,7 +306,7 @@ struct Genotyper {
     uint32_t S, H, K, nvar;
     uint64_t row0, var0;
     const uint8_t *M;
-    Philox prng, prng_freq;
+    Rng prng, prng_freq;
     std::vector<uint32_t> uniq, multi, uniq_sub, multi_sub;
     // SparseFrequencyDistribution / FrequencyDistribution state
     bool sparse = false;
@@ -217,7 +314,7 @@ struct Genotyper {
     std::vector<uint32_t> obs;
     std::vector<double> freq;
     std::vector<uint8_t> nz;
-    std::set<uint32_t> plus, zero;
+    std::unordered_set<uint32_t> plus, zero;  // plus_count_indices, zero_count_indices (FrequencyDistribution.hpp)
     uint32_t num_hap_count = 0, num_missing_count = 0;
     std::map<std::pair<uint32_t, uint32_t>, std::vector<double> > simplex_cache;
     // VariantClusterGenotyper state
@@ -227,7 +324,7 @@ struct Genotyper {
     uint8_t *shared = nullptr;          // KmerCounts::multiplicities of the group-shared k-mer records [id][S]
     uint64_t hap0 = 0;                  // index of this cluster's first haplotype in hap_nested_off
     std::vector<Dipl> dipl;
-    std::map<Dipl, std::vector<uint32_t> > tally;
+    std::unordered_map<Dipl, std::vector<uint32_t>, PairHash> tally;  // diplotype_sampling_frequencies
     struct StatsCache { bool update = true; std::vector<KStats> h1, h2; };
     std::vector<StatsCache> stats_cache;
     std::vector<std::vector<AlleleKStats> > allele_stats;  // [var][sample]
@@ -286,7 +383,7 @@ struct Genotyper {
         allele_stats.clear();
         for (uint32_t v = 0; v < nvar; v++) allele_stats.emplace_back(S, AlleleKStats(nalleles(v)));
         // SparsityEstimator::estimateMinimumColumnCover (SparsityEstimator.cpp:41-90), own stream (kind 1)
-        Philox sp;
+        Rng sp;
         sp.init(o->random_seed, group_index, d->cluster_idx[c], 1, chain);
         std::vector<uint8_t> uncovered(K);
         uint32_t n_unc = 0;
@@ -340,12 +437,12 @@ struct Genotyper {
     void reset() {
         uniq_sub.clear();
         multi_sub.clear();
-        const double rate = (double)o->kmer_subsampling_rate;
+        const float rate = o->kmer_subsampling_rate;
         std::vector<uint32_t> cnt((size_t)H * nvar, 0);
         prng.shuffle(uniq);
-        for (auto k : uniq) if (prng.u01() < rate) if (!isMaxHapVarKmer(cnt, k)) uniq_sub.push_back(k);
+        for (auto k : uniq) if (prng.bernoulli(rate)) if (!isMaxHapVarKmer(cnt, k)) uniq_sub.push_back(k);
         prng.shuffle(multi);
-        for (auto k : multi) if (prng.u01() < rate) if (!isMaxHapVarKmer(cnt, k)) multi_sub.push_back(k);
+        for (auto k : multi) if (prng.bernoulli(rate)) if (!isMaxHapVarKmer(cnt, k)) multi_sub.push_back(k);
         sample_multi.assign(multi_sub.size() * (size_t)S, 0);
         for (auto &sc : stats_cache) sc.update = true;
         use_multi = false;
@@ -431,7 +528,7 @@ struct Genotyper {
             outcomes.emplace_back(NONE, NONE);
         }
         // LogDiscreteSampler::sample + DiscreteSampler::search (DiscreteSampler.cpp:120-126,68-87)
-        double x = std::log(prng.u01()) + cum.back();
+        double x = std::log(prng.u01_draw(s)) + cum.back();
         uint32_t idx = 0;
         if (cum.size() > 1) { idx = (uint32_t)(std::upper_bound(cum.begin(), cum.end(), x) - cum.begin()); assert(idx < cum.size()); }
         dipl[s] = outcomes[idx];
@@ -515,6 +612,7 @@ struct Genotyper {
                 it->second[s]++;
             }
         }
+        prng.draws_done();
         if (collect) updateAlleleKmerStats(nested);
         use_multi = !multi_sub.empty();
     }
@@ -561,20 +659,18 @@ struct Genotyper {
                 const std::vector<double> &pv = it->second;
                 uint32_t simplex_size = (uint32_t)(std::upper_bound(pv.begin(), pv.end(), prng_freq.u01()) - pv.begin()) + (uint32_t)plus.size();
                 double norm = 0;
-                for (auto h : plus) { freq[h] = prng_freq.gamma(obs[h] + 1.0); norm += freq[h]; nz[h] = 1; }  // ascending haplotype index
+                for (auto h : walk(plus)) { freq[h] = prng_freq.gamma(obs[h] + 1.0); norm += freq[h]; nz[h] = 1; }
                 while (plus.size() < simplex_size) {
                     uint32_t posn = prng_freq.uniform_int((uint32_t)zero.size());
-                    auto zit = zero.begin();
-                    std::advance(zit, posn);  // posn-th zero-count haplotype in ascending index order
-                    uint32_t h = *zit;
+                    uint32_t h = walk(zero)[posn];  // posn-th zero-count haplotype of the walk
                     freq[h] = prng_freq.gamma(1.0);
                     norm += freq[h];
                     nz[h] = 1;
                     plus.insert(h);
-                    zero.erase(zit);
+                    zero.erase(h);
                 }
                 for (auto h : zero) { freq[h] = 0; nz[h] = 0; obs[h] = 0; }
-                for (auto h : plus) { freq[h] /= norm; zero.insert(h); obs[h] = 0; }
+                for (auto h : walk(plus)) { freq[h] /= norm; zero.insert(h); obs[h] = 0; }
                 plus.clear();
             }
         }
@@ -603,7 +699,7 @@ struct Group {
         c0 = d->group_cluster_off[g];
         const uint32_t n = (uint32_t)(d->group_cluster_off[g + 1] - c0);
         gts.resize(n);
-        for (uint32_t i = 0; i < n; i++) gts[i].init(d, o, (uint32_t)(c0 + i), o->group_index_base + g, chain, shared, hap_start[c0 + i]);
+        for (uint32_t i = 0; i < n; i++) gts[i].init(d, o, (uint32_t)(c0 + i), groupIndex(o, g), chain, shared, hap_start[c0 + i]);
         src.assign(d->group_src + d->group_src_off[g], d->group_src + d->group_src_off[g + 1]);
         out_edges.assign(n, std::vector<uint32_t>());
         for (uint64_t e = d->group_edge_off[g]; e < d->group_edge_off[g + 1]; e++) out_edges[d->group_edge_src[e]].push_back(d->group_edge_dst[e]);
@@ -611,8 +707,8 @@ struct Group {
     void reset() { for (auto &gt : gts) gt.reset(); }  // VariantClusterGroup::initGenotyper (…Group.cpp:175-186)
     // VariantClusterGroup::shuffleBranchOrdering (…Group.cpp:208-218): cumulative, own stream (kind 3)
     void shuffleBranchOrdering(const btg_gibbs_opts *o, uint32_t chain) {
-        Philox br;
-        br.init(o->random_seed, o->group_index_base + g, 0, 3, chain);
+        Rng br;
+        br.init(o->random_seed, groupIndex(o, g), 0, 3, chain);
         br.shuffle(src);
         for (auto &e : out_edges) br.shuffle(e);
     }
@@ -678,7 +774,8 @@ void summarise(const Genotyper &g, const uint8_t *ploidy, btg_genotype_result *o
             uint32_t n_it = 0;
             std::vector<Dipl> best;
             float best_p = 0;
-            for (auto &kv : g.tally) {
+            for (auto &key : walkKeys(g.tally)) {  // mt19937 mode: the reference's walk of diplotype_sampling_frequencies (…Genotyper.cpp:277)
+                const auto &kv = *g.tally.find(key);
                 const uint32_t cnt = kv.second[s];
                 if (cnt == 0) continue;
                 Dipl ge(NONE, NONE);
@@ -789,6 +886,10 @@ void bto_nb_moments_to_parameters(double mean, double var, uint32_t multiplicity
     *size_out = std::pow(mean, 2) / (var - mean) / multiplicity;
 }
 
+void bto_set_rng_mode(int mode) { g_rng_mode = mode; }
+// index of every group of the descriptors passed from now on in the full unit (NULL: group_index_base + position)
+void bto_set_group_indices(const uint64_t *idx) { g_group_index = idx; }
+
 // InferenceEngine::estimateGenotypesCallback (InferenceEngine.cpp:278-333) for every group of the unit.
 // tally_out (optional): per cluster dense [(H+1)(H+2)/2][S] tallies concatenated (tally_off[c]).
 int bto_estimate_genotypes(const btg_unit_desc *d, void *cd, const btg_gibbs_opts *o, btg_genotype_result *out,
@@ -801,13 +902,13 @@ int bto_estimate_genotypes(const btg_unit_desc *d, void *cd, const btg_gibbs_opt
         Group grp;
         grp.init(d, o, g, 0, shared.data(), hap_start);  // genotypers are constructed once and persist across chains
         for (uint32_t chain = 0; chain < o->n_chains; chain++) {
-            if (grp.gts.size() == 1) {
+            if (!mt() && grp.gts.size() == 1) {
                 // stream contract of the default mode for single-cluster groups (csrc/gibbs.cu, k_estimate_genotypes): chains are
                 // independent — each chain re-keys the genotyper's two streams with its index and shuffles the original k-mer
                 // order.  (The reference keeps one mt19937 running through all chains, InferenceEngine.cpp:292-306.)
                 Genotyper &gt = grp.gts[0];
-                gt.prng.init(o->random_seed, o->group_index_base + g, d->cluster_idx[gt.c], 0, chain);
-                gt.prng_freq.init(o->random_seed, o->group_index_base + g, d->cluster_idx[gt.c], 2, chain);
+                gt.prng.init(o->random_seed, groupIndex(o, g), d->cluster_idx[gt.c], 0, chain);
+                gt.prng_freq.init(o->random_seed, groupIndex(o, g), d->cluster_idx[gt.c], 2, chain);
                 gt.uniq.assign(d->uniq_idx + d->cl_uniq_off[gt.c], d->uniq_idx + d->cl_uniq_off[gt.c + 1]);
             }
             grp.reset();
@@ -830,6 +931,24 @@ int bto_estimate_genotypes(const btg_unit_desc *d, void *cd, const btg_gibbs_opt
     return 0;
 }
 
+// CountDistribution::sampleNoiseParameters (CountDistribution.cpp:173-200): the reference evaluates both parameters in FLOAT
+// (pair<float,float> prior combined with ulong)
+static void sampleNoiseParameters(CountTables &T, Rng &noise_prng, const std::vector<uint64_t> &hist) {
+    for (uint32_t s = 0; s < T.S; s++) {
+        uint64_t n_obs = 0, sum = 0;
+        for (uint32_t i = 0; i < 256; i++) { n_obs += hist[(size_t)s * 256 + i]; sum += i * hist[(size_t)s * 256 + i]; }
+        const float shape_f = (float)T.prior_shape + (float)sum;
+        const float scale_f = (float)T.prior_scale / ((float)n_obs * (float)T.prior_scale + 1);
+        T.noise_rates[s] = noise_prng.gamma(shape_f, scale_f);
+    }
+    T.updateNoise();
+}
+// CountDistribution::resetNoiseRates (CountDistribution.cpp:163-171)
+static void resetNoiseRates(CountTables &T, Rng &noise_prng) {
+    for (uint32_t s = 0; s < T.S; s++) T.noise_rates[s] = noise_prng.gamma((float)T.prior_shape, (float)T.prior_scale);
+    T.updateNoise();
+}
+
 // InferenceEngine::estimateNoise (InferenceEngine.cpp:135-276)
 int bto_estimate_noise(const btg_unit_desc *d, void *cd, const btg_gibbs_opts *o, double *trace_out) {
     CountTables &T = *asTables(cd);
@@ -843,17 +962,14 @@ int bto_estimate_noise(const btg_unit_desc *d, void *cd, const btg_gibbs_opts *o
         for (uint64_t c = d->group_cluster_off[g]; c < d->group_cluster_off[g + 1]; c++) n += (uint32_t)(d->cl_var_off[c + 1] - d->cl_var_off[c]);
         return n;
     };
-    Philox engine, noise_prng;
+    Rng engine, noise_prng;
     engine.init(o->random_seed, (uint64_t)-1, 0, 5);  // key1 = 0: InferenceEngine's own stream (InferenceEngine.cpp:174)
     noise_prng.init(o->random_seed, (uint64_t)-1, 0, 4);  // CountDistribution::prng (CountDistribution.cpp:53)
-    auto sampleGamma = [&](double shape, double scale) { return noise_prng.gamma(shape) * scale; };
-    auto resetNoiseRates = [&]() {  // CountDistribution::resetNoiseRates (CountDistribution.cpp:163-171)
-        for (uint32_t s = 0; s < S; s++) T.noise_rates[s] = sampleGamma(T.prior_shape, T.prior_scale);
-        T.updateNoise();
-    };
     // Stream contract (csrc/gibbs.cu, estimate_noise_concurrent): the chains of estimateNoise are independent — chain c draws its noise
-    // rates from its own stream (kind 4, chain c + 1), starting with the prior draw that the reference takes from the running
-    // CountDistribution stream in the ctor / at the end of the previous chain (CountDistribution.cpp:62, InferenceEngine.cpp:253).
+    // rates from its own stream (kind 4, chain c + 1), starting with the prior draw.  The reference takes that draw from the running
+    // CountDistribution stream: in the ctor for the first chain, at the end of the previous chain afterwards (CountDistribution.cpp:62,
+    // InferenceEngine.cpp:253).
+    if (mt()) resetNoiseRates(T, noise_prng);
     std::vector<double> mean_rates(S, 0);
     size_t row = 0;
     auto trace = [&](double chain, double it) {
@@ -868,11 +984,13 @@ int bto_estimate_noise(const btg_unit_desc *d, void *cd, const btg_gibbs_opts *o
         uint32_t end = 0, nv = 0;
         while (nv < noise_variants_batch_size && end < noise_groups.size()) { nv += groupVariants(noise_groups[end]); end++; }
         std::sort(noise_groups.begin(), noise_groups.begin() + end);
-        noise_prng.init(o->random_seed, (uint64_t)-1, 0, 4, chain + 1);
-        resetNoiseRates();
+        if (!mt()) {
+            noise_prng.init(o->random_seed, (uint64_t)-1, 0, 4, chain + 1);
+            resetNoiseRates(T, noise_prng);
+        }
         std::vector<Genotyper> gts(end);
         for (uint32_t i = 0; i < end; i++) {  // initGenotypersCallback (InferenceEngine.cpp:60-75): fresh genotypers per chain
-            gts[i].init(d, o, (uint32_t)d->group_cluster_off[noise_groups[i]], o->group_index_base + noise_groups[i], chain + 1);
+            gts[i].init(d, o, (uint32_t)d->group_cluster_off[noise_groups[i]], groupIndex(o, noise_groups[i]), mt() ? chain : chain + 1);
             gts[i].reset();
         }
         trace(chain + 1, 0);
@@ -885,18 +1003,11 @@ int bto_estimate_noise(const btg_unit_desc *d, void *cd, const btg_gibbs_opts *o
                 gts[i].getNoiseCounts(hist);
                 gts[i].clearCache();  // clearGenotyperCache
             }
-            for (uint32_t s = 0; s < S; s++) {  // CountDistribution::sampleNoiseParameters (CountDistribution.cpp:173-200)
-                uint64_t n_obs = 0, sum = 0;
-                for (uint32_t i = 0; i < 256; i++) { n_obs += hist[(size_t)s * 256 + i]; sum += i * hist[(size_t)s * 256 + i]; }
-                // the reference evaluates both parameters in FLOAT (pair<float,float> prior combined with ulong)
-                const float shape_f = (float)T.prior_shape + (float)sum;
-                const float scale_f = (float)T.prior_scale / ((float)n_obs * (float)T.prior_scale + 1);
-                T.noise_rates[s] = sampleGamma(shape_f, scale_f);
-            }
-            T.updateNoise();
+            sampleNoiseParameters(T, noise_prng, hist);
             trace(chain + 1, it);
             if (o->gibbs_burn_in < it) for (uint32_t s = 0; s < S; s++) mean_rates[s] += T.noise_rates[s];
         }
+        if (mt()) resetNoiseRates(T, noise_prng);  // InferenceEngine.cpp:253
     }
     for (uint32_t s = 0; s < S; s++) mean_rates[s] /= (double)o->gibbs_samples * o->n_chains;
     T.noise_rates = mean_rates;
@@ -912,16 +1023,11 @@ int bto_estimate_noise(const btg_unit_desc *d, void *cd, const btg_gibbs_opts *o
 int bto_estimate_noise_and_genotypes(const btg_unit_desc *d, void *cd, const btg_gibbs_opts *o, btg_genotype_result *out, double *trace_out) {
     CountTables &T = *asTables(cd);
     const uint32_t S = d->n_samples;
-    for (uint32_t g = 0; g < d->n_groups; g++)
-        if (d->group_cluster_off[g + 1] - d->group_cluster_off[g] != 1) return -1;
-    Philox noise_prng;
+    const std::vector<uint64_t> hap_start = haplotypeStarts(d);
+    std::vector<uint8_t> shared(sharedRecords(d) * (size_t)S, 0);
+    Rng noise_prng;
     noise_prng.init(o->random_seed, (uint64_t)-1, 0, 4);
-    auto sampleGamma = [&](double shape, double scale) { return noise_prng.gamma(shape) * scale; };
-    auto resetNoiseRates = [&]() {
-        for (uint32_t s = 0; s < S; s++) T.noise_rates[s] = sampleGamma(T.prior_shape, T.prior_scale);
-        T.updateNoise();
-    };
-    resetNoiseRates();  // CountDistribution ctor
+    resetNoiseRates(T, noise_prng);  // CountDistribution ctor
     size_t row = 0;
     auto trace = [&](double chain, double it) {
         if (!trace_out) return;
@@ -930,35 +1036,28 @@ int bto_estimate_noise_and_genotypes(const btg_unit_desc *d, void *cd, const btg
         for (uint32_t s = 0; s < S; s++) r[2 + s] = T.noise_rates[s];
         row++;
     };
-    std::vector<Genotyper> gts(d->n_groups);
+    std::vector<Group> grps(d->n_groups);
     for (uint32_t chain = 0; chain < o->n_chains; chain++) {
-        for (uint32_t g = 0; g < d->n_groups; g++) {
-            if (chain == 0) gts[g].init(d, o, (uint32_t)d->group_cluster_off[g], o->group_index_base + g, 0);
-            gts[g].reset();
+        for (uint32_t g = 0; g < d->n_groups; g++) {  // initGenotypersCallback
+            if (chain == 0) grps[g].init(d, o, g, 0, shared.data(), hap_start);
+            grps[g].reset();
+            grps[g].shuffleBranchOrdering(o, chain);
         }
         trace(chain + 1, 0);
         for (uint32_t it = 1; it <= (uint32_t)o->gibbs_burn_in + o->gibbs_samples; it++) {
             std::vector<uint64_t> hist((size_t)S * 256, 0);
-            for (uint32_t g = 0; g < d->n_groups; g++) {
-                const uint8_t *ploidy = d->group_ploidy + (size_t)g * S;
-                gts[g].sampleDiplotypes(T, ploidy, it > o->gibbs_burn_in);
-                gts[g].sampleHaplotypeFrequencies();
-                gts[g].getNoiseCounts(hist);
-                gts[g].clearCache();
+            for (uint32_t g = 0; g < d->n_groups; g++) {  // sampleGenotypesCallback
+                grps[g].estimateGenotypes(T, it > o->gibbs_burn_in);
+                for (auto &gt : grps[g].gts) gt.getNoiseCounts(hist);
+                for (auto &gt : grps[g].gts) gt.clearCache();
             }
-            for (uint32_t s = 0; s < S; s++) {
-                uint64_t n_obs = 0, sum = 0;
-                for (uint32_t i = 0; i < 256; i++) { n_obs += hist[(size_t)s * 256 + i]; sum += i * hist[(size_t)s * 256 + i]; }
-                const float shape_f = (float)T.prior_shape + (float)sum;
-                const float scale_f = (float)T.prior_scale / ((float)n_obs * (float)T.prior_scale + 1);
-                T.noise_rates[s] = sampleGamma(shape_f, scale_f);
-            }
-            T.updateNoise();
+            sampleNoiseParameters(T, noise_prng, hist);
             trace(chain + 1, it);
         }
-        resetNoiseRates();
+        resetNoiseRates(T, noise_prng);
     }
-    for (uint32_t g = 0; g < d->n_groups; g++) summarise(gts[g], d->group_ploidy + (size_t)g * S, out);
+    for (uint32_t g = 0; g < d->n_groups; g++)
+        for (auto &gt : grps[g].gts) summarise(gt, d->group_ploidy + (size_t)g * S, out);
     return 0;
 }
 

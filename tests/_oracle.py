@@ -119,7 +119,28 @@ def _bind_gibbs(L):
     L.bto_estimate_genotypes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.bto_estimate_noise.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.bto_estimate_noise_and_genotypes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.bto_set_rng_mode.argtypes = [C.c_int]
+    L.bto_set_group_indices.argtypes = [C.c_void_p]
     L._gibbs_bound = True
+
+
+class reference_streams:
+    """`with reference_streams(group_indices):` — oracle-P draws from std::mt19937 + libstdc++ distributions with the reference's
+    seeds (gibbs_oracle.cpp mode 1); group_indices = index of every group of the unit in the reference's full unit."""
+
+    def __init__(self, group_indices=None):
+        self.idx = None if group_indices is None else np.ascontiguousarray(group_indices, np.uint64)
+
+    def __enter__(self):
+        L = load(); _bind_gibbs(L)
+        L.bto_set_rng_mode(1)
+        L.bto_set_group_indices(self.idx.ctypes.data if self.idx is not None else None)
+        return self
+
+    def __exit__(self, *a):
+        L = load()
+        L.bto_set_rng_mode(0)
+        L.bto_set_group_indices(None)
 
 
 class OracleCountDist:

@@ -22,7 +22,7 @@ from bayestyper_b200 import btd, synth, unit as U, vcfio  # noqa: E402
 BTREF = ROOT / "oracle" / "_ref" / "btref"
 
 
-def make(name, workload, n_groups, seed=20190401, n_errors=20000, extra_args=()):
+def make(name, workload, n_groups, seed=20190401, n_errors=20000, extra_args=(), store_tables=True):
     with tempfile.TemporaryDirectory() as td:
         wd = synth.write_workdir(workload, td, n_errors=n_errors)
         subprocess.check_call([str(BTREF), "run", "--workdir", str(wd), "--threads", "8", "--seed", str(seed), "--dump-graphs", "--dump-haps", *extra_args],
@@ -71,7 +71,8 @@ def make(name, workload, n_groups, seed=20190401, n_errors=20000, extra_args=())
                     if k.upper() in sr:
                         ref[k][a0:a0 + nA] = np.array(sr[k.upper()], ref[k].dtype)
         pack = {"unit." + k: v for k, v in sub.a.items()}
-        pack.update({"tab." + k: v for k, v in t.items()})
+        # the two log-pmf caches are 0.5 MB per sample: fixtures with many samples keep the parameters only (the caches are pinned by the others)
+        pack.update({"tab." + k: v for k, v in t.items() if store_tables or k not in ("genomic_log_pmf", "noise_log_pmf")})
         pack.update({"ref." + k: v for k, v in ref.items()})
         pack["meta.n_samples"] = np.array([S], np.uint32)
         pack["meta.groups"] = keep.astype(np.uint32)            # indices in the full unit (seed derivation)
@@ -199,6 +200,13 @@ if __name__ == "__main__":
         _sys.exit(0)
     if len(_sys.argv) > 1 and _sys.argv[1] == "joint":
         make("gibbs_joint_2s", synth.small_mixed(260, 24_000, 2, seed=83), 400, extra_args=("--noise-genotyping",))
+        _sys.exit(0)
+    if len(_sys.argv) > 1 and _sys.argv[1] == "exact":
+        # fixtures that hold EVERY group of the reference run: the lock-step modes can be reproduced row for row (tests/test_ref_parity_exact.py)
+        make("gibbs_full_2s", synth.small_mixed(150, 15_000, 2, seed=91), 10**6, n_errors=4000)
+        make("gibbs_joint_30s", synth.small_mixed(110, 11_000, 30, seed=97), 10**6, n_errors=3000, extra_args=("--noise-genotyping",), store_tables=False)
+        make("gibbs_joint_nested_2s", synth.nested_sv(8, 30_000, 2, seed=15, n_background=60, sv_len=(150, 500), repeat_frac=0.6), 10**6, n_errors=4000,
+             extra_args=("--noise-genotyping",))
         _sys.exit(0)
     if len(_sys.argv) > 1 and _sys.argv[1] == "nested-kmer":
         make_pipeline("pipe_nested_2s", PIPE_WORKLOADS["pipe_nested_2s"]())

@@ -96,5 +96,8 @@ def main_genome():
 
 
 if __name__ == "__main__":
+    from bayestyper_b200 import capi
+    _lib = capi.load()
+    capi.check(_lib.btg_init(0), _lib)
     name = sys.argv[1] if len(sys.argv) > 1 else "e2e_nested_2s"
     sys.exit(main_genome() if name == "genome" else main(name))
