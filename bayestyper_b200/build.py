@@ -28,7 +28,7 @@ NVCC_FLAGS = [
 # The Gibbs path restates the reference's f32/f64 expressions; the reference is built without FMA contraction
 # (x86-64 baseline), so the sampler is too: a contracted a*b+c rounds once instead of twice and shifts e.g. the
 # float-typed Gamma parameters of CountDistribution.cpp:182 by one ulp.
-PER_FILE_FLAGS = {"gibbs.cu": ["-fmad=false"]}
+PER_FILE_FLAGS = {"gibbs.cu": ["-fmad=false"], "gibbs_wide.cu": ["-fmad=false"]}
 
 
 def _newer(target: Path, sources) -> bool:

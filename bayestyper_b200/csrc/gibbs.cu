@@ -739,6 +739,7 @@ btg_unit *btg_unit_upload_dev(const btg_unit_desc *d, const btg_unit_desc *dev, 
     const uint32_t n_pos = (uint32_t)ext_cluster.size();
     // one arena slot per warp of the position order, sized by the largest cluster in it (wide layout: one slot per position)
     const uint32_t per_slot = du.wide ? 1u : 32u;
+    const uint64_t cache_cap = getenv("BTG_WIDE_CACHE_CAP") ? strtoull(getenv("BTG_WIDE_CACHE_CAP"), nullptr, 10) : kWideCacheCap;  // tests lower it
     const uint32_t n_slots = (n_pos + per_slot - 1) / per_slot;
     u->h_slots.assign(n_slots ? n_slots : 1, SlotLayout{});
     uint64_t f64_total = 0, u32_total = 0, u8_total = 0;
@@ -750,9 +751,11 @@ btg_unit *btg_unit_upload_dev(const btg_unit_desc *d, const btg_unit_desc *dev, 
             SL.H = std::max(SL.H, D.H); SL.K = std::max(SL.K, D.K); SL.nvar = std::max(SL.nvar, D.nv);
             SL.n_uniq = std::max(SL.n_uniq, D.nu); SL.n_alleles = std::max(SL.n_alleles, D.nal); SL.Dall = std::max(SL.Dall, D.Dall);
             SL.n_multi = std::max(SL.n_multi, D.nm);
+            // a unit with nested groups runs its lock-step joint mode on the warp-per-group kernel (lane = sample) whatever the layout
+            if (du.wide || du.n_regular < C) SL.cum_rows = 1;
         }
-        const ArenaSizes a = arena_sizes(S, SL.H, SL.K, SL.nvar, SL.n_uniq, SL.n_alleles, SL.Dall, SL.n_multi, du.wide);
-        SL.has_cache = arena_has_cache(S, SL.Dall, SL.n_multi, du.wide);
+        const ArenaSizes a = arena_sizes(S, SL.H, SL.K, SL.nvar, SL.n_uniq, SL.n_alleles, SL.Dall, SL.n_multi, du.wide, cache_cap, SL.cum_rows);
+        SL.has_cache = arena_has_cache(S, SL.Dall, SL.n_multi, du.wide, cache_cap);
         SL.f64_off = f64_total; SL.u32_off = u32_total; SL.u8_off = u8_total;
         f64_total += a.f64 * per_slot; u32_total += a.u32 * per_slot; u8_total += a.u8 * per_slot;
     }
@@ -943,6 +946,32 @@ int btg_unit_cluster_tally(const btg_unit *u, uint32_t cluster, uint32_t *tally_
     return BTG_OK;
 }
 
+// large clusters of the lock-step chains: their cache fill is spread over the grid as fill tasks.  One-thread kernel (gibbs.cu): the
+// clusters with a dense tile, cost PER SAMPLE (a one-thread cluster walks its samples in turn).  Warp kernel (gibbs_wide.cu, lane =
+// sample): the same per-lane cost bound, for single-cluster groups whose slot holds the dense caches.
+static bool lockstep_is_big(const btg_unit *u, uint32_t c, bool warp_kernel) {
+    const uint32_t S = u->du.S;
+    if (!(u->h_fill_cost[c] > (uint64_t)kBigFillCost * S)) return false;
+    if (!warp_kernel) return true;
+    const uint32_t g = u->h_layout[c].group;
+    if (u->h_group_cluster_off[g + 1] - u->h_group_cluster_off[g] != 1) return false;
+    return u->h_slots[u->du.wide ? u->h_layout[c].pos : u->h_layout[c].pos >> 5].has_cache != 0;
+}
+// fill tasks of one large cluster: (index in sel, part, parts).  One-thread kernel: one warp per 32 cache entries (S x diplotypes,
+// upper bound; 4 with >= 16 k-mers per entry), at most 64.  Warp kernel: a task takes every parts-th PAIR of live haplotypes for
+// all samples at once (lane = sample): one part per two pairs of the full enumeration, at most 64.
+static void lockstep_fill_tasks(const btg_unit *u, uint32_t c, uint32_t sel_idx, bool warp_kernel, std::vector<uint32_t> &tasks) {
+    const uint64_t H = u->h_nhap[c], pairs = H * (H + 1) / 2, entries = (uint64_t)u->du.S * pairs;
+    uint32_t parts;
+    if (warp_kernel) {
+        parts = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, (pairs + 1) / 2));
+    } else {
+        const bool by_terms = (u->h_fill_cost[c] / std::max<uint64_t>(1, entries)) >= 16;
+        parts = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, by_terms ? (entries + 3) / 4 : (entries + 31) / 32));
+    }
+    for (uint32_t p = 0; p < parts; p++) { tasks.push_back(sel_idx); tasks.push_back(p); tasks.push_back(parts); }
+}
+
 static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, double *trace_out, int joint);
 static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, double *trace_out);
 
@@ -1077,13 +1106,13 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
             return (uint32_t)n;
         };
         const uint32_t noise_variants_batch_size = 100000;  // InferenceEngine.cpp:50
-        auto is_big = [&](uint32_t c) { return !u->du.wide && u->h_fill_cost[c] > (uint64_t)kBigFillCost * S; };  // the clusters with a dense tile: cost PER SAMPLE (a one-thread cluster walks its samples in turn)
+        auto is_big = [&](uint32_t c) { return lockstep_is_big(u, c, u->du.wide); };
         // upper bounds per chain: every local single-cluster group selected; every large cluster with its maximal number of fill tasks
         for (uint32_t g = 0; g < G; g++) {
             if (u->h_group_cluster_off[g + 1] - u->h_group_cluster_off[g] != 1) continue;
             const uint32_t c = (uint32_t)u->h_group_cluster_off[g];
             sel_cap++;
-            if (is_big(c)) task_cap += 3 * (size_t)std::min<uint64_t>(64, std::max<uint64_t>(1, ((uint64_t)S * ((uint64_t)u->h_nhap[c] * (u->h_nhap[c] + 1) / 2) + 3) / 4));
+            if (is_big(c)) task_cap += 3 * 64;
         }
         d_sel = (uint32_t *)dalloc(std::max<size_t>(1, sel_cap) * nc * 4);
         d_tasks = (uint32_t *)dalloc(std::max<size_t>(1, task_cap) * nc * 4);
@@ -1105,13 +1134,7 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
             uint32_t n_big = 0;
             while (n_big < sel.size() && is_big(sel[n_big])) n_big++;
             n_bigs[b] = n_big;
-            for (uint32_t i = 0; i < n_big; i++) {  // a large cluster gets one warp per 32 cache entries (upper bound), at most 64
-                const uint64_t H = u->h_nhap[sel[i]], entries = (uint64_t)S * (H * (H + 1) / 2);
-                // entry-parallel fill: 32 entries per warp; term-parallel fill (>= 16 k-mers per entry expected): 4 entries per warp
-                const bool by_terms = (u->h_fill_cost[sel[i]] / std::max<uint64_t>(1, entries)) >= 16;
-                const uint32_t parts = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, by_terms ? (entries + 3) / 4 : (entries + 31) / 32));
-                for (uint32_t p = 0; p < parts; p++) { tasks[b].push_back(i); tasks[b].push_back(p); tasks[b].push_back(parts); }
-            }
+            for (uint32_t i = 0; i < n_big; i++) lockstep_fill_tasks(u, sel[i], i, u->du.wide, tasks[b]);
         };
     }
     if (rc == BTG_OK) {
@@ -1174,7 +1197,7 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
             void *args[] = {&du_k, &T, &o, &sel_b, &n_sel, &n_big, &chain_id, &iters_arg, &ns, &ps, &pc, &hist, &joint, &px, &tasks_b, &n_tasks, &gb};
             cudaError_t e;
             if (u->du.wide) {  // warp per cluster, lane = sample (gibbs_wide.cu)
-                e = wide_noise_chain(du_k, T, o, sel_b, n_sel, chain_id, iters_arg, ns, ps, pc, hist, joint, px, gb, K, ctx().sm_count, st);
+                e = wide_noise_chain(du_k, T, o, sel_b, n_sel, n_big, tasks_b, n_tasks, chain_id, iters_arg, ns, ps, pc, hist, joint, px, gb, K, ctx().sm_count, st);
             } else {
                 e = cudaLaunchCooperativeKernel((void *)k_noise_chain, dim3(grid), dim3(bs), args, 0, st);
                 BTG_LAUNCHED();
@@ -1337,7 +1360,7 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
                 if (g >= base && g < base + G) sel.push_back((uint32_t)u->h_group_cluster_off[g - base]);  // this rank's share
             }
             // large clusters first (one warp each in the chain kernel), then by position in the cost order (neighbours share arena slots)
-            auto is_big = [&](uint32_t c) { return !use_wide && u->h_fill_cost[c] > (uint64_t)kBigFillCost * S; };  // the clusters with a dense tile: cost PER SAMPLE (a one-thread cluster walks its samples in turn)
+            auto is_big = [&](uint32_t c) { return lockstep_is_big(u, c, use_wide); };
             std::sort(sel.begin(), sel.end(), [&](uint32_t a, uint32_t b) {
                 const bool ba = is_big(a), bb = is_big(b);
                 return ba != bb ? ba : u->h_layout[a].pos < u->h_layout[b].pos;
@@ -1346,13 +1369,7 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
             while (n_big < sel.size() && is_big(sel[n_big])) n_big++;
             // fill tasks: a large cluster gets one warp per 32 cache entries (S x diplotypes, upper bound), at most 64
             tasks.clear();
-            for (uint32_t i = 0; i < n_big; i++) {
-                const uint64_t H = u->h_nhap[sel[i]], entries = (uint64_t)S * (H * (H + 1) / 2);
-                // entry-parallel fill: 32 entries per warp; term-parallel fill (>= 16 k-mers per entry expected): 4 entries per warp
-                const bool by_terms = (u->h_fill_cost[sel[i]] / std::max<uint64_t>(1, entries)) >= 16;
-                const uint32_t parts = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, by_terms ? (entries + 3) / 4 : (entries + 31) / 32));
-                for (uint32_t p = 0; p < parts; p++) { tasks.push_back(i); tasks.push_back(p); tasks.push_back(parts); }
-            }
+            for (uint32_t i = 0; i < n_big; i++) lockstep_fill_tasks(u, sel[i], i, use_wide, tasks);
             if (tasks.size() > tasks_cap) {
                 if (d_tasks) cudaFree(d_tasks);
                 tasks_cap = tasks.size() * 2;
@@ -1380,7 +1397,7 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
                 void *args[] = {&u->du, &T, &o, &d_sel, &n_sel_arg, &n_big, &chain_id, &iters_arg, &ns, &ps, &pc, &hist, &joint, &px, &d_tasks, &n_tasks, &gb};
                 cudaError_t e;
                 if (use_wide) {
-                    e = wide_noise_chain(u->du, T, o, d_sel, n_sel_arg, chain_id, iters_arg, ns, ps, pc, hist, joint, px, gb, 1, ctx().sm_count, s);
+                    e = wide_noise_chain(u->du, T, o, d_sel, n_sel_arg, n_big, d_tasks, n_tasks, chain_id, iters_arg, ns, ps, pc, hist, joint, px, gb, 1, ctx().sm_count, s);
                 } else {
                     e = cudaLaunchCooperativeKernel((void *)k_noise_chain, dim3(grid), dim3(bs), args, smem, s);
                     BTG_LAUNCHED();

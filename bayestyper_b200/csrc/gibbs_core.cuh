@@ -100,6 +100,8 @@ struct SlotLayout {
     uint32_t H, K, nvar, n_uniq, n_alleles, Dall;  // per-lane capacities = max over the slot's clusters
     uint32_t n_multi;                   // multicluster k-mers (0 for every slot of single-cluster groups)
     uint32_t has_cache;                 // dense per-(sample, diplotype) caches allocated (always in the interleaved layout)
+    uint32_t cum_rows;                  // one row of cumulative log-probs per sample (wide layout; slots holding clusters of nested groups,
+                                        // which the warp-per-group kernel of the joint mode works on with one lane per sample)
 };
 // st = 32 for the lane-interleaved slots, 1 for the dense slots of the wide layout (one cluster per slot, worked on by a whole warp)
 template <class T> struct LaneArr {
@@ -189,18 +191,18 @@ struct ArenaSizes { uint64_t f64, u32, u8; };
 // the value of an entry does not depend on whether it was cached
 constexpr uint64_t kWideCacheCap = 16384;
 constexpr uint32_t kWideMinSamples = 8;   // units with at least this many samples get the wide layout (BTG_WIDE=0/1 overrides)
-__host__ __device__ inline bool arena_has_cache(uint32_t S, uint32_t Dall, uint32_t n_multi, bool wide) {
-    return !wide || n_multi > 0 || (uint64_t)S * Dall <= kWideCacheCap;
+__host__ __device__ inline bool arena_has_cache(uint32_t S, uint32_t Dall, uint32_t n_multi, bool wide, uint64_t cap = kWideCacheCap) {
+    return !wide || n_multi > 0 || (uint64_t)S * Dall <= cap;
 }
 __host__ __device__ inline ArenaSizes arena_sizes(uint32_t S, uint32_t H, uint32_t K, uint32_t nvar, uint32_t n_uniq, uint32_t n_alleles, uint32_t Dall,
-                                                  uint32_t n_multi, bool wide = false) {
-    const bool cache = arena_has_cache(S, Dall, n_multi, wide);
+                                                  uint32_t n_multi, bool wide = false, uint64_t cache_cap = kWideCacheCap, bool cum_rows = false) {
+    const bool cache = arena_has_cache(S, Dall, n_multi, wide, cache_cap);
     ArenaSizes a;
     a.f64 = (uint64_t)H * 2        /* freq, log(freq) */
           + (H + 1)                /* simplex prob vector (H > kSimplexTableMaxH: most recent key only) */
           + (H <= kSimplexTableMaxH ? (uint64_t)H * (H + 1) : 0) /* else: one vector per plus-count, + lengths */
           + (cache ? (uint64_t)S * Dall : 0)     /* unique diplotype log-prob cache */
-          + (cache ? (wide ? (uint64_t)S * Dall : Dall) : 0)   /* cumulative log-probs of one draw (wide: of one draw per sample) */
+          + (cache ? (wide || cum_rows ? (uint64_t)S * Dall : Dall) : 0)   /* cumulative log-probs of one draw (or of one draw per sample) */
           + (uint64_t)S * 2 * nvar * 2   /* k-mer stats cache (fraction, mean) */
           + (uint64_t)n_alleles * S * 3  /* allele k-mer stats: 3 sums (count, fraction, mean) */
           + (n_multi ? (uint64_t)S * Dall : 0)  /* multicluster diplotype log-prob cache */
@@ -256,7 +258,7 @@ struct Cl {
         const SlotLayout SL = du.slots[du.wide ? L.pos : L.pos >> 5];
         const uint32_t lane = du.wide ? 0u : L.pos & 31u, st = du.wide ? 1u : 32u;
         has_cache = SL.has_cache;
-        cum_stride = du.wide ? SL.Dall : 0u;
+        cum_stride = SL.cum_rows ? SL.Dall : 0u;
         LaneArr<double> f{du.f64_pool + SL.f64_off + lane, st};
         freq = f; f = f + SL.H;
         logf = f; f = f + SL.H;
@@ -264,7 +266,7 @@ struct Cl {
         has_simplex_tab = SL.H <= kSimplexTableMaxH;
         simplex_tab = f; f = f + (has_simplex_tab ? (uint64_t)SL.H * (SL.H + 1) : 0);
         ucache = f; f = f + (has_cache ? (uint64_t)S * SL.Dall : 0);
-        cum = f; f = f + (has_cache ? (du.wide ? (uint64_t)S * SL.Dall : SL.Dall) : 0);
+        cum = f; f = f + (has_cache ? (SL.cum_rows ? (uint64_t)S * SL.Dall : SL.Dall) : 0);
         kc_f = f; f = f + (uint64_t)S * 2 * SL.nvar * 2;
         as_f = f; f = f + (uint64_t)SL.n_alleles * S * 3;
         mcache = f; f = f + (SL.n_multi ? (uint64_t)S * SL.Dall : 0);
@@ -1335,7 +1337,8 @@ template <class T> T *upload(const T *h, size_t n, bool &ok) {
 
 // gibbs_wide.cu: the warp-per-cluster kernels (lane = sample)
 cudaError_t wide_estimate_genotypes(const DevUnit &du, const Tables &T, const btg_gibbs_opts &o, const ResultView &R, cudaStream_t st);
-cudaError_t wide_noise_chain(const DevUnit &du, const Tables &T, const btg_gibbs_opts &o, const uint32_t *d_sel, uint32_t n_sel, uint32_t chain, uint32_t iters,
+cudaError_t wide_noise_chain(const DevUnit &du, const Tables &T, const btg_gibbs_opts &o, const uint32_t *d_sel, uint32_t n_sel, uint32_t n_big,
+                             const uint32_t *d_tasks, uint32_t n_tasks, uint32_t chain, uint32_t iters,
                              const NoiseState &ns, float prior_shape, float prior_scale, unsigned long long *hist, int joint, const PeerExchange &px,
                              const GridBarrier &gb, uint32_t share, int sm_count, cudaStream_t st);
 }  // namespace btg_gibbs

@@ -145,6 +145,25 @@ __device__ __forceinline__ void clw_noise_counts(const Cl &cl, unsigned long lon
     if (n0) { atomicAdd(sh_stat + 2 * s, (unsigned long long)n0); atomicAdd(sh_stat + 2 * s + 1, (unsigned long long)c0); }
 }
 
+// One fill task of a large cluster (lock-step modes, where the caches are cleared every iteration): the task takes every parts-th
+// pair of live haplotypes and lane s sums the k-mer tile for sample s — the sums that calcDiplotypeLogProb
+// (VariantClusterGenotyper.cpp:597-666) would take on first use, in the same order, so the cached values are the same bits.
+__device__ __forceinline__ void clw_fill_cache(Cl &cl, const Tables &T, const uint8_t *ploidy, uint32_t lane, uint32_t part, uint32_t parts) {
+    const uint32_t H = cl.H, s = lane, n_sub = cl.misc[kNSub];
+    const uint8_t pl = s < cl.S ? ploidy[s] : 0;
+    uint32_t e = 0;
+    for (uint32_t a = 0; a < H; a++) {
+        if (!cl.nz[a]) continue;
+        for (uint32_t b = a; b < H; b++) {
+            if (!cl.nz[b]) continue;
+            const uint32_t mine = e++;
+            if (mine % parts != part) continue;
+            if (pl == 2) cl.ucache[(size_t)s * cl.Dall + cl.slot(a, b)] = tile_entry_sum(cl, T, s, a, b, n_sub);
+            else if (pl == 1 && a == b) cl.ucache[(size_t)s * cl.Dall + cl.slot(a, H)] = tile_entry_sum(cl, T, s, a, NONE, n_sub);
+        }
+    }
+}
+
 // VariantClusterGenotyper::clearCache (…Genotyper.cpp:131-138)
 template <bool MC>
 __device__ __forceinline__ void clw_clear_cache(Cl &cl, uint32_t lane) {
@@ -336,7 +355,10 @@ __global__ void __launch_bounds__(128) k_estimate_genotypes_nested_wide(DevUnit 
 // sel[i] = first cluster of the i-th selected group.  joint = 0: estimateNoise (fresh genotypers each chain, streams of chain
 // `chain`); joint = 1: estimateNoiseAndGenotypes — genotypers constructed in the first chain only (streams of chain 0), samples
 // collected after the burn-in, groups may hold nested clusters.
-__global__ void __launch_bounds__(256, 2) k_noise_chain_wide(DevUnit du, Tables T, btg_gibbs_opts o, const uint32_t *sel, uint32_t n_sel, uint32_t chain, uint32_t iters,
+// sel[0 .. n_big): large single-cluster groups — their caches are filled by the whole grid (fill_tasks: (index in sel, part, parts)) while the
+// other groups take their step, and they sample from the filled caches after a grid barrier.
+__global__ void __launch_bounds__(256, 2) k_noise_chain_wide(DevUnit du, Tables T, btg_gibbs_opts o, const uint32_t *sel, uint32_t n_sel, uint32_t n_big,
+                                                            const uint32_t *fill_tasks, uint32_t n_fill_tasks, uint32_t chain, uint32_t iters,
                                                             NoiseState ns, float prior_shape, float prior_scale, unsigned long long *hist, int joint, PeerExchange px,
                                                             GridBarrier gb) {
     __shared__ unsigned long long sh_tot[kMailRow];
@@ -381,11 +403,21 @@ __global__ void __launch_bounds__(256, 2) k_noise_chain_wide(DevUnit du, Tables 
         if (threadIdx.x < 2 * du.S) sh_stat[threadIdx.x] = 0;
         __syncthreads();
         const bool collect = joint && it > o.gibbs_burn_in;
-        for (uint32_t i = w; i < n_sel; i += n_warps) {  // sampleGenotypesCallback
+        // phase A: fill tasks of the large clusters, dealt from the LAST warp downwards (the other groups occupy the first warps) ...
+        for (uint32_t t = n_warps - 1 - w; t < n_fill_tasks; t += n_warps) {
+            Cl cl;
+            cl.bind(du, sel[fill_tasks[3 * t]]);
+            clw_fill_cache(cl, T, du.group_ploidy + (size_t)cl.g * du.S, lane, fill_tasks[3 * t + 1], fill_tasks[3 * t + 2]);
+        }
+        // ... while every other group takes its whole step (sampleGenotypesCallback)
+        for (uint32_t i = n_big + w; i < n_sel; i += n_warps) {
             const uint32_t g = du.layout[sel[i]].group;
             if (du.group_cluster_off[g + 1] - du.group_cluster_off[g] > 1) group_iteration<true>(du, T, o, g, collect, sh_stat, lane);
             else group_iteration<false>(du, T, o, g, collect, sh_stat, lane);
         }
+        if (n_fill_tasks) grid_barrier(gb);
+        // phase B: the large clusters sample from their filled caches
+        for (uint32_t i = w; i < n_big; i += n_warps) group_iteration<false>(du, T, o, du.layout[sel[i]].group, collect, sh_stat, lane);
         __syncthreads();
         if (threadIdx.x < 2 * du.S && sh_stat[threadIdx.x]) atomicAdd(hist + threadIdx.x, sh_stat[threadIdx.x]);
         grid_barrier(gb);
@@ -419,7 +451,8 @@ cudaError_t wide_estimate_genotypes(const DevUnit &du, const Tables &T, const bt
     return cudaGetLastError();
 }
 
-cudaError_t wide_noise_chain(const DevUnit &du, const Tables &T, const btg_gibbs_opts &o, const uint32_t *d_sel, uint32_t n_sel, uint32_t chain, uint32_t iters,
+cudaError_t wide_noise_chain(const DevUnit &du, const Tables &T, const btg_gibbs_opts &o, const uint32_t *d_sel, uint32_t n_sel, uint32_t n_big,
+                             const uint32_t *d_tasks, uint32_t n_tasks, uint32_t chain, uint32_t iters,
                              const NoiseState &ns, float prior_shape, float prior_scale, unsigned long long *hist, int joint, const PeerExchange &px,
                              const GridBarrier &gb, uint32_t share, int sm_count, cudaStream_t st) {
     const uint32_t bs = 256;
@@ -427,9 +460,9 @@ cudaError_t wide_noise_chain(const DevUnit &du, const Tables &T, const btg_gibbs
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_noise_chain_wide, bs, 0);
     const uint32_t capacity = (uint32_t)std::max(1, per_sm) * (uint32_t)sm_count;
     const uint32_t max_blocks = std::max(1u, (share > 1 ? capacity - capacity / 16 : capacity) / std::max(1u, share));
-    const uint32_t grid = std::max(1u, std::min((n_sel + 7) / 8, max_blocks));
+    const uint32_t grid = std::max(1u, std::min((std::max(n_sel, n_tasks) + 7) / 8, max_blocks));
     DevUnit du_ = du; Tables T_ = T; btg_gibbs_opts o_ = o; NoiseState ns_ = ns; PeerExchange px_ = px; GridBarrier gb_ = gb;
-    void *args[] = {&du_, &T_, &o_, &d_sel, &n_sel, &chain, &iters, &ns_, &prior_shape, &prior_scale, &hist, &joint, &px_, &gb_};
+    void *args[] = {&du_, &T_, &o_, &d_sel, &n_sel, &n_big, &d_tasks, &n_tasks, &chain, &iters, &ns_, &prior_shape, &prior_scale, &hist, &joint, &px_, &gb_};
     BTG_LAUNCHED();
     return cudaLaunchCooperativeKernel((void *)k_noise_chain_wide, dim3(grid), dim3(bs), args, 0, st);
 }

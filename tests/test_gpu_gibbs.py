@@ -168,15 +168,6 @@ def test_malformed_group_forest_rejected_loudly(btg):
         engine.InferenceEngine(bad)
 
 
-def test_joint_mode_rejects_nested_groups_loudly(btg):
-    fx = GibbsFixture("gibbs_nested_2s")
-    _, gcd = _both(fx, None)
-    eng = engine.InferenceEngine(fx.unit)
-    with pytest.raises(Exception, match="nested"):
-        eng.estimate_noise_and_genotypes(gcd, fx.opts(chains=1, burn=2, samples=2))
-    eng.close()
-
-
 def test_nested_unit_noise_estimation_uses_single_cluster_groups_only(btg):
     """InferenceEngine::estimateNoise draws from groups of ONE cluster (InferenceEngine.cpp:144-151)."""
     fx = GibbsFixture("gibbs_nested_2s")
