@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(64, MIN_BLOCKS) k_estimate_genotypes(DevUnit d
     }
     Cl cl;
     cl.bind(du, cluster, pos);
-    const uint64_t gidx = o.group_index_base + cl.g;
+    const uint64_t gidx = group_index(o, cl.g);
     const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
     Philox prng, fr;
     prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, 0);
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(64) k_estimate_genotypes_nested(DevUnit du, Ta
     const uint32_t g = du.nested_groups[i], S = du.S;
     const uint64_t c0 = du.group_cluster_off[g];
     const uint32_t n = (uint32_t)(du.group_cluster_off[g + 1] - c0);
-    const uint64_t gidx = o.group_index_base + g;
+    const uint64_t gidx = group_index(o, g);
     const uint8_t *ploidy = du.group_ploidy + (size_t)g * S;
     const uint64_t s0 = du.group_src_off[g], s1 = du.group_src_off[g + 1];
     const uint64_t e0 = du.cl_edge_off[c0], e1 = du.cl_edge_off[c0 + n];
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256, BTG_NOISE_MINBLOCKS) k_noise_chain(DevUni
     for (uint32_t i = tid >> 5; i < n_big; i += nthreads >> 5) {  // large clusters: constructed by a warp, reset by its lane 0
         Cl cl;
         cl.bind(du, sel[i]);
-        const uint64_t gidx = o.group_index_base + cl.g;
+        const uint64_t gidx = group_index(o, cl.g);
         const uint32_t stream_chain = joint ? 0 : chain;
         if (!joint || chain == 1) cl_construct_warp(cl, o, gidx, stream_chain, tid & 31u);
         if ((tid & 31u) == 0) {
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(256, BTG_NOISE_MINBLOCKS) k_noise_chain(DevUni
     for (uint32_t i = n_big + tid; i < n_sel; i += nthreads) {  // initGenotypersCallback: fresh genotypers every chain
         Cl cl;
         cl.bind(du, sel[i]);
-        const uint64_t gidx = o.group_index_base + cl.g;
+        const uint64_t gidx = group_index(o, cl.g);
         Philox prng, fr;
         if (!joint || chain == 1) {
             const uint32_t stream_chain = joint ? 0 : chain;
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(256, BTG_NOISE_MINBLOCKS) k_noise_chain(DevUni
             cl_fill_cache_rows(cl, T, ploidy_i);  // > 4 live haplotypes: entries are filled on demand
             tick(1);
             {
-                const uint64_t gidx = o.group_index_base + cl.g;
+                const uint64_t gidx = group_index(o, cl.g);
                 Philox prng, fr;
                 prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
                 fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
@@ -1053,9 +1053,9 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
     if (!u || !cd || !opts) { set_error("null argument"); return BTG_EINVAL; }
     btg_comm *comm = sh ? sh->comm : nullptr;
     const uint32_t world = comm ? comm->world : 1;
-    if (sh && (!sh->group_n_clusters || !sh->group_n_variants || opts->group_index_base + u->du.G > sh->n_groups_total)) {
-        set_error("bad shard descriptor: this rank's groups [%llu, %llu) do not fit the %llu groups of the unit", (unsigned long long)opts->group_index_base,
-                  (unsigned long long)(opts->group_index_base + u->du.G), (unsigned long long)(sh ? sh->n_groups_total : 0));
+    if (sh && (!sh->group_n_clusters || !sh->group_n_variants || (u->du.G && group_index(*opts, u->du.G - 1) >= sh->n_groups_total))) {
+        set_error("bad shard descriptor: this rank's groups (first %llu, stride %u, %u of them) do not fit the %llu groups of the unit", (unsigned long long)opts->group_index_base,
+                  (unsigned)opts->group_index_stride, u->du.G, (unsigned long long)(sh ? sh->n_groups_total : 0));
         return BTG_EINVAL;
     }
     if (comm && !comm->connected) { set_error("communicator is not connected (btg_comm_connect)"); return BTG_ESTATE; }
@@ -1095,7 +1095,7 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
         // ---- group selection of every chain (InferenceEngine.cpp:174-189), on the host, in chain order ----
         HostEnginePhilox engine;
         engine.init(opts->random_seed);
-        const uint64_t base = sh ? opts->group_index_base : 0;
+        const uint64_t base = sh ? opts->group_index_base : 0, stride = sh && opts->group_index_stride ? opts->group_index_stride : 1;
         std::vector<uint32_t> noise_groups;  // single-cluster groups of the WHOLE unit (InferenceEngine.cpp:144-151)
         if (sh) { for (uint64_t g = 0; g < sh->n_groups_total; g++) if (sh->group_n_clusters[g] == 1) noise_groups.push_back((uint32_t)g); }
         else { for (uint32_t g = 0; g < G; g++) if (u->h_group_cluster_off[g + 1] - u->h_group_cluster_off[g] == 1) noise_groups.push_back(g); }
@@ -1116,7 +1116,7 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
         }
         d_sel = (uint32_t *)dalloc(std::max<size_t>(1, sel_cap) * nc * 4);
         d_tasks = (uint32_t *)dalloc(std::max<size_t>(1, task_cap) * nc * 4);
-        select_chain = [&, base, noise_groups, engine, group_variants, is_big, noise_variants_batch_size](uint32_t b) mutable {
+        select_chain = [&, base, stride, noise_groups, engine, group_variants, is_big, noise_variants_batch_size](uint32_t b) mutable {
             uint32_t end = 0, nvv = 0;
             for (size_t i = noise_groups.size(); i > 1; i--) std::swap(noise_groups[i - 1], noise_groups[engine.uniform_int((uint32_t)i)]);
             while (nvv < noise_variants_batch_size && end < noise_groups.size()) { nvv += group_variants(noise_groups[end]); end++; }
@@ -1124,7 +1124,7 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
             auto &sel = sels[b];
             for (uint32_t i = 0; i < end; i++) {
                 const uint64_t g = noise_groups[i];
-                if (g >= base && g < base + G) sel.push_back((uint32_t)u->h_group_cluster_off[g - base]);  // this rank's share
+                if (g >= base && (g - base) % stride == 0 && (g - base) / stride < G) sel.push_back((uint32_t)u->h_group_cluster_off[(g - base) / stride]);  // this rank's share
             }
             // large clusters first (fill tasks + one warp each), then by position in the cost order (neighbours share arena slots)
             std::sort(sel.begin(), sel.end(), [&](uint32_t a, uint32_t c) {
@@ -1247,9 +1247,9 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
     if (!u || !cd || !opts) { set_error("null argument"); return BTG_EINVAL; }
     btg_comm *comm = sh ? sh->comm : nullptr;
     const uint32_t world = comm ? comm->world : 1;
-    if (sh && (!sh->group_n_clusters || !sh->group_n_variants || opts->group_index_base + u->du.G > sh->n_groups_total)) {
-        set_error("bad shard descriptor: this rank's groups [%llu, %llu) do not fit the %llu groups of the unit", (unsigned long long)opts->group_index_base,
-                  (unsigned long long)(opts->group_index_base + u->du.G), (unsigned long long)(sh ? sh->n_groups_total : 0));
+    if (sh && (!sh->group_n_clusters || !sh->group_n_variants || (u->du.G && group_index(*opts, u->du.G - 1) >= sh->n_groups_total))) {
+        set_error("bad shard descriptor: this rank's groups (first %llu, stride %u, %u of them) do not fit the %llu groups of the unit", (unsigned long long)opts->group_index_base,
+                  (unsigned)opts->group_index_stride, u->du.G, (unsigned long long)(sh ? sh->n_groups_total : 0));
         return BTG_EINVAL;
     }
     if (comm && !comm->connected) { set_error("communicator is not connected (btg_comm_connect)"); return BTG_ESTATE; }
@@ -1310,7 +1310,7 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
         engine.init(opts->random_seed);
         // single-cluster groups (InferenceEngine.cpp:144-151) of the WHOLE unit: with a shard descriptor every rank walks the
         // same global list with the same engine stream, so the selection does not depend on the sharding
-        const uint64_t base = sh ? opts->group_index_base : 0;
+        const uint64_t base = sh ? opts->group_index_base : 0, stride = sh && opts->group_index_stride ? opts->group_index_stride : 1;
         std::vector<uint32_t> noise_groups;
         // estimateNoise: groups of one cluster (InferenceEngine.cpp:144-151); estimateNoiseAndGenotypes: every group (:407-408)
         if (sh) {
@@ -1357,7 +1357,7 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
             sel.clear();
             for (uint32_t i = 0; i < end; i++) {
                 const uint64_t g = noise_groups[i];
-                if (g >= base && g < base + G) sel.push_back((uint32_t)u->h_group_cluster_off[g - base]);  // this rank's share
+                if (g >= base && (g - base) % stride == 0 && (g - base) / stride < G) sel.push_back((uint32_t)u->h_group_cluster_off[(g - base) / stride]);  // this rank's share
             }
             // large clusters first (one warp each in the chain kernel), then by position in the cost order (neighbours share arena slots)
             auto is_big = [&](uint32_t c) { return lockstep_is_big(u, c, use_wide); };
@@ -1454,7 +1454,7 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
                                 best < u->du.C ? (unsigned long long)(u->h_cl_var_off[best + 1] - u->h_cl_var_off[best]) : 0ull, best < u->du.C ? u->h_fill_cost[best] : 0);
                     }
                 }
-                for (int k = 0; k < 3 && BTG_NOISE_TIMING; k++) {
+                for (int k = 0; k < 3 && (BTG_NOISE_TIMING || use_wide); k++) {
                     const uint32_t c = (uint32_t)(ph[4 + k] & 0xFFFFFFFFu);
                     if (ph[4 + k] && c < u->du.C)
                         fprintf(stderr, "[btgpu]   slowest %s: %.1f us, cluster %u (H %u, variants %llu, fill cost %u)\n", what[k], (ph[4 + k] >> 32) / 1e3, c, u->h_nhap[c],

@@ -31,6 +31,10 @@ namespace btg_gibbs {
 
 
 constexpr uint16_t NONE = 0xFFFF;  // Utils::ushort_overflow
+// index in the whole unit of group g of this btg_unit (btg_gibbs_opts: base + g * stride)
+__host__ __device__ inline uint64_t group_index(const btg_gibbs_opts &o, uint32_t g) {
+    return o.group_index_base + (uint64_t)g * (o.group_index_stride ? o.group_index_stride : 1u);
+}
 constexpr double kDoubleEps100 = 2.220446049250313e-16 * 100;
 constexpr float kFloatEps100 = 1.1920929e-07f * 100;
 
@@ -1283,7 +1287,7 @@ __device__ __forceinline__ void cl_fill_cache_warp(Cl &cl, const Tables &T, cons
 
 // one lock-step iteration of one cluster by a single thread (sampleGenotypesCallback body without the noise counts)
 __device__ __forceinline__ void noise_iteration_thread(Cl &cl, const DevUnit &du, const Tables &T, const btg_gibbs_opts &o, bool collect) {
-    const uint64_t gidx = o.group_index_base + cl.g;
+    const uint64_t gidx = group_index(o, cl.g);
     const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
     Philox prng, fr;
     prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);

@@ -202,7 +202,7 @@ __device__ __forceinline__ void group_branch_order(const DevUnit &du, const btg_
     const uint32_t n = (uint32_t)(du.group_cluster_off[g + 1] - c0);
     const uint64_t s0 = du.group_src_off[g], s1 = du.group_src_off[g + 1];
     Philox br;
-    br.init(o.random_seed, o.group_index_base + g, 0, kRngBranch, chain);
+    br.init(o.random_seed, group_index(o, g), 0, kRngBranch, chain);
     for (uint64_t m = s1 - s0; m > 1; m--) {
         const uint32_t j = br.uniform_int((uint32_t)m);
         const uint32_t t = du.src_mut[s0 + m - 1]; du.src_mut[s0 + m - 1] = du.src_mut[s0 + j]; du.src_mut[s0 + j] = t;
@@ -235,7 +235,7 @@ __device__ __forceinline__ void group_iteration(const DevUnit &du, const Tables 
                                                 uint32_t lane) {
     const uint64_t c0 = du.group_cluster_off[g];
     const uint32_t n = MC ? (uint32_t)(du.group_cluster_off[g + 1] - c0) : 1u, S = du.S;
-    const uint64_t gidx = o.group_index_base + g;
+    const uint64_t gidx = group_index(o, g);
     for (uint32_t pos = 0; pos < n; pos++) {
         const uint32_t v = MC ? du.dfs_order[c0 + pos] : 0u;
         Cl cl;
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(128) k_estimate_genotypes_wide(DevUnit du, Tab
     }
     Cl cl;
     cl.bind(du, cluster, pos);
-    const uint64_t gidx = o.group_index_base + cl.g;
+    const uint64_t gidx = group_index(o, cl.g);
     const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
     cl_construct_warp(cl, o, gidx, 0, lane);
     const uint32_t iters = (uint32_t)o.gibbs_burn_in + o.gibbs_samples;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(128) k_estimate_genotypes_nested_wide(DevUnit 
     const uint32_t g = du.nested_groups[w];
     const uint64_t c0 = du.group_cluster_off[g];
     const uint32_t n = (uint32_t)(du.group_cluster_off[g + 1] - c0);
-    const uint64_t gidx = o.group_index_base + g;
+    const uint64_t gidx = group_index(o, g);
     if (lane == 0) {
         for (uint64_t e = du.group_src_off[g]; e < du.group_src_off[g + 1]; e++) du.src_mut[e] = du.group_src[e];
         for (uint64_t e = du.cl_edge_off[c0]; e < du.cl_edge_off[c0 + n]; e++) du.edge_mut[e] = du.edge_dst[e];
@@ -367,11 +367,12 @@ __global__ void __launch_bounds__(256, 2) k_noise_chain_wide(DevUnit du, Tables 
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u, n_warps = (gridDim.x * blockDim.x) >> 5;
     const bool first = !joint || chain == 1;
     const uint32_t stream_chain = joint ? 0 : chain;
+    const unsigned long long t_start = ns.phase_ns && blockIdx.x == 0 && threadIdx.x == 0 ? global_timer_ns() : 0;
     for (uint32_t i = w; i < n_sel; i += n_warps) {  // initGenotypersCallback (InferenceEngine.cpp:60-75)
         const uint32_t g = du.layout[sel[i]].group;
         const uint64_t c0 = du.group_cluster_off[g];
         const uint32_t n = (uint32_t)(du.group_cluster_off[g + 1] - c0);
-        const uint64_t gidx = o.group_index_base + g;
+        const uint64_t gidx = group_index(o, g);
         if (n > 1 && first && lane == 0) {
             for (uint64_t e = du.group_src_off[g]; e < du.group_src_off[g + 1]; e++) du.src_mut[e] = du.group_src[e];
             for (uint64_t e = du.cl_edge_off[c0]; e < du.cl_edge_off[c0 + n]; e++) du.edge_mut[e] = du.edge_dst[e];
@@ -399,28 +400,46 @@ __global__ void __launch_bounds__(256, 2) k_noise_chain_wide(DevUnit du, Tables 
     }
     if (blockIdx.x == 0 && ns.trace) noise_update_block(ns, du.S, prior_shape, prior_scale, o.random_seed, 3, 0, (double)chain, 0, 1, sh_rates);
     grid_barrier(gb);
+    // BTG_NOISE_PHASES=1: block 0's laps through [fill + small groups, large clusters, exchange + update, release]; [4] = slowest fill
+    // task, [5] = slowest large cluster of phase B, [6] = slowest other group (ns << 32 | cluster)
+    const bool timing = ns.phase_ns && blockIdx.x == 0 && threadIdx.x == 0;
+    unsigned long long t_prev = timing ? global_timer_ns() : 0;
+    auto lap = [&](int phase) {
+        if (timing) { const unsigned long long t = global_timer_ns(); ns.phase_ns[phase] += t - t_prev; t_prev = t; }
+    };
+    if (timing) ns.phase_ns[7] += t_prev - t_start;
     for (uint32_t it = 1; it <= iters; it++) {
         if (threadIdx.x < 2 * du.S) sh_stat[threadIdx.x] = 0;
         __syncthreads();
         const bool collect = joint && it > o.gibbs_burn_in;
         // phase A: fill tasks of the large clusters, dealt from the LAST warp downwards (the other groups occupy the first warps) ...
         for (uint32_t t = n_warps - 1 - w; t < n_fill_tasks; t += n_warps) {
+            const unsigned long long t_in = ns.phase_ns ? global_timer_ns() : 0;
             Cl cl;
             cl.bind(du, sel[fill_tasks[3 * t]]);
             clw_fill_cache(cl, T, du.group_ploidy + (size_t)cl.g * du.S, lane, fill_tasks[3 * t + 1], fill_tasks[3 * t + 2]);
+            if (ns.phase_ns && lane == 0) atomicMax(ns.phase_ns + 4, ((global_timer_ns() - t_in) << 32) | cl.c);
         }
         // ... while every other group takes its whole step (sampleGenotypesCallback)
         for (uint32_t i = n_big + w; i < n_sel; i += n_warps) {
+            const unsigned long long t_in = ns.phase_ns ? global_timer_ns() : 0;
             const uint32_t g = du.layout[sel[i]].group;
             if (du.group_cluster_off[g + 1] - du.group_cluster_off[g] > 1) group_iteration<true>(du, T, o, g, collect, sh_stat, lane);
             else group_iteration<false>(du, T, o, g, collect, sh_stat, lane);
+            if (ns.phase_ns && lane == 0) atomicMax(ns.phase_ns + 6, ((global_timer_ns() - t_in) << 32) | sel[i]);
         }
         if (n_fill_tasks) grid_barrier(gb);
+        lap(0);
         // phase B: the large clusters sample from their filled caches
-        for (uint32_t i = w; i < n_big; i += n_warps) group_iteration<false>(du, T, o, du.layout[sel[i]].group, collect, sh_stat, lane);
+        for (uint32_t i = w; i < n_big; i += n_warps) {
+            const unsigned long long t_in = ns.phase_ns ? global_timer_ns() : 0;
+            group_iteration<false>(du, T, o, du.layout[sel[i]].group, collect, sh_stat, lane);
+            if (ns.phase_ns && lane == 0) atomicMax(ns.phase_ns + 5, ((global_timer_ns() - t_in) << 32) | sel[i]);
+        }
         __syncthreads();
         if (threadIdx.x < 2 * du.S && sh_stat[threadIdx.x]) atomicAdd(hist + threadIdx.x, sh_stat[threadIdx.x]);
         grid_barrier(gb);
+        lap(1);
         if (blockIdx.x == 0) {
             if (px.world > 1) {  // sharded unit: add up the ranks' statistics over peer memory (comm.cuh) before the draw
                 if (threadIdx.x < 2 * du.S) sh_tot[threadIdx.x] = hist[threadIdx.x];
@@ -430,7 +449,9 @@ __global__ void __launch_bounds__(256, 2) k_noise_chain_wide(DevUnit du, Tables 
             }
             noise_update_block(ns, du.S, prior_shape, prior_scale, o.random_seed, 1, o.gibbs_burn_in < it, (double)chain, (double)it, 1, sh_rates);
         }
+        lap(2);
         grid_barrier(gb);
+        lap(3);
     }
 }
 

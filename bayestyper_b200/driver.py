@@ -39,6 +39,62 @@ class Options:
     bloom_fpr: float = 0.001          # bayesTyperTools makeBloom default (src/bayesTyperTools/main.cpp:127)
     max_parameter_kmers: int = 1_000_000
     chromosome_ploidy_file: str = None   # --chromosome-ploidy-file (ChromosomePloidy.cpp:96-180); default: human X / Y rules by name
+    noise_genotyping: bool = False       # --noise-genotyping: InferenceEngine::estimateNoiseAndGenotypes instead of estimateNoise + estimateGenotypes
+
+
+@dataclasses.dataclass
+class Shard:
+    """One inference unit over several GPUs (one rank per process and GPU).  Rank r takes the groups r, r + world,
+    r + 2 world ... of the size-sorted unit (balanced shards; btg_gibbs_opts.group_index_base / group_index_stride keep every group's
+    streams).  `allgather(obj) -> [obj of every rank]` is the host transport (torch.distributed.all_gather_object over NCCL or gloo) for the
+    one real exchange of the k-mer path — every rank needs the best paths of ALL clusters to tell which path k-mers occur in several
+    groups — and for the mailbox handles of `comm` (shard.Comm), through which the lock-step Gibbs modes add up their noise counts
+    inside the chain kernel."""
+    world: int
+    rank: int
+    allgather: object
+    comm: object = None
+
+    def my_groups(self, n_groups: int) -> np.ndarray:
+        return np.arange(self.rank, n_groups, self.world, dtype=np.int64)
+
+
+def _take_csr(off, idx):
+    off = np.asarray(off).astype(np.int64)
+    lens = off[idx + 1] - off[idx]
+    new_off = np.concatenate([[0], np.cumsum(lens)])
+    return new_off, np.repeat(off[idx] - new_off[:-1], lens) + np.arange(int(new_off[-1]))
+
+
+def subset_graphs_for_paths(graphs: dict, groups: np.ndarray):
+    """The arrays findVariantClusterPaths reads, for the clusters of `groups` only (the clusters keep the index of their group in the
+    whole unit: it seeds their path search, KmerCounter.cpp:65).  Returns (graphs subset, cluster indices in the whole unit)."""
+    gco = np.asarray(graphs["group_cluster_off"], np.int64)
+    new_gco, clusters = _take_csr(gco, groups)
+    cvo, verts = _take_csr(graphs["cl_vertex_off"], clusters)
+    vso, nts = _take_csr(graphs["v_seq_off"], verts)
+    vio, ins = _take_csr(graphs["v_in_off"], verts)
+    sub = {"group_cluster_off": new_gco.astype(np.uint64), "cl_vertex_off": cvo.astype(np.uint64), "v_seq_off": vso.astype(np.uint64),
+           "seq": np.asarray(graphs["seq"])[nts], "v_flags": np.asarray(graphs["v_flags"])[verts], "v_in_off": vio.astype(np.uint64),
+           "v_in_src": np.asarray(graphs["v_in_src"])[ins], "cluster_idx": np.asarray(graphs["cluster_idx"])[clusters],
+           "cl_group_global": np.repeat(groups.astype(np.uint32), np.diff(new_gco))}
+    return sub, clusters
+
+
+def merge_best_paths(graphs: dict, parts, cluster_lists):
+    """Best paths of every cluster of the unit from the per-rank results [(n_paths, membership bytes)] (cluster_lists[r] = the
+    whole-unit cluster indices rank r searched, in its order)."""
+    V = np.diff(np.asarray(graphs["cl_vertex_off"], np.int64))
+    n_paths = np.zeros(len(V), np.int64)
+    for (np_r, _), cl in zip(parts, cluster_lists):
+        n_paths[cl] = np_r
+    off = np.concatenate([[0], np.cumsum(n_paths * V)])
+    mem = np.zeros(int(off[-1]), np.uint8)
+    for (np_r, mem_r), cl in zip(parts, cluster_lists):
+        lens = (n_paths * V)[cl]
+        loc = np.concatenate([[0], np.cumsum(lens)])
+        mem[np.repeat(off[cl] - loc[:-1], lens) + np.arange(int(loc[-1]))] = mem_r
+    return n_paths, mem
 
 
 def find_variant_cluster_paths(lib, graphs: dict, sample_blooms, opt: Options):
@@ -48,7 +104,8 @@ def find_variant_cluster_paths(lib, graphs: dict, sample_blooms, opt: Options):
         "cl_vertex_off": np.ascontiguousarray(graphs["cl_vertex_off"], np.uint64), "v_seq_off": np.ascontiguousarray(graphs["v_seq_off"], np.uint64),
         "seq": np.ascontiguousarray(graphs["seq"], np.uint8), "v_flags": np.ascontiguousarray(graphs["v_flags"], np.uint8),
         "v_in_off": np.ascontiguousarray(graphs["v_in_off"], np.uint64), "v_in_src": np.ascontiguousarray(graphs["v_in_src"], np.uint32),
-        "cl_group": np.repeat(np.arange(len(gco) - 1, dtype=np.uint32), np.diff(gco).astype(np.int64)),
+        "cl_group": np.ascontiguousarray(graphs["cl_group_global"], np.uint32) if "cl_group_global" in graphs
+                    else np.repeat(np.arange(len(gco) - 1, dtype=np.uint32), np.diff(gco).astype(np.int64)),
         "cl_idx": np.ascontiguousarray(graphs["cluster_idx"], np.uint32),
     }
     d = GraphsDesc()
@@ -122,8 +179,15 @@ def estimate_nb_parameters(pipe: kmer_pipeline.KmerPipeline, region_buf, spectra
         for si in range(S):
             mult = torch.clamp(occ * ploidy[0 if genders[si] in ("F", 0) else 1], max=255)
             hist = torch.bincount(mult, minlength=256)[1:33]            # max_nb_kmer_multiplicity = 32 (CountDistribution.cpp:42)
+            # CountDistribution::setGenomicCountDistributions asserts a modal class and valid moments (CountDistribution.cpp:113-119): a sample
+            # whose ploidy on this contig is 0, or a unit without parameter k-mers, must not reach the Gibbs stage with NaN tables
+            if int(hist.max()) == 0:
+                raise capi.BtgError(f"sample {si}: no parameter k-mer with genomic multiplicity 1..32 (ploidy {ploidy[0 if genders[si] in ('F', 0) else 1]} on this contig, "
+                                    f"{len(occ)} parameter k-mers): the negative binomial cannot be fitted")
             m = int(torch.argmax(hist)) + 1                             # first maximum, as the reference's strict '>' scan
             c = counts[mult == m, si].to(torch.float64)
+            if c.numel() < 2:
+                raise capi.BtgError(f"sample {si}: {c.numel()} parameter k-mer(s) at the modal multiplicity {m}: mean and variance undefined")
             mean = float(c.mean()); var = float(c.var(unbiased=True))
             p, size = C.c_double(), C.c_double()
             lib.btg_nb_moments_to_parameters(mean, var, m, C.byref(p), C.byref(size))
@@ -211,16 +275,24 @@ def inputs_from_kmc(chrom: str, reference: bytes, variants, samples) -> Inputs:
         genders.append("F" if str(gender).upper().startswith("F") else "M")
         meta = Path(str(prefix) + ".bloomMeta")
         if meta.exists():
-            n, bits, _k = (int(x) for x in meta.read_text().split())
-            blooms.append((np.fromfile(str(prefix) + ".bloomData", np.uint8), n, bits))
+            n, bits, k_file = (int(x) for x in meta.read_text().split())
+            data = np.fromfile(str(prefix) + ".bloomData", np.uint8)
+            if k_file != K:                                            # KmerBloom(prefix) asserts the k-mer size (KmerBloom.cpp:83)
+                raise capi.BtgError(f"{meta}: filter built for k = {k_file}, this library is built for k = {K}")
+            if data.size != (bits + 7) // 8:
+                raise capi.BtgError(f"{prefix}.bloomData holds {data.size} bytes, {meta.name} declares {bits} bits ({(bits + 7) // 8} bytes)")
+            blooms.append((data, n, bits))
     return Inputs(chrom, reference, variants, genders, spectra, blooms=blooms if len(blooms) == len(samples) else None)
 
 
 def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rates=None, resident: bool = False, want_unit: bool = False,
-             vcf_out=None, sample_names=None):
+             vcf_out=None, sample_names=None, shard: Shard | None = None):
     """One pass of both hot paths: path search -> k-mer table -> haplotype candidates -> NB fit -> noise -> Gibbs.
     resident=True uses the device copies made by Inputs.make_resident (the `value` leg of bench.py); otherwise every
-    input crosses the boundary from host memory inside this call (the `e2e` leg)."""
+    input crosses the boundary from host memory inside this call (the `e2e` leg).
+    shard: this process is one rank of a unit sharded over several GPUs (see Shard): it searches the paths of its own groups, exchanges
+    the best paths, runs the (cheap) k-mer table stages on the whole unit and the Gibbs stages on its own groups; the returned result
+    arrays and info["n_clusters"] cover this rank's groups only (info["n_clusters_total"]: the unit)."""
     opt = opt or Options()
     lib = capi.load()
     inp.prepare()
@@ -245,7 +317,16 @@ def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rate
         region_buf = torch.from_numpy(_region_buffer(inp.reference, inp.regions)).to(dev)
         torch.cuda.synchronize()
     female_ploidy, male_ploidy = ploidy_rules.ChromosomePloidy([inp.chrom], inp.genders, opt.chromosome_ploidy_file).gender_ploidy(inp.chrom)
-    n_paths, mem = find_variant_cluster_paths(lib, inp.graphs, blooms, opt)
+    sharded = shard is not None and shard.world > 1
+    G = len(inp.graphs["group_cluster_off"]) - 1
+    if sharded:
+        mine = shard.my_groups(G)
+        sub, my_clusters = subset_graphs_for_paths(inp.graphs, mine)
+        part = find_variant_cluster_paths(lib, sub, blooms, opt)
+        parts = shard.allgather((part[0], part[1], my_clusters))
+        n_paths, mem = merge_best_paths(inp.graphs, [(p[0], p[1]) for p in parts], [p[2] for p in parts])
+    else:
+        n_paths, mem = find_variant_cluster_paths(lib, inp.graphs, blooms, opt)
     if own_blooms:
         for b in blooms:
             lib.btg_bloom_free(b)
@@ -254,7 +335,6 @@ def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rate
     pipe.scan_buffer(region_buf, female_ploidy, male_ploidy, False)
     for s, (kd, cdv) in enumerate(spectra_dev):
         pipe.add_sample(s, kd, cdv)
-    G = len(inp.graphs["group_cluster_off"]) - 1
     ploidy = np.tile(np.array([female_ploidy if g in ("F", 0) else male_ploidy for g in inp.genders], np.uint8), G)
     # row-level unit arrays stay in HBM unless the caller wants the unit on the host (tests, fixtures)
     unit = pipe.build_unit(multigroup_bloom=None, ploidy=ploidy, device_resident=not want_unit)
@@ -264,17 +344,28 @@ def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rate
     else:
         nb_p, nb_size = nb_params
     cd = engine.CountDistribution(nb_p, nb_size, opt.noise_rate_prior)
+    info["n_clusters_total"] = unit.Cn
+    sdesc = keep = None
+    if sharded:   # the Gibbs stages on this rank's groups; the lock-step modes see the whole unit through the shard descriptor
+        from . import shard as shard_mod
+        sdesc, keep = shard_mod.shard_desc(unit, shard.comm)
+        unit = unit.subset_groups(mine)
     eng = engine.InferenceEngine(unit)
     gopts = U.default_opts(seed=opt.random_seed, burn=opt.gibbs_burn_in, samples=opt.gibbs_samples, chains=opt.n_chains, rate=opt.kmer_subsampling_rate,
                            max_hv=opt.max_haplotype_variant_kmers, min_gpp=opt.min_genotype_posterior, min_kmers=opt.min_number_of_kmers,
-                           min_frac=None if opt.disable_observed_kmers else U.min_fraction_observed(nb_p, nb_size))
-    if noise_rates is None:
-        info["noise_trace"] = eng.estimate_noise(cd, gopts, want_trace=False)
+                           min_frac=None if opt.disable_observed_kmers else U.min_fraction_observed(nb_p, nb_size),
+                           group_base=shard.rank if sharded else 0, group_stride=shard.world if sharded else 1)
+    if opt.noise_genotyping:
+        res, info["noise_trace"] = eng.estimate_noise_and_genotypes(cd, gopts, want_trace=False, shard=sdesc)
+        info["noise_rates"] = cd.noise_rates()
     else:
-        cd.set_noise_rates(noise_rates)
-    info["noise_rates"] = cd.noise_rates()
+        if noise_rates is None:
+            info["noise_trace"] = eng.estimate_noise(cd, gopts, want_trace=False, shard=sdesc)
+        else:
+            cd.set_noise_rates(noise_rates)
+        info["noise_rates"] = cd.noise_rates()
+        res = eng.estimate_genotypes(cd, gopts)
     info["nb"] = (nb_p, nb_size)
-    res = eng.estimate_genotypes(cd, gopts)
     info["n_clusters"] = unit.Cn
     eng.close(); cd.close()
     if vcf_out is not None:   # GenotypeWriter (include/btgpu_vcf.hpp through host/btvcf): the result arrays are in unit order, so is the description

@@ -30,7 +30,7 @@ class UnitDesc(C.Structure):
 class GibbsOpts(C.Structure):
     _fields_ = [
         ("random_seed", C.c_uint32), ("gibbs_burn_in", C.c_uint16), ("gibbs_samples", C.c_uint16),
-        ("n_chains", C.c_uint16), ("first_group_index", C.c_uint16), ("kmer_subsampling_rate", C.c_float),
+        ("n_chains", C.c_uint16), ("group_index_stride", C.c_uint16), ("kmer_subsampling_rate", C.c_float),
         ("max_haplotype_variant_kmers", C.c_uint32), ("min_genotype_posterior", C.c_float),
         ("min_number_of_kmers", C.c_float), ("min_fraction_observed_kmers", C.c_float * MAX_SAMPLES),
         ("group_index_base", C.c_uint64),
@@ -50,7 +50,7 @@ class GenotypeResult(C.Structure):
 
 
 def default_opts(seed: int = 20190401, burn: int = 100, samples: int = 250, chains: int = 20, rate: float = 0.1,
-                 max_hv: int = 500, min_gpp: float = 0.99, min_kmers: float = 1.0, min_frac=None, group_base: int = 0) -> GibbsOpts:
+                 max_hv: int = 500, min_gpp: float = 0.99, min_kmers: float = 1.0, min_frac=None, group_base: int = 0, group_stride: int = 1) -> GibbsOpts:
     o = GibbsOpts()
     o.random_seed, o.gibbs_burn_in, o.gibbs_samples, o.n_chains = seed, burn, samples, chains
     o.kmer_subsampling_rate, o.max_haplotype_variant_kmers = rate, max_hv
@@ -58,6 +58,7 @@ def default_opts(seed: int = 20190401, burn: int = 100, samples: int = 250, chai
     for i in range(MAX_SAMPLES):
         o.min_fraction_observed_kmers[i] = 0.0 if min_frac is None or i >= len(min_frac) else float(min_frac[i])
     o.group_index_base = group_base
+    o.group_index_stride = group_stride
     return o
 
 
@@ -141,50 +142,76 @@ class Unit:
         return np.concatenate([[0], np.cumsum(n)]).astype(np.uint64)
 
     def subset_groups(self, groups) -> "Unit":
-        """A new Unit holding only the given groups (used for shards and bounded CPU samples)."""
+        """A new Unit holding only the given groups (used for shards and bounded CPU samples).  Row-level arrays that live on the
+        device (self.dev) are gathered there: nothing crosses the bus."""
         groups = np.asarray(groups, np.int64)
         a = self.a
-        out = {k: [] for k, _ in _DESC_FIELDS}
-        gco = a["group_cluster_off"]
-        clusters = np.concatenate([np.arange(gco[g], gco[g + 1]) for g in groups]).astype(np.int64) if len(groups) else np.zeros(0, np.int64)
+        dev = self.dev or {}
 
-        def take_csr(off_name, data_names, idx, width=None):
-            off = a[off_name]
-            lens = (off[idx + 1] - off[idx]).astype(np.int64)
-            sel = np.concatenate([np.arange(off[i], off[i + 1]) for i in idx]).astype(np.int64) if len(idx) else np.zeros(0, np.int64)
-            new_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        def take_csr(off, idx):
+            """(new offsets, selected element indices) of rows `idx` of a CSR offset array — numpy or torch (device) alike."""
+            if isinstance(off, np.ndarray):
+                off = off.astype(np.int64)
+                lens = off[idx + 1] - off[idx]
+                new_off = np.concatenate([[0], np.cumsum(lens)])
+                sel = np.repeat(off[idx] - new_off[:-1], lens) + np.arange(int(new_off[-1]))
+                return new_off.astype(np.uint64), sel
+            import torch
+            idx_t = idx if isinstance(idx, torch.Tensor) else torch.from_numpy(idx).to(off.device)
+            lens = off[idx_t + 1] - off[idx_t]
+            new_off = torch.zeros(lens.numel() + 1, dtype=torch.int64, device=off.device)
+            torch.cumsum(lens, 0, out=new_off[1:])
+            total = int(new_off[-1])
+            sel = torch.repeat_interleave(off[idx_t] - new_off[:-1], lens, output_size=total) + torch.arange(total, device=off.device)
             return new_off, sel
 
+        def field(name):
+            return dev[name] if name in dev and name not in a else a[name]
+
+        def gather(name, sel, width=1):
+            x = field(name)
+            if isinstance(x, np.ndarray):
+                sel_h = sel if isinstance(sel, np.ndarray) else sel.cpu().numpy()
+                return x.reshape(-1, width)[sel_h].reshape(-1) if width > 1 else x[sel_h]
+            import torch
+            sel_t = sel if isinstance(sel, torch.Tensor) else torch.from_numpy(sel).to(x.device)
+            return (x.reshape(-1, width)[sel_t].reshape(-1) if width > 1 else x[sel_t]).contiguous()
+
         S = self.S
+        _, clusters = take_csr(a["group_cluster_off"], groups)
         new = {}
         new["sample_gender"] = a["sample_gender"]
         new["group_ploidy"] = a["group_ploidy"].reshape(-1, S)[groups].reshape(-1)
-        new["group_cluster_off"], _ = take_csr("group_cluster_off", [], groups)
-        new["group_src_off"], sel = take_csr("group_src_off", [], groups); new["group_src"] = a["group_src"][sel]
-        new["group_edge_off"], sel = take_csr("group_edge_off", [], groups)
+        new["group_cluster_off"], _ = take_csr(a["group_cluster_off"], groups)
+        new["group_src_off"], sel = take_csr(a["group_src_off"], groups); new["group_src"] = a["group_src"][sel]
+        new["group_edge_off"], sel = take_csr(a["group_edge_off"], groups)
         new["group_edge_src"] = a["group_edge_src"][sel]; new["group_edge_dst"] = a["group_edge_dst"][sel]
         new["cluster_idx"] = a["cluster_idx"][clusters]
         new["cl_nhap"] = a["cl_nhap"][clusters]
-        new["cl_kmer_off"], rows = take_csr("cl_kmer_off", [], clusters)
-        new["cl_var_off"], vars_ = take_csr("cl_var_off", [], clusters)
-        new["cl_mult_off"], sel = take_csr("cl_mult_off", [], clusters); new["mult"] = a["mult"][sel]
-        new["k_has_counts"] = a["k_has_counts"][rows]
-        new["k_counts"] = a["k_counts"].reshape(-1, S)[rows].reshape(-1)
-        new["k_ic"] = a["k_ic"].reshape(-1, 2)[rows].reshape(-1)
-        new["k_shared"] = a["k_shared"][rows]
-        new["cl_uniq_off"], sel = take_csr("cl_uniq_off", [], clusters); new["uniq_idx"] = a["uniq_idx"][sel]
-        new["cl_multi_off"], sel = take_csr("cl_multi_off", [], clusters); new["multi_idx"] = a["multi_idx"][sel]
-        new["kmer_vh_off"], vh = take_csr("kmer_vh_off", [], rows); new["vh_var"] = a["vh_var"][vh]
-        new["vh_bits_off"], sel = take_csr("vh_bits_off", [], vh); new["vh_bits"] = a["vh_bits"][sel]
-        new["cl_hapvar_off"], sel = take_csr("cl_hapvar_off", [], clusters); new["hap_alleles"] = a["hap_alleles"][sel]
+        new["cl_kmer_off"], rows = take_csr(a["cl_kmer_off"], clusters)
+        new["cl_var_off"], vars_ = take_csr(a["cl_var_off"], clusters)
+        new["cl_mult_off"], sel = take_csr(a["cl_mult_off"], clusters); new["mult"] = gather("mult", sel)
+        new["k_has_counts"] = gather("k_has_counts", rows)
+        new["k_counts"] = gather("k_counts", rows, S)
+        new["k_ic"] = gather("k_ic", rows, 2)
+        new["k_shared"] = gather("k_shared", rows)
+        new["cl_uniq_off"], sel = take_csr(a["cl_uniq_off"], clusters); new["uniq_idx"] = gather("uniq_idx", sel)
+        new["cl_multi_off"], sel = take_csr(a["cl_multi_off"], clusters); new["multi_idx"] = a["multi_idx"][sel]
+        vh_off = field("kmer_vh_off")
+        new["kmer_vh_off"], vh = take_csr(vh_off, rows if isinstance(vh_off, np.ndarray) else rows)
+        new["vh_var"] = gather("vh_var", vh)
+        new["vh_bits_off"], sel = take_csr(field("vh_bits_off"), vh); new["vh_bits"] = gather("vh_bits", sel)
+        new["cl_hapvar_off"], sel = take_csr(a["cl_hapvar_off"], clusters); new["hap_alleles"] = gather("hap_alleles", sel)
         new["var_nalleles"] = a["var_nalleles"][vars_]; new["var_dep"] = a["var_dep"][vars_]
         # haplotype-indexed arrays
-        hap_start = np.concatenate([[0], np.cumsum(a["cl_nhap"].astype(np.int64))])
-        haps = np.concatenate([np.arange(hap_start[c], hap_start[c + 1]) for c in clusters]).astype(np.int64) if len(clusters) else np.zeros(0, np.int64)
-        new["hap_nested_off"], sel = take_csr("hap_nested_off", [], haps); new["hap_nested"] = a["hap_nested"][sel]
-        new["cl_dep_off"], deps = take_csr("cl_dep_off", [], clusters); new["dep_cluster"] = a["dep_cluster"][deps]
-        new["dep_var_off"], sel = take_csr("dep_var_off", [], deps); new["dep_var"] = a["dep_var"][sel]
-        return Unit(new, S)
+        hap_off = np.concatenate([[0], np.cumsum(a["cl_nhap"].astype(np.int64))])
+        _, haps = take_csr(hap_off, clusters)
+        new["hap_nested_off"], sel = take_csr(a["hap_nested_off"], haps); new["hap_nested"] = a["hap_nested"][sel]
+        new["cl_dep_off"], deps = take_csr(a["cl_dep_off"], clusters); new["dep_cluster"] = a["dep_cluster"][deps]
+        new["dep_var_off"], sel = take_csr(a["dep_var_off"], deps); new["dep_var"] = a["dep_var"][sel]
+        host = {k: v for k, v in new.items() if isinstance(v, np.ndarray)}
+        on_dev = {k: v for k, v in new.items() if not isinstance(v, np.ndarray)}
+        return Unit(host, S, on_dev or None)
 
 
 def from_ref_dumps(haps: dict, graphs: dict, genders, ploidy=None) -> Unit:

@@ -3,17 +3,21 @@
 
   python bench.py --gpus N --steps K --warmup W          our arm (libbtgpu, B200)
   python bench.py --impl reference ...                   the reference's own CPU code (oracle/_ref/btref)
+  python bench.py --config D ...                         configs[3] shape: 30 samples, --noise-genotyping joint mode
 
-One "step" = one pass of both hot paths over one synthetic batch of the named shape
-(configs[1]: 1 sample, chr22-like SNV+indel candidate set, ~300k variants, k=55), bayestyper_b200/driver.py:
+One "step" = one pass of both hot paths over one synthetic batch of the named shape (default configs[1]: 1 sample, chr22-like
+SNV+indel candidate set, ~300k variants, k=55), bayestyper_b200/driver.py:
   k-mer match   findVariantClusterPaths (a7) -> path k-mer enumeration + exact table (a9, a12) -> genome scan (a10)
                 -> sample k-mer stream (a11) -> classify + haplotype candidates (a13, a14) -> NB fit (a18)
-  Gibbs         estimateNoise + estimateGenotypes: 20 chains x (100 + 250) iterations per cluster (a15-a23)
-`value` times the step with the sample k-mer set, sample Bloom and reference already in HBM (CUDA events on the
-library stream); `e2e` runs the same call with every input in host memory (H2D inside the timed region) and the
-results read back.
-N > 1 (torchrun): groups are independent -> every rank runs its own shard of the same size, no
-data-path collective ("weak"); time = max over ranks.
+  Gibbs         estimateNoise + estimateGenotypes (or estimateNoiseAndGenotypes): 20 chains x (100 + 250) iterations (a15-a23)
+`value` times the step with the sample k-mer sets, sample Bloom filters and reference already in HBM (CUDA events on the library
+stream); `e2e` runs the same call with every input in host memory (H2D inside the timed region) and the results read back.
+
+N > 1 (torchrun), default `--mode sharded`: ONE unit of the named size is sharded over the N ranks (strong scaling) — rank r
+takes every N-th group of the size-sorted unit, searches the paths of its groups, the ranks exchange their best paths (the one real
+exchange of the k-mer path), and the lock-step Gibbs chains add up their noise counts once per iteration INSIDE the chain kernel
+over NVLink peer mailboxes (csrc/comm.cuh; 7000 exchanges per step).  `--mode replicas`: every rank runs its own unit of the named
+size with no data-path exchange (weak scaling, the round-1 line).  Time = max over ranks.
 """
 from __future__ import annotations
 
@@ -35,7 +39,12 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "variant_clusters_genotyped_per_sec"
 UNIT = "clusters/s"
-WORKLOAD = "configs[1]: 1 sample, chr22-like SNV+indel candidate VCF (~300k variants), k=55, default Gibbs 20x(100+250)"
+WORKLOADS = {
+    "B": "configs[1]: 1 sample, chr22-like SNV+indel candidate VCF (~300k variants), k=55, default Gibbs 20x(100+250)",
+    "D": "configs[3] shape: 30 samples, --noise-genotyping joint mode, --max-number-of-sample-haplotypes 32, k=55, 20x(100+250); a 2.7 Mb / 20k-variant "
+         "slice of the whole-genome set (population allele frequencies ~ Beta(0.2,0.8), Hardy-Weinberg genotypes), SURVEY.md section 8d",
+}
+WORKLOAD = WORKLOADS["B"]
 
 
 def measured_peaks():
@@ -138,6 +147,26 @@ def device_spectrum(lib, haplotypes, mean, var, seed, n_errors, dev):
     return keys[o].contiguous(), counts[o].contiguous()
 
 
+def build_batch_d(lib, rank: int, scale: float, dev):
+    """configs[3] shape on one contig: 30 samples (alternating genders, diploid chr1), 20k SNV/indel candidates on 2.7 Mb, population
+    allele frequencies ~ Beta(0.2, 0.8) (seed 31), Hardy-Weinberg genotypes (seed 32), 30x spectra synthesised on the device."""
+    from bayestyper_b200 import driver, synth
+    S = 30
+    n_var = max(60, int(20_000 * scale))
+    ref = synth.random_reference(n_var * 136, 11 + 1000 * rank)
+    var = synth.make_variants(ref, n_var, 12 + 1000 * rank, 0.075, 0.075)
+    af = np.random.default_rng(31 + 1000 * rank).beta(0.2, 0.8, size=len(var))
+    g = synth.make_genotypes(len(var), S, 32 + 1000 * rank, allele_freq=af)
+    spectra = []
+    for s_ in range(S):
+        haps = [synth.apply_variants(ref, var, g[s_, :, h]) for h in range(2)]
+        spectra.append(device_spectrum(lib, haps, 15.0, 25.0, 14 + 1000 * rank + 7 * s_, int(50_000 * scale), dev))
+    inp = driver.Inputs("chr1", ref, var, ["F" if i % 2 == 0 else "M" for i in range(S)], spectra=None)
+    inp.spectra_dev = spectra
+    inp.prepare()
+    return inp
+
+
 def build_batch(lib, rank: int, scale: float, dev):
     """configs[1]: chr22-like reference (10 Mb N + 40.8 Mb), ~300k SNV/indel candidates, 1 female sample at 30x."""
     from bayestyper_b200 import driver, synth
@@ -172,13 +201,24 @@ def run_ours(args):
     capi.check(lib.btg_init(local_rank), lib)
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.ExternalStream(lib.btg_get_stream(), device=dev)
-    opt = driver.Options(random_seed=20190401)
+    opt = driver.Options(random_seed=20190401, noise_genotyping=args.config == "D")
+    sharded = world > 1 and args.mode in ("auto", "sharded")
+    shard_ctx = None
+    if sharded:   # one unit over all ranks: every rank builds the SAME batch; mailbox handles + best paths travel over torch.distributed
+        from bayestyper_b200 import shard as shard_mod
+
+        def allgather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+        shard_ctx = driver.Shard(world, rank, allgather, shard_mod.Comm.torch(world, rank))
 
     t0 = time.time()
-    inp = build_batch(lib, rank, args.scale, dev)
+    inp = (build_batch_d if args.config == "D" else build_batch)(lib, 0 if sharded else rank, args.scale, dev)
     inp.make_resident(lib, opt)
     setup_s = time.time() - t0
-    n_sample = int(inp.spectra_dev[0][0].shape[0])
+    n_sample = int(sum(k.shape[0] for k, _ in inp.spectra_dev))
+    S = len(inp.spectra_dev)
 
     def barrier():
         torch.cuda.synchronize()
@@ -189,7 +229,7 @@ def run_ours(args):
     # ---- value: inputs resident in HBM -------------------------------------------------------------
     info = None
     for _ in range(args.warmup):
-        _, _, _, info = driver.genotype(inp, opt, resident=True)
+        _, _, _, info = driver.genotype(inp, opt, resident=True, shard=shard_ctx)
     n_clusters = info["n_clusters"] if info else None
     barrier()
     lib.btg_launch_count_reset()
@@ -197,17 +237,18 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
-            _, _, res, info = driver.genotype(inp, opt, resident=True)
+            _, _, res, info = driver.genotype(inp, opt, resident=True, shard=shard_ctx)
         e1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
     launches = int(lib.btg_launch_count())
     n_clusters = info["n_clusters"]
+    n_total = info["n_clusters_total"] if sharded else world * n_clusters      # clusters genotyped by ALL ranks in one step
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
-    value = world * n_clusters / (ms_per_step / 1e3)
+    value = n_total / (ms_per_step / 1e3)
 
     if args.timed_only:          # profiler runs (ncu launch list): the warm-up + timed steps only; not a bench line
         if rank == 0:
@@ -215,54 +256,57 @@ def run_ours(args):
         inp.free(lib)
         return
     # ---- e2e: every input crosses the boundary from host memory inside the call --------------------------
-    keys_d, counts_d = inp.spectra_dev[0]
-    h_keys = torch.empty(keys_d.shape, dtype=torch.int64, pin_memory=True); h_keys.copy_(keys_d)
-    h_counts = torch.empty(counts_d.shape, dtype=torch.uint8, pin_memory=True); h_counts.copy_(counts_d)
+    h_spectra, h_blooms, h2d, bloom_total = [], [], 0, 0
     nk, nb, nh = C.c_uint64(), C.c_uint64(), C.c_uint32()
-    lib.btg_bloom_info(inp.blooms_dev[0], C.byref(nk), C.byref(nb), C.byref(nh))
-    bloom_bytes = np.zeros((nb.value + 7) // 8, np.uint8)
-    capi.check(lib.btg_bloom_download(inp.blooms_dev[0], capi.ptr(bloom_bytes), bloom_bytes.size), lib)
-    host_inp = driver.Inputs(inp.chrom, inp.reference, inp.variants, inp.genders, spectra=[(h_keys, h_counts)],
-                             blooms=[(bloom_bytes, nk.value, nb.value)], graphs=inp.graphs, regions=inp.regions)
-    region_bytes = int(inp.region_buf_dev.numel())
-    h2d = h_keys.numel() * 8 + h_counts.numel() + bloom_bytes.size + region_bytes
+    for (keys_d, counts_d), bl in zip(inp.spectra_dev, inp.blooms_dev):
+        h_keys = torch.empty(keys_d.shape, dtype=torch.int64, pin_memory=True); h_keys.copy_(keys_d)
+        h_counts = torch.empty(counts_d.shape, dtype=torch.uint8, pin_memory=True); h_counts.copy_(counts_d)
+        lib.btg_bloom_info(bl, C.byref(nk), C.byref(nb), C.byref(nh))
+        bloom_bytes = np.zeros((nb.value + 7) // 8, np.uint8)
+        capi.check(lib.btg_bloom_download(bl, capi.ptr(bloom_bytes), bloom_bytes.size), lib)
+        h_spectra.append((h_keys, h_counts)); h_blooms.append((bloom_bytes, nk.value, nb.value))
+        h2d += h_keys.numel() * 8 + h_counts.numel() + bloom_bytes.size
+        bloom_total += nb.value
+    host_inp = driver.Inputs(inp.chrom, inp.reference, inp.variants, inp.genders, spectra=h_spectra, blooms=h_blooms, graphs=inp.graphs, regions=inp.regions)
+    h2d += int(inp.region_buf_dev.numel())
     torch.cuda.synchronize()
-    _, unit, res, _ = driver.genotype(host_inp, opt, resident=False, want_unit=True)      # warm-up; also sizes the unit traffic
+    _, unit, res, _ = driver.genotype(host_inp, opt, resident=False, want_unit=not sharded, shard=shard_ctx)      # warm-up; also sizes the unit traffic
     from bayestyper_b200.unit import Unit as _Unit
-    small = sum(v.nbytes for k, v in unit.a.items() if k not in _Unit.DEVICE_FIELDS)      # per-cluster / per-group descriptors cross (down, up);
+    small = 0 if unit is None else sum(v.nbytes for k, v in unit.a.items() if k not in _Unit.DEVICE_FIELDS)   # per-cluster / per-group descriptors cross (down, up);
     h2d += small                                                                          # the row-level arrays stay in HBM (btg_unit_upload_dev)
     d2h = sum(v.nbytes for v in res.values()) + small
     barrier()
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = args.steps                                                                # the same number of steps as `value`
     t1 = time.perf_counter()
     for _ in range(e2e_steps):
-        driver.genotype(host_inp, opt, resident=False)
+        driver.genotype(host_inp, opt, resident=False, shard=shard_ctx)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t1) / e2e_steps
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_clusters / float(t.item())
+    e2e_value = n_total / float(t.item())
 
     # ---- stage breakdown + roofline of the k-mer-match stream kernel (measured live, CUDA events) ---------
-    stage_ms, roof = stage_breakdown(lib, inp, opt, stream, dev)
+    stage_ms, roof = stage_breakdown(lib, inp, opt, stream, dev, shard_ctx)
 
     peak, peak_src = measured_peaks()
-    roof.update({"peak": peak, "unit": "GB/s", "frac": roof["achieved"] / peak, "peak_source": peak_src, "bound": "hbm", "traffic": None,
-                 # no ncu capture of THIS launch; the same kernel on tools/prof_stream.py's 40.6 M records / 21.0 M keys moved 1.15 GB of DRAM
-                 # traffic for 1.04 GB of algorithmic bytes (profiles/r1_stream_tiled_ncu_full.txt): no wasted re-reads
-                 "traffic_reference": {"profile": "profiles/r1_stream_tiled_ncu_full.txt", "dram_bytes": 1150482000, "algorithmic_bytes": 1038973086,
-                                       "workload": "tools/prof_stream.py: 40,620,727 records, 21,000,000 keys"}})
+    roof.update({"peak": peak, "unit": "GB/s", "frac": roof["achieved"] / peak, "peak_source": peak_src, "bound": "hbm", "traffic": stream_traffic(roof)})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
         "dtype": "f64 (Gibbs log-likelihoods) / u64 (k-mer hashing)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clusters_per_gpu": n_clusters, "variants_per_gpu": len(inp.variants), "samples": 1,
-                   "reference_nt": len(inp.reference), "sample_kmers": n_sample, "path_kmers": info["n_path_kmers"],
-                   "step": "findVariantClusterPaths -> path k-mer table -> genome scan -> sample k-mer stream -> classify/haplotype candidates -> NB fit -> estimateNoise -> estimateGenotypes",
+        "config": {"workload": WORKLOADS[args.config], "clusters": n_total, "clusters_per_gpu": n_clusters, "variants": len(inp.variants) * (1 if sharded else world),
+                   "samples": S, "reference_nt": len(inp.reference), "sample_kmers": n_sample, "path_kmers": info["n_path_kmers"],
+                   "step": "findVariantClusterPaths -> path k-mer table -> genome scan -> sample k-mer stream -> classify/haplotype candidates -> NB fit -> "
+                           + ("estimateNoiseAndGenotypes" if args.config == "D" else "estimateNoise -> estimateGenotypes"),
                    "gibbs": "20 chains x (100 burn-in + 250 samples), k-mer subsampling 0.1",
-                   "l2": "inputs exceed L2 (sample k-mer stream %.2f GB, sample Bloom %.0f MB)" % (n_sample * 17 / 1e9, nb.value / 8e6),
-                   "parallelism": "groups sharded across ranks, no collective" if world > 1 else "1 GPU", "scale": args.scale},
+                   "l2": "inputs exceed L2 (sample k-mer streams %.2f GB, sample Bloom filters %.0f MB)" % (n_sample * 17 / 1e9, bloom_total / 8e6),
+                   "parallelism": ("1 GPU" if world == 1 else
+                                   "ONE unit sharded over %d ranks (every %d-th group of the size-sorted unit): path search + Gibbs per rank, best paths all-gathered, "
+                                   "noise counts of the lock-step chains added up inside the chain kernel over NVLink peer mailboxes (%d exchanges per step)"
+                                   % (world, world, 20 * 350) if sharded else "%d replicas, one unit of the named size each, no data-path exchange" % world),
+                   "scale": args.scale},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
@@ -272,17 +316,30 @@ def run_ours(args):
     }
     if rank == 0:
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference(args.cpu_variants, os.cpu_count() or 1)
+            line["cpu_baseline"] = cpu_reference(args.config, args.cpu_variants or (3000 if args.config == "B" else 120), os.cpu_count() or 1)
         print(json.dumps(line), flush=True)
     inp.free(lib)
+    if shard_ctx is not None:
+        shard_ctx.comm.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def stage_breakdown(lib, inp, opt, stream, dev):
-    """One extra (untimed for `value`) pass with a synchronisation after every stage, and the isolated timing of the
-    stream kernel k_table_add_sample for the roofline object."""
+def stream_traffic(roof):
+    """DRAM bytes per launch of the stream kernel (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu capture of
+    THIS bench's launch (profiles/r2_stream_traffic.json, written by tools/ncu_stream_traffic.py from an `ncu --set full` capture of
+    `bench.py --timed-only`); null when the capture is of another launch shape."""
+    p = ROOT / "profiles" / "r2_stream_traffic.json"
+    if not p.exists():
+        return None
+    d = json.loads(p.read_text())
+    return d["dram_bytes"] if (d.get("records"), d.get("table_keys")) == (roof["records"], roof["table_keys"]) else None
+
+
+def stage_breakdown(lib, inp, opt, stream, dev, shard_ctx=None):
+    """One extra (untimed for `value`) pass with a synchronisation after every stage (a sharded run reports rank 0's stages; the
+    exchanges are inside them), and the isolated timing of the stream kernel k_table_add_sample for the roofline object."""
     import torch
     from bayestyper_b200 import capi, driver, engine, kmer_pipeline, unit as U
     out = {}
@@ -295,32 +352,51 @@ def stage_breakdown(lib, inp, opt, stream, dev):
         out[name] = (time.perf_counter() - t) * 1e3
         return r
 
-    n_paths, mem = timed("findVariantClusterPaths", lambda: driver.find_variant_cluster_paths(lib, inp.graphs, inp.blooms_dev, opt))
-    pipe = kmer_pipeline.KmerPipeline(inp.graphs, n_paths, mem, 1, inp.genders)
+    S = len(inp.spectra_dev)
+    sharded = shard_ctx is not None
+    G = len(inp.graphs["group_cluster_off"]) - 1
+    if sharded:
+        mine = shard_ctx.my_groups(G)
+        sub, my_clusters = driver.subset_graphs_for_paths(inp.graphs, mine)
+        part = timed("findVariantClusterPaths (own groups)", lambda: driver.find_variant_cluster_paths(lib, sub, inp.blooms_dev, opt))
+        parts = timed("best paths all-gather", lambda: shard_ctx.allgather((part[0], part[1], my_clusters)))
+        n_paths, mem = driver.merge_best_paths(inp.graphs, [(p[0], p[1]) for p in parts], [p[2] for p in parts])
+    else:
+        n_paths, mem = timed("findVariantClusterPaths", lambda: driver.find_variant_cluster_paths(lib, inp.graphs, inp.blooms_dev, opt))
+    pipe = kmer_pipeline.KmerPipeline(inp.graphs, n_paths, mem, S, inp.genders)
     timed("countPathKmers(enumerate+sort)", pipe.enumerate_path_kmers)
     timed("countInterclusterKmers(scan)", lambda: pipe.scan_buffer(inp.region_buf_dev, 2, 2, False))
+    timed("parseSampleKmers(stream, all samples)", lambda: [pipe.add_sample(i, kd_, cd_) for i, (kd_, cd_) in enumerate(inp.spectra_dev)])
     kd, cdv = inp.spectra_dev[0]
-    timed("parseSampleKmers(stream)", lambda: pipe.add_sample(0, kd, cdv))
     unit = timed("classify+getHaplotypeCandidates", lambda: pipe.build_unit(multigroup_bloom=None, device_resident=True))
     nb = timed("NB fit (parameter k-mers)", lambda: driver.estimate_nb_parameters(pipe, inp.region_buf_dev, inp.spectra_dev, inp.genders, opt))
     cd = engine.CountDistribution(nb[0], nb[1])
+    sdesc = keep = None
+    if sharded:
+        from bayestyper_b200 import shard as shard_mod
+        sdesc, keep = shard_mod.shard_desc(unit, shard_ctx.comm)
+        unit = timed("unit subset (own groups, on the device)", lambda: unit.subset_groups(mine))
     eng = timed("unit upload", lambda: engine.InferenceEngine(unit))
-    gopts = U.default_opts(seed=opt.random_seed, min_frac=U.min_fraction_observed(nb[0], nb[1]))
-    timed("estimateNoise", lambda: eng.estimate_noise(cd, gopts, want_trace=False))
-    timed("estimateGenotypes", lambda: eng.estimate_genotypes(cd, gopts))
+    gopts = U.default_opts(seed=opt.random_seed, min_frac=U.min_fraction_observed(nb[0], nb[1]),
+                           group_base=shard_ctx.rank if sharded else 0, group_stride=shard_ctx.world if sharded else 1)
+    if opt.noise_genotyping:
+        timed("estimateNoiseAndGenotypes", lambda: eng.estimate_noise_and_genotypes(cd, gopts, want_trace=False, shard=sdesc))
+    else:
+        timed("estimateNoise", lambda: eng.estimate_noise(cd, gopts, want_trace=False, shard=sdesc))
+        timed("estimateGenotypes", lambda: eng.estimate_genotypes(cd, gopts))
     eng.close(); cd.close()
-    # roofline: the sample k-mer stream probing the exact path-k-mer table
+    # roofline: the sample k-mer stream probing the exact path-k-mer table (sample 0)
     pipe.use_index()
     counts = torch.zeros_like(pipe.counts); rec = torch.zeros_like(pipe.has_record)
     torch.cuda.synchronize()
     n = kd.shape[0]
     for _ in range(3):
-        capi.check(lib.btg_table_add_sample_kmers_dev(pipe.kw0.data_ptr(), pipe.kw1.data_ptr(), pipe.n_keys, kd.data_ptr(), cdv.data_ptr(), n, 1, 0, counts.data_ptr(), rec.data_ptr(), None), lib)
+        capi.check(lib.btg_table_add_sample_kmers_dev(pipe.kw0.data_ptr(), pipe.kw1.data_ptr(), pipe.n_keys, kd.data_ptr(), cdv.data_ptr(), n, S, 0, counts.data_ptr(), rec.data_ptr(), None), lib)
     reps = 5
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(reps):
-        capi.check(lib.btg_table_add_sample_kmers_dev(pipe.kw0.data_ptr(), pipe.kw1.data_ptr(), pipe.n_keys, kd.data_ptr(), cdv.data_ptr(), n, 1, 0, counts.data_ptr(), rec.data_ptr(), None), lib)
+        capi.check(lib.btg_table_add_sample_kmers_dev(pipe.kw0.data_ptr(), pipe.kw1.data_ptr(), pipe.n_keys, kd.data_ptr(), cdv.data_ptr(), n, S, 0, counts.data_ptr(), rec.data_ptr(), None), lib)
     e1.record(stream)
     stream.synchronize()
     ms = e0.elapsed_time(e1) / reps
@@ -329,38 +405,69 @@ def stage_breakdown(lib, inp, opt, stream, dev):
     roof = {"kernel": "k_table_add_sample (parseSampleKmers: sample k-mer stream probing the exact path-k-mer table, a11)",
             "achieved": alg / (ms / 1e3) / 1e9, "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms,
             "records": n, "table_keys": pipe.n_keys, "hits": hits,
-            "bytes_model": "17 B per record + 16 B per path k-mer + S B per hit (SURVEY.md section 8d, merge-join form)"}
+            "bytes_model": "17 B per record + 16 B per path k-mer + 1 B per hit (SURVEY.md section 8d, merge-join form)"}
     return out, roof
 
 
 # ------------------------------------------------------------------------------------------------
 # the reference's own CPU path (oracle-R), bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(n_variants: int, threads: int):
-    """Runs the reference's translation units (oracle/_ref/btref: cluster + genotype stage order) on a
-    bounded sample of the same workload shape and reports its estimateGenotypes throughput."""
+FULL_B = {"variants": 300_000, "noise_cap_variants": 100_000}      # configs[1]; InferenceEngine.cpp:50 noise_variants_batch_size
+
+
+def cpu_reference(config: str, n_variants: int, threads: int):
+    """Runs the reference's translation units (oracle/_ref/btref: cluster + genotype stage order) on a bounded sample of the same
+    workload shape, all host threads.
+
+    configs[1] (B): the sample has the full config's per-cluster shape but the reference's estimateNoise works on at most 100,000
+    variants (InferenceEngine.cpp:50): in the full 300k-variant config it touches one third of the unit, in a small sample all of it.
+    `value` is therefore the FULL-CONFIG rate projected from the sample's measured stage times — k-mer stages and estimateGenotypes
+    scale with the clusters, estimateNoise with min(variants, 100k) — i.e. full_clusters / (t_kmer * r + t_geno * r + t_noise * r_noise),
+    r = 300k / sample variants, r_noise = 100k / sample variants; the unprojected sample rate is reported beside it.
+    configs[3] shape (D): the joint mode touches every cluster in every iteration, so the sample rate is the rate."""
     from bayestyper_b200 import synth
     btref = ROOT / "oracle" / "_ref" / "btref"
     if not btref.exists():
         return {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": "oracle/_ref/btref not built"}
+    S = 30 if config == "D" else 1
     length = int(n_variants * 136)
     ref = synth.random_reference(length, 11)
     var = synth.make_variants(ref, n_variants, 12, 0.075, 0.075)
-    g = synth.make_genotypes(len(var), 1, 13)
-    w = synth.Workload("B-sample", "chr22", ref, var, g, ["F"])
+    if config == "D":
+        af = np.random.default_rng(31).beta(0.2, 0.8, size=len(var))
+        g = synth.make_genotypes(len(var), S, 32, allele_freq=af)
+        w = synth.Workload("D-sample", "chr1", ref, var, g, ["F" if i % 2 == 0 else "M" for i in range(S)])
+    else:
+        g = synth.make_genotypes(len(var), 1, 13)
+        w = synth.Workload("B-sample", "chr22", ref, var, g, ["F"])
     with tempfile.TemporaryDirectory() as td:
-        synth.write_workdir(w, td, n_errors=50_000)
+        synth.write_workdir(w, td, n_errors=max(1000, int(50_000 * n_variants / 3000)) if config == "B" else 2000)
         t0 = time.time()
-        subprocess.check_call([str(btref), "run", "--workdir", td, "--threads", str(threads), "--seed", "20190401"], stdout=subprocess.DEVNULL)
+        subprocess.check_call([str(btref), "run", "--workdir", td, "--threads", str(threads), "--seed", "20190401"] + (["--noise-genotyping"] if config == "D" else []),
+                              stdout=subprocess.DEVNULL)
         wall = time.time() - t0
         tj = json.loads((Path(td) / "ref_out" / "timings.json").read_text())
     kmer_s = sum(tj.get(k, 0.0) for k in ("findVariantClusterPaths", "countPathMultigroupKmers", "countPathKmers", "countInterclusterKmers", "parseSampleKmers", "classifyPathKmers"))
-    total_s = tj["estimateGenotypes"] + tj.get("estimateNoise", 0.0) + kmer_s
-    return {"value": tj["clusters_genotyped"] / total_s, "unit": UNIT, "cores": threads, "kind": "reference", "step_s": total_s,
-            "sample": f"{len(var)} variants / {tj['num_clusters']} clusters of the same chr22-like shape through the reference's own stages "
-                      f"(estimateGenotypes {tj['estimateGenotypes']:.2f} s, estimateNoise {tj.get('estimateNoise', 0):.2f} s, k-mer stages {kmer_s:.2f} s, wall {wall:.1f} s)",
-            "clusters": tj["clusters_genotyped"], "estimateGenotypes_s": tj["estimateGenotypes"], "kmer_stages_s": kmer_s,
-            "clusters_per_s_gibbs_only": tj["clusters_genotyped"] / tj["estimateGenotypes"]}
+    geno_s, noise_s = tj.get("estimateGenotypes", 0.0) + tj.get("estimateNoiseAndGenotypes", 0.0), tj.get("estimateNoise", 0.0)
+    total_s = geno_s + noise_s + kmer_s
+    sample_rate = tj["clusters_genotyped"] / total_s
+    out = {"unit": UNIT, "cores": threads, "kind": "reference", "step_s": total_s, "clusters": tj["clusters_genotyped"], "sample_variants": len(var),
+           "measured_sample_value": sample_rate, "estimateGenotypes_s": geno_s, "estimateNoise_s": noise_s, "kmer_stages_s": kmer_s}
+    if config == "B":
+        r = FULL_B["variants"] / len(var)
+        r_noise = min(FULL_B["variants"], FULL_B["noise_cap_variants"]) / min(len(var), FULL_B["noise_cap_variants"])
+        full_s = (kmer_s + geno_s) * r + noise_s * r_noise
+        out.update({"value": tj["clusters_genotyped"] * r / full_s, "projected_full_step_s": full_s,
+                    "sample": f"{len(var)} variants / {tj['num_clusters']} clusters of the same chr22-like shape through the reference's own stages, {threads} threads "
+                              f"(estimateGenotypes {geno_s:.2f} s, estimateNoise {noise_s:.2f} s, k-mer stages {kmer_s:.2f} s, wall {wall:.1f} s = {sample_rate:.0f} clusters/s on the sample); "
+                              f"value = rate of the full 300k-variant config projected from these stage times (estimateNoise is capped at 100k variants, InferenceEngine.cpp:50: "
+                              f"x{r_noise:.1f}; the other stages x{r:.1f})"})
+    else:
+        out.update({"value": sample_rate,
+                    "sample": f"{len(var)} variants / {tj['num_clusters']} clusters x {S} samples of the same shape through the reference's own stages, {threads} threads "
+                              f"(estimateNoiseAndGenotypes {geno_s:.2f} s, k-mer stages {kmer_s:.2f} s, wall {wall:.1f} s); the joint mode touches every cluster in every "
+                              f"iteration, so the sample rate is the rate of the shape"})
+    return out
 
 
 def run_reference(args):
@@ -368,21 +475,28 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    n_var = args.cpu_variants if args.cpu_variants else (12_000 if args.config == "B" else 120)
     vals = []
     last = None
     for i in range(args.warmup + args.steps):
-        last = cpu_reference(args.cpu_variants, threads)
+        if i < args.warmup and i > 0:
+            continue            # a CPU process has no clocks or caches to warm beyond the first run: one warm-up run stands for all W
+        last = cpu_reference(args.config, n_var, threads)
         if last["value"] is None:
             print(json.dumps({"impl": "reference", "unavailable": last["sample"]}))
             return
         if i >= args.warmup:
             vals.append(last)
-    value = float(np.mean([v["clusters"] / v["step_s"] for v in vals]))
-    ms = float(np.mean([v["step_s"] * 1e3 for v in vals]))
+    value = float(np.mean([v["value"] for v in vals]))
+    ms = float(np.mean([v.get("projected_full_step_s", v["step_s"]) * 1e3 for v in vals]))
     cb = dict(last); cb["value"] = value
+    full_clusters = int(round(last["clusters"] * (FULL_B["variants"] / last["sample_variants"]))) if args.config == "B" else last["clusters"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 / u64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": last["sample"], "threads": threads},
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 and args.mode != "replicas" else "weak", "vs_baseline": None,
+            "dtype": "f64 (Gibbs log-likelihoods) / u64 (k-mer hashing)", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.config], "clusters": full_clusters, "variants": FULL_B["variants"] if args.config == "B" else last["sample_variants"],
+                       "samples": 30 if args.config == "D" else 1, "gibbs": "20 chains x (100 burn-in + 250 samples), k-mer subsampling 0.1",
+                       "step": "the reference's own cluster + genotype stages on the host cores", "sample": last["sample"], "threads": threads},
             "cpu_baseline": cb, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -394,7 +508,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the chr22-sized batch (tests use small values)")
-    ap.add_argument("--cpu-variants", type=int, default=3000, help="size of the bounded CPU sample")
+    ap.add_argument("--config", default="B", choices=["B", "D"], help="B = configs[1] (default, the metric's config); D = configs[3] shape (30 samples, joint mode)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "sharded", "replicas"], help="N > 1: one unit sharded over the ranks (default) or one unit per rank")
+    ap.add_argument("--cpu-variants", type=int, default=0, help="size of the bounded CPU sample (0: 12000 for B in the reference arm, 3000 for the cpu_baseline leg; 120 for D)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timed-only", action="store_true", help="warm-up + timed steps only (for ncu launch lists); prints no bench line")
     args = ap.parse_args()

@@ -305,7 +305,8 @@ typedef struct btg_gibbs_opts {
     uint16_t gibbs_burn_in;               /* 100 */
     uint16_t gibbs_samples;               /* 250 */
     uint16_t n_chains;                    /* 20  */
-    uint16_t first_group_index;           /* unused (0) */
+    uint16_t group_index_stride;          /* group j of this btg_unit is group group_index_base + j * stride of the whole unit (0 = 1): a rank of a
+                                             sharded unit takes every world-th group of the size-sorted unit, which balances the shards */
     float kmer_subsampling_rate;          /* 0.1 */
     uint32_t max_haplotype_variant_kmers; /* 500 */
     float min_genotype_posterior;         /* 0.99 (Filters) */
@@ -351,8 +352,8 @@ int btg_estimate_noise(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *op
 int btg_estimate_noise_and_genotypes(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, btg_genotype_result *out,
                                      double *trace_out);
 /* ---- one inference unit sharded over several GPUs (one rank per process and GPU) ----------
- * Groups are independent, so a rank uploads the groups [group_index_base, group_index_base + n_groups) of the unit as
- * its btg_unit and keeps the reference's per-group seeds through btg_gibbs_opts.group_index_base.  btg_estimate_genotypes
+ * Groups are independent, so a rank uploads the groups group_index_base + j * group_index_stride (j < n_groups) of the unit as
+ * its btg_unit and keeps the reference's per-group seeds through btg_gibbs_opts.group_index_base / group_index_stride.  btg_estimate_genotypes
  * needs nothing else.  The lock-step modes (estimateNoise, estimateNoiseAndGenotypes) merge every thread's
  * CountAllocation once per iteration (InferenceEngine.cpp:226-229,445-448); across ranks that merge is the per-sample
  * (n_obs, sum) pair written into every peer's mailbox over NVLink from inside the chain kernel, after which all ranks

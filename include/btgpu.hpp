@@ -114,6 +114,21 @@ struct GenotypeArrays {
         gt.resize(n_variants * S * 2); gq.resize(n_variants * S); gpp.resize(ngen); app.resize(nall); nak.resize(nall); fak.resize(nall); mac.resize(nall);
         saf.resize(nall); ploidy.resize(n_variants * S); an.resize(n_variants); ac.resize(nalt); af.resize(nalt); acp.resize(nalt); anc.resize(nalt);
         hc.resize(n_variants);
+        bind();
+    }
+    // `view` points into this object's own vectors: a copy must not keep the source's pointers.  Moves keep the heap buffers, so the
+    // view of a moved-to object is rebuilt from its own (now owning) vectors; copies are not offered.
+    GenotypeArrays(const GenotypeArrays &) = delete;
+    GenotypeArrays &operator=(const GenotypeArrays &) = delete;
+    GenotypeArrays(GenotypeArrays &&o) noexcept
+        : allele_off(std::move(o.allele_off)), geno_off(std::move(o.geno_off)), valt_off(std::move(o.valt_off)), gt(std::move(o.gt)), saf(std::move(o.saf)),
+          hc(std::move(o.hc)), gq(std::move(o.gq)), an(std::move(o.an)), ac(std::move(o.ac)), gpp(std::move(o.gpp)), app(std::move(o.app)), nak(std::move(o.nak)),
+          fak(std::move(o.fak)), mac(std::move(o.mac)), af(std::move(o.af)), acp(std::move(o.acp)), ploidy(std::move(o.ploidy)), anc(std::move(o.anc)) { bind(); }
+    GenotypeArrays &operator=(GenotypeArrays &&) = delete;
+
+private:
+    void bind() {
+        const uint64_t n_variants = hc.size();
         view = btg_genotype_result{n_variants, allele_off.data(), geno_off.data(), gt.data(), gq.data(), gpp.data(), app.data(), nak.data(), fak.data(),
                                    mac.data(), saf.data(), ploidy.data(), an.data(), valt_off.data(), ac.data(), af.data(), acp.data(), anc.data(), hc.data()};
     }

@@ -52,7 +52,7 @@ const uint16_t NONE = 0xFFFF;  // Utils::ushort_overflow
 int g_rng_mode = 0;                          // 0 = Philox (the kernels' streams), 1 = mt19937 (the reference's)
 const uint64_t *g_group_index = nullptr;     // optional: index of every group of the descriptor in the FULL unit (seeds)
 inline bool mt() { return g_rng_mode == 1; }
-inline uint64_t groupIndex(const btg_gibbs_opts *o, uint32_t g) { return g_group_index ? g_group_index[g] : o->group_index_base + g; }
+inline uint64_t groupIndex(const btg_gibbs_opts *o, uint32_t g) { return g_group_index ? g_group_index[g] : o->group_index_base + (uint64_t)g * (o->group_index_stride ? o->group_index_stride : 1); }
 
 // ------------------------------------------------------------------ Philox4x32-10
 struct Philox {
