@@ -9,10 +9,16 @@
 // std::shuffle (libstdc++ 13: pairwise swaps drawn with Lemire's method from std::mt19937) leaves the candidate
 // paths before the greedy filter.  The kernel therefore carries a real mt19937 and the exact libstdc++ shuffle.
 //
-// Mapping: clusters are independent; one thread walks one cluster's vertex DP for the current sample (the
-// algorithm is a sequential dynamic programme over vertices), rolling each path's k-mer + ntHash incrementally
-// (kmer.cuh Roller) and probing the sample's Bloom filter in HBM for every completed k-mer.  Per-thread state
-// (path slots, lists, Mersenne state) lives in a scratch arena sized per cluster on the host.
+// Mapping: clusters are independent; ONE WARP walks one cluster's vertex DP for the current sample.  The DP itself (merge,
+// shuffle, greedy filter) is a sequential programme over small lists: lane 0 runs it on a working set that lives in SHARED
+// memory (path slots, per-vertex lists; clusters whose working set exceeds the per-warp budget fall back to a global scratch
+// arena).  The part that costs memory latency — one Bloom lookup per completed k-mer of every candidate path that is extended
+// by a vertex — is spread over the lanes: lane j rebuilds the window that ends at the j-th nucleotide of the vertex from the
+// path's 110-bit tail register, hashes its canonical form from the 4-nucleotide ntHash table and issues all its probes, so 32
+// lookups (up to 320 probes) are in flight per warp; the hit mask comes back through a ballot and lane 0 books the scores in
+// sequence order (VariantClusterGraphPath::updateScore).  Round 1 ran one THREAD per cluster on a global scratch arena:
+// 7.9 of 32 lanes active, every list access an L2 round trip (profiles/r1_find_sample_paths_ncu_full.txt).  The kernel is
+// persistent: warps draw clusters (largest first) from an atomic counter, so a few huge clusters do not leave a tail.
 #include <algorithm>
 #include <vector>
 
@@ -53,8 +59,11 @@ struct DevGraphs {
     const uint32_t *best_cap;       // [C] capacity in paths
     uint32_t *best_n;               // [C] current number of best paths
     uint8_t *best;                  // path x vertex membership bytes
-    uint32_t *status;               // [C] 0 ok, 1 scratch overflow
-    const uint32_t *order;          // [C] clusters sorted by (vertices, sequence length): the 32 clusters of a warp have the same shape
+    uint32_t *status;               // [0] = 1 + first cluster whose scratch overflowed (0 = none)
+    const uint32_t *order;          // [C] clusters sorted by (vertices, sequence length), largest first: the draw order of the warps
+    const uint32_t *cl_smem;        // [C] bytes of the cluster's working set when it fits the per-warp shared-memory budget, else 0
+    uint32_t *mt_pool;              // [resident warps][624] Mersenne states (materialised only when a cluster draws > kMtWindow numbers)
+    uint32_t *next;                 // work counter
 };
 
 // ---- std::mt19937 -------------------------------------------------------------------------------
@@ -152,8 +161,8 @@ __device__ void std_shuffle(uint16_t *a, uint32_t n, Mt19937 &g) {
 }
 
 // ---- one cluster's working set -------------------------------------------------------------------
-struct PathHdr {        // 64 bytes, followed by V bytes of per-vertex state (kAbsent or num_observed_kmers 0..2)
-    uint64_t fhi, flo, rhi, rlo, F, R;
+struct PathHdr {        // 32 bytes, followed by V bytes of per-vertex state (kAbsent or num_observed_kmers 0..2)
+    uint64_t fhi, flo;  // the last <= 55 nucleotides of the path (KmerPair's forward register, kmer.cuh internal form)
     uint32_t filled, score_first, score_second, nverts;
 };
 
@@ -272,24 +281,53 @@ __device__ void update_score(Work &w, PathHdr *h, uint8_t *pv, uint32_t cur_vert
     h->score_second++;
 }
 
-// VariantClusterGraphPath::addVertex (VariantClusterGraphPath.cpp:46-87)
-__device__ void add_vertex(Work &w, uint32_t slot, uint32_t v, const BloomView &bloom) {
+// VariantClusterGraphPath::addVertex (VariantClusterGraphPath.cpp:46-87) by the whole warp: lane j takes the k-mer window that ends
+// at nucleotide base + j of the vertex; lane 0 books the scores in order.  T = 4-nucleotide ntHash table (shared).
+__device__ void add_vertex_warp(Work &w, uint32_t slot, uint32_t v, const BloomView &bloom, const uint64_t *T, uint32_t lane) {
     PathHdr *h = w.hdr(slot);
     uint8_t *pv = w.verts(slot);
-    pv[v] = 0;
-    h->nverts++;
-    Roller r;
-    r.f.hi = h->fhi; r.f.lo = h->flo; r.r.hi = h->rhi; r.r.lo = h->rlo; r.F = h->F; r.R = h->R; r.filled = (int)h->filled;
     const uint32_t len = w.seq_len(v);
-    if (w.disconnected(v)) {
-        if (len == 0) pv[v] = kMinObserved;
-        r.reset();
+    const bool disc = w.disconnected(v);
+    if (lane == 0) {
+        pv[v] = 0;
+        h->nverts++;
+        if (disc) {
+            if (len == 0) pv[v] = kMinObserved;
+            h->fhi = h->flo = 0; h->filled = 0;  // KmerPair::reset
+        }
     }
+    __syncwarp();
+    Kmer128 f0{h->fhi, h->flo};
+    uint32_t filled0 = h->filled;
     const uint8_t *s = w.seq(v);
-    for (uint32_t i = 0; i < len; i++) {
-        if (r.push(s[i])) update_score(w, h, pv, v, bloom_contains(bloom, r.canonical_hash()), i + 1);
+    for (uint32_t base = 0; base < len; base += 32) {
+        const uint32_t n = len - base < 32 ? len - base : 32;   // nucleotides of this round
+        const uint32_t c_mine = lane < n ? s[base + lane] : 0u;
+        Kmer128 f = f0;
+        for (uint32_t t = 0; t < n; t++) {                      // shift in nucleotides base .. base + lane
+            const uint32_t ct = __shfl_sync(0xFFFFFFFFu, c_mine, t);
+            if (t <= lane) {
+                f.hi = ((f.hi << 2) | (f.lo >> 62)) & kHiMask;
+                f.lo = (f.lo << 2) | ct;
+            }
+        }
+        const bool complete = lane < n && filled0 + lane + 1 >= (uint32_t)K;
+        bool hit = false;
+        if (complete) {
+            const Kmer128 r = revcomp(f);
+            hit = bloom_contains(bloom, ntp64(forward_is_canonical(f, r) ? f : r, T));
+        }
+        const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, complete), hmask = __ballot_sync(0xFFFFFFFFu, hit);
+        f0.hi = __shfl_sync(0xFFFFFFFFu, f.hi, n - 1);
+        f0.lo = __shfl_sync(0xFFFFFFFFu, f.lo, n - 1);
+        filled0 = filled0 + n < (uint32_t)K ? filled0 + n : (uint32_t)K;
+        if (lane == 0)
+            for (uint32_t t = 0; t < n; t++)
+                if ((cmask >> t) & 1u) update_score(w, h, pv, v, (hmask >> t) & 1u, base + t + 1);
+        __syncwarp();
     }
-    h->fhi = r.f.hi; h->flo = r.f.lo; h->rhi = r.r.hi; h->rlo = r.r.lo; h->F = r.F; h->R = r.R; h->filled = (uint32_t)r.filled;
+    if (lane == 0) { h->fhi = f0.hi; h->flo = f0.lo; h->filled = filled0; }
+    __syncwarp();
 }
 
 __device__ __forceinline__ double kmer_score(const PathHdr *h) {  // getKmerScore (…GraphPath.cpp:137-149)
@@ -402,70 +440,105 @@ __device__ void add_path_indices(Work &w, const uint16_t *paths, uint32_t n) {
     g.best_n[w.c] = n_best;
 }
 
-// VariantClusterGraph::findSamplePaths (VariantClusterGraph.cpp:389-482), one thread per cluster
-__global__ void __launch_bounds__(64) k_find_sample_paths(DevGraphs g, BloomView bloom, uint32_t random_seed, uint32_t sample_idx, uint32_t max_paths) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= g.C) return;
-    // thread -> cluster through the shape order: neighbours along the genome differ in vertex count and sequence length and
-    // would keep 8 of 32 lanes busy (profiles/r1_find_sample_paths_ncu_full.txt)
-    const uint32_t c = g.order[t];
-    Work w;
-    w.g = &g; w.c = c;
-    w.v0 = g.cl_vertex_off[c];
-    w.V = (uint32_t)(g.cl_vertex_off[c + 1] - w.v0);
-    w.pool = g.cl_pool[c]; w.tmp_cap = g.cl_tmp[c];
-    w.slot_bytes = (uint32_t)(sizeof(PathHdr) + ((w.V + 7) & ~7u));
-    uint8_t *p = g.scratch + g.scr_off[c];
-    w.mt = reinterpret_cast<uint32_t *>(p); p += 624 * 4;
-    w.slots = p; p += (size_t)w.pool * w.slot_bytes;
-    w.lists = reinterpret_cast<uint16_t *>(p); p += (size_t)w.V * 32 * 2;
-    w.tmp = reinterpret_cast<uint16_t *>(p); p += (size_t)((w.tmp_cap + 3) & ~3u) * 2;
-    w.free_stack = reinterpret_cast<uint16_t *>(p); p += (size_t)((w.pool + 3) & ~3u) * 2;
-    w.list_n = p; p += (w.V + 7) & ~7u;
-    w.covered = p;
-    w.overflow = false;
-    w.n_free = w.pool;
-    for (uint32_t i = 0; i < w.pool; i++) w.free_stack[i] = (uint16_t)(w.pool - 1 - i);
-    // seed = r + (g+1)(s+1) + cluster_idx (KmerCounter.cpp:65, VariantClusterGroup.cpp:142)
-    Mt19937 rng;
-    rng.mt = w.mt;
-    rng.seed(random_seed + (g.cl_group[c] + 1) * (sample_idx + 1) + g.cl_idx[c]);
+// VariantClusterGraph::findSamplePaths (VariantClusterGraph.cpp:389-482): persistent kernel, one warp per cluster at a time
+constexpr uint32_t kPathWarps = 4;            // warps per block
+constexpr uint32_t kPathSmemPerWarp = 8192;   // shared-memory budget of one cluster's working set
 
-    for (uint32_t v = 0; v < w.V && !w.overflow; v++) {
-        uint32_t n = 0;
-        const uint64_t e0 = g.v_in_off[w.v0 + v], e1 = g.v_in_off[w.v0 + v + 1];
-        if (e0 == e1) {
-            const uint32_t s = w.alloc();
-            PathHdr *h = w.hdr(s);
-            h->fhi = h->flo = h->rhi = h->rlo = h->F = h->R = 0;
-            h->filled = h->score_first = h->score_second = h->nverts = 0;
-            uint8_t *pv = w.verts(s);
-            for (uint32_t i = 0; i < w.V; i++) pv[i] = kAbsent;
-            w.tmp[n++] = (uint16_t)s;
-        } else {
-            for (uint64_t e = e0; e < e1 && !w.overflow; e++) {
-                const uint32_t u = g.v_in_src[e];
-                merge_paths(w, n, w.lists + (size_t)u * 32, w.list_n[u]);
-                if (g.v_max_target[w.v0 + u] == v) {  // last consumer of u's paths
-                    for (uint32_t i = 0; i < w.list_n[u]; i++) w.release(w.lists[(size_t)u * 32 + i]);
-                    w.list_n[u] = 0;
-                }
-            }
+__global__ void __launch_bounds__(kPathWarps * 32) k_find_sample_paths(DevGraphs g, BloomView bloom, uint32_t random_seed, uint32_t sample_idx, uint32_t max_paths) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t *T = reinterpret_cast<uint64_t *>(smem);                    // [256] ntHash 4-nucleotide table
+    build_hash_table(T);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    uint8_t *my_smem = smem + 2048 + (size_t)wib * kPathSmemPerWarp;
+    uint32_t *my_mt = g.mt_pool + ((size_t)blockIdx.x * kPathWarps + wib) * 624;
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(g.next, 1u);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= g.C) break;
+        const uint32_t c = g.order[t];
+        Work w;
+        w.g = &g; w.c = c;
+        w.v0 = g.cl_vertex_off[c];
+        w.V = (uint32_t)(g.cl_vertex_off[c + 1] - w.v0);
+        w.pool = g.cl_pool[c]; w.tmp_cap = g.cl_tmp[c];
+        w.slot_bytes = (uint32_t)(sizeof(PathHdr) + ((w.V + 7) & ~7u));
+        uint8_t *p = g.cl_smem[c] ? my_smem : g.scratch + g.scr_off[c];
+        w.mt = my_mt;
+        w.slots = p; p += (size_t)w.pool * w.slot_bytes;
+        w.lists = reinterpret_cast<uint16_t *>(p); p += (size_t)w.V * 32 * 2;
+        w.tmp = reinterpret_cast<uint16_t *>(p); p += (size_t)((w.tmp_cap + 3) & ~3u) * 2;
+        w.free_stack = reinterpret_cast<uint16_t *>(p); p += (size_t)((w.pool + 3) & ~3u) * 2;
+        w.list_n = p; p += (w.V + 7) & ~7u;
+        w.covered = p;
+        w.overflow = false;
+        w.n_free = w.pool;
+        // seed = r + (g+1)(s+1) + cluster_idx (KmerCounter.cpp:65, VariantClusterGroup.cpp:142)
+        Mt19937 rng;
+        rng.mt = w.mt;
+        rng.seed(random_seed + (g.cl_group[c] + 1) * (sample_idx + 1) + g.cl_idx[c]);
+        if (lane == 0) {
+            for (uint32_t i = 0; i < w.pool; i++) w.free_stack[i] = (uint16_t)(w.pool - 1 - i);
+            for (uint32_t v = 0; v < w.V; v++) w.list_n[v] = 0;
         }
-        if (w.overflow) break;
-        std_shuffle(w.tmp, n, rng);
-        for (uint32_t i = 0; i < n; i++) add_vertex(w, w.tmp[i], v, bloom);
-        n = filter_paths(w, w.tmp, n, max_paths, false);
-        for (uint32_t i = 0; i < n; i++) w.lists[(size_t)v * 32 + i] = w.tmp[i];
-        w.list_n[v] = (uint8_t)n;
+        __syncwarp();
+        for (uint32_t v = 0; v < w.V; v++) {
+            uint32_t n = 0;
+            if (lane == 0 && !w.overflow) {
+                const uint64_t e0 = g.v_in_off[w.v0 + v], e1 = g.v_in_off[w.v0 + v + 1];
+                if (e0 == e1) {
+                    const uint32_t s = w.alloc();
+                    PathHdr *h = w.hdr(s);
+                    h->fhi = h->flo = 0;
+                    h->filled = h->score_first = h->score_second = h->nverts = 0;
+                    uint8_t *pv = w.verts(s);
+                    for (uint32_t i = 0; i < w.V; i++) pv[i] = kAbsent;
+                    w.tmp[n++] = (uint16_t)s;
+                } else {
+                    for (uint64_t e = e0; e < e1 && !w.overflow; e++) {
+                        const uint32_t u = g.v_in_src[e];
+                        merge_paths(w, n, w.lists + (size_t)u * 32, w.list_n[u]);
+                        if (g.v_max_target[w.v0 + u] == v) {  // last consumer of u's paths
+                            for (uint32_t i = 0; i < w.list_n[u]; i++) w.release(w.lists[(size_t)u * 32 + i]);
+                            w.list_n[u] = 0;
+                        }
+                    }
+                }
+                if (!w.overflow) std_shuffle(w.tmp, n, rng);
+            }
+            // lane 0's view of the DP state (n, overflow) for the cooperative part
+            n = __shfl_sync(0xFFFFFFFFu, n, 0);
+            const bool ovf = __shfl_sync(0xFFFFFFFFu, (uint32_t)w.overflow, 0) != 0;
+            __syncwarp();
+            if (ovf) { w.overflow = true; break; }
+            for (uint32_t i = 0; i < n; i++) add_vertex_warp(w, w.tmp[i], v, bloom, T, lane);
+            if (lane == 0) {
+                n = filter_paths(w, w.tmp, n, max_paths, false);
+                for (uint32_t i = 0; i < n; i++) w.lists[(size_t)v * 32 + i] = w.tmp[i];
+                w.list_n[v] = (uint8_t)n;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            if (!w.overflow) {
+                const uint32_t last = w.V - 1;
+                uint16_t *fin = w.lists + (size_t)last * 32;
+                const uint32_t n = filter_paths(w, fin, w.list_n[last], max_paths, true);
+                add_path_indices(w, fin, n);
+            }
+            if (w.overflow) atomicMax(g.status, c + 1);
+        }
+        __syncwarp();
     }
-    if (!w.overflow) {
-        const uint32_t last = w.V - 1;
-        uint16_t *fin = w.lists + (size_t)last * 32;
-        const uint32_t n = filter_paths(w, fin, w.list_n[last], max_paths, true);
-        add_path_indices(w, fin, n);
-    }
-    if (w.overflow) g.status[c] = 1;
+}
+
+// best_paths_indices as one byte per (path, vertex), cluster-major, without the unused capacity rows
+__global__ void k_compact_best(DevGraphs g, const uint64_t *out_off, uint8_t *out) {
+    const uint32_t c = blockIdx.x;
+    const uint64_t n = out_off[c + 1] - out_off[c];
+    const uint8_t *src = g.best + g.best_off[c];
+    for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) out[out_off[c] + i] = src[i] != kAbsent;
 }
 
 template <class T> T *upload(const T *h, size_t n, bool &ok) {
@@ -483,6 +556,7 @@ struct btg_graphs {
     std::vector<uint64_t> h_best_off, h_vertex_off;
     std::vector<uint32_t> h_best_cap;
     uint32_t n_samples_cap = 0;
+    uint32_t grid = 1;
 };
 
 extern "C" {
@@ -509,7 +583,7 @@ btg_graphs *btg_graphs_upload(const btg_graphs_desc *d, uint32_t max_samples, ui
     g.cl_group = keep(upload(d->cl_group, C, ok));
     g.cl_idx = keep(upload(d->cl_idx, C, ok));
     // per-cluster sizing: simulate the candidate counts of the vertex DP (upper bounds)
-    std::vector<uint32_t> max_target(Vtot), pool(C), tmpc(C), best_cap(C);
+    std::vector<uint32_t> max_target(Vtot), pool(C), tmpc(C), best_cap(C), cl_smem(C, 0);
     std::vector<uint64_t> scr_off(C + 1, 0), best_off(C + 1, 0);
     for (uint32_t c = 0; c < C; c++) {
         const uint64_t v0 = d->cl_vertex_off[c];
@@ -540,9 +614,11 @@ btg_graphs *btg_graphs_upload(const btg_graphs_desc *d, uint32_t max_samples, ui
         tmpc[c] = need_tmp + 1;
         best_cap[c] = max_sample_haplotypes * max_samples;
         const uint64_t slot_bytes = sizeof(PathHdr) + ((V + 7) & ~7u);
-        uint64_t bytes = 624 * 4 + (uint64_t)pool[c] * slot_bytes + (uint64_t)V * 64 + (uint64_t)((tmpc[c] + 3) & ~3u) * 2 +
-                         (uint64_t)((pool[c] + 3) & ~3u) * 2 + 2 * (uint64_t)((V + 7) & ~7u);
-        scr_off[c + 1] = scr_off[c] + ((bytes + 15) & ~15ull);
+        const uint64_t bytes = (uint64_t)pool[c] * slot_bytes + (uint64_t)V * 64 + (uint64_t)((tmpc[c] + 3) & ~3u) * 2 +
+                               (uint64_t)((pool[c] + 3) & ~3u) * 2 + 2 * (uint64_t)((V + 7) & ~7u);
+        // the working set of most clusters fits the per-warp shared-memory budget; only the others get a slice of the global arena
+        if (bytes <= kPathSmemPerWarp) cl_smem[c] = (uint32_t)bytes;
+        scr_off[c + 1] = scr_off[c] + (cl_smem[c] ? 0 : ((bytes + 15) & ~15ull));
         best_off[c + 1] = best_off[c] + (uint64_t)best_cap[c] * V;
     }
     if (ok) {
@@ -560,18 +636,24 @@ btg_graphs *btg_graphs_upload(const btg_graphs_desc *d, uint32_t max_samples, ui
         g.cl_tmp = keep(upload(tmpc.data(), C, ok));
         g.best_off = keep(upload(best_off.data(), C + 1, ok));
         g.best_cap = keep(upload(best_cap.data(), C, ok));
+        g.cl_smem = keep(upload(cl_smem.data(), C, ok));
+        // persistent grid: as many blocks as are co-resident; one Mersenne state per warp of the grid
+        int per_sm = 0;
+        const size_t smem = 2048 + (size_t)kPathWarps * kPathSmemPerWarp;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_find_sample_paths, kPathWarps * 32, smem);
+        gr->grid = (uint32_t)std::max(1, per_sm) * (uint32_t)ctx().sm_count;
         uint8_t *scratch = nullptr, *best = nullptr;
-        uint32_t *best_n = nullptr, *status = nullptr;
+        uint32_t *best_n = nullptr, *status = nullptr, *mt_pool = nullptr;
         ok = ok && cudaMalloc(&scratch, scr_off[C] + 16) == cudaSuccess;
         ok = ok && cudaMalloc(&best, best_off[C] + 16) == cudaSuccess;
-        ok = ok && cudaMalloc(&best_n, (C + 1) * 4) == cudaSuccess && cudaMalloc(&status, (C + 1) * 4) == cudaSuccess;
-        keep(scratch); keep(best); keep(best_n); keep(status);
+        ok = ok && cudaMalloc(&best_n, (C + 1) * 4) == cudaSuccess && cudaMalloc(&status, 2 * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&mt_pool, (size_t)gr->grid * kPathWarps * 624 * 4) == cudaSuccess;
+        keep(scratch); keep(best); keep(best_n); keep(status); keep(mt_pool);
         if (ok) {
-            cudaMemset(best_n, 0, (C + 1) * 4);
-            cudaMemset(status, 0, (C + 1) * 4);
-            cudaMemset(scratch, 0, scr_off[C] + 16);
+            cudaMemsetAsync(best_n, 0, (C + 1) * 4, ctx().stream);
+            cudaMemsetAsync(status, 0, 2 * 4, ctx().stream);
         }
-        g.scratch = scratch; g.best = best; g.best_n = best_n; g.status = status;
+        g.scratch = scratch; g.best = best; g.best_n = best_n; g.status = status; g.mt_pool = mt_pool; g.next = status + 1;
     }
     if (!ok) {
         if (!*btg_last_error()) set_error("graph upload failed (%s)", cudaGetErrorString(cudaGetLastError()));
@@ -583,6 +665,14 @@ btg_graphs *btg_graphs_upload(const btg_graphs_desc *d, uint32_t max_samples, ui
     gr->h_vertex_off.assign(d->cl_vertex_off, d->cl_vertex_off + C + 1);
     gr->n_samples_cap = max_samples;
     return gr;
+}
+
+int btg_graphs_reset(btg_graphs *gr) {
+    BTG_REQUIRE_INIT();
+    if (!gr) { set_error("null argument"); return BTG_EINVAL; }
+    BTG_CUDA(cudaMemsetAsync(gr->g.best_n, 0, ((size_t)gr->g.C + 1) * 4, ctx().stream));
+    BTG_CUDA(cudaMemsetAsync(gr->g.status, 0, 2 * 4, ctx().stream));
+    return BTG_OK;
 }
 
 void btg_graphs_free(btg_graphs *gr) {
@@ -598,15 +688,14 @@ int btg_find_sample_paths(btg_graphs *gr, const btg_bloom *sample_bloom, uint32_
     if (sample_idx >= gr->n_samples_cap) { set_error("sample index %u beyond the capacity given at upload (%u)", sample_idx, gr->n_samples_cap); return BTG_EINVAL; }
     if (max_sample_haplotypes == 0 || max_sample_haplotypes > 32) { set_error("max_sample_haplotypes must be 1..32"); return BTG_EINVAL; }
     if (gr->g.C == 0) return BTG_OK;
+    // asynchronous on the library stream: the samples of a unit queue up behind each other (addPathIndices merges in sample order);
+    // a scratch overflow is reported by btg_get_best_paths
     auto s = ctx().stream;
-    k_find_sample_paths<<<(gr->g.C + 63) / 64, 64, 0, s>>>(gr->g, btg_internal::bloom_view(sample_bloom), random_seed, sample_idx, max_sample_haplotypes);
+    BTG_CUDA(cudaMemsetAsync(gr->g.next, 0, 4, s));
+    const size_t smem = 2048 + (size_t)kPathWarps * kPathSmemPerWarp;
+    k_find_sample_paths<<<gr->grid, kPathWarps * 32, smem, s>>>(gr->g, btg_internal::bloom_view(sample_bloom), random_seed, sample_idx, max_sample_haplotypes);
     BTG_LAUNCHED();
     BTG_CUDA(cudaGetLastError());
-    BTG_CUDA(cudaStreamSynchronize(s));
-    std::vector<uint32_t> status(gr->g.C);
-    BTG_CUDA(cudaMemcpy(status.data(), gr->g.status, gr->g.C * 4, cudaMemcpyDeviceToHost));
-    for (uint32_t c = 0; c < gr->g.C; c++)
-        if (status[c]) { set_error("cluster %u: path-search scratch overflow", c); return BTG_ESTATE; }
     return BTG_OK;
 }
 
@@ -614,20 +703,32 @@ int btg_get_best_paths(const btg_graphs *gr, uint32_t *n_paths_out, uint64_t *pa
     BTG_REQUIRE_INIT();
     if (!gr || !n_paths_out) { set_error("null argument"); return BTG_EINVAL; }
     const uint32_t C = gr->g.C;
-    BTG_CUDA(cudaStreamSynchronize(ctx().stream));
+    auto s = ctx().stream;
+    BTG_CUDA(cudaStreamSynchronize(s));
+    uint32_t status = 0;
+    BTG_CUDA(cudaMemcpy(&status, gr->g.status, 4, cudaMemcpyDeviceToHost));
+    if (status) { set_error("cluster %u: path-search scratch overflow", status - 1); return BTG_ESTATE; }
     BTG_CUDA(cudaMemcpy(n_paths_out, gr->g.best_n, C * 4, cudaMemcpyDeviceToHost));
     if (!path_off_out) return BTG_OK;
     path_off_out[0] = 0;
     for (uint32_t c = 0; c < C; c++) path_off_out[c + 1] = path_off_out[c] + (uint64_t)n_paths_out[c] * (gr->h_vertex_off[c + 1] - gr->h_vertex_off[c]);
     if (!membership_out) return BTG_OK;
     if (membership_bytes < path_off_out[C]) { set_error("membership buffer too small"); return BTG_EINVAL; }
-    std::vector<uint8_t> all(gr->h_best_off[C]);
-    BTG_CUDA(cudaMemcpy(all.data(), gr->g.best, all.size(), cudaMemcpyDeviceToHost));
-    for (uint32_t c = 0; c < C; c++) {
-        const uint64_t n = path_off_out[c + 1] - path_off_out[c];
-        for (uint64_t i = 0; i < n; i++) membership_out[path_off_out[c] + i] = all[gr->h_best_off[c] + i] != kAbsent;
+    if (C == 0 || path_off_out[C] == 0) return BTG_OK;
+    // compact on the device (the capacity rows of best_paths_indices never cross the bus), then one copy out
+    uint64_t *d_off = nullptr;
+    uint8_t *d_out = nullptr;
+    int rc = BTG_OK;
+    if (cudaMalloc(&d_off, (C + 1) * 8) != cudaSuccess || cudaMalloc(&d_out, path_off_out[C]) != cudaSuccess) { set_error("best-path compaction: allocation failed"); rc = BTG_ENOMEM; }
+    if (rc == BTG_OK) {
+        cudaMemcpyAsync(d_off, path_off_out, (C + 1) * 8, cudaMemcpyHostToDevice, s);
+        k_compact_best<<<C, 64, 0, s>>>(gr->g, d_off, d_out);
+        BTG_LAUNCHED();
+        cudaMemcpyAsync(membership_out, d_out, path_off_out[C], cudaMemcpyDeviceToHost, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("best-path compaction failed: %s", cudaGetErrorString(cudaGetLastError())); rc = BTG_ECUDA; }
     }
-    return BTG_OK;
+    cudaFree(d_off); cudaFree(d_out);
+    return rc;
 }
 
 }  // extern "C"

@@ -97,7 +97,7 @@ def merge_best_paths(graphs: dict, parts, cluster_lists):
     return n_paths, mem
 
 
-def find_variant_cluster_paths(lib, graphs: dict, sample_blooms, opt: Options):
+def find_variant_cluster_paths(lib, graphs: dict, sample_blooms, opt: Options, cache: dict | None = None):
     """KmerCounter::findVariantClusterPaths (KmerCounter.cpp:70-103): samples in order, one Bloom at a time."""
     gco = graphs["group_cluster_off"]
     keep = {
@@ -112,7 +112,15 @@ def find_variant_cluster_paths(lib, graphs: dict, sample_blooms, opt: Options):
     d.n_clusters = len(keep["cl_vertex_off"]) - 1
     for k, v in keep.items():
         setattr(d, k, v.ctypes.data)
-    gr = capi.check(lib.btg_graphs_upload(C.addressof(d), len(sample_blooms), opt.max_sample_haplotypes), lib)
+    # the graphs of a unit (and the path-search scratch) stay in HBM between passes when the caller gives a cache (Inputs.resident_cache)
+    key = ("graphs", id(graphs), len(sample_blooms), opt.max_sample_haplotypes)
+    gr = cache.get(key) if cache is not None else None
+    if gr is None:
+        gr = capi.check(lib.btg_graphs_upload(C.addressof(d), len(sample_blooms), opt.max_sample_haplotypes), lib)
+        if cache is not None:
+            cache[key] = gr
+    else:
+        capi.check(lib.btg_graphs_reset(gr), lib)
     try:
         for s, b in enumerate(sample_blooms):
             capi.check(lib.btg_find_sample_paths(gr, b, s, opt.random_seed, opt.max_sample_haplotypes), lib)
@@ -122,7 +130,8 @@ def find_variant_cluster_paths(lib, graphs: dict, sample_blooms, opt: Options):
         mem = np.zeros(int(off[-1]), np.uint8)
         capi.check(lib.btg_get_best_paths(gr, capi.ptr(n_paths), capi.ptr(off), capi.ptr(mem), mem.size), lib)
     finally:
-        lib.btg_graphs_free(gr)
+        if cache is None:
+            lib.btg_graphs_free(gr)
     return n_paths.astype(np.int64), mem
 
 
@@ -212,6 +221,7 @@ class Inputs:
     blooms_dev: list = None
     region_buf_dev: object = None
     native_builder: bool = False       # cluster construction through host/btcluster (same arrays, ~15x faster) instead of graph_builder.py
+    resident_cache: dict = dataclasses.field(default_factory=dict)   # device handles that outlive a pass (graphs of the unit + path-search scratch)
 
     def prepare(self):
         if self.graphs is None:
@@ -243,6 +253,10 @@ class Inputs:
         for b in self.blooms_dev or []:
             lib.btg_bloom_free(b)
         self.blooms_dev = None
+        for k, h in list(self.resident_cache.items()):
+            if k[0] == "graphs":
+                lib.btg_graphs_free(h)
+        self.resident_cache.clear()
 
 
 def _to_dev(a, dtype, dev):
@@ -322,11 +336,13 @@ def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rate
     if sharded:
         mine = shard.my_groups(G)
         sub, my_clusters = subset_graphs_for_paths(inp.graphs, mine)
-        part = find_variant_cluster_paths(lib, sub, blooms, opt)
+        if resident:                                   # the shard's sub-graphs are part of the resident state too
+            sub = inp.resident_cache.setdefault(("subgraphs", shard.rank, shard.world), sub)
+        part = find_variant_cluster_paths(lib, sub, blooms, opt, inp.resident_cache if resident else None)
         parts = shard.allgather((part[0], part[1], my_clusters))
         n_paths, mem = merge_best_paths(inp.graphs, [(p[0], p[1]) for p in parts], [p[2] for p in parts])
     else:
-        n_paths, mem = find_variant_cluster_paths(lib, inp.graphs, blooms, opt)
+        n_paths, mem = find_variant_cluster_paths(lib, inp.graphs, blooms, opt, inp.resident_cache if resident else None)
     if own_blooms:
         for b in blooms:
             lib.btg_bloom_free(b)

@@ -252,7 +252,7 @@ def run_ours(args):
 
     if args.timed_only:          # profiler runs (ncu launch list): the warm-up + timed steps only; not a bench line
         if rank == 0:
-            print(json.dumps({"timed_only": True, "ms_per_step": ms_per_step, "value": value, "gpu_launches": launches, "n_clusters": n_clusters}), flush=True)
+            emit({"timed_only": True, "ms_per_step": ms_per_step, "value": value, "gpu_launches": launches, "n_clusters": n_clusters})
         inp.free(lib)
         return
     # ---- e2e: every input crosses the boundary from host memory inside the call --------------------------
@@ -317,7 +317,7 @@ def run_ours(args):
     if rank == 0:
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(args.config, args.cpu_variants or (3000 if args.config == "B" else 120), os.cpu_count() or 1)
-        print(json.dumps(line), flush=True)
+        emit(line)
     inp.free(lib)
     if shard_ctx is not None:
         shard_ctx.comm.close()
@@ -483,7 +483,7 @@ def run_reference(args):
             continue            # a CPU process has no clocks or caches to warm beyond the first run: one warm-up run stands for all W
         last = cpu_reference(args.config, n_var, threads)
         if last["value"] is None:
-            print(json.dumps({"impl": "reference", "unavailable": last["sample"]}))
+            emit({"impl": "reference", "unavailable": last["sample"]})
             return
         if i >= args.warmup:
             vals.append(last)
@@ -498,7 +498,25 @@ def run_reference(args):
                        "samples": 30 if args.config == "D" else 1, "gibbs": "20 chains x (100 burn-in + 250 samples), k-mer subsampling 0.1",
                        "step": "the reference's own cluster + genotype stages on the host cores", "sample": last["sample"], "threads": threads},
             "cpu_baseline": cb, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line: everything else that libraries print there (NCCL's version banner at communicator creation,
+    whatever NCCL_DEBUG_FILE says) is sent to stderr by pointing fd 1 at fd 2; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
@@ -514,6 +532,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timed-only", action="store_true", help="warm-up + timed steps only (for ncu launch lists); prints no bench line")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

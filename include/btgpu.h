@@ -143,9 +143,13 @@ typedef struct btg_graphs_desc {
 
 typedef struct btg_graphs btg_graphs;
 btg_graphs *btg_graphs_upload(const btg_graphs_desc *desc, uint32_t max_samples, uint32_t max_sample_haplotypes);
+/* forget the best paths found so far (a new pass over the samples of the same unit: the graphs and the scratch stay in HBM) */
+int btg_graphs_reset(btg_graphs *g);
 void btg_graphs_free(btg_graphs *g);
 /* one sample's pass (samples must be submitted in order 0..S-1: addPathIndices merges order-dependently,
- * VariantClusterGraph.cpp:726-798).  seed of cluster c: random_seed + (group+1)*(sample_idx+1) + cluster_idx */
+ * VariantClusterGraph.cpp:726-798).  seed of cluster c: random_seed + (group+1)*(sample_idx+1) + cluster_idx.
+ * Asynchronous on the library stream (the passes of a unit queue up behind each other; the Bloom filter must stay alive until
+ * btg_get_best_paths or a synchronisation); a scratch overflow is reported by btg_get_best_paths. */
 int btg_find_sample_paths(btg_graphs *g, const btg_bloom *sample_bloom, uint32_t sample_idx, uint32_t random_seed,
                           uint32_t max_sample_haplotypes);
 /* best_paths_indices: n_paths_out[C]; path_off_out[C+1] (prefix sums of n_paths*V, optional); membership_out
