@@ -70,7 +70,7 @@ __global__ void k_lgamma_int(double *out, uint32_t n) {
 // which otherwise set the kernel's tail (one thread: 1.3 s while the mean thread takes 0.16 s, profiles/r1_gibbs_tail.txt), run
 // their chains on kChainSplit threads with private arena positions; k_merge_split adds the pieces up and summarises.
 template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(64, MIN_BLOCKS) k_estimate_genotypes(DevUnit du, Tables T, btg_gibbs_opts o, ResultView R, int reconverge, unsigned long long *dbg) {
+__global__ void __launch_bounds__(64, MIN_BLOCKS) k_estimate_genotypes(DevUnit du, Tables T, btg_gibbs_opts o, ResultView R, int reconverge, unsigned long long *dbg, int hot) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long t_in = dbg ? global_timer_ns() : 0;
     // no early return: every lane of the warp reaches the __syncwarp()s below
@@ -90,8 +90,10 @@ __global__ void __launch_bounds__(64, MIN_BLOCKS) k_estimate_genotypes(DevUnit d
         cluster = du.order[live ? i : 0];
         if (live && du.split_of[cluster] != NONE32) live = false;  // handled above
     }
+    extern __shared__ __align__(16) uint8_t hot_smem[];
     Cl cl;
     cl.bind(du, cluster, pos);
+    if (hot && live && !split && cl.H <= kHotH) cl.bind_hot(hot_smem, threadIdx.x, blockDim.x);  // small cluster: hot state in shared memory
     const uint64_t gidx = group_index(o, cl.g);
     const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
     Philox prng, fr;
@@ -165,17 +167,17 @@ __global__ void __launch_bounds__(64) k_estimate_genotypes_nested(DevUnit du, Ta
         Philox prng, fr;
         prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, 0);
         fr.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngFrequency, 0);
-        prng.save(cl.misc, kRng0);
-        fr.save(cl.misc, kRng1);
+        prng.save(cl.rng, kRng0);
+        fr.save(cl.rng, kRng1);
     }
     const uint32_t iters = (uint32_t)o.gibbs_burn_in + o.gibbs_samples;
     for (uint32_t chain = 0; chain < o.n_chains; chain++) {
         for (uint32_t j = 0; j < n; j++) {
             cl.bind(du, (uint32_t)(c0 + j));
             Philox prng;
-            prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+            prng.load(cl.rng, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
             cl_reset<true>(cl, o, prng);
-            prng.save(cl.misc, kRng0);
+            prng.save(cl.rng, kRng0);
         }
         {   // shuffleBranchOrdering: sources, then every vertex's out-edges in vertex order (stream kind 3)
             Philox br;
@@ -212,13 +214,13 @@ __global__ void __launch_bounds__(64) k_estimate_genotypes_nested(DevUnit du, Ta
                 cl.bind(du, (uint32_t)(c0 + v));
                 const uint32_t ns = du.nest_slot[c0 + v];
                 Philox prng, fr;
-                prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
-                fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
+                prng.load(cl.rng, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+                fr.load(cl.rng, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
                 cl_sample_diplotypes<true>(cl, T, du.nest_pl + (size_t)ns * S, collect, prng);
                 if (collect) cl_add_nested_stats(cl, ns);
                 cl_sample_frequencies(cl, fr);
-                prng.save(cl.misc, kRng0);
-                fr.save(cl.misc, kRng1);
+                prng.save(cl.rng, kRng0);
+                fr.save(cl.rng, kRng1);
                 for (uint64_t e = du.cl_edge_off[c0 + v]; e < du.cl_edge_off[c0 + v + 1]; e++) {
                     const uint32_t t = du.edge_mut[e], nt = du.nest_slot[c0 + t];
                     for (uint32_t s = 0; s < S; s++) {
@@ -268,7 +270,8 @@ __global__ void k_noise_update(NoiseState ns, uint32_t S, float prior_shape, flo
 #endif
 __global__ void __launch_bounds__(256, BTG_NOISE_MINBLOCKS) k_noise_chain(DevUnit du, Tables T, btg_gibbs_opts o, const uint32_t *sel, uint32_t n_sel, uint32_t n_big, uint32_t chain,
                                                        uint32_t iters, NoiseState ns, float prior_shape, float prior_scale, unsigned long long *hist, int joint,
-                                                       PeerExchange px, const uint32_t *fill_tasks, uint32_t n_fill_tasks, GridBarrier gb) {
+                                                       PeerExchange px, const uint32_t *fill_tasks, uint32_t n_fill_tasks, GridBarrier gb, int hot) {
+    extern __shared__ __align__(16) uint8_t hot_smem[];
     __shared__ unsigned long long sh_tot[kMailRow];
     __shared__ double sh_rates[BTG_MAX_SAMPLES];
     // getNoiseCounts of the block's clusters: only (n_obs, sum) per sample are ever read from the merged CountAllocation,
@@ -288,18 +291,22 @@ __global__ void __launch_bounds__(256, BTG_NOISE_MINBLOCKS) k_noise_chain(DevUni
                 prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, stream_chain);
                 fr.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngFrequency, stream_chain);
             } else {
-                prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
-                fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
+                prng.load(cl.rng, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+                fr.load(cl.rng, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
             }
             cl_reset<false, true>(cl, o, prng);
-            prng.save(cl.misc, kRng0);
-            fr.save(cl.misc, kRng1);
+            prng.save(cl.rng, kRng0);
+            fr.save(cl.rng, kRng1);
         }
         __syncwarp();
     }
     for (uint32_t i = n_big + tid; i < n_sel; i += nthreads) {  // initGenotypersCallback: fresh genotypers every chain
         Cl cl;
         cl.bind(du, sel[i]);
+        // a thread's FIRST cluster keeps its hot state in the thread's slice of shared memory for the whole chain when it is small
+        // (estimateNoise only: the joint mode keeps its genotypers across chains, i.e. across launches, in the arena)
+        const bool resident = hot && i == n_big + tid && cl.H <= kHotH;
+        if (resident) cl.bind_hot(hot_smem, threadIdx.x, blockDim.x);
         const uint64_t gidx = group_index(o, cl.g);
         Philox prng, fr;
         if (!joint || chain == 1) {
@@ -308,12 +315,13 @@ __global__ void __launch_bounds__(256, BTG_NOISE_MINBLOCKS) k_noise_chain(DevUni
             prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, stream_chain);
             fr.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngFrequency, stream_chain);
         } else {
-            prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
-            fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
+            prng.load(cl.rng, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+            fr.load(cl.rng, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
         }
         cl_reset<false, true>(cl, o, prng);
-        prng.save(cl.misc, kRng0);
-        fr.save(cl.misc, kRng1);
+        if (resident && cl.tile_fits_hot()) cl.move_tile_to_hot();
+        prng.save(cl.rng, kRng0);
+        fr.save(cl.rng, kRng1);
     }
     if (blockIdx.x == 0 && ns.trace) noise_update_block(ns, du.S, prior_shape, prior_scale, o.random_seed, 3, 0, (double)chain, 0, 1, sh_rates);
     grid_barrier(gb);
@@ -354,6 +362,10 @@ __global__ void __launch_bounds__(256, BTG_NOISE_MINBLOCKS) k_noise_chain(DevUni
 #endif
             Cl cl;
             cl.bind(du, sel[i]);
+            if (hot && i == n_big + tid && cl.H <= kHotH) {
+                cl.bind_hot(hot_smem, threadIdx.x, blockDim.x);
+                if (cl.tile_fits_hot()) cl.bind_hot_tile();
+            }
             tick(0);
             const uint8_t *ploidy_i = du.group_ploidy + (size_t)cl.g * du.S;
             cl_fill_cache_rows(cl, T, ploidy_i);  // > 4 live haplotypes: entries are filled on demand
@@ -361,15 +373,15 @@ __global__ void __launch_bounds__(256, BTG_NOISE_MINBLOCKS) k_noise_chain(DevUni
             {
                 const uint64_t gidx = group_index(o, cl.g);
                 Philox prng, fr;
-                prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
-                fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
+                prng.load(cl.rng, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+                fr.load(cl.rng, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
                 tick(2);
                 cl_sample_diplotypes<false, true>(cl, T, ploidy_i, joint && it > o.gibbs_burn_in, prng);
                 tick(3);
                 cl_sample_frequencies(cl, fr);
                 tick(4);
-                prng.save(cl.misc, kRng0);
-                fr.save(cl.misc, kRng1);
+                prng.save(cl.rng, kRng0);
+                fr.save(cl.rng, kRng1);
                 tick(5);
             }
 #if BTG_NOISE_TIMING
@@ -875,9 +887,19 @@ int btg_estimate_genotypes_async(btg_unit *u, const btg_count_dist *cd, const bt
         const unsigned grid = (u->du.n_regular + u->du.n_split * kChainSplit + 63) / 64;
         unsigned long long *dbg = nullptr;
         if (getenv("BTG_GIBBS_TIMING")) { cudaMalloc(&dbg, 32); cudaMemset(dbg, 0, 32); }
-        if (occ >= 16) k_estimate_genotypes<16><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R, reconverge, dbg);
-        else if (occ >= 12) k_estimate_genotypes<12><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R, reconverge, dbg);
-        else k_estimate_genotypes<8><<<grid, 64, 0, pick_stream(stream)>>>(u->du, T, *opts, dr->R, reconverge, dbg);
+        // hot state of the small clusters in shared memory (gibbs_core.cuh): hot_bytes(S) per thread, as long as the blocks of an SM still fit
+        const size_t hot_smem = (size_t)hot_bytes(u->du.S) * 64;
+        static const int hot_env = getenv("BTG_HOT") ? atoi(getenv("BTG_HOT")) : 1;
+        const int hot = hot_env && hot_smem * 6 <= 220 * 1024;
+        const size_t smem = hot ? hot_smem : 0;
+        if (hot) {
+            cudaFuncSetAttribute(k_estimate_genotypes<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_estimate_genotypes<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_estimate_genotypes<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
+        if (occ >= 16) k_estimate_genotypes<16><<<grid, 64, smem, pick_stream(stream)>>>(u->du, T, *opts, dr->R, reconverge, dbg, hot);
+        else if (occ >= 12) k_estimate_genotypes<12><<<grid, 64, smem, pick_stream(stream)>>>(u->du, T, *opts, dr->R, reconverge, dbg, hot);
+        else k_estimate_genotypes<8><<<grid, 64, smem, pick_stream(stream)>>>(u->du, T, *opts, dr->R, reconverge, dbg, hot);
         BTG_LAUNCHED();
         BTG_CUDA(cudaGetLastError());
         if (u->du.n_split) {
@@ -970,6 +992,16 @@ static void lockstep_fill_tasks(const btg_unit *u, uint32_t c, uint32_t sel_idx,
         parts = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, by_terms ? (entries + 3) / 4 : (entries + 31) / 32));
     }
     for (uint32_t p = 0; p < parts; p++) { tasks.push_back(sel_idx); tasks.push_back(p); tasks.push_back(parts); }
+}
+
+// dynamic shared memory of k_noise_chain: the hot state of each thread's first cluster (gibbs_core.cuh), as long as two blocks still fit an SM
+static size_t noise_chain_hot_smem(uint32_t S, uint32_t bs, int *hot_out) {
+    static const int hot_env = getenv("BTG_HOT") ? atoi(getenv("BTG_HOT")) : 1;
+    const size_t bytes = (size_t)hot_bytes(S) * bs;
+    const int hot = hot_env && bytes * 2 <= 220 * 1024;
+    if (hot) cudaFuncSetAttribute(k_noise_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    *hot_out = hot;
+    return hot ? bytes : 0;
 }
 
 static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, double *trace_out, int joint);
@@ -1154,8 +1186,9 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
             px.timeout_ns = (tmo ? strtoull(tmo, nullptr, 10) : 20000ull) * 1000000ull;
         }
         const uint32_t bs = 256;
-        int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_noise_chain, bs, 0);
+        int per_sm = 0, hot = 0;
+        const size_t hot_smem = noise_chain_hot_smem(S, bs, &hot);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_noise_chain, bs, hot_smem);
         const uint32_t capacity = (uint32_t)std::max(1, per_sm) * (uint32_t)ctx().sm_count;
         const uint32_t max_blocks = std::max(1u, (K > 1 ? capacity - capacity / 16 : capacity) / K);  // this chain's share of the SMs (a few block slots stay free)
         for (auto &st : streams) cudaStreamWaitEvent(st, ev_ready, 0);
@@ -1194,12 +1227,12 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
             unsigned long long *hist = (unsigned long long *)ns.hist;
             if (comm) { px.seq0 = comm->seq; comm->seq += iters; }
             DevUnit du_k = u->shadow_du[k];
-            void *args[] = {&du_k, &T, &o, &sel_b, &n_sel, &n_big, &chain_id, &iters_arg, &ns, &ps, &pc, &hist, &joint, &px, &tasks_b, &n_tasks, &gb};
+            void *args[] = {&du_k, &T, &o, &sel_b, &n_sel, &n_big, &chain_id, &iters_arg, &ns, &ps, &pc, &hist, &joint, &px, &tasks_b, &n_tasks, &gb, &hot};
             cudaError_t e;
             if (u->du.wide) {  // warp per cluster, lane = sample (gibbs_wide.cu)
                 e = wide_noise_chain(du_k, T, o, sel_b, n_sel, n_big, tasks_b, n_tasks, chain_id, iters_arg, ns, ps, pc, hist, joint, px, gb, K, ctx().sm_count, st);
             } else {
-                e = cudaLaunchCooperativeKernel((void *)k_noise_chain, dim3(grid), dim3(bs), args, 0, st);
+                e = cudaLaunchCooperativeKernel((void *)k_noise_chain, dim3(grid), dim3(bs), args, hot_smem, st);
                 BTG_LAUNCHED();
             }
             if (e != cudaSuccess) { set_error("cooperative launch failed: %s", cudaGetErrorString(e)); rc = BTG_ECUDA; break; }
@@ -1382,9 +1415,9 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
             if (n_sel || world > 1) {  // a rank with nothing selected still takes part in every exchange
                 // (a shared-memory window of the log-pmf tables was tried and made the fill slower: the chain is bound by instruction issue
                 //  at 16 warps/SM, not by the gathers — profiles/r1_noise_chain_phases.txt)
-                const size_t smem = 0;
                 const uint32_t bs = 256;
-                int per_sm = 0;
+                int per_sm = 0, hot = 0;
+                const size_t smem = use_wide || joint ? 0 : noise_chain_hot_smem(S, bs, &hot);
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_noise_chain, bs, smem);
                 const uint32_t max_blocks = (uint32_t)std::max(1, per_sm) * (uint32_t)ctx().sm_count;
                 const uint32_t want_threads = std::max<uint32_t>({n_big * 32u, n_sel - n_big, (uint32_t)(tasks.size() / 3) * 32u});
@@ -1394,7 +1427,7 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
                 btg_gibbs_opts o = *opts;
                 if (comm) { px.seq0 = comm->seq; comm->seq += iters; }
                 uint32_t n_tasks = (uint32_t)(tasks.size() / 3);
-                void *args[] = {&u->du, &T, &o, &d_sel, &n_sel_arg, &n_big, &chain_id, &iters_arg, &ns, &ps, &pc, &hist, &joint, &px, &d_tasks, &n_tasks, &gb};
+                void *args[] = {&u->du, &T, &o, &d_sel, &n_sel_arg, &n_big, &chain_id, &iters_arg, &ns, &ps, &pc, &hist, &joint, &px, &d_tasks, &n_tasks, &gb, &hot};
                 cudaError_t e;
                 if (use_wide) {
                     e = wide_noise_chain(u->du, T, o, d_sel, n_sel_arg, n_big, d_tasks, n_tasks, chain_id, iters_arg, ns, ps, pc, hist, joint, px, gb, 1, ctx().sm_count, s);

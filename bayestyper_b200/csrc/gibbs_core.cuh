@@ -227,8 +227,21 @@ __host__ __device__ inline ArenaSizes arena_sizes(uint32_t S, uint32_t H, uint32
     return a;
 }
 
-enum Misc { kNSub = 0, kNumHap = 1, kNumMissing = 2, kSimplexNobs = 3, kSimplexPlus = 4, kSimplexLen = 5, kSparse = 6, kCover = 7, kRng0 = 8, kRng1 = 17,
-            kNMultiSub = 26, kUseMulti = 27 };   // a saved stream takes 9 words (Philox::save)
+enum Misc { kNSub = 0, kNumHap = 1, kNumMissing = 2, kSimplexNobs = 3, kSimplexPlus = 4, kSimplexLen = 5, kSparse = 6, kCover = 7, kNMultiSub = 8, kUseMulti = 9,
+            kMiscWords = 12 };
+enum RngSave { kRng0 = 0, kRng1 = 9, kRngWords = 20 };   // a saved stream takes 9 words (Philox::save)
+
+// HOT STATE IN SHARED MEMORY.  The sampler's step is a chain of dependent accesses to the cluster's own small arrays (frequencies,
+// counts, caches, cumulative log-probs, the k-mer tile); in the arena every one of them is an L2 round trip, and that latency was the
+// whole cost of an iteration (85-110 k cycles per one-thread SNV cluster, profiles/r1_noise_chain_phases.txt).  A thread that keeps ONE
+// cluster for a whole chain binds these arrays to a slice of the block's shared memory instead (element e of thread t at e * blockDim + t:
+// conflict-free), when the cluster has at most kHotH haplotype candidates — > 90 % of the clusters of a real unit.  Same code, same
+// arithmetic: only the addresses change.
+constexpr uint32_t kHotH = 2, kHotDall = (kHotH + 1) * (kHotH + 2) / 2, kHotTile = 24;
+__host__ __device__ inline uint32_t hot_f64(uint32_t S) { return kHotH * 2 + (kHotH + 1) + kHotH * (kHotH + 1) + S * kHotDall + kHotDall + 2; }
+__host__ __device__ inline uint32_t hot_u32(uint32_t S) { return kHotH + S + kMiscWords; }
+__host__ __device__ inline uint32_t hot_u8(uint32_t S) { return (kHotH + S + kHotTile * (kHotH + S + 2) + 3u) & ~3u; }
+__host__ __device__ inline uint32_t hot_bytes(uint32_t S) { return hot_f64(S) * 8 + hot_u32(S) * 4 + hot_u8(S); }
 
 // per-cluster view
 struct Cl {
@@ -239,9 +252,11 @@ struct Cl {
     const DevUnit *u;
     const uint8_t *M;
     LaneArr<double> freq, logf, simplex, simplex_tab, ucache, cum, kc_f, as_f, mcache, fmisc;
-    LaneArr<uint32_t> obs, uniq, uniq_sub, cnt, tally, kc_n, as_n, dipl, multi, multi_sub, misc;
+    LaneArr<uint32_t> obs, uniq, uniq_sub, cnt, tally, kc_n, as_n, dipl, multi, multi_sub, misc, rng;
     LaneArr<uint8_t> nz, uncovered, stats_update, sample_multi;
     TileArr tile_m, tile_c, tile_ic;
+    uint8_t *hot_tile = nullptr;   // shared-memory tile of a cluster whose hot state is bound to shared memory (bind_hot)
+    uint32_t hot_stride = 0;
 
     __device__ void bind(const DevUnit &du, uint32_t cluster, uint32_t pos_override = 0xFFFFFFFFu) {
         u = &du; c = cluster;
@@ -286,7 +301,8 @@ struct Cl {
         dipl = w; w = w + S;
         multi = w; w = w + SL.n_multi;
         multi_sub = w; w = w + SL.n_multi;
-        misc = w;
+        misc = w; w = w + kMiscWords;
+        rng = w;
         LaneArr<uint8_t> b{du.u8_pool + SL.u8_off + lane, st};
         nz = b; b = b + SL.H;
         uncovered = b; b = b + SL.K;
@@ -303,6 +319,45 @@ struct Cl {
             tile_c = TileArr{b.p, st}; b = b + (uint64_t)SL.n_uniq * S;
             tile_ic = TileArr{b.p, st};
         }
+    }
+    // rebinds the hot arrays to this thread's slice of the block's shared memory (smem: hot_bytes(S) * nthreads bytes); requires H <= kHotH
+    // and no multicluster k-mers.  Whatever the arrays held in the arena is NOT carried over (see hot_copy).
+    __device__ void bind_hot(uint8_t *smem, uint32_t tid, uint32_t nthreads) {
+        LaneArr<double> f{reinterpret_cast<double *>(smem) + tid, nthreads};
+        freq = f; f = f + kHotH;
+        logf = f; f = f + kHotH;
+        simplex = f; f = f + (kHotH + 1);
+        has_simplex_tab = true;
+        simplex_tab = f; f = f + kHotH * (kHotH + 1);
+        ucache = f; f = f + S * kHotDall;
+        cum = f; f = f + kHotDall;
+        cum_stride = 0;
+        fmisc = f;
+        LaneArr<uint32_t> w{reinterpret_cast<uint32_t *>(smem + (size_t)hot_f64(S) * 8 * nthreads) + tid, nthreads};
+        obs = w; w = w + kHotH;
+        dipl = w; w = w + S;
+        misc = w;
+        LaneArr<uint8_t> b{smem + ((size_t)hot_f64(S) * 8 + (size_t)hot_u32(S) * 4) * nthreads + tid, nthreads};
+        nz = b; b = b + kHotH;
+        stats_update = b; b = b + S;
+        hot_tile = b.p;
+        hot_stride = nthreads;
+    }
+    // the k-mer tile of the current subsample moves into the shared slice when it has at most kHotTile rows (after cl_reset built it)
+    __device__ __forceinline__ bool tile_fits_hot() const { return hot_tile != nullptr && misc[kNSub] <= kHotTile; }
+    __device__ void bind_hot_tile() {
+        uint8_t *t = hot_tile;
+        tile_m = TileArr{t, hot_stride}; t += (size_t)kHotTile * kHotH * hot_stride;
+        tile_c = TileArr{t, hot_stride}; t += (size_t)kHotTile * S * hot_stride;
+        tile_ic = TileArr{t, hot_stride};
+    }
+    __device__ void move_tile_to_hot() {
+        const uint32_t n_sub = misc[kNSub];
+        const TileArr am = tile_m, ac = tile_c, ai = tile_ic;
+        bind_hot_tile();
+        for (uint32_t i = 0; i < n_sub * H; i++) tile_m[i] = am[i];
+        for (uint32_t i = 0; i < n_sub * S; i++) tile_c[i] = ac[i];
+        for (uint32_t i = 0; i < n_sub * 2; i++) tile_ic[i] = ai[i];
     }
     // k-mer tile (lock-step modes, where the diplotype caches are cleared every iteration): row i holds everything the
     // likelihood reads about the i-th k-mer of the current subsample, so the per-iteration gathers touch three compact
@@ -1290,12 +1345,12 @@ __device__ __forceinline__ void noise_iteration_thread(Cl &cl, const DevUnit &du
     const uint64_t gidx = group_index(o, cl.g);
     const uint8_t *ploidy = du.group_ploidy + (size_t)cl.g * du.S;
     Philox prng, fr;
-    prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
-    fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
+    prng.load(cl.rng, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+    fr.load(cl.rng, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
     cl_sample_diplotypes<false, true>(cl, T, ploidy, collect, prng);
     cl_sample_frequencies(cl, fr);
-    prng.save(cl.misc, kRng0);
-    fr.save(cl.misc, kRng1);
+    prng.save(cl.rng, kRng0);
+    fr.save(cl.rng, kRng1);
 }
 
 // Grid-wide barrier of the persistent chain kernel (all blocks are co-resident: cooperative launch).  One thread per block

@@ -243,16 +243,16 @@ __device__ __forceinline__ void group_iteration(const DevUnit &du, const Tables 
         const uint32_t ns = MC ? du.nest_slot[c0 + v] : 0u;
         const uint8_t *ploidy = MC ? du.nest_pl + (size_t)ns * S : du.group_ploidy + (size_t)g * S;
         Philox prng, fr;
-        prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+        prng.load(cl.rng, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
         clw_sample_diplotypes<MC>(cl, T, ploidy, collect, prng, lane);
         if constexpr (MC) {
             if (collect && lane < S) cl_add_nested_stats(cl, ns, lane, lane + 1);
         }
         if (lane == 0) {
-            fr.load(cl.misc, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
+            fr.load(cl.rng, kRng1, o.random_seed, gidx, du.cluster_idx[cl.c]);
             cl_sample_frequencies(cl, fr);
-            fr.save(cl.misc, kRng1);
-            cl.misc[kRng0 + 8] = prng.t_draw;  // the sequential part of the genotyper's stream is untouched by an iteration
+            fr.save(cl.rng, kRng1);
+            cl.rng[kRng0 + 8] = prng.t_draw;  // the sequential part of the genotyper's stream is untouched by an iteration
         }
         __syncwarp();
         if constexpr (MC) clw_pass_nested_info(cl, du, c0, v, ns, lane);
@@ -323,8 +323,8 @@ __global__ void __launch_bounds__(128) k_estimate_genotypes_nested_wide(DevUnit 
             Philox prng, fr;
             prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, 0);
             fr.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngFrequency, 0);
-            prng.save(cl.misc, kRng0);
-            fr.save(cl.misc, kRng1);
+            prng.save(cl.rng, kRng0);
+            fr.save(cl.rng, kRng1);
         }
         __syncwarp();
     }
@@ -334,9 +334,9 @@ __global__ void __launch_bounds__(128) k_estimate_genotypes_nested_wide(DevUnit 
             Cl cl;
             cl.bind(du, (uint32_t)(c0 + j));
             Philox prng;
-            prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+            prng.load(cl.rng, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
             clw_reset<true>(cl, o, prng, lane, false);
-            if (lane == 0) prng.save(cl.misc, kRng0);
+            if (lane == 0) prng.save(cl.rng, kRng0);
             __syncwarp();
         }
         if (lane == 0) group_branch_order(du, o, g, chain);
@@ -385,12 +385,12 @@ __global__ void __launch_bounds__(256, 2) k_noise_chain_wide(DevUnit du, Tables 
                 cl_construct_warp(cl, o, gidx, stream_chain, lane);
                 prng.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngGenotyper, stream_chain);
                 fr.init(o.random_seed, gidx, du.cluster_idx[cl.c], kRngFrequency, stream_chain);
-                if (lane == 0) fr.save(cl.misc, kRng1);
+                if (lane == 0) fr.save(cl.rng, kRng1);
             } else {
-                prng.load(cl.misc, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
+                prng.load(cl.rng, kRng0, o.random_seed, gidx, du.cluster_idx[cl.c]);
             }
             if (n > 1) clw_reset<true>(cl, o, prng, lane, false); else clw_reset<false>(cl, o, prng, lane, false);
-            if (lane == 0) prng.save(cl.misc, kRng0);
+            if (lane == 0) prng.save(cl.rng, kRng0);
             __syncwarp();
         }
         if (n > 1) {
