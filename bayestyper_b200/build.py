@@ -55,7 +55,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
         objs.append(obj)
         if not force and _newer(obj, [cu] + [d for d in deps if d.suffix in (".cuh", ".h")]):
             continue
-        cmd = [NVCC, *NVCC_FLAGS, *PER_FILE_FLAGS.get(cu.name, []), "-I", str(ROOT / "include"), "-c", str(cu), "-o", str(obj)]
+        cmd = [NVCC, *NVCC_FLAGS, *PER_FILE_FLAGS.get(cu.name, []), *os.environ.get("BTG_EXTRA_NVCC_FLAGS", "").split(), "-I", str(ROOT / "include"), "-c", str(cu), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((cu, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

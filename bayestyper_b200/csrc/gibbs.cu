@@ -22,6 +22,13 @@
 // reference's depth-first order every iteration.  The joint noise mode still requires single-cluster groups.
 #include "gibbs_core.cuh"
 
+// clusters whose cache fill costs more than this many table lookups PER SAMPLE are worked on by a warp in the lock-step chains (dense
+// k-mer tile, grid-wide fill in the first iteration); the others run one per thread.  BTG_NOISE_BIG overrides (sweeps: profiles/).
+static uint32_t big_fill_cost() {
+    static const uint32_t v = getenv("BTG_NOISE_BIG") ? (uint32_t)strtoul(getenv("BTG_NOISE_BIG"), nullptr, 10) : kBigFillCost;
+    return v;
+}
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------
@@ -342,15 +349,50 @@ __global__ void __launch_bounds__(256, BTG_NOISE_MINBLOCKS) k_noise_chain(DevUni
         // (cluster, part, parts) gives one warp every parts-th round of 32 cache entries of that cluster, so the slowest
         // cluster no longer sets the pace of the iteration with a single warp
         // (tasks are dealt from the LAST warp downwards: the one-thread clusters below occupy the first threads of the grid)
-        for (uint32_t t = (nthreads >> 5) - 1 - (tid >> 5); t < n_fill_tasks; t += nthreads >> 5) {
+        // That matters in the FIRST iteration of a chain only: reset leaves every haplotype live (H (H + 1) / 2 entries per sample), after one
+        // sampleHaplotypeFrequencies the sparse prior keeps a handful.  From the second iteration on a large cluster is ONE warp's job — fill
+        // (lanes = entries or terms), sample, count — in the same phase as everything else: no fill tasks whose only content is the bind of a
+        // cluster with nothing to fill (80 per warp and iteration on configs[1]), no second phase, one grid barrier less.
+        const bool spread = it == 1;
+        // the step of a large cluster's owner warp once its caches are filled (lane 0 samples; counts and cache clear by all lanes)
+        auto owner_step = [&](Cl &cl, uint32_t lane) {
             const unsigned long long t_in = BTG_NOISE_TIMING && ns.phase_ns ? global_timer_ns() : 0;
-            Cl cl;
-            cl.bind(du, sel[fill_tasks[3 * t]]);
-            cl_fill_cache_warp(cl, T, du.group_ploidy + (size_t)cl.g * du.S, tid & 31u, fill_tasks[3 * t + 1], fill_tasks[3 * t + 2]);
-            if (BTG_NOISE_TIMING && ns.phase_ns) { const unsigned long long v = ((global_timer_ns() - t_in) << 32) | cl.c; atomicMax(ns.phase_ns + 4, v); atomicMax(ns.phase_ns + 8 + 3 * (it - 1), v); }
+            if (lane == 0) noise_iteration_thread(cl, du, T, o, joint && it > o.gibbs_burn_in);
+            if (BTG_NOISE_TIMING && ns.phase_ns && lane == 0) { const unsigned long long v = ((global_timer_ns() - t_in) << 32) | cl.c; atomicMax(ns.phase_ns + 5, v); atomicMax(ns.phase_ns + 8 + 3 * (it - 1) + 1, v); }
+            __syncwarp();
+            const uint32_t n_sub = cl.misc[kNSub];
+            for (uint32_t s = 0; s < cl.S; s++) {  // getNoiseCounts
+                const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
+                uint32_t n0 = 0, c0 = 0;
+                const uint32_t g = du.sample_gender[s];
+                for (uint32_t j = lane; j < n_sub; j += 32)
+                    if ((uint8_t)(cl.tileDiplMult(j, da, db) + cl.tile_ic[j * 2 + g]) == 0) { n0++; c0 += cl.tile_c[j * cl.S + s]; }
+                if (n0) { atomicAdd(sh_stat + 2 * s, (unsigned long long)n0); atomicAdd(sh_stat + 2 * s + 1, (unsigned long long)c0); }
+            }
+            for (uint32_t j = lane; j < cl.S * cl.Dall; j += 32) cl.ucache[j] = nan;  // clearGenotyperCache
+            __syncwarp();
+        };
+        if (spread) {
+            for (uint32_t t = (nthreads >> 5) - 1 - (tid >> 5); t < n_fill_tasks; t += nthreads >> 5) {
+                const unsigned long long t_in = BTG_NOISE_TIMING && ns.phase_ns ? global_timer_ns() : 0;
+                Cl cl;
+                cl.bind(du, sel[fill_tasks[3 * t]]);
+                cl_fill_cache_warp(cl, T, du.group_ploidy + (size_t)cl.g * du.S, tid & 31u, fill_tasks[3 * t + 1], fill_tasks[3 * t + 2]);
+                if (BTG_NOISE_TIMING && ns.phase_ns) { const unsigned long long v = ((global_timer_ns() - t_in) << 32) | cl.c; atomicMax(ns.phase_ns + 4, v); atomicMax(ns.phase_ns + 8 + 3 * (it - 1), v); }
+            }
+        } else {
+            for (uint32_t i = (nthreads >> 5) - 1 - (tid >> 5); i < n_big; i += nthreads >> 5) {
+                Cl cl;
+                cl.bind(du, sel[i]);
+                cl_fill_cache_warp(cl, T, du.group_ploidy + (size_t)cl.g * du.S, tid & 31u, 0, 1);
+                __syncwarp();
+                owner_step(cl, tid & 31u);
+            }
         }
         // ... while the one-thread clusters sel[n_big .. n_sel) take their whole step in the same phase (they do not depend on the
         // fill tasks): the warps that hold no fill task are not idle at the barrier while the large caches are filled
+        constexpr uint32_t kAccSamples = 4;
+        uint32_t acc_n0[kAccSamples] = {0, 0, 0, 0}, acc_c0[kAccSamples] = {0, 0, 0, 0};
         for (uint32_t i = n_big + tid; i < n_sel; i += nthreads) {  // sampleGenotypesCallback
             const unsigned long long t_in = BTG_NOISE_TIMING && ns.phase_ns ? global_timer_ns() : 0;
 #if BTG_NOISE_TIMING
@@ -398,35 +440,26 @@ __global__ void __launch_bounds__(256, BTG_NOISE_MINBLOCKS) k_noise_chain(DevUni
                     const uint8_t mm = (uint8_t)(cl.tileDiplMult(j, da, db) + cl.tile_ic[j * 2 + g]), cc = cl.tile_c[j * cl.S + s];
                     n0 += mm == 0; c0 += mm == 0 ? cc : 0u;
                 }
-                if (n0) { atomicAdd(sh_stat + 2 * s, (unsigned long long)n0); atomicAdd(sh_stat + 2 * s + 1, (unsigned long long)c0); }
+                if (s < kAccSamples) { acc_n0[s] += n0; acc_c0[s] += c0; }   // one reduction per phase instead of two shared atomics per cluster
+                else if (n0) { atomicAdd(sh_stat + 2 * s, (unsigned long long)n0); atomicAdd(sh_stat + 2 * s + 1, (unsigned long long)c0); }
             }
             tick(6);
             for (uint32_t j = 0; j < cl.S * cl.Dall; j++) cl.ucache[j] = nan;  // clearGenotyperCache
             tick(7);
         }
-        if (n_fill_tasks) grid_barrier(gb);
-        lap(0);
-        // phase B: sel[0 .. n_big): one WARP each (lane 0 samples from the filled cache; counts and cache clear by all lanes)
-        for (uint32_t i = tid >> 5; i < n_big; i += nthreads >> 5) {
-            const uint32_t lane = tid & 31u;
-            const unsigned long long t_in = BTG_NOISE_TIMING && ns.phase_ns ? global_timer_ns() : 0;
-            Cl cl;
-            cl.bind(du, sel[i]);
-            if (lane == 0) noise_iteration_thread(cl, du, T, o, joint && it > o.gibbs_burn_in);
-            if (BTG_NOISE_TIMING && ns.phase_ns && lane == 0) { const unsigned long long v = ((global_timer_ns() - t_in) << 32) | cl.c; atomicMax(ns.phase_ns + 5, v); atomicMax(ns.phase_ns + 8 + 3 * (it - 1) + 1, v); }
-            __syncwarp();
-            const uint32_t n_sub = cl.misc[kNSub];
-            for (uint32_t s = 0; s < cl.S; s++) {  // getNoiseCounts
-                const uint32_t da = cl.dipl[s] & 0xFFFFu, db = cl.dipl[s] >> 16;
-                uint32_t n0 = 0, c0 = 0;
-                const uint32_t g = du.sample_gender[s];
-                for (uint32_t j = lane; j < n_sub; j += 32)
-                    if ((uint8_t)(cl.tileDiplMult(j, da, db) + cl.tile_ic[j * 2 + g]) == 0) { n0++; c0 += cl.tile_c[j * cl.S + s]; }
-                if (n0) { atomicAdd(sh_stat + 2 * s, (unsigned long long)n0); atomicAdd(sh_stat + 2 * s + 1, (unsigned long long)c0); }
-            }
-            for (uint32_t j = lane; j < cl.S * cl.Dall; j += 32) cl.ucache[j] = nan;  // clearGenotyperCache
-            __syncwarp();
+        for (uint32_t s = 0; s < kAccSamples && s < du.S; s++) {   // the noise counts of this thread's clusters: warp sum, one atomic per warp
+            const uint32_t n0 = __reduce_add_sync(0xFFFFFFFFu, acc_n0[s]), c0 = __reduce_add_sync(0xFFFFFFFFu, acc_c0[s]);
+            if ((threadIdx.x & 31u) == 0 && n0) { atomicAdd(sh_stat + 2 * s, (unsigned long long)n0); atomicAdd(sh_stat + 2 * s + 1, (unsigned long long)c0); }
         }
+        if (spread && n_fill_tasks) grid_barrier(gb);
+        lap(0);
+        // phase B (first iteration of the chain): sel[0 .. n_big), one WARP each, sample from the caches the grid has filled
+        if (spread)
+            for (uint32_t i = tid >> 5; i < n_big; i += nthreads >> 5) {
+                Cl cl;
+                cl.bind(du, sel[i]);
+                owner_step(cl, tid & 31u);
+            }
         __syncthreads();
         if (threadIdx.x < 2 * du.S && sh_stat[threadIdx.x]) atomicAdd(hist + threadIdx.x, sh_stat[threadIdx.x]);
         grid_barrier(gb);
@@ -774,7 +807,7 @@ btg_unit *btg_unit_upload_dev(const btg_unit_desc *d, const btg_unit_desc *dev, 
     std::vector<uint64_t> tile_off(C ? C : 1, ~0ull);
     uint64_t tile_total = 0;
     for (uint32_t c = 0; c < C; c++)
-        if (!du.wide && u->h_fill_cost[c] > (uint64_t)kBigFillCost * S) { tile_off[c] = tile_total; tile_total += ((uint64_t)dims[c].nu * (dims[c].H + S + 2) + 31) & ~31ull; }
+        if (!du.wide && u->h_fill_cost[c] > (uint64_t)big_fill_cost() * S) { tile_off[c] = tile_total; tile_total += ((uint64_t)dims[c].nu * (dims[c].H + S + 2) + 31) & ~31ull; }
     du.big_tile_off = keep(upload(tile_off.data(), C, ok));
     uint8_t *tile_pool = nullptr;
     ok = ok && cudaMalloc(&tile_pool, tile_total + 32) == cudaSuccess;
@@ -973,7 +1006,7 @@ int btg_unit_cluster_tally(const btg_unit *u, uint32_t cluster, uint32_t *tally_
 // sample): the same per-lane cost bound, for single-cluster groups whose slot holds the dense caches.
 static bool lockstep_is_big(const btg_unit *u, uint32_t c, bool warp_kernel) {
     const uint32_t S = u->du.S;
-    if (!(u->h_fill_cost[c] > (uint64_t)kBigFillCost * S)) return false;
+    if (!(u->h_fill_cost[c] > (uint64_t)big_fill_cost() * S)) return false;
     if (!warp_kernel) return true;
     const uint32_t g = u->h_layout[c].group;
     if (u->h_group_cluster_off[g + 1] - u->h_group_cluster_off[g] != 1) return false;
@@ -1264,6 +1297,32 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
             const double n_it = (double)n_chains * iters;
             fprintf(stderr, "[btgpu] noise chain phases, us per iteration (block 0, chains one after the other): fill+one-thread %.1f  large owners %.1f  exchange+update %.1f  release %.1f; construct+reset %.2f ms per chain\n",
                     ph[0] / n_it / 1e3, ph[1] / n_it / 1e3, ph[2] / n_it / 1e3, ph[3] / n_it / 1e3, ph[7] / 1e6 / std::max(1u, n_chains));
+            const char *what[3] = {"fill task", "large-cluster owner", "one-thread cluster"};
+            for (int k = 0; k < 3 && BTG_NOISE_TIMING; k++) {
+                const uint32_t c = (uint32_t)(ph[4 + k] & 0xFFFFFFFFu);
+                if (ph[4 + k] && c < u->du.C)
+                    fprintf(stderr, "[btgpu]   slowest %s: %.1f us, cluster %u (H %u, variants %llu, fill cost %u)\n", what[k], (ph[4 + k] >> 32) / 1e3, c, u->h_nhap[c],
+                            (unsigned long long)(u->h_cl_var_off[c + 1] - u->h_cl_var_off[c]), u->h_fill_cost[c]);
+            }
+            if (BTG_NOISE_TIMING) {   // per-iteration maxima: median over iterations
+                std::vector<unsigned long long> it_max(3 * (size_t)iters);
+                cudaMemcpy(it_max.data(), d_phase + 8, it_max.size() * 8, cudaMemcpyDeviceToHost);
+                for (int k = 0; k < 3; k++) {
+                    std::vector<double> us;
+                    for (uint32_t i = 10; i < iters; i++) us.push_back((it_max[3 * i + k] >> 32) / 1e3);
+                    if (us.empty()) continue;
+                    std::sort(us.begin(), us.end());
+                    fprintf(stderr, "[btgpu]   per-iteration slowest %s: median %.1f us, p90 %.1f us\n", what[k], us[us.size() / 2], us[us.size() * 9 / 10]);
+                }
+                unsigned long long sub[16];
+                cudaMemcpy(sub, d_phase + 8 + 3 * (size_t)iters, sizeof sub, cudaMemcpyDeviceToHost);
+                const char *nm[8] = {"bind", "fill rows", "rng load", "sample diplotypes", "sample frequencies", "rng save", "noise counts", "clear cache"};
+                if (sub[8]) {
+                    fprintf(stderr, "[btgpu]   one-thread clusters, mean cycles per cluster-iteration:");
+                    for (int k = 0; k < 8; k++) fprintf(stderr, " %s %.0f;", nm[k], (double)sub[k] / (double)sub[8]);
+                    fprintf(stderr, "\n");
+                }
+            }
         }
     } else if (rc != BTG_OK && !*btg_last_error()) {
         set_error("noise estimation allocation failed");

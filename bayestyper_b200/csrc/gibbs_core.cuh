@@ -45,8 +45,13 @@ __host__ __device__ inline bool floatCompare(float a, float b) {  // Utils.hpp:8
     return (a == b) || (fabsf(a - b) < fabsf(a < b ? a : b) * kFloatEps100);
 }
 __host__ __device__ inline bool floatLess(float a, float b) { return (a < b) && !floatCompare(a, b); }
-BTG_LEAF double logAddition(double a, double b) {  // Utils.hpp:105-124
-    return a < b ? b + m_log1p(m_exp(a - b)) : a + m_log1p(m_exp(b - a));
+// Utils::logAddition (Utils.hpp:105-124): hi + log1p(exp(lo - hi)).  When lo - hi < -45 the addend is below exp(-45) = 2.9e-20, less than
+// half an ulp of any |hi| >= 2^-9, so the sum rounds to hi whatever the libm: the two transcendental calls are skipped and the result is the
+// same bits.  Most diplotypes of a large cluster are that far below the best one, and the running sum is a chain of these calls.
+BTG_LEAF double logAddition(double a, double b) {
+    const double hi = a < b ? b : a, lo = a < b ? a : b;
+    if (lo - hi < -45.0 && fabs(hi) >= 0.001953125) return hi;
+    return hi + m_log1p(m_exp(lo - hi));
 }
 
 static __device__ double nbLogPmf(double p, double size, uint32_t obs, uint32_t scale) {  // NegativeBinomialDistribution.cpp:121-147
@@ -123,7 +128,7 @@ struct TileArr {
     uint32_t stride;
     __device__ __forceinline__ uint8_t &operator[](uint32_t i) const { return p[(size_t)i * stride]; }
 };
-constexpr uint32_t kBigFillCost = 128;
+constexpr uint32_t kBigFillCost = 384;   // sweep on configs[1] with the hot state and the merged phases: profiles/r2_noise_chain_big_sweep.txt (128 was the round-1 value)
 constexpr uint32_t kChainSplit = 20;      // virtual threads of a chain-split cluster (chain c runs on thread c % kChainSplit)
 constexpr uint32_t kSplitFillCost = 64;   // clusters above this fill cost are chain-split in the default mode (sweep: profiles/r1_gibbs_tail.txt)
 constexpr uint32_t NONE32 = 0xFFFFFFFFu;
@@ -443,6 +448,56 @@ __device__ __forceinline__ double tile_entry_sum(const Cl &cl, const Tables &T, 
 // tile is walked once per sample and every k-mer updates all diplotype sums, so the gathers of one k-mer (up to 10,
 // independent) are in flight together and each tile byte is read once instead of once per diplotype.  Every entry is
 // still the sum of its terms in subsample order.  Used where the caches are cleared every iteration (lock-step modes).
+// The common case — at most two live haplotypes, i.e. three diplotype sums — walks the tile FOUR k-mers at a time: the (up to) twelve table
+// gathers of a round are issued before any of them is added, so a cluster-iteration waits for ceil(n_sub / 4) L2 round trips instead of n_sub
+// (50 k cycles per SNV cluster-iteration were spent waiting for one gather after the other, profiles/r2_noise_chain_phases.txt).  The sums
+// are still taken in subsample order.
+__device__ __forceinline__ void cl_fill_cache_rows2(Cl &cl, const Tables &T, const uint8_t *ploidy, uint32_t hs0, uint32_t hs1, uint32_t n) {
+    const uint32_t H = cl.H, n_sub = cl.misc[kNSub];
+    for (uint32_t s = 0; s < cl.S; s++) {
+        const uint8_t pl = ploidy[s];
+        if (pl == 0) continue;
+        const uint32_t g = cl.u->sample_gender[s];
+        double a00 = 0, a01 = 0, a11 = 0;
+        for (uint32_t i0 = 0; i0 < n_sub; i0 += 4) {
+            const double *p00[4], *p01[4], *p11[4];
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++) {
+                const uint32_t i = i0 + j < n_sub ? i0 + j : n_sub - 1;   // the tail repeats the last row; its values are not added
+                const uint8_t c = cl.tile_c[i * cl.S + s], base = cl.tile_ic[i * 2 + g];
+                const uint8_t m0 = cl.tile_m[i * H + hs0], m1 = n > 1 ? cl.tile_m[i * H + hs1] : 0;
+                if (pl == 2) {
+                    p00[j] = T.entry(s, (uint8_t)(m0 + m0 + base), c);
+                    p01[j] = T.entry(s, (uint8_t)(m0 + m1 + base), c);
+                    p11[j] = T.entry(s, (uint8_t)(m1 + m1 + base), c);
+                } else {
+                    p00[j] = T.entry(s, (uint8_t)(m0 + base), c);
+                    p11[j] = T.entry(s, (uint8_t)(m1 + base), c);
+                    p01[j] = p00[j];
+                }
+            }
+            double v00[4], v01[4], v11[4];
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++) {
+                v00[j] = *p00[j];
+                v01[j] = n > 1 && pl == 2 ? *p01[j] : 0.0;
+                v11[j] = n > 1 ? *p11[j] : 0.0;
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++)
+                if (i0 + j < n_sub) { a00 += v00[j]; a01 += v01[j]; a11 += v11[j]; }
+        }
+        const size_t cb = (size_t)s * cl.Dall;
+        if (pl == 2) {
+            cl.ucache[cb + cl.slot(hs0, hs0)] = a00;
+            if (n > 1) { cl.ucache[cb + cl.slot(hs0, hs1)] = a01; cl.ucache[cb + cl.slot(hs1, hs1)] = a11; }
+        } else {  // haploid entries live in the (h, "missing") slots
+            cl.ucache[cb + cl.slot(hs0, H)] = a00;
+            if (n > 1) cl.ucache[cb + cl.slot(hs1, H)] = a11;
+        }
+    }
+}
+
 __device__ __forceinline__ bool cl_fill_cache_rows(Cl &cl, const Tables &T, const uint8_t *ploidy) {
     const uint32_t H = cl.H, n_sub = cl.misc[kNSub];
     uint32_t hs0 = 0, hs1 = 0, hs2 = 0, hs3 = 0, n = 0;
@@ -451,6 +506,7 @@ __device__ __forceinline__ bool cl_fill_cache_rows(Cl &cl, const Tables &T, cons
             if (n == 0) hs0 = h; else if (n == 1) hs1 = h; else if (n == 2) hs2 = h; else if (n == 3) hs3 = h; else return false;
             n++;
         }
+    if (n <= 2 && n_sub > 0) { cl_fill_cache_rows2(cl, T, ploidy, hs0, hs1, n); return true; }
     for (uint32_t s = 0; s < cl.S; s++) {
         const uint8_t pl = ploidy[s];
         if (pl == 0) continue;
