@@ -56,26 +56,66 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    """SM clocks + throttle reasons sampled DURING the timed region, through NVML in-process (nvidia_ml_py): spawning nvidia-smi every
+    100 ms (round 1) takes the driver lock ~10 times a second and slowed the step it was watching by 15 %; even NVML at 5 Hz slowed the
+    persistent lock-step kernels progressively (2.1 -> 3.9 s per step over four steps), so the rate is 1 Hz.  Falls back to nvidia-smi
+    when NVML cannot be loaded."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.rows = []          # (sm_mhz, sm_max_mhz, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap)
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        self.nvml = None
+        self._max = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                idx = int(vis.split(",")[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        if self._max is None:
+            self._max = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = self._max
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        bit = lambda name_new, name_old: getattr(n, name_new, getattr(n, name_old, 0))
+        self.rows.append((sm, mx,
+                          bool(r & bit("nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown")),
+                          bool(r & bit("nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown")),
+                          bool(r & bit("nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown")),
+                          bool(r & bit("nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            f = [x.strip() for x in out.split(",")]
+            if f[0].isdigit():
+                self.rows.append((int(f[0]), int(f[1]) if f[1].isdigit() else None, *[x.lower().startswith("active") for x in f[2:6]]))
 
     def _run(self):
+        if os.environ.get("BTG_BENCH_NO_CLOCKS"):
+            return
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(1.0)     # 1 Hz: every query of the driver slows the lock-step chain kernel it is watching (5 Hz cost the step up to 1.8x)
 
     def __enter__(self):
         self._t.start()
@@ -88,11 +128,11 @@ class ClockSampler:
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        sm = sorted(r[0] for r in self.rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i] for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons, "samples": len(self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -236,8 +276,11 @@ def run_ours(args):
     with ClockSampler(local_rank) as clocks:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        step_wall = []
         for _ in range(args.steps):
-            _, _, res, info = driver.genotype(inp, opt, resident=True, shard=shard_ctx)
+            t_step = time.perf_counter()
+            _, _, res, info = driver.genotype(inp, opt, resident=True, shard=shard_ctx)     # returns with the results on the host: the step has ended
+            step_wall.append((time.perf_counter() - t_step) * 1e3)
         e1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
@@ -312,6 +355,7 @@ def run_ours(args):
         "clocks": clocks.summary(),
         "roofline": roof,
         "stage_ms": stage_ms,
+        "step_wall_ms": step_wall,
         "setup_s": setup_s,
     }
     if rank == 0:
