@@ -80,11 +80,13 @@ def write_parameter_kmers(prefix, kmers: np.ndarray, max_kmers: int = 1_000_000)
 
 
 def read_parameter_kmers(prefix) -> np.ndarray:
-    with gzip.open(str(prefix) + ".fa.gz", "rb") as f:
-        head = f.readline().rstrip(b"\n")
-        if head != f">k{K}".encode():
-            raise ValueError(f"parameter k-mer file starts with {head!r}, expected >k{K}")
-        body = f.read()
+    raw = open(str(prefix) + ".fa.gz", "rb").read()
+    if raw[:2] == b"\x1f\x8b":           # gzip as the reference writes it; a plain-text file (oracle-R's iostreams shim does not compress) is accepted too
+        raw = gzip.decompress(raw)
+    nl = raw.find(b"\n")
+    head, body = raw[:nl], raw[nl + 1:]
+    if head != f">k{K}".encode():
+        raise ValueError(f"parameter k-mer file starts with {head!r}, expected >k{K}")
     if len(body) % (K + 1):
         raise ValueError("parameter k-mer file holds a line that is not 55 nucleotides long")
     lines = np.frombuffer(body, np.uint8).reshape(-1, K + 1)

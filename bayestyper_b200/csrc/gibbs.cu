@@ -1006,7 +1006,7 @@ int btg_unit_cluster_tally(const btg_unit *u, uint32_t cluster, uint32_t *tally_
 // sample): the same per-lane cost bound, for single-cluster groups whose slot holds the dense caches.
 static bool lockstep_is_big(const btg_unit *u, uint32_t c, bool warp_kernel) {
     const uint32_t S = u->du.S;
-    if (!(u->h_fill_cost[c] > (uint64_t)big_fill_cost() * S)) return false;
+    if (!(u->h_fill_cost[c] > (uint64_t)(warp_kernel ? kBigFillCostWarp : big_fill_cost()) * S)) return false;
     if (!warp_kernel) return true;
     const uint32_t g = u->h_layout[c].group;
     if (u->h_group_cluster_off[g + 1] - u->h_group_cluster_off[g] != 1) return false;

@@ -129,6 +129,7 @@ struct TileArr {
     __device__ __forceinline__ uint8_t &operator[](uint32_t i) const { return p[(size_t)i * stride]; }
 };
 constexpr uint32_t kBigFillCost = 384;   // sweep on configs[1] with the hot state and the merged phases: profiles/r2_noise_chain_big_sweep.txt (128 was the round-1 value)
+constexpr uint32_t kBigFillCostWarp = 128;   // the same bound for the warp-per-cluster kernel (lane = sample): per-lane lookups of one fill
 constexpr uint32_t kChainSplit = 20;      // virtual threads of a chain-split cluster (chain c runs on thread c % kChainSplit)
 constexpr uint32_t kSplitFillCost = 64;   // clusters above this fill cost are chain-split in the default mode (sweep: profiles/r1_gibbs_tail.txt)
 constexpr uint32_t NONE32 = 0xFFFFFFFFu;

@@ -135,13 +135,16 @@ def find_variant_cluster_paths(lib, graphs: dict, sample_blooms, opt: Options, c
     return n_paths.astype(np.int64), mem
 
 
-def estimate_nb_parameters(pipe: kmer_pipeline.KmerPipeline, region_buf, spectra_dev, genders, opt: Options, ploidy=(2, 2)):
+def estimate_nb_parameters(pipe: kmer_pipeline.KmerPipeline, region_buf, spectra_dev, genders, opt: Options, ploidy=(2, 2), parameter_kmers=None):
     """Parameter k-mers -> per-sample negative-binomial (p, size): the genotype-side half of
     countInterclusterParameterKmers + calculateKmerStats + setGenomicCountDistributions
     (KmerCounter.cpp:171-250, KmerHash.cpp:257-347, CountDistribution.cpp:66-141).
     Parameter k-mers = inter-cluster reference k-mers that are not path k-mers, Bernoulli-subsampled to at most
     3 x max_parameter_kmers and capped at max_parameter_kmers (the reference's draw order comes from mt19937 +
-    hash iteration order; here it is a seeded device permutation — same population, different sample)."""
+    hash iteration order; here it is a seeded device permutation — same population, different sample).
+    parameter_kmers: (n, 2) uint64 packed k-mers of <out>_cluster_data/parameter_kmers.fa.gz as the `cluster` stage wrote them
+    (cluster_data.read_parameter_kmers; main.cpp:543-584 reads the same file): the fit then uses exactly those k-mers, as
+    `bayesTyper genotype` does, and the negative-binomial parameters equal the reference's for the same file."""
     lib, dev = pipe.lib, pipe.dev
     with torch.cuda.stream(pipe.ext):
         buf = region_buf
@@ -168,14 +171,32 @@ def estimate_nb_parameters(pipe: kmer_pipeline.KmerPipeline, region_buf, spectra
         capi.check(lib.btg_table_lookup_dev(pipe.kw0.data_ptr(), pipe.kw1.data_ptr(), pipe.n_keys, keys.data_ptr(), len(keys), idx.data_ptr(), None), lib)
         not_path = idx < 0
         kw0, kw1, occ = kw0[not_path], kw1[not_path], occ[not_path]
-        total = int(km.shape[0])
-        frac = min(1.0, 3.0 * opt.max_parameter_kmers / max(total, 1))
-        g = torch.Generator(device=dev).manual_seed(opt.random_seed)
-        sel = torch.rand(len(occ), device=dev, generator=g) < frac
-        kw0, kw1, occ = kw0[sel], kw1[sel], occ[sel]
-        if len(occ) > opt.max_parameter_kmers:
-            perm = torch.randperm(len(occ), device=dev, generator=g)[:opt.max_parameter_kmers].sort().values
-            kw0, kw1, occ = kw0[perm], kw1[perm], occ[perm]
+        if parameter_kmers is not None:
+            # the k-mers the cluster stage chose: keep the inter-cluster k-mers that are on the list (their genomic multiplicity is the
+            # occurrence count of the scan, KmerCounts::addInterclusterMultiplicity)
+            pk = _to_dev(np.ascontiguousarray(parameter_kmers, np.uint64), np.int64, dev).reshape(-1, 2).contiguous()
+            p_lo = torch.empty(len(pk), dtype=torch.int64, device=dev); p_hi = torch.empty_like(p_lo)
+            capi.check(lib.btg_table_keys_from_kmers_dev(pk.data_ptr(), len(pk), p_lo.data_ptr(), p_hi.data_ptr(), None), lib)
+            po = torch.sort(p_lo, stable=True).indices
+            po = po[torch.sort(p_hi[po], stable=True).indices]
+            p_lo, p_hi = p_lo[po].contiguous(), p_hi[po].contiguous()
+            cand = torch.empty((len(occ), 2), dtype=torch.int64, device=dev)
+            kw0c, kw1c = kw0.contiguous(), kw1.contiguous()
+            capi.check(lib.btg_table_keys_to_kmers_dev(kw0c.data_ptr(), kw1c.data_ptr(), len(occ), cand.data_ptr(), None), lib)
+            hit = torch.empty(len(occ), dtype=torch.int64, device=dev)
+            pipe.use_index(False)
+            capi.check(lib.btg_table_lookup_dev(p_lo.data_ptr(), p_hi.data_ptr(), len(pk), cand.data_ptr(), len(occ), hit.data_ptr(), None), lib)
+            sel = hit >= 0
+            kw0, kw1, occ = kw0[sel], kw1[sel], occ[sel]
+        else:
+            total = int(km.shape[0])
+            frac = min(1.0, 3.0 * opt.max_parameter_kmers / max(total, 1))
+            g = torch.Generator(device=dev).manual_seed(opt.random_seed)
+            sel = torch.rand(len(occ), device=dev, generator=g) < frac
+            kw0, kw1, occ = kw0[sel], kw1[sel], occ[sel]
+            if len(occ) > opt.max_parameter_kmers:
+                perm = torch.randperm(len(occ), device=dev, generator=g)[:opt.max_parameter_kmers].sort().values
+                kw0, kw1, occ = kw0[perm], kw1[perm], occ[perm]
         kw0, kw1 = kw0.contiguous(), kw1.contiguous()
         S = len(spectra_dev)
         counts = torch.zeros((len(occ), S), dtype=torch.uint8, device=dev)
@@ -221,6 +242,7 @@ class Inputs:
     blooms_dev: list = None
     region_buf_dev: object = None
     native_builder: bool = False       # cluster construction through host/btcluster (same arrays, ~15x faster) instead of graph_builder.py
+    parameter_kmers: object = None     # (n, 2) uint64: <out>_cluster_data/parameter_kmers.fa.gz of the cluster stage (None: chosen here)
     resident_cache: dict = dataclasses.field(default_factory=dict)   # device handles that outlive a pass (graphs of the unit + path-search scratch)
 
     def prepare(self):
@@ -355,7 +377,7 @@ def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rate
     # row-level unit arrays stay in HBM unless the caller wants the unit on the host (tests, fixtures)
     unit = pipe.build_unit(multigroup_bloom=None, ploidy=ploidy, device_resident=not want_unit)
     if nb_params is None:
-        nb_p, nb_size, used = estimate_nb_parameters(pipe, region_buf, spectra_dev, inp.genders, opt, (female_ploidy, male_ploidy))
+        nb_p, nb_size, used = estimate_nb_parameters(pipe, region_buf, spectra_dev, inp.genders, opt, (female_ploidy, male_ploidy), inp.parameter_kmers)
         info["nb_fit"] = used
     else:
         nb_p, nb_size = nb_params

@@ -163,6 +163,24 @@ def make_e2e(name, workload, seed=20190401, n_errors=20000):
     print(name, "variants", len(ids), "nb", t["nb_p_size"].tolist(), "noise", t["noise_rates"].tolist())
 
 
+def make_nbfit(name, workload, seed=20190401, n_errors=8000):
+    """NB-fit fixture: the parameter k-mers the reference's cluster stage wrote (<out>_cluster_data/parameter_kmers.fa.gz) and the negative
+    binomial (p, size) its genotype stage fitted from them (CountDistribution::setGenomicCountDistributions)."""
+    from bayestyper_b200 import cluster_data
+    with tempfile.TemporaryDirectory() as td:
+        spectra = synth.sample_spectra(workload, 4, n_errors)
+        wd = synth.write_workdir(workload, td, spectra=spectra)
+        subprocess.check_call([str(BTREF), "run", "--workdir", str(wd), "--threads", "4", "--seed", str(seed), "--skip-genotype"], stdout=subprocess.DEVNULL)
+        out = Path(wd) / "ref_out"
+        t = btd.read(out / "tables.btd")
+        pk = cluster_data.read_parameter_kmers(out / "bayestyper_cluster_data" / "parameter_kmers")
+    btd.write(Path(__file__).parent / f"{name}.btd", {"parameter_kmers": np.ascontiguousarray(pk, np.uint64), "tab.nb_p_size": t["nb_p_size"],
+                                                         "meta.seed": np.array([seed], np.uint32), "meta.n_errors": np.array([n_errors], np.uint32)})
+    print(name, "parameter k-mers", len(pk), "nb", t["nb_p_size"].tolist())
+
+
+NBFIT_WORKLOADS = {"nbfit_mixed_2s": lambda: synth.small_mixed(250, 30_000, 2, seed=77)}
+
 E2E_WORKLOADS = {
     "e2e_snv_1s": lambda: synth.config_a(n_variants=1500, length=150_000),
     "e2e_mixed_3s": lambda: synth.small_mixed(800, 80_000, 3, seed=71),
@@ -200,6 +218,10 @@ if __name__ == "__main__":
         _sys.exit(0)
     if len(_sys.argv) > 1 and _sys.argv[1] == "joint":
         make("gibbs_joint_2s", synth.small_mixed(260, 24_000, 2, seed=83), 400, extra_args=("--noise-genotyping",))
+        _sys.exit(0)
+    if len(_sys.argv) > 1 and _sys.argv[1] == "nbfit":
+        for nm, fn in NBFIT_WORKLOADS.items():
+            make_nbfit(nm, fn())
         _sys.exit(0)
     if len(_sys.argv) > 1 and _sys.argv[1] == "exact":
         # fixtures that hold EVERY group of the reference run: the lock-step modes can be reproduced row for row (tests/test_ref_parity_exact.py)
