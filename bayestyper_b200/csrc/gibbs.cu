@@ -784,7 +784,22 @@ btg_unit *btg_unit_upload_dev(const btg_unit_desc *d, const btg_unit_desc *dev, 
     const uint32_t n_pos = (uint32_t)ext_cluster.size();
     // one arena slot per warp of the position order, sized by the largest cluster in it (wide layout: one slot per position)
     const uint32_t per_slot = du.wide ? 1u : 32u;
-    const uint64_t cache_cap = getenv("BTG_WIDE_CACHE_CAP") ? strtoull(getenv("BTG_WIDE_CACHE_CAP"), nullptr, 10) : kWideCacheCap;  // tests lower it
+    // dense diplotype caches of the wide layout: 16 B x S x (H+1)(H+2)/2 per cluster.  Every cluster gets them as long as the total stays within a
+    // quarter of the free HBM; otherwise the cap on S x Dall is halved until it does (clusters above the cap recompute their sums, which is
+    // correct but costs them two walks of the live diplotypes per iteration).  BTG_WIDE_CACHE_CAP fixes the cap (tests lower it).
+    uint64_t cache_cap = kWideCacheCap;
+    if (getenv("BTG_WIDE_CACHE_CAP")) cache_cap = strtoull(getenv("BTG_WIDE_CACHE_CAP"), nullptr, 10);
+    else if (du.wide) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        cache_cap = 1ull << 24;
+        for (;;) {
+            uint64_t bytes = 0;
+            for (uint32_t c = 0; c < C; c++) { const uint64_t e = (uint64_t)S * dims[c].Dall; if (e <= cache_cap || dims[c].nm) bytes += 16 * e; }
+            if (bytes <= free_b / 4 || cache_cap <= kWideCacheCap) break;
+            cache_cap >>= 1;
+        }
+    }
     const uint32_t n_slots = (n_pos + per_slot - 1) / per_slot;
     u->h_slots.assign(n_slots ? n_slots : 1, SlotLayout{});
     uint64_t f64_total = 0, u32_total = 0, u8_total = 0;

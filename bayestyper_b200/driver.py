@@ -405,6 +405,9 @@ def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rate
         res = eng.estimate_genotypes(cd, gopts)
     info["nb"] = (nb_p, nb_size)
     info["n_clusters"] = unit.Cn
+    nh = np.asarray(unit.a["cl_nhap"], np.int64)
+    info["haplotype_candidates"] = {"max": int(nh.max()) if len(nh) else 0, "q50": float(np.quantile(nh, 0.5)) if len(nh) else 0, "q99": float(np.quantile(nh, 0.99)) if len(nh) else 0,
+                                    "clusters_over_32": int((nh > 32).sum())}
     eng.close(); cd.close()
     if vcf_out is not None:   # GenotypeWriter (include/btgpu_vcf.hpp through host/btvcf): the result arrays are in unit order, so is the description
         from . import vcf_desc

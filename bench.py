@@ -340,7 +340,7 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
         "dtype": "f64 (Gibbs log-likelihoods) / u64 (k-mer hashing)", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.config], "clusters": n_total, "clusters_per_gpu": n_clusters, "variants": len(inp.variants) * (1 if sharded else world),
-                   "samples": S, "reference_nt": len(inp.reference), "sample_kmers": n_sample, "path_kmers": info["n_path_kmers"],
+                   "samples": S, "haplotype_candidates_per_cluster": info.get("haplotype_candidates"), "reference_nt": len(inp.reference), "sample_kmers": n_sample, "path_kmers": info["n_path_kmers"],
                    "step": "findVariantClusterPaths -> path k-mer table -> genome scan -> sample k-mer stream -> classify/haplotype candidates -> NB fit -> "
                            + ("estimateNoiseAndGenotypes" if args.config == "D" else "estimateNoise -> estimateGenotypes"),
                    "gibbs": "20 chains x (100 burn-in + 250 samples), k-mer subsampling 0.1",
