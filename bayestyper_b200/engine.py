@@ -62,6 +62,15 @@ class InferenceEngine:
             self._dev_desc, n_vh, n_vh_bits = dd
             self.h = capi.check(self.lib.btg_unit_upload_dev(C.addressof(self._desc), C.addressof(self._dev_desc), n_vh, n_vh_bits), self.lib)
 
+    @classmethod
+    def from_handle(cls, unit: Unit, handle):
+        """Wraps a btg_unit that already lives in HBM (btg_counter_build_unit); `unit` only sizes the result arrays."""
+        self = cls.__new__(cls)
+        self.lib = capi.load()
+        self.unit = unit
+        self.h = handle
+        return self
+
     def estimate_genotypes(self, cd: CountDistribution, opts: GibbsOpts) -> dict:
         res, arrays = self.unit.alloc_result()
         capi.check(self.lib.btg_estimate_genotypes(self.h, cd.h, C.addressof(opts), C.addressof(res)), self.lib)

@@ -66,6 +66,7 @@ void btg_launch_count_reset(void);
 
 /* ---- KmerBloom  (include/kmerBloom/KmerBloom.hpp:48-77) ----------------- */
 typedef struct btg_bloom btg_bloom;
+typedef struct btg_unit btg_unit;   /* an inference unit resident in HBM (defined with the Gibbs entry points below) */
 
 /* KmerBloom(num_kmers, fpr)            src/kmerBloom/KmerBloom.cpp:53-60 */
 btg_bloom *btg_bloom_create(uint64_t num_kmers, float fpr, int k);
@@ -220,6 +221,54 @@ int btg_table_scan_region_dev(const int64_t *key_lo, const int64_t *key_hi, int6
                               int is_decoy, uint32_t ploidy_female, uint32_t ploidy_male, uint8_t *ic, uint8_t *max_mult,
                               uint8_t *decoy, uint8_t *has_record, void *stream);
 
+/* ======================= KmerCounter: the genotype-side k-mer stages behind one handle ======= *
+ * Replaces the stage methods KmerCounter::{countPathKmers, countInterclusterKmers, parseSampleKmers, classifyPathKmers}
+ * (include/bayesTyper/KmerCounter.hpp:61-67; called from src/bayesTyper/main.cpp:594-603), the count table they share
+ * (KmerCountsHash / KmerCounts, include/bayesTyper/KmerHash.hpp:73-108, src/bayesTyper/KmerCounts.cpp:93-189) and
+ * VariantClusterGraph::{countPathKmers, classifyPathKmers, getHaplotypeCandidates} (src/bayesTyper/VariantClusterGraph.cpp:
+ * 800-1184) for one inference unit.  The handle owns the table (sorted 128-bit keys + count / multiplicity / flag columns)
+ * and every intermediate in HBM; the relational steps between the kernels are device sorts / run-length encodings / scans.
+ * All arrays of the descriptor are host memory (copied by btg_counter_create).                                            */
+typedef struct btg_counter_desc {
+    uint32_t n_samples, n_groups, n_clusters;
+    const uint8_t *sample_gender;        /* [S] 0 = Female, 1 = Male */
+    const uint64_t *group_cluster_off;   /* [G+1] as btg_unit_desc (passed through to the unit) */
+    const uint64_t *group_src_off;       /* [G+1] */
+    const uint32_t *group_src;
+    const uint64_t *group_edge_off;      /* [G+1] */
+    const uint32_t *group_edge_src, *group_edge_dst;
+    const uint32_t *cluster_idx;         /* [C] */
+    const uint64_t *cl_vertex_off;       /* [C+1] graphs as btg_pathwalk_desc, host side */
+    const uint64_t *v_seq_off;           /* [V+1] */
+    const uint8_t *seq;
+    const uint8_t *v_flags;              /* [V] */
+    const uint16_t *v_var, *v_allele;    /* [V] variant_allele_idx (0xFFFF none) */
+    const uint64_t *v_refvar_off;        /* [V+1] */
+    const uint16_t *v_refvar;
+    const uint32_t *v_nested;            /* [V] nested_variant_cluster_idx of the vertex or 0xFFFFFFFF; NULL: no nested clusters */
+    const uint32_t *n_paths;             /* [C] best paths per cluster (btg_get_best_paths) */
+    const uint8_t *path_mem;             /* best_paths_indices, one byte per (path, vertex), cluster-major */
+    const uint64_t *cl_var_off;          /* [C+1] */
+    const uint16_t *var_nalleles;        /* [n_variants] */
+    const uint8_t *var_dep;              /* [n_variants] */
+} btg_counter_desc;
+typedef struct btg_counter btg_counter;
+btg_counter *btg_counter_create(const btg_counter_desc *desc);
+void btg_counter_free(btg_counter *k);
+/* KmerCounter::countPathKmers (KmerCounter.cpp:252-289): the distinct canonical k-mers of every best path become the table keys */
+int btg_counter_count_path_kmers(btg_counter *k, uint64_t *n_path_kmers_out);
+/* KmerCounter::countInterclusterKmers (KmerCounter.cpp:291-386) for a device buffer of inter-cluster regions separated by 'N' */
+int btg_counter_count_intercluster_kmers(btg_counter *k, const char *seq_dev, size_t len, int is_decoy, uint32_t ploidy_female, uint32_t ploidy_male);
+/* KmerCounter::parseSampleKmers (KmerCounter.cpp:431-524) for one sample's (k-mer, count) records resident in HBM */
+int btg_counter_parse_sample_kmers(btg_counter *k, uint32_t sample_idx, const uint64_t *kmers_dev, const uint8_t *counts_dev, size_t n);
+/* KmerCounter::classifyPathKmers (KmerCounter.cpp:526-600) + getHaplotypeCandidates of every cluster: the inference unit, resident in HBM.
+ * multigroup = the cluster stage's multigroup_kmers filter (main.cpp:345-351) or NULL (exact: k-mers that occur in several groups);
+ * group_ploidy [G*S] as btg_unit_desc.                                                                                        */
+btg_unit *btg_counter_build_unit(btg_counter *k, const btg_bloom *multigroup, const uint8_t *group_ploidy);
+/* number of elements (out = NULL) or a host copy of an array of the last btg_counter_build_unit, by its btg_unit_desc field name; also
+ * "key_lo" / "key_hi" (table keys) and "key_flags" (bit0 record, bit1 multicluster, bit2 multigroup, bit3 excluded)               */
+int64_t btg_counter_array(btg_counter *k, const char *field, void *out, uint64_t out_bytes);
+
 /* ======================= per-cluster Gibbs sampler =========================== *
  * Replaces InferenceEngine::{estimateNoise,estimateGenotypes,estimateNoiseAndGenotypes}
  * (include/bayesTyper/InferenceEngine.hpp:62-64, src/bayesTyper/InferenceEngine.cpp:135-472)
@@ -293,7 +342,6 @@ typedef struct btg_unit_desc {
     const uint16_t *dep_var;
 } btg_unit_desc;
 
-typedef struct btg_unit btg_unit;
 btg_unit *btg_unit_upload(const btg_unit_desc *desc);
 /* The same for callers that built the row-level arrays on the device (the k-mer stages do): every non-NULL pointer in `dev`
  * is a DEVICE pointer that replaces the host array of the same name in `desc` (which may then be NULL) — for these fields only:
