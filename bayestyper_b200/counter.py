@@ -61,6 +61,7 @@ class KmerCounter:
         L.btg_counter_parse_sample_kmers.argtypes = [_P, C.c_uint32, _P, _P, C.c_size_t]
         L.btg_counter_build_unit.restype = _P; L.btg_counter_build_unit.argtypes = [_P, _P, _P]
         L.btg_counter_array.restype = C.c_int64; L.btg_counter_array.argtypes = [_P, C.c_char_p, _P, C.c_uint64]
+        L.btg_counter_fit_nb.argtypes = [_P, _P, C.c_size_t, C.c_uint32, C.c_uint32, _P, _P, _P, _P, C.c_size_t, C.c_uint32, C.c_uint64, _P, _P, _P, _P]
         L._counter_bound = True
 
     def count_path_kmers(self) -> int:
@@ -79,6 +80,21 @@ class KmerCounter:
         pl = np.ascontiguousarray(np.full(self.G * self.S, 2, np.uint8) if group_ploidy is None else group_ploidy, np.uint8)
         self._ploidy = pl
         return capi.check(self.lib.btg_counter_build_unit(self.h, multigroup_bloom, pl.ctypes.data), self.lib)
+
+    def fit_nb(self, buf_dev_ptr: int, length: int, spectra_dev, ploidy=(2, 2), parameter_kmers=None, random_seed: int = 0, max_parameter_kmers: int = 1_000_000):
+        """btg_counter_fit_nb: per-sample negative binomial (p, size) from the parameter k-mers; spectra_dev = [(kmers tensor, counts tensor)] in HBM.
+        Returns (nb_p, nb_size, [(modal multiplicity, k-mers in the class)])."""
+        S = self.S
+        kp = (C.c_void_p * S)(*[int(k.data_ptr()) for k, _ in spectra_dev])
+        cp = (C.c_void_p * S)(*[int(c.data_ptr()) for _, c in spectra_dev])
+        nn = (C.c_size_t * S)(*[int(c.numel()) for _, c in spectra_dev])
+        pk = None if parameter_kmers is None else np.ascontiguousarray(parameter_kmers, np.uint64).reshape(-1, 2)
+        nb_p, nb_size = np.zeros(S), np.zeros(S)
+        modal, n_modal = np.zeros(S, np.uint32), np.zeros(S, np.uint64)
+        capi.check(self.lib.btg_counter_fit_nb(self.h, buf_dev_ptr, length, ploidy[0], ploidy[1], kp, cp, nn, None if pk is None else pk.ctypes.data,
+                                               0 if pk is None else len(pk), random_seed, max_parameter_kmers, nb_p.ctypes.data, nb_size.ctypes.data,
+                                               modal.ctypes.data, n_modal.ctypes.data), self.lib)
+        return nb_p, nb_size, [(int(m), int(n)) for m, n in zip(modal, n_modal)]
 
     def array(self, field: str, dtype) -> np.ndarray:
         n = self.lib.btg_counter_array(self.h, field.encode(), None, 0)

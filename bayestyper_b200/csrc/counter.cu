@@ -28,6 +28,21 @@ using namespace btg;
 namespace {
 
 // ---- device buffers ------------------------------------------------------------------------------------------------------
+// Stream-ordered allocations from the device's default memory pool (cudaMallocAsync on the library stream): the stages allocate ~100
+// intermediates of up to a few hundred MB per unit; with cudaMalloc / cudaFree each of them is a driver call that synchronises the device
+// (0.4 s per stage on configs[1]); the pool keeps the memory between stages and units (release threshold = never).
+inline void pool_setup() {
+    static bool done = false;
+    if (done) return;
+    cudaMemPool_t pool;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done = true;
+}
 template <class T> struct DBuf {
     T *p = nullptr;
     size_t n = 0;
@@ -37,12 +52,14 @@ template <class T> struct DBuf {
     DBuf(DBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
     DBuf &operator=(DBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
     ~DBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) cudaFreeAsync(p, ctx().stream); p = nullptr; n = 0; }
     bool alloc(size_t count, bool zero = false, cudaStream_t s = nullptr) {
         release();
+        pool_setup();
         n = count;
-        if (cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) { p = nullptr; n = 0; return false; }
-        if (zero) cudaMemsetAsync(p, 0, std::max<size_t>(count, 1) * sizeof(T), s);
+        if (cudaMallocAsync(&p, std::max<size_t>(count, 1) * sizeof(T), ctx().stream) != cudaSuccess) { p = nullptr; n = 0; cudaGetLastError(); return false; }
+        if (zero) cudaMemsetAsync(p, 0, std::max<size_t>(count, 1) * sizeof(T), ctx().stream);
+        (void)s;
         return true;
     }
     bool upload(const T *h, size_t count, cudaStream_t s) {
@@ -59,12 +76,13 @@ template <class T> struct DBuf {
 struct Temp {   // CUB temporary storage, grown on demand
     void *p = nullptr;
     size_t cap = 0;
-    ~Temp() { if (p) cudaFree(p); }
+    ~Temp() { if (p) cudaFreeAsync(p, ctx().stream); }
     bool need(size_t bytes) {
         if (bytes <= cap) return true;
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, ctx().stream);
         cap = bytes + bytes / 4 + 256;
-        return cudaMalloc(&p, cap) == cudaSuccess;
+        pool_setup();
+        return cudaMallocAsync(&p, cap, ctx().stream) == cudaSuccess;
     }
 };
 
@@ -277,6 +295,38 @@ __global__ void k_vh_bits(const uint32_t *rank, const uint32_t *ev_order, const 
     vh_bits[vh_bits_off[rank[j] - 1] + local_path[cov_occ[ev_order[j]]]] = 1;
 }
 
+// ---- NB fit (parameter k-mers) ------------------------------------------------------------------------------------------------
+__global__ void k_valid_flags(const uint8_t *valid, uint32_t *flag, size_t n) { const size_t i = blockIdx.x * (size_t)kB + threadIdx.x; if (i < n) flag[i] = valid[i] != 0; }
+__global__ void k_compact_kmers(const ulonglong2 *km, const uint32_t *flag, const uint32_t *rank /* exclusive */, ulonglong2 *out, size_t n) {
+    const size_t i = blockIdx.x * (size_t)kB + threadIdx.x;
+    if (i < n && flag[i]) out[rank[i]] = km[i];
+}
+// distinct sorted keys: start index of every run
+__global__ void k_run_starts(const uint32_t *flag, const uint32_t *rank /* inclusive */, const int64_t *lo, const int64_t *hi, int64_t *u_lo, int64_t *u_hi, uint32_t *start, size_t n) {
+    const size_t i = blockIdx.x * (size_t)kB + threadIdx.x;
+    if (i < n && flag[i]) { const uint32_t r = rank[i] - 1; u_lo[r] = lo[i]; u_hi[r] = hi[i]; start[r] = (uint32_t)i; }
+}
+// splitmix64 of (seed, key): the Bernoulli of the parameter k-mer subsample (a property of the k-mer, so the choice does not depend on the scan order)
+__device__ __forceinline__ uint64_t mix64(uint64_t x) { x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31); }
+// select[i] = the inter-cluster k-mer is not a path k-mer and is a parameter k-mer (on the list when one is given, else a Bernoulli draw); occ = run length
+__global__ void k_param_select(const uint32_t *start, size_t n_distinct, size_t n_total, const int64_t *path_idx, const int64_t *list_idx, const int64_t *u_lo, const int64_t *u_hi,
+                               uint64_t seed, double frac, uint32_t *sel, uint32_t *occ) {
+    const size_t i = blockIdx.x * (size_t)kB + threadIdx.x;
+    if (i >= n_distinct) return;
+    occ[i] = (uint32_t)((i + 1 < n_distinct ? start[i + 1] : n_total) - start[i]);
+    bool ok = path_idx[i] < 0;
+    if (ok) {
+        if (list_idx) ok = list_idx[i] >= 0;
+        else ok = (double)(mix64(mix64(seed ^ (uint64_t)u_lo[i]) ^ (uint64_t)u_hi[i]) >> 11) * (1.0 / 9007199254740992.0) < frac;
+    }
+    sel[i] = ok;
+}
+__global__ void k_compact_params(const uint32_t *sel, const uint32_t *rank /* exclusive */, const int64_t *u_lo, const int64_t *u_hi, const uint32_t *occ, int64_t *p_lo, int64_t *p_hi,
+                                 uint32_t *p_occ, size_t n) {
+    const size_t i = blockIdx.x * (size_t)kB + threadIdx.x;
+    if (i < n && sel[i]) { const uint32_t r = rank[i]; p_lo[r] = u_lo[i]; p_hi[r] = u_hi[i]; p_occ[r] = occ[i]; }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -326,6 +376,36 @@ struct btg_counter {
 namespace {
 
 template <class T> void copy_vec(std::vector<T> &dst, const T *src, size_t n) { dst.assign(src, src + n); }
+
+// sorted distinct table keys of a set of packed k-mers on the device: (lo, hi) ascending, optionally the start of every run
+bool distinct_keys(btg_counter &k, const uint64_t *kmers_dev, size_t n, DBuf<int64_t> &u_lo, DBuf<int64_t> &u_hi, DBuf<uint32_t> *starts, size_t &n_distinct) {
+    cudaStream_t s = k.s;
+    n_distinct = 0;
+    DBuf<int64_t> lo, hi, key;
+    DBuf<uint32_t> order, flag, rank;
+    if (!lo.alloc(n) || !hi.alloc(n) || !key.alloc(n) || !order.alloc(n) || !flag.alloc(n) || !rank.alloc(n)) return false;
+    if (n == 0) { u_lo.alloc(0); u_hi.alloc(0); if (starts) starts->alloc(0); return true; }
+    if (btg_table_keys_from_kmers_dev(kmers_dev, n, lo.p, hi.p, s) != BTG_OK) return false;
+    k_iota<<<grid_of(n), kB, 0, s>>>(order.p, n);
+    CK(cudaMemcpyAsync(key.p, lo.p, n * 8, cudaMemcpyDeviceToDevice, s));
+    if (!sort_pairs(k.tmp, key, order, n, s)) return false;
+    k_gather_i64<<<grid_of(n), kB, 0, s>>>(hi.p, order.p, key.p, n);
+    if (!sort_pairs(k.tmp, key, order, n, s, 47)) return false;
+    DBuf<int64_t> s_lo;
+    if (!s_lo.alloc(n)) return false;
+    k_gather_i64<<<grid_of(n), kB, 0, s>>>(lo.p, order.p, s_lo.p, n);     // key.p holds the sorted hi
+    k_key_flags<<<grid_of(n), kB, 0, s>>>(s_lo.p, key.p, flag.p, n);
+    if (!inclusive_sum(k.tmp, flag.p, rank.p, n, s)) return false;
+    uint32_t nd = 0;
+    CK(cudaMemcpyAsync(&nd, rank.p + n - 1, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    n_distinct = nd;
+    DBuf<uint32_t> st;
+    if (!u_lo.alloc(nd) || !u_hi.alloc(nd) || !st.alloc(nd)) return false;
+    k_run_starts<<<grid_of(n), kB, 0, s>>>(flag.p, rank.p, s_lo.p, key.p, u_lo.p, u_hi.p, st.p, n);
+    if (starts) *starts = std::move(st);
+    return true;
+}
 
 bool count_path_kmers(btg_counter &k) {
     cudaStream_t s = k.s;
@@ -728,6 +808,101 @@ btg_unit *btg_counter_build_unit(btg_counter *k, const btg_bloom *multigroup, co
     if (has_multi) { host.k_shared = h_shared.data(); host.k_has_counts = h_has.data(); }
     else { dev.k_shared = k->u_shared.p; dev.k_has_counts = k->u_has_counts.p; }
     return btg_unit_upload_dev(&host, &dev, k->n_vh, k->n_vh_bits);
+}
+
+int btg_counter_fit_nb(btg_counter *k, const char *seq_dev, size_t len, uint32_t ploidy_female, uint32_t ploidy_male, const uint64_t *const *sample_kmers_dev,
+                       const uint8_t *const *sample_counts_dev, const size_t *sample_n, const uint64_t *parameter_kmers, size_t n_parameter_kmers, uint32_t random_seed,
+                       uint64_t max_parameter_kmers, double *nb_p_out, double *nb_size_out, uint32_t *modal_multiplicity_out, uint64_t *n_modal_kmers_out) {
+    BTG_REQUIRE_INIT();
+    if (!k || !k->counted || !nb_p_out || !nb_size_out || (k->S && (!sample_kmers_dev || !sample_counts_dev || !sample_n))) { set_error("countPathKmers has not run, or null argument"); return BTG_EINVAL; }
+    cudaStream_t s = k->s;
+    const uint32_t S = k->S;
+    auto fail = [&](const char *what) { if (!*btg_last_error()) set_error("NB fit: %s (%s)", what, cudaGetErrorString(cudaGetLastError())); return BTG_ECUDA; };
+    // every valid canonical k-mer of the inter-cluster regions
+    DBuf<uint64_t> km, kmv;
+    DBuf<uint8_t> valid;
+    DBuf<uint32_t> flag, rank;
+    if (!km.alloc(len * 2) || !valid.alloc(len) || !flag.alloc(len) || !rank.alloc(len)) return fail("allocation");
+    size_t n_valid = 0;
+    if (len) {
+        if (btg_scan_sequence_dev(seq_dev, len, km.p, valid.p, s) != BTG_OK) return BTG_ECUDA;
+        k_valid_flags<<<grid_of(len), kB, 0, s>>>(valid.p, flag.p, len);
+        if (!exclusive_sum(k->tmp, flag.p, rank.p, len, s)) return fail("scan");
+        uint32_t last_r = 0, last_f = 0;
+        cudaMemcpyAsync(&last_r, rank.p + len - 1, 4, cudaMemcpyDeviceToHost, s); cudaMemcpyAsync(&last_f, flag.p + len - 1, 4, cudaMemcpyDeviceToHost, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) return fail("scan");
+        n_valid = (size_t)last_r + last_f;
+        if (!kmv.alloc(std::max<size_t>(n_valid, 1) * 2)) return fail("allocation");
+        k_compact_kmers<<<grid_of(len), kB, 0, s>>>((const ulonglong2 *)km.p, flag.p, rank.p, (ulonglong2 *)kmv.p, len);
+    }
+    km.release(); valid.release(); flag.release(); rank.release();
+    // distinct k-mers with their genomic multiplicity; not path k-mers; on the list / Bernoulli
+    DBuf<int64_t> u_lo, u_hi;
+    DBuf<uint32_t> starts;
+    size_t nd = 0;
+    if (!distinct_keys(*k, kmv.p, n_valid, u_lo, u_hi, &starts, nd)) return fail("sort");
+    kmv.release();
+    DBuf<uint64_t> cand;
+    DBuf<int64_t> path_idx, list_idx, l_lo, l_hi;
+    if (!cand.alloc(std::max<size_t>(nd, 1) * 2) || !path_idx.alloc(nd)) return fail("allocation");
+    if (nd) {
+        if (btg_table_keys_to_kmers_dev(u_lo.p, u_hi.p, nd, cand.p, s) != BTG_OK) return BTG_ECUDA;
+        k->use_index();
+        if (btg_table_lookup_dev(k->kw0.p, k->kw1.p, (int64_t)k->n_keys, cand.p, nd, path_idx.p, s) != BTG_OK) return BTG_ECUDA;
+    }
+    if (parameter_kmers) {
+        DBuf<uint64_t> lk;
+        size_t nl = 0;
+        if (!lk.upload(parameter_kmers, n_parameter_kmers * 2, s) || !distinct_keys(*k, lk.p, n_parameter_kmers, l_lo, l_hi, nullptr, nl) || !list_idx.alloc(nd)) return fail("parameter k-mer list");
+        if (nd) {
+            btg_table_set_index_dev(nullptr, 0);
+            if (btg_table_lookup_dev(l_lo.p, l_hi.p, (int64_t)nl, cand.p, nd, list_idx.p, s) != BTG_OK) return BTG_ECUDA;
+        }
+    }
+    DBuf<uint32_t> sel, occ, srank;
+    if (!sel.alloc(nd) || !occ.alloc(nd) || !srank.alloc(nd)) return fail("allocation");
+    const double frac = std::min(1.0, 3.0 * (double)max_parameter_kmers / (double)std::max<size_t>(n_valid, 1));   // at most 3 x the cap is drawn (main.cpp:330-333)
+    if (nd) k_param_select<<<grid_of(nd), kB, 0, s>>>(starts.p, nd, n_valid, path_idx.p, parameter_kmers ? list_idx.p : nullptr, u_lo.p, u_hi.p, random_seed, frac, sel.p, occ.p);
+    if (!exclusive_sum(k->tmp, sel.p, srank.p, nd, s)) return fail("scan");
+    size_t n_par = 0;
+    if (nd) {
+        uint32_t a = 0, b = 0;
+        cudaMemcpyAsync(&a, srank.p + nd - 1, 4, cudaMemcpyDeviceToHost, s); cudaMemcpyAsync(&b, sel.p + nd - 1, 4, cudaMemcpyDeviceToHost, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) return fail("scan");
+        n_par = (size_t)a + b;
+    }
+    DBuf<int64_t> p_lo, p_hi;
+    DBuf<uint32_t> p_occ;
+    DBuf<uint8_t> p_counts, p_rec;
+    if (!p_lo.alloc(n_par) || !p_hi.alloc(n_par) || !p_occ.alloc(n_par) || !p_counts.alloc(n_par * S + 4, true, s) || !p_rec.alloc(n_par + 4, true, s)) return fail("allocation");
+    if (nd) k_compact_params<<<grid_of(nd), kB, 0, s>>>(sel.p, srank.p, u_lo.p, u_hi.p, occ.p, p_lo.p, p_hi.p, p_occ.p, nd);
+    if (!parameter_kmers && n_par > max_parameter_kmers) n_par = max_parameter_kmers;   // the cap of parameter_kmers.fa.gz (main.cpp:543-581): the first in key order
+    btg_table_set_index_dev(nullptr, 0);                                                   // the parameter k-mers are a second, un-indexed table
+    for (uint32_t si = 0; si < S && n_par; si++)
+        if (btg_table_add_sample_kmers_dev(p_lo.p, p_hi.p, (int64_t)n_par, sample_kmers_dev[si], sample_counts_dev[si], sample_n[si], S, si, p_counts.p, p_rec.p, s) != BTG_OK) return BTG_ECUDA;
+    // modal multiplicity and the moments of its class, per sample (KmerHash.cpp:257-347, CountDistribution.cpp:66-141), in f64 on the host
+    std::vector<uint32_t> h_occ(n_par);
+    std::vector<uint8_t> h_cnt(n_par * S);
+    if (n_par) { cudaMemcpyAsync(h_occ.data(), p_occ.p, n_par * 4, cudaMemcpyDeviceToHost, s); cudaMemcpyAsync(h_cnt.data(), p_counts.p, n_par * S, cudaMemcpyDeviceToHost, s); }
+    if (cudaStreamSynchronize(s) != cudaSuccess) return fail("copy");
+    for (uint32_t si = 0; si < S; si++) {
+        const uint32_t ploidy = k->h_gender[si] == 0 ? ploidy_female : ploidy_male;
+        uint64_t hist[33] = {0};
+        for (size_t i = 0; i < n_par; i++) { const uint64_t m = std::min<uint64_t>(255, (uint64_t)h_occ[i] * ploidy); if (m >= 1 && m <= 32) hist[m]++; }   // max_nb_kmer_multiplicity = 32
+        uint32_t modal = 0; uint64_t best = 0;
+        for (uint32_t m = 1; m <= 32; m++) if (hist[m] > best) { best = hist[m]; modal = m; }
+        if (best == 0) { set_error("sample %u: no parameter k-mer with genomic multiplicity 1..32 (ploidy %u on this contig, %zu parameter k-mers): the negative binomial cannot be fitted", si, ploidy, n_par); return BTG_ESTATE; }
+        if (best < 2) { set_error("sample %u: %llu parameter k-mer(s) at the modal multiplicity %u: mean and variance undefined", si, (unsigned long long)best, modal); return BTG_ESTATE; }
+        double sum = 0;
+        for (size_t i = 0; i < n_par; i++) if (std::min<uint64_t>(255, (uint64_t)h_occ[i] * ploidy) == modal) sum += h_cnt[i * S + si];
+        const double mean = sum / (double)best;
+        double ss = 0;
+        for (size_t i = 0; i < n_par; i++) if (std::min<uint64_t>(255, (uint64_t)h_occ[i] * ploidy) == modal) { const double dlt = h_cnt[i * S + si] - mean; ss += dlt * dlt; }
+        btg_nb_moments_to_parameters(mean, ss / (double)(best - 1), modal, nb_p_out + si, nb_size_out + si);
+        if (modal_multiplicity_out) modal_multiplicity_out[si] = modal;
+        if (n_modal_kmers_out) n_modal_kmers_out[si] = best;
+    }
+    return BTG_OK;
 }
 
 // sizes (elements) and copies of the arrays of the last btg_counter_build_unit, by the field names of btg_unit_desc (tests, fixtures, hosts that

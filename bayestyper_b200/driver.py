@@ -40,6 +40,8 @@ class Options:
     max_parameter_kmers: int = 1_000_000
     chromosome_ploidy_file: str = None   # --chromosome-ploidy-file (ChromosomePloidy.cpp:96-180); default: human X / Y rules by name
     noise_genotyping: bool = False       # --noise-genotyping: InferenceEngine::estimateNoiseAndGenotypes instead of estimateNoise + estimateGenotypes
+    kmer_stages: str = "abi"             # "abi": KmerCounter's stages through the btg_counter handle of the C ABI (csrc/counter.cu, what a C++ host calls);
+                                         # "torch": the torch-glue mirror (kmer_pipeline.py) — also what a sharded unit uses (it subsets the unit on the device)
 
 
 @dataclasses.dataclass
@@ -368,6 +370,9 @@ def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rate
     if own_blooms:
         for b in blooms:
             lib.btg_bloom_free(b)
+    ploidy = np.tile(np.array([female_ploidy if g in ("F", 0) else male_ploidy for g in inp.genders], np.uint8), G)
+    if opt.kmer_stages == "abi" and not sharded and not want_unit:
+        return _genotype_abi(lib, inp, opt, n_paths, mem, S, spectra_dev, region_buf, (female_ploidy, male_ploidy), ploidy, nb_params, noise_rates, info, vcf_out, sample_names)
     pipe = kmer_pipeline.KmerPipeline(inp.graphs, n_paths, mem, S, inp.genders)
     info["n_path_kmers"] = pipe.enumerate_path_kmers()
     pipe.scan_buffer(region_buf, female_ploidy, male_ploidy, False)
@@ -414,6 +419,55 @@ def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rate
         names = list(sample_names) if sample_names is not None else [f"S{i + 1}" for i in range(S)]
         vcf_desc.write_vcf(vcf_out, res, vcf_desc.describe(inp.chrom, inp.reference, inp.variants, inp.graphs, names), S)
     return (inp.graphs, unit if want_unit else None, res, info)
+
+
+def _genotype_abi(lib, inp, opt, n_paths, mem, S, spectra_dev, region_buf, gender_ploidy, ploidy, nb_params, noise_rates, info, vcf_out, sample_names):
+    """The stages after the path search through handles of the C ABI only (what host/btpipeline.cpp does in C++): btg_counter (countPathKmers,
+    countInterclusterKmers, parseSampleKmers, classifyPathKmers + getHaplotypeCandidates, NB fit) -> btg_unit -> btg_count_dist -> Gibbs."""
+    from . import counter
+    torch.cuda.synchronize()
+    kc = counter.KmerCounter(inp.graphs, n_paths, mem, S, inp.genders)
+    try:
+        info["n_path_kmers"] = kc.count_path_kmers()
+        kc.count_intercluster_kmers(region_buf.data_ptr(), region_buf.numel(), gender_ploidy[0], gender_ploidy[1], False)
+        for s, (kd, cdv) in enumerate(spectra_dev):
+            kc.parse_sample_kmers(s, kd.data_ptr(), cdv.data_ptr(), cdv.numel())
+        handle = kc.build_unit(ploidy)
+        if nb_params is None:
+            nb_p, nb_size, used = kc.fit_nb(region_buf.data_ptr(), region_buf.numel(), spectra_dev, gender_ploidy, inp.parameter_kmers, opt.random_seed, opt.max_parameter_kmers)
+            info["nb_fit"] = [(m, n, None, None) for m, n in used]
+        else:
+            nb_p, nb_size = nb_params
+        sizes = U.Unit({**{k: np.zeros(0, dt) for k, dt in U._DESC_FIELDS}, "group_cluster_off": inp.graphs["group_cluster_off"], "cl_kmer_off": np.zeros(kc.Cn + 1, np.uint64),
+                        "cl_var_off": inp.graphs["cl_var_off"], "var_nalleles": kc._keep["var_nalleles"], "cl_nhap": np.asarray(n_paths, np.uint32)}, S)   # sizes the result arrays only
+    finally:
+        kc_done = kc
+    cd = engine.CountDistribution(nb_p, nb_size, opt.noise_rate_prior)
+    eng = engine.InferenceEngine.from_handle(sizes, handle)
+    kc_done.close()
+    gopts = U.default_opts(seed=opt.random_seed, burn=opt.gibbs_burn_in, samples=opt.gibbs_samples, chains=opt.n_chains, rate=opt.kmer_subsampling_rate,
+                           max_hv=opt.max_haplotype_variant_kmers, min_gpp=opt.min_genotype_posterior, min_kmers=opt.min_number_of_kmers,
+                           min_frac=None if opt.disable_observed_kmers else U.min_fraction_observed(nb_p, nb_size))
+    if opt.noise_genotyping:
+        res, info["noise_trace"] = eng.estimate_noise_and_genotypes(cd, gopts, want_trace=False)
+    else:
+        if noise_rates is None:
+            info["noise_trace"] = eng.estimate_noise(cd, gopts, want_trace=False)
+        else:
+            cd.set_noise_rates(noise_rates)
+        res = eng.estimate_genotypes(cd, gopts)
+    info["noise_rates"] = cd.noise_rates()
+    info["nb"] = (nb_p, nb_size)
+    info["n_clusters"] = info["n_clusters_total"] = sizes.Cn
+    nh = np.asarray(n_paths, np.int64)
+    info["haplotype_candidates"] = {"max": int(nh.max()) if len(nh) else 0, "q50": float(np.quantile(nh, 0.5)) if len(nh) else 0, "q99": float(np.quantile(nh, 0.99)) if len(nh) else 0,
+                                    "clusters_over_32": int((nh > 32).sum())}
+    eng.close(); cd.close()
+    if vcf_out is not None:
+        from . import vcf_desc
+        names = list(sample_names) if sample_names is not None else [f"S{i + 1}" for i in range(S)]
+        vcf_desc.write_vcf(vcf_out, res, vcf_desc.describe(inp.chrom, inp.reference, inp.variants, inp.graphs, names), S)
+    return (inp.graphs, None, res, info)
 
 
 def run(chrom: str, reference: bytes, variants, spectra, genders, opt: Options | None = None, nb_params=None, noise_rates=None):

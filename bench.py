@@ -407,20 +407,34 @@ def stage_breakdown(lib, inp, opt, stream, dev, shard_ctx=None):
         n_paths, mem = driver.merge_best_paths(inp.graphs, [(p[0], p[1]) for p in parts], [p[2] for p in parts])
     else:
         n_paths, mem = timed("findVariantClusterPaths", lambda: driver.find_variant_cluster_paths(lib, inp.graphs, inp.blooms_dev, opt))
-    pipe = kmer_pipeline.KmerPipeline(inp.graphs, n_paths, mem, S, inp.genders)
-    timed("countPathKmers(enumerate+sort)", pipe.enumerate_path_kmers)
-    timed("countInterclusterKmers(scan)", lambda: pipe.scan_buffer(inp.region_buf_dev, 2, 2, False))
-    timed("parseSampleKmers(stream, all samples)", lambda: [pipe.add_sample(i, kd_, cd_) for i, (kd_, cd_) in enumerate(inp.spectra_dev)])
     kd, cdv = inp.spectra_dev[0]
-    unit = timed("classify+getHaplotypeCandidates", lambda: pipe.build_unit(multigroup_bloom=None, device_resident=True))
-    nb = timed("NB fit (parameter k-mers)", lambda: driver.estimate_nb_parameters(pipe, inp.region_buf_dev, inp.spectra_dev, inp.genders, opt))
-    cd = engine.CountDistribution(nb[0], nb[1])
     sdesc = keep = None
-    if sharded:
+    if sharded:   # a sharded unit subsets the unit on the device: the torch-glue mirror of the k-mer stages (driver.genotype does the same)
+        pipe = kmer_pipeline.KmerPipeline(inp.graphs, n_paths, mem, S, inp.genders)
+        timed("countPathKmers(enumerate+sort)", pipe.enumerate_path_kmers)
+        timed("countInterclusterKmers(scan)", lambda: pipe.scan_buffer(inp.region_buf_dev, 2, 2, False))
+        timed("parseSampleKmers(stream, all samples)", lambda: [pipe.add_sample(i, kd_, cd_) for i, (kd_, cd_) in enumerate(inp.spectra_dev)])
+        unit = timed("classify+getHaplotypeCandidates", lambda: pipe.build_unit(multigroup_bloom=None, device_resident=True))
+        nb = timed("NB fit (parameter k-mers)", lambda: driver.estimate_nb_parameters(pipe, inp.region_buf_dev, inp.spectra_dev, inp.genders, opt))
         from bayestyper_b200 import shard as shard_mod
         sdesc, keep = shard_mod.shard_desc(unit, shard_ctx.comm)
         unit = timed("unit subset (own groups, on the device)", lambda: unit.subset_groups(mine))
-    eng = timed("unit upload", lambda: engine.InferenceEngine(unit))
+        eng = timed("unit upload", lambda: engine.InferenceEngine(unit))
+    else:         # the product path of one GPU: every stage through a handle of the C ABI (csrc/counter.cu)
+        from bayestyper_b200 import counter
+        kc = counter.KmerCounter(inp.graphs, n_paths, mem, S, inp.genders)
+        timed("countPathKmers(enumerate+sort)", kc.count_path_kmers)
+        timed("countInterclusterKmers(scan)", lambda: kc.count_intercluster_kmers(inp.region_buf_dev.data_ptr(), inp.region_buf_dev.numel(), 2, 2, False))
+        timed("parseSampleKmers(stream, all samples)", lambda: [kc.parse_sample_kmers(i, kd_.data_ptr(), cd_.data_ptr(), cd_.numel()) for i, (kd_, cd_) in enumerate(inp.spectra_dev)])
+        handle = timed("classify+getHaplotypeCandidates+unit", lambda: kc.build_unit(np.full(G * S, 2, np.uint8)))
+        nb = timed("NB fit (parameter k-mers)", lambda: kc.fit_nb(inp.region_buf_dev.data_ptr(), inp.region_buf_dev.numel(), inp.spectra_dev, (2, 2), None, opt.random_seed, opt.max_parameter_kmers))
+        sizes = U.Unit({**{k_: np.zeros(0, dt) for k_, dt in U._DESC_FIELDS}, "group_cluster_off": inp.graphs["group_cluster_off"], "cl_kmer_off": np.zeros(kc.Cn + 1, np.uint64),
+                        "cl_var_off": inp.graphs["cl_var_off"], "var_nalleles": kc._keep["var_nalleles"], "cl_nhap": np.asarray(n_paths, np.uint32)}, S)
+        eng = engine.InferenceEngine.from_handle(sizes, handle)
+        kc.close()
+        pipe = kmer_pipeline.KmerPipeline(inp.graphs, n_paths, mem, S, inp.genders)      # the same table once more, for the isolated timing of the stream kernel below
+        pipe.enumerate_path_kmers()
+    cd = engine.CountDistribution(nb[0], nb[1])
     gopts = U.default_opts(seed=opt.random_seed, min_frac=U.min_fraction_observed(nb[0], nb[1]),
                            group_base=shard_ctx.rank if sharded else 0, group_stride=shard_ctx.world if sharded else 1)
     if opt.noise_genotyping:

@@ -265,6 +265,16 @@ int btg_counter_parse_sample_kmers(btg_counter *k, uint32_t sample_idx, const ui
  * multigroup = the cluster stage's multigroup_kmers filter (main.cpp:345-351) or NULL (exact: k-mers that occur in several groups);
  * group_ploidy [G*S] as btg_unit_desc.                                                                                        */
 btg_unit *btg_counter_build_unit(btg_counter *k, const btg_bloom *multigroup, const uint8_t *group_ploidy);
+/* The negative-binomial fit of every sample from the parameter k-mers: the genotype-side half of countInterclusterParameterKmers +
+ * calculateKmerStats + setGenomicCountDistributions (KmerCounter.cpp:171-250, KmerHash.cpp:257-347, CountDistribution.cpp:66-141).
+ * seq_dev: the inter-cluster regions ('N'-separated) on the device; sample_*: every sample's (k-mer, count) records in HBM.
+ * parameter_kmers (host, n x 2 packed words) = <out>_cluster_data/parameter_kmers.fa.gz of the cluster stage: the fit then uses exactly
+ * those k-mers, as `bayesTyper genotype` does (main.cpp:543-584); NULL: a seeded Bernoulli subsample of the inter-cluster k-mers that are
+ * not path k-mers, capped at max_parameter_kmers.  Outputs per sample: NB (p, size) of one haploid copy, the modal multiplicity used and
+ * the number of k-mers in that class (both optional).  Fails (BTG_ESTATE) when a sample has no modal class (ploidy 0 on the contig).   */
+int btg_counter_fit_nb(btg_counter *k, const char *seq_dev, size_t len, uint32_t ploidy_female, uint32_t ploidy_male, const uint64_t *const *sample_kmers_dev,
+                       const uint8_t *const *sample_counts_dev, const size_t *sample_n, const uint64_t *parameter_kmers, size_t n_parameter_kmers, uint32_t random_seed,
+                       uint64_t max_parameter_kmers, double *nb_p_out, double *nb_size_out, uint32_t *modal_multiplicity_out, uint64_t *n_modal_kmers_out);
 /* number of elements (out = NULL) or a host copy of an array of the last btg_counter_build_unit, by its btg_unit_desc field name; also
  * "key_lo" / "key_hi" (table keys) and "key_flags" (bit0 record, bit1 multicluster, bit2 multigroup, bit3 excluded)               */
 int64_t btg_counter_array(btg_counter *k, const char *field, void *out, uint64_t out_bytes);
