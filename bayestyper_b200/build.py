@@ -72,7 +72,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
 
 
 def build_host(force: bool = False) -> Path:
-    """g++ build of the C++ host programs over the C ABI: host/btgenotype (Gibbs stage order, links libbtgpu.so) and host/btvcf
+    """g++ build of the C++ host programs over the C ABI: host/btgenotype (Gibbs stage order, links libbtgpu.so), host/btpipeline (both hot paths end to end) and host/btvcf
     (GenotypeWriter, host-only), host/btkmc (KMC database listing, makeBloom), host/btcluster (cluster / group / graph construction, host-only)."""
     hdrs = [ROOT / "include" / "btgpu.hpp", ROOT / "include" / "btgpu.h", ROOT / "include" / "btgpu_vcf.hpp", ROOT / "include" / "btgpu_params.hpp", ROOT / "host" / "btd.hpp", ROOT / "host" / "vcf_desc.hpp"]
     inc = ["-I", str(ROOT / "include"), "-I", str(ROOT / "host")]
@@ -84,6 +84,10 @@ def build_host(force: bool = False) -> Path:
     if force or not _newer(kmc, [ROOT / "host" / "btkmc.cpp", ROOT / "include" / "btgpu_kmc.hpp", LIB, *hdrs]):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", *inc, str(ROOT / "host" / "btkmc.cpp"), "-L", str(LIBDIR), "-lbtgpu",
                                "-Wl,-rpath,$ORIGIN/../bayestyper_b200/lib", "-o", str(kmc)])
+    pipe = ROOT / "host" / "btpipeline"
+    if force or not _newer(pipe, [ROOT / "host" / "btpipeline.cpp", LIB, *hdrs]):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", *inc, str(ROOT / "host" / "btpipeline.cpp"), "-L", str(LIBDIR), "-lbtgpu",
+                               "-Wl,-rpath,$ORIGIN/../bayestyper_b200/lib", "-o", str(pipe)])
     vcf = ROOT / "host" / "btvcf"
     if force or not _newer(vcf, [ROOT / "host" / "btvcf.cpp", *hdrs]):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", *inc, str(ROOT / "host" / "btvcf.cpp"), "-o", str(vcf)])

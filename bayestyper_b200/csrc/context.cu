@@ -85,6 +85,32 @@ void btg_host_free(void *p) {
     if (p) cudaFreeHost(p);
 }
 
+// device buffers for hosts that do not link the CUDA runtime themselves (host/btpipeline.cpp): sample k-mer records and region buffers that the
+// *_dev entry points read
+void *btg_device_alloc(size_t bytes) {
+    if (!btg::ctx().ready) { btg::set_error("btg_init() has not been called"); return nullptr; }
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { btg::set_error("cudaMalloc(%zu) failed", bytes); cudaGetLastError(); return nullptr; }
+    return p;
+}
+void btg_device_free(void *p) {
+    if (p) { cudaStreamSynchronize(btg::ctx().stream); cudaFree(p); }
+}
+int btg_copy_to_device(void *dst_dev, const void *src_host, size_t bytes) {
+    BTG_REQUIRE_INIT();
+    if (bytes == 0) return BTG_OK;
+    BTG_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, btg::ctx().stream));
+    BTG_CUDA(cudaStreamSynchronize(btg::ctx().stream));
+    return BTG_OK;
+}
+int btg_copy_to_host(void *dst_host, const void *src_dev, size_t bytes) {
+    BTG_REQUIRE_INIT();
+    if (bytes == 0) return BTG_OK;
+    BTG_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, btg::ctx().stream));
+    BTG_CUDA(cudaStreamSynchronize(btg::ctx().stream));
+    return BTG_OK;
+}
+
 void *btg_get_stream(void) { return btg::ctx().ready ? (void *)btg::ctx().stream : nullptr; }
 uint64_t btg_launch_count(void) { return btg::g_launches.load(); }
 void btg_launch_count_reset(void) { btg::g_launches = 0; }

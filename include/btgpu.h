@@ -58,6 +58,11 @@ int btg_device_sm_count(void);
 /* pinned host memory for callers that want overlapped staging */
 void *btg_host_alloc(size_t bytes);
 void btg_host_free(void *p);
+/* device memory for callers that do not link the CUDA runtime (the *_dev entry points read device pointers); copies are synchronous */
+void *btg_device_alloc(size_t bytes);
+void btg_device_free(void *p);
+int btg_copy_to_device(void *dst_dev, const void *src_host, size_t bytes);
+int btg_copy_to_host(void *dst_host, const void *src_dev, size_t bytes);
 /* number of kernel launches issued by this library since btg_init / last reset */
 /* the library's cudaStream_t (host entry points run on it), for callers that time with CUDA events */
 void *btg_get_stream(void);
