@@ -64,6 +64,7 @@ struct DevGraphs {
     const uint32_t *cl_smem;        // [C] bytes of the cluster's working set when it fits the per-warp shared-memory budget, else 0
     uint32_t *mt_pool;              // [resident warps][624] Mersenne states (materialised only when a cluster draws > kMtWindow numbers)
     uint32_t *next;                 // work counter
+    unsigned long long *stats;      // [3] k-mer lookups, Bloom probes executed under the reference's early-exit order, nucleotides walked (roofline)
 };
 
 // ---- std::mt19937 -------------------------------------------------------------------------------
@@ -313,11 +314,14 @@ __device__ void add_vertex_warp(Work &w, uint32_t slot, uint32_t v, const BloomV
         }
         const bool complete = lane < n && filled0 + lane + 1 >= (uint32_t)K;
         bool hit = false;
+        unsigned probes = 0;
         if (complete) {
             const Kmer128 r = revcomp(f);
-            hit = bloom_contains(bloom, ntp64(forward_is_canonical(f, r) ? f : r, T));
+            hit = bloom_contains(bloom, ntp64(forward_is_canonical(f, r) ? f : r, T), &probes);
         }
         const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, complete), hmask = __ballot_sync(0xFFFFFFFFu, hit);
+        const uint32_t np = __reduce_add_sync(0xFFFFFFFFu, probes);
+        if (lane == 0) { atomicAdd(w.g->stats, (unsigned long long)__popc(cmask)); atomicAdd(w.g->stats + 1, (unsigned long long)np); atomicAdd(w.g->stats + 2, (unsigned long long)n); }
         f0.hi = __shfl_sync(0xFFFFFFFFu, f.hi, n - 1);
         f0.lo = __shfl_sync(0xFFFFFFFFu, f.lo, n - 1);
         filled0 = filled0 + n < (uint32_t)K ? filled0 + n : (uint32_t)K;
@@ -326,6 +330,7 @@ __device__ void add_vertex_warp(Work &w, uint32_t slot, uint32_t v, const BloomV
                 if ((cmask >> t) & 1u) update_score(w, h, pv, v, (hmask >> t) & 1u, base + t + 1);
         __syncwarp();
     }
+    __syncwarp();   // every lane has read the header (a vertex without nucleotides runs no round above)
     if (lane == 0) { h->fhi = f0.hi; h->flo = f0.lo; h->filled = filled0; }
     __syncwarp();
 }
@@ -644,11 +649,15 @@ btg_graphs *btg_graphs_upload(const btg_graphs_desc *d, uint32_t max_samples, ui
         gr->grid = (uint32_t)std::max(1, per_sm) * (uint32_t)ctx().sm_count;
         uint8_t *scratch = nullptr, *best = nullptr;
         uint32_t *best_n = nullptr, *status = nullptr, *mt_pool = nullptr;
+        unsigned long long *stats = nullptr;
         ok = ok && cudaMalloc(&scratch, scr_off[C] + 16) == cudaSuccess;
         ok = ok && cudaMalloc(&best, best_off[C] + 16) == cudaSuccess;
         ok = ok && cudaMalloc(&best_n, (C + 1) * 4) == cudaSuccess && cudaMalloc(&status, 2 * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&mt_pool, (size_t)gr->grid * kPathWarps * 624 * 4) == cudaSuccess;
-        keep(scratch); keep(best); keep(best_n); keep(status); keep(mt_pool);
+        ok = ok && cudaMalloc(&stats, 3 * 8) == cudaSuccess;
+        keep(scratch); keep(best); keep(best_n); keep(status); keep(mt_pool); keep(stats);
+        if (ok) cudaMemsetAsync(stats, 0, 3 * 8, ctx().stream);
+        g.stats = stats;
         if (ok) {
             cudaMemsetAsync(best_n, 0, (C + 1) * 4, ctx().stream);
             cudaMemsetAsync(status, 0, 2 * 4, ctx().stream);
@@ -667,11 +676,20 @@ btg_graphs *btg_graphs_upload(const btg_graphs_desc *d, uint32_t max_samples, ui
     return gr;
 }
 
+int btg_graphs_path_stats(const btg_graphs *gr, uint64_t *out3) {
+    BTG_REQUIRE_INIT();
+    if (!gr || !out3) { set_error("null argument"); return BTG_EINVAL; }
+    BTG_CUDA(cudaStreamSynchronize(ctx().stream));
+    BTG_CUDA(cudaMemcpy(out3, gr->g.stats, 3 * 8, cudaMemcpyDeviceToHost));
+    return BTG_OK;
+}
+
 int btg_graphs_reset(btg_graphs *gr) {
     BTG_REQUIRE_INIT();
     if (!gr) { set_error("null argument"); return BTG_EINVAL; }
     BTG_CUDA(cudaMemsetAsync(gr->g.best_n, 0, ((size_t)gr->g.C + 1) * 4, ctx().stream));
     BTG_CUDA(cudaMemsetAsync(gr->g.status, 0, 2 * 4, ctx().stream));
+    BTG_CUDA(cudaMemsetAsync(gr->g.stats, 0, 3 * 8, ctx().stream));
     return BTG_OK;
 }
 

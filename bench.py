@@ -332,6 +332,7 @@ def run_ours(args):
 
     # ---- stage breakdown + roofline of the k-mer-match stream kernel (measured live, CUDA events) ---------
     stage_ms, roof = stage_breakdown(lib, inp, opt, stream, dev, shard_ctx)
+    paths_roof = stage_ms.pop("__paths_roofline", None)
 
     peak, peak_src = measured_peaks()
     roof.update({"peak": peak, "unit": "GB/s", "frac": roof["achieved"] / peak, "peak_source": peak_src, "bound": "hbm", "traffic": stream_traffic(roof)})
@@ -354,6 +355,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": roof,
+        "roofline_paths": None if paths_roof is None else {**paths_roof, "peak": peak, "unit": "GB/s", "frac": paths_roof["achieved"] / peak, "peak_source": peak_src},
         "stage_ms": stage_ms,
         "step_wall_ms": step_wall,
         "setup_s": setup_s,
@@ -443,6 +445,38 @@ def stage_breakdown(lib, inp, opt, stream, dev, shard_ctx=None):
         timed("estimateNoise", lambda: eng.estimate_noise(cd, gopts, want_trace=False, shard=sdesc))
         timed("estimateGenotypes", lambda: eng.estimate_genotypes(cd, gopts))
     eng.close(); cd.close()
+    # roofline of the k-mer-match kernel that costs the time: k_find_sample_paths, one sample's pass over the (rank's) graphs, CUDA events on the library stream
+    import ctypes as _C
+    from bayestyper_b200.driver import GraphsDesc
+    gsrc = sub if sharded else inp.graphs
+    gco_ = gsrc["group_cluster_off"]
+    keep_ = {"cl_vertex_off": np.ascontiguousarray(gsrc["cl_vertex_off"], np.uint64), "v_seq_off": np.ascontiguousarray(gsrc["v_seq_off"], np.uint64),
+             "seq": np.ascontiguousarray(gsrc["seq"], np.uint8), "v_flags": np.ascontiguousarray(gsrc["v_flags"], np.uint8),
+             "v_in_off": np.ascontiguousarray(gsrc["v_in_off"], np.uint64), "v_in_src": np.ascontiguousarray(gsrc["v_in_src"], np.uint32),
+             "cl_group": np.ascontiguousarray(gsrc["cl_group_global"], np.uint32) if "cl_group_global" in gsrc
+                         else np.repeat(np.arange(len(gco_) - 1, dtype=np.uint32), np.diff(np.asarray(gco_, np.int64))),
+             "cl_idx": np.ascontiguousarray(gsrc["cluster_idx"], np.uint32)}
+    gd_ = GraphsDesc(); gd_.n_clusters = len(keep_["cl_vertex_off"]) - 1
+    for k_, v_ in keep_.items():
+        setattr(gd_, k_, v_.ctypes.data)
+    gr_ = capi.check(lib.btg_graphs_upload(_C.addressof(gd_), 1, opt.max_sample_haplotypes), lib)
+    capi.check(lib.btg_find_sample_paths(gr_, inp.blooms_dev[0], 0, opt.random_seed, opt.max_sample_haplotypes), lib)      # warm-up
+    capi.check(lib.btg_graphs_reset(gr_), lib)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    capi.check(lib.btg_find_sample_paths(gr_, inp.blooms_dev[0], 0, opt.random_seed, opt.max_sample_haplotypes), lib)
+    p1.record(stream)
+    stream.synchronize()
+    pst = np.zeros(3, np.uint64)
+    capi.check(lib.btg_graphs_path_stats(gr_, pst.ctypes.data), lib)
+    lib.btg_graphs_free(gr_)
+    p_ms = p0.elapsed_time(p1)
+    p_alg = int(pst[1]) * 32 + int(pst[2]) // 4
+    out["__paths_roofline"] = {"kernel": "k_find_sample_paths (findSamplePaths: one sample's Bloom filter probed for every k-mer of every candidate path, a7)",
+                               "achieved": p_alg / (p_ms / 1e3) / 1e9, "algorithmic_bytes_per_launch": p_alg, "ms_per_launch": p_ms, "kmer_lookups": int(pst[0]),
+                               "bloom_probes_executed": int(pst[1]), "nucleotides": int(pst[2]),
+                               "bytes_model": "32 B per Bloom probe executed under the reference's early-exit order + 0.25 B per nucleotide walked (SURVEY.md section 8d)",
+                               "bound": "latency of the sequential vertex DP per cluster (lane 0) between the lane-parallel probe rounds; the sample's filter is L2-resident"}
     # roofline: the sample k-mer stream probing the exact path-k-mer table (sample 0)
     pipe.use_index()
     counts = torch.zeros_like(pipe.counts); rec = torch.zeros_like(pipe.has_record)

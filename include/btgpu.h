@@ -149,6 +149,9 @@ typedef struct btg_graphs_desc {
 
 typedef struct btg_graphs btg_graphs;
 btg_graphs *btg_graphs_upload(const btg_graphs_desc *desc, uint32_t max_samples, uint32_t max_sample_haplotypes);
+/* work done by the path searches since upload / reset: out3 = {k-mer lookups, Bloom probes executed under the reference's early-exit order
+ * (BloomFilter.hpp:149-161), nucleotides walked} — the units of the algorithmic-bytes model of the k-mer-match kernel */
+int btg_graphs_path_stats(const btg_graphs *g, uint64_t *out3);
 /* forget the best paths found so far (a new pass over the samples of the same unit: the graphs and the scratch stay in HBM) */
 int btg_graphs_reset(btg_graphs *g);
 void btg_graphs_free(btg_graphs *g);
