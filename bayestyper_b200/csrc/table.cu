@@ -327,6 +327,161 @@ __global__ void __launch_bounds__(kStreamWarps * 32) k_table_add_sample(const in
     }
 }
 
+// ---- second form of the same merge-join (the default) ------------------------------------------------------------
+// What the profile of the form above showed (profiles/r2_stream_bench_ncu_full.txt: ~1000 warp instructions per tile,
+// issue slots 60 % busy, long-scoreboard stalls on four dependent loads per tile) and what this form changes:
+//  * the search runs on a 32-bit delta of key_hi against the tile's bucket base (one LDS.32 + one ISETP per step) and is
+//    unrolled for the tile's key count (switch on log2), 3 instructions per step instead of 11;
+//  * the records' counts are loaded together with the records, not after each match (one dependent load less per record);
+//  * key_hi is not staged: with the delta exact (bucket range < 2^32) equal deltas mean equal key_hi, so a tile needs
+//    4 KB of shared memory instead of 5 and more CTAs fit;
+//  * tiles without keys end after the index read.
+// Tiles that do not qualify (no index, >= kTileKeys keys, bucket range >= 2^32: a sparse or unsorted stream) probe the
+// table record by record as before.  Results are identical (tests/test_gpu_kmer.py runs every variant).
+template <int LOG>
+__device__ __forceinline__ uint32_t lower_bound_delta(const uint32_t *__restrict__ sd, uint32_t q) {
+    uint32_t pos = 0;
+#pragma unroll
+    for (int b = LOG - 1; b >= 0; --b)
+        if (sd[pos + (1u << b) - 1u] < q) pos += 1u << b;
+    return pos;
+}
+
+template <int LOG, int LANES>
+__device__ __forceinline__ void tile_match(const uint32_t *__restrict__ sd, const int64_t *__restrict__ slo, uint32_t *sacc,
+                                           const uint32_t (&qd)[LANES], const int64_t (&qlo)[LANES], const uint32_t (&cnt)[LANES]) {
+#pragma unroll
+    for (int j = 0; j < LANES; j++) {
+        uint32_t pos = lower_bound_delta<LOG>(sd, qd[j]);
+        while (sd[pos] == qd[j] && slo[pos] < qlo[j]) pos++;  // ties on key_hi; the +inf slot past the last key ends the walk
+        if (cnt[j] && sd[pos] == qd[j] && slo[pos] == qlo[j]) atomicAdd(&sacc[pos], cnt[j]);
+    }
+}
+
+// adds the tile's accumulated counts (sacc[0..nk)) to column `sample` of table rows [t0, t0 + nk), saturating at 255
+__device__ __forceinline__ void tile_write_back(const uint32_t *sacc, int64_t t0, int64_t nk, uint32_t lane, uint32_t S, uint32_t sample,
+                                                uint8_t *table_counts, uint8_t *has_record) {
+    if (S == 1) {
+        // one lane per aligned 32-bit word of the count column (4 consecutive keys): no collisions inside the warp
+        const int64_t t1 = t0 + nk;
+        const int64_t w_first = t0 >> 2, w_last = (t1 - 1) >> 2;
+        for (int64_t wd = w_first + lane; wd <= w_last; wd += 32) {
+            uint32_t add[4];
+            bool any = false;
+#pragma unroll
+            for (int bt = 0; bt < 4; bt++) {
+                const int64_t i = wd * 4 + bt - t0;
+                add[bt] = (i >= 0 && i < nk) ? min(sacc[i], 255u) : 0u;
+                if (add[bt]) { any = true; has_record[t0 + i] = 1; }
+            }
+            if (!any) continue;
+            uint32_t *word = reinterpret_cast<uint32_t *>(table_counts) + wd;  // cudaMalloc'd column: 4-byte aligned
+            uint32_t old = *word, assumed;
+            do {
+                assumed = old;
+                uint32_t nw = 0;
+#pragma unroll
+                for (int bt = 0; bt < 4; bt++) {
+                    const uint32_t cur = (assumed >> (8 * bt)) & 0xFFu;
+                    nw |= ((255u - cur) <= add[bt] ? 255u : cur + add[bt]) << (8 * bt);
+                }
+                old = atomicCAS(word, assumed, nw);
+            } while (old != assumed);
+        }
+    } else {
+        for (int64_t i0 = 0; i0 < nk; i0 += 32) {  // one coalesced pass over the tile's keys
+            const int64_t i = i0 + lane;
+            const uint32_t add = i < nk ? sacc[i] : 0;
+            if (add) has_record[t0 + i] = 1;
+            uint8_t *p = table_counts + (size_t)(t0 + (i < nk ? i : 0)) * S + sample;
+            if (S >= 4) { if (add) sat_add_u8(p, add > 255u ? 255u : add); }   // distinct keys, distinct words
+            else sat_add_u8_warp(add != 0, p, add > 255u ? 255u : add);
+        }
+    }
+}
+
+template <int LANES, int MIN_CTAS>
+__global__ void __launch_bounds__(kStreamWarps * 32, MIN_CTAS) k_table_add_sample_v2(const int64_t *__restrict__ kw0, const int64_t *__restrict__ kw1, int64_t n_keys,
+                                                          const longlong2 *__restrict__ kmers, const uint8_t *__restrict__ counts, size_t n,
+                                                          uint32_t S, uint32_t sample, uint8_t *table_counts, uint8_t *has_record, TableIndex ix) {
+    __shared__ uint32_t s_d[kStreamWarps][kTileKeys];
+    __shared__ int64_t s_lo[kStreamWarps][kTileKeys];
+    __shared__ uint32_t s_acc[kStreamWarps][kTileKeys];
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const size_t n_tiles = (n + 32 * LANES - 1) / (32 * LANES);
+    const size_t warp_id = (size_t)blockIdx.x * kStreamWarps + w, n_warps = (size_t)gridDim.x * kStreamWarps;
+    uint32_t *sd = s_d[w], *sacc = s_acc[w];
+    int64_t *slo = s_lo[w];
+    for (size_t tile = warp_id; tile < n_tiles; tile += n_warps) {  // warp-uniform trip count
+        const size_t r0 = tile * (32 * LANES);
+        int64_t qhi[LANES], qlo[LANES];
+        uint32_t cnt[LANES];
+        uint32_t bmin = 0xFFFFFFFFu, bmax = 0;
+#pragma unroll
+        for (int j = 0; j < LANES; j++) {
+            const size_t i = r0 + (size_t)j * 32 + lane;
+            if (i < n) {
+                const longlong2 k = __ldg(kmers + i);
+                cnt[j] = __ldg(counts + i);
+                const TableKey q = key_of_boundary(k.x, k.y);
+                qhi[j] = q.hi; qlo[j] = q.lo;
+                const uint32_t b = (uint32_t)(q.hi >> ix.shift);
+                bmin = min(bmin, b); bmax = max(bmax, b);
+            } else { cnt[j] = 0; qhi[j] = -1; qlo[j] = 0; }
+        }
+        bool tiled = false;
+        int64_t t0 = 0, nk = 0;
+        if (ix.lut) {
+            bmin = __reduce_min_sync(0xFFFFFFFFu, bmin);
+            bmax = __reduce_max_sync(0xFFFFFFFFu, bmax);
+            int64_t v = 0;
+            if (lane == 0) v = __ldg(ix.lut + bmin); else if (lane == 1) v = __ldg(ix.lut + bmax + 1);
+            t0 = __shfl_sync(0xFFFFFFFFu, v, 0);
+            nk = __shfl_sync(0xFFFFFFFFu, v, 1) - t0;
+            if (nk == 0) continue;                          // no table key in the tile's buckets (warp-uniform)
+            tiled = nk < kTileKeys && ((uint64_t)(bmax - bmin + 1u) << ix.shift) < 0xFFFFFFFFull;
+        }
+        if (tiled) {
+            const int64_t base = (int64_t)bmin << ix.shift;
+            const int log_top = 32 - __clz((uint32_t)nk);   // 2^log_top > nk: the search covers 2^log_top - 1 >= nk slots
+            const uint32_t top = 1u << log_top;
+            for (uint32_t i = lane; i < top; i += 32) {     // slots past the last key hold +inf: no bound checks in the search
+                const bool in = (int64_t)i < nk;
+                sd[i] = in ? (uint32_t)(__ldg(kw1 + t0 + i) - base) : 0xFFFFFFFFu;
+                slo[i] = in ? __ldg(kw0 + t0 + i) : INT64_MAX;
+                sacc[i] = 0;
+            }
+            uint32_t qd[LANES];
+#pragma unroll
+            for (int j = 0; j < LANES; j++) qd[j] = cnt[j] ? (uint32_t)(qhi[j] - base) : 0xFFFFFFFFu;   // in-range deltas are < 2^32 - 1
+            __syncwarp();
+            switch (log_top) {
+                case 1: tile_match<1, LANES>(sd, slo, sacc, qd, qlo, cnt); break;
+                case 2: tile_match<2, LANES>(sd, slo, sacc, qd, qlo, cnt); break;
+                case 3: tile_match<3, LANES>(sd, slo, sacc, qd, qlo, cnt); break;
+                case 4: tile_match<4, LANES>(sd, slo, sacc, qd, qlo, cnt); break;
+                case 5: tile_match<5, LANES>(sd, slo, sacc, qd, qlo, cnt); break;
+                case 6: tile_match<6, LANES>(sd, slo, sacc, qd, qlo, cnt); break;
+                case 7: tile_match<7, LANES>(sd, slo, sacc, qd, qlo, cnt); break;
+                default: tile_match<8, LANES>(sd, slo, sacc, qd, qlo, cnt); break;
+            }
+            __syncwarp();
+            tile_write_back(sacc, t0, nk, lane, S, sample, table_counts, has_record);
+        } else {
+#pragma unroll
+            for (int j = 0; j < LANES; j++) {
+                if (r0 + (size_t)j * 32 + lane >= n) continue;
+                const int64_t idx = table_find(kw0, kw1, n_keys, qlo[j], qhi[j], ix);
+                if (idx >= 0 && cnt[j]) {
+                    sat_add_u8(table_counts + (size_t)idx * S + sample, cnt[j]);
+                    has_record[idx] = 1;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // table keys <-> packed k-mers in the ABI's boundary layout
 __global__ void __launch_bounds__(256) k_keys_from_kmers(const longlong2 *__restrict__ kmers, size_t n, int64_t *__restrict__ kw0, int64_t *__restrict__ kw1) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -458,8 +613,20 @@ int btg_table_add_sample_kmers_dev(const int64_t *key_w0, const int64_t *key_w1,
     if (sample_idx >= n_samples) { set_error("sample index out of range"); return BTG_EINVAL; }
     if (reinterpret_cast<uintptr_t>(table_counts) & 3u) { set_error("table_counts must be 4-byte aligned"); return BTG_EINVAL; }
     if (n == 0) return BTG_OK;
-    k_table_add_sample<<<btg_grid_for((n + kTileLanes - 1) / kTileLanes, kStreamWarps * 32, 5), kStreamWarps * 32, 0, pick_stream(stream)>>>(key_w0, key_w1, n_keys, (const longlong2 *)kmers, counts, n, n_samples,
-                                                                               sample_idx, table_counts, has_record, g_index);
+    static const int variant = [] { const char *e = getenv("BTG_STREAM_VARIANT"); return e ? atoi(e) : 1; }();
+    const cudaStream_t st = pick_stream(stream);
+#define BTG_STREAM_LAUNCH(KERNEL, LANES, CTAS)                                                                                              \
+    KERNEL<<<btg_grid_for((n + (LANES) - 1) / (LANES), kStreamWarps * 32, CTAS), kStreamWarps * 32, 0, st>>>(                                   \
+        key_w0, key_w1, n_keys, (const longlong2 *)kmers, counts, n, n_samples, sample_idx, table_counts, has_record, g_index)
+    switch (variant) {
+        case 0: BTG_STREAM_LAUNCH(k_table_add_sample, kTileLanes, 5); break;
+        case 2: BTG_STREAM_LAUNCH((k_table_add_sample_v2<4, 6>), 4, 6); break;
+        case 3: BTG_STREAM_LAUNCH((k_table_add_sample_v2<4, 7>), 4, 7); break;
+        case 4: BTG_STREAM_LAUNCH((k_table_add_sample_v2<8, 4>), 8, 4); break;
+        case 5: BTG_STREAM_LAUNCH((k_table_add_sample_v2<2, 7>), 2, 7); break;
+        default: BTG_STREAM_LAUNCH((k_table_add_sample_v2<4, 5>), 4, 5); break;
+    }
+#undef BTG_STREAM_LAUNCH
     BTG_LAUNCHED();
     BTG_CUDA(cudaGetLastError());
     return BTG_OK;

@@ -8,6 +8,8 @@ from __future__ import annotations
 
 import ctypes as C
 import dataclasses
+import os
+import time
 
 import numpy as np
 import torch
@@ -323,6 +325,25 @@ def inputs_from_kmc(chrom: str, reference: bytes, variants, samples) -> Inputs:
     return Inputs(chrom, reference, variants, genders, spectra, blooms=blooms if len(blooms) == len(samples) else None)
 
 
+class _StageClock:
+    """BTG_STAGE_TIMES=1: wall time of every stage of genotype() with a device synchronisation after each (diagnostics; off by default)."""
+
+    def __init__(self):
+        self.on = os.environ.get("BTG_STAGE_TIMES") == "1"
+        self.out = {}
+        if self.on:
+            torch.cuda.synchronize()
+        self.t = time.perf_counter()
+
+    def mark(self, name):
+        if not self.on:
+            return
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        self.out[name] = self.out.get(name, 0.0) + (now - self.t) * 1e3
+        self.t = now
+
+
 def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rates=None, resident: bool = False, want_unit: bool = False,
              vcf_out=None, sample_names=None, shard: Shard | None = None):
     """One pass of both hot paths: path search -> k-mer table -> haplotype candidates -> NB fit -> noise -> Gibbs.
@@ -337,6 +358,8 @@ def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rate
     S = len(inp.spectra) if inp.spectra is not None else len(inp.spectra_dev)
     dev = torch.device("cuda", torch.cuda.current_device())
     info = {}
+    clk = _StageClock()
+    info["stage_wall_ms"] = clk.out
     own_blooms = False
     if resident:
         spectra_dev, blooms, region_buf = inp.spectra_dev, inp.blooms_dev, inp.region_buf_dev
@@ -367,12 +390,13 @@ def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rate
         n_paths, mem = merge_best_paths(inp.graphs, [(p[0], p[1]) for p in parts], [p[2] for p in parts])
     else:
         n_paths, mem = find_variant_cluster_paths(lib, inp.graphs, blooms, opt, inp.resident_cache if resident else None)
+    clk.mark("inputs+paths")
     if own_blooms:
         for b in blooms:
             lib.btg_bloom_free(b)
     ploidy = np.tile(np.array([female_ploidy if g in ("F", 0) else male_ploidy for g in inp.genders], np.uint8), G)
     if opt.kmer_stages == "abi" and not sharded and not want_unit:
-        return _genotype_abi(lib, inp, opt, n_paths, mem, S, spectra_dev, region_buf, (female_ploidy, male_ploidy), ploidy, nb_params, noise_rates, info, vcf_out, sample_names)
+        return _genotype_abi(lib, inp, opt, n_paths, mem, S, spectra_dev, region_buf, (female_ploidy, male_ploidy), ploidy, nb_params, noise_rates, info, vcf_out, sample_names, clk)
     pipe = kmer_pipeline.KmerPipeline(inp.graphs, n_paths, mem, S, inp.genders)
     info["n_path_kmers"] = pipe.enumerate_path_kmers()
     pipe.scan_buffer(region_buf, female_ploidy, male_ploidy, False)
@@ -421,18 +445,22 @@ def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rate
     return (inp.graphs, unit if want_unit else None, res, info)
 
 
-def _genotype_abi(lib, inp, opt, n_paths, mem, S, spectra_dev, region_buf, gender_ploidy, ploidy, nb_params, noise_rates, info, vcf_out, sample_names):
+def _genotype_abi(lib, inp, opt, n_paths, mem, S, spectra_dev, region_buf, gender_ploidy, ploidy, nb_params, noise_rates, info, vcf_out, sample_names, clk=None):
     """The stages after the path search through handles of the C ABI only (what host/btpipeline.cpp does in C++): btg_counter (countPathKmers,
     countInterclusterKmers, parseSampleKmers, classifyPathKmers + getHaplotypeCandidates, NB fit) -> btg_unit -> btg_count_dist -> Gibbs."""
     from . import counter
+    clk = clk or _StageClock()
     torch.cuda.synchronize()
     kc = counter.KmerCounter(inp.graphs, n_paths, mem, S, inp.genders)
     try:
+        clk.mark("counter create")
         info["n_path_kmers"] = kc.count_path_kmers()
         kc.count_intercluster_kmers(region_buf.data_ptr(), region_buf.numel(), gender_ploidy[0], gender_ploidy[1], False)
         for s, (kd, cdv) in enumerate(spectra_dev):
             kc.parse_sample_kmers(s, kd.data_ptr(), cdv.data_ptr(), cdv.numel())
+        clk.mark("k-mer table stages")
         handle = kc.build_unit(ploidy)
+        clk.mark("build unit")
         if nb_params is None:
             nb_p, nb_size, used = kc.fit_nb(region_buf.data_ptr(), region_buf.numel(), spectra_dev, gender_ploidy, inp.parameter_kmers, opt.random_seed, opt.max_parameter_kmers)
             info["nb_fit"] = [(m, n, None, None) for m, n in used]
@@ -442,9 +470,11 @@ def _genotype_abi(lib, inp, opt, n_paths, mem, S, spectra_dev, region_buf, gende
                         "cl_var_off": inp.graphs["cl_var_off"], "var_nalleles": kc._keep["var_nalleles"], "cl_nhap": np.asarray(n_paths, np.uint32)}, S)   # sizes the result arrays only
     finally:
         kc_done = kc
+    clk.mark("NB fit")
     cd = engine.CountDistribution(nb_p, nb_size, opt.noise_rate_prior)
     eng = engine.InferenceEngine.from_handle(sizes, handle)
     kc_done.close()
+    clk.mark("count distribution + counter free")
     gopts = U.default_opts(seed=opt.random_seed, burn=opt.gibbs_burn_in, samples=opt.gibbs_samples, chains=opt.n_chains, rate=opt.kmer_subsampling_rate,
                            max_hv=opt.max_haplotype_variant_kmers, min_gpp=opt.min_genotype_posterior, min_kmers=opt.min_number_of_kmers,
                            min_frac=None if opt.disable_observed_kmers else U.min_fraction_observed(nb_p, nb_size))
@@ -455,7 +485,9 @@ def _genotype_abi(lib, inp, opt, n_paths, mem, S, spectra_dev, region_buf, gende
             info["noise_trace"] = eng.estimate_noise(cd, gopts, want_trace=False)
         else:
             cd.set_noise_rates(noise_rates)
+        clk.mark("estimateNoise")
         res = eng.estimate_genotypes(cd, gopts)
+    clk.mark("estimateNoiseAndGenotypes" if opt.noise_genotyping else "estimateGenotypes")
     info["noise_rates"] = cd.noise_rates()
     info["nb"] = (nb_p, nb_size)
     info["n_clusters"] = info["n_clusters_total"] = sizes.Cn
@@ -463,6 +495,7 @@ def _genotype_abi(lib, inp, opt, n_paths, mem, S, spectra_dev, region_buf, gende
     info["haplotype_candidates"] = {"max": int(nh.max()) if len(nh) else 0, "q50": float(np.quantile(nh, 0.5)) if len(nh) else 0, "q99": float(np.quantile(nh, 0.99)) if len(nh) else 0,
                                     "clusters_over_32": int((nh > 32).sum())}
     eng.close(); cd.close()
+    clk.mark("free")
     if vcf_out is not None:
         from . import vcf_desc
         names = list(sample_names) if sample_names is not None else [f"S{i + 1}" for i in range(S)]

@@ -281,6 +281,8 @@ def run_ours(args):
             t_step = time.perf_counter()
             _, _, res, info = driver.genotype(inp, opt, resident=True, shard=shard_ctx)     # returns with the results on the host: the step has ended
             step_wall.append((time.perf_counter() - t_step) * 1e3)
+            if info.get("stage_wall_ms"):
+                print("step stages (BTG_STAGE_TIMES):", {k: round(v, 1) for k, v in info["stage_wall_ms"].items()}, file=sys.stderr)
         e1.record(stream)
         stream.synchronize()
         torch.cuda.synchronize()
@@ -295,7 +297,7 @@ def run_ours(args):
 
     if args.timed_only:          # profiler runs (ncu launch list): the warm-up + timed steps only; not a bench line
         if rank == 0:
-            emit({"timed_only": True, "ms_per_step": ms_per_step, "value": value, "gpu_launches": launches, "n_clusters": n_clusters})
+            emit({"timed_only": True, "ms_per_step": ms_per_step, "value": value, "gpu_launches": launches, "n_clusters": n_clusters, "step_wall_ms": step_wall})
         inp.free(lib)
         return
     # ---- e2e: every input crosses the boundary from host memory inside the call --------------------------

@@ -49,6 +49,7 @@ def test_two_rank_sharding_equals_single_process(tmp_path):
     cost = shard.group_costs(fx.unit)
     c0, c1 = cost[parts[0][0]:parts[0][1]].sum(), cost[parts[1][0]:parts[1][1]].sum()
     assert abs(c0 - c1) / (c0 + c1) < 0.25
+    O.load()          # build the oracle library once here: two workers running `make` at the same time would race
     mp.spawn(_worker, args=(2, 29517, str(tmp_path)), nprocs=2, join=True)
     got = np.load(tmp_path / "sharded.npz")
     cd = O.OracleCountDist(fx.nb_p, fx.nb_size)
@@ -88,3 +89,77 @@ def test_group_tables_describe_the_whole_unit():
         # the shards tile the group axis, so group_index_base + local index addresses these tables
         parts = shard.partition(fx.unit, 3)
         assert sum(hi - lo for lo, hi in parts) == fx.unit.G
+
+
+# ---- the k-mer path's one exchange: best paths of every cluster (driver.Shard / subset_graphs_for_paths / merge_best_paths) ----------
+
+def _paths_worker(rank, world, port, out_dir, name):
+    sys.path.insert(0, str(ROOT))
+    import torch.distributed as dist
+    from bayestyper_b200 import btd, driver
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def allgather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+    sh = driver.Shard(world, rank, allgather)
+    d = btd.read(ROOT / "tests" / "golden" / f"{name}.btd")
+    g = {k[2:]: v for k, v in d.items() if k.startswith("g.")}
+    G = len(g["group_cluster_off"]) - 1
+    mine = sh.my_groups(G)
+    sub, clusters = driver.subset_graphs_for_paths(g, mine)
+    # stand-in for this rank's path search (no GPU here): the golden best paths of its own clusters, in the sub-graph's order
+    V = np.diff(g["cl_vertex_off"].astype(np.int64))
+    po = g["cl_path_off"].astype(np.int64)
+    n_paths = (np.diff(po) // np.maximum(V, 1))[clusters]
+    mem = np.concatenate([g["path_bits"][po[c]:po[c + 1]] for c in clusters]) if len(clusters) else np.zeros(0, np.uint8)
+    assert (np.diff(sub["cl_vertex_off"].astype(np.int64)) == V[clusters]).all()
+    parts = sh.allgather((n_paths, mem, clusters))
+    merged_n, merged_mem = driver.merge_best_paths(g, [(p[0], p[1]) for p in parts], [p[2] for p in parts])
+    np.savez(Path(out_dir) / f"merged_{rank}.npz", n=merged_n, mem=merged_mem)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_best_paths_exchange_two_ranks(tmp_path):
+    """Every rank searches the paths of its own (strided) groups; after the all-gather every rank holds the best paths of the
+    whole unit, identical to the single-rank result (here: the reference's golden best paths)."""
+    sys.path.insert(0, str(ROOT))
+    from bayestyper_b200 import btd
+    name = "paths_nested_2s"
+    mp.spawn(_paths_worker, args=(2, 29531, str(tmp_path), name), nprocs=2, join=True)
+    d = btd.read(ROOT / "tests" / "golden" / f"{name}.btd")
+    V = np.diff(d["g.cl_vertex_off"].astype(np.int64))
+    want_n = np.diff(d["g.cl_path_off"].astype(np.int64)) // np.maximum(V, 1)
+    for r in range(2):
+        got = np.load(tmp_path / f"merged_{r}.npz")
+        assert (got["n"] == want_n).all()
+        assert (got["mem"] == d["g.path_bits"]).all()
+
+
+def test_subset_graphs_keeps_vertices_edges_and_group_indices():
+    sys.path.insert(0, str(ROOT))
+    from bayestyper_b200 import btd, driver
+    d = btd.read(ROOT / "tests" / "golden" / "paths_nested_2s.btd")
+    g = {k[2:]: v for k, v in d.items() if k.startswith("g.")}
+    G = len(g["group_cluster_off"]) - 1
+    groups = np.arange(1, G, 3, dtype=np.int64)
+    sub, clusters = driver.subset_graphs_for_paths(g, groups)
+    gco = g["group_cluster_off"].astype(np.int64)
+    assert (clusters == np.concatenate([np.arange(gco[x], gco[x + 1]) for x in groups])).all()
+    assert (sub["cl_group_global"] == np.repeat(groups, np.diff(gco)[groups])).all()      # the seed of a cluster's path search is its group's index in the WHOLE unit
+    assert (sub["cluster_idx"] == g["cluster_idx"][clusters]).all()
+    cvo, vso, vio = (g[k].astype(np.int64) for k in ("cl_vertex_off", "v_seq_off", "v_in_off"))
+    s_cvo, s_vso, s_vio = (sub[k].astype(np.int64) for k in ("cl_vertex_off", "v_seq_off", "v_in_off"))
+    for i, c in enumerate(clusters):
+        assert s_cvo[i + 1] - s_cvo[i] == cvo[c + 1] - cvo[c]
+        for j in range(cvo[c + 1] - cvo[c]):
+            v, sv = cvo[c] + j, s_cvo[i] + j
+            assert (sub["seq"][s_vso[sv]:s_vso[sv + 1]] == g["seq"][vso[v]:vso[v + 1]]).all()
+            assert sub["v_flags"][sv] == g["v_flags"][v]
+            assert (sub["v_in_src"][s_vio[sv]:s_vio[sv + 1]] == g["v_in_src"][vio[v]:vio[v + 1]]).all()     # edge sources are vertex indices inside the cluster
+    empty, cl = driver.subset_graphs_for_paths(g, np.zeros(0, np.int64))
+    assert len(cl) == 0 and len(empty["cl_vertex_off"]) == 1
