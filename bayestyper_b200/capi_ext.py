@@ -49,3 +49,5 @@ def bind(L):
     L.btg_comm_free.restype = None
     L.btg_estimate_noise_sharded.argtypes = [vp, vp, vp, vp, vp]
     L.btg_estimate_noise_and_genotypes_sharded.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.btg_estimate_noise_chains.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp]
+    L.btg_count_dist_finish_noise.argtypes = [vp, vp, C.c_uint32, C.c_uint32]

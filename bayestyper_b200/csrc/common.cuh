@@ -25,6 +25,17 @@ extern std::atomic<uint64_t> g_launches;
 
 inline cudaStream_t pick_stream(void *s) { return s ? (cudaStream_t)s : ctx().stream; }
 
+// Device allocations of the per-unit objects (unit arrays, sampler arena, results, path-search scratch) go through a block cache
+// (context.cu): a multi-GB cudaMalloc / cudaFree pair maps and unmaps physical memory in the driver (measured on configs[1]: 20-500 ms
+// per freed unit, different every time), the cache hands the same blocks to the next unit.  dfree waits for the device like cudaFree
+// does.  (The stream-ordered pool of the CUDA runtime was tried for these blocks too: sharing it with the ~100 small stream-ordered
+// allocations of counter.cu made multi-GB requests remap physical memory, 0.4 s stalls at random stages.)
+cudaError_t dmalloc_bytes(void **p, size_t bytes);
+void dfree(void *p);
+void release_cached_blocks();   // btg_shutdown
+size_t free_device_memory();   // cudaMemGetInfo's free bytes + what the pool holds without using it
+template <class T> inline cudaError_t dmalloc(T **p, size_t bytes) { return dmalloc_bytes(reinterpret_cast<void **>(p), bytes); }
+
 }  // namespace btg
 
 #define BTG_CUDA(call)                                                                              \

@@ -530,8 +530,8 @@ btg_count_dist *btg_count_dist_create(uint32_t S, const double *nb_p, const doub
     cd->size = upload(nb_size, S, ok);
     std::vector<double> ones(S, 1.0);
     cd->rates = upload(ones.data(), S, ok);
-    ok = ok && cudaMalloc(&cd->genomic, (size_t)S * 65536 * sizeof(double)) == cudaSuccess;
-    ok = ok && cudaMalloc(&cd->noise, (size_t)S * 256 * sizeof(double)) == cudaSuccess;
+    ok = ok && btg::dmalloc(&cd->genomic, (size_t)S * 65536 * sizeof(double)) == cudaSuccess;
+    ok = ok && btg::dmalloc(&cd->noise, (size_t)S * 256 * sizeof(double)) == cudaSuccess;
     if (!ok) { set_error("count distribution allocation failed"); btg_count_dist_free(cd); return nullptr; }
     auto s = ctx().stream;
     k_genomic_table<<<(S * 65536 + 255) / 256, 256, 0, s>>>(cd->p, cd->size, S, cd->genomic);
@@ -579,7 +579,7 @@ int btg_count_dist_tables(const btg_count_dist *cd, double *genomic_out, double 
 
 void btg_count_dist_free(btg_count_dist *cd) {
     if (!cd) return;
-    cudaFree(cd->p); cudaFree(cd->size); cudaFree(cd->rates); cudaFree(cd->genomic); cudaFree(cd->noise);
+    btg::dfree(cd->p); btg::dfree(cd->size); btg::dfree(cd->rates); btg::dfree(cd->genomic); btg::dfree(cd->noise);
     delete cd;
 }
 
@@ -594,7 +594,7 @@ btg_unit *btg_unit_upload_dev(const btg_unit_desc *d, const btg_unit_desc *dev, 
         using T = std::remove_cv_t<std::remove_pointer_t<decltype(host_ptr)>>;
         if (!dev_ptr) return upload(host_ptr, n, ok_flag);
         T *p = nullptr;
-        if (cudaMalloc(&p, (n ? n : 1) * sizeof(T)) != cudaSuccess) { ok_flag = false; return (T *)nullptr; }
+        if (btg::dmalloc(&p, (n ? n : 1) * sizeof(T)) != cudaSuccess) { ok_flag = false; return (T *)nullptr; }
         if (n && cudaMemcpyAsync(p, dev_ptr, n * sizeof(T), cudaMemcpyDeviceToDevice, ctx().stream) != cudaSuccess) ok_flag = false;
         return p;
     };
@@ -707,7 +707,7 @@ btg_unit *btg_unit_upload_dev(const btg_unit_desc *d, const btg_unit_desc *dev, 
         du.nest_slot = keep(upload(nest_slot.data(), C, ok));
         auto dmalloc = [&](auto *&dst, size_t n) {
             void *p = nullptr;
-            if (cudaMalloc(&p, (n ? n : 1) * sizeof(*dst)) != cudaSuccess) { ok = false; dst = nullptr; return; }
+            if (btg::dmalloc(&p, (n ? n : 1) * sizeof(*dst)) != cudaSuccess) { ok = false; dst = nullptr; return; }
             u->allocs.push_back(p);
             dst = static_cast<std::remove_reference_t<decltype(dst)>>(p);
         };
@@ -790,8 +790,7 @@ btg_unit *btg_unit_upload_dev(const btg_unit_desc *d, const btg_unit_desc *dev, 
     uint64_t cache_cap = kWideCacheCap;
     if (getenv("BTG_WIDE_CACHE_CAP")) cache_cap = strtoull(getenv("BTG_WIDE_CACHE_CAP"), nullptr, 10);
     else if (du.wide) {
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
+        const size_t free_b = btg::free_device_memory();
         cache_cap = 1ull << 24;
         for (;;) {
             uint64_t bytes = 0;
@@ -825,7 +824,7 @@ btg_unit *btg_unit_upload_dev(const btg_unit_desc *d, const btg_unit_desc *dev, 
         if (!du.wide && u->h_fill_cost[c] > (uint64_t)big_fill_cost() * S) { tile_off[c] = tile_total; tile_total += ((uint64_t)dims[c].nu * (dims[c].H + S + 2) + 31) & ~31ull; }
     du.big_tile_off = keep(upload(tile_off.data(), C, ok));
     uint8_t *tile_pool = nullptr;
-    ok = ok && cudaMalloc(&tile_pool, tile_total + 32) == cudaSuccess;
+    ok = ok && btg::dmalloc(&tile_pool, tile_total + 32) == cudaSuccess;
     keep(tile_pool);
     du.big_tile_pool = tile_pool;
     up_lap("host layout");
@@ -838,11 +837,11 @@ btg_unit *btg_unit_upload_dev(const btg_unit_desc *d, const btg_unit_desc *dev, 
     du.slots = keep(upload(u->h_slots.data(), u->h_slots.size(), ok));
     du.order = keep(upload(order.data(), C, ok));
     double *f64_pool = nullptr; uint32_t *u32_pool = nullptr; uint8_t *u8_pool = nullptr; double *lg = nullptr;
-    ok = ok && cudaMalloc(&f64_pool, (f64_total + 1) * sizeof(double)) == cudaSuccess;
-    ok = ok && cudaMalloc(&u32_pool, (u32_total + 1) * sizeof(uint32_t)) == cudaSuccess;
-    ok = ok && cudaMalloc(&u8_pool, u8_total + 8) == cudaSuccess;
+    ok = ok && btg::dmalloc(&f64_pool, (f64_total + 1) * sizeof(double)) == cudaSuccess;
+    ok = ok && btg::dmalloc(&u32_pool, (u32_total + 1) * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && btg::dmalloc(&u8_pool, u8_total + 8) == cudaSuccess;
     const uint32_t n_lg = u->max_h + 2 * S + 4;
-    ok = ok && cudaMalloc(&lg, n_lg * sizeof(double)) == cudaSuccess;
+    ok = ok && btg::dmalloc(&lg, n_lg * sizeof(double)) == cudaSuccess;
     keep(f64_pool); keep(u32_pool); keep(u8_pool); keep(lg);
     u->f64_total = f64_total; u->u32_total = u32_total; u->u8_total = u8_total; u->tile_total = tile_total;
     du.f64_pool = f64_pool; du.u32_pool = u32_pool; du.u8_pool = u8_pool; du.lgamma_int = lg;
@@ -863,7 +862,7 @@ btg_unit *btg_unit_upload_dev(const btg_unit_desc *d, const btg_unit_desc *dev, 
 void btg_unit_free(btg_unit *u) {
     if (!u) return;
     cudaStreamSynchronize(ctx().stream);
-    for (void *p : u->allocs) cudaFree(p);
+    for (void *p : u->allocs) btg::dfree(p);
     btg_unit_free_result(u);
     delete u;
 }
@@ -876,7 +875,7 @@ struct DevResult {
     ResultView R{};
     std::vector<void *> allocs;
     uint64_t nv = 0, nall = 0, ngen = 0, nalt = 0;
-    ~DevResult() { for (void *p : allocs) cudaFree(p); }
+    ~DevResult() { for (void *p : allocs) btg::dfree(p); }
 };
 
 DevResult *unit_result(btg_unit *u) {
@@ -888,7 +887,7 @@ DevResult *unit_result(btg_unit *u) {
     bool ok = true;
     auto mk = [&](auto *&dst, size_t n) {
         void *d = nullptr;
-        if (cudaMalloc(&d, (n ? n : 1) * sizeof(*dst)) != cudaSuccess) { ok = false; return; }
+        if (btg::dmalloc(&d, (n ? n : 1) * sizeof(*dst)) != cudaSuccess) { ok = false; return; }
         dr->allocs.push_back(d);
         dst = static_cast<std::remove_reference_t<decltype(dst)>>(d);
     };
@@ -934,7 +933,7 @@ int btg_estimate_genotypes_async(btg_unit *u, const btg_count_dist *cd, const bt
         const int reconverge = getenv("BTG_GIBBS_SYNC") ? atoi(getenv("BTG_GIBBS_SYNC")) : 1;
         const unsigned grid = (u->du.n_regular + u->du.n_split * kChainSplit + 63) / 64;
         unsigned long long *dbg = nullptr;
-        if (getenv("BTG_GIBBS_TIMING")) { cudaMalloc(&dbg, 32); cudaMemset(dbg, 0, 32); }
+        if (getenv("BTG_GIBBS_TIMING")) { btg::dmalloc(&dbg, 32); cudaMemset(dbg, 0, 32); }
         // hot state of the small clusters in shared memory (gibbs_core.cuh): hot_bytes(S) per thread, as long as the blocks of an SM still fit
         const size_t hot_smem = (size_t)hot_bytes(u->du.S) * 64;
         static const int hot_env = getenv("BTG_HOT") ? atoi(getenv("BTG_HOT")) : 1;
@@ -959,7 +958,7 @@ int btg_estimate_genotypes_async(btg_unit *u, const btg_count_dist *cd, const bt
             unsigned long long h[4];
             cudaStreamSynchronize(pick_stream(stream));
             cudaMemcpy(h, dbg, 32, cudaMemcpyDeviceToHost);
-            cudaFree(dbg);
+            btg::dfree(dbg);
             const uint32_t c = (uint32_t)(h[0] & 0xFFFFFFFFu);
             fprintf(stderr, "[btgpu] k_estimate_genotypes: slowest thread %.1f ms (cluster %u, H %u, fill cost %u); mean thread %.2f ms over %u clusters; clusters with H > 4 hold %.1f %% of the thread time\n",
                     (h[0] >> 32) / 1e6, c, c < u->du.C ? u->h_nhap[c] : 0, c < u->du.C ? u->h_fill_cost[c] : 0, h[1] / 1e6 / std::max(1u, u->du.n_regular), u->du.n_regular, 100.0 * h[2] / std::max<unsigned long long>(1, h[1]));
@@ -1053,7 +1052,8 @@ static size_t noise_chain_hot_smem(uint32_t S, uint32_t bs, int *hot_out) {
 }
 
 static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, double *trace_out, int joint);
-static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, double *trace_out);
+static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, double *trace_out,
+                                     uint32_t chain_first = 0, uint32_t chain_stride = 1, double *chain_sums_out = nullptr);
 
 int btg_estimate_noise(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, double *trace_out) {
     return estimate_noise_concurrent(u, cd, opts, nullptr, trace_out);
@@ -1061,6 +1061,28 @@ int btg_estimate_noise(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *op
 
 int btg_estimate_noise_sharded(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, double *trace_out) {
     return estimate_noise_concurrent(u, cd, opts, sh, trace_out);
+}
+
+int btg_estimate_noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, uint32_t chain_first, uint32_t chain_stride, double *chain_sums_out,
+                              double *trace_out) {
+    if (!chain_sums_out || chain_stride == 0 || chain_first >= chain_stride) { set_error("bad chain partition (first %u, stride %u)", chain_first, chain_stride); return BTG_EINVAL; }
+    return estimate_noise_concurrent(u, cd, opts, nullptr, trace_out, chain_first, chain_stride, chain_sums_out);
+}
+
+int btg_count_dist_finish_noise(btg_count_dist *cd, const double *chain_sums, uint32_t n_chains, uint32_t gibbs_samples) {
+    BTG_REQUIRE_INIT();
+    if (!cd || !chain_sums || n_chains == 0 || gibbs_samples == 0) { set_error("bad argument"); return BTG_EINVAL; }
+    double *d = nullptr;
+    const size_t bytes = (size_t)n_chains * cd->S * sizeof(double);
+    if (btg::dmalloc(&d, bytes) != cudaSuccess) { set_error("allocation failed"); return BTG_ENOMEM; }
+    auto s0 = ctx().stream;
+    cudaMemcpyAsync(d, chain_sums, bytes, cudaMemcpyHostToDevice, s0);
+    k_noise_finish<<<1, 256, 0, s0>>>(d, n_chains, cd->S, (double)gibbs_samples * n_chains, cd->rates, cd->noise, nullptr);
+    BTG_LAUNCHED();
+    const cudaError_t e = cudaStreamSynchronize(s0);
+    btg::dfree(d);
+    if (e != cudaSuccess) { set_error("noise finish failed: %s", cudaGetErrorString(e)); return BTG_ECUDA; }
+    return BTG_OK;
 }
 
 int btg_estimate_noise_and_genotypes(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, btg_genotype_result *out, double *trace_out) {
@@ -1110,9 +1132,9 @@ static uint32_t ensure_shadows(btg_unit *u, uint32_t want) {
     if (u->shadow_du.empty()) u->shadow_du.push_back(u->du);
     while (u->shadow_du.size() < want) {
         double *f = nullptr; uint32_t *w = nullptr; uint8_t *b = nullptr, *t = nullptr;
-        const bool ok = cudaMalloc(&f, (u->f64_total + 1) * sizeof(double)) == cudaSuccess && cudaMalloc(&w, (u->u32_total + 1) * sizeof(uint32_t)) == cudaSuccess &&
-                        cudaMalloc(&b, u->u8_total + 8) == cudaSuccess && cudaMalloc(&t, u->tile_total + 32) == cudaSuccess;
-        if (!ok) { cudaFree(f); cudaFree(w); cudaFree(b); cudaFree(t); cudaGetLastError(); break; }  // fewer concurrent chains
+        const bool ok = btg::dmalloc(&f, (u->f64_total + 1) * sizeof(double)) == cudaSuccess && btg::dmalloc(&w, (u->u32_total + 1) * sizeof(uint32_t)) == cudaSuccess &&
+                        btg::dmalloc(&b, u->u8_total + 8) == cudaSuccess && btg::dmalloc(&t, u->tile_total + 32) == cudaSuccess;
+        if (!ok) { btg::dfree(f); btg::dfree(w); btg::dfree(b); btg::dfree(t); cudaGetLastError(); break; }  // fewer concurrent chains
         for (void *p : {(void *)f, (void *)w, (void *)b, (void *)t}) u->allocs.push_back(p);
         DevUnit d = u->du;
         d.f64_pool = f; d.u32_pool = w; d.u8_pool = b; d.big_tile_pool = t;
@@ -1128,7 +1150,8 @@ static uint32_t ensure_shadows(btg_unit *u, uint32_t want) {
 // Measured (profiles/r1_noise_chain_phases.txt): K = 4 or 8 chains side by side take as long as one after the other — an iteration
 // costs (clusters per thread) x (slowest lane's step), so a chain on 1/K of the SMs is K times slower — hence the default K = 1;
 // the per-chain contract is what makes the results independent of K.
-static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, double *trace_out) {
+static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *sh, double *trace_out,
+                                     uint32_t chain_first, uint32_t chain_stride, double *chain_sums_out) {
     BTG_REQUIRE_INIT();
     if (!u || !cd || !opts) { set_error("null argument"); return BTG_EINVAL; }
     btg_comm *comm = sh ? sh->comm : nullptr;
@@ -1150,7 +1173,7 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
     K = ensure_shadows(u, std::min(K, std::max(1u, n_chains)));
     int rc = BTG_OK;
     std::vector<void *> tmp;
-    auto dalloc = [&](size_t bytes) { void *p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 8) != cudaSuccess) { rc = BTG_ENOMEM; return (void *)nullptr; } tmp.push_back(p); cudaMemsetAsync(p, 0, bytes ? bytes : 8, s0); return p; };
+    auto dalloc = [&](size_t bytes) { void *p = nullptr; if (btg::dmalloc(&p, bytes ? bytes : 8) != cudaSuccess) { rc = BTG_ENOMEM; return (void *)nullptr; } tmp.push_back(p); cudaMemsetAsync(p, 0, bytes ? bytes : 8, s0); return p; };
     // per-chain state, one allocation each: [n_chains][...]
     const size_t nc = std::max(1u, n_chains);
     auto *d_hist = (unsigned long long *)dalloc(nc * 2 * S * 8);
@@ -1240,9 +1263,11 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
         const uint32_t capacity = (uint32_t)std::max(1, per_sm) * (uint32_t)ctx().sm_count;
         const uint32_t max_blocks = std::max(1u, (K > 1 ? capacity - capacity / 16 : capacity) / K);  // this chain's share of the SMs (a few block slots stay free)
         for (auto &st : streams) cudaStreamWaitEvent(st, ev_ready, 0);
+        uint32_t launched = 0;
         for (uint32_t b = 0; b < n_chains && rc == BTG_OK; b++) {
-            select_chain(b);  // while the previous chains run on the device
-            const uint32_t k = b % K;
+            select_chain(b);  // while the previous chains run on the device (every chain's selection: the engine stream is sequential)
+            if (b % chain_stride != chain_first) continue;     // a chain of another rank (btg_estimate_noise_chains)
+            const uint32_t k = launched++ % K;
             cudaStream_t st = streams[k];
             NoiseState ns{};
             ns.hist = (uint64_t *)(d_hist + (size_t)b * 2 * S);
@@ -1288,9 +1313,13 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
         // join the chain streams, then: mean of the post-burn-in rates -> setNoiseRates, final trace row "0 0"
         for (auto &st : streams) { cudaEvent_t ev; if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) { cudaEventRecord(ev, st); cudaStreamWaitEvent(s0, ev, 0); cudaEventDestroy(ev); } }
         if (rc == BTG_OK) {
-            k_noise_finish<<<1, 256, 0, s0>>>(d_means, n_chains, S, (double)opts->gibbs_samples * n_chains, cd->rates, cd->noise,
-                                              d_trace ? d_trace + (trace_rows - 1) * row_len : nullptr);
-            BTG_LAUNCHED();
+            if (chain_sums_out) {   // this rank's chains only: the caller adds the ranks' rows up and ends with btg_count_dist_finish_noise
+                cudaMemcpyAsync(chain_sums_out, d_means, (size_t)n_chains * S * 8, cudaMemcpyDeviceToHost, s0);
+            } else {
+                k_noise_finish<<<1, 256, 0, s0>>>(d_means, n_chains, S, (double)opts->gibbs_samples * n_chains, cd->rates, cd->noise,
+                                                  d_trace ? d_trace + (trace_rows - 1) * row_len : nullptr);
+                BTG_LAUNCHED();
+            }
             if (trace_out) cudaMemcpyAsync(trace_out, d_trace, trace_rows * row_len * 8, cudaMemcpyDeviceToHost, s0);
         }
         cudaError_t e = cudaStreamSynchronize(s0);
@@ -1345,7 +1374,7 @@ static int estimate_noise_concurrent(btg_unit *u, btg_count_dist *cd, const btg_
     cudaStreamSynchronize(s0);
     for (auto &st : streams) if (st) cudaStreamDestroy(st);
     if (ev_ready) cudaEventDestroy(ev_ready);
-    for (void *p : tmp) cudaFree(p);
+    for (void *p : tmp) btg::dfree(p);
     return rc;
 }
 
@@ -1372,7 +1401,7 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
     uint32_t *d_sel = nullptr, *d_tasks = nullptr;
     size_t tasks_cap = 0;
     std::vector<void *> tmp;
-    auto dalloc = [&](size_t bytes) { void *p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 8) != cudaSuccess) return (void *)nullptr; tmp.push_back(p); cudaMemsetAsync(p, 0, bytes ? bytes : 8, s); return p; };
+    auto dalloc = [&](size_t bytes) { void *p = nullptr; if (btg::dmalloc(&p, bytes ? bytes : 8) != cudaSuccess) return (void *)nullptr; tmp.push_back(p); cudaMemsetAsync(p, 0, bytes ? bytes : 8, s); return p; };
     hist = (unsigned long long *)dalloc((size_t)S * 2 * 8);
     ns.hist = (uint64_t *)hist;
     ns.rates = cd->rates;
@@ -1478,9 +1507,9 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
             tasks.clear();
             for (uint32_t i = 0; i < n_big; i++) lockstep_fill_tasks(u, sel[i], i, use_wide, tasks);
             if (tasks.size() > tasks_cap) {
-                if (d_tasks) cudaFree(d_tasks);
+                if (d_tasks) btg::dfree(d_tasks);
                 tasks_cap = tasks.size() * 2;
-                if (cudaMalloc(&d_tasks, tasks_cap * 4) != cudaSuccess) { d_tasks = nullptr; tasks_cap = 0; rc = BTG_ENOMEM; set_error("fill task allocation failed"); break; }
+                if (btg::dmalloc(&d_tasks, tasks_cap * 4) != cudaSuccess) { d_tasks = nullptr; tasks_cap = 0; rc = BTG_ENOMEM; set_error("fill task allocation failed"); break; }
             }
             if (!tasks.empty() && cudaMemcpyAsync(d_tasks, tasks.data(), tasks.size() * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BTG_ECUDA; break; }
             if (cudaMemcpyAsync(d_sel, sel.data(), sel.size() * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = BTG_ECUDA; break; }
@@ -1581,8 +1610,8 @@ static int noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *o
         }
     }
     cudaStreamSynchronize(s);
-    for (void *p : tmp) cudaFree(p);
-    if (d_tasks) cudaFree(d_tasks);
+    for (void *p : tmp) btg::dfree(p);
+    if (d_tasks) btg::dfree(d_tasks);
     return rc;
 }
 

@@ -1446,7 +1446,7 @@ __device__ __forceinline__ void grid_barrier(const GridBarrier &b) {
 
 template <class T> T *upload(const T *h, size_t n, bool &ok) {
     T *d = nullptr;
-    if (cudaMalloc(&d, (n ? n : 1) * sizeof(T)) != cudaSuccess) { ok = false; return nullptr; }
+    if (btg::dmalloc(&d, (n ? n : 1) * sizeof(T)) != cudaSuccess) { ok = false; return nullptr; }
     if (n && cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
     return d;
 }

@@ -548,7 +548,7 @@ __global__ void k_compact_best(DevGraphs g, const uint64_t *out_off, uint8_t *ou
 
 template <class T> T *upload(const T *h, size_t n, bool &ok) {
     T *d = nullptr;
-    if (cudaMalloc(&d, (n ? n : 1) * sizeof(T)) != cudaSuccess) { ok = false; return nullptr; }
+    if (btg::dmalloc(&d, (n ? n : 1) * sizeof(T)) != cudaSuccess) { ok = false; return nullptr; }
     if (n && cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
     return d;
 }
@@ -650,11 +650,11 @@ btg_graphs *btg_graphs_upload(const btg_graphs_desc *d, uint32_t max_samples, ui
         uint8_t *scratch = nullptr, *best = nullptr;
         uint32_t *best_n = nullptr, *status = nullptr, *mt_pool = nullptr;
         unsigned long long *stats = nullptr;
-        ok = ok && cudaMalloc(&scratch, scr_off[C] + 16) == cudaSuccess;
-        ok = ok && cudaMalloc(&best, best_off[C] + 16) == cudaSuccess;
-        ok = ok && cudaMalloc(&best_n, (C + 1) * 4) == cudaSuccess && cudaMalloc(&status, 2 * 4) == cudaSuccess;
-        ok = ok && cudaMalloc(&mt_pool, (size_t)gr->grid * kPathWarps * 624 * 4) == cudaSuccess;
-        ok = ok && cudaMalloc(&stats, 3 * 8) == cudaSuccess;
+        ok = ok && btg::dmalloc(&scratch, scr_off[C] + 16) == cudaSuccess;
+        ok = ok && btg::dmalloc(&best, best_off[C] + 16) == cudaSuccess;
+        ok = ok && btg::dmalloc(&best_n, (C + 1) * 4) == cudaSuccess && btg::dmalloc(&status, 2 * 4) == cudaSuccess;
+        ok = ok && btg::dmalloc(&mt_pool, (size_t)gr->grid * kPathWarps * 624 * 4) == cudaSuccess;
+        ok = ok && btg::dmalloc(&stats, 3 * 8) == cudaSuccess;
         keep(scratch); keep(best); keep(best_n); keep(status); keep(mt_pool); keep(stats);
         if (ok) cudaMemsetAsync(stats, 0, 3 * 8, ctx().stream);
         g.stats = stats;
@@ -696,7 +696,7 @@ int btg_graphs_reset(btg_graphs *gr) {
 void btg_graphs_free(btg_graphs *gr) {
     if (!gr) return;
     cudaStreamSynchronize(ctx().stream);
-    for (void *p : gr->allocs) cudaFree(p);
+    for (void *p : gr->allocs) btg::dfree(p);
     delete gr;
 }
 
@@ -737,7 +737,7 @@ int btg_get_best_paths(const btg_graphs *gr, uint32_t *n_paths_out, uint64_t *pa
     uint64_t *d_off = nullptr;
     uint8_t *d_out = nullptr;
     int rc = BTG_OK;
-    if (cudaMalloc(&d_off, (C + 1) * 8) != cudaSuccess || cudaMalloc(&d_out, path_off_out[C]) != cudaSuccess) { set_error("best-path compaction: allocation failed"); rc = BTG_ENOMEM; }
+    if (btg::dmalloc(&d_off, (C + 1) * 8) != cudaSuccess || btg::dmalloc(&d_out, path_off_out[C]) != cudaSuccess) { set_error("best-path compaction: allocation failed"); rc = BTG_ENOMEM; }
     if (rc == BTG_OK) {
         cudaMemcpyAsync(d_off, path_off_out, (C + 1) * 8, cudaMemcpyHostToDevice, s);
         k_compact_best<<<C, 64, 0, s>>>(gr->g, d_off, d_out);
@@ -745,7 +745,7 @@ int btg_get_best_paths(const btg_graphs *gr, uint32_t *n_paths_out, uint64_t *pa
         cudaMemcpyAsync(membership_out, d_out, path_off_out[C], cudaMemcpyDeviceToHost, s);
         if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("best-path compaction failed: %s", cudaGetErrorString(cudaGetLastError())); rc = BTG_ECUDA; }
     }
-    cudaFree(d_off); cudaFree(d_out);
+    btg::dfree(d_off); btg::dfree(d_out);
     return rc;
 }
 

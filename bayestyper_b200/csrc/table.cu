@@ -417,17 +417,26 @@ __global__ void __launch_bounds__(kStreamWarps * 32, MIN_CTAS) k_table_add_sampl
         int64_t qhi[LANES], qlo[LANES];
         uint32_t cnt[LANES];
         uint32_t bmin = 0xFFFFFFFFu, bmax = 0;
+        {
+            // all loads of the tile first, branch-free (the last tile re-reads record n - 1 with count 0): one DRAM round trip per
+            // tile instead of one per record row (with `if (i < n)` around each load the compiler kept load -> use -> load order)
+            longlong2 k[LANES];
+            const bool full = r0 + 32 * LANES <= n;
 #pragma unroll
-        for (int j = 0; j < LANES; j++) {
-            const size_t i = r0 + (size_t)j * 32 + lane;
-            if (i < n) {
-                const longlong2 k = __ldg(kmers + i);
-                cnt[j] = __ldg(counts + i);
-                const TableKey q = key_of_boundary(k.x, k.y);
+            for (int j = 0; j < LANES; j++) {
+                const size_t i = r0 + (size_t)j * 32 + lane;
+                const size_t ii = full || i < n ? i : n - 1;
+                k[j] = __ldg(kmers + ii);
+                cnt[j] = __ldg(counts + ii);
+                if (!(full || i < n)) cnt[j] = 0;
+            }
+#pragma unroll
+            for (int j = 0; j < LANES; j++) {
+                const TableKey q = key_of_boundary(k[j].x, k[j].y);
                 qhi[j] = q.hi; qlo[j] = q.lo;
                 const uint32_t b = (uint32_t)(q.hi >> ix.shift);
-                bmin = min(bmin, b); bmax = max(bmax, b);
-            } else { cnt[j] = 0; qhi[j] = -1; qlo[j] = 0; }
+                bmin = min(bmin, b); bmax = max(bmax, b);       // record n - 1 again in the last tile: inside the tile's range anyway
+            }
         }
         bool tiled = false;
         int64_t t0 = 0, nk = 0;
@@ -445,11 +454,19 @@ __global__ void __launch_bounds__(kStreamWarps * 32, MIN_CTAS) k_table_add_sampl
             const int64_t base = (int64_t)bmin << ix.shift;
             const int log_top = 32 - __clz((uint32_t)nk);   // 2^log_top > nk: the search covers 2^log_top - 1 >= nk slots
             const uint32_t top = 1u << log_top;
-            for (uint32_t i = lane; i < top; i += 32) {     // slots past the last key hold +inf: no bound checks in the search
-                const bool in = (int64_t)i < nk;
-                sd[i] = in ? (uint32_t)(__ldg(kw1 + t0 + i) - base) : 0xFFFFFFFFu;
-                slo[i] = in ? __ldg(kw0 + t0 + i) : INT64_MAX;
+            for (uint32_t i = lane; i < top; i += 64) {     // slots past the last key hold +inf: no bound checks in the search
+                const uint32_t i2 = i + 32;                 // two rows per round, their four loads in flight together
+                const bool in = (int64_t)i < nk, in2 = (int64_t)i2 < nk;
+                const int64_t h1 = in ? __ldg(kw1 + t0 + i) : 0, l1 = in ? __ldg(kw0 + t0 + i) : INT64_MAX;
+                const int64_t h2 = in2 ? __ldg(kw1 + t0 + i2) : 0, l2 = in2 ? __ldg(kw0 + t0 + i2) : INT64_MAX;
+                sd[i] = in ? (uint32_t)(h1 - base) : 0xFFFFFFFFu;
+                slo[i] = l1;
                 sacc[i] = 0;
+                if (i2 < top) {
+                    sd[i2] = in2 ? (uint32_t)(h2 - base) : 0xFFFFFFFFu;
+                    slo[i2] = l2;
+                    sacc[i2] = 0;
+                }
             }
             uint32_t qd[LANES];
 #pragma unroll
@@ -620,10 +637,7 @@ int btg_table_add_sample_kmers_dev(const int64_t *key_w0, const int64_t *key_w1,
         key_w0, key_w1, n_keys, (const longlong2 *)kmers, counts, n, n_samples, sample_idx, table_counts, has_record, g_index)
     switch (variant) {
         case 0: BTG_STREAM_LAUNCH(k_table_add_sample, kTileLanes, 5); break;
-        case 2: BTG_STREAM_LAUNCH((k_table_add_sample_v2<4, 6>), 4, 6); break;
-        case 3: BTG_STREAM_LAUNCH((k_table_add_sample_v2<4, 7>), 4, 7); break;
-        case 4: BTG_STREAM_LAUNCH((k_table_add_sample_v2<8, 4>), 8, 4); break;
-        case 5: BTG_STREAM_LAUNCH((k_table_add_sample_v2<2, 7>), 2, 7); break;
+        case 2: BTG_STREAM_LAUNCH((k_table_add_sample_v2<4, 6>), 4, 6); break;     // 40 registers, 6 CTAs per SM: measured equal to the default
         default: BTG_STREAM_LAUNCH((k_table_add_sample_v2<4, 5>), 4, 5); break;
     }
 #undef BTG_STREAM_LAUNCH

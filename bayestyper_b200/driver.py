@@ -42,6 +42,9 @@ class Options:
     max_parameter_kmers: int = 1_000_000
     chromosome_ploidy_file: str = None   # --chromosome-ploidy-file (ChromosomePloidy.cpp:96-180); default: human X / Y rules by name
     noise_genotyping: bool = False       # --noise-genotyping: InferenceEngine::estimateNoiseAndGenotypes instead of estimateNoise + estimateGenotypes
+    noise_split: str = "chains"          # a sharded unit's estimateNoise: "chains" = every rank runs its share of the (independent) chains on the whole unit,
+                                         # no exchange while they run; "groups" = every rank runs all chains on its own groups and the ranks add up their
+                                         # noise counts inside the chain kernel after every iteration (NVLink mailboxes; what the joint mode always does)
     kmer_stages: str = "abi"             # "abi": KmerCounter's stages through the btg_counter handle of the C ABI (csrc/counter.cu, what a C++ host calls);
                                          # "torch": the torch-glue mirror (kmer_pipeline.py) — also what a sharded unit uses (it subsets the unit on the device)
 
@@ -413,6 +416,20 @@ def genotype(inp: Inputs, opt: Options | None = None, nb_params=None, noise_rate
     cd = engine.CountDistribution(nb_p, nb_size, opt.noise_rate_prior)
     info["n_clusters_total"] = unit.Cn
     sdesc = keep = None
+    min_frac = None if opt.disable_observed_kmers else U.min_fraction_observed(nb_p, nb_size)
+    if sharded and not opt.noise_genotyping and noise_rates is None and opt.noise_split == "chains":
+        # estimateNoise by chains: this rank runs the chains rank, rank + world, ... on the WHOLE unit; the ranks' per-chain sums are added up on the host
+        whole = engine.InferenceEngine(unit)
+        wopts = U.default_opts(seed=opt.random_seed, burn=opt.gibbs_burn_in, samples=opt.gibbs_samples, chains=opt.n_chains, rate=opt.kmer_subsampling_rate,
+                               max_hv=opt.max_haplotype_variant_kmers, min_gpp=opt.min_genotype_posterior, min_kmers=opt.min_number_of_kmers, min_frac=min_frac)
+        sums, _ = whole.estimate_noise_chains(cd, wopts, shard.rank, shard.world)
+        whole.close()
+        total = np.zeros_like(sums)
+        for part in shard.allgather(sums):           # rank order; every row is non-zero on exactly one rank, so the order does not matter
+            total += part
+        cd.finish_noise(total, opt.gibbs_samples)
+        noise_rates = cd.noise_rates()
+        info["noise_split"] = "chains"
     if sharded:   # the Gibbs stages on this rank's groups; the lock-step modes see the whole unit through the shard descriptor
         from . import shard as shard_mod
         sdesc, keep = shard_mod.shard_desc(unit, shard.comm)

@@ -26,6 +26,12 @@ class CountDistribution:
         assert len(r) == self.S
         capi.check(self.lib.btg_count_dist_set_noise_rates(self.h, capi.ptr(r)), self.lib)
 
+    def finish_noise(self, chain_sums, gibbs_samples: int):
+        """The end of estimateNoise from the per-chain rate sums of all ranks (btg_estimate_noise_chains): mean -> setNoiseRates."""
+        cs = np.ascontiguousarray(chain_sums, np.float64)
+        assert cs.ndim == 2 and cs.shape[1] == self.S
+        capi.check(self.lib.btg_count_dist_finish_noise(self.h, capi.ptr(cs), cs.shape[0], gibbs_samples), self.lib)
+
     def noise_rates(self):
         out = np.zeros(self.S)
         capi.check(self.lib.btg_count_dist_get_noise_rates(self.h, capi.ptr(out)), self.lib)
@@ -87,6 +93,16 @@ class InferenceEngine:
         else:
             capi.check(self.lib.btg_estimate_noise_sharded(self.h, cd.h, C.addressof(opts), C.addressof(shard), tp), self.lib)
         return trace
+
+    def estimate_noise_chains(self, cd: CountDistribution, opts: GibbsOpts, chain_first: int, chain_stride: int, want_trace: bool = False):
+        """The chains c = chain_first (mod chain_stride) of estimateNoise on this (whole) unit: returns ([n_chains][S] post-burn-in rate sums,
+        rows of the other chains 0; trace or None).  cd's rates are set by CountDistribution.finish_noise once the ranks' sums are added up."""
+        sums = np.zeros((opts.n_chains, self.unit.S))
+        rows = opts.n_chains * (opts.gibbs_burn_in + opts.gibbs_samples + 1) + 1
+        trace = np.zeros((rows, 2 + self.unit.S)) if want_trace else None
+        capi.check(self.lib.btg_estimate_noise_chains(self.h, cd.h, C.addressof(opts), chain_first, chain_stride, capi.ptr(sums),
+                                                      capi.ptr(trace) if want_trace else None), self.lib)
+        return sums, trace
 
     def estimate_noise_and_genotypes(self, cd: CountDistribution, opts: GibbsOpts, want_trace: bool = True, shard=None):
         """InferenceEngine::estimateNoiseAndGenotypes (--noise-genotyping)."""

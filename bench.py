@@ -241,7 +241,7 @@ def run_ours(args):
     capi.check(lib.btg_init(local_rank), lib)
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.ExternalStream(lib.btg_get_stream(), device=dev)
-    opt = driver.Options(random_seed=20190401, noise_genotyping=args.config == "D")
+    opt = driver.Options(random_seed=20190401, noise_genotyping=args.config == "D", noise_split=args.noise_split)
     sharded = world > 1 and args.mode in ("auto", "sharded")
     shard_ctx = None
     if sharded:   # one unit over all ranks: every rank builds the SAME batch; mailbox handles + best paths travel over torch.distributed
@@ -349,9 +349,12 @@ def run_ours(args):
                    "gibbs": "20 chains x (100 burn-in + 250 samples), k-mer subsampling 0.1",
                    "l2": "inputs exceed L2 (sample k-mer streams %.2f GB, sample Bloom filters %.0f MB)" % (n_sample * 17 / 1e9, bloom_total / 8e6),
                    "parallelism": ("1 GPU" if world == 1 else
-                                   "ONE unit sharded over %d ranks (every %d-th group of the size-sorted unit): path search + Gibbs per rank, best paths all-gathered, "
-                                   "noise counts of the lock-step chains added up inside the chain kernel over NVLink peer mailboxes (%d exchanges per step)"
-                                   % (world, world, 20 * 350) if sharded else "%d replicas, one unit of the named size each, no data-path exchange" % world),
+                                   ("ONE unit sharded over %d ranks (every %d-th group of the size-sorted unit): path search + estimateGenotypes per rank, best paths all-gathered; "
+                                    % (world, world)
+                                    + ("estimateNoise: rank r runs the chains r, r + %d, ... of the whole unit (chains are independent streams), per-chain sums all-gathered" % world
+                                       if args.config == "B" and args.noise_split == "chains" else
+                                       "noise counts of the lock-step chains added up inside the chain kernel over NVLink peer mailboxes (%d exchanges per step)" % (20 * 350)))
+                                   if sharded else "%d replicas, one unit of the named size each, no data-path exchange" % world),
                    "scale": args.scale},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
         "gpu_launches": launches,
@@ -421,6 +424,17 @@ def stage_breakdown(lib, inp, opt, stream, dev, shard_ctx=None):
         unit = timed("classify+getHaplotypeCandidates", lambda: pipe.build_unit(multigroup_bloom=None, device_resident=True))
         nb = timed("NB fit (parameter k-mers)", lambda: driver.estimate_nb_parameters(pipe, inp.region_buf_dev, inp.spectra_dev, inp.genders, opt))
         from bayestyper_b200 import shard as shard_mod
+        chain_rates = None
+        if not opt.noise_genotyping and opt.noise_split == "chains":      # estimateNoise by chains on the whole unit (driver.genotype does the same)
+            whole = timed("whole-unit upload (noise chains)", lambda: engine.InferenceEngine(unit))
+            cd_w = engine.CountDistribution(nb[0], nb[1])
+            wopts = U.default_opts(seed=opt.random_seed, min_frac=U.min_fraction_observed(nb[0], nb[1]))
+            sums = timed("estimateNoise (chains rank::world of the whole unit)", lambda: whole.estimate_noise_chains(cd_w, wopts, shard_ctx.rank, shard_ctx.world)[0])
+            whole.close()
+            total = timed("noise chain sums all-gather", lambda: sum(shard_ctx.allgather(sums)))
+            cd_w.finish_noise(total, opt.gibbs_samples)
+            chain_rates = cd_w.noise_rates()
+            cd_w.close()
         sdesc, keep = shard_mod.shard_desc(unit, shard_ctx.comm)
         unit = timed("unit subset (own groups, on the device)", lambda: unit.subset_groups(mine))
         eng = timed("unit upload", lambda: engine.InferenceEngine(unit))
@@ -444,7 +458,10 @@ def stage_breakdown(lib, inp, opt, stream, dev, shard_ctx=None):
     if opt.noise_genotyping:
         timed("estimateNoiseAndGenotypes", lambda: eng.estimate_noise_and_genotypes(cd, gopts, want_trace=False, shard=sdesc))
     else:
-        timed("estimateNoise", lambda: eng.estimate_noise(cd, gopts, want_trace=False, shard=sdesc))
+        if sharded and chain_rates is not None:
+            cd.set_noise_rates(chain_rates)
+        else:
+            timed("estimateNoise", lambda: eng.estimate_noise(cd, gopts, want_trace=False, shard=sdesc))
         timed("estimateGenotypes", lambda: eng.estimate_genotypes(cd, gopts))
     eng.close(); cd.close()
     # roofline of the k-mer-match kernel that costs the time: k_find_sample_paths, one sample's pass over the (rank's) graphs, CUDA events on the library stream
@@ -621,6 +638,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the chr22-sized batch (tests use small values)")
     ap.add_argument("--config", default="B", choices=["B", "D"], help="B = configs[1] (default, the metric's config); D = configs[3] shape (30 samples, joint mode)")
+    ap.add_argument("--noise-split", default="chains", choices=["chains", "groups"],
+                    help="sharded estimateNoise: every rank runs its share of the independent chains on the whole unit (default), or all chains on its own groups "
+                         "with the per-iteration noise counts added up inside the chain kernel over NVLink mailboxes (what the joint mode of --config D always does)")
     ap.add_argument("--mode", default="auto", choices=["auto", "sharded", "replicas"], help="N > 1: one unit sharded over the ranks (default) or one unit per rank")
     ap.add_argument("--cpu-variants", type=int, default=0, help="size of the bounded CPU sample (0: 12000 for B in the reference arm, 3000 for the cpu_baseline leg; 120 for D)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -443,6 +443,17 @@ typedef struct btg_shard_desc {
 int btg_estimate_noise_sharded(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *shard, double *trace_out);
 int btg_estimate_noise_and_genotypes_sharded(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, const btg_shard_desc *shard,
                                              btg_genotype_result *out, double *trace_out);
+/* estimateNoise of ONE unit spread over several GPUs by CHAINS.  Under this library's stream contract the chains of estimateNoise
+ * are independent (own noise stream per chain, reset frequencies, fresh k-mer subsample) and the result is the
+ * mean of their post-burn-in rates (InferenceEngine.cpp:259-264), so rank r of N can run the chains c = r (mod N) of the WHOLE unit
+ * with no exchange while they run — the per-iteration merge of the reference (InferenceEngine.cpp:226-229) stays inside one GPU.
+ * chain_sums_out [n_chains][S] receives the post-burn-in rate sums of the chains this call ran (other rows 0); cd is not
+ * updated.  The host adds the ranks' arrays up (every row is non-zero on exactly one rank) and calls
+ * btg_count_dist_finish_noise on every rank: same summation order as btg_estimate_noise, same rates bit for bit.
+ * trace_out (optional): as btg_estimate_noise, rows of the other ranks' chains and the final row 0.                              */
+int btg_estimate_noise_chains(btg_unit *u, btg_count_dist *cd, const btg_gibbs_opts *opts, uint32_t chain_first, uint32_t chain_stride,
+                              double *chain_sums_out, double *trace_out);
+int btg_count_dist_finish_noise(btg_count_dist *cd, const double *chain_sums /* [n_chains][S] */, uint32_t n_chains, uint32_t gibbs_samples);
 
 /* raw diplotype tallies of one cluster (tests): [(H+1)(H+2)/2][S] uint32, pair (h1<=h2), index h2*(h2+1)/2+h1, H = "missing" */
 int btg_unit_cluster_tally(const btg_unit *u, uint32_t cluster, uint32_t *tally_out, uint64_t n);

@@ -123,6 +123,33 @@ def test_estimate_noise_matches_oracle(btg):
     eng.close()
 
 
+@pytest.mark.parametrize("name,parts", [("gibbs_snv_1s", 2), ("gibbs_chrx_2s", 3), ("gibbs_mixed_3s", 8)])
+def test_estimate_noise_by_chains_equals_the_whole_run(btg, name, parts):
+    """btg_estimate_noise_chains: the chains of estimateNoise dealt to `parts` ranks (here one after the other on one GPU), their per-chain
+    sums added up and finished by btg_count_dist_finish_noise = btg_estimate_noise, bit for bit (rates and every trace row)."""
+    fx = GibbsFixture(name)
+    opts = fx.opts(chains=5, burn=10, samples=25)
+    _, whole_cd = _both(fx, opts)
+    eng = engine.InferenceEngine(fx.unit)
+    want = eng.estimate_noise(whole_cd, opts)
+    _, cd = _both(fx, opts)
+    total = np.zeros((opts.n_chains, fx.S))
+    trace = np.zeros_like(want)
+    for r in range(parts):
+        sums, tr = eng.estimate_noise_chains(cd, opts, r, parts, want_trace=True)
+        mine = np.arange(opts.n_chains) % parts == r
+        assert (sums[~mine] == 0).all() and (sums[mine] > 0).all()
+        total += sums
+        trace += tr
+    cd.finish_noise(total, opts.gibbs_samples)
+    assert (cd.noise_rates() == whole_cd.noise_rates()).all()
+    assert (trace[:-1] == want[:-1]).all()                      # the last row ("0 0", final rates) is written by the finish of a whole run only
+    assert (want[-1, 2:] == cd.noise_rates()).all()
+    g1, n1 = cd.tables(); g2, n2 = whole_cd.tables()
+    assert (n1 == n2).all()
+    eng.close()
+
+
 def test_multi_sample_noise(btg):
     fx = GibbsFixture("gibbs_chrx_2s")
     opts = fx.opts(chains=2, burn=10, samples=20)

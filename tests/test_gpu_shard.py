@@ -83,3 +83,82 @@ def test_two_ranks_equal_one(btg, tmp_path, name, joint):
     if joint:
         for k in shard.RESULT_KEYS:
             assert (np.concatenate([got[f"{k}_0"], got[f"{k}_1"]]) == want[k]).all(), k
+
+
+# ---- the whole step of a sharded unit (driver.genotype with a Shard): what bench.py --gpus N runs ----------------------------------
+
+def _small_batch(lib, dev):
+    import bench
+    return bench.build_batch(lib, 0, 0.01, dev)          # every rank builds the SAME 3,000-variant batch
+
+
+def _driver_worker(rank, world, port, out_dir, noise_split):
+    sys.path.insert(0, str(ROOT))
+    import torch
+    import torch.distributed as dist
+    from bayestyper_b200 import capi, driver, shard
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ.setdefault("BTG_PEER_TIMEOUT_MS", "60000")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = rank % torch.cuda.device_count()
+    torch.cuda.set_device(dev)
+    lib = capi.load()
+    capi.check(lib.btg_init(dev), lib)
+    opt = driver.Options(random_seed=77, n_chains=3, gibbs_burn_in=8, gibbs_samples=12, noise_split=noise_split)
+    inp = _small_batch(lib, torch.device("cuda", dev))
+    inp.make_resident(lib, opt)
+
+    def allgather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+    ctx = driver.Shard(world, rank, allgather, shard.Comm.torch(world, rank))
+    _, _, res, info = driver.genotype(inp, opt, resident=True, shard=ctx)
+    G = len(inp.graphs["group_cluster_off"]) - 1
+    parts = allgather({"res": {k: res[k] for k in shard.RESULT_KEYS}, "groups": ctx.my_groups(G), "rates": info["noise_rates"], "n": info["n_clusters"]})
+    if rank == 0:
+        import pickle
+        with open(Path(out_dir) / "parts.pkl", "wb") as f:
+            pickle.dump(parts, f)
+    dist.barrier()
+    inp.free(lib)
+    ctx.comm.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("noise_split", ["chains", "groups"])
+def test_sharded_step_equals_the_single_rank_step(btg, tmp_path, noise_split):
+    """Two ranks share ONE unit (strided groups): own path search + best-path all-gather, estimateNoise split by chains (no exchange while the
+    chains run) or by groups (in-kernel mailbox exchange), estimateGenotypes on the own groups.  Noise rates and every result row must equal
+    the single-rank step's, bit for bit."""
+    import pickle
+    import torch
+    from bayestyper_b200 import capi, driver, shard
+    lib = capi.load()
+    opt = driver.Options(random_seed=77, n_chains=3, gibbs_burn_in=8, gibbs_samples=12)
+    inp = _small_batch(lib, torch.device("cuda", 0))
+    inp.make_resident(lib, opt)
+    graphs, _, want, winfo = driver.genotype(inp, opt, resident=True)
+    mp.spawn(_driver_worker, args=(2, 29541 + (noise_split == "groups"), str(tmp_path), noise_split), nprocs=2, join=True)
+    with open(tmp_path / "parts.pkl", "rb") as f:
+        parts = pickle.load(f)
+    gco = np.asarray(graphs["group_cluster_off"], np.int64)
+    cvo = np.asarray(graphs["cl_var_off"], np.int64)
+    assert sum(p["n"] for p in parts) == winfo["n_clusters"]
+    nv, S = int(cvo[-1]), 1
+    level_off = {"v2": np.arange(nv + 1) * 2 * S, "v1": np.arange(nv + 1) * S, "v": np.arange(nv + 1),
+                 "geno": np.asarray(want["geno_off"], np.int64), "allele": np.asarray(want["allele_off"], np.int64), "valt": np.asarray(want["valt_off"], np.int64)}
+    level = {"gt": "v2", "gq": "v1", "ploidy": "v1", "gpp": "geno", "app": "allele", "nak": "allele", "fak": "allele", "mac": "allele", "saf": "allele",
+             "an": "v", "hc": "v", "ac": "valt", "af": "valt", "acp": "valt", "anc": "valt"}
+    for p in parts:
+        assert (p["rates"] == winfo["noise_rates"]).all()
+        clusters = np.concatenate([np.arange(gco[g], gco[g + 1]) for g in p["groups"]])
+        variants = np.concatenate([np.arange(cvo[c], cvo[c + 1]) for c in clusters])
+        for k in shard.RESULT_KEYS:
+            _, rows = driver._take_csr(level_off[level[k]], variants)
+            got = np.asarray(p["res"][k])
+            assert len(got) == len(rows), k
+            assert (got == np.asarray(want[k])[rows]).all(), k
+    inp.free(lib)
