@@ -587,7 +587,9 @@ int btg_path_alleles_dev(const btg_pathwalk_desc *d, const uint64_t *cl_var_off,
     return BTG_OK;
 }
 
-static TableIndex g_index{nullptr, 0};
+// Per host thread: two threads (or two KmerPipelines driven from different threads) never see each other's index.  A probe without an
+// index is correct (binary search over all keys), only slower; btg_counter installs its own index around each of its passes.
+static thread_local TableIndex g_index{nullptr, 0};
 
 // Installs (or clears, lut = NULL) the prefix index used by the table probes that follow: lut[b] = index of the first
 // key whose word-1 top `lut_bits` bits (of 46) are >= b, for b in [0, 2^lut_bits]; built by the caller from the keys.

@@ -203,6 +203,7 @@ def build_batch_d(lib, rank: int, scale: float, dev):
         spectra.append(device_spectrum(lib, haps, 15.0, 25.0, 14 + 1000 * rank + 7 * s_, int(50_000 * scale), dev))
     inp = driver.Inputs("chr1", ref, var, ["F" if i % 2 == 0 else "M" for i in range(S)], spectra=None)
     inp.spectra_dev = spectra
+    inp.truth = g
     inp.prepare()
     return inp
 
@@ -220,8 +221,37 @@ def build_batch(lib, rank: int, scale: float, dev):
     keys, counts = device_spectrum(lib, haps, 15.0, 25.0, 14 + 1000 * rank, int(500_000 * scale), dev)
     inp = driver.Inputs("chr22", ref, var, ["F"], spectra=None)
     inp.spectra_dev = [(keys, counts)]
+    inp.truth = g
     inp.prepare()
     return inp
+
+
+def truth_agreement(inp, res, S):
+    """Correctness of the FULL-SIZE step, printed in the bench line (`parity_at_size`): the genotypes called by the last timed step against
+    the genotypes the sample spectra were synthesised from (alt-allele count per variant and sample; tests/test_gpu_e2e.py asserts the same
+    quantity on the small fixtures, where the reference's own calls are available too).  Not a substitute for the oracle parity tests: a
+    property the domain offers at a size the CPU reference needs minutes for."""
+    g = getattr(inp, "truth", None)
+    if g is None or res is None:
+        return None
+    try:
+        truth = np.asarray(g).transpose(1, 0, 2).sum(axis=2)                 # (variants, S) alt-allele count
+        pos = np.array([v.pos + 1 for v in inp.variants], np.int64)
+        order = np.argsort(pos, kind="stable")
+        vp = np.asarray(inp.graphs["var_pos"], np.int64)
+        at = np.searchsorted(pos[order], vp)
+        if len(vp) != len(res["gt"]) // (2 * S) or (pos[order][np.minimum(at, len(pos) - 1)] != vp).any():
+            return {"error": "result rows do not line up with the candidate variants"}
+        t = truth[order[at]]
+        gt = np.asarray(res["gt"]).reshape(-1, S, 2)
+        called = gt[..., 0] != 0xFFFF
+        alt = gt.astype(np.int64).sum(axis=2)
+        return {"what": "called genotype (alt-allele count) == genotype the spectra were drawn from, over called (variant, sample) pairs of the last timed step",
+                "variant_sample_pairs": int(called.size), "called_frac": float(called.mean()),
+                "gt_matches_truth_frac": float((alt[called] == t[called]).mean()) if called.any() else None,
+                "hom_ref_truth_frac": float((t == 0).mean())}
+    except Exception as e:          # the check must never cost the bench line
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def run_ours(args):
@@ -288,6 +318,7 @@ def run_ours(args):
         torch.cuda.synchronize()
     launches = int(lib.btg_launch_count())
     n_clusters = info["n_clusters"]
+    parity_at_size = None if sharded else truth_agreement(inp, res, S)      # a shard's result rows cover its own groups only
     n_total = info["n_clusters_total"] if sharded else world * n_clusters      # clusters genotyped by ALL ranks in one step
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -361,6 +392,7 @@ def run_ours(args):
         "clocks": clocks.summary(),
         "roofline": roof,
         "roofline_paths": None if paths_roof is None else {**paths_roof, "peak": peak, "unit": "GB/s", "frac": paths_roof["achieved"] / peak, "peak_source": peak_src},
+        "parity_at_size": parity_at_size,
         "stage_ms": stage_ms,
         "step_wall_ms": step_wall,
         "setup_s": setup_s,

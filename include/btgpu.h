@@ -212,7 +212,8 @@ int btg_path_alleles_dev(const btg_pathwalk_desc *d, const uint64_t *cl_var_off,
 /* Optional prefix index over the sorted keys (cf. the prefix LUT of a KMC database, external/kmc_api/kmc_file.cpp:236-290):
  * lut[b] = index of the first key whose key_hi top lut_bits bits (of 46; the first lut_bits/2 nucleotides) are >= b,
  * b in [0, 2^lut_bits]; NULL clears.
- * Applies to the three table probes below until changed. */
+ * Applies to the three table probes below, on the CALLING HOST THREAD, until changed (thread-local: a probe of another key table
+ * must clear or replace it first; a probe without an index is correct, only slower).  btg_counter handles install their own. */
 int btg_table_set_index_dev(const int64_t *lut, int lut_bits);
 /* KmerCountsHash::findKmer on a batch: index into the key arrays or -1 */
 int btg_table_lookup_dev(const int64_t *key_lo, const int64_t *key_hi, int64_t n_keys, const uint64_t *kmers, size_t n,
