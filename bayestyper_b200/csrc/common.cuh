@@ -7,6 +7,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: a no-op unless a tool (nsys, ncu --nvtx) injects itself
+
 #include "../../include/btgpu.h"
 
 namespace btg {
@@ -22,6 +24,15 @@ struct Context {
 Context &ctx();
 void set_error(const char *fmt, ...);
 extern std::atomic<uint64_t> g_launches;
+
+// NVTX range over one entry point of the C ABI (the reference has no tracing; a timeline of the stage calls —
+// btg_find_sample_paths, btg_counter_*, btg_estimate_* — is what a profiler needs to attribute kernels to stages)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 inline cudaStream_t pick_stream(void *s) { return s ? (cudaStream_t)s : ctx().stream; }
 
@@ -57,6 +68,7 @@ template <class T> inline cudaError_t dmalloc(T **p, size_t bytes) { return dmal
     } while (0)
 
 #define BTG_REQUIRE_INIT()                                                   \
+    btg::NvtxRange _btg_nvtx_range(__func__);                                \
     do {                                                                     \
         if (!btg::ctx().ready) {                                             \
             btg::set_error("btg_init() has not been called");                \

@@ -288,6 +288,52 @@ def nested_sv(n_sv: int, length: int, n_samples: int, seed: int, sv_len=(150, 50
     return Workload("nested", chrom, ref, var, g, genders)
 
 
+def deep_nested(n_top: int, length: int, n_samples: int, seed: int, n_background: int = 0, chrom: str = "chr1") -> Workload:
+    """Deletions inside deletions inside deletions (up to four levels) with SNVs at the bottom: groups of ten and more clusters whose
+    dependency forest is several levels deep (VariantFileParser.cpp:735-1000, VariantClusterGroup.cpp:88-137), and variants that overlap
+    three or more clusters at once.  The generator of tools/fuzz_graph_builder.py --deep, with genotypes and background variants."""
+    rng = np.random.default_rng(seed)
+    ref = random_reference(length, seed + 100)
+    var = {}
+
+    def put(p, r, alts):
+        if p not in var and 60 < p and p + len(r) < length - 60:
+            var[p] = Variant(p, r, alts)
+
+    def snv(p):
+        put(p, ref[p:p + 1], [bytes([_ACGT[(int(_CODE[ref[p]]) + 1) % 4]])])
+
+    def fill(lo, hi, depth):
+        if hi - lo < 250 or depth > 3:
+            for p in rng.integers(lo + 60, max(lo + 61, hi - 60), size=int(rng.integers(0, 3))).tolist():
+                snv(int(p))
+            return
+        cuts = np.sort(rng.integers(lo + 70, hi - 70, size=2 * int(rng.integers(1, 4))))
+        for a, b in zip(cuts[0::2].tolist(), cuts[1::2].tolist()):
+            if b - a > 120:
+                put(a, ref[a:a + 1 + b - a], [ref[a:a + 1]])
+                fill(a, b, depth + 1)
+            else:
+                snv(a)
+
+    slot = (length - 400) // n_top
+    for t in range(n_top):
+        a = 200 + t * slot + int(rng.integers(0, max(1, slot // 8)))
+        ln = int(rng.integers(1500, max(1501, min(3500, slot - slot // 8 - 300))))
+        put(a, ref[a:a + 1 + ln], [ref[a:a + 1]])
+        fill(a, a + ln, 1)
+    out = [var[p] for p in sorted(var)]
+    if n_background:
+        taken = [(v.pos - K, v.pos + len(v.ref) + K) for v in out if len(v.ref) > 1]
+        for v in make_variants(ref, n_background, seed + 3, 0.05, 0.05, max_indel=20):
+            if v.pos not in var and not any(a <= v.pos <= b for a, b in taken):
+                out.append(v)
+    out.sort(key=lambda v: (v.pos, -len(v.ref)))
+    af = rng.beta(0.8, 0.8, len(out))
+    g = make_genotypes(len(out), n_samples, seed + 2, allele_freq=af)
+    return Workload("deep", chrom, ref, out, g, ["F" if i % 2 == 0 else "M" for i in range(n_samples)])
+
+
 def sample_spectra(w: Workload, seed: int = 4, n_errors: int = 0):
     out = []
     for s in range(w.genotypes.shape[0]):

@@ -271,7 +271,7 @@ def run_ours(args):
     capi.check(lib.btg_init(local_rank), lib)
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.ExternalStream(lib.btg_get_stream(), device=dev)
-    opt = driver.Options(random_seed=20190401, noise_genotyping=args.config == "D", noise_split=args.noise_split)
+    opt = driver.Options(random_seed=20190401, noise_genotyping=args.config == "D", noise_split=args.noise_split, gibbs_samples=args.gibbs_samples)
     sharded = world > 1 and args.mode in ("auto", "sharded")
     shard_ctx = None
     if sharded:   # one unit over all ranks: every rank builds the SAME batch; mailbox handles + best paths travel over torch.distributed
@@ -377,14 +377,14 @@ def run_ours(args):
                    "samples": S, "haplotype_candidates_per_cluster": info.get("haplotype_candidates"), "reference_nt": len(inp.reference), "sample_kmers": n_sample, "path_kmers": info["n_path_kmers"],
                    "step": "findVariantClusterPaths -> path k-mer table -> genome scan -> sample k-mer stream -> classify/haplotype candidates -> NB fit -> "
                            + ("estimateNoiseAndGenotypes" if args.config == "D" else "estimateNoise -> estimateGenotypes"),
-                   "gibbs": "20 chains x (100 burn-in + 250 samples), k-mer subsampling 0.1",
+                   "gibbs": "20 chains x (100 burn-in + %d samples), k-mer subsampling 0.1" % opt.gibbs_samples,
                    "l2": "inputs exceed L2 (sample k-mer streams %.2f GB, sample Bloom filters %.0f MB)" % (n_sample * 17 / 1e9, bloom_total / 8e6),
                    "parallelism": ("1 GPU" if world == 1 else
                                    ("ONE unit sharded over %d ranks (every %d-th group of the size-sorted unit): path search + estimateGenotypes per rank, best paths all-gathered; "
                                     % (world, world)
                                     + ("estimateNoise: rank r runs the chains r, r + %d, ... of the whole unit (chains are independent streams), per-chain sums all-gathered" % world
                                        if args.config == "B" and args.noise_split == "chains" else
-                                       "noise counts of the lock-step chains added up inside the chain kernel over NVLink peer mailboxes (%d exchanges per step)" % (20 * 350)))
+                                       "noise counts of the lock-step chains added up inside the chain kernel over NVLink peer mailboxes (%d exchanges per step)" % (20 * (100 + opt.gibbs_samples))))
                                    if sharded else "%d replicas, one unit of the named size each, no data-path exchange" % world),
                    "scale": args.scale},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
@@ -399,7 +399,7 @@ def run_ours(args):
     }
     if rank == 0:
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference(args.config, args.cpu_variants or (3000 if args.config == "B" else 120), os.cpu_count() or 1)
+            line["cpu_baseline"] = cpu_reference(args.config, args.cpu_variants or (3000 if args.config == "B" else 120), os.cpu_count() or 1, args.gibbs_samples)
         emit(line)
     inp.free(lib)
     if shard_ctx is not None:
@@ -558,7 +558,7 @@ def stage_breakdown(lib, inp, opt, stream, dev, shard_ctx=None):
 FULL_B = {"variants": 300_000, "noise_cap_variants": 100_000}      # configs[1]; InferenceEngine.cpp:50 noise_variants_batch_size
 
 
-def cpu_reference(config: str, n_variants: int, threads: int):
+def cpu_reference(config: str, n_variants: int, threads: int, gibbs_samples: int = 250):
     """Runs the reference's translation units (oracle/_ref/btref: cluster + genotype stage order) on a bounded sample of the same
     workload shape, all host threads.
 
@@ -586,7 +586,7 @@ def cpu_reference(config: str, n_variants: int, threads: int):
     with tempfile.TemporaryDirectory() as td:
         synth.write_workdir(w, td, n_errors=max(1000, int(50_000 * n_variants / 3000)) if config == "B" else 2000)
         t0 = time.time()
-        subprocess.check_call([str(btref), "run", "--workdir", td, "--threads", str(threads), "--seed", "20190401"] + (["--noise-genotyping"] if config == "D" else []),
+        subprocess.check_call([str(btref), "run", "--workdir", td, "--threads", str(threads), "--seed", "20190401", "--gibbs-samples", str(gibbs_samples)] + (["--noise-genotyping"] if config == "D" else []),
                               stdout=subprocess.DEVNULL)
         wall = time.time() - t0
         tj = json.loads((Path(td) / "ref_out" / "timings.json").read_text())
@@ -618,13 +618,19 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_var = args.cpu_variants if args.cpu_variants else (12_000 if args.config == "B" else 120)
+    # every step is one run of the reference on a bounded sample; the sample is sized so that the W > 0 warm-up run plus the K timed runs end
+    # within a few minutes on a 16-thread host (measured: ~3.5 ms of wall per sample variant for B, ~0.25 s for the 30-sample D shape):
+    # K = 1..4 -> 12,000 variants per run, the driver's K = 20 -> 2,857.  The projection to the full config (cpu_reference) is the same
+    # for every sample size; the size is printed in config.sample.
+    runs = args.steps + (1 if args.warmup > 0 else 0)
+    auto = int(min(12_000, max(2_000, 60_000 // max(1, runs)))) if args.config == "B" else int(min(120, max(40, 720 // max(1, runs))))
+    n_var = args.cpu_variants if args.cpu_variants else auto
     vals = []
     last = None
     for i in range(args.warmup + args.steps):
         if i < args.warmup and i > 0:
             continue            # a CPU process has no clocks or caches to warm beyond the first run: one warm-up run stands for all W
-        last = cpu_reference(args.config, n_var, threads)
+        last = cpu_reference(args.config, n_var, threads, args.gibbs_samples)
         if last["value"] is None:
             emit({"impl": "reference", "unavailable": last["sample"]})
             return
@@ -638,7 +644,7 @@ def run_reference(args):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 and args.mode != "replicas" else "weak", "vs_baseline": None,
             "dtype": "f64 (Gibbs log-likelihoods) / u64 (k-mer hashing)", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.config], "clusters": full_clusters, "variants": FULL_B["variants"] if args.config == "B" else last["sample_variants"],
-                       "samples": 30 if args.config == "D" else 1, "gibbs": "20 chains x (100 burn-in + 250 samples), k-mer subsampling 0.1",
+                       "samples": 30 if args.config == "D" else 1, "gibbs": "20 chains x (100 burn-in + %d samples), k-mer subsampling 0.1" % args.gibbs_samples,
                        "step": "the reference's own cluster + genotype stages on the host cores", "sample": last["sample"], "threads": threads},
             "cpu_baseline": cb, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -673,8 +679,10 @@ def main():
     ap.add_argument("--noise-split", default="chains", choices=["chains", "groups"],
                     help="sharded estimateNoise: every rank runs its share of the independent chains on the whole unit (default), or all chains on its own groups "
                          "with the per-iteration noise counts added up inside the chain kernel over NVLink mailboxes (what the joint mode of --config D always does)")
+    ap.add_argument("--gibbs-samples", type=int, default=250, help="--gibbs-samples of the reference (post-burn-in iterations per chain; default 250): the sweep axis of BASELINE.json configs[4] "
+                                                                    "(250 / 500 / 1000 / 2000), e.g. --config D --gibbs-samples 1000")
     ap.add_argument("--mode", default="auto", choices=["auto", "sharded", "replicas"], help="N > 1: one unit sharded over the ranks (default) or one unit per rank")
-    ap.add_argument("--cpu-variants", type=int, default=0, help="size of the bounded CPU sample (0: 12000 for B in the reference arm, 3000 for the cpu_baseline leg; 120 for D)")
+    ap.add_argument("--cpu-variants", type=int, default=0, help="size of the bounded CPU sample (0: the reference arm sizes it from --steps so that the run ends in minutes — 12000 variants per step for B up to 4 steps, 2857 at 20 steps; 3000 for the cpu_baseline leg; at most 120 for D)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timed-only", action="store_true", help="warm-up + timed steps only (for ncu launch lists); prints no bench line")
     args = ap.parse_args()

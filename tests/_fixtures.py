@@ -6,7 +6,7 @@ import numpy as np
 from bayestyper_b200 import btd, unit as U
 
 GOLD = Path(__file__).parent / "golden"
-GIBBS_FIXTURES = ["gibbs_snv_1s", "gibbs_mixed_3s", "gibbs_chrx_2s", "gibbs_nested_2s"]
+GIBBS_FIXTURES = ["gibbs_snv_1s", "gibbs_mixed_3s", "gibbs_chrx_2s", "gibbs_nested_2s", "gibbs_deep_2s"]
 
 
 class GibbsFixture:

@@ -184,7 +184,9 @@ NBFIT_WORKLOADS = {"nbfit_mixed_2s": lambda: synth.small_mixed(250, 30_000, 2, s
 E2E_WORKLOADS = {
     "e2e_snv_1s": lambda: synth.config_a(n_variants=1500, length=150_000),
     "e2e_mixed_3s": lambda: synth.small_mixed(800, 80_000, 3, seed=71),
+    "e2e_configA_1s": lambda: synth.config_a(),          # BASELINE.json configs[0] at FULL size: 1 sample, 10k SNVs on 1 Mb (70 s of the reference here)
 }
+E2E_N_ERRORS = {"e2e_configA_1s": 100_000}              # sequencing-error k-mers added to the spectra (default 20,000)
 
 # end-to-end cases whose fixtures exist but which have not run on a GPU yet (tools/e2e_check.py runs them; a case moves up to
 # E2E_WORKLOADS once it is green there)
@@ -192,11 +194,14 @@ E2E_NEXT_WORKLOADS = {
     "e2e_nested_2s": lambda: synth.nested_sv(25, 100_000, 2, seed=31, n_background=400, sv_len=(150, 600), repeat_frac=0.4),
 }
 
+DEEP_WORKLOAD = lambda: synth.deep_nested(4, 22_000, 2, seed=7, n_background=400)   # noqa: E731
+
 PIPE_WORKLOADS = {
     "pipe_snv_1s": lambda: synth.config_a(n_variants=500, length=50_000),
     "pipe_mixed_3s": lambda: synth.small_mixed(350, 25_000, 3, seed=52),
     "pipe_chrx_2s": lambda: synth.small_mixed(250, 20_000, 2, seed=61, chrom="chrX"),
     "pipe_nested_2s": lambda: synth.nested_sv(12, 50_000, 2, seed=9, n_background=120, sv_len=(150, 600), repeat_frac=0.6),
+    "pipe_deep_2s": DEEP_WORKLOAD,
 }
 
 PATH_WORKLOADS = {
@@ -204,6 +209,7 @@ PATH_WORKLOADS = {
     "paths_mixed_3s": lambda: synth.small_mixed(900, 60_000, 3, seed=21),
     "paths_dense_2s": lambda: synth.small_mixed(1500, 40_000, 2, seed=44, frac_indel=0.3),
     "paths_nested_2s": lambda: synth.nested_sv(20, 80_000, 2, seed=13, n_background=200, sv_len=(150, 600), repeat_frac=0.5),
+    "paths_deep_2s": DEEP_WORKLOAD,
 }
 
 if __name__ == "__main__":
@@ -230,6 +236,14 @@ if __name__ == "__main__":
         make("gibbs_joint_nested_2s", synth.nested_sv(8, 30_000, 2, seed=15, n_background=60, sv_len=(150, 500), repeat_frac=0.6), 10**6, n_errors=4000,
              extra_args=("--noise-genotyping",))
         _sys.exit(0)
+    if len(_sys.argv) > 1 and _sys.argv[1] == "deep":
+        # deletions inside deletions inside deletions: groups of ten and more clusters, dependency forests several levels deep; the Gibbs fixture holds
+        # every group of the reference run
+        w = DEEP_WORKLOAD()
+        make("gibbs_deep_2s", w, 10**6, n_errors=4000)
+        make_pipeline("pipe_deep_2s", w)
+        make_paths("paths_deep_2s", w)
+        _sys.exit(0)
     if len(_sys.argv) > 1 and _sys.argv[1] == "nested-kmer":
         make_pipeline("pipe_nested_2s", PIPE_WORKLOADS["pipe_nested_2s"]())
         make_paths("paths_nested_2s", PATH_WORKLOADS["paths_nested_2s"]())
@@ -240,7 +254,7 @@ if __name__ == "__main__":
         _sys.exit(0)
     if len(_sys.argv) > 1 and _sys.argv[1] == "e2e":
         for nm, fn in E2E_WORKLOADS.items():
-            make_e2e(nm, fn())
+            make_e2e(nm, fn(), n_errors=E2E_N_ERRORS.get(nm, 20000))
         _sys.exit(0)
     for nm, fn in PATH_WORKLOADS.items():
         make_paths(nm, fn(), max_hap=8 if nm == "paths_dense_2s" else 32)

@@ -46,3 +46,32 @@ def test_pipeline_matches_reference_calls(btg, name):
     alt_count = np.where(called, gt_o.astype(np.int64).sum(axis=2), -1)
     assert (alt_count[called] == t[called]).mean() > 0.995
     assert called.mean() > 0.93
+
+
+def _e2e_tool():
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("e2e_check", Path(__file__).resolve().parent.parent / "tools" / "e2e_check.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_nested_composition_matches_reference_calls(btg, capsys):
+    """Deletions that contain other variants, end to end: host cluster construction -> nested path search -> nested tables -> group-per-thread
+    Gibbs, against the reference's calls for the same candidate set (fixture e2e_nested_2s; the checks are tools/e2e_check.py's, the same
+    statistical bars as above)."""
+    rc = _e2e_tool().main("e2e_nested_2s")
+    out = capsys.readouterr().out
+    assert rc == 0, out
+    assert "FAIL" not in out
+
+
+def test_genome_composition_matches_reference_vcf(btg, capsys):
+    """driver_genome.genotype_genome — several contigs, a contig without variants, a decoy, haploid chrX calls of the male sample — against
+    the VCF the reference wrote for the same genome (tests/golden/vcf_genome_2s.vcf.gz): same records in the same order, same VCS / VCR /
+    VCGS / VCGR, GT agreement and posterior distance at the bars of the single-contig cases."""
+    rc = _e2e_tool().main_genome()
+    out = capsys.readouterr().out
+    assert rc == 0, out
+    assert "FAIL" not in out
