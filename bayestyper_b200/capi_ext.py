@@ -32,6 +32,7 @@ def bind(L):
     L.btg_graphs_reset.argtypes = [vp]
     L.btg_graphs_path_stats.argtypes = [vp, vp]
     L.btg_find_sample_paths.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.btg_find_sample_paths_batch.argtypes = [vp, C.POINTER(vp), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     L.btg_get_best_paths.argtypes = [vp, vp, vp, vp, C.c_uint64]
     L.btg_walk_paths_dev.argtypes = [vp, C.c_int] + [vp] * 11 + [vp]
     L.btg_path_alleles_dev.argtypes = [vp, vp, vp, vp, vp, vp]

@@ -65,6 +65,13 @@ struct DevGraphs {
     uint32_t *mt_pool;              // [resident warps][624] Mersenne states (materialised only when a cluster draws > kMtWindow numbers)
     uint32_t *next;                 // work counter
     unsigned long long *stats;      // [3] k-mer lookups, Bloom probes executed under the reference's early-exit order, nucleotides walked (roofline)
+    // several samples in ONE launch (btg_find_sample_paths_batch): work item = (cluster, sample); 0 = one sample per launch
+    uint32_t batch_n;               // samples in this launch
+    uint32_t batch_first;           // sample index of the first one
+    const BloomView *batch_blooms;  // [batch_n]
+    uint32_t *turn;                 // [C] samples of the cluster whose paths have been merged into `best` so far (addPathIndices is order-dependent)
+    uint8_t *warp_scratch;          // [resident warps][warp_scratch_bytes]: working sets that exceed the shared-memory budget (one per warp, not per cluster)
+    uint64_t warp_scratch_bytes;
 };
 
 // ---- std::mt19937 -------------------------------------------------------------------------------
@@ -449,6 +456,9 @@ __device__ void add_path_indices(Work &w, const uint16_t *paths, uint32_t n) {
 constexpr uint32_t kPathWarps = 4;            // warps per block
 constexpr uint32_t kPathSmemPerWarp = 8192;   // shared-memory budget of one cluster's working set
 
+// BATCH: work item = (cluster, sample of the batch) — the samples of a cluster run side by side on different warps and merge their paths into
+// the cluster's best paths in sample order (btg_find_sample_paths_batch); otherwise one sample per launch, exactly the round-2 kernel.
+template <bool BATCH>
 __global__ void __launch_bounds__(kPathWarps * 32) k_find_sample_paths(DevGraphs g, BloomView bloom, uint32_t random_seed, uint32_t sample_idx, uint32_t max_paths) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *T = reinterpret_cast<uint64_t *>(smem);                    // [256] ntHash 4-nucleotide table
@@ -457,19 +467,25 @@ __global__ void __launch_bounds__(kPathWarps * 32) k_find_sample_paths(DevGraphs
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     uint8_t *my_smem = smem + 2048 + (size_t)wib * kPathSmemPerWarp;
     uint32_t *my_mt = g.mt_pool + ((size_t)blockIdx.x * kPathWarps + wib) * 624;
+    const uint32_t per_cluster = BATCH ? g.batch_n : 1u;           // work items per cluster: the samples of the batch, handed out in sample order
+    const uint64_t n_items = (uint64_t)g.C * per_cluster;
     for (;;) {
         uint32_t t = 0;
         if (lane == 0) t = atomicAdd(g.next, 1u);
         t = __shfl_sync(0xFFFFFFFFu, t, 0);
-        if (t >= g.C) break;
-        const uint32_t c = g.order[t];
+        if (t >= n_items) break;
+        const uint32_t c = g.order[BATCH ? t / per_cluster : t];
+        const uint32_t batch_pos = BATCH ? t % per_cluster : 0u;
+        if constexpr (BATCH) { sample_idx = g.batch_first + batch_pos; bloom = g.batch_blooms[batch_pos]; }
         Work w;
         w.g = &g; w.c = c;
         w.v0 = g.cl_vertex_off[c];
         w.V = (uint32_t)(g.cl_vertex_off[c + 1] - w.v0);
         w.pool = g.cl_pool[c]; w.tmp_cap = g.cl_tmp[c];
         w.slot_bytes = (uint32_t)(sizeof(PathHdr) + ((w.V + 7) & ~7u));
-        uint8_t *p = g.cl_smem[c] ? my_smem : g.scratch + g.scr_off[c];
+        uint8_t *p = g.cl_smem[c] ? my_smem
+                     : BATCH ? g.warp_scratch + ((size_t)blockIdx.x * kPathWarps + wib) * g.warp_scratch_bytes   // the samples of a cluster run side by side
+                                 : g.scratch + g.scr_off[c];
         w.mt = my_mt;
         w.slots = p; p += (size_t)w.pool * w.slot_bytes;
         w.lists = reinterpret_cast<uint16_t *>(p); p += (size_t)w.V * 32 * 2;
@@ -526,13 +542,23 @@ __global__ void __launch_bounds__(kPathWarps * 32) k_find_sample_paths(DevGraphs
             __syncwarp();
         }
         if (lane == 0) {
-            if (!w.overflow) {
-                const uint32_t last = w.V - 1;
-                uint16_t *fin = w.lists + (size_t)last * 32;
-                const uint32_t n = filter_paths(w, fin, w.list_n[last], max_paths, true);
-                add_path_indices(w, fin, n);
+            uint32_t n = 0;
+            uint16_t *fin = w.lists + (size_t)(w.V - 1) * 32;
+            if (!w.overflow) n = filter_paths(w, fin, w.list_n[w.V - 1], max_paths, true);
+            if constexpr (BATCH) {
+                // addPathIndices merges order-dependently (VariantClusterGraph.cpp:726-798): wait until the earlier samples of the batch have merged
+                // theirs.  Items are handed out in (cluster, sample) order and every warp that holds an earlier one is running (persistent,
+                // co-resident grid), so the wait ends; the fence makes their rows of `best` visible to this warp's plain loads.
+                volatile uint32_t *turn = g.turn + c;
+                while (*turn != batch_pos) __nanosleep(64);
+                __threadfence();
             }
+            if (!w.overflow) add_path_indices(w, fin, n);
             if (w.overflow) atomicMax(g.status, c + 1);
+            if constexpr (BATCH) {
+                __threadfence();
+                atomicExch(g.turn + c, batch_pos + 1);       // also after an overflow: the later samples must not wait for ever
+            }
         }
         __syncwarp();
     }
@@ -561,7 +587,9 @@ struct btg_graphs {
     std::vector<uint64_t> h_best_off, h_vertex_off;
     std::vector<uint32_t> h_best_cap;
     uint32_t n_samples_cap = 0;
-    uint32_t grid = 1;
+    uint32_t grid = 1, grid_batch = 1;
+    uint64_t scratch_max = 0;          // largest working set that does not fit the shared-memory budget (bytes, 16-aligned)
+    BloomView *d_batch_blooms = nullptr;   // [n_samples_cap]
 };
 
 extern "C" {
@@ -624,6 +652,7 @@ btg_graphs *btg_graphs_upload(const btg_graphs_desc *d, uint32_t max_samples, ui
         // the working set of most clusters fits the per-warp shared-memory budget; only the others get a slice of the global arena
         if (bytes <= kPathSmemPerWarp) cl_smem[c] = (uint32_t)bytes;
         scr_off[c + 1] = scr_off[c] + (cl_smem[c] ? 0 : ((bytes + 15) & ~15ull));
+        if (!cl_smem[c]) gr->scratch_max = std::max<uint64_t>(gr->scratch_max, (bytes + 15) & ~15ull);
         best_off[c + 1] = best_off[c] + (uint64_t)best_cap[c] * V;
     }
     if (ok) {
@@ -645,8 +674,11 @@ btg_graphs *btg_graphs_upload(const btg_graphs_desc *d, uint32_t max_samples, ui
         // persistent grid: as many blocks as are co-resident; one Mersenne state per warp of the grid
         int per_sm = 0;
         const size_t smem = 2048 + (size_t)kPathWarps * kPathSmemPerWarp;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_find_sample_paths, kPathWarps * 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_find_sample_paths<false>, kPathWarps * 32, smem);
         gr->grid = (uint32_t)std::max(1, per_sm) * (uint32_t)ctx().sm_count;
+        int per_sm_batch = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_batch, k_find_sample_paths<true>, kPathWarps * 32, smem);
+        gr->grid_batch = (uint32_t)std::max(1, std::min(per_sm, per_sm_batch)) * (uint32_t)ctx().sm_count;   // <= grid: the Mersenne pool is sized by `grid`
         uint8_t *scratch = nullptr, *best = nullptr;
         uint32_t *best_n = nullptr, *status = nullptr, *mt_pool = nullptr;
         unsigned long long *stats = nullptr;
@@ -656,6 +688,10 @@ btg_graphs *btg_graphs_upload(const btg_graphs_desc *d, uint32_t max_samples, ui
         ok = ok && btg::dmalloc(&mt_pool, (size_t)gr->grid * kPathWarps * 624 * 4) == cudaSuccess;
         ok = ok && btg::dmalloc(&stats, 3 * 8) == cudaSuccess;
         keep(scratch); keep(best); keep(best_n); keep(status); keep(mt_pool); keep(stats);
+        uint32_t *turn = nullptr;
+        ok = ok && btg::dmalloc(&turn, ((size_t)C + 1) * 4) == cudaSuccess && btg::dmalloc(&gr->d_batch_blooms, (size_t)max_samples * sizeof(BloomView)) == cudaSuccess;
+        keep(turn); keep(gr->d_batch_blooms);
+        g.turn = turn;
         if (ok) cudaMemsetAsync(stats, 0, 3 * 8, ctx().stream);
         g.stats = stats;
         if (ok) {
@@ -711,7 +747,65 @@ int btg_find_sample_paths(btg_graphs *gr, const btg_bloom *sample_bloom, uint32_
     auto s = ctx().stream;
     BTG_CUDA(cudaMemsetAsync(gr->g.next, 0, 4, s));
     const size_t smem = 2048 + (size_t)kPathWarps * kPathSmemPerWarp;
-    k_find_sample_paths<<<gr->grid, kPathWarps * 32, smem, s>>>(gr->g, btg_internal::bloom_view(sample_bloom), random_seed, sample_idx, max_sample_haplotypes);
+    k_find_sample_paths<false><<<gr->grid, kPathWarps * 32, smem, s>>>(gr->g, btg_internal::bloom_view(sample_bloom), random_seed, sample_idx, max_sample_haplotypes);
+    BTG_LAUNCHED();
+    BTG_CUDA(cudaGetLastError());
+    return BTG_OK;
+}
+
+// KmerCounter::findVariantClusterPaths for SEVERAL samples in one launch.  The reference searches one sample at a time because it holds one
+// sample's Bloom filter at a time (main.cpp:219-247); the searches themselves are independent — only addPathIndices, which merges a sample's
+// paths into the cluster's best paths, depends on the sample order — so with the filters of the batch resident the (cluster, sample) pairs
+// run side by side and each cluster merges in sample order (k_find_sample_paths<true>).  A launch of one sample is bounded by the sequential
+// vertex DP of the unit's slowest cluster; a batch pays that latency once instead of once per sample.  Same best paths, bit for bit.
+int btg_find_sample_paths_batch(btg_graphs *gr, const btg_bloom *const *sample_blooms, uint32_t sample_first, uint32_t n_samples, uint32_t random_seed,
+                                uint32_t max_sample_haplotypes) {
+    BTG_REQUIRE_INIT();
+    if (!gr || !sample_blooms) { set_error("null argument"); return BTG_EINVAL; }
+    if (n_samples == 0) return BTG_OK;
+    if ((uint64_t)sample_first + n_samples > gr->n_samples_cap) {
+        set_error("samples %u..%u beyond the capacity given at upload (%u)", sample_first, sample_first + n_samples - 1, gr->n_samples_cap);
+        return BTG_EINVAL;
+    }
+    if (max_sample_haplotypes == 0 || max_sample_haplotypes > 32) { set_error("max_sample_haplotypes must be 1..32"); return BTG_EINVAL; }
+    for (uint32_t i = 0; i < n_samples; i++) if (!sample_blooms[i]) { set_error("null Bloom filter for sample %u", sample_first + i); return BTG_EINVAL; }
+    if (gr->g.C == 0) return BTG_OK;
+    // working sets beyond the shared-memory budget: one slice per resident warp (the per-cluster slices of the one-sample kernel would be shared
+    // by the samples of a cluster); allocated on first use, kept with the graphs.  Too large (or a batch of one): the samples one after the other.
+    const uint64_t n_warps = (uint64_t)gr->grid_batch * kPathWarps;
+    const uint64_t need = gr->scratch_max * n_warps;
+    bool batch = n_samples > 1 && (uint64_t)gr->g.C * n_samples < 0xFFFFFFFFull;
+    if (batch && need && !gr->g.warp_scratch) {
+        const uint64_t cap = std::min<uint64_t>(btg::free_device_memory() / 4, 16ull << 30);
+        uint8_t *ws = nullptr;
+        if (need <= cap && btg::dmalloc(&ws, need + 16) == cudaSuccess) {
+            gr->allocs.push_back(ws);
+            gr->g.warp_scratch = ws;
+            gr->g.warp_scratch_bytes = gr->scratch_max;
+        } else {
+            cudaGetLastError();
+            batch = false;
+        }
+    }
+    if (!batch) {
+        for (uint32_t i = 0; i < n_samples; i++) {
+            const int rc = btg_find_sample_paths(gr, sample_blooms[i], sample_first + i, random_seed, max_sample_haplotypes);
+            if (rc != BTG_OK) return rc;
+        }
+        return BTG_OK;
+    }
+    auto s = ctx().stream;
+    std::vector<BloomView> views(n_samples);
+    for (uint32_t i = 0; i < n_samples; i++) views[i] = btg_internal::bloom_view(sample_blooms[i]);
+    BTG_CUDA(cudaMemcpyAsync(gr->d_batch_blooms, views.data(), (size_t)n_samples * sizeof(BloomView), cudaMemcpyHostToDevice, s));   // pageable source: staged before the call returns
+    BTG_CUDA(cudaMemsetAsync(gr->g.next, 0, 4, s));
+    BTG_CUDA(cudaMemsetAsync(gr->g.turn, 0, ((size_t)gr->g.C + 1) * 4, s));
+    DevGraphs g = gr->g;
+    g.batch_n = n_samples;
+    g.batch_first = sample_first;
+    g.batch_blooms = gr->d_batch_blooms;
+    const size_t smem = 2048 + (size_t)kPathWarps * kPathSmemPerWarp;
+    k_find_sample_paths<true><<<gr->grid_batch, kPathWarps * 32, smem, s>>>(g, BloomView{}, random_seed, sample_first, max_sample_haplotypes);
     BTG_LAUNCHED();
     BTG_CUDA(cudaGetLastError());
     return BTG_OK;

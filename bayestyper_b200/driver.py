@@ -45,6 +45,8 @@ class Options:
     noise_split: str = "chains"          # a sharded unit's estimateNoise: "chains" = every rank runs its share of the (independent) chains on the whole unit,
                                          # no exchange while they run; "groups" = every rank runs all chains on its own groups and the ranks add up their
                                          # noise counts inside the chain kernel after every iteration (NVLink mailboxes; what the joint mode always does)
+    paths_batch: bool = dataclasses.field(default_factory=lambda: os.environ.get("BTG_PATHS_BATCH", "0") != "0")
+                                         # findVariantClusterPaths of all samples in one launch (btg_find_sample_paths_batch) instead of one launch per sample
     kmer_stages: str = "abi"             # "abi": KmerCounter's stages through the btg_counter handle of the C ABI (csrc/counter.cu, what a C++ host calls);
                                          # "torch": the torch-glue mirror (kmer_pipeline.py) — also what a sharded unit uses (it subsets the unit on the device)
 
@@ -129,8 +131,13 @@ def find_variant_cluster_paths(lib, graphs: dict, sample_blooms, opt: Options, c
     else:
         capi.check(lib.btg_graphs_reset(gr), lib)
     try:
-        for s, b in enumerate(sample_blooms):
-            capi.check(lib.btg_find_sample_paths(gr, b, s, opt.random_seed, opt.max_sample_haplotypes), lib)
+        if len(sample_blooms) > 1 and opt.paths_batch:
+            # all samples of the unit in one launch (their filters are resident anyway): same best paths, the slowest cluster's latency paid once
+            arr = (C.c_void_p * len(sample_blooms))(*sample_blooms)
+            capi.check(lib.btg_find_sample_paths_batch(gr, arr, 0, len(sample_blooms), opt.random_seed, opt.max_sample_haplotypes), lib)
+        else:
+            for s, b in enumerate(sample_blooms):
+                capi.check(lib.btg_find_sample_paths(gr, b, s, opt.random_seed, opt.max_sample_haplotypes), lib)
         n_paths = np.zeros(d.n_clusters, np.uint32)
         off = np.zeros(d.n_clusters + 1, np.uint64)
         capi.check(lib.btg_get_best_paths(gr, capi.ptr(n_paths), capi.ptr(off), None, 0), lib)

@@ -161,6 +161,13 @@ void btg_graphs_free(btg_graphs *g);
  * btg_get_best_paths or a synchronisation); a scratch overflow is reported by btg_get_best_paths. */
 int btg_find_sample_paths(btg_graphs *g, const btg_bloom *sample_bloom, uint32_t sample_idx, uint32_t random_seed,
                           uint32_t max_sample_haplotypes);
+/* the passes of the samples sample_first .. sample_first + n_samples - 1 in ONE launch (their filters resident at the same time): the
+ * (cluster, sample) searches run side by side and every cluster merges its samples' paths in sample order, so the best paths equal those of
+ * n_samples btg_find_sample_paths calls bit for bit, while the latency of the unit's slowest cluster is paid once instead of once per sample.
+ * Batches must be submitted in sample order like single samples; falls back to one launch per sample when n_samples == 1 or the per-warp
+ * scratch of the unit's largest clusters does not fit. */
+int btg_find_sample_paths_batch(btg_graphs *g, const btg_bloom *const *sample_blooms, uint32_t sample_first, uint32_t n_samples,
+                                uint32_t random_seed, uint32_t max_sample_haplotypes);
 /* best_paths_indices: n_paths_out[C]; path_off_out[C+1] (prefix sums of n_paths*V, optional); membership_out
  * (optional) one byte per (path, vertex), path-major                                             */
 int btg_get_best_paths(const btg_graphs *g, uint32_t *n_paths_out, uint64_t *path_off_out, uint8_t *membership_out,

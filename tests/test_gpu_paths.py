@@ -45,29 +45,83 @@ def _desc(g):
     return d, keep
 
 
+@pytest.mark.parametrize("mode", ["per_sample", "batch", "first_then_batch"])
 @pytest.mark.parametrize("name", list(PATH_WORKLOADS))
-def test_best_paths_identical_to_reference(btg, name):
+def test_best_paths_identical_to_reference(btg, name, mode):
+    """per_sample: one launch per sample (KmerCounter::findVariantClusterPaths as the reference calls it); batch: all samples in one launch
+    (btg_find_sample_paths_batch: the (cluster, sample) searches side by side, merged per cluster in sample order); first_then_batch: sample 0
+    alone, the others as a batch that starts at sample 1.  All three must leave the reference's best_paths_indices."""
     g, spectra, seed, max_hap = _load(name)
     desc, keep = _desc(g)
     S = len(spectra)
     gr = capi.check(btg.btg_graphs_upload(C.addressof(desc), S, max_hap), btg)
-    for s, (km, _) in enumerate(spectra):
+    blooms = []
+    for km, _ in spectra:
         b = capi.check(btg.btg_bloom_create(len(km), 1e-3, K), btg)       # makeBloom: KmerBloom(n, 0.001)
         capi.check(btg.btg_bloom_insert(b, capi.ptr(km), len(km)), btg)
-        capi.check(btg.btg_find_sample_paths(gr, b, s, seed, max_hap), btg)
-        btg.btg_bloom_free(b)
+        blooms.append(b)
+    arr = (C.c_void_p * S)(*blooms)
+    if mode == "per_sample":
+        for s, b in enumerate(blooms):
+            capi.check(btg.btg_find_sample_paths(gr, b, s, seed, max_hap), btg)
+    elif mode == "batch":
+        capi.check(btg.btg_find_sample_paths_batch(gr, arr, 0, S, seed, max_hap), btg)
+    else:
+        capi.check(btg.btg_find_sample_paths(gr, blooms[0], 0, seed, max_hap), btg)
+        if S > 1:
+            rest = (C.c_void_p * (S - 1))(*blooms[1:])
+            capi.check(btg.btg_find_sample_paths_batch(gr, rest, 1, S - 1, seed, max_hap), btg)
     Cn = desc.n_clusters
     n_paths = np.zeros(Cn, np.uint32)
     off = np.zeros(Cn + 1, np.uint64)
     capi.check(btg.btg_get_best_paths(gr, capi.ptr(n_paths), capi.ptr(off), None, 0), btg)
     mem = np.zeros(int(off[-1]), np.uint8)
     capi.check(btg.btg_get_best_paths(gr, capi.ptr(n_paths), capi.ptr(off), capi.ptr(mem), mem.size), btg)
+    for b in blooms:
+        btg.btg_bloom_free(b)
     V = np.diff(g["cl_vertex_off"]).astype(np.int64)
     ref_n = (np.diff(g["cl_path_off"]).astype(np.int64) // V)
     assert (n_paths == ref_n).all(), f"{(n_paths != ref_n).sum()} clusters differ in the number of best paths"
     assert (off == g["cl_path_off"]).all()
     assert (mem == g["path_bits"]).all()
     btg.btg_graphs_free(gr)
+
+
+def test_batch_with_global_scratch_equals_per_sample(btg, monkeypatch):
+    """Working sets that do not fit the shared-memory budget take a per-warp slice of a global arena in the batch kernel (a per-cluster slice
+    in the one-sample kernel): the dense 3-sample fixture searched with a pool of 32 haplotypes per sample, both ways, a second pass after
+    btg_graphs_reset included (the arena and the turn counters are reused)."""
+    g, spectra, seed, _ = _load("paths_mixed_3s")
+    desc, keep = _desc(g)
+    S = len(spectra)
+    blooms = []
+    for km, _ in spectra:
+        b = capi.check(btg.btg_bloom_create(len(km), 1e-3, K), btg)
+        capi.check(btg.btg_bloom_insert(b, capi.ptr(km), len(km)), btg)
+        blooms.append(b)
+    arr = (C.c_void_p * S)(*blooms)
+    got = []
+    for mode in ("per_sample", "batch", "batch"):
+        if not got:
+            gr = capi.check(btg.btg_graphs_upload(C.addressof(desc), S, 32), btg)
+        else:
+            capi.check(btg.btg_graphs_reset(gr), btg)
+        if mode == "per_sample":
+            for s, b in enumerate(blooms):
+                capi.check(btg.btg_find_sample_paths(gr, b, s, seed, 32), btg)
+        else:
+            capi.check(btg.btg_find_sample_paths_batch(gr, arr, 0, S, seed, 32), btg)
+        n_paths = np.zeros(desc.n_clusters, np.uint32)
+        off = np.zeros(desc.n_clusters + 1, np.uint64)
+        capi.check(btg.btg_get_best_paths(gr, capi.ptr(n_paths), capi.ptr(off), None, 0), btg)
+        mem = np.zeros(int(off[-1]), np.uint8)
+        capi.check(btg.btg_get_best_paths(gr, capi.ptr(n_paths), capi.ptr(off), capi.ptr(mem), mem.size), btg)
+        got.append((n_paths, mem))
+    btg.btg_graphs_free(gr)
+    for b in blooms:
+        btg.btg_bloom_free(b)
+    for n_paths, mem in got[1:]:
+        assert (n_paths == got[0][0]).all() and (mem == got[0][1]).all()
 
 
 def test_rejects_bad_arguments(btg):
