@@ -550,7 +550,16 @@ __global__ void __launch_bounds__(kPathWarps * 32) k_find_sample_paths(DevGraphs
                 // theirs.  Items are handed out in (cluster, sample) order and every warp that holds an earlier one is running (persistent,
                 // co-resident grid), so the wait ends; the fence makes their rows of `best` visible to this warp's plain loads.
                 volatile uint32_t *turn = g.turn + c;
-                while (*turn != batch_pos) __nanosleep(64);
+                unsigned long long t0 = 0;
+                for (uint32_t spins = 0; *turn != batch_pos; spins++) {
+                    __nanosleep(64);
+                    if ((spins & 0xFFFFu) == 0xFFFFu) {      // a wait of 20 s means a lost turn, not a slow cluster: report it instead of hanging the device
+                        unsigned long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (t0 == 0) t0 = now;
+                        else if (now - t0 > 20000000000ull) { atomicMax(g.status, 0xFFFFFFFFu); break; }
+                    }
+                }
                 __threadfence();
             }
             if (!w.overflow) add_path_indices(w, fin, n);
@@ -819,6 +828,7 @@ int btg_get_best_paths(const btg_graphs *gr, uint32_t *n_paths_out, uint64_t *pa
     BTG_CUDA(cudaStreamSynchronize(s));
     uint32_t status = 0;
     BTG_CUDA(cudaMemcpy(&status, gr->g.status, 4, cudaMemcpyDeviceToHost));
+    if (status == 0xFFFFFFFFu) { set_error("batched path search: a cluster waited 20 s for the paths of an earlier sample (lost turn)"); return BTG_ECUDA; }
     if (status) { set_error("cluster %u: path-search scratch overflow", status - 1); return BTG_ESTATE; }
     BTG_CUDA(cudaMemcpy(n_paths_out, gr->g.best_n, C * 4, cudaMemcpyDeviceToHost));
     if (!path_off_out) return BTG_OK;
