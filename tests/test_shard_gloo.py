@@ -163,3 +163,51 @@ def test_subset_graphs_keeps_vertices_edges_and_group_indices():
             assert (sub["v_in_src"][s_vio[sv]:s_vio[sv + 1]] == g["v_in_src"][vio[v]:vio[v + 1]]).all()     # edge sources are vertex indices inside the cluster
     empty, cl = driver.subset_graphs_for_paths(g, np.zeros(0, np.int64))
     assert len(cl) == 0 and len(empty["cl_vertex_off"]) == 1
+
+
+def _chains_worker(rank, world, port, out_dir):
+    """estimateNoise split by CHAINS: this rank runs the chains rank, rank + world, ... of the WHOLE unit — here the
+    oracle stands in for btg_estimate_noise_chains (its chains are the same independent streams: the rows of the other ranks' chains are
+    simply not used) — and returns the [n_chains][S] post-burn-in rate sums of its own chains, zeros elsewhere; the exchange and the finish
+    are the host code of driver.genotype."""
+    sys.path.insert(0, str(ROOT))
+    import torch.distributed as dist
+    from tests import _oracle as O
+    from tests._fixtures import GibbsFixture
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fx = GibbsFixture("gibbs_snv_1s")
+    CH, BURN, SAMPLES = 5, 6, 9
+    cd = O.OracleCountDist(fx.nb_p, fx.nb_size)
+    trace = O.oracle_estimate_noise(fx.unit, cd, fx.opts(chains=CH, burn=BURN, samples=SAMPLES))
+    rows = trace[:-1].reshape(CH, BURN + SAMPLES + 1, 2 + fx.S)
+    sums = np.zeros((CH, fx.S))
+    for c in range(rank, CH, world):
+        sums[c] = rows[c, 1 + BURN:, 2:].sum(axis=0)
+    parts = [None] * world
+    dist.all_gather_object(parts, sums)
+    total = np.zeros_like(sums)
+    for p in parts:                      # rank order; every row is non-zero on exactly one rank
+        total += p
+    assert all((np.count_nonzero([p[c].any() for p in parts]) == 1) for c in range(CH))
+    rates = total.sum(axis=0) / (CH * SAMPLES)          # btg_count_dist_finish_noise
+    np.save(Path(out_dir) / f"rates_{rank}.npy", rates)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_noise_chain_sums_exchange_two_ranks(tmp_path):
+    """Both ranks end with the noise rates of the single-process run, and with the SAME bits as each other (the sums are added in rank order on
+    every rank)."""
+    sys.path.insert(0, str(ROOT))
+    from tests import _oracle as O
+    from tests._fixtures import GibbsFixture
+    O.load()
+    mp.spawn(_chains_worker, args=(2, 29523, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "rates_0.npy"), np.load(tmp_path / "rates_1.npy")
+    assert (r0 == r1).all()
+    fx = GibbsFixture("gibbs_snv_1s")
+    cd = O.OracleCountDist(fx.nb_p, fx.nb_size)
+    O.oracle_estimate_noise(fx.unit, cd, fx.opts(chains=5, burn=6, samples=9))
+    assert np.abs(r0 / cd.noise_rates() - 1).max() < 1e-12
