@@ -45,8 +45,8 @@ class Options:
     noise_split: str = "chains"          # a sharded unit's estimateNoise: "chains" = every rank runs its share of the (independent) chains on the whole unit,
                                          # no exchange while they run; "groups" = every rank runs all chains on its own groups and the ranks add up their
                                          # noise counts inside the chain kernel after every iteration (NVLink mailboxes; what the joint mode always does)
-    paths_batch: bool = dataclasses.field(default_factory=lambda: os.environ.get("BTG_PATHS_BATCH", "0") != "0")
-                                         # findVariantClusterPaths of all samples in one launch (btg_find_sample_paths_batch) instead of one launch per sample
+    paths_batch: bool = dataclasses.field(default_factory=lambda: os.environ.get("BTG_PATHS_BATCH", "1") != "0")
+                                         # findVariantClusterPaths of all samples in one launch (btg_find_sample_paths_batch; BTG_PATHS_BATCH=0: one launch per sample)
     kmer_stages: str = "abi"             # "abi": KmerCounter's stages through the btg_counter handle of the C ABI (csrc/counter.cu, what a C++ host calls);
                                          # "torch": the torch-glue mirror (kmer_pipeline.py) — also what a sharded unit uses (it subsets the unit on the device)
 

@@ -94,7 +94,7 @@ int main(int argc, char **argv) {
         gd.v_flags = get(b, "g.v_flags").as<uint8_t>(); gd.v_in_off = get(b, "g.v_in_off").as<uint64_t>(); gd.v_in_src = get(b, "g.v_in_src").as<uint32_t>();
         gd.cl_group = cl_group.data(); gd.cl_idx = get(b, "g.cluster_idx").as<uint32_t>();
         btg_graphs *gr = nonnull(btg_graphs_upload(&gd, S, max_hap));
-        for (uint32_t s = 0; s < S; s++) check(btg_find_sample_paths(gr, blooms[s], s, o.random_seed, max_hap));
+        check(btg_find_sample_paths_batch(gr, blooms.data(), 0, S, o.random_seed, max_hap));   // all samples' filters are resident: one launch (KmerCounter.cpp:70-103 per sample)
         std::vector<uint32_t> n_paths(C);
         std::vector<uint64_t> path_off((size_t)C + 1);
         check(btg_get_best_paths(gr, n_paths.data(), path_off.data(), nullptr, 0));
