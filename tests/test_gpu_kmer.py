@@ -217,3 +217,23 @@ def test_full_size_properties(btg):
     capi.check(btg.btg_scan_sequence(seq, len(seq), capi.ptr(k1), capi.ptr(v1)))
     capi.check(btg.btg_scan_sequence(rc, len(rc), capi.ptr(k2), capi.ptr(v2)))
     assert (k1[54:] == k2[54:][::-1]).all()
+
+
+def test_bloom_self_test_rates_on_device(btg, oracle):
+    """The reference's own (disabled) Bloom self-test, MakeBloom::testbloom (src/bayesTyperTools/MakeBloom.cpp:311-375), through btg_bloom_*:
+    every inserted k-mer is found; k-mers one bit away from an inserted one, and random k-mers, are found at the design false-positive rate —
+    and k-mer for k-mer where the oracle's filter finds them."""
+    from tests.test_oracle_kmer import _perturbed
+    n, fpr = 100_000, 1e-3
+    kmers = O.random_kmers(n, 11)
+    b = capi.check(btg.btg_bloom_create(n, fpr, K))
+    nk, m, nh = _info(btg, b)
+    capi.check(btg.btg_bloom_insert(b, capi.ptr(kmers), n))
+    ref_bits = O.bloom_build(kmers, m, nh)
+    for probe, lo, hi in ((kmers, 1.0, 1.0), (_perturbed(kmers, 12), fpr / 2, fpr * 2), (O.random_kmers(n, 13), fpr / 2, fpr * 2)):
+        probe = np.ascontiguousarray(probe)
+        hit = np.zeros(len(probe), np.uint8)
+        capi.check(btg.btg_bloom_lookup(b, capi.ptr(probe), len(probe), capi.ptr(hit)))
+        assert (hit == O.bloom_lookup(ref_bits, m, nh, probe)).all()
+        assert lo <= hit.mean() <= hi, hit.mean()
+    btg.btg_bloom_free(b)

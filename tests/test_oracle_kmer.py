@@ -83,3 +83,31 @@ def test_canonical_is_min_of_strand_strings(oracle):
         out = np.zeros(2, np.uint64)
         oracle.bto_canonical(km, 55, out)
         assert O.unpack(out) == min(s, rc)
+
+
+def _perturbed(kmers, seed):
+    """One random bit of the 110 flipped per k-mer (MakeBloom::testbloom, MakeBloom.cpp:333-334)."""
+    rng = np.random.default_rng(seed)
+    bit = rng.integers(0, 2 * 55, len(kmers))
+    out = kmers.copy()
+    lo = bit < 64
+    out[lo, 0] ^= np.uint64(1) << bit[lo].astype(np.uint64)
+    out[~lo, 1] ^= np.uint64(1) << (bit[~lo] - 64).astype(np.uint64)
+    return out
+
+
+def test_bloom_self_test_rates(oracle):
+    """The reference's own (disabled) Bloom self-test, MakeBloom::testbloom (src/bayesTyperTools/MakeBloom.cpp:311-375): every inserted k-mer is
+    found; k-mers one bit away from an inserted one and random k-mers that are not in the set are found at the design false-positive rate."""
+    n, fpr = 100_000, 1e-3
+    kmers = O.random_kmers(n, 11)
+    m = oracle.bto_bloom_num_bits(n, fpr)
+    nh = oracle.bto_bloom_num_hashes(m, n)
+    bits = O.bloom_build(kmers, m, nh)
+    assert O.bloom_lookup(bits, m, nh, kmers).all()                                  # original: all found
+    present = {tuple(k) for k in kmers.tolist()}
+    for probe in (_perturbed(kmers, 12), O.random_kmers(n, 13)):
+        absent = np.array([tuple(k) not in present for k in probe.tolist()])
+        assert absent.mean() > 0.999                                                 # a 110-bit k-mer space: collisions with the set are not expected
+        fp = O.bloom_lookup(bits, m, nh, probe[absent]).mean()
+        assert fpr / 2 < fp < fpr * 2, fp                                            # 100 expected hits: +-100 % is > 6 sigma
