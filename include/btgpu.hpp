@@ -8,6 +8,8 @@
 //   btg::CountDistribution  ≡ CountDistribution      include/bayesTyper/CountDistribution.hpp:44-90
 //   btg::InferenceUnit      ≡ the VariantClusterHaplotypes of an InferenceUnit (flat descriptors)
 //   btg::InferenceEngine    ≡ InferenceEngine        include/bayesTyper/InferenceEngine.hpp:56-98
+//   btg::VariantClusterGraphs ≡ the VariantClusterGraph set of an InferenceUnit + findVariantClusterPaths' best paths
+//   btg::KmerCounter        ≡ KmerCounter + KmerCountsHash for one unit   include/bayesTyper/KmerCounter.hpp:53-67
 //
 // There is no CPU implementation behind any of it: every method is one or two libbtgpu calls.
 #pragma once
@@ -143,12 +145,123 @@ class InferenceUnit {
     explicit InferenceUnit(const btg_unit_desc &d) : u_(check_ptr(btg_unit_upload(&d))), n_samples_(d.n_samples) {
         var_nalleles_.assign(d.var_nalleles, d.var_nalleles + d.cl_var_off[d.n_clusters]);
     }
+    // adopts a unit that is already resident in HBM (KmerCounter::classifyPathKmers below)
+    InferenceUnit(btg_unit *resident, uint32_t n_samples, const uint16_t *var_nalleles, uint64_t n_variants)
+        : u_(check_ptr(resident)), n_samples_(n_samples), var_nalleles_(var_nalleles, var_nalleles + n_variants) {}
     ~InferenceUnit() { btg_unit_free(u_); }
     InferenceUnit(const InferenceUnit &) = delete;
     InferenceUnit &operator=(const InferenceUnit &) = delete;
     btg_unit *handle() const { return u_; }
     uint32_t numSamples() const { return n_samples_; }
     GenotypeArrays allocResult() const { return GenotypeArrays(n_samples_, var_nalleles_.data(), var_nalleles_.size()); }
+};
+
+// The VariantClusterGraph set of one inference unit (CSR-flattened, btg_graphs_desc) and the best paths that
+// KmerCounter::findVariantClusterPaths leaves in it (VariantClusterGraph::best_paths_indices).
+class VariantClusterGraphs {
+    btg_graphs *g_;
+    uint32_t n_clusters_;
+
+  public:
+    struct BestPaths {
+        std::vector<uint32_t> n_paths;     // [C]
+        std::vector<uint64_t> path_off;    // [C+1] byte offset of a cluster's rows in membership
+        std::vector<uint8_t> membership;   // one byte per (path, vertex), path-major
+    };
+    VariantClusterGraphs(const btg_graphs_desc &d, uint32_t num_samples, uint32_t max_sample_haplotypes)
+        : g_(check_ptr(btg_graphs_upload(&d, num_samples, max_sample_haplotypes))), n_clusters_(d.n_clusters) {}
+    ~VariantClusterGraphs() { btg_graphs_free(g_); }
+    VariantClusterGraphs(const VariantClusterGraphs &) = delete;
+    VariantClusterGraphs &operator=(const VariantClusterGraphs &) = delete;
+    btg_graphs *handle() const { return g_; }
+    uint32_t numClusters() const { return n_clusters_; }
+    void reset() { check(btg_graphs_reset(g_)); }
+    BestPaths bestPaths() const {
+        BestPaths b;
+        b.n_paths.resize(n_clusters_);
+        b.path_off.resize((size_t)n_clusters_ + 1);
+        check(btg_get_best_paths(g_, b.n_paths.data(), b.path_off.data(), nullptr, 0));
+        b.membership.resize(b.path_off[n_clusters_]);
+        check(btg_get_best_paths(g_, b.n_paths.data(), b.path_off.data(), b.membership.data(), b.membership.size()));
+        return b;
+    }
+};
+
+// KmerCounter (include/bayesTyper/KmerCounter.hpp:53-67) with the KmerCountsHash it fills (KmerHash.hpp:73-87), for one inference unit.
+// The reference's methods take the unit, the hash and Bloom filters as arguments and spawn threads; here the table lives in HBM
+// behind the handle, the sample k-mers and the inter-cluster regions are device buffers (btg_device_alloc / btg_copy_to_device), and
+// every method is one launch sequence on the library stream.  Stage order as main.cpp:594-617.
+class KmerCounter {
+    btg_counter *k_ = nullptr;
+    uint32_t n_samples_ = 0;
+    std::vector<uint16_t> var_nalleles_;
+    uint32_t prng_seed_;
+
+  public:
+    explicit KmerCounter(uint32_t prng_seed) : prng_seed_(prng_seed) {}
+    ~KmerCounter() { btg_counter_free(k_); }
+    KmerCounter(const KmerCounter &) = delete;
+    KmerCounter &operator=(const KmerCounter &) = delete;
+
+    // KmerCounter::findVariantClusterPaths (KmerCounter.cpp:70-103) for ONE sample: the reference holds one sample's filter at a time
+    // (main.cpp:219-247); samples must come in order
+    void findVariantClusterPaths(VariantClusterGraphs *graphs, const KmerBloom &sample_bloom, uint32_t sample_idx, uint16_t max_sample_haplotypes) const {
+        check(btg_find_sample_paths(graphs->handle(), sample_bloom.handle(), sample_idx, prng_seed_, max_sample_haplotypes));
+    }
+    // ... and for the samples first .. first + n - 1 in one launch, when their filters are resident together (same best paths)
+    void findVariantClusterPaths(VariantClusterGraphs *graphs, const std::vector<const KmerBloom *> &sample_blooms, uint32_t first_sample_idx,
+                                 uint16_t max_sample_haplotypes) const {
+        std::vector<const btg_bloom *> h;
+        for (const KmerBloom *b : sample_blooms) h.push_back(b->handle());
+        check(btg_find_sample_paths_batch(graphs->handle(), h.data(), first_sample_idx, (uint32_t)h.size(), prng_seed_, max_sample_haplotypes));
+    }
+    // KmerCounter::countPathKmers (KmerCounter.cpp:252-289): `unit` describes the graphs, the best paths and the variant tables of the unit
+    // (btg_counter_desc; host arrays, copied); returns the number of distinct path k-mers
+    uint64_t countPathKmers(const btg_counter_desc &unit) {
+        btg_counter_free(k_);
+        k_ = check_ptr(btg_counter_create(&unit));
+        n_samples_ = unit.n_samples;
+        var_nalleles_.assign(unit.var_nalleles, unit.var_nalleles + unit.cl_var_off[unit.n_clusters]);
+        uint64_t n = 0;
+        check(btg_counter_count_path_kmers(k_, &n));
+        return n;
+    }
+    // KmerCounter::countInterclusterKmers (KmerCounter.cpp:291-386) for the regions of one ploidy class ('N'-separated text in HBM)
+    void countInterclusterKmers(const char *regions_dev, size_t len, bool is_decoy, uint32_t ploidy_female, uint32_t ploidy_male) {
+        check(btg_counter_count_intercluster_kmers(need(), regions_dev, len, is_decoy ? 1 : 0, ploidy_female, ploidy_male));
+    }
+    // KmerCounter::parseSampleKmers (KmerCounter.cpp:431-524) for one sample's KMC records (listing order) in HBM
+    void parseSampleKmers(uint32_t sample_idx, const uint64_t *kmers_dev, const uint8_t *counts_dev, size_t n) {
+        check(btg_counter_parse_sample_kmers(need(), sample_idx, kmers_dev, counts_dev, n));
+    }
+    // KmerCounter::classifyPathKmers (KmerCounter.cpp:526-600) + VariantClusterGraph::getHaplotypeCandidates of every cluster:
+    // the inference unit the genotypers are built from, resident in HBM (nothing crosses the boundary).
+    // multigroup_kmers: <cluster_data>/multigroup_kmers filter of the cluster stage, or nullptr (exact)
+    InferenceUnit classifyPathKmers(const KmerBloom *multigroup_kmers, const std::vector<uint8_t> &group_ploidy) {
+        btg_unit *u = btg_counter_build_unit(need(), multigroup_kmers ? multigroup_kmers->handle() : nullptr, group_ploidy.data());
+        return InferenceUnit(u, n_samples_, var_nalleles_.data(), var_nalleles_.size());
+    }
+    // countInterclusterParameterKmers' genotype-side half + calculateKmerStats + setGenomicCountDistributions (KmerCounter.cpp:171-250,
+    // KmerHash.cpp:257-347, CountDistribution.cpp:66-141): negative-binomial (p, size) per sample
+    struct GenomicParameters { std::vector<double> nb_p, nb_size; std::vector<uint32_t> modal_multiplicity; std::vector<uint64_t> n_modal_kmers; };
+    GenomicParameters fitGenomicCountDistributions(const char *regions_dev, size_t len, uint32_t ploidy_female, uint32_t ploidy_male,
+                                                   const std::vector<const uint64_t *> &sample_kmers_dev, const std::vector<const uint8_t *> &sample_counts_dev,
+                                                   const std::vector<size_t> &sample_n, const uint64_t *parameter_kmers, size_t n_parameter_kmers,
+                                                   uint64_t max_parameter_kmers) {
+        GenomicParameters p;
+        p.nb_p.resize(n_samples_); p.nb_size.resize(n_samples_); p.modal_multiplicity.resize(n_samples_); p.n_modal_kmers.resize(n_samples_);
+        check(btg_counter_fit_nb(need(), regions_dev, len, ploidy_female, ploidy_male, sample_kmers_dev.data(), sample_counts_dev.data(), sample_n.data(),
+                                 parameter_kmers, n_parameter_kmers, prng_seed_, max_parameter_kmers, p.nb_p.data(), p.nb_size.data(),
+                                 p.modal_multiplicity.data(), p.n_modal_kmers.data()));
+        return p;
+    }
+    btg_counter *handle() const { return k_; }
+
+  private:
+    btg_counter *need() const {
+        if (!k_) throw Error("KmerCounter: countPathKmers has not been called");
+        return k_;
+    }
 };
 
 class InferenceEngine {
