@@ -241,6 +241,7 @@ if __name__ == "__main__":
         # every group of the reference run
         w = DEEP_WORKLOAD()
         make("gibbs_deep_2s", w, 10**6, n_errors=4000)
+        make("gibbs_joint_deep_2s", w, 10**6, n_errors=4000, extra_args=("--noise-genotyping",))     # CPU parity chain only (oracle-P == reference)
         make_pipeline("pipe_deep_2s", w)
         make_paths("paths_deep_2s", w)
         _sys.exit(0)

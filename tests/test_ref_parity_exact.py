@@ -42,7 +42,7 @@ def test_default_mode_equals_reference(name):
     _print_equal(res["mac"], fx.ref["mac"])
 
 
-@pytest.mark.parametrize("name", ["gibbs_joint_2s", "gibbs_joint_30s", "gibbs_joint_nested_2s"])
+@pytest.mark.parametrize("name", ["gibbs_joint_2s", "gibbs_joint_30s", "gibbs_joint_nested_2s", "gibbs_joint_deep_2s"])
 def test_joint_mode_equals_reference(name):
     """--noise-genotyping (InferenceEngine::estimateNoiseAndGenotypes): the fixture holds every group of the reference run, so
     the lock-step noise-rate trace is reproduced row for row as well."""
@@ -60,11 +60,13 @@ def test_joint_mode_equals_reference(name):
     _print_equal(res["mac"], fx.ref["mac"])
 
 
-def test_noise_estimation_equals_reference():
+@pytest.mark.parametrize("name", ["gibbs_full_2s", "gibbs_deep_2s"])
+def test_noise_estimation_equals_reference(name):
     """InferenceEngine::estimateNoise on a fixture that holds the reference's whole unit: group selection (the engine's own
     mt19937 + std::shuffle), per-chain genotyper seeds and the running CountDistribution stream give the reference's trace and
-    final rates."""
-    fx = GibbsFixture("gibbs_full_2s")
+    final rates.  gibbs_deep_2s: a unit whose multi-cluster groups are deeply nested (they are skipped by the selection, and
+    genotyped exactly afterwards)."""
+    fx = GibbsFixture(name)
     assert (fx.groups == np.arange(fx.unit.G)).all()
     cd = O.OracleCountDist(fx.nb_p, fx.nb_size)
     with O.reference_streams(fx.groups):
