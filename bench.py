@@ -555,7 +555,9 @@ def stage_breakdown(lib, inp, opt, stream, dev, shard_ctx=None):
 # ------------------------------------------------------------------------------------------------
 # the reference's own CPU path (oracle-R), bounded sample
 # ------------------------------------------------------------------------------------------------
-FULL_B = {"variants": 300_000, "noise_cap_variants": 100_000}      # configs[1]; InferenceEngine.cpp:50 noise_variants_batch_size
+# configs[1] as build_batch() makes it at --scale 1 (seeded: the same candidate set on every run; the numbers are the ones our arm's line reports);
+# InferenceEngine.cpp:50 noise_variants_batch_size
+FULL_B = {"variants": 299_455, "clusters": 200_730, "noise_cap_variants": 100_000}
 
 
 def cpu_reference(config: str, n_variants: int, threads: int, gibbs_samples: int = 250):
@@ -600,10 +602,10 @@ def cpu_reference(config: str, n_variants: int, threads: int, gibbs_samples: int
         r = FULL_B["variants"] / len(var)
         r_noise = min(FULL_B["variants"], FULL_B["noise_cap_variants"]) / min(len(var), FULL_B["noise_cap_variants"])
         full_s = (kmer_s + geno_s) * r + noise_s * r_noise
-        out.update({"value": tj["clusters_genotyped"] * r / full_s, "projected_full_step_s": full_s,
+        out.update({"value": FULL_B["clusters"] / full_s, "projected_full_step_s": full_s,
                     "sample": f"{len(var)} variants / {tj['num_clusters']} clusters of the same chr22-like shape through the reference's own stages, {threads} threads "
                               f"(estimateGenotypes {geno_s:.2f} s, estimateNoise {noise_s:.2f} s, k-mer stages {kmer_s:.2f} s, wall {wall:.1f} s = {sample_rate:.0f} clusters/s on the sample); "
-                              f"value = rate of the full 300k-variant config projected from these stage times (estimateNoise is capped at 100k variants, InferenceEngine.cpp:50: "
+                              f"value = rate of the full config ({FULL_B['variants']} variants / {FULL_B['clusters']} clusters) projected from these stage times (estimateNoise is capped at 100k variants, InferenceEngine.cpp:50: "
                               f"x{r_noise:.1f}; the other stages x{r:.1f})"})
     else:
         out.update({"value": sample_rate,
@@ -640,7 +642,7 @@ def run_reference(args):
     ms = float(np.mean([v["step_s"] * 1e3 for v in vals]))            # MEASURED: the reference's stages on one bounded sample (what the K timed steps actually took)
     proj = [v["projected_full_step_s"] * 1e3 for v in vals if "projected_full_step_s" in v]
     cb = dict(last); cb["value"] = value
-    full_clusters = int(round(last["clusters"] * (FULL_B["variants"] / last["sample_variants"]))) if args.config == "B" else last["clusters"]
+    full_clusters = FULL_B["clusters"] if args.config == "B" else last["clusters"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 and args.mode != "replicas" else "weak", "vs_baseline": None,
             "dtype": "f64 (Gibbs log-likelihoods) / u64 (k-mer hashing)", "data": "synthetic",
