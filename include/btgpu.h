@@ -77,7 +77,7 @@ typedef struct btg_unit btg_unit;   /* an inference unit resident in HBM (define
 btg_bloom *btg_bloom_create(uint64_t num_kmers, float fpr, int k);
 /* KmerBloom(prefix): <prefix>.bloomMeta / .bloomData    KmerBloom.cpp:62-89 */
 btg_bloom *btg_bloom_load(const char *prefix, int k);
-/* same, from memory (meta fields + raw filter bytes, (num_bits+7)/8 of them) */
+/* same, from memory (the .bloomMeta fields + the raw .bloomData bytes, (num_bits+7)/8 of them; KmerBloom.cpp:62-89) */
 btg_bloom *btg_bloom_from_bytes(const uint8_t *data, uint64_t num_kmers, uint64_t num_bits, int k);
 /* KmerBloom::save(prefix)              KmerBloom.cpp:148-164 */
 int btg_bloom_save(const btg_bloom *b, const char *prefix);
@@ -161,14 +161,15 @@ void btg_graphs_free(btg_graphs *g);
  * btg_get_best_paths or a synchronisation); a scratch overflow is reported by btg_get_best_paths. */
 int btg_find_sample_paths(btg_graphs *g, const btg_bloom *sample_bloom, uint32_t sample_idx, uint32_t random_seed,
                           uint32_t max_sample_haplotypes);
-/* the passes of the samples sample_first .. sample_first + n_samples - 1 in ONE launch (their filters resident at the same time): the
+/* KmerCounter::findVariantClusterPaths (KmerCounter.cpp:70-103) for the samples sample_first .. sample_first + n_samples - 1 in ONE launch — the
+ * reference loops over the samples with one filter resident at a time (main.cpp:219-247); here their filters are resident together: the
  * (cluster, sample) searches run side by side and every cluster merges its samples' paths in sample order, so the best paths equal those of
  * n_samples btg_find_sample_paths calls bit for bit, while the latency of the unit's slowest cluster is paid once instead of once per sample.
  * Batches must be submitted in sample order like single samples; falls back to one launch per sample when n_samples == 1 or the per-warp
  * scratch of the unit's largest clusters does not fit. */
 int btg_find_sample_paths_batch(btg_graphs *g, const btg_bloom *const *sample_blooms, uint32_t sample_first, uint32_t n_samples,
                                 uint32_t random_seed, uint32_t max_sample_haplotypes);
-/* best_paths_indices: n_paths_out[C]; path_off_out[C+1] (prefix sums of n_paths*V, optional); membership_out
+/* VariantClusterGraph::best_paths_indices (VariantClusterGraph.hpp:98; filled by addPathIndices, VariantClusterGraph.cpp:726-798): n_paths_out[C]; path_off_out[C+1] (prefix sums of n_paths*V, optional); membership_out
  * (optional) one byte per (path, vertex), path-major                                             */
 int btg_get_best_paths(const btg_graphs *g, uint32_t *n_paths_out, uint64_t *path_off_out, uint8_t *membership_out,
                        uint64_t membership_bytes);
@@ -222,7 +223,7 @@ int btg_path_alleles_dev(const btg_pathwalk_desc *d, const uint64_t *cl_var_off,
  * Applies to the three table probes below, on the CALLING HOST THREAD, until changed (thread-local: a probe of another key table
  * must clear or replace it first; a probe without an index is correct, only slower).  btg_counter handles install their own. */
 int btg_table_set_index_dev(const int64_t *lut, int lut_bits);
-/* KmerCountsHash::findKmer on a batch: index into the key arrays or -1 */
+/* KmerCountsHash::findKmer (KmerHash.hpp:82, ObservedKmerCountsHash: KmerHash.cpp:230-243) on a batch: index into the key arrays or -1 */
 int btg_table_lookup_dev(const int64_t *key_lo, const int64_t *key_hi, int64_t n_keys, const uint64_t *kmers, size_t n,
                          int64_t *idx_out, void *stream);
 /* KmerCounter::parseSampleKmers for one batch of one sample (KmerCounter.cpp:388-429): for every (k-mer, count)
