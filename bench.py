@@ -287,6 +287,12 @@ def run_ours(args):
     inp = (build_batch_d if args.config == "D" else build_batch)(lib, 0 if sharded else rank, args.scale, dev)
     inp.make_resident(lib, opt)
     setup_s = time.time() - t0
+    # the synthetic batch is ~1.5 M long-lived Python objects (300k Variant records, the graph arrays' wrappers): a full collection of the cyclic
+    # GC walks all of them (100-300 ms) whenever it triggers inside a step — one step in three was that much slower.  Park them in the permanent
+    # generation; the steps' own garbage is still collected.
+    import gc
+    gc.collect()
+    gc.freeze()
     n_sample = int(sum(k.shape[0] for k, _ in inp.spectra_dev))
     S = len(inp.spectra_dev)
 
