@@ -288,7 +288,7 @@ def run_ours(args):
     inp.make_resident(lib, opt)
     setup_s = time.time() - t0
     # the synthetic batch is ~1.5 M long-lived Python objects (300k Variant records, the graph arrays' wrappers): a full collection of the cyclic
-    # GC walks all of them (100-300 ms on this container's CPU) whenever it triggers inside a step — the suspected cause of the one step in three
+    # GC walks all of them (75 ms for the Variant records alone on this container) whenever it triggers inside a step — the suspected cause of the one step in three
     # that took 150-300 ms longer in profiles/r2_bench_n1_v{1,2}.json (not re-measured: the round's GPU minutes were spent).  Park them in the
     # permanent generation; the steps' own garbage is still collected.
     import gc
