@@ -622,6 +622,14 @@ def cpu_reference(config: str, n_variants: int, threads: int, gibbs_samples: int
     return out
 
 
+def reference_sample_variants(config: str, steps: int, warmup: int) -> int:
+    """Variants per sample run of the reference arm: (one warm-up run when W > 0) + K timed runs must end within a few minutes."""
+    runs = steps + (1 if warmup > 0 else 0)
+    if config == "B":
+        return int(min(12_000, max(2_000, 60_000 // max(1, runs))))
+    return int(min(120, max(40, 720 // max(1, runs))))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -631,9 +639,7 @@ def run_reference(args):
     # within a few minutes on a 16-thread host (measured: ~3.5 ms of wall per sample variant for B, ~0.25 s for the 30-sample D shape):
     # K = 1..4 -> 12,000 variants per run, the driver's K = 20 -> 2,857.  The projection to the full config (cpu_reference) is the same
     # for every sample size; the size is printed in config.sample.
-    runs = args.steps + (1 if args.warmup > 0 else 0)
-    auto = int(min(12_000, max(2_000, 60_000 // max(1, runs)))) if args.config == "B" else int(min(120, max(40, 720 // max(1, runs))))
-    n_var = args.cpu_variants if args.cpu_variants else auto
+    n_var = args.cpu_variants if args.cpu_variants else reference_sample_variants(args.config, args.steps, args.warmup)
     vals = []
     last = None
     for i in range(args.warmup + args.steps):
