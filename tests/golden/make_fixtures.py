@@ -188,8 +188,7 @@ E2E_WORKLOADS = {
 }
 E2E_N_ERRORS = {"e2e_configA_1s": 100_000}              # sequencing-error k-mers added to the spectra (default 20,000)
 
-# end-to-end cases whose fixtures exist but which have not run on a GPU yet (tools/e2e_check.py runs them; a case moves up to
-# E2E_WORKLOADS once it is green there)
+# the nested end-to-end case: run by tools/e2e_check.py and, since round 2, by tests/test_gpu_e2e.py::test_nested_composition_matches_reference_calls
 E2E_NEXT_WORKLOADS = {
     "e2e_nested_2s": lambda: synth.nested_sv(25, 100_000, 2, seed=31, n_background=400, sv_len=(150, 600), repeat_frac=0.4),
 }
