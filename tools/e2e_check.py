@@ -1,5 +1,6 @@
-"""End-to-end check of a staged fixture on a GPU box: tests/golden/make_fixtures.py E2E_NEXT_WORKLOADS -> driver.run -> the
-reference's calls (same statistical bars as tests/test_gpu_e2e.py).  A case that is green here moves to E2E_WORKLOADS.
+"""End-to-end check of a composition on a GPU box: tests/golden/make_fixtures.py E2E_NEXT_WORKLOADS -> driver.run -> the
+reference's calls (same statistical bars as tests/test_gpu_e2e.py).  Both checks below are also `-m gpu` tests since round 2
+(tests/test_gpu_e2e.py imports main / main_genome from here).
 
     gpurun --timeout 600 -- 'python tools/e2e_check.py e2e_nested_2s; python tools/e2e_check.py genome'
 
