@@ -12,13 +12,15 @@
 // function (citations are file:line under /root/reference) with std containers, and is
 // deliberately written independently of bayestyper_b200/csrc/gibbs*.cu.
 //
-// Parity status:
-//   * vs the CUDA path: same random streams -> posteriors must agree to 1e-4 (in practice
-//     bit-identical tallies); checked in tests/test_gpu_gibbs.py.
-//   * vs the reference (oracle-R, mt19937 + libstdc++ distributions): the reference's draws
-//     cannot be reproduced by a counter-based generator (SURVEY.md §7 hard part 1), so that
-//     comparison is statistical: identical hard calls on confident sites, GPP within Monte-Carlo
-//     error.  Checked in tests/test_ref_parity.py (pins this file to the reference's behaviour).
+// Parity status: PINNED, exactly.
+//   * vs the reference (oracle-R = the reference's own translation units, oracle/ref_build): in mt19937 mode this file
+//     reproduces the reference's diplotype tallies, hence every genotype field, the allele statistics and the full
+//     noise-rate trace EXACTLY — default mode, estimateNoise, --noise-genotyping with 2 and 30 samples, nested and deeply
+//     nested groups (tests/test_ref_parity_exact.py, 12 cases against fixtures dumped by oracle-R).
+//   * vs the CUDA path: in Philox mode the kernels must reproduce this file's tallies (posteriors to 1e-4; in practice
+//     identical tallies): tests/test_gpu_gibbs.py, tests/test_gpu_gibbs_wide.py.
+//   * the Philox mode is also compared statistically with reference runs (identical hard calls on confident sites, GPP
+//     within Monte-Carlo error): tests/test_ref_parity.py — a second, independent check of the same restatement.
 //
 // Random-stream specification (shared with the kernels):
 //   Philox4x32-10, key = (random_seed, uint32(group_index + 1)),
