@@ -19,7 +19,7 @@
 // Groups made of ONE cluster (the bulk of any unit) run one thread per cluster in k_estimate_genotypes.  Groups
 // with nested clusters (VariantClusterGroup::runGibbsSample recursion, multicluster k-mers sharing a multiplicity
 // record) run one thread per GROUP in k_estimate_genotypes_nested, which walks the group's clusters in the
-// reference's depth-first order every iteration.  The joint noise mode still requires single-cluster groups.
+// reference's depth-first order every iteration.  In the joint noise mode such units take the warp-per-group kernel of gibbs_wide.cu.
 #include "gibbs_core.cuh"
 
 // clusters whose cache fill costs more than this many table lookups PER SAMPLE are worked on by a warp in the lock-step chains (dense
