@@ -15,3 +15,5 @@ compute-sanitizer --tool racecheck python -m pytest "tests/test_gpu_paths.py" -q
 compute-sanitizer --tool memcheck python -m pytest "tests/test_gpu_gibbs.py::test_estimate_noise_matches_oracle" "tests/test_gpu_gibbs_wide.py::test_joint_mode_wide" -q > gpurun_out/r2_sanitizer_memcheck_chain.log 2>&1
 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_shard.py -q > gpurun_out/r2_sanitizer_memcheck_shard.log 2>&1
 # scaling: gpurun --gpus 8 -- 'bash tools/scale_run.sh 8 B --steps 3 --warmup 2; bash tools/scale_run.sh 8 D --steps 2 --warmup 1'
+#          (profiles/r2_scale_sharded_*: group split; profiles/r2_scale_chains_B_n{2,4}.json: gpurun --gpus N -- 'bash tools/scale_run.sh N B --steps 2 --warmup 1')
+# the last calls of round 2: tools/gpu_call_a.sh (batched path search first, whole suite, smoke, bench line, configs[3] shape both ways, memcheck)
