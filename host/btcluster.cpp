@@ -84,6 +84,8 @@ static std::vector<std::pair<std::string, std::vector<Candidate>>> readCandidate
         if (t.size() < 8) throw btg::Error("variant line with fewer than 8 columns");
         if (t[3].find(',') != std::string::npos) throw btg::Error("REF holds several alleles");
         Candidate c;
+        if (t[1].empty() || t[1].find_first_not_of("0123456789") != std::string::npos || t[1].size() > 9 || std::stoul(t[1]) == 0)
+            throw btg::Error("POS of the variant line \"" + t[0] + "\t" + t[1] + "\t" + t[2] + " ...\" is not a positive integer");
         c.pos = (uint32_t)std::stoul(t[1]) - 1; c.id = t[2]; c.ref = t[3]; c.alts = split(t[4], ',');
         for (auto &kv : split(t[7], ';'))
             if (kv.compare(0, 4, "ACO=") == 0) {

@@ -118,6 +118,13 @@ def test_origins_ids_and_errors(tmp_path):
     assert r.returncode == 1 and "does not hold" in r.stderr
     r = subprocess.run([str(_exe()), str(tmp_path / "genome.fa"), str(tmp_path / "genome.fa"), str(tmp_path / "o.btd")], capture_output=True, text=True)
     assert r.returncode == 1 and ".vcf" in r.stderr
+    # malformed records are named, not reported as a bare std::stoul failure
+    (tmp_path / "pos.vcf").write_text("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n" + w.chrom + "\tabc\t.\tA\tC\t.\t.\t.\n")
+    r = subprocess.run([str(_exe()), str(tmp_path / "genome.fa"), str(tmp_path / "pos.vcf"), str(tmp_path / "o.btd")], capture_output=True, text=True)
+    assert r.returncode == 1 and "not a positive integer" in r.stderr
+    (tmp_path / "nohdr.vcf").write_text(w.chrom + "\t5\t.\tA\tC\t.\t.\t.\n")
+    r = subprocess.run([str(_exe()), str(tmp_path / "genome.fa"), str(tmp_path / "nohdr.vcf"), str(tmp_path / "o.btd")], capture_output=True, text=True)
+    assert r.returncode == 1 and "#CHROM" in r.stderr
 
 
 def test_native_builder_behind_the_python_interface():
