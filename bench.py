@@ -605,6 +605,12 @@ def cpu_reference(config: str, n_variants: int, threads: int, gibbs_samples: int
     sample_rate = tj["clusters_genotyped"] / total_s
     out = {"unit": UNIT, "cores": threads, "kind": "reference", "step_s": total_s, "clusters": tj["clusters_genotyped"], "sample_variants": len(var),
            "measured_sample_value": sample_rate, "estimateGenotypes_s": geno_s, "estimateNoise_s": noise_s, "kmer_stages_s": kmer_s}
+    try:    # the one-off measurement of the FULL config through the reference (tools/reference_full_config.py, build container): quoted beside the projection
+        fm = json.loads((ROOT / "profiles" / f"r2_reference_full_config{config}.json").read_text())
+        out["full_config_measured"] = {"clusters_per_s": fm["clusters_per_s"], "step_s": fm["step_s"], "clusters": fm["clusters_genotyped"], "variants": fm["variants"],
+                                       "threads": fm["threads"], "host": fm["host"], "profile": f"profiles/r2_reference_full_config{config}.json"}
+    except Exception:
+        pass
     if config == "B":
         r = FULL_B["variants"] / len(var)
         r_noise = min(FULL_B["variants"], FULL_B["noise_cap_variants"]) / min(len(var), FULL_B["noise_cap_variants"])
